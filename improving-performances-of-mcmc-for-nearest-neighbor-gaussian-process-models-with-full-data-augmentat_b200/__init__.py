@@ -1,0 +1,14 @@
+"""nngp_b200 -- B200-native hot path of the NNGP full-data-augmentation sampler.
+
+Host-side mirror of the reference's R entry points (mcmc_nngp_initialize / mcmc_nngp_run / mcmc_nngp_update_Gaussian /
+mcmc_nngp_predict_field / mcmc_nngp_estimate) over the C ABI of libnngp_b200.so (include/nngp_b200.h).  R is not available
+in this image, so the host side above the ABI is Python; R/ holds the equivalent .C() glue.
+"""
+from . import _lib
+from ._lib import (COVFUN_IDS, LAYOUT_COLOR, LAYOUT_COLOR_MORTON, NA_INT, RNG_PHILOX, RNG_SUPPLIED, SLOT_CURRENT,
+                   SLOT_PROPOSAL, NNGPError, device_count, launch_count)
+from .context import NNGPContext, find_ordered_nn, greedy_coloring, order_maxmin
+
+__all__ = ["NNGPContext", "find_ordered_nn", "greedy_coloring", "order_maxmin", "NNGPError", "device_count", "launch_count",
+           "COVFUN_IDS", "NA_INT", "SLOT_CURRENT", "SLOT_PROPOSAL", "RNG_SUPPLIED", "RNG_PHILOX", "LAYOUT_COLOR",
+           "LAYOUT_COLOR_MORTON"]

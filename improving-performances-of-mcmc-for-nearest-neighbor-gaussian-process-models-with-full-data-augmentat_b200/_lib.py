@@ -1,0 +1,102 @@
+"""ctypes binding of libnngp_b200.so (the C ABI in include/nngp_b200.h).
+
+This is the same binding an R maintainer would write with dyn.load()/.C(): every argument is a pointer, the last one is
+`status`.  There is no CPU fallback here: if the shared library is missing or no CUDA device is usable, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+NA_INT = -2147483648
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(PKG_DIR, "libnngp_b200.so")
+
+COVFUN_IDS = {
+    "exponential_isotropic": 0, "exponential_sphere": 1, "exponential_scaledim": 2, "exponential_spacetime": 3,
+    "matern_isotropic": 4, "matern_sphere": 5, "matern_scaledim": 6, "matern_spacetime": 7,
+}
+SLOT_CURRENT, SLOT_PROPOSAL = 0, 1
+RNG_SUPPLIED, RNG_PHILOX = 0, 1
+LAYOUT_COLOR, LAYOUT_COLOR_MORTON = 1, 2
+
+# every symbol include/nngp_b200.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "nngp_version", "nngp_device_count", "nngp_last_error", "nngp_host_find_ordered_nn", "nngp_host_greedy_coloring",
+    "nngp_host_order_maxmin", "nngp_ctx_create", "nngp_ctx_destroy", "nngp_ctx_info", "nngp_factor_build",
+    "nngp_factor_get", "nngp_factor_accept", "nngp_factor_commit", "nngp_precision_diag", "nngp_field_set",
+    "nngp_field_get", "nngp_obs_set", "nngp_loglik", "nngp_loglik_host", "nngp_spmv", "nngp_sptmv", "nngp_sptrsv",
+    "nngp_gibbs_sweep", "nngp_ancillary_propose", "nngp_ancillary_accept", "nngp_beta0_moments", "nngp_ssr",
+    "nngp_field_init", "nngp_chain_run", "nngp_predict_sample", "nngp_time_op", "nngp_launch_count",
+]
+
+
+class NNGPError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libnngp_b200 status {status}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library; fails loudly (no fallback) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise FileNotFoundError(
+                f"{SO_PATH} is missing: build it with `python {os.path.join(PKG_DIR, 'build.py')}` "
+                "(the NNGP hot path has no CPU fallback)")
+        _lib = C.CDLL(SO_PATH)
+    return _lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(1024)
+    load().nngp_last_error(buf, C.byref(C.c_int(1024)))
+    return buf.value.decode(errors="replace")
+
+
+def check(status: C.c_int) -> None:
+    if status.value != 0:
+        raise NNGPError(status.value, last_error())
+
+
+def ci(v: int):
+    return C.byref(C.c_int(int(v)))
+
+
+def cd(v: float):
+    return C.byref(C.c_double(float(v)))
+
+
+def f64(a) -> np.ndarray:
+    """column-major flat float64 copy/view, as R would hand the array to .C()"""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F"))
+
+
+def i32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32).ravel(order="F"))
+
+
+def dptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def iptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def launch_count() -> int:
+    v = C.c_double(0.0)
+    load().nngp_launch_count(C.byref(v))
+    return int(v.value)
+
+
+def device_count() -> int:
+    n, st = C.c_int(0), C.c_int(0)
+    load().nngp_device_count(C.byref(n), C.byref(st))
+    return n.value if st.value == 0 else 0

@@ -1,0 +1,241 @@
+"""NNGPContext: thin object wrapper over the context handle of the C ABI (one model graph + one chain state on one GPU)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class NNGPContext:
+    """Device-resident Vecchia structure (vecchia_approx of the reference, Scripts/mcmc_nngp_initialize.R:80-110).
+
+    All arrays use R's conventions: column-major, 1-based indices, NA = INT_MIN; `field` includes beta_0.
+    """
+
+    def __init__(self, locs, NNarray, coloring, locs_match, covfun_name="exponential_isotropic", device=0,
+                 layout=L.LAYOUT_COLOR_MORTON):
+        locs = np.asarray(locs, dtype=np.float64)
+        if locs.ndim == 1:
+            locs = locs[:, None]
+        NNarray = np.asarray(NNarray, dtype=np.int32)
+        self.n, self.d = locs.shape
+        self.m = NNarray.shape[1] - 1
+        self.covfun_name = covfun_name
+        lm = L.i32(locs_match)
+        self.n_obs = lm.size
+        self._id = None
+        cid, st = C.c_int(-1), C.c_int(0)
+        lib = L.load()
+        lib.nngp_ctx_create(L.ci(self.n), L.ci(self.d), L.ci(self.m), L.dptr(L.f64(locs)), L.iptr(L.i32(NNarray)),
+                            L.iptr(L.i32(coloring)), L.ci(self.n_obs), L.iptr(lm), L.ci(L.COVFUN_IDS[covfun_name]),
+                            L.ci(device), L.ci(layout), C.byref(cid), C.byref(st))
+        L.check(st)
+        self._id = cid.value
+        info = (C.c_int * 8)()
+        lib.nngp_ctx_info(L.ci(self._id), info, C.byref(st))
+        L.check(st)
+        self.n_colors, self.n_levels, self.nnz, self.max_col = info[2], info[3], info[4], info[5]
+        self.device, self.layout = info[6], info[7]
+
+    # ---- lifecycle
+    def close(self):
+        if self._id is not None:
+            st = C.c_int(0)
+            L.load().nngp_ctx_destroy(L.ci(self._id), C.byref(st))
+            self._id = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _call(self, name, *args):
+        st = C.c_int(0)
+        getattr(L.load(), name)(L.ci(self._id), *args, C.byref(st))
+        L.check(st)
+
+    # ---- factor
+    def factor_build(self, covparms, slot=L.SLOT_CURRENT) -> int:
+        cp = L.f64(covparms)
+        bad = C.c_int(0)
+        self._call("nngp_factor_build", L.ci(slot), L.dptr(cp), L.ci(cp.size), C.byref(bad))
+        return bad.value
+
+    def factor_get(self, slot=L.SLOT_CURRENT) -> np.ndarray:
+        out = np.empty(self.n * (self.m + 1))
+        self._call("nngp_factor_get", L.ci(slot), L.dptr(out))
+        return out.reshape((self.n, self.m + 1), order="F")
+
+    def factor_accept(self):
+        self._call("nngp_factor_accept")
+
+    def factor_commit(self, slot=L.SLOT_CURRENT):
+        self._call("nngp_factor_commit", L.ci(slot))
+
+    def precision_diag(self) -> np.ndarray:
+        out = np.empty(self.n)
+        self._call("nngp_precision_diag", L.dptr(out))
+        return out
+
+    # ---- state
+    def field_set(self, field):
+        f = L.f64(field)
+        assert f.size == self.n
+        self._call("nngp_field_set", L.dptr(f))
+
+    def field_get(self) -> np.ndarray:
+        out = np.empty(self.n)
+        self._call("nngp_field_get", L.dptr(out))
+        return out
+
+    def obs_set(self, y_minus_xb):
+        y = L.f64(y_minus_xb)
+        assert y.size == self.n_obs
+        self._call("nngp_obs_set", L.dptr(y))
+
+    # ---- log-likelihood and products
+    def loglik(self, beta_0, log_scale, slot=L.SLOT_CURRENT) -> float:
+        out = C.c_double(0.0)
+        self._call("nngp_loglik", L.ci(slot), L.cd(beta_0), L.cd(log_scale), C.byref(out))
+        return out.value
+
+    def loglik_host(self, z, log_scale, slot=L.SLOT_CURRENT) -> float:
+        zz = L.f64(z)
+        assert zz.size == self.n
+        out = C.c_double(0.0)
+        self._call("nngp_loglik_host", L.ci(slot), L.dptr(zz), L.cd(log_scale), C.byref(out))
+        return out.value
+
+    def _vec_op(self, name, v, slot):
+        vv = L.f64(v)
+        assert vv.size == self.n
+        out = np.empty(self.n)
+        self._call(name, L.ci(slot), L.dptr(vv), L.dptr(out))
+        return out
+
+    def spmv(self, v, slot=L.SLOT_CURRENT):
+        return self._vec_op("nngp_spmv", v, slot)
+
+    def sptmv(self, u, slot=L.SLOT_CURRENT):
+        return self._vec_op("nngp_sptmv", u, slot)
+
+    def sptrsv(self, b, slot=L.SLOT_CURRENT):
+        return self._vec_op("nngp_sptrsv", b, slot)
+
+    # ---- sampler steps
+    def gibbs_sweep(self, beta_0, log_scale, log_noise_variance, n_sweeps=1, z=None, seed=0):
+        if z is None:
+            self._call("nngp_gibbs_sweep", L.ci(n_sweeps), L.cd(beta_0), L.cd(log_scale), L.cd(log_noise_variance),
+                       L.ci(L.RNG_PHILOX), None, L.cd(seed))
+        else:
+            zz = L.f64(z)
+            assert zz.size == self.n * n_sweeps
+            self._call("nngp_gibbs_sweep", L.ci(n_sweeps), L.cd(beta_0), L.cd(log_scale), L.cd(log_noise_variance),
+                       L.ci(L.RNG_SUPPLIED), L.dptr(zz), L.cd(seed))
+
+    def ancillary_propose(self, beta_0, delta_log_scale, log_noise_variance) -> float:
+        out = C.c_double(0.0)
+        self._call("nngp_ancillary_propose", L.cd(beta_0), L.cd(delta_log_scale), L.cd(log_noise_variance), C.byref(out))
+        return out.value
+
+    def ancillary_accept(self):
+        self._call("nngp_ancillary_accept")
+
+    def beta0_moments(self, log_scale):
+        mean, var = C.c_double(0.0), C.c_double(0.0)
+        self._call("nngp_beta0_moments", L.cd(log_scale), C.byref(mean), C.byref(var))
+        return mean.value, var.value
+
+    def ssr(self) -> float:
+        out = C.c_double(0.0)
+        self._call("nngp_ssr", C.byref(out))
+        return out.value
+
+    def field_init(self, beta_0, log_scale, z, slot=L.SLOT_CURRENT):
+        zz = L.f64(z)
+        assert zz.size == self.n
+        self._call("nngp_field_init", L.ci(slot), L.cd(beta_0), L.cd(log_scale), L.dptr(zz))
+
+    def chain_run(self, params: dict, n_iter, var_y, thin=1.0, n_chromatic=10, iter_start=0, chain_index=1,
+                  rng_mode=L.RNG_PHILOX, keep_field=True):
+        """nngp_chain_run: the whole reference loop (update_Gaussian.R:101-314, no regressors) behind the ABI."""
+        shape = np.atleast_1d(np.asarray(params["shape"], dtype=np.float64))
+        p = np.concatenate([[params["beta_0"], params["log_scale"], params["log_noise_variance"],
+                             params.get("logvar_sufficient", -2.0), params.get("logvar_ancillary", -2.0)], shape])
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        n_iter = int(n_iter)
+        rec = np.zeros(n_iter * (3 + shape.size))
+        n_frec = int(round(n_iter * thin))
+        frec = np.zeros(max(n_frec, 1) * self.n) if keep_field else None
+        acc = np.zeros(2 * n_iter, dtype=np.int32)
+        self._call("nngp_chain_run", L.ci(shape.size), L.dptr(p), L.ci(n_iter), L.cd(thin), L.ci(n_chromatic),
+                   L.ci(iter_start), L.ci(chain_index), L.ci(rng_mode), L.cd(var_y), L.dptr(rec),
+                   L.dptr(frec) if keep_field else None, L.iptr(acc))
+        out = dict(beta_0=p[0], log_scale=p[1], log_noise_variance=p[2], logvar_sufficient=p[3], logvar_ancillary=p[4],
+                   shape=p[5:].copy())
+        frec_m = frec[: n_frec * self.n].reshape((n_frec, self.n), order="F") if keep_field else None
+        return out, rec.reshape((n_iter, 3 + shape.size), order="F"), frec_m, acc.reshape((n_iter, 2), order="F")
+
+    def predict_sample(self, n_obs_sites, field, beta_0, log_scale, z_pred, slot=L.SLOT_CURRENT):
+        f = L.f64(field)
+        z = L.f64(z_pred)
+        out = np.empty(self.n - n_obs_sites)
+        self._call("nngp_predict_sample", L.ci(slot), L.ci(n_obs_sites), L.dptr(f), L.cd(beta_0), L.cd(log_scale),
+                   L.dptr(z), L.dptr(out))
+        return out
+
+    # ---- measurement
+    OPS = {"factor_build": 0, "loglik": 1, "gibbs_sweep": 2, "spmv": 3, "sptrsv": 4, "commit": 5, "sweep_loglik": 6}
+
+    def time_op(self, op: str, reps=20, flush_l2=False):
+        ms = np.zeros(reps)
+        nl = C.c_int(0)
+        self._call("nngp_time_op", L.ci(self.OPS[op]), L.ci(reps), L.ci(1 if flush_l2 else 0), L.dptr(ms), C.byref(nl))
+        return ms, nl.value
+
+
+# ---- host set-up utilities (init-time code of the reference)
+def find_ordered_nn(locs, m) -> np.ndarray:
+    """GpGp::find_ordered_nn replacement (Scripts/mcmc_nngp_initialize.R:93): exact, ties by lower index."""
+    locs = np.asarray(locs, dtype=np.float64)
+    if locs.ndim == 1:
+        locs = locs[:, None]
+    n, d = locs.shape
+    out = np.empty(n * (m + 1), dtype=np.int32)
+    st = C.c_int(0)
+    L.load().nngp_host_find_ordered_nn(L.dptr(L.f64(locs)), L.ci(n), L.ci(d), L.ci(m), L.iptr(out), C.byref(st))
+    L.check(st)
+    return out.reshape((n, m + 1), order="F")
+
+
+def greedy_coloring(NNarray) -> np.ndarray:
+    """moral graph + naive_greedy_coloring (initialize.R:103-110, Coloring.R:2-20) without the dense scratch."""
+    NNarray = np.asarray(NNarray, dtype=np.int32)
+    n, M = NNarray.shape
+    out = np.empty(n, dtype=np.int32)
+    K, st = C.c_int(0), C.c_int(0)
+    L.load().nngp_host_greedy_coloring(L.iptr(L.i32(NNarray)), L.ci(n), L.ci(M - 1), L.iptr(out), C.byref(K), C.byref(st))
+    L.check(st)
+    return out
+
+
+def order_maxmin(locs) -> np.ndarray:
+    """exact max-min ordering, 1-based permutation (GpGp::order_maxmin is a randomised approximation of this)."""
+    locs = np.asarray(locs, dtype=np.float64)
+    if locs.ndim == 1:
+        locs = locs[:, None]
+    n, d = locs.shape
+    out = np.empty(n, dtype=np.int32)
+    st = C.c_int(0)
+    L.load().nngp_host_order_maxmin(L.dptr(L.f64(locs)), L.ci(n), L.ci(d), L.iptr(out), C.byref(st))
+    L.check(st)
+    return out

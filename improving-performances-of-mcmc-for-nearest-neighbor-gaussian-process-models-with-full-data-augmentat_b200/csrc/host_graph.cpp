@@ -1,0 +1,321 @@
+// host_graph.cpp -- host-side set-up utilities of libnngp_b200.so (C ABI: include/nngp_b200.h, nngp_host_*).
+//
+// These replace init-time code of the reference (GpGp::find_ordered_nn, GpGp::order_maxmin, the crossprod() moral graph
+// and Coloring.R), which runs once per model on the host in the reference too.  They are NOT a CPU fallback of the GPU
+// hot path.  Semantics (and the reference lines they replace) are documented in the header.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <queue>
+#include <vector>
+
+#include "../../include/nngp_b200.h"
+#include "nngp_internal.h"
+
+namespace {
+
+struct Cand {
+    double d2;
+    int idx;
+    bool operator<(const Cand &o) const { return d2 < o.d2 || (d2 == o.d2 && idx < o.idx); }
+};
+
+// Uniform grid over (up to) the first three coordinate dimensions of the first `cnt` points.
+struct Grid {
+    int gd;              // gridded dims (<= 3)
+    double lo[3], h[3];  // origin and cell edge per gridded dim
+    int nc[3];           // cells per gridded dim
+    double hmin;         // smallest edge among non-collapsed dims (inf if all collapsed)
+    std::vector<int> start, pts;  // CSR: points of each cell, ascending index
+
+    int cell_coord(double x, int k) const {
+        int c = (int)std::floor((x - lo[k]) / h[k]);
+        return c < 0 ? 0 : (c >= nc[k] ? nc[k] - 1 : c);
+    }
+    void build(const double *P /* row-major cnt x d */, int cnt, int d, double target_per_cell) {
+        gd = std::min(d, 3);
+        double ext[3] = {0, 0, 0}, hi[3];
+        for (int k = 0; k < gd; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+        for (int i = 0; i < cnt; i++)
+            for (int k = 0; k < gd; k++) {
+                double x = P[(size_t)i * d + k];
+                if (x < lo[k]) lo[k] = x;
+                if (x > hi[k]) hi[k] = x;
+            }
+        for (int k = 0; k < gd; k++) ext[k] = hi[k] - lo[k];
+        // choose a common edge so that (non-degenerate) cells are roughly cubic and hold ~target points; dims whose
+        // extent is below the edge collapse to a single cell.  Iterate because collapsing changes the effective dim.
+        double ncell_target = std::max(1.0, cnt / target_per_cell);
+        bool active[3] = {true, true, true};
+        double edge = 1.0;
+        for (int it = 0; it < 4; it++) {
+            double vol = 1.0; int na = 0;
+            for (int k = 0; k < gd; k++) if (active[k] && ext[k] > 0) { vol *= ext[k]; na++; } else active[k] = false;
+            if (na == 0) { edge = 1.0; break; }
+            edge = std::pow(vol / ncell_target, 1.0 / na);
+            bool changed = false;
+            for (int k = 0; k < gd; k++) if (active[k] && ext[k] < edge) { active[k] = false; changed = true; }
+            if (!changed) break;
+        }
+        hmin = INFINITY;
+        size_t total = 1;
+        for (int k = 0; k < gd; k++) {
+            if (active[k]) {
+                nc[k] = std::max(1, (int)std::ceil(ext[k] / edge));
+                if (nc[k] > 4096) nc[k] = 4096;
+                h[k] = ext[k] / nc[k];
+                if (!(h[k] > 0)) { h[k] = 1.0; nc[k] = 1; }
+                else hmin = std::min(hmin, h[k]);
+            } else { nc[k] = 1; h[k] = (ext[k] > 0 ? ext[k] : 1.0) * 1.0000001; }
+            total *= (size_t)nc[k];
+        }
+        for (int k = gd; k < 3; k++) { nc[k] = 1; lo[k] = 0; h[k] = 1; }
+        start.assign(total + 1, 0);
+        std::vector<int> cell(cnt);
+        for (int i = 0; i < cnt; i++) {
+            int c[3] = {0, 0, 0};
+            for (int k = 0; k < gd; k++) c[k] = cell_coord(P[(size_t)i * d + k], k);
+            cell[i] = (c[2] * nc[1] + c[1]) * nc[0] + c[0];
+            start[cell[i] + 1]++;
+        }
+        for (size_t c = 0; c < total; c++) start[c + 1] += start[c];
+        pts.resize(cnt);
+        std::vector<int> pos(start.begin(), start.end() - 1);
+        for (int i = 0; i < cnt; i++) pts[pos[cell[i]]++] = i;  // ascending index inside each cell
+    }
+};
+
+inline double dist2(const double *P, int d, int a, int b) {
+    double s = 0.0;
+    for (int k = 0; k < d; k++) {
+        double t = P[(size_t)a * d + k] - P[(size_t)b * d + k];
+        s += t * t;
+    }
+    return s;
+}
+
+// m nearest among points with index < i, result ascending by (d2, idx) into out[0..found)
+int query_prev(const Grid &g, const double *P, int d, int i, int m, Cand *heap /* size m */) {
+    int found = 0;
+    int ci[3] = {0, 0, 0};
+    for (int k = 0; k < g.gd; k++) ci[k] = g.cell_coord(P[(size_t)i * d + k], k);
+    int maxr = 0;
+    for (int k = 0; k < g.gd; k++) maxr = std::max(maxr, std::max(ci[k], g.nc[k] - 1 - ci[k]));
+    for (int r = 0; r <= maxr; r++) {
+        int z0 = std::max(0, ci[2] - r), z1 = std::min(g.nc[2] - 1, ci[2] + r);
+        int y0 = std::max(0, ci[1] - r), y1 = std::min(g.nc[1] - 1, ci[1] + r);
+        int x0 = std::max(0, ci[0] - r), x1 = std::min(g.nc[0] - 1, ci[0] + r);
+        for (int z = z0; z <= z1; z++)
+            for (int y = y0; y <= y1; y++) {
+                bool edge_zy = (std::abs(z - ci[2]) == r) || (std::abs(y - ci[1]) == r);
+                for (int x = x0; x <= x1; x++) {
+                    if (!edge_zy && std::abs(x - ci[0]) != r) {  // interior of the ring: jump to the far side
+                        if (x < ci[0] + r) { x = ci[0] + r - 1; }
+                        continue;
+                    }
+                    int c = (z * g.nc[1] + y) * g.nc[0] + x;
+                    for (int q = g.start[c]; q < g.start[c + 1]; q++) {
+                        int p = g.pts[q];
+                        if (p >= i) break;  // ascending inside the cell
+                        Cand cd{dist2(P, d, i, p), p};
+                        if (found < m) {
+                            heap[found++] = cd;
+                            std::push_heap(heap, heap + found);
+                        } else if (cd < heap[0]) {
+                            std::pop_heap(heap, heap + found);
+                            heap[found - 1] = cd;
+                            std::push_heap(heap, heap + found);
+                        }
+                    }
+                }
+            }
+        if (found == m && std::isfinite(g.hmin)) {
+            double bound = r * g.hmin * (1.0 - 1e-12);
+            if (heap[0].d2 < bound * bound) break;
+        }
+    }
+    std::sort_heap(heap, heap + found);
+    return found;
+}
+
+}  // namespace
+
+namespace nngp {
+
+void find_ordered_nn(const double *locs_cm, int n, int d, int m, int *NNarray) {
+    std::vector<double> P((size_t)n * d);
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < d; k++) P[(size_t)i * d + k] = locs_cm[(size_t)i + (size_t)n * k];
+    auto put = [&](int i, const Cand *c, int found) {
+        NNarray[(size_t)i] = i + 1;
+        for (int j = 1; j <= m; j++) NNarray[(size_t)i + (size_t)n * j] = (j <= found) ? c[j - 1].idx + 1 : NNGP_NA_INT;
+    };
+    // brute force head
+    int head = std::min(n, std::max(4 * m + 8, 256));
+    {
+        std::vector<Cand> c(head);
+        for (int i = 0; i < head; i++) {
+            for (int p = 0; p < i; p++) c[p] = Cand{dist2(P.data(), d, i, p), p};
+            int take = std::min(i, m);
+            std::partial_sort(c.begin(), c.begin() + take, c.begin() + i);
+            put(i, c.data(), take);
+        }
+    }
+    // doubling generations: sites [s, e) query a grid over sites [0, e), filtering index < i
+    for (int s = head; s < n;) {
+        int e = (int)std::min<int64_t>((int64_t)s * 2, n);
+        Grid g;
+        g.build(P.data(), e, d, 3.0);
+#pragma omp parallel
+        {
+            std::vector<Cand> heap(m);
+#pragma omp for schedule(dynamic, 256)
+            for (int i = s; i < e; i++) {
+                int found = query_prev(g, P.data(), d, i, m, heap.data());
+                put(i, heap.data(), found);
+            }
+        }
+        s = e;
+    }
+}
+
+// children lists: for site s the rows r (0-based) that contain s, r ascending (includes r == s)
+void build_csc(const int *NNarray, int n, int m, std::vector<int64_t> &ptr, std::vector<int> &rows, std::vector<int> &slots) {
+    ptr.assign((size_t)n + 1, 0);
+    for (int j = 0; j <= m; j++)
+        for (int i = 0; i < n; i++) {
+            int v = NNarray[(size_t)i + (size_t)n * j];
+            if (v != NNGP_NA_INT) ptr[v]++;
+        }
+    for (int s = 0; s < n; s++) ptr[s + 1] += ptr[s];
+    rows.resize(ptr[n]);
+    slots.resize(ptr[n]);
+    std::vector<int64_t> pos(ptr.begin(), ptr.end() - 1);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= m; j++) {
+            int v = NNarray[(size_t)i + (size_t)n * j];
+            if (v != NNGP_NA_INT) { rows[pos[v - 1]] = i; slots[pos[v - 1]] = j; pos[v - 1]++; }
+        }
+}
+
+int greedy_coloring(const int *NNarray, int n, int m, int *coloring) {
+    std::vector<int64_t> ptr; std::vector<int> rows, slots;
+    build_csc(NNarray, n, m, ptr, rows, slots);
+    std::vector<int> stamp(64, -1);
+    int K = 0;
+    for (int i = 0; i < n; i++) coloring[i] = 0;
+    for (int i = 0; i < n; i++) {
+        // moral neighbours of i = members of every row that contains i (Scripts/mcmc_nngp_initialize.R:103)
+        for (int64_t k = ptr[i]; k < ptr[i + 1]; k++) {
+            int r = rows[k];
+            for (int j = 0; j <= m; j++) {
+                int v = NNarray[(size_t)r + (size_t)n * j];
+                if (v == NNGP_NA_INT) continue;
+                int c = coloring[v - 1];
+                if (c > 0) {
+                    if (c >= (int)stamp.size()) stamp.resize(2 * c + 2, -1);
+                    stamp[c] = i;
+                }
+            }
+        }
+        int c = 1;
+        while (c < (int)stamp.size() && stamp[c] == i) c++;   // Coloring.R:16  match(0, incompatibilities[i,])
+        if (c >= (int)stamp.size()) stamp.resize(2 * c + 2, -1);
+        coloring[i] = c;
+        if (c > K) K = c;
+    }
+    return K;
+}
+
+// exact farthest-point ordering: start from the site closest to the centroid, then repeatedly take the site whose
+// distance to the already-ordered set is largest (ties: lower index).
+void order_maxmin(const double *locs_cm, int n, int d, int *order) {
+    std::vector<double> P((size_t)n * d);
+    std::vector<double> cen(d, 0.0);
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < d; k++) { P[(size_t)i * d + k] = locs_cm[(size_t)i + (size_t)n * k]; cen[k] += P[(size_t)i * d + k]; }
+    for (int k = 0; k < d; k++) cen[k] /= std::max(n, 1);
+    if (n == 0) return;
+    int first = 0; double best = INFINITY;
+    for (int i = 0; i < n; i++) {
+        double s = 0; for (int k = 0; k < d; k++) { double t = P[(size_t)i * d + k] - cen[k]; s += t * t; }
+        if (s < best) { best = s; first = i; }
+    }
+    Grid g; g.build(P.data(), n, d, 2.0);
+    std::vector<double> dist(n, INFINITY);
+    std::vector<char> done(n, 0);
+    struct HE { double d2; int idx; bool operator<(const HE &o) const { return d2 < o.d2 || (d2 == o.d2 && idx > o.idx); } };
+    std::priority_queue<HE> heap;
+    auto relax_around = [&](int p, double r2) {
+        // every unselected q with |q-p|^2 < dist[q] has dist[q] <= r2, hence lies within radius sqrt(r2) of p
+        double r = std::sqrt(r2);
+        int c0[3] = {0, 0, 0}, c1[3] = {0, 0, 0};
+        for (int k = 0; k < g.gd; k++) {
+            double x = P[(size_t)p * d + k];
+            if (std::isfinite(r)) { c0[k] = g.cell_coord(x - r, k); c1[k] = g.cell_coord(x + r, k); }
+            else { c0[k] = 0; c1[k] = g.nc[k] - 1; }
+        }
+        for (int z = c0[2]; z <= c1[2]; z++)
+            for (int y = c0[1]; y <= c1[1]; y++)
+                for (int x = c0[0]; x <= c1[0]; x++) {
+                    int c = (z * g.nc[1] + y) * g.nc[0] + x;
+                    for (int q = g.start[c]; q < g.start[c + 1]; q++) {
+                        int s = g.pts[q];
+                        if (done[s]) continue;
+                        double dd = dist2(P.data(), d, s, p);
+                        if (dd < dist[s]) { dist[s] = dd; heap.push(HE{dd, s}); }
+                    }
+                }
+    };
+    int cnt = 0;
+    done[first] = 1; order[cnt++] = first + 1;
+    relax_around(first, INFINITY);
+    while (cnt < n) {
+        HE t = heap.top(); heap.pop();
+        if (done[t.idx] || t.d2 != dist[t.idx]) continue;   // stale entry
+        done[t.idx] = 1; order[cnt++] = t.idx + 1;
+        relax_around(t.idx, t.d2);
+    }
+}
+
+// depth of every row in the solve DAG: 0 for rows without parents, else 1 + max over parents
+int solve_levels(const int *NNarray, int n, int m, std::vector<int> &level) {
+    level.assign(n, 0);
+    int depth = 0;
+    for (int i = 0; i < n; i++) {
+        int l = 0;
+        for (int j = 1; j <= m; j++) {
+            int v = NNarray[(size_t)i + (size_t)n * j];
+            if (v != NNGP_NA_INT) l = std::max(l, level[v - 1] + 1);
+        }
+        level[i] = l;
+        depth = std::max(depth, l + 1);
+    }
+    return depth;
+}
+
+}  // namespace nngp
+
+extern "C" {
+
+void nngp_host_find_ordered_nn(const double *locs, const int *n, const int *d, const int *m, int *NNarray, int *status) {
+    if (!locs || !n || !d || !m || !NNarray || *n < 0 || *d < 1 || *m < 0) { nngp::set_error("nngp_host_find_ordered_nn: bad argument"); if (status) *status = NNGP_ERR_ARG; return; }
+    nngp::find_ordered_nn(locs, *n, *d, *m, NNarray);
+    *status = NNGP_OK;
+}
+
+void nngp_host_greedy_coloring(const int *NNarray, const int *n, const int *m, int *coloring, int *n_colors, int *status) {
+    if (!NNarray || !n || !m || !coloring || *n < 0 || *m < 0) { nngp::set_error("nngp_host_greedy_coloring: bad argument"); if (status) *status = NNGP_ERR_ARG; return; }
+    int K = nngp::greedy_coloring(NNarray, *n, *m, coloring);
+    if (n_colors) *n_colors = K;
+    *status = NNGP_OK;
+}
+
+void nngp_host_order_maxmin(const double *locs, const int *n, const int *d, int *order, int *status) {
+    if (!locs || !n || !d || !order || *n < 0 || *d < 1) { nngp::set_error("nngp_host_order_maxmin: bad argument"); if (status) *status = NNGP_ERR_ARG; return; }
+    nngp::order_maxmin(locs, *n, *d, order);
+    *status = NNGP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,471 @@
+// kernels.cuh -- sm_100a kernels of the NNGP hot path.
+//
+// Device layout (all arrays in the INTERNAL site numbering: colour-major, optionally Morton inside a colour):
+//   nn    int32  [M][ld]   neighbour table, slot-major ("column-major" as R stores NNarray): nn[j*ld + q]; -1 = NA
+//   linv  double [M][ld]   compressed factor, same shape: linv[j*ld + q]     (slot 0 = 1/sqrt(F_q), slot j = -B_qj/sqrt(F_q))
+//   tl    double [n][DT]   coordinates after the covariance family's transformation (range-scaled / unit sphere)
+//   CSC (transpose) of the factor pattern, used by the Gibbs sweep:
+//     colptr int32 [n+1], crow int32 [nnz] (row of each entry), csrc int32 [nnz] (position of the entry in linv),
+//     valT double [nnz] (values gathered from the CURRENT factor), pd double [n] (precision_diag)
+// Slot-major storage makes every thread-per-row access of nn / linv a perfectly coalesced 128 B / 256 B warp transaction;
+// the only irregular accesses are the gathers of 8-byte operands (coordinates, field, residual), which stay in L2.
+#pragma once
+#include "device_math.cuh"
+
+namespace nngp {
+
+struct CovConst {
+    double variance, nugget, smooth, normcon;
+    double range[4];  // per-dimension divisors (after the family's mapping)
+    int covfun;       // NNGP_* id
+    int d;            // raw coordinate dimension
+    int dt;           // transformed dimension
+};
+
+// parameters of the sweep that change between launches live in device memory so that the captured graph is static
+struct SweepParams {
+    double beta0, e_ls, e_ln;  // exp(-log_scale), exp(-log_noise_variance)
+    unsigned long long sweep_counter;
+    unsigned long long z_offset;  // offset of the current sweep's normals inside zbuf (supplied mode)
+    unsigned int key0, key1;
+    int rng_mode;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// permutation / utility kernels
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void gather_f64_kernel(double *__restrict__ dst, const double *__restrict__ src, const int *__restrict__ map, int n) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) dst[t] = src[map[t]];
+}
+
+// dst (n x M, column-major with leading dim n, reference order) <- linv (slot-major, ld, internal order)
+__global__ void linv_to_host_order_kernel(double *__restrict__ dst, const double *__restrict__ linv, const int *__restrict__ g2i,
+                                          int n, int ld, int M) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const int q = g2i[t];
+        for (int j = 0; j < M; j++) dst[(size_t)j * n + t] = linv[(size_t)j * ld + q];
+    }
+}
+
+__global__ void fill_f64_kernel(double *__restrict__ dst, double v, size_t n) {
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) dst[t] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// coordinate transformation (once per factor build): divide by the range(s); lon/lat -> unit sphere for *_sphere
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void transform_locs_kernel(const double *__restrict__ locs /* [n][d] */, double *__restrict__ tl /* [n][dt] */, int n,
+                                      CovConst cc) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const double *p = locs + (size_t)q * cc.d;
+        double *o = tl + (size_t)q * cc.dt;
+        if (cc.covfun == 1 || cc.covfun == 5) {
+            const double lon = p[0] * 3.14159265358979323846 / 180.0, lat = p[1] * 3.14159265358979323846 / 180.0;
+            o[0] = cos(lat) * cos(lon) / cc.range[0];
+            o[1] = cos(lat) * sin(lon) / cc.range[0];
+            o[2] = sin(lat) / cc.range[0];
+        } else {
+            for (int k = 0; k < cc.d; k++) o[k] = p[k] / cc.range[k];
+        }
+    }
+}
+
+template <bool MATERN>
+__device__ __forceinline__ double kernel_value(const CovConst &cc, double dist) {
+    if (!MATERN) return cc.variance * exp(-dist);
+    if (dist == 0.0) return cc.variance;
+    return cc.normcon * pow(dist, cc.smooth) * bessel_k_real(cc.smooth, dist);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Vecchia factor build, register-resident: one thread per row, M = m+1 and DT compile-time, the (M x M) lower triangle
+// lives in registers, all loops fully unrolled.  Rows with fewer than m neighbours (at most m of them) are skipped here and
+// done by the generic kernel.  FP64-pipe bound: ~M(M-1)/2 exp + sqrt, M^3/6 FMA, M(M+1)/2 div.
+// Operation order = oracle_vecchia_linv (oracle/nngp_oracle.c): neighbours farthest-first, self last; row-by-row Cholesky;
+// back-substitution for the last row of L^-1.
+// ---------------------------------------------------------------------------------------------------------------
+template <int M, int DT, bool MATERN>
+__global__ void __launch_bounds__(128) vecchia_factor_reg_kernel(const int *__restrict__ nn, const double *__restrict__ tl,
+                                                                 double *__restrict__ linv, int n, int ld, CovConst cc,
+                                                                 int *__restrict__ n_bad) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int idx[M];
+    bool full = true;
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+        idx[j] = nn[(size_t)j * ld + q];
+        full = full && (idx[j] >= 0);
+    }
+    if (!full) return;
+    double p[M][DT];
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+        const double *src = tl + (size_t)idx[M - 1 - k] * DT;
+        if (DT == 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(src);
+            p[k][0] = v.x;
+            p[k][1] = v.y;
+        } else {
+#pragma unroll
+            for (int c = 0; c < DT; c++) p[k][c] = src[c];
+        }
+    }
+    double L[M * (M + 1) / 2];
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+            double s;
+            if (a == b) {
+                s = cc.variance + cc.nugget;
+            } else {
+                double d2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < DT; c++) {
+                    const double t = p[a][c] - p[b][c];
+                    d2 += t * t;
+                }
+                s = kernel_value<MATERN>(cc, sqrt(d2));
+            }
+#pragma unroll
+            for (int k = 0; k < b; k++) s -= L[a * (a + 1) / 2 + k] * L[b * (b + 1) / 2 + k];
+            if (a == b) {
+                ok = ok && (s > 0.0);
+                L[a * (a + 1) / 2 + a] = sqrt(s);
+            } else {
+                L[a * (a + 1) / 2 + b] = s / L[b * (b + 1) / 2 + b];
+            }
+        }
+    }
+    double x[M];
+#pragma unroll
+    for (int a = M - 1; a >= 0; a--) {
+        double s = (a == M - 1) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = a + 1; k < M; k++) s -= L[k * (k + 1) / 2 + a] * x[k];
+        x[a] = s / L[a * (a + 1) / 2 + a];
+    }
+#pragma unroll
+    for (int j = 0; j < M; j++) linv[(size_t)j * ld + q] = x[M - 1 - j];
+    if (!ok) atomicAdd(n_bad, 1);
+}
+
+// Generic factor build: any M <= MCAP, any DT <= 4, rows listed in `rows` (or all rows when rows == nullptr); handles
+// partial rows (fewer than m neighbours).  Triangle in local memory.
+template <int MCAP, bool MATERN>
+__global__ void __launch_bounds__(128) vecchia_factor_generic_kernel(const int *__restrict__ nn, const double *__restrict__ tl,
+                                                                     double *__restrict__ linv, const int *__restrict__ rows,
+                                                                     int n_rows, int ld, int M, CovConst cc,
+                                                                     int *__restrict__ n_bad) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows) return;
+    const int q = rows ? rows[t] : t;
+    const int DT = cc.dt;
+    int idx[MCAP];
+    int bsize = 0;
+    for (int j = 0; j < M; j++) {
+        const int v = nn[(size_t)j * ld + q];
+        if (v >= 0) idx[bsize++] = v;  // valid slots are a prefix of the row
+    }
+    double L[MCAP * (MCAP + 1) / 2];
+    double x[MCAP];
+    bool ok = true;
+    for (int a = 0; a < bsize; a++) {
+        const double *pa = tl + (size_t)idx[bsize - 1 - a] * DT;
+        for (int b = 0; b <= a; b++) {
+            double s;
+            if (a == b) {
+                s = cc.variance + cc.nugget;
+            } else {
+                const double *pb = tl + (size_t)idx[bsize - 1 - b] * DT;
+                double d2 = 0.0;
+                for (int c = 0; c < DT; c++) {
+                    const double u = pa[c] - pb[c];
+                    d2 += u * u;
+                }
+                s = kernel_value<MATERN>(cc, sqrt(d2));
+            }
+            for (int k = 0; k < b; k++) s -= L[a * (a + 1) / 2 + k] * L[b * (b + 1) / 2 + k];
+            if (a == b) {
+                ok = ok && (s > 0.0);
+                L[a * (a + 1) / 2 + a] = sqrt(s);
+            } else {
+                L[a * (a + 1) / 2 + b] = s / L[b * (b + 1) / 2 + b];
+            }
+        }
+    }
+    for (int a = bsize - 1; a >= 0; a--) {
+        double s = (a == bsize - 1) ? 1.0 : 0.0;
+        for (int k = a + 1; k < bsize; k++) s -= L[k * (k + 1) / 2 + a] * x[k];
+        x[a] = s / L[a * (a + 1) / 2 + a];
+    }
+    for (int j = 0; j < M; j++) linv[(size_t)j * ld + q] = (j < bsize) ? x[bsize - 1 - j] : 0.0;
+    if (!ok) atomicAdd(n_bad, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// row kernels: u_q = sum_j linv[j,q] * (v[nn[j,q]] - shift)
+// ---------------------------------------------------------------------------------------------------------------
+template <int MT>
+__device__ __forceinline__ double row_dot(const int *__restrict__ nn, const double *__restrict__ linv, const double *__restrict__ v,
+                                          double shift, int q, int ld, int M) {
+    double u = 0.0;
+    if (MT > 0) {
+        int idx[MT > 0 ? MT : 1];
+        double a[MT > 0 ? MT : 1];
+#pragma unroll
+        for (int j = 0; j < MT; j++) {
+            idx[j] = nn[(size_t)j * ld + q];
+            a[j] = linv[(size_t)j * ld + q];
+        }
+#pragma unroll
+        for (int j = 0; j < MT; j++)
+            if (idx[j] >= 0) u += a[j] * (v[idx[j]] - shift);
+    } else {
+        for (int j = 0; j < M; j++) {
+            const int id = nn[(size_t)j * ld + q];
+            if (id >= 0) u += linv[(size_t)j * ld + q] * (v[id] - shift);
+        }
+    }
+    return u;
+}
+
+// Vecchia log-likelihood partial sums: partials[b] = (sum log linv[0,q], sum u_q^2) over the rows of block b
+// (ll_compressed_sparse_chol, Scripts/mcmc_nngp_update_Gaussian.R:8-12; GpGp::Linv_mult fused with the reductions)
+template <int MT>
+__global__ void __launch_bounds__(256) loglik_partial_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
+                                                             const double *__restrict__ field, double shift, int n, int ld, int M,
+                                                             double2 *__restrict__ partials) {
+    double acc[2] = {0.0, 0.0};
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const double u = row_dot<MT>(nn, linv, field, shift, q, ld, M);
+        acc[0] += log(linv[q]);
+        acc[1] += u * u;
+    }
+    block_reduce_sum<2>(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = make_double2(acc[0], acc[1]);
+}
+
+// generic final reduction of NV-vectors of per-block partials: out[k] = sum_b partials[b*NV + k]
+template <int NV>
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__restrict__ partials, int n_blocks, double *__restrict__ out) {
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) acc[k] = 0.0;
+    for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) acc[k] += partials[(size_t)b * NV + k];
+    }
+    block_reduce_sum<NV>(acc);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) out[k] = acc[k];
+    }
+}
+
+// out_q = u_q (sparse_chol %*% (v - shift))
+template <int MT>
+__global__ void __launch_bounds__(256) spmv_rows_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
+                                                        const double *__restrict__ v, double shift, int n, int ld, int M,
+                                                        double *__restrict__ out) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
+        out[q] = row_dot<MT>(nn, linv, v, shift, q, ld, M);
+}
+
+// two fused products for the beta_0 update: partial sums of (v.v, u.v) with v = L^-1 1, u = L^-1 field
+// (Scripts/mcmc_nngp_update_Gaussian.R:221-222)
+template <int MT>
+__global__ void __launch_bounds__(256) beta0_partial_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
+                                                            const double *__restrict__ field, int n, int ld, int M,
+                                                            double2 *__restrict__ partials) {
+    double acc[2] = {0.0, 0.0};
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        double u = 0.0, v = 0.0;
+        for (int j = 0; j < (MT > 0 ? MT : M); j++) {
+            const int id = nn[(size_t)j * ld + q];
+            if (id >= 0) {
+                const double a = linv[(size_t)j * ld + q];
+                u += a * field[id];
+                v += a * 1.0;
+            }
+        }
+        acc[0] += v * v;
+        acc[1] += u * v;
+    }
+    block_reduce_sum<2>(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = make_double2(acc[0], acc[1]);
+}
+
+// t(sparse_chol) %*% u through the transpose map (no atomics)
+__global__ void __launch_bounds__(256) sptmv_kernel(const int *__restrict__ colptr, const int *__restrict__ crow,
+                                                    const int *__restrict__ csrc, const double *__restrict__ linv,
+                                                    const double *__restrict__ u, int n, double *__restrict__ out) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = colptr[q]; k < colptr[q + 1]; k++) s += linv[csrc[k]] * u[crow[k]];
+        out[q] = s;
+    }
+}
+
+// accept branch: gather the CSC values of the new current factor and its precision_diag in one pass
+// (replaces Matrix::sparseMatrix assembly + the (x^2) %*% indicator product, update_Gaussian.R:73-74,141-142,196-197)
+__global__ void __launch_bounds__(256) transpose_values_kernel(const int *__restrict__ colptr, const int *__restrict__ csrc,
+                                                               const double *__restrict__ linv, int n, double *__restrict__ valT,
+                                                               double *__restrict__ pd) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = colptr[q]; k < colptr[q + 1]; k++) {
+            const double v = linv[csrc[k]];
+            valT[k] = v;
+            s += v * v;
+        }
+        pd[q] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// level-scheduled sparse triangular solve: rows of one level (or, single-block variant, of a run of narrow levels)
+//   x_q = (b_q - sum_{j>=1} linv[j,q] x[nn[j,q]]) / linv[0,q]
+// optional fused epilogue: y_q = shift + scale * x_q   (initial field draw / ancillary proposal)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sptrsv_row(const int *__restrict__ nn, const double *__restrict__ linv, const double *__restrict__ b,
+                                           double *__restrict__ x, double *__restrict__ y, double shift, double scale, int q, int ld,
+                                           int M) {
+    double s = b[q];
+    for (int j = 1; j < M; j++) {
+        const int id = nn[(size_t)j * ld + q];
+        if (id >= 0) s -= linv[(size_t)j * ld + q] * x[id];
+    }
+    const double xv = s / linv[q];
+    x[q] = xv;
+    if (y) y[q] = shift + scale * xv;
+}
+
+__global__ void __launch_bounds__(256) sptrsv_level_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
+                                                           const int *__restrict__ lvl_rows, int lo, int hi,
+                                                           const double *__restrict__ b, double *__restrict__ x,
+                                                           double *__restrict__ y, double shift, double scale, int ld, int M) {
+    const int t = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < hi) sptrsv_row(nn, linv, b, x, y, shift, scale, lvl_rows[t], ld, M);
+}
+
+// one CTA walks levels [l0, l1) with a block barrier between them (the head and tail of the DAG are narrow)
+__global__ void __launch_bounds__(1024) sptrsv_multilevel_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
+                                                                 const int *__restrict__ lvl_rows, const int *__restrict__ lvl_ptr,
+                                                                 int l0, int l1, const double *__restrict__ b,
+                                                                 double *__restrict__ x, double *__restrict__ y, double shift,
+                                                                 double scale, int ld, int M) {
+    for (int l = l0; l < l1; l++) {
+        const int lo = lvl_ptr[l], hi = lvl_ptr[l + 1];
+        for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) sptrsv_row(nn, linv, b, x, y, shift, scale, lvl_rows[t], ld, M);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// observation-side kernels (gathers through locs_match)
+// ---------------------------------------------------------------------------------------------------------------
+// S_q = sum of y_minus_xb over the observations located at site q   (residuals_sum_matrix %*% ., update_Gaussian.R:90,260)
+__global__ void __launch_bounds__(256) site_obs_sum_kernel(const int *__restrict__ optr, const int *__restrict__ oidx,
+                                                           const double *__restrict__ ymx, int n, double *__restrict__ S) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = optr[q]; k < optr[q + 1]; k++) s += ymx[oidx[k]];
+        S[q] = s;
+    }
+}
+
+// partial sums of ( (ymx - fnew[lm])^2 , (ymx - f[lm])^2 ); fnew may alias f for a plain SSR
+__global__ void __launch_bounds__(256) obs_sq_partial_kernel(const int *__restrict__ lm, const double *__restrict__ ymx,
+                                                             const double *__restrict__ fnew, const double *__restrict__ f,
+                                                             int n_obs, double2 *__restrict__ partials) {
+    double acc[2] = {0.0, 0.0};
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) {
+        const int s = lm[o];
+        const double y = ymx[o];
+        const double en = y - fnew[s], eo = y - f[s];
+        acc[0] += en * en;
+        acc[1] += eo * eo;
+    }
+    block_reduce_sum<2>(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = make_double2(acc[0], acc[1]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// chromatic Gibbs sweep, one launch per colour: sites [q0, q1) are one colour class (contiguous in the internal
+// numbering).  Residual-maintained form: r = L^-1 (field - beta0) is kept up to date, so one site costs
+// one pass over its CSC column for the conditional mean and one to patch r.  Same-colour sites never share a row
+// (they would be moral neighbours), so the r updates inside a launch are conflict-free: no atomics.
+// (Scripts/mcmc_nngp_update_Gaussian.R:261-274)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sweep_normal(const SweepParams &sp, const double *__restrict__ zbuf, const int *__restrict__ zpos,
+                                               const int *__restrict__ gid, int q) {
+    if (sp.rng_mode == 0) return zbuf[sp.z_offset + (unsigned long long)zpos[q]];
+    return philox_normal((uint32_t)gid[q], (uint32_t)sp.sweep_counter, (uint32_t)(sp.sweep_counter >> 32), sp.key0, sp.key1);
+}
+
+__global__ void __launch_bounds__(256) gibbs_color_kernel(const int *__restrict__ colptr, const int *__restrict__ crow,
+                                                          const double *__restrict__ valT, const double *__restrict__ pd,
+                                                          const double *__restrict__ nobs, const double *__restrict__ S,
+                                                          const int *__restrict__ zpos, const int *__restrict__ gid,
+                                                          const double *__restrict__ zbuf, const SweepParams *__restrict__ spp,
+                                                          double *__restrict__ field, double *__restrict__ r, int q0, int q1) {
+    const int q = q0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= q1) return;
+    const SweepParams sp = *spp;
+    const int k0 = colptr[q], k1 = colptr[q + 1];
+    const double f_old = field[q];
+    const double w_old = f_old - sp.beta0;
+    double a = 0.0;
+    for (int k = k0; k < k1; k++) a += valT[k] * r[crow[k]];
+    const double Qss = pd[q], no = nobs[q];
+    const double prec = sp.e_ls * Qss + sp.e_ln * no;
+    const double t = a - Qss * w_old;
+    const double resid = S[q] - no * sp.beta0;
+    const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
+    const double z = sweep_normal(sp, zbuf, zpos, gid, q);
+    const double f_new = mean + z / sqrt(prec);
+    const double delta = (f_new - sp.beta0) - w_old;
+    for (int k = k0; k < k1; k++) r[crow[k]] += valT[k] * delta;
+    field[q] = f_new;
+}
+
+// tail of the colour sequence: colours [c0, c1) are small; one CTA walks them with a block barrier in between
+__global__ void __launch_bounds__(1024) gibbs_tail_kernel(const int *__restrict__ colptr, const int *__restrict__ crow,
+                                                          const double *__restrict__ valT, const double *__restrict__ pd,
+                                                          const double *__restrict__ nobs, const double *__restrict__ S,
+                                                          const int *__restrict__ zpos, const int *__restrict__ gid,
+                                                          const double *__restrict__ zbuf, const SweepParams *__restrict__ spp,
+                                                          double *__restrict__ field, double *__restrict__ r,
+                                                          const int *__restrict__ cstart, int c0, int c1) {
+    const SweepParams sp = *spp;
+    for (int c = c0; c < c1; c++) {
+        const int q0 = cstart[c], q1 = cstart[c + 1];
+        for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+            const int k0 = colptr[q], k1 = colptr[q + 1];
+            const double w_old = field[q] - sp.beta0;
+            double a = 0.0;
+            for (int k = k0; k < k1; k++) a += valT[k] * r[crow[k]];
+            const double Qss = pd[q], no = nobs[q];
+            const double prec = sp.e_ls * Qss + sp.e_ln * no;
+            const double t = a - Qss * w_old;
+            const double resid = S[q] - no * sp.beta0;
+            const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
+            const double z = sweep_normal(sp, zbuf, zpos, gid, q);
+            const double f_new = mean + z / sqrt(prec);
+            const double delta = (f_new - sp.beta0) - w_old;
+            for (int k = k0; k < k1; k++) r[crow[k]] += valT[k] * delta;
+            field[q] = f_new;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n) {
+    spp->sweep_counter += 1ull;
+    spp->z_offset += n;
+}
+
+}  // namespace nngp

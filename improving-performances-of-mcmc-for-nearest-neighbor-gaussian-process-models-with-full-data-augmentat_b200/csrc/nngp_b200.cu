@@ -1,0 +1,1131 @@
+// nngp_b200.cu -- context management and the C-ABI entry points of libnngp_b200.so (see include/nngp_b200.h).
+//
+// One context = one model's graph structure resident on one B200 plus the device-resident state of one chain
+// (current + proposal factor, field, residual r = L^-1 (field - beta_0)).  Only scalars and explicitly requested vectors
+// cross PCIe.  There is no CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <vector>
+
+#include "../../include/nngp_b200.h"
+#include "kernels.cuh"
+#include "nngp_internal.h"
+
+namespace nngp {
+
+// ------------------------------------------------------------------------------------------------------------------
+// errors, launch counter
+// ------------------------------------------------------------------------------------------------------------------
+static std::mutex g_err_mu;
+static char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct CudaFail {};
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            nngp::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));       \
+            throw nngp::CudaFail();                                                                      \
+        }                                                                                                \
+    } while (0)
+#define LAUNCHED(c) do { nngp::g_launches.fetch_add(1, std::memory_order_relaxed); (c)->launches_in_op++; } while (0)
+
+struct ArgFail {};
+#define REQUIRE(cond, ...)                    \
+    do {                                      \
+        if (!(cond)) {                        \
+            nngp::set_error(__VA_ARGS__);     \
+            throw nngp::ArgFail();            \
+        }                                     \
+    } while (0)
+struct StateFail {};
+
+// ------------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T> &h, cudaStream_t s) {
+        alloc(h.size());
+        if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct Ctx {
+    int device = 0, layout = NNGP_LAYOUT_COLOR_MORTON;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int n = 0, d = 0, m = 0, M = 0, ld = 0, n_obs = 0, covfun = 0, dt = 0, K = 0, n_levels = 0, max_col = 0;
+    long long nnz = 0;
+    int n_sm = 148;
+    long long launches_in_op = 0;
+
+    // host-side structure
+    std::vector<int> i2g, g2i, cstart, lvl_ptr, partial_rows;
+    struct Seg { int l0, l1; bool single_block; };
+    std::vector<Seg> solve_plan;
+    int tail_color = 0;  // colours [tail_color, K) are walked by one CTA
+
+    // device structure
+    DevBuf<int> d_i2g, d_g2i, d_nn, d_colptr, d_crow, d_csrc, d_zpos, d_lvl_rows, d_lvl_ptr, d_lm, d_optr, d_oidx, d_cstart,
+        d_partial_rows, d_nbad;
+    DevBuf<double> d_locs, d_tl, d_linv[2], d_valT, d_pd, d_nobs, d_ymx, d_S, d_field, d_newfield, d_r, d_tmp1, d_tmp2, d_io,
+        d_zbuf, d_partials, d_scalars, d_flush;
+    DevBuf<SweepParams> d_sp;
+    double *h_pinned = nullptr;       // 64 doubles of pinned scratch for scalar results
+    double *h_stage = nullptr;        // pinned staging for vectors (n doubles at least)
+    size_t h_stage_n = 0;
+
+    int cur = 0;                      // which linv buffer is the current factor (slot 0); the other one is the proposal
+    bool have_factor[2] = {false, false};
+    bool committed = false;           // valT / pd correspond to linv[cur]
+    bool have_field = false, have_obs = false, have_newfield = false;
+    CovConst last_cc{};
+    bool have_cc = false;
+    unsigned long long sweep_counter = 0;
+    cudaGraphExec_t sweep_graph = nullptr;
+    bool use_graph = true;
+
+    double *linv_slot(int slot) { return d_linv[slot == NNGP_SLOT_CURRENT ? cur : 1 - cur].p; }
+    bool &have_slot(int slot) { return have_factor[slot == NNGP_SLOT_CURRENT ? cur : 1 - cur]; }
+};
+
+static std::mutex g_ctx_mu;
+static std::vector<Ctx *> g_ctx;
+
+static Ctx *get_ctx(const int *id) {
+    REQUIRE(id != nullptr, "null ctx_id");
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    REQUIRE(*id >= 0 && *id < (int)g_ctx.size() && g_ctx[*id] != nullptr, "unknown context id %d", *id);
+    Ctx *c = g_ctx[*id];
+    return c;
+}
+
+static void use(Ctx *c) { CK(cudaSetDevice(c->device)); }
+
+static int grid_for(Ctx *c, long long work, int block, int per_sm = 8) {
+    long long b = (work + block - 1) / block;
+    long long cap = (long long)c->n_sm * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+static void ensure_stage(Ctx *c, size_t count) {
+    if (c->h_stage_n >= count) return;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr;
+    c->h_stage_n = 0;
+    CK(cudaMallocHost(&c->h_stage, count * sizeof(double)));
+    c->h_stage_n = count;
+}
+
+// host vector (reference order) -> device vector (internal order)
+static void upload_site_vector(Ctx *c, const double *host, double *dev) {
+    ensure_stage(c, c->n);
+    std::memcpy(c->h_stage, host, sizeof(double) * c->n);
+    CK(cudaMemcpyAsync(c->d_io.p, c->h_stage, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+    gather_f64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(dev, c->d_io.p, c->d_i2g.p, c->n);
+    LAUNCHED(c);
+}
+
+// device vector (internal order) -> host vector (reference order)
+static void download_site_vector(Ctx *c, const double *dev, double *host) {
+    ensure_stage(c, c->n);
+    gather_f64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_io.p, dev, c->d_g2i.p, c->n);
+    LAUNCHED(c);
+    CK(cudaMemcpyAsync(c->h_stage, c->d_io.p, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::memcpy(host, c->h_stage, sizeof(double) * c->n);
+}
+
+static uint32_t morton2(uint32_t x, uint32_t y) {
+    auto spread = [](uint32_t v) {
+        v &= 0xffffu;
+        v = (v | (v << 8)) & 0x00ff00ffu;
+        v = (v | (v << 4)) & 0x0f0f0f0fu;
+        v = (v | (v << 2)) & 0x33333333u;
+        v = (v | (v << 1)) & 0x55555555u;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1);
+}
+
+static CovConst make_cov(Ctx *c, const double *cp, int ncp) {
+    CovConst cc{};
+    cc.covfun = c->covfun;
+    cc.d = c->d;
+    cc.dt = c->dt;
+    const bool matern = c->covfun >= NNGP_MATERN_ISOTROPIC;
+    int n_range;
+    switch (c->covfun) {
+        case NNGP_EXPONENTIAL_SCALEDIM: case NNGP_MATERN_SCALEDIM: n_range = c->d; break;
+        case NNGP_EXPONENTIAL_SPACETIME: case NNGP_MATERN_SPACETIME: n_range = 2; break;
+        default: n_range = 1;
+    }
+    REQUIRE(ncp == 2 + n_range + (matern ? 1 : 0), "covparms has %d entries, covfun %d with d=%d needs %d", ncp, c->covfun, c->d,
+            2 + n_range + (matern ? 1 : 0));
+    cc.variance = cp[0];
+    cc.nugget = cp[ncp - 1] * cp[0];
+    cc.smooth = matern ? cp[ncp - 2] : 0.0;
+    cc.normcon = matern ? cc.variance / (std::pow(2.0, cc.smooth - 1.0) * std::tgamma(cc.smooth)) : 0.0;
+    for (int k = 0; k < 4; k++) cc.range[k] = 1.0;
+    switch (c->covfun) {
+        case NNGP_EXPONENTIAL_SCALEDIM: case NNGP_MATERN_SCALEDIM:
+            for (int k = 0; k < c->d; k++) cc.range[k] = cp[1 + k];
+            break;
+        case NNGP_EXPONENTIAL_SPACETIME: case NNGP_MATERN_SPACETIME:
+            for (int k = 0; k < c->d - 1; k++) cc.range[k] = cp[1];
+            cc.range[c->d - 1] = cp[2];
+            break;
+        default:
+            for (int k = 0; k < 4; k++) cc.range[k] = cp[1];
+    }
+    return cc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// device ops (all asynchronous on c->stream unless they return a scalar)
+// ------------------------------------------------------------------------------------------------------------------
+template <bool MATERN>
+static void launch_factor(Ctx *c, double *linv, const CovConst &cc) {
+    const int n = c->n, ld = c->ld, M = c->M;
+    bool specialised = false;
+    const int blk = 128, grd = (n + blk - 1) / blk;
+#define FACTOR_CASE(MM, DD)                                                                                              \
+    if (M == MM && c->dt == DD) {                                                                                        \
+        vecchia_factor_reg_kernel<MM, DD, MATERN><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p); \
+        specialised = true;                                                                                              \
+    }
+    FACTOR_CASE(6, 2)
+    FACTOR_CASE(6, 3)
+    FACTOR_CASE(11, 2)
+    FACTOR_CASE(11, 3)
+#undef FACTOR_CASE
+    if (specialised) {
+        LAUNCHED(c);
+        const int np = (int)c->partial_rows.size();
+        if (np > 0) {
+            vecchia_factor_generic_kernel<16, MATERN><<<(np + blk - 1) / blk, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, c->d_partial_rows.p, np, ld, M, cc, c->d_nbad.p);
+            LAUNCHED(c);
+        }
+        return;
+    }
+    if (M <= 8) vecchia_factor_generic_kernel<8, MATERN><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, nullptr, n, ld, M, cc, c->d_nbad.p);
+    else if (M <= 16) vecchia_factor_generic_kernel<16, MATERN><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, nullptr, n, ld, M, cc, c->d_nbad.p);
+    else if (M <= 24) vecchia_factor_generic_kernel<24, MATERN><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, nullptr, n, ld, M, cc, c->d_nbad.p);
+    else vecchia_factor_generic_kernel<32, MATERN><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, nullptr, n, ld, M, cc, c->d_nbad.p);
+    LAUNCHED(c);
+}
+
+static void op_factor_build(Ctx *c, int slot, const CovConst &cc) {
+    CK(cudaMemsetAsync(c->d_nbad.p, 0, sizeof(int), c->stream));
+    transform_locs_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_locs.p, c->d_tl.p, c->n, cc);
+    LAUNCHED(c);
+    double *linv = c->linv_slot(slot);
+    if (c->covfun >= NNGP_MATERN_ISOTROPIC) launch_factor<true>(c, linv, cc);
+    else launch_factor<false>(c, linv, cc);
+    CK(cudaGetLastError());
+    c->have_slot(slot) = true;
+    if (slot == NNGP_SLOT_CURRENT) c->committed = false;
+}
+
+#define DISPATCH_MT(M, CALL)          \
+    switch (M) {                      \
+        case 6: { constexpr int MT = 6; CALL; } break;   \
+        case 11: { constexpr int MT = 11; CALL; } break; \
+        case 21: { constexpr int MT = 21; CALL; } break; \
+        default: { constexpr int MT = 0; CALL; } break;  \
+    }
+
+static const int kReduceBlocks = 148 * 8;
+
+// partial sums -> d_scalars[off..off+1]
+static void op_loglik_sums(Ctx *c, const double *linv, const double *field, double shift, int scal_off) {
+    const int blocks = std::min(kReduceBlocks, (c->n + 255) / 256);
+    DISPATCH_MT(c->M, (loglik_partial_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, field, shift, c->n, c->ld, c->M, reinterpret_cast<double2 *>(c->d_partials.p))));
+    LAUNCHED(c);
+    reduce_partials_kernel<2><<<1, 1024, 0, c->stream>>>(c->d_partials.p, blocks, c->d_scalars.p + scal_off);
+    LAUNCHED(c);
+}
+
+static void op_spmv(Ctx *c, const double *linv, const double *v, double shift, double *out) {
+    DISPATCH_MT(c->M, (spmv_rows_kernel<MT><<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_nn.p, linv, v, shift, c->n, c->ld, c->M, out)));
+    LAUNCHED(c);
+}
+
+// x = solve(linv, b); optional y = shift + scale * x
+static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, double *y, double shift, double scale) {
+    for (const auto &s : c->solve_plan) {
+        if (s.single_block) {
+            sptrsv_multilevel_kernel<<<1, 1024, 0, c->stream>>>(c->d_nn.p, linv, c->d_lvl_rows.p, c->d_lvl_ptr.p, s.l0, s.l1, b, x, y, shift, scale, c->ld, c->M);
+        } else {
+            const int lo = c->lvl_ptr[s.l0], hi = c->lvl_ptr[s.l0 + 1];
+            sptrsv_level_kernel<<<(hi - lo + 255) / 256, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_lvl_rows.p, lo, hi, b, x, y, shift, scale, c->ld, c->M);
+        }
+        LAUNCHED(c);
+    }
+}
+
+static void op_commit(Ctx *c) {
+    transpose_values_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, c->n, c->d_valT.p, c->d_pd.p);
+    LAUNCHED(c);
+    c->committed = true;
+}
+
+static void launch_sweep_colors(Ctx *c) {
+    for (int col = 0; col < c->tail_color; col++) {
+        const int q0 = c->cstart[col], q1 = c->cstart[col + 1];
+        gibbs_color_kernel<<<(q1 - q0 + 255) / 256, 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, q0, q1);
+    }
+    if (c->tail_color < c->K)
+        gibbs_tail_kernel<<<1, 1024, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, c->d_cstart.p, c->tail_color, c->K);
+    advance_sweep_kernel<<<1, 1, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n);
+}
+
+static int sweep_launches(Ctx *c) { return c->tail_color + (c->tail_color < c->K ? 1 : 0) + 1; }
+
+// one sweep over all colours; parameters are read from d_sp
+static void op_sweep_once(Ctx *c) {
+    if (c->use_graph) {
+        if (!c->sweep_graph) {
+            cudaGraph_t g;
+            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            launch_sweep_colors(c);
+            CK(cudaStreamEndCapture(c->stream, &g));
+            CK(cudaGraphInstantiate(&c->sweep_graph, g, 0));
+            CK(cudaGraphDestroy(g));
+        }
+        CK(cudaGraphLaunch(c->sweep_graph, c->stream));
+    } else {
+        launch_sweep_colors(c);
+        CK(cudaGetLastError());
+    }
+    const int nl = sweep_launches(c);
+    g_launches.fetch_add(nl, std::memory_order_relaxed);
+    c->launches_in_op += nl;
+}
+
+static void set_sweep_params(Ctx *c, double beta0, double log_scale, double log_noise_variance, int rng_mode, double seed) {
+    SweepParams *sp = reinterpret_cast<SweepParams *>(c->h_pinned + 32);
+    sp->beta0 = beta0;
+    sp->e_ls = std::exp(-log_scale);
+    sp->e_ln = std::exp(-log_noise_variance);
+    sp->sweep_counter = c->sweep_counter;
+    sp->z_offset = 0;
+    const unsigned long long s = (unsigned long long)(long long)seed;
+    sp->key0 = (unsigned int)(s & 0xffffffffull);
+    sp->key1 = (unsigned int)(s >> 32) ^ 0x5eed5eedu;
+    sp->rng_mode = rng_mode;
+    CK(cudaMemcpyAsync(c->d_sp.p, sp, sizeof(SweepParams), cudaMemcpyHostToDevice, c->stream));
+}
+
+static void fetch_scalars(Ctx *c, int count) {
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars.p, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+}
+
+static double ll_from_sums(Ctx *c, double sum_log, double sum_sq, double log_scale) {
+    return sum_log - c->n * 0.5 * log_scale - 0.5 * sum_sq / std::exp(log_scale);
+}
+
+static void op_obs_sq(Ctx *c, const double *fnew, const double *f, int scal_off) {
+    const int blocks = std::min(kReduceBlocks, (c->n_obs + 255) / 256);
+    obs_sq_partial_kernel<<<blocks, 256, 0, c->stream>>>(c->d_lm.p, c->d_ymx.p, fnew, f, c->n_obs, reinterpret_cast<double2 *>(c->d_partials.p));
+    LAUNCHED(c);
+    reduce_partials_kernel<2><<<1, 1024, 0, c->stream>>>(c->d_partials.p, blocks, c->d_scalars.p + scal_off);
+    LAUNCHED(c);
+}
+
+static void op_beta0_sums(Ctx *c, int scal_off) {
+    const int blocks = std::min(kReduceBlocks, (c->n + 255) / 256);
+    DISPATCH_MT(c->M, (beta0_partial_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, c->d_linv[c->cur].p, c->d_field.p, c->n, c->ld, c->M, reinterpret_cast<double2 *>(c->d_partials.p))));
+    LAUNCHED(c);
+    reduce_partials_kernel<2><<<1, 1024, 0, c->stream>>>(c->d_partials.p, blocks, c->d_scalars.p + scal_off);
+    LAUNCHED(c);
+}
+
+static void ensure_zbuf(Ctx *c, size_t count) {
+    if (c->d_zbuf.n >= count) return;
+    CK(cudaStreamSynchronize(c->stream));
+    c->d_zbuf.alloc(count);
+    if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; }  // zbuf pointer is baked in
+}
+
+static void refresh_r(Ctx *c, double beta0) { op_spmv(c, c->d_linv[c->cur].p, c->d_field.p, beta0, c->d_r.p); }
+
+static void flush_l2(Ctx *c) {
+    if (c->d_flush.n == 0) c->d_flush.alloc((size_t)32 << 20);  // 256 MB of doubles
+    fill_f64_kernel<<<c->n_sm * 8, 256, 0, c->stream>>>(c->d_flush.p, 1.0, c->d_flush.n);
+}
+
+static void destroy_ctx(Ctx *c) {
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->sweep_graph) cudaGraphExecDestroy(c->sweep_graph);
+    DevBuf<int> *ib[] = {&c->d_i2g, &c->d_g2i, &c->d_nn, &c->d_colptr, &c->d_crow, &c->d_csrc, &c->d_zpos, &c->d_lvl_rows, &c->d_lvl_ptr,
+                         &c->d_lm, &c->d_optr, &c->d_oidx, &c->d_cstart, &c->d_partial_rows, &c->d_nbad};
+    for (auto *b : ib) b->release();
+    DevBuf<double> *db[] = {&c->d_locs, &c->d_tl, &c->d_linv[0], &c->d_linv[1], &c->d_valT, &c->d_pd, &c->d_nobs, &c->d_ymx, &c->d_S,
+                            &c->d_field, &c->d_newfield, &c->d_r, &c->d_tmp1, &c->d_tmp2, &c->d_io, &c->d_zbuf, &c->d_partials,
+                            &c->d_scalars, &c->d_flush};
+    for (auto *b : db) b->release();
+    c->d_sp.release();
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+}  // namespace nngp
+
+using namespace nngp;
+
+// every ABI function runs its body through this wrapper: exceptions never cross the C boundary
+#define ABI_BEGIN try {
+#define ABI_END                                                   \
+    if (status) *status = NNGP_OK;                                \
+    }                                                             \
+    catch (const nngp::ArgFail &) { if (status) *status = NNGP_ERR_ARG; }     \
+    catch (const nngp::CudaFail &) { if (status) *status = NNGP_ERR_CUDA; }   \
+    catch (const nngp::StateFail &) { if (status) *status = NNGP_ERR_STATE; } \
+    catch (const std::bad_alloc &) { nngp::set_error("host allocation failed"); if (status) *status = NNGP_ERR_ALLOC; } \
+    catch (...) { nngp::set_error("unexpected exception"); if (status) *status = NNGP_ERR_ARG; }
+#define NEED(cond, msg) do { if (!(cond)) { nngp::set_error(msg); throw nngp::StateFail(); } } while (0)
+
+extern "C" {
+
+void nngp_version(int *major, int *minor) { if (major) *major = 0; if (minor) *minor = 1; }
+
+void nngp_last_error(char *buf, const int *len) {
+    if (!buf || !len || *len <= 0) return;
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    std::strncpy(buf, g_err, (size_t)*len - 1);
+    buf[*len - 1] = '\0';
+}
+
+void nngp_launch_count(double *count) { if (count) *count = (double)g_launches.load(); }
+
+void nngp_device_count(int *count, int *status) {
+    ABI_BEGIN
+    REQUIRE(count != nullptr, "null count");
+    int k = 0;
+    cudaError_t e = cudaGetDeviceCount(&k);
+    if (e != cudaSuccess) { k = 0; set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); *count = 0; throw CudaFail(); }
+    *count = k;
+    ABI_END
+}
+
+void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *locs, const int *NNarray, const int *coloring,
+                     const int *n_obs_, const int *locs_match, const int *covfun_id, const int *device, const int *layout,
+                     int *ctx_id, int *status) {
+    Ctx *c = nullptr;
+    ABI_BEGIN
+    REQUIRE(n_ && d_ && m_ && locs && NNarray && coloring && n_obs_ && locs_match && covfun_id && device && layout && ctx_id, "nngp_ctx_create: null argument");
+    const int n = *n_, d = *d_, m = *m_, M = m + 1, n_obs = *n_obs_;
+    REQUIRE(n >= 1 && d >= 1 && d <= 4 && m >= 1 && m <= 31 && n_obs >= 0, "nngp_ctx_create: need n>=1, 1<=d<=4, 1<=m<=31 (got n=%d d=%d m=%d)", n, d, m);
+    REQUIRE(*covfun_id >= 0 && *covfun_id <= 7, "unknown covfun_id %d", *covfun_id);
+    REQUIRE((long long)n * M < 2147483647LL, "n*(m+1) must fit int32");
+    if ((*covfun_id == NNGP_EXPONENTIAL_SPHERE || *covfun_id == NNGP_MATERN_SPHERE)) REQUIRE(d == 2, "*_sphere needs lon/lat (d=2)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: libnngp_b200 has no CPU fallback"); throw CudaFail(); }
+    REQUIRE(*device >= 0 && *device < ndev, "device %d out of range (%d devices)", *device, ndev);
+
+    c = new Ctx();
+    c->device = *device;
+    c->layout = (*layout == NNGP_LAYOUT_COLOR) ? NNGP_LAYOUT_COLOR : NNGP_LAYOUT_COLOR_MORTON;
+    c->n = n; c->d = d; c->m = m; c->M = M; c->n_obs = n_obs; c->covfun = *covfun_id;
+    c->dt = (*covfun_id == NNGP_EXPONENTIAL_SPHERE || *covfun_id == NNGP_MATERN_SPHERE) ? 3 : d;
+    c->ld = (n + 31) / 32 * 32;
+    use(c);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    c->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    CK(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
+
+    // ---- validate structure, colour classes ----
+    int K = 0;
+    for (int i = 0; i < n; i++) { REQUIRE(coloring[i] >= 1, "coloring[%d] = %d (colours are 1..K)", i, coloring[i]); K = std::max(K, coloring[i]); }
+    c->K = K;
+    for (int i = 0; i < n; i++) {
+        REQUIRE(NNarray[i] == i + 1, "NNarray[%d,1] must be the row itself", i + 1);
+        bool seen_na = false;
+        for (int j = 1; j < M; j++) {
+            const int v = NNarray[(size_t)i + (size_t)n * j];
+            if (v == NNGP_NA_INT) { seen_na = true; continue; }
+            REQUIRE(!seen_na, "NNarray row %d has a neighbour after an NA", i + 1);
+            REQUIRE(v >= 1 && v <= i, "NNarray[%d,%d] = %d is not a previous site", i + 1, j + 1, v);
+        }
+    }
+    // ---- internal numbering: colour-major; inside a colour reference order or Morton order ----
+    std::vector<uint32_t> key(n, 0);
+    if (c->layout == NNGP_LAYOUT_COLOR_MORTON) {
+        double lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
+        const int dd = std::min(d, 2);
+        for (int k = 0; k < dd; k++)
+            for (int i = 0; i < n; i++) { const double x = locs[(size_t)i + (size_t)n * k]; lo[k] = std::min(lo[k], x); hi[k] = std::max(hi[k], x); }
+        for (int i = 0; i < n; i++) {
+            uint32_t g[2] = {0, 0};
+            for (int k = 0; k < dd; k++) {
+                const double ext = hi[k] - lo[k];
+                double t = ext > 0 ? (locs[(size_t)i + (size_t)n * k] - lo[k]) / ext : 0.0;
+                g[k] = (uint32_t)std::min(65535.0, std::max(0.0, t * 65536.0));
+            }
+            key[i] = morton2(g[0], g[1]);
+        }
+    }
+    c->i2g.resize(n);
+    std::iota(c->i2g.begin(), c->i2g.end(), 0);
+    std::stable_sort(c->i2g.begin(), c->i2g.end(), [&](int a, int b) {
+        if (coloring[a] != coloring[b]) return coloring[a] < coloring[b];
+        return key[a] < key[b];
+    });
+    c->g2i.resize(n);
+    for (int q = 0; q < n; q++) c->g2i[c->i2g[q]] = q;
+    c->cstart.assign(K + 1, 0);
+    for (int i = 0; i < n; i++) c->cstart[coloring[i]]++;
+    for (int k = 0; k < K; k++) c->cstart[k + 1] += c->cstart[k];
+    // position of each site inside the reference's rnorm() hand-out order: colour 1..K, ascending reference index
+    std::vector<int> zpos(n);
+    {
+        std::vector<int> next(c->cstart.begin(), c->cstart.end() - 1);
+        std::vector<int> zg(n);
+        for (int i = 0; i < n; i++) zg[i] = next[coloring[i] - 1]++;
+        for (int q = 0; q < n; q++) zpos[q] = zg[c->i2g[q]];
+    }
+    // colours small enough to be walked by a single CTA form the tail
+    c->tail_color = K;
+    while (c->tail_color > 0 && (c->cstart[c->tail_color] - c->cstart[c->tail_color - 1]) <= 2048) c->tail_color--;
+
+    // ---- row structure in internal numbering ----
+    const int ld = c->ld;
+    std::vector<int> nn((size_t)ld * M, -1);
+    for (int q = 0; q < n; q++) {
+        const int i = c->i2g[q];
+        bool partial = false;
+        for (int j = 0; j < M; j++) {
+            const int v = NNarray[(size_t)i + (size_t)n * j];
+            if (v == NNGP_NA_INT) partial = true;
+            else nn[(size_t)j * ld + q] = c->g2i[v - 1];
+        }
+        if (partial) c->partial_rows.push_back(q);
+    }
+    std::vector<double> locs_int((size_t)n * d);
+    for (int q = 0; q < n; q++)
+        for (int k = 0; k < d; k++) locs_int[(size_t)q * d + k] = locs[(size_t)c->i2g[q] + (size_t)n * k];
+    // ---- transpose (CSC) structure ----
+    std::vector<int> colptr(n + 1, 0);
+    for (int q = 0; q < n; q++)
+        for (int j = 0; j < M; j++) { const int v = nn[(size_t)j * ld + q]; if (v >= 0) colptr[v + 1]++; }
+    for (int q = 0; q < n; q++) { c->max_col = std::max(c->max_col, colptr[q + 1]); colptr[q + 1] += colptr[q]; }
+    c->nnz = colptr[n];
+    std::vector<int> crow(c->nnz), csrc(c->nnz);
+    {
+        std::vector<int> pos(colptr.begin(), colptr.end() - 1);
+        for (int q = 0; q < n; q++)  // rows ascending => every column's entries are sorted by row
+            for (int j = 0; j < M; j++) {
+                const int v = nn[(size_t)j * ld + q];
+                if (v >= 0) { crow[pos[v]] = q; csrc[pos[v]] = j * ld + q; pos[v]++; }
+            }
+    }
+    // ---- solve DAG levels ----
+    std::vector<int> level;
+    c->n_levels = solve_levels(NNarray, n, m, level);
+    c->lvl_ptr.assign(c->n_levels + 1, 0);
+    for (int i = 0; i < n; i++) c->lvl_ptr[level[i] + 1]++;
+    for (int l = 0; l < c->n_levels; l++) c->lvl_ptr[l + 1] += c->lvl_ptr[l];
+    std::vector<int> lvl_rows(n);
+    {
+        std::vector<int> pos(c->lvl_ptr.begin(), c->lvl_ptr.end() - 1);
+        for (int q = 0; q < n; q++) lvl_rows[pos[level[c->i2g[q]]]++] = q;  // internal ids ascending inside a level
+    }
+    // plan: runs of narrow levels -> one single-CTA launch; wide levels -> one launch each
+    for (int l = 0; l < c->n_levels;) {
+        const int w = c->lvl_ptr[l + 1] - c->lvl_ptr[l];
+        if (w <= 4096) {
+            int l1 = l;
+            while (l1 < c->n_levels && (c->lvl_ptr[l1 + 1] - c->lvl_ptr[l1]) <= 4096) l1++;
+            c->solve_plan.push_back({l, l1, true});
+            l = l1;
+        } else {
+            c->solve_plan.push_back({l, l + 1, false});
+            l++;
+        }
+    }
+    // ---- observations ----
+    std::vector<int> lm(n_obs), optr(n + 1, 0), oidx(n_obs);
+    for (int o = 0; o < n_obs; o++) {
+        REQUIRE(locs_match[o] >= 1 && locs_match[o] <= n, "locs_match[%d] = %d out of range", o + 1, locs_match[o]);
+        lm[o] = c->g2i[locs_match[o] - 1];
+        optr[lm[o] + 1]++;
+    }
+    std::vector<double> nobs(n);
+    for (int q = 0; q < n; q++) { nobs[q] = optr[q + 1]; optr[q + 1] += optr[q]; }
+    {
+        std::vector<int> pos(optr.begin(), optr.end() - 1);
+        for (int o = 0; o < n_obs; o++) oidx[pos[lm[o]]++] = o;
+    }
+    // ---- upload ----
+    cudaStream_t s = c->stream;
+    c->d_i2g.upload(c->i2g, s); c->d_g2i.upload(c->g2i, s); c->d_nn.upload(nn, s); c->d_colptr.upload(colptr, s);
+    c->d_crow.upload(crow, s); c->d_csrc.upload(csrc, s); c->d_zpos.upload(zpos, s); c->d_lvl_rows.upload(lvl_rows, s);
+    c->d_lvl_ptr.upload(c->lvl_ptr, s); c->d_lm.upload(lm, s); c->d_optr.upload(optr, s); c->d_oidx.upload(oidx, s);
+    c->d_cstart.upload(c->cstart, s); c->d_locs.upload(locs_int, s); c->d_nobs.upload(nobs, s);
+    if (!c->partial_rows.empty()) c->d_partial_rows.upload(c->partial_rows, s);
+    c->d_nbad.alloc(1);
+    c->d_tl.alloc((size_t)n * c->dt);
+    for (int k = 0; k < 2; k++) { c->d_linv[k].alloc((size_t)ld * M); CK(cudaMemsetAsync(c->d_linv[k].p, 0, sizeof(double) * ld * M, s)); }
+    c->d_valT.alloc(c->nnz); c->d_pd.alloc(n); c->d_ymx.alloc(std::max(n_obs, 1)); c->d_S.alloc(n); c->d_field.alloc(n);
+    c->d_newfield.alloc(n); c->d_r.alloc(n); c->d_tmp1.alloc(n); c->d_tmp2.alloc(n); c->d_io.alloc((size_t)std::max(n, n_obs));
+    c->d_zbuf.alloc(n); c->d_partials.alloc((size_t)kReduceBlocks * 4); c->d_scalars.alloc(64); c->d_sp.alloc(1);
+    CK(cudaMemsetAsync(c->d_S.p, 0, sizeof(double) * n, s));
+    CK(cudaStreamSynchronize(s));   // host vectors go out of scope below
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        int id = -1;
+        for (size_t k = 0; k < g_ctx.size(); k++) if (!g_ctx[k]) { id = (int)k; break; }
+        if (id < 0) { g_ctx.push_back(nullptr); id = (int)g_ctx.size() - 1; }
+        g_ctx[id] = c;
+        *ctx_id = id;
+    }
+    c = nullptr;
+    ABI_END
+    if (c) destroy_ctx(c);
+}
+
+void nngp_ctx_destroy(const int *ctx_id, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    { std::lock_guard<std::mutex> lk(g_ctx_mu); g_ctx[*ctx_id] = nullptr; }
+    destroy_ctx(c);
+    ABI_END
+}
+
+void nngp_ctx_info(const int *ctx_id, int *info8, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(info8 != nullptr, "null info");
+    info8[0] = c->n; info8[1] = c->m; info8[2] = c->K; info8[3] = c->n_levels; info8[4] = (int)c->nnz; info8[5] = c->max_col;
+    info8[6] = c->device; info8[7] = c->layout;
+    ABI_END
+}
+
+void nngp_factor_build(const int *ctx_id, const int *slot, const double *covparms, const int *n_covparms, int *n_not_pd, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(slot && covparms && n_covparms && (*slot == 0 || *slot == 1), "nngp_factor_build: bad argument");
+    use(c);
+    const CovConst cc = make_cov(c, covparms, *n_covparms);
+    c->last_cc = cc; c->have_cc = true;
+    op_factor_build(c, *slot, cc);
+    int bad = 0;
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_nbad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::memcpy(&bad, c->h_pinned, sizeof(int));
+    if (n_not_pd) *n_not_pd = bad;
+    ABI_END
+}
+
+void nngp_factor_get(const int *ctx_id, const int *slot, double *Linv, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(slot && Linv && (*slot == 0 || *slot == 1), "nngp_factor_get: bad argument");
+    NEED(c->have_slot(*slot), "nngp_factor_get: that slot holds no factor");
+    use(c);
+    DevBuf<double> tmp;
+    tmp.alloc((size_t)c->n * c->M);
+    linv_to_host_order_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(tmp.p, c->linv_slot(*slot), c->d_g2i.p, c->n, c->ld, c->M);
+    LAUNCHED(c);
+    CK(cudaMemcpyAsync(Linv, tmp.p, sizeof(double) * (size_t)c->n * c->M, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    tmp.release();
+    ABI_END
+}
+
+void nngp_factor_accept(const int *ctx_id, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    NEED(c->have_slot(NNGP_SLOT_PROPOSAL), "nngp_factor_accept: no proposal factor");
+    use(c);
+    c->cur = 1 - c->cur;
+    op_commit(c);
+    ABI_END
+}
+
+void nngp_factor_commit(const int *ctx_id, const int *slot, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(slot && (*slot == 0 || *slot == 1), "nngp_factor_commit: bad slot");
+    NEED(c->have_slot(*slot), "nngp_factor_commit: that slot holds no factor");
+    use(c);
+    if (*slot == NNGP_SLOT_PROPOSAL) c->cur = 1 - c->cur;
+    op_commit(c);
+    ABI_END
+}
+
+void nngp_precision_diag(const int *ctx_id, double *out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(out != nullptr, "null out");
+    NEED(c->have_slot(NNGP_SLOT_CURRENT), "nngp_precision_diag: no current factor");
+    use(c);
+    if (!c->committed) op_commit(c);
+    download_site_vector(c, c->d_pd.p, out);
+    ABI_END
+}
+
+void nngp_field_set(const int *ctx_id, const double *field, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(field != nullptr, "null field");
+    use(c);
+    upload_site_vector(c, field, c->d_field.p);
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_field = true;
+    ABI_END
+}
+
+void nngp_field_get(const int *ctx_id, double *field, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(field != nullptr, "null field");
+    NEED(c->have_field, "nngp_field_get: no field on the device");
+    use(c);
+    download_site_vector(c, c->d_field.p, field);
+    ABI_END
+}
+
+void nngp_obs_set(const int *ctx_id, const double *y_minus_xb, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(y_minus_xb != nullptr || c->n_obs == 0, "null observations");
+    use(c);
+    if (c->n_obs > 0) {
+        ensure_stage(c, std::max(c->n_obs, c->n));
+        std::memcpy(c->h_stage, y_minus_xb, sizeof(double) * c->n_obs);
+        CK(cudaMemcpyAsync(c->d_ymx.p, c->h_stage, sizeof(double) * c->n_obs, cudaMemcpyHostToDevice, c->stream));
+        site_obs_sum_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_optr.p, c->d_oidx.p, c->d_ymx.p, c->n, c->d_S.p);
+        LAUNCHED(c);
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->have_obs = true;
+    ABI_END
+}
+
+void nngp_loglik(const int *ctx_id, const int *slot, const double *beta_0, const double *log_scale, double *ll, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(slot && beta_0 && log_scale && ll && (*slot == 0 || *slot == 1), "nngp_loglik: bad argument");
+    NEED(c->have_slot(*slot), "nngp_loglik: that slot holds no factor");
+    NEED(c->have_field, "nngp_loglik: no field on the device");
+    use(c);
+    op_loglik_sums(c, c->linv_slot(*slot), c->d_field.p, *beta_0, 0);
+    fetch_scalars(c, 2);
+    *ll = ll_from_sums(c, c->h_pinned[0], c->h_pinned[1], *log_scale);
+    ABI_END
+}
+
+void nngp_loglik_host(const int *ctx_id, const int *slot, const double *z, const double *log_scale, double *ll, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(slot && z && log_scale && ll && (*slot == 0 || *slot == 1), "nngp_loglik_host: bad argument");
+    NEED(c->have_slot(*slot), "nngp_loglik_host: that slot holds no factor");
+    use(c);
+    upload_site_vector(c, z, c->d_tmp1.p);
+    op_loglik_sums(c, c->linv_slot(*slot), c->d_tmp1.p, 0.0, 0);
+    fetch_scalars(c, 2);
+    *ll = ll_from_sums(c, c->h_pinned[0], c->h_pinned[1], *log_scale);
+    ABI_END
+}
+
+void nngp_spmv(const int *ctx_id, const int *slot, const double *v, double *out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(slot && v && out && (*slot == 0 || *slot == 1), "nngp_spmv: bad argument");
+    NEED(c->have_slot(*slot), "nngp_spmv: that slot holds no factor");
+    use(c);
+    upload_site_vector(c, v, c->d_tmp1.p);
+    op_spmv(c, c->linv_slot(*slot), c->d_tmp1.p, 0.0, c->d_tmp2.p);
+    download_site_vector(c, c->d_tmp2.p, out);
+    ABI_END
+}
+
+void nngp_sptmv(const int *ctx_id, const int *slot, const double *u, double *out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(slot && u && out && (*slot == 0 || *slot == 1), "nngp_sptmv: bad argument");
+    NEED(c->have_slot(*slot), "nngp_sptmv: that slot holds no factor");
+    use(c);
+    upload_site_vector(c, u, c->d_tmp1.p);
+    sptmv_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_csrc.p, c->linv_slot(*slot), c->d_tmp1.p, c->n, c->d_tmp2.p);
+    LAUNCHED(c);
+    download_site_vector(c, c->d_tmp2.p, out);
+    ABI_END
+}
+
+void nngp_sptrsv(const int *ctx_id, const int *slot, const double *b, double *x, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(slot && b && x && (*slot == 0 || *slot == 1), "nngp_sptrsv: bad argument");
+    NEED(c->have_slot(*slot), "nngp_sptrsv: that slot holds no factor");
+    use(c);
+    upload_site_vector(c, b, c->d_tmp1.p);
+    op_sptrsv(c, c->linv_slot(*slot), c->d_tmp1.p, c->d_tmp2.p, nullptr, 0.0, 1.0);
+    CK(cudaGetLastError());
+    download_site_vector(c, c->d_tmp2.p, x);
+    ABI_END
+}
+
+void nngp_gibbs_sweep(const int *ctx_id, const int *n_sweeps, const double *beta_0, const double *log_scale,
+                      const double *log_noise_variance, const int *rng_mode, const double *z, const double *seed, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(n_sweeps && beta_0 && log_scale && log_noise_variance && rng_mode && *n_sweeps >= 0, "nngp_gibbs_sweep: bad argument");
+    REQUIRE(*rng_mode == NNGP_RNG_PHILOX || (*rng_mode == NNGP_RNG_SUPPLIED && z != nullptr), "nngp_gibbs_sweep: rng_mode 0 needs z");
+    NEED(c->have_slot(NNGP_SLOT_CURRENT), "nngp_gibbs_sweep: no current factor");
+    NEED(c->have_field && c->have_obs, "nngp_gibbs_sweep: field and observations must be set first");
+    use(c);
+    if (!c->committed) op_commit(c);
+    const size_t nz = (size_t)c->n * (size_t)std::max(1, *n_sweeps);
+    if (*rng_mode == NNGP_RNG_SUPPLIED) {
+        ensure_zbuf(c, nz);
+        CK(cudaMemcpyAsync(c->d_zbuf.p, z, sizeof(double) * nz, cudaMemcpyHostToDevice, c->stream));
+    }
+    set_sweep_params(c, *beta_0, *log_scale, *log_noise_variance, *rng_mode, seed ? *seed : 0.0);
+    refresh_r(c, *beta_0);
+    for (int s = 0; s < *n_sweeps; s++) op_sweep_once(c);
+    c->sweep_counter += (unsigned long long)*n_sweeps;
+    CK(cudaStreamSynchronize(c->stream));
+    ABI_END
+}
+
+void nngp_ancillary_propose(const int *ctx_id, const double *beta_0, const double *delta_log_scale,
+                            const double *log_noise_variance, double *field_response_ratio, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(beta_0 && delta_log_scale && log_noise_variance && field_response_ratio, "nngp_ancillary_propose: bad argument");
+    NEED(c->have_slot(NNGP_SLOT_CURRENT) && c->have_slot(NNGP_SLOT_PROPOSAL), "nngp_ancillary_propose: needs current and proposal factors");
+    NEED(c->have_field && c->have_obs, "nngp_ancillary_propose: field and observations must be set first");
+    use(c);
+    // tmp1 = current %*% (field - beta_0); tmp2 = solve(proposal, tmp1); newfield = beta_0 + exp(.5 dls) * tmp2
+    op_spmv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, *beta_0, c->d_tmp1.p);
+    op_sptrsv(c, c->linv_slot(NNGP_SLOT_PROPOSAL), c->d_tmp1.p, c->d_tmp2.p, c->d_newfield.p, *beta_0, std::exp(0.5 * *delta_log_scale));
+    op_obs_sq(c, c->d_newfield.p, c->d_field.p, 0);
+    CK(cudaGetLastError());
+    fetch_scalars(c, 2);
+    // sum(dnorm(y, new) - dnorm(y, old)) = -(SSR_new - SSR_old) / (2 tau^2)
+    *field_response_ratio = -0.5 * (c->h_pinned[0] - c->h_pinned[1]) * std::exp(-*log_noise_variance);
+    c->have_newfield = true;
+    ABI_END
+}
+
+void nngp_ancillary_accept(const int *ctx_id, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    NEED(c->have_newfield, "nngp_ancillary_accept: no proposal field");
+    use(c);
+    // D2D copy (16 MB of traffic at n = 1M) rather than a pointer swap: the captured sweep graph bakes the field pointer in
+    CK(cudaMemcpyAsync(c->d_field.p, c->d_newfield.p, sizeof(double) * c->n, cudaMemcpyDeviceToDevice, c->stream));
+    c->have_newfield = false;
+    c->cur = 1 - c->cur;
+    op_commit(c);
+    ABI_END
+}
+
+void nngp_beta0_moments(const int *ctx_id, const double *log_scale, double *mean, double *var, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(log_scale && mean && var, "nngp_beta0_moments: bad argument");
+    NEED(c->have_slot(NNGP_SLOT_CURRENT) && c->have_field, "nngp_beta0_moments: needs a current factor and a field");
+    use(c);
+    op_beta0_sums(c, 0);
+    fetch_scalars(c, 2);
+    const double vv = c->h_pinned[0], uv = c->h_pinned[1];
+    *var = (1.0 / vv) * std::exp(*log_scale);
+    *mean = std::exp(-*log_scale) * uv * *var;
+    ABI_END
+}
+
+void nngp_ssr(const int *ctx_id, double *ssr, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(ssr != nullptr, "null ssr");
+    NEED(c->have_field && c->have_obs, "nngp_ssr: field and observations must be set first");
+    use(c);
+    op_obs_sq(c, c->d_field.p, c->d_field.p, 0);
+    fetch_scalars(c, 2);
+    *ssr = c->h_pinned[0];
+    ABI_END
+}
+
+void nngp_field_init(const int *ctx_id, const int *slot, const double *beta_0, const double *log_scale, const double *z, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(slot && beta_0 && log_scale && z && (*slot == 0 || *slot == 1), "nngp_field_init: bad argument");
+    NEED(c->have_slot(*slot), "nngp_field_init: that slot holds no factor");
+    use(c);
+    upload_site_vector(c, z, c->d_tmp1.p);
+    op_sptrsv(c, c->linv_slot(*slot), c->d_tmp1.p, c->d_tmp2.p, c->d_field.p, *beta_0, std::sqrt(std::exp(*log_scale)));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_field = true;
+    ABI_END
+}
+
+void nngp_predict_sample(const int *ctx_id, const int *slot, const int *n_obs_sites, const double *field, const double *beta_0,
+                         const double *log_scale, const double *z_pred, double *out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(slot && n_obs_sites && field && beta_0 && log_scale && z_pred && out && (*slot == 0 || *slot == 1), "nngp_predict_sample: bad argument");
+    REQUIRE(*n_obs_sites >= 0 && *n_obs_sites <= c->n, "nngp_predict_sample: n_obs_sites out of range");
+    NEED(c->have_slot(*slot), "nngp_predict_sample: that slot holds no factor");
+    use(c);
+    // rhs (reference order) = c( sparse_chol[1:n,1:n] %*% (field - beta_0) / sd , z_pred ); the first n rows of the solve then
+    // return (field - beta_0)/sd exactly, so build rhs by spmv over the joint factor with x_pred = 0 on the new rows.
+    const int n0 = *n_obs_sites, np = c->n - n0;
+    const double sd = std::exp(0.5 * *log_scale);
+    std::vector<double> host(c->n);
+    for (int i = 0; i < n0; i++) host[i] = (field[i] - *beta_0) / sd;
+    for (int i = 0; i < np; i++) host[n0 + i] = 0.0;
+    upload_site_vector(c, host.data(), c->d_tmp1.p);
+    op_spmv(c, c->linv_slot(*slot), c->d_tmp1.p, 0.0, c->d_tmp2.p);   // rows < n0 only involve observed sites
+    // overwrite the rhs of the new rows with z_pred
+    download_site_vector(c, c->d_tmp2.p, host.data());
+    for (int i = 0; i < np; i++) host[n0 + i] = z_pred[i];
+    upload_site_vector(c, host.data(), c->d_tmp1.p);
+    op_sptrsv(c, c->linv_slot(*slot), c->d_tmp1.p, c->d_tmp2.p, nullptr, 0.0, 1.0);
+    CK(cudaGetLastError());
+    download_site_vector(c, c->d_tmp2.p, host.data());
+    for (int i = 0; i < np; i++) out[i] = sd * host[n0 + i];
+    ABI_END
+}
+
+void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, const int *n_iter_, const double *thin_,
+                    const int *n_chromatic_, const int *iter_start_, const int *chain_index_, const int *rng_mode_,
+                    const double *var_y_, double *records_out, double *field_records_out, int *accept_out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(n_shape_ && params_io && n_iter_ && thin_ && n_chromatic_ && iter_start_ && chain_index_ && rng_mode_ && var_y_, "nngp_chain_run: null argument");
+    const int ns = *n_shape_, n_iter = *n_iter_, n_chromatic = *n_chromatic_, iter_start = *iter_start_, rng_mode = *rng_mode_;
+    const double thin = *thin_, var_y = *var_y_;
+    REQUIRE(ns >= 1 && ns <= 5 && n_iter >= 0 && n_chromatic >= 0, "nngp_chain_run: bad sizes");
+    NEED(c->have_field && c->have_obs, "nngp_chain_run: field and observations must be set first");
+    use(c);
+    const int n = c->n, n_obs = c->n_obs;
+    const bool matern = c->covfun >= NNGP_MATERN_ISOTROPIC;
+    double beta_0 = params_io[0], log_scale = params_io[1], lnv = params_io[2], logvar_suf = params_io[3], logvar_anc = params_io[4];
+    double shape[5], new_shape[5], cp[8], innovation[6];
+    for (int k = 0; k < ns; k++) shape[k] = params_io[5 + k];
+    auto to_covparms = [&](const double *sh) {   // update_Gaussian.R:67-71,117-122,173-178
+        cp[0] = 1.0;
+        for (int j = 0; j < ns; j++) cp[1 + j] = (matern && j == ns - 1) ? 0.5 + 0.5 / (1.0 + std::exp(-sh[j])) : std::exp(sh[j]);
+        cp[1 + ns] = 0.0;
+        return make_cov(c, cp, ns + 2);
+    };
+    auto n_bad = [&]() {
+        int bad;
+        CK(cudaMemcpyAsync(c->h_pinned + 8, c->d_nbad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        std::memcpy(&bad, c->h_pinned + 8, sizeof(int));
+        return bad;
+    };
+    RStream rs;
+    rs.set_seed((uint32_t)(iter_start + *chain_index_));                         // :36
+    op_factor_build(c, NNGP_SLOT_CURRENT, to_covparms(shape));                   // :72
+    op_commit(c);                                                                // :73-74
+    std::vector<double> zhost;
+    if (rng_mode == NNGP_RNG_SUPPLIED) { zhost.resize(n); rs.rnorm(zhost.data(), n); }   // :75 current_p consumes n normals
+    else for (int i = 0; i < n; i++) (void)rs.norm_rand();
+    std::vector<int> acc_anc(n_iter + 1, 0), acc_suf(n_iter + 1, 0);
+    const int n_frec = (int)std::nearbyint(n_iter * thin);
+    const unsigned long long philox_seed = ((unsigned long long)(uint32_t)iter_start << 20) ^ (unsigned long long)(uint32_t)*chain_index_;
+    for (int iter = 1; iter <= n_iter; iter++) {
+        // ---- (A) ancillary :113-157 ----
+        const double sd_anc = std::exp(.5 * logvar_anc);
+        for (int k = 0; k < ns + 1; k++) innovation[k] = 0.0 + sd_anc * rs.norm_rand();
+        double new_log_scale = log_scale + innovation[0];
+        for (int k = 0; k < ns; k++) new_shape[k] = shape[k] + innovation[1 + k];
+        op_factor_build(c, NNGP_SLOT_PROPOSAL, to_covparms(new_shape));          // :123
+        op_spmv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, beta_0, c->d_tmp1.p);
+        op_sptrsv(c, c->linv_slot(NNGP_SLOT_PROPOSAL), c->d_tmp1.p, c->d_tmp2.p, c->d_newfield.p, beta_0, std::exp(.5 * (new_log_scale - log_scale)));  // :127
+        op_obs_sq(c, c->d_newfield.p, c->d_field.p, 0);
+        fetch_scalars(c, 2);
+        const int bad_a = n_bad();
+        const double ratio = -0.5 * (c->h_pinned[0] - c->h_pinned[1]) * std::exp(-lnv);   // :129-131
+        if (ratio + 0.0 > std::log(rs.unif_rand()) && bad_a == 0) {              // :133
+            std::memcpy(shape, new_shape, sizeof(double) * ns);
+            log_scale = new_log_scale;
+            CK(cudaMemcpyAsync(c->d_field.p, c->d_newfield.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+            c->cur = 1 - c->cur;
+            op_commit(c);
+            acc_anc[iter] = 1;
+        }
+        if (iter_start >= 0 && iter_start <= 2000 && iter % 25 == 0) {           // :153-157
+            int a = 0;
+            for (int k = iter - 24; k <= iter; k++) a += acc_anc[k];
+            const double mean_acc = a / 25.0;
+            if (mean_acc < .05) logvar_anc -= (.4 + .05 * rs.norm_rand());
+            if (mean_acc > .15) logvar_anc += (.4 + .05 * rs.norm_rand());
+        }
+        // ---- (B) sufficient :165-213 ----
+        const double sd_suf = std::exp(.5 * logvar_suf);
+        for (int k = 0; k < ns + 1; k++) innovation[k] = 0.0 + sd_suf * rs.norm_rand();
+        new_log_scale = log_scale + innovation[0];
+        if (std::exp(new_log_scale) < var_y) {                                    // :167
+            for (int k = 0; k < ns; k++) new_shape[k] = shape[k] + innovation[1 + k];
+            op_factor_build(c, NNGP_SLOT_PROPOSAL, to_covparms(new_shape));      // :179
+            op_loglik_sums(c, c->linv_slot(NNGP_SLOT_PROPOSAL), c->d_field.p, beta_0, 0);
+            op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, beta_0, 2);
+            fetch_scalars(c, 4);
+            const int bad_s = n_bad();
+            const double GP_ratio = ll_from_sums(c, c->h_pinned[0], c->h_pinned[1], new_log_scale) -
+                                    ll_from_sums(c, c->h_pinned[2], c->h_pinned[3], log_scale);   // :184-186
+            if (GP_ratio > std::log(rs.unif_rand()) && bad_s == 0) {              // :189
+                std::memcpy(shape, new_shape, sizeof(double) * ns);
+                log_scale = new_log_scale;
+                c->cur = 1 - c->cur;
+                op_commit(c);
+                acc_suf[iter] = 1;
+            }
+        }
+        if (iter_start >= 0 && iter_start <= 2000 && iter % 25 == 0) {           // :209-213
+            int a = 0;
+            for (int k = iter - 24; k <= iter; k++) a += acc_suf[k];
+            const double mean_acc = a / 25.0;
+            if (mean_acc < .05) logvar_suf -= (.2 + .05 * rs.norm_rand());
+            if (mean_acc > .15) logvar_suf += (.2 + .05 * rs.norm_rand());
+        }
+        // ---- (C) beta_0 :219-224 ----
+        op_beta0_sums(c, 0);
+        fetch_scalars(c, 2);
+        {
+            const double bvar = (1.0 / c->h_pinned[0]) * std::exp(log_scale);
+            const double bmean = std::exp(-log_scale) * c->h_pinned[1] * bvar;
+            beta_0 = bmean + std::sqrt(bvar) * rs.norm_rand();
+        }
+        // ---- (D) chromatic sweeps :257-275 ----
+        if (rng_mode == NNGP_RNG_SUPPLIED) {
+            ensure_zbuf(c, (size_t)n * std::max(1, n_chromatic));
+            zhost.resize((size_t)n * std::max(1, n_chromatic));
+            rs.rnorm(zhost.data(), (int64_t)n * n_chromatic);
+            CK(cudaMemcpyAsync(c->d_zbuf.p, zhost.data(), sizeof(double) * (size_t)n * n_chromatic, cudaMemcpyHostToDevice, c->stream));
+        }
+        set_sweep_params(c, beta_0, log_scale, lnv, rng_mode, (double)philox_seed);
+        refresh_r(c, beta_0);
+        for (int s = 0; s < n_chromatic; s++) op_sweep_once(c);
+        c->sweep_counter += (unsigned long long)n_chromatic;
+        // ---- (E) noise variance :281-293 ----
+        op_obs_sq(c, c->d_field.p, c->d_field.p, 0);
+        fetch_scalars(c, 2);
+        const double ssr = c->h_pinned[0];
+        for (int k = 0; k < 10; k++) {
+            const double inn = 0.0 + .01 * rs.norm_rand();
+            if (std::exp(lnv + inn) < var_y) {
+                if (-.5 * n_obs * inn - .5 * ssr * (std::exp(-lnv - inn) - std::exp(-lnv)) > std::log(rs.unif_rand())) lnv += inn;
+            }
+        }
+        // ---- (F) records :305-311 ----
+        if (records_out) {
+            records_out[(size_t)(iter - 1)] = beta_0;
+            records_out[(size_t)(iter - 1) + (size_t)n_iter] = log_scale;
+            records_out[(size_t)(iter - 1) + (size_t)n_iter * 2] = lnv;
+            for (int k = 0; k < ns; k++) records_out[(size_t)(iter - 1) + (size_t)n_iter * (3 + k)] = shape[k];
+        }
+        if (field_records_out) {
+            const double t = iter * thin;
+            if (std::nearbyint(t) == t) {
+                const int row = (int)t - 1;
+                if (row >= 0 && row < n_frec) {
+                    std::vector<double> f(n);
+                    download_site_vector(c, c->d_field.p, f.data());
+                    for (int s = 0; s < n; s++) field_records_out[(size_t)row + (size_t)n_frec * s] = f[s];
+                }
+            }
+        }
+        if (accept_out) { accept_out[iter - 1] = acc_anc[iter]; accept_out[n_iter + iter - 1] = acc_suf[iter]; }
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    params_io[0] = beta_0; params_io[1] = log_scale; params_io[2] = lnv; params_io[3] = logvar_suf; params_io[4] = logvar_anc;
+    for (int k = 0; k < ns; k++) params_io[5 + k] = shape[k];
+    ABI_END
+}
+
+void nngp_time_op(const int *ctx_id, const int *op_, const int *reps_, const int *flush_l2_, double *ms_out, int *launches_out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(op_ && reps_ && flush_l2_ && ms_out && *reps_ >= 1, "nngp_time_op: bad argument");
+    const int op = *op_;
+    use(c);
+    NEED(c->have_slot(NNGP_SLOT_CURRENT), "nngp_time_op: build and commit a factor first");
+    if (!c->committed) op_commit(c);
+    if (op == 0) NEED(c->have_cc, "nngp_time_op(factor): call nngp_factor_build once first");
+    if (op == 2 || op == 6) {
+        NEED(c->have_field && c->have_obs, "nngp_time_op(sweep): field and observations must be set first");
+        const SweepParams *sp = reinterpret_cast<SweepParams *>(c->h_pinned + 32);
+        set_sweep_params(c, sp->beta0, -std::log(sp->e_ls > 0 ? sp->e_ls : 1.0), -std::log(sp->e_ln > 0 ? sp->e_ln : 1.0), NNGP_RNG_PHILOX, 12345.0);
+        refresh_r(c, sp->beta0);
+    }
+    if (op == 1 || op == 3 || op == 4 || op == 6) NEED(c->have_field, "nngp_time_op: field must be set first");
+    CK(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < *reps_; r++) {
+        if (*flush_l2_) flush_l2(c);
+        c->launches_in_op = 0;
+        CK(cudaEventRecord(c->ev0, c->stream));
+        switch (op) {
+            case 0: op_factor_build(c, NNGP_SLOT_PROPOSAL, c->last_cc); break;
+            case 1: op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, 0); break;
+            case 2: op_sweep_once(c); c->sweep_counter++; break;
+            case 3: op_spmv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, c->d_tmp1.p); break;
+            case 4: op_spmv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, c->d_tmp1.p);
+                    op_sptrsv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_tmp1.p, c->d_tmp2.p, nullptr, 0.0, 1.0); break;
+            case 5: op_commit(c); break;
+            case 6: op_sweep_once(c); c->sweep_counter++;
+                    op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, 0); break;
+            default: REQUIRE(false, "nngp_time_op: unknown op %d", op);
+        }
+        CK(cudaEventRecord(c->ev1, c->stream));
+        CK(cudaEventSynchronize(c->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        ms_out[r] = ms;
+        if (launches_out) *launches_out = (int)c->launches_in_op;
+    }
+    CK(cudaGetLastError());
+    ABI_END
+}
+
+}  // extern "C"

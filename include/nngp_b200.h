@@ -1,0 +1,201 @@
+/*
+ * include/nngp_b200.h -- C ABI of libnngp_b200.so, the B200-native replacement for the inner loop of the reference's
+ * NNGP sampler (reference = R scripts under /root/reference/Scripts; citations below are relative to that tree).
+ *
+ * The reference has no FFI of its own: its hot path is the body of mcmc_nngp_update_Gaussian and the GpGp / Matrix
+ * calls it makes.  Each entry point below names the reference call site(s) it replaces.
+ *
+ * Calling convention: every function is extern "C", returns void, and takes ONLY pointers, so that it can be bound with
+ * R's .C() (dyn.load + .C, no R headers needed), with ctypes, or with any other FFI.  The last argument is always
+ * `int *status`: 0 = ok, otherwise one of NNGP_ERR_*; the message is retrievable with nngp_last_error().
+ *
+ * Data conventions at the boundary are R's: column-major matrices, FP64 (`double`), `int` = int32, indices 1-based,
+ * NA_integer_ = INT_MIN.  `field` always includes beta_0 (state$params$field, Scripts/mcmc_nngp_initialize.R:208).
+ * Any internal re-numbering of sites (colour-major / Morton) is invisible here.
+ *
+ * The library needs a CUDA device (sm_100a); there is no CPU fallback: every compute entry point fails with
+ * NNGP_ERR_CUDA when no device is usable.  The nngp_host_* functions are set-up utilities that run on the host by design
+ * (they replace GpGp::find_ordered_nn / Coloring.R, which are init-time code in the reference as well).
+ */
+#ifndef NNGP_B200_H
+#define NNGP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNGP_OK 0
+#define NNGP_ERR_ARG 1      /* bad argument / unknown context */
+#define NNGP_ERR_CUDA 2     /* CUDA runtime error or no device */
+#define NNGP_ERR_NCCL 3     /* communicator error */
+#define NNGP_ERR_STATE 4    /* call order (e.g. sweep before a factor was built) */
+#define NNGP_ERR_ALLOC 5
+
+#define NNGP_NA_INT (-2147483647 - 1)
+
+/* covfun_id: the reference's stationary_covfun strings (Scripts/mcmc_nngp_initialize.R:62-69) */
+#define NNGP_EXPONENTIAL_ISOTROPIC 0
+#define NNGP_EXPONENTIAL_SPHERE 1
+#define NNGP_EXPONENTIAL_SCALEDIM 2
+#define NNGP_EXPONENTIAL_SPACETIME 3
+#define NNGP_MATERN_ISOTROPIC 4
+#define NNGP_MATERN_SPHERE 5
+#define NNGP_MATERN_SCALEDIM 6
+#define NNGP_MATERN_SPACETIME 7
+
+/* factor slots: the sampler keeps a current factor and a proposal (compressed_sparse_chol / new_compressed_sparse_chol,
+ * Scripts/mcmc_nngp_update_Gaussian.R:72,123,179) */
+#define NNGP_SLOT_CURRENT 0
+#define NNGP_SLOT_PROPOSAL 1
+
+/* rng_mode for the field draws of the chromatic sweep */
+#define NNGP_RNG_SUPPLIED 0 /* caller passes the normals (R's rnorm stream): bit-comparable with the reference order */
+#define NNGP_RNG_PHILOX 1   /* counter-based Philox4x32-10 keyed by (seed, sweep counter, global site id) */
+
+/* internal site layout (performance knob; results are layout-independent up to FP64 summation order) */
+#define NNGP_LAYOUT_COLOR 1        /* colour-major, reference order inside a colour */
+#define NNGP_LAYOUT_COLOR_MORTON 2 /* colour-major, Morton (Z-curve) order inside a colour */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * library / device
+ * ------------------------------------------------------------------------------------------------------------------ */
+void nngp_version(int *major, int *minor);
+void nngp_device_count(int *count, int *status);
+/* copies the last error message (NUL-terminated, truncated to *len bytes) */
+void nngp_last_error(char *buf, const int *len);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * host-side set-up utilities (init-time in the reference too)
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* replaces GpGp::find_ordered_nn(locs, m)  (Scripts/mcmc_nngp_initialize.R:93, Scripts/mcmc_nngp_predict.R:5).
+ * Exact m nearest PREVIOUS sites by Euclidean distance on the raw coordinates, ties by lower index; column 1 = self;
+ * NA padding.  locs n x d column-major; NNarray n x (m+1) column-major out. */
+void nngp_host_find_ordered_nn(const double *locs, const int *n, const int *d, const int *m, int *NNarray, int *status);
+/* replaces the crossprod() moral graph + naive_greedy_coloring (Scripts/mcmc_nngp_initialize.R:103-110,
+ * Scripts/Coloring.R:2-20) without the dense (n+1) x maxdeg scratch: identical first-fit colours 1..K. */
+void nngp_host_greedy_coloring(const int *NNarray, const int *n, const int *m, int *coloring, int *n_colors, int *status);
+/* exact max-min (farthest-point) ordering, 1-based permutation (replaces GpGp::order_maxmin,
+ * Scripts/mcmc_nngp_initialize.R:29; GpGp's is a randomised approximation and cannot be reproduced bit-for-bit) */
+void nngp_host_order_maxmin(const double *locs, const int *n, const int *d, int *order, int *status);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * context: graph structure uploaded once (vecchia_approx, Scripts/mcmc_nngp_initialize.R:80-110)
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* locs n x d; NNarray n x (m+1); coloring n (1..K); locs_match n_obs (1-based site of each observation);
+ * device: CUDA ordinal; layout: NNGP_LAYOUT_*.  Returns a context id. */
+void nngp_ctx_create(const int *n, const int *d, const int *m, const double *locs, const int *NNarray,
+                     const int *coloring, const int *n_obs, const int *locs_match, const int *covfun_id,
+                     const int *device, const int *layout, int *ctx_id, int *status);
+void nngp_ctx_destroy(const int *ctx_id, int *status);
+/* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,
+ * [6]=device, [7]=layout */
+void nngp_ctx_info(const int *ctx_id, int *info8, int *status);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Vecchia factor  (GpGp::vecchia_Linv + Matrix::sparseMatrix assembly)
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* replaces GpGp::vecchia_Linv(covparms, covfun_name, locs, NNarray) followed by Matrix::sparseMatrix(...)
+ * (Scripts/mcmc_nngp_update_Gaussian.R:72-73,123-124,179-180; initialize.R:201-207; predict.R:39-40).
+ * covparms = c(variance, shape..., nugget) exactly as the reference passes them (c(1, shape, 0)).
+ * n_not_pd = number of rows whose neighbour block was not positive definite (the proposal must then be rejected). */
+void nngp_factor_build(const int *ctx_id, const int *slot, const double *covparms, const int *n_covparms,
+                       int *n_not_pd, int *status);
+/* copies the compressed factor (n x (m+1), column-major, unused slots 0) to the host */
+void nngp_factor_get(const int *ctx_id, const int *slot, double *Linv, int *status);
+/* the accept branch (Scripts/mcmc_nngp_update_Gaussian.R:139-142,194-197): proposal becomes current and
+ * precision_diag is recomputed */
+void nngp_factor_accept(const int *ctx_id, int *status);
+/* makes `slot` the sweep's factor without swapping (used after the initial build, update_Gaussian.R:72-74) */
+void nngp_factor_commit(const int *ctx_id, const int *slot, int *status);
+/* precision_diag (Scripts/mcmc_nngp_update_Gaussian.R:74,142,197) of the current factor */
+void nngp_precision_diag(const int *ctx_id, double *out, int *status);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * device-resident chain state
+ * ------------------------------------------------------------------------------------------------------------------ */
+void nngp_field_set(const int *ctx_id, const double *field, int *status);
+void nngp_field_get(const int *ctx_id, double *field, int *status);
+/* y_minus_xb[o] = observed_field[o] - (mu[o] - beta_0), i.e. the response minus the non-intercept fixed effects
+ * (equal to observed_field when there are no regressors).  Everything the sampler needs from the observations
+ * (residuals_sum update_Gaussian.R:260, the dnorm ratio :129-131, the SSR :281) is derived from it on the device. */
+void nngp_obs_set(const int *ctx_id, const double *y_minus_xb, int *status);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Vecchia log-likelihood and sparse products
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* replaces ll_compressed_sparse_chol(Linv, field - beta_0, NNarray, log_scale)
+ * (Scripts/mcmc_nngp_update_Gaussian.R:8-12, called :185-186) on the device-resident field */
+void nngp_loglik(const int *ctx_id, const int *slot, const double *beta_0, const double *log_scale, double *ll,
+                 int *status);
+/* same, with the (already centred) field passed from the host: the end-to-end form of one log-lik evaluation */
+void nngp_loglik_host(const int *ctx_id, const int *slot, const double *z, const double *log_scale, double *ll,
+                      int *status);
+/* sparse_chol %*% v   (GpGp::Linv_mult; Scripts/mcmc_nngp_update_Gaussian.R:10,127,221-222,241) */
+void nngp_spmv(const int *ctx_id, const int *slot, const double *v, double *out, int *status);
+/* crossprod(sparse_chol, u) = t(sparse_chol) %*% u  (Scripts/mcmc_nngp_update_Gaussian.R:269) */
+void nngp_sptmv(const int *ctx_id, const int *slot, const double *u, double *out, int *status);
+/* Matrix::solve(sparse_chol, b)  (initialize.R:208; update_Gaussian.R:127; predict.R:46) */
+void nngp_sptrsv(const int *ctx_id, const int *slot, const double *b, double *x, int *status);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * sampler steps on the device-resident state
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* n_sweeps chromatic Gibbs sweeps of the latent field (Scripts/mcmc_nngp_update_Gaussian.R:257-275) with the current
+ * factor.  rng_mode NNGP_RNG_SUPPLIED: z holds n_sweeps * n normals, sweep-major, each sweep in the order in which the
+ * reference's rnorm(length(selected_locs)) calls hand them out (colour 1..K, sites ascending inside a colour).
+ * NNGP_RNG_PHILOX: z is ignored (may be NULL); seed/stream pick the Philox key, and the library advances a per-context
+ * sweep counter. */
+void nngp_gibbs_sweep(const int *ctx_id, const int *n_sweeps, const double *beta_0, const double *log_scale,
+                      const double *log_noise_variance, const int *rng_mode, const double *z, const double *seed,
+                      int *status);
+/* ancillary proposal (Scripts/mcmc_nngp_update_Gaussian.R:127-131): new_field = beta_0 + exp(.5 dls) *
+ * solve(proposal, current %*% (field - beta_0)) is formed on the device and the Gaussian observation log-density
+ * difference field_response_ratio is returned.  nngp_ancillary_accept() makes new_field the field. */
+void nngp_ancillary_propose(const int *ctx_id, const double *beta_0, const double *delta_log_scale,
+                            const double *log_noise_variance, double *field_response_ratio, int *status);
+void nngp_ancillary_accept(const int *ctx_id, int *status);
+/* beta_0 | field without regressors (Scripts/mcmc_nngp_update_Gaussian.R:219-224): returns mean and variance */
+void nngp_beta0_moments(const int *ctx_id, const double *log_scale, double *mean, double *var, int *status);
+/* sum_squared_residuals (Scripts/mcmc_nngp_update_Gaussian.R:281) */
+void nngp_ssr(const int *ctx_id, double *ssr, int *status);
+/* initial field draw (Scripts/mcmc_nngp_initialize.R:201-208): field = beta_0 + exp(.5 log_scale) * solve(slot, z) */
+void nngp_field_init(const int *ctx_id, const int *slot, const double *beta_0, const double *log_scale,
+                     const double *z, int *status);
+
+/* one chain, n_iter iterations of the reference loop for the no-regressor model (Scripts/mcmc_nngp_update_Gaussian.R:
+ * 101-314) entirely behind the ABI: scalars only cross PCIe, plus the thinned field rows.
+ * params_io: [beta_0, log_scale, log_noise_variance, logvar_sufficient, logvar_ancillary, shape_1..shape_k]
+ * records_out: n_iter x (3 + k) column-major [beta_0, log_scale, log_noise_variance, shape...]
+ * field_records_out: round(n_iter * thin) x n column-major, or NULL
+ * rng_mode NNGP_RNG_SUPPLIED reproduces R's stream (set.seed(iter_start + chain_index), Mersenne-Twister + inversion)
+ * for every draw including the field normals; NNGP_RNG_PHILOX uses R's stream for the scalar draws and Philox for the
+ * field. */
+void nngp_chain_run(const int *ctx_id, const int *n_shape, double *params_io, const int *n_iter, const double *thin,
+                    const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode,
+                    const double *var_y, double *records_out, double *field_records_out, int *accept_out, int *status);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * prediction  (mcmc_nngp_predict_field, Scripts/mcmc_nngp_predict.R:25-54)
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* The context must have been created over the joint (observed ++ predicted) site set (predict.R:4-5), n_obs_sites =
+ * number of observed sites (the first rows).  For one stored sample: builds nothing (uses factor `slot`), forms
+ * x_obs = (field - beta_0)/sd and conditionally simulates the n_pred new rows; out = sd * x_pred (predict.R:43-53). */
+void nngp_predict_sample(const int *ctx_id, const int *slot, const int *n_obs_sites, const double *field,
+                         const double *beta_0, const double *log_scale, const double *z_pred, double *out, int *status);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * measurement
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Times `reps` back-to-back launches of one device op with CUDA events on the library's own stream (inputs resident in
+ * HBM). op: 0 factor_build(proposal slot, last covparms) 1 loglik 2 one Gibbs sweep (Philox) 3 spmv 4 sptrsv
+ * 5 precision_diag/transposition 6 sweep + loglik.  ms_out[reps] per-launch milliseconds; launches_out = kernels launched
+ * per repetition. flush_l2 != 0 writes a 256 MB scratch buffer between repetitions (outside the timed events). */
+void nngp_time_op(const int *ctx_id, const int *op, const int *reps, const int *flush_l2, double *ms_out,
+                  int *launches_out, int *status);
+/* cumulative number of kernels this library has launched in this process (for bench.py's gpu_launches) */
+void nngp_launch_count(double *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNGP_B200_H */

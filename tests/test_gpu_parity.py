@@ -1,0 +1,248 @@
+"""GPU parity tests: every call goes through the C ABI (libnngp_b200.so via ctypes) and is compared with the CPU oracle on
+the same seeded inputs.  Tolerances (FP64): deterministic kernels <= 1e-10 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import nngp_b200 as nb
+from oracle import oracle as O
+from problems import make_problem
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def rel_rows(a, b):
+    """max over rows of ||a_i - b_i|| / ||b_i||  (tolerance stated on the factor row)"""
+    num = np.linalg.norm(a - b, axis=1)
+    den = np.linalg.norm(b, axis=1)
+    return float(np.max(num / den))
+
+
+def rel_vec(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+CASES = [
+    ("exponential_isotropic", 2, 10, [1.0, 0.07, 0.0]),
+    ("exponential_isotropic", 2, 5, [1.0, 0.05, 0.0]),
+    ("exponential_isotropic", 3, 10, [1.0, 0.3, 0.0]),
+    ("exponential_isotropic", 2, 7, [1.0, 0.1, 0.0]),       # generic (non-specialised) M
+    ("exponential_isotropic", 2, 20, [1.0, 0.1, 0.0]),
+    ("exponential_scaledim", 2, 10, [1.0, 0.05, 0.11, 0.0]),
+    ("exponential_spacetime", 3, 10, [1.0, 0.2, 0.5, 0.0]),
+    ("matern_isotropic", 2, 10, [1.0, 0.07, 0.75, 0.0]),
+    ("matern_isotropic", 2, 20, [1.0, 0.1, 0.6, 0.0]),
+    ("matern_scaledim", 2, 5, [1.0, 0.05, 0.11, 0.9, 0.0]),
+    ("matern_spacetime", 3, 5, [1.0, 0.2, 0.5, 0.55, 0.0]),
+]
+
+
+@pytest.mark.parametrize("covfun,d,m,cp", CASES)
+@pytest.mark.parametrize("layout", [nb.LAYOUT_COLOR, nb.LAYOUT_COLOR_MORTON])
+def test_factor_and_products(covfun, d, m, cp, layout):
+    P = make_problem(4000, m, d=d, seed=11)
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], covfun, layout=layout) as ctx:
+        assert ctx.factor_build(cp) == 0
+        Lg = ctx.factor_get()
+        Lo = O.vecchia_Linv(cp, covfun, P["locs"], P["NNarray"])
+        assert rel_rows(Lg, Lo) < TOL
+        assert np.all(Lg[P["NNarray"] == nb.NA_INT] == 0.0)
+        # precision_diag
+        assert rel_vec(ctx.precision_diag(), O.precision_diag(Lo, P["NNarray"])) < TOL
+        # log-likelihood, both entry points
+        z = P["field"] - 0.3
+        ll_o = O.ll_compressed_sparse_chol(Lo, z, P["NNarray"], 0.4)
+        ctx.field_set(P["field"])
+        assert abs(ctx.loglik(0.3, 0.4) - ll_o) < TOL * abs(ll_o)
+        assert abs(ctx.loglik_host(z, 0.4) - ll_o) < TOL * abs(ll_o)
+        # products and the triangular solve
+        v = P["rng"].standard_normal(P["n"])
+        assert rel_vec(ctx.spmv(v), O.Linv_mult(Lo, v, P["NNarray"])) < TOL
+        assert rel_vec(ctx.sptmv(v), O.sparse_chol_tmult(Lo, P["NNarray"], v)) < TOL
+        assert rel_vec(ctx.sptrsv(v), O.sparse_chol_solve(Lo, P["NNarray"], v)) < 1e-9   # conditioning of the solve
+
+
+def test_sphere_factor():
+    rng = np.random.default_rng(3)
+    n, m = 3000, 5
+    lonlat = np.column_stack([rng.uniform(-120, -70, n), rng.uniform(25, 50, n)])
+    P = make_problem(n, m, locs=lonlat, seed=3)
+    for covfun, cp in (("exponential_sphere", [1.0, 0.05, 0.0]), ("matern_sphere", [1.0, 0.05, 0.8, 0.0])):
+        with nb.NNGPContext(lonlat, P["NNarray"], P["coloring"], P["locs_match"], covfun) as ctx:
+            assert ctx.factor_build(cp) == 0
+            assert rel_rows(ctx.factor_get(), O.vecchia_Linv(cp, covfun, lonlat, P["NNarray"])) < 1e-9
+
+
+@pytest.mark.parametrize("n,m", [(1, 3), (5, 10), (12, 10), (40, 1), (1000, 10)])
+def test_small_and_ragged(n, m):
+    """n <= m: every row is partial (NA-padded)."""
+    P = make_problem(n, m, seed=n)
+    cp = [1.0, 0.2, 0.0]
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        assert ctx.factor_build(cp) == 0
+        Lo = O.vecchia_Linv(cp, "exponential_isotropic", P["locs"], P["NNarray"])
+        assert rel_rows(ctx.factor_get(), Lo) < TOL
+        v = P["rng"].standard_normal(n)
+        assert rel_vec(ctx.sptrsv(v), O.sparse_chol_solve(Lo, P["NNarray"], v)) < 1e-9
+        ctx.field_set(P["field"])
+        ll_o = O.ll_compressed_sparse_chol(Lo, P["field"] - 0.1, P["NNarray"], -0.2)
+        assert abs(ctx.loglik(0.1, -0.2) - ll_o) < TOL * max(1.0, abs(ll_o))
+
+
+def test_not_positive_definite_is_flagged_not_fatal():
+    P = make_problem(500, 5, seed=5)
+    locs = P["locs"].copy()
+    locs[300] = locs[P["NNarray"][300, 1] - 1]          # duplicate a neighbour -> singular block
+    with nb.NNGPContext(locs, P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        assert ctx.factor_build([1.0, 0.2, 0.0]) >= 1
+
+
+@pytest.mark.parametrize("layout", [nb.LAYOUT_COLOR, nb.LAYOUT_COLOR_MORTON])
+@pytest.mark.parametrize("m,n_extra,drop", [(10, 0, 0.0), (5, 300, 0.0), (10, 200, 0.3)])
+def test_chromatic_sweep_supplied_normals(layout, m, n_extra, drop):
+    """Same normals in the reference's hand-out order => same field as update_Gaussian.R:257-275 written literally."""
+    P = make_problem(3000, m, seed=21, n_extra_obs=n_extra, drop_obs_frac=drop)
+    cp = [1.0, 0.08, 0.0]
+    beta_0, ls, lnv = 0.3, 0.2, -1.1
+    Lo = O.vecchia_Linv(cp, "exponential_isotropic", P["locs"], P["NNarray"])
+    pd = O.precision_diag(Lo, P["NNarray"])
+    mu = np.full(P["n_obs"], beta_0)
+    n_sweeps = 3
+    z = P["rng"].standard_normal(n_sweeps * P["n"])
+    f = P["field"].copy()
+    for s in range(n_sweeps):
+        rs = O.residuals_sum(P["locs_match"], P["n"], P["y"], mu)
+        f = O.chromatic_sweep(Lo, P["NNarray"], P["coloring"], pd, P["obs_per_loc"], rs, beta_0, ls, lnv,
+                              z[s * P["n"]:(s + 1) * P["n"]], f, form="reference")
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], layout=layout) as ctx:
+        ctx.factor_build(cp)
+        ctx.factor_commit()
+        ctx.field_set(P["field"])
+        ctx.obs_set(P["y"])
+        ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=n_sweeps, z=z)
+        assert rel_vec(ctx.field_get(), f) < TOL
+        assert abs(ctx.ssr() - O.ssr(P["locs_match"], P["y"], f, mu, beta_0)) < TOL * P["n_obs"]
+
+
+def test_philox_sweep_is_stationary_for_the_exact_conditional():
+    """many Philox sweeps on a tiny model reproduce the posterior mean and covariance
+    (Q/s2 + D/t2)^-1 -- a distributional check of the on-device generator and of the sweep."""
+    n, m = 30, 4
+    P = make_problem(n, m, seed=2)
+    cp = [1.0, 0.5, 0.0]
+    beta_0, ls, lnv = 0.0, 0.1, -0.5
+    Lo = O.vecchia_Linv(cp, "exponential_isotropic", P["locs"], P["NNarray"])
+    A = np.zeros((n, n))
+    for i in range(n):
+        for j in range(m + 1):
+            if P["NNarray"][i, j] != nb.NA_INT:
+                A[i, P["NNarray"][i, j] - 1] = Lo[i, j]
+    prec = A.T @ A * np.exp(-ls) + np.diag(P["obs_per_loc"]) * np.exp(-lnv)
+    cov = np.linalg.inv(prec)
+    mean = cov @ (np.exp(-lnv) * np.bincount(P["locs_match"] - 1, weights=P["y"], minlength=n))
+    n_samp = 20000
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.factor_build(cp)
+        ctx.factor_commit()
+        ctx.field_set(np.zeros(n))
+        ctx.obs_set(P["y"])
+        ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=200, seed=7)
+        S = np.empty((n_samp, n))
+        for k in range(n_samp):
+            ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=1, seed=7)
+            S[k] = ctx.field_get()
+    sd = np.sqrt(np.diag(cov))
+    assert np.max(np.abs(S.mean(0) - mean) / sd) < 0.08
+    emp = np.cov(S.T)
+    assert np.max(np.abs(emp - cov)) / np.max(np.abs(cov)) < 0.08
+
+
+def test_ancillary_beta0_and_field_init():
+    P = make_problem(3000, 10, seed=31, n_extra_obs=100)
+    cp_cur, cp_new = [1.0, 0.08, 0.0], [1.0, 0.09, 0.0]
+    beta_0, ls, dls, lnv = 0.3, 0.2, 0.05, -1.0
+    Lc = O.vecchia_Linv(cp_cur, "exponential_isotropic", P["locs"], P["NNarray"])
+    Ln = O.vecchia_Linv(cp_new, "exponential_isotropic", P["locs"], P["NNarray"])
+    mu = np.full(P["n_obs"], beta_0)
+    new_field = beta_0 + np.exp(0.5 * dls) * O.sparse_chol_solve(Ln, P["NNarray"], O.Linv_mult(Lc, P["field"] - beta_0, P["NNarray"]))
+    ratio_o = (O.obs_loglik(P["locs_match"], P["y"], new_field, mu, beta_0, lnv)
+               - O.obs_loglik(P["locs_match"], P["y"], P["field"], mu, beta_0, lnv))
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.factor_build(cp_cur, nb.SLOT_CURRENT)
+        ctx.factor_build(cp_new, nb.SLOT_PROPOSAL)
+        ctx.field_set(P["field"])
+        ctx.obs_set(P["y"])
+        ratio = ctx.ancillary_propose(beta_0, dls, lnv)
+        assert abs(ratio - ratio_o) < 1e-9 * max(1.0, abs(ratio_o))
+        bm, bv = ctx.beta0_moments(ls)
+        bm_o, bv_o = O.beta0_moments(Lc, P["NNarray"], P["field"], ls)
+        assert abs(bm - bm_o) < TOL * max(1, abs(bm_o)) and abs(bv - bv_o) < TOL * bv_o
+        ctx.ancillary_accept()
+        assert rel_vec(ctx.field_get(), new_field) < 1e-9
+        assert rel_rows(ctx.factor_get(nb.SLOT_CURRENT), Ln) < TOL          # proposal became current
+        assert rel_vec(ctx.precision_diag(), O.precision_diag(Ln, P["NNarray"])) < TOL
+        z = P["rng"].standard_normal(P["n"])
+        ctx.field_init(0.7, 0.3, z)
+        want = 0.7 + np.sqrt(np.exp(0.3)) * O.sparse_chol_solve(Ln, P["NNarray"], z)
+        assert rel_vec(ctx.field_get(), want) < 1e-9
+
+
+def test_predict_sample():
+    n, n_pred, m = 1500, 700, 10
+    rng = np.random.default_rng(8)
+    locs = rng.random((n + n_pred, 2))
+    nn = nb.find_ordered_nn(locs, m)
+    cp = [1.0, 0.2, 0.0]
+    Lo = O.vecchia_Linv(cp, "exponential_isotropic", locs, nn)
+    field = 0.3 + rng.standard_normal(n)
+    z = rng.standard_normal(n_pred)
+    want = O.predict_field_sample(Lo, nn, n, field, 0.3, 0.5, z)
+    with nb.NNGPContext(locs, nn, np.ones(n + n_pred, dtype=np.int32), np.zeros(0, dtype=np.int32)) as ctx:
+        ctx.factor_build(cp)
+        got = ctx.predict_sample(n, field, 0.3, 0.5, z)
+    assert rel_vec(got, want) < 1e-9
+
+
+@pytest.mark.parametrize("covfun,shape", [("exponential_isotropic", [np.log(0.1)]), ("matern_isotropic", [np.log(0.1), 0.3])])
+def test_chain_run_matches_oracle_chain_with_r_stream(covfun, shape):
+    """nngp_chain_run in NNGP_RNG_SUPPLIED mode consumes R's stream (set.seed(iter_start + i)) exactly like
+    update_Gaussian.R:34-315; the oracle chain does the same on the CPU."""
+    n, m = 1200, 5
+    P = make_problem(n, m, seed=41)
+    cp = [1.0, 0.1, 0.0] if covfun.startswith("exp") else [1.0, 0.1, 0.7, 0.0]
+    L0 = O.vecchia_Linv(cp, covfun, P["locs"], P["NNarray"])
+    w = O.sparse_chol_solve(L0, P["NNarray"], P["rng"].standard_normal(n))
+    y = 1.0 + w + np.sqrt(0.1) * P["rng"].standard_normal(n)
+    lm = np.arange(1, n + 1, dtype=np.int32)
+    p0 = dict(shape=shape, beta_0=0.9, log_scale=0.1, log_noise_variance=np.log(0.2))
+    n_iter = 50
+    po, fo, reco, freco, acco = O.update_gaussian_chain(P["locs"], P["NNarray"], P["coloring"], lm, np.ones(n), y, covfun,
+                                                        p0, 0.9 + w, n_iter, 0.5, 2, 0, 1, 0)
+    var_y = np.var(y, ddof=1)
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], lm, covfun) as ctx:
+        ctx.field_set(0.9 + w)
+        ctx.obs_set(y)
+        pg, recg, frecg, accg = ctx.chain_run(p0, n_iter, var_y, thin=0.5, n_chromatic=2, iter_start=0, chain_index=1,
+                                              rng_mode=nb.RNG_SUPPLIED)
+        fg = ctx.field_get()
+    assert np.array_equal(accg, acco)                         # same accept/reject decisions
+    assert np.max(np.abs(recg - reco)) < 1e-8
+    assert np.max(np.abs(fg - fo)) < 1e-7
+    assert np.max(np.abs(frecg - freco)) < 1e-7
+    assert abs(pg["logvar_ancillary"] - po["logvar_ancillary"]) < 1e-12
+
+
+def test_error_paths():
+    P = make_problem(200, 5, seed=1)
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        with pytest.raises(nb.NNGPError) as e:
+            ctx.loglik(0.0, 0.0)                                # no factor yet
+        assert e.value.status == 4
+        with pytest.raises(nb.NNGPError) as e:
+            ctx.factor_build([1.0, 0.1, 0.2, 0.0])              # wrong covparms length
+        assert e.value.status == 1
+    bad = P["NNarray"].copy()
+    bad[10, 1] = 50                                              # a "neighbour" that is not a previous site
+    with pytest.raises(nb.NNGPError):
+        nb.NNGPContext(P["locs"], bad, P["coloring"], P["locs_match"])
