@@ -53,19 +53,31 @@ def test_transpose_consistency(big):
         assert abs(np.dot(col, col) - pd[s]) < 1e-10 * pd[s]
 
 
-def test_zero_noise_sweeps_reach_the_posterior_mean(big):
-    """With z = 0 the chromatic sweep is coloured Gauss-Seidel on (Q/s2 + D/t2) w = D(y - beta_0)/t2: the fixed point must
-    satisfy that linear system (checked with the independent spmv / sptmv kernels)."""
+def test_one_sweep_equals_the_reference_colour_loop_built_from_independent_kernels(big):
+    """Full-size restatement of update_Gaussian.R:257-275 with the library's own spmv / sptmv kernels (which the sweep kernel
+    does not use): colour by colour, Q (w * 1[colour != c]) restricted to colour c gives the conditional mean; the sweep
+    kernel (residual-maintained form) must land on the same field given the same normals."""
     P, ctx = big
+    n = P["n"]
     beta_0, ls, lnv = 0.3, 0.0, np.log(0.1)
+    z = P["rng"].standard_normal(n)
     ctx.field_set(P["field"])
-    zeros = np.zeros(P["n"])
-    for _ in range(60):
-        ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=1, z=zeros)
-    w = ctx.field_get() - beta_0
-    lhs = np.exp(-ls) * ctx.sptmv(ctx.spmv(w)) + np.exp(-lnv) * P["obs_per_loc"] * w
-    rhs = np.exp(-lnv) * np.bincount(P["locs_match"] - 1, weights=P["y"] - beta_0, minlength=P["n"])
-    assert np.max(np.abs(lhs - rhs)) < 1e-6 * np.max(np.abs(rhs))
+    ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=1, z=z)
+    got = ctx.field_get()
+    pd = ctx.precision_diag()
+    col = P["coloring"]
+    rs = np.bincount(P["locs_match"] - 1, weights=P["y"] - beta_0, minlength=n)
+    f = P["field"].copy()
+    zi = 0
+    for c in range(1, int(col.max()) + 1):
+        sel = np.where(col == c)[0]
+        v = (f - beta_0) * (col != c)
+        t = ctx.sptmv(ctx.spmv(v))[sel]
+        prec = np.exp(-ls) * pd[sel] + np.exp(-lnv) * P["obs_per_loc"][sel]
+        mean = beta_0 - (t * np.exp(-ls) - np.exp(-lnv) * rs[sel]) / prec
+        f[sel] = mean + z[zi:zi + sel.size] / np.sqrt(prec)
+        zi += sel.size
+    assert np.max(np.abs(got - f)) < 1e-9 * np.max(np.abs(f))
 
 
 def test_philox_sweep_is_deterministic_in_seed_and_counter(big):
