@@ -63,6 +63,11 @@ class NNGPContext:
         getattr(L.load(), name)(L.ci(self._id), *args, C.byref(st))
         L.check(st)
 
+    OPTIONS = {"sweep_variant": 1, "solve_variant": 2, "use_graph": 3}
+
+    def set_option(self, name: str, value: int):
+        self._call("nngp_ctx_set_option", L.ci(self.OPTIONS[name]), L.ci(value))
+
     # ---- factor
     def factor_build(self, covparms, slot=L.SLOT_CURRENT) -> int:
         cp = L.f64(covparms)

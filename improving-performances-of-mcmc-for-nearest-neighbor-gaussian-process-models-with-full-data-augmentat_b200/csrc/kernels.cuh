@@ -364,6 +364,70 @@ __global__ void __launch_bounds__(1024) sptrsv_multilevel_kernel(const int *__re
     }
 }
 
+// Synchronisation-free variant (the production path): ONE launch for the whole DAG.  Threads are laid out in level order
+// (each level padded to a multiple of 32 so that a warp never holds both a row and one of its ancestors); the solution
+// vector doubles as the ready flag: it is pre-filled with a NaN payload that arithmetic never produces, and a thread polls
+// its parents in L2 (ld.relaxed.gpu) until their value has been published (st.relaxed.gpu).  Dependencies only point to
+// threads with a smaller logical index, and logical CTA indices are handed out by an atomic ticket at CTA start, so every
+// CTA a thread can wait on has already started: no deadlock even when the grid exceeds residency.  All index / coefficient
+// loads of all levels are in flight at once; only the chain of x dependencies (DAG depth ~200 L2 round trips) serialises.
+#define NNGP_SOLVE_SENTINEL 0xFFF8DEADBEEF0001ull
+
+__global__ void fill_u64_kernel(unsigned long long *__restrict__ dst, unsigned long long v, int n) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) dst[t] = v;
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int MT>
+__global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
+                                                              const int *__restrict__ rows_padded, int n_slots,
+                                                              const double *__restrict__ b, unsigned long long *x,
+                                                              double *__restrict__ y, double shift, double scale, int ld, int M,
+                                                              int *ticket, int *err) {
+    __shared__ int s_bid;
+    if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int t = s_bid * blockDim.x + threadIdx.x;
+    if (t >= n_slots) return;
+    const int q = rows_padded[t];
+    if (q < 0) return;
+    constexpr int MC = MT > 0 ? MT : 32;
+    int idx[MC];
+    double a[MC];
+    const int Mr = MT > 0 ? MT : M;
+#pragma unroll
+    for (int j = 0; j < MC; j++) {
+        if (j < Mr) {
+            idx[j] = nn[(size_t)j * ld + q];
+            a[j] = linv[(size_t)j * ld + q];
+        }
+    }
+    double s = b[q];
+#pragma unroll
+    for (int j = 1; j < MC; j++) {
+        if (j < Mr && idx[j] >= 0) {
+            unsigned long long bits = ld_relaxed_gpu_u64(x + idx[j]);
+            unsigned int spins = 0;
+            while (bits == NNGP_SOLVE_SENTINEL) {
+                if (++spins > (1u << 26)) { atomicExch(err, 1); break; }   // never hang the device on a corrupted structure
+                bits = ld_relaxed_gpu_u64(x + idx[j]);
+            }
+            s -= a[j] * __longlong_as_double((long long)bits);
+        }
+    }
+    const double xv = s / a[0];
+    st_relaxed_gpu_u64(x + q, (unsigned long long)__double_as_longlong(xv));
+    if (y) y[q] = shift + scale * xv;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // observation-side kernels (gathers through locs_match)
 // ---------------------------------------------------------------------------------------------------------------
@@ -430,6 +494,95 @@ __global__ void __launch_bounds__(256) gibbs_color_kernel(const int *__restrict_
     const double delta = (f_new - sp.beta0) - w_old;
     for (int k = k0; k < k1; k++) r[crow[k]] += valT[k] * delta;
     field[q] = f_new;
+}
+
+// Tiled variant (the production path).  A CTA owns a tile = a run of consecutive same-colour sites whose CSC entries
+// [e0, e1) are contiguous; the host packs tiles with <= THREADS sites and <= THREADS*EPT entries.
+//   phase 1: every thread loads EPT entries of the flat entry stream (val, row: fully coalesced), gathers r[row] and leaves
+//            val*r in shared memory;  val / row / r stay in registers
+//   phase 2: one thread per site sums its segment of shared memory, draws the site, overwrites the segment with delta
+//   phase 3: every thread scatters r[row] = r_old + val*delta for the entries it still holds (no second read of r)
+// Compared with the thread-per-site form this turns 2x(m+1) strided loads per site into coalesced 128/256 B transactions
+// and halves the traffic on r.
+template <int THREADS, int EPT>
+__global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ colptr,
+                                                             const int *__restrict__ crow, const double *__restrict__ valT,
+                                                             const double *__restrict__ pd, const double *__restrict__ nobs,
+                                                             const double *__restrict__ S, const int *__restrict__ zpos,
+                                                             const int *__restrict__ gid, const double *__restrict__ zbuf,
+                                                             const SweepParams *__restrict__ spp, double *__restrict__ field,
+                                                             double *__restrict__ r) {
+    constexpr int ECAP = THREADS * EPT;
+    __shared__ double sprod[ECAP];
+    __shared__ double sbc[2];
+    const int tid = threadIdx.x;
+    const int2 tile = tiles[blockIdx.x];
+    const int s0 = tile.x, s1 = tile.y;
+    const int e0 = colptr[s0], e1 = colptr[s1];
+    const SweepParams sp = *spp;
+    if (e1 - e0 > ECAP) {
+        // a single site whose column does not fit the tile (pathological fan-out): whole-CTA reduction
+        const int q = s0;
+        double acc[1] = {0.0};
+        for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * r[crow[e]];
+        block_reduce_sum<1>(acc);
+        if (tid == 0) {
+            const double w_old = field[q] - sp.beta0;
+            const double Qss = pd[q], no = nobs[q];
+            const double prec = sp.e_ls * Qss + sp.e_ln * no;
+            const double t = acc[0] - Qss * w_old;
+            const double resid = S[q] - no * sp.beta0;
+            const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
+            const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
+            sbc[0] = (f_new - sp.beta0) - w_old;
+            field[q] = f_new;
+        }
+        __syncthreads();
+        const double delta = sbc[0];
+        for (int e = e0 + tid; e < e1; e += THREADS) r[crow[e]] += valT[e] * delta;
+        return;
+    }
+    double val[EPT], rr[EPT];
+    int row[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        const int e = e0 + k * THREADS + tid;
+        if (e < e1) {
+            val[k] = valT[e];
+            row[k] = crow[e];
+        } else {
+            val[k] = 0.0;
+            row[k] = -1;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        if (row[k] >= 0) {
+            rr[k] = r[row[k]];
+            sprod[k * THREADS + tid] = val[k] * rr[k];
+        }
+    }
+    __syncthreads();
+    if (tid < s1 - s0) {
+        const int q = s0 + tid;
+        const int k0 = colptr[q] - e0, k1 = colptr[q + 1] - e0;
+        double a = 0.0;
+        for (int k = k0; k < k1; k++) a += sprod[k];
+        const double w_old = field[q] - sp.beta0;
+        const double Qss = pd[q], no = nobs[q];
+        const double prec = sp.e_ls * Qss + sp.e_ln * no;
+        const double t = a - Qss * w_old;
+        const double resid = S[q] - no * sp.beta0;
+        const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
+        const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
+        const double delta = (f_new - sp.beta0) - w_old;
+        for (int k = k0; k < k1; k++) sprod[k] = delta;
+        field[q] = f_new;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) r[row[k]] = rr[k] + val[k] * sprod[k * THREADS + tid];
 }
 
 // tail of the colour sequence: colours [c0, c1) are small; one CTA walks them with a block barrier in between

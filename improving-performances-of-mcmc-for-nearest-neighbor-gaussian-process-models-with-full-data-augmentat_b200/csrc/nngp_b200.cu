@@ -94,6 +94,12 @@ struct Ctx {
     struct Seg { int l0, l1; bool single_block; };
     std::vector<Seg> solve_plan;
     int tail_color = 0;  // colours [tail_color, K) are walked by one CTA
+    // tiles of the sweep: cfg 0 = 256 threads x 8 entries, cfg 1 = 128 threads x 8 entries
+    std::vector<int> tile_ptr[2];          // per colour, into d_tiles[cfg]
+    std::vector<int> color_cfg;            // chosen cfg per colour
+    int sweep_variant = 0;                 // 0 auto tiles, 1 force cfg 0, 2 force cfg 1, 3 thread-per-site kernel
+    int solve_variant = 0;                 // 0 sync-free single launch, 1 level-scheduled launches
+    int n_slots = 0;                       // padded length of the level-ordered row list
 
     // device structure
     DevBuf<int> d_i2g, d_g2i, d_nn, d_colptr, d_crow, d_csrc, d_zpos, d_lvl_rows, d_lvl_ptr, d_lm, d_optr, d_oidx, d_cstart,
@@ -101,6 +107,8 @@ struct Ctx {
     DevBuf<double> d_locs, d_tl, d_linv[2], d_valT, d_pd, d_nobs, d_ymx, d_S, d_field, d_newfield, d_r, d_tmp1, d_tmp2, d_io,
         d_zbuf, d_partials, d_scalars, d_flush;
     DevBuf<SweepParams> d_sp;
+    DevBuf<int2> d_tiles[2];
+    DevBuf<int> d_rows_padded, d_ticket;
     double *h_pinned = nullptr;       // 64 doubles of pinned scratch for scalar results
     double *h_stage = nullptr;        // pinned staging for vectors (n doubles at least)
     size_t h_stage_n = 0;
@@ -248,7 +256,7 @@ static void launch_factor(Ctx *c, double *linv, const CovConst &cc) {
 }
 
 static void op_factor_build(Ctx *c, int slot, const CovConst &cc) {
-    CK(cudaMemsetAsync(c->d_nbad.p, 0, sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->d_nbad.p, 0, 2 * sizeof(int), c->stream));
     transform_locs_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_locs.p, c->d_tl.p, c->n, cc);
     LAUNCHED(c);
     double *linv = c->linv_slot(slot);
@@ -285,6 +293,15 @@ static void op_spmv(Ctx *c, const double *linv, const double *v, double shift, d
 
 // x = solve(linv, b); optional y = shift + scale * x
 static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, double *y, double shift, double scale) {
+    if (c->solve_variant == 0) {
+        CK(cudaMemsetAsync(c->d_ticket.p, 0, sizeof(int), c->stream));
+        fill_u64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(reinterpret_cast<unsigned long long *>(x), NNGP_SOLVE_SENTINEL, c->n);
+        LAUNCHED(c);
+        const int blocks = (c->n_slots + 255) / 256;
+        DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1)));
+        LAUNCHED(c);
+        return;
+    }
     for (const auto &s : c->solve_plan) {
         if (s.single_block) {
             sptrsv_multilevel_kernel<<<1, 1024, 0, c->stream>>>(c->d_nn.p, linv, c->d_lvl_rows.p, c->d_lvl_ptr.p, s.l0, s.l1, b, x, y, shift, scale, c->ld, c->M);
@@ -305,7 +322,16 @@ static void op_commit(Ctx *c) {
 static void launch_sweep_colors(Ctx *c) {
     for (int col = 0; col < c->tail_color; col++) {
         const int q0 = c->cstart[col], q1 = c->cstart[col + 1];
-        gibbs_color_kernel<<<(q1 - q0 + 255) / 256, 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, q0, q1);
+        if (c->sweep_variant == 3) {
+            gibbs_color_kernel<<<(q1 - q0 + 255) / 256, 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, q0, q1);
+            continue;
+        }
+        const int cfg = c->sweep_variant == 1 ? 0 : (c->sweep_variant == 2 ? 1 : c->color_cfg[col]);
+        const int t0 = c->tile_ptr[cfg][col], nt = c->tile_ptr[cfg][col + 1] - t0;
+        if (cfg == 0)
+            gibbs_tile_kernel<256, 8><<<nt, 256, 0, c->stream>>>(c->d_tiles[0].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
+        else
+            gibbs_tile_kernel<128, 8><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
     }
     if (c->tail_color < c->K)
         gibbs_tail_kernel<<<1, 1024, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, c->d_cstart.p, c->tail_color, c->K);
@@ -354,6 +380,15 @@ static void fetch_scalars(Ctx *c, int count) {
     CK(cudaStreamSynchronize(c->stream));
 }
 
+// the sync-free solve raises a device flag instead of spinning forever on a corrupted structure
+static void check_solve_flag(Ctx *c) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(c->h_pinned + 9, c->d_nbad.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::memcpy(&flag, c->h_pinned + 9, sizeof(int));
+    if (flag) { set_error("triangular solve: dependency wait timed out (corrupted neighbour structure?)"); throw CudaFail(); }
+}
+
 static double ll_from_sums(Ctx *c, double sum_log, double sum_sq, double log_scale) {
     return sum_log - c->n * 0.5 * log_scale - 0.5 * sum_sq / std::exp(log_scale);
 }
@@ -400,6 +435,7 @@ static void destroy_ctx(Ctx *c) {
                             &c->d_scalars, &c->d_flush};
     for (auto *b : db) b->release();
     c->d_sp.release();
+    c->d_tiles[0].release(); c->d_tiles[1].release(); c->d_rows_padded.release(); c->d_ticket.release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -586,6 +622,35 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
             l++;
         }
     }
+    // level-ordered row list, every level padded to a warp multiple (sync-free solve)
+    std::vector<int> rows_padded;
+    rows_padded.reserve((size_t)n + 32 * (size_t)c->n_levels);
+    for (int l = 0; l < c->n_levels; l++) {
+        for (int t = c->lvl_ptr[l]; t < c->lvl_ptr[l + 1]; t++) rows_padded.push_back(lvl_rows[t]);
+        while (rows_padded.size() % 32) rows_padded.push_back(-1);
+    }
+    c->n_slots = (int)rows_padded.size();
+    // ---- sweep tiles: runs of consecutive same-colour sites with <= T sites and <= T*8 CSC entries ----
+    std::vector<int2> tiles[2];
+    const int tcfg_threads[2] = {256, 128};
+    for (int cfg = 0; cfg < 2; cfg++) {
+        const int T = tcfg_threads[cfg], ECAP = T * 8;
+        c->tile_ptr[cfg].assign(K + 1, 0);
+        for (int col = 0; col < K; col++) {
+            int s0 = c->cstart[col];
+            const int send = c->cstart[col + 1];
+            while (s0 < send) {
+                int s1 = s0 + 1;   // at least one site (an oversize column is handled inside the kernel)
+                while (s1 < send && s1 - s0 < T && colptr[s1 + 1] - colptr[s0] <= ECAP) s1++;
+                tiles[cfg].push_back(make_int2(s0, s1));
+                s0 = s1;
+            }
+            c->tile_ptr[cfg][col + 1] = (int)tiles[cfg].size();
+        }
+    }
+    c->color_cfg.assign(K, 0);
+    for (int col = 0; col < K; col++)
+        c->color_cfg[col] = (c->tile_ptr[0][col + 1] - c->tile_ptr[0][col] >= 2 * c->n_sm) ? 0 : 1;
     // ---- observations ----
     std::vector<int> lm(n_obs), optr(n + 1, 0), oidx(n_obs);
     for (int o = 0; o < n_obs; o++) {
@@ -606,7 +671,11 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
     c->d_lvl_ptr.upload(c->lvl_ptr, s); c->d_lm.upload(lm, s); c->d_optr.upload(optr, s); c->d_oidx.upload(oidx, s);
     c->d_cstart.upload(c->cstart, s); c->d_locs.upload(locs_int, s); c->d_nobs.upload(nobs, s);
     if (!c->partial_rows.empty()) c->d_partial_rows.upload(c->partial_rows, s);
-    c->d_nbad.alloc(1);
+    c->d_nbad.alloc(2);
+    CK(cudaMemsetAsync(c->d_nbad.p, 0, 2 * sizeof(int), s));
+    c->d_ticket.alloc(1);
+    c->d_rows_padded.upload(rows_padded, s);
+    for (int cfg = 0; cfg < 2; cfg++) c->d_tiles[cfg].upload(tiles[cfg], s);
     c->d_tl.alloc((size_t)n * c->dt);
     for (int k = 0; k < 2; k++) { c->d_linv[k].alloc((size_t)ld * M); CK(cudaMemsetAsync(c->d_linv[k].p, 0, sizeof(double) * ld * M, s)); }
     c->d_valT.alloc(c->nnz); c->d_pd.alloc(n); c->d_ymx.alloc(std::max(n_obs, 1)); c->d_S.alloc(n); c->d_field.alloc(n);
@@ -632,6 +701,22 @@ void nngp_ctx_destroy(const int *ctx_id, int *status) {
     Ctx *c = get_ctx(ctx_id);
     { std::lock_guard<std::mutex> lk(g_ctx_mu); g_ctx[*ctx_id] = nullptr; }
     destroy_ctx(c);
+    ABI_END
+}
+
+void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(key && value, "nngp_ctx_set_option: null argument");
+    use(c);
+    CK(cudaStreamSynchronize(c->stream));
+    switch (*key) {
+        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 3, "sweep variant must be 0..3"); c->sweep_variant = *value; break;
+        case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
+        case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
+        default: REQUIRE(false, "unknown option key %d", *key);
+    }
+    if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; }
     ABI_END
 }
 
@@ -807,6 +892,7 @@ void nngp_sptrsv(const int *ctx_id, const int *slot, const double *b, double *x,
     op_sptrsv(c, c->linv_slot(*slot), c->d_tmp1.p, c->d_tmp2.p, nullptr, 0.0, 1.0);
     CK(cudaGetLastError());
     download_site_vector(c, c->d_tmp2.p, x);
+    check_solve_flag(c);
     ABI_END
 }
 
@@ -847,6 +933,7 @@ void nngp_ancillary_propose(const int *ctx_id, const double *beta_0, const doubl
     op_obs_sq(c, c->d_newfield.p, c->d_field.p, 0);
     CK(cudaGetLastError());
     fetch_scalars(c, 2);
+    check_solve_flag(c);
     // sum(dnorm(y, new) - dnorm(y, old)) = -(SSR_new - SSR_old) / (2 tau^2)
     *field_response_ratio = -0.5 * (c->h_pinned[0] - c->h_pinned[1]) * std::exp(-*log_noise_variance);
     c->have_newfield = true;
@@ -901,7 +988,7 @@ void nngp_field_init(const int *ctx_id, const int *slot, const double *beta_0, c
     upload_site_vector(c, z, c->d_tmp1.p);
     op_sptrsv(c, c->linv_slot(*slot), c->d_tmp1.p, c->d_tmp2.p, c->d_field.p, *beta_0, std::sqrt(std::exp(*log_scale)));
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));
+    check_solve_flag(c);
     c->have_field = true;
     ABI_END
 }

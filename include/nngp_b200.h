@@ -87,6 +87,15 @@ void nngp_ctx_create(const int *n, const int *d, const int *m, const double *loc
                      const int *coloring, const int *n_obs, const int *locs_match, const int *covfun_id,
                      const int *device, const int *layout, int *ctx_id, int *status);
 void nngp_ctx_destroy(const int *ctx_id, int *status);
+/* performance knobs (results are identical up to FP64 summation order):
+ *   NNGP_OPT_SWEEP_VARIANT 0 = tiled kernel, tile shape chosen per colour; 1 = 256x8 tiles; 2 = 128x8 tiles;
+ *                          3 = thread-per-site kernel
+ *   NNGP_OPT_SOLVE_VARIANT 0 = synchronisation-free single-launch triangular solve; 1 = one launch per DAG level
+ *   NNGP_OPT_USE_GRAPH     1 = the colour launches of a sweep are replayed from a captured CUDA graph (default) */
+#define NNGP_OPT_SWEEP_VARIANT 1
+#define NNGP_OPT_SOLVE_VARIANT 2
+#define NNGP_OPT_USE_GRAPH 3
+void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);
 /* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,
  * [6]=device, [7]=layout */
 void nngp_ctx_info(const int *ctx_id, int *info8, int *status);
