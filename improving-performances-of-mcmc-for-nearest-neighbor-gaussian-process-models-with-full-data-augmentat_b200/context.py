@@ -63,7 +63,7 @@ class NNGPContext:
         getattr(L.load(), name)(L.ci(self._id), *args, C.byref(st))
         L.check(st)
 
-    OPTIONS = {"sweep_variant": 1, "solve_variant": 2, "use_graph": 3}
+    OPTIONS = {"sweep_variant": 1, "solve_variant": 2, "use_graph": 3, "solve_ctas_per_sm": 4, "solve_sleep_ns": 5, "debug_timeline": 6, "solve_window_ctas": 7}
 
     def set_option(self, name: str, value: int):
         self._call("nngp_ctx_set_option", L.ci(self.OPTIONS[name]), L.ci(value))
@@ -206,6 +206,15 @@ class NNGPContext:
         nl = C.c_int(0)
         self._call("nngp_time_op", L.ci(self.OPS[op]), L.ci(reps), L.ci(1 if flush_l2 else 0), L.dptr(ms), C.byref(nl))
         return ms, nl.value
+
+
+def debug_timeline():
+    """(time_ns, stage) stamps of CTA 0 from the last persistent sweep launch (development aid)."""
+    out = np.zeros(2 * 8190)
+    nw, st = C.c_int(0), C.c_int(0)
+    L.load().nngp_debug_timeline(L.dptr(out), L.ci(out.size), C.byref(nw), C.byref(st))
+    L.check(st)
+    return out[: 2 * nw.value].reshape(-1, 2)
 
 
 # ---- host set-up utilities (init-time code of the reference)

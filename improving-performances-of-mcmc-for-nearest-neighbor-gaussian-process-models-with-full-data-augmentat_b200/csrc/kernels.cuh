@@ -391,41 +391,59 @@ __global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restr
                                                               const int *__restrict__ rows_padded, int n_slots,
                                                               const double *__restrict__ b, unsigned long long *x,
                                                               double *__restrict__ y, double shift, double scale, int ld, int M,
-                                                              int *ticket, int *err) {
-    __shared__ int s_bid;
-    if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1);
-    __syncthreads();
-    const int t = s_bid * blockDim.x + threadIdx.x;
-    if (t >= n_slots) return;
-    const int q = rows_padded[t];
-    if (q < 0) return;
+                                                              int *ticket, int *err, unsigned int sleep_ns) {
+    // The grid is a sliding window over the level-ordered rows: each CTA repeatedly takes the next chunk of 256 slots.  A
+    // bounded window (gridDim.x * 256 rows, a few DAG levels wide) keeps the number of polling threads -- and the L2 traffic
+    // they generate -- small; with one thread per row for the whole DAG in flight ncu showed 1.1 GB of DRAM reads and 3 ms.
+    __shared__ int s_chunk;
     constexpr int MC = MT > 0 ? MT : 32;
-    int idx[MC];
-    double a[MC];
     const int Mr = MT > 0 ? MT : M;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int base = s_chunk * (int)blockDim.x;
+        if (base >= n_slots) return;
+        const int t = base + threadIdx.x;
+        const int q = (t < n_slots) ? rows_padded[t] : -1;
+        if (q < 0) continue;
+        int idx[MC];
+        double a[MC];
 #pragma unroll
-    for (int j = 0; j < MC; j++) {
-        if (j < Mr) {
-            idx[j] = nn[(size_t)j * ld + q];
-            a[j] = linv[(size_t)j * ld + q];
-        }
-    }
-    double s = b[q];
-#pragma unroll
-    for (int j = 1; j < MC; j++) {
-        if (j < Mr && idx[j] >= 0) {
-            unsigned long long bits = ld_relaxed_gpu_u64(x + idx[j]);
-            unsigned int spins = 0;
-            while (bits == NNGP_SOLVE_SENTINEL) {
-                if (++spins > (1u << 26)) { atomicExch(err, 1); break; }   // never hang the device on a corrupted structure
-                bits = ld_relaxed_gpu_u64(x + idx[j]);
+        for (int j = 0; j < MC; j++) {
+            if (j < Mr) {
+                idx[j] = nn[(size_t)j * ld + q];
+                a[j] = linv[(size_t)j * ld + q];
             }
-            s -= a[j] * __longlong_as_double((long long)bits);
         }
+        double s = b[q];
+        // Poll ALL still-pending parents in every round: the loads of one round are independent and overlap, so a round
+        // costs one L2 round trip however many parents are outstanding (polling them one after the other cost up to m
+        // serial round trips per DAG level: 7 us per level measured, against a 0.38 us flag hop).
+        unsigned long long bits[MC];
+#pragma unroll
+        for (int j = 1; j < MC; j++) bits[j] = (j < Mr && idx[j] >= 0) ? NNGP_SOLVE_SENTINEL : 0ull;
+        unsigned int spins = 0;
+        bool pending = true;
+        while (pending) {
+#pragma unroll
+            for (int j = 1; j < MC; j++)
+                if (bits[j] == NNGP_SOLVE_SENTINEL) bits[j] = ld_relaxed_gpu_u64(x + idx[j]);
+            pending = false;
+#pragma unroll
+            for (int j = 1; j < MC; j++) pending = pending || (bits[j] == NNGP_SOLVE_SENTINEL);
+            if (pending) {
+                if (++spins > (1u << 22)) { atomicExch(err, 1); break; }   // never hang the device on a corrupted structure
+                if (sleep_ns) __nanosleep(sleep_ns);
+            }
+        }
+#pragma unroll
+        for (int j = 1; j < MC; j++)
+            if (j < Mr && idx[j] >= 0) s -= a[j] * __longlong_as_double((long long)bits[j]);
+        const double xv = s / a[0];
+        st_relaxed_gpu_u64(x + q, (unsigned long long)__double_as_longlong(xv));
+        if (y) y[q] = shift + scale * xv;
     }
-    const double xv = s / a[0];
-    st_relaxed_gpu_u64(x + q, (unsigned long long)__double_as_longlong(xv));
-    if (y) y[q] = shift + scale * xv;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -470,6 +488,40 @@ __device__ __forceinline__ double sweep_normal(const SweepParams &sp, const doub
     return philox_normal((uint32_t)gid[q], (uint32_t)sp.sweep_counter, (uint32_t)(sp.sweep_counter >> 32), sp.key0, sp.key1);
 }
 
+// r-independent part of one site's update, computed while the tile is staged (i.e. off the critical path):
+//   f_new = c0 - c1 * a,  a = sum_k valT[k] r[crow[k]]   with
+//   c1 = e_ls / prec,  c0 = beta0 + (Qss w_old e_ls + e_ln resid) / prec + z / sqrt(prec)
+// (algebraically identical to update_Gaussian.R:264-273; differs from the literal order of operations by FP64 rounding)
+struct SiteConst { double c0, c1, f_old; };
+
+// sum of a contiguous shared-memory segment with four independent accumulators: the per-site loop is a chain of dependent
+// LDS (29 cycles) + DADD; at a column length of 30-40 (the longest lane of a warp sets the pace) the plain loop cost 1.4 us
+// per tile in the %globaltimer timeline of the persistent kernel
+__device__ __forceinline__ double segment_sum(const double *__restrict__ sh, int k0, int k1) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+        a0 += sh[k];
+        a1 += sh[k + 1];
+        a2 += sh[k + 2];
+        a3 += sh[k + 3];
+    }
+    for (; k < k1; k++) a0 += sh[k];
+    return (a0 + a1) + (a2 + a3);
+}
+
+__device__ __forceinline__ SiteConst site_const(const SweepParams &sp, double f_old, double Qss, double no, double Sq, double z) {
+    SiteConst sc;
+    const double w_old = f_old - sp.beta0;
+    const double prec = sp.e_ls * Qss + sp.e_ln * no;
+    const double inv = 1.0 / prec;
+    const double resid = Sq - no * sp.beta0;
+    sc.c1 = sp.e_ls * inv;
+    sc.c0 = sp.beta0 + (Qss * w_old * sp.e_ls + sp.e_ln * resid) * inv + z * sqrt(inv);
+    sc.f_old = f_old;
+    return sc;
+}
+
 __global__ void __launch_bounds__(256) gibbs_color_kernel(const int *__restrict__ colptr, const int *__restrict__ crow,
                                                           const double *__restrict__ valT, const double *__restrict__ pd,
                                                           const double *__restrict__ nobs, const double *__restrict__ S,
@@ -505,7 +557,7 @@ __global__ void __launch_bounds__(256) gibbs_color_kernel(const int *__restrict_
 // Compared with the thread-per-site form this turns 2x(m+1) strided loads per site into coalesced 128/256 B transactions
 // and halves the traffic on r.
 template <int THREADS, int EPT>
-__global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int2 *__restrict__ tiles, const int *__restrict__ colptr,
+__global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restrict__ tiles, const int *__restrict__ colptr,
                                                              const int *__restrict__ crow, const double *__restrict__ valT,
                                                              const double *__restrict__ pd, const double *__restrict__ nobs,
                                                              const double *__restrict__ S, const int *__restrict__ zpos,
@@ -516,9 +568,8 @@ __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int2 *__restr
     __shared__ double sprod[ECAP];
     __shared__ double sbc[2];
     const int tid = threadIdx.x;
-    const int2 tile = tiles[blockIdx.x];
-    const int s0 = tile.x, s1 = tile.y;
-    const int e0 = colptr[s0], e1 = colptr[s1];
+    const int4 tile = tiles[blockIdx.x];
+    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
     const SweepParams sp = *spp;
     if (e1 - e0 > ECAP) {
         // a single site whose column does not fit the tile (pathological fan-out): whole-CTA reduction
@@ -556,33 +607,263 @@ __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int2 *__restr
         }
     }
 #pragma unroll
-    for (int k = 0; k < EPT; k++) {
-        if (row[k] >= 0) {
-            rr[k] = r[row[k]];
-            sprod[k * THREADS + tid] = val[k] * rr[k];
-        }
-    }
-    __syncthreads();
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) rr[k] = r[row[k]];
+    // r-independent part of the site update (Philox + Box-Muller, 1/prec, sqrt): overlaps with the gathers in flight
+    int k0 = 0, k1 = 0;
+    SiteConst sc{0.0, 0.0, 0.0};
     if (tid < s1 - s0) {
         const int q = s0 + tid;
-        const int k0 = colptr[q] - e0, k1 = colptr[q + 1] - e0;
-        double a = 0.0;
-        for (int k = k0; k < k1; k++) a += sprod[k];
-        const double w_old = field[q] - sp.beta0;
-        const double Qss = pd[q], no = nobs[q];
-        const double prec = sp.e_ls * Qss + sp.e_ln * no;
-        const double t = a - Qss * w_old;
-        const double resid = S[q] - no * sp.beta0;
-        const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
-        const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
-        const double delta = (f_new - sp.beta0) - w_old;
+        k0 = colptr[q] - e0;
+        k1 = colptr[q + 1] - e0;
+        sc = site_const(sp, field[q], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
+    }
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) sprod[k * THREADS + tid] = val[k] * rr[k];
+    __syncthreads();
+    if (tid < s1 - s0) {
+        const double a = segment_sum(sprod, k0, k1);
+        const double f_new = sc.c0 - sc.c1 * a;
+        const double delta = f_new - sc.f_old;
         for (int k = k0; k < k1; k++) sprod[k] = delta;
-        field[q] = f_new;
+        field[s0 + tid] = f_new;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < EPT; k++)
         if (row[k] >= 0) r[row[k]] = rr[k] + val[k] * sprod[k * THREADS + tid];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent sweep kernel (the production path): ONE cooperative launch runs n_sweeps full sweeps.  The grid is
+// co-resident (cudaLaunchCooperativeKernel); colour classes are separated by a hand-rolled grid barrier (one atomic
+// arrival per CTA + acquire polling), not by kernel boundaries.  Every per-colour kernel launch cost ~10 us of pure latency
+// (descriptor -> colptr -> entry stream -> r gather, each a dependent DRAM/L2 round trip, ncu: 0.8 waves, 15 % DRAM);
+// here the stream of the NEXT colour's tile (descriptor, values, row ids, per-site constants: everything that does not
+// depend on r) is issued BEFORE the barrier and lands while the CTA waits, so that after the barrier only the r gather, the
+// per-site draw and the r scatter remain on the critical path.
+// r and field are accessed with ld.global.cg / st.global.cg (L2 only): L1 is not coherent across SMs and, unlike the
+// multi-launch form, there is no launch boundary to invalidate it.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// split grid barrier over a co-resident grid: arrive publishes this CTA's stores, wait blocks until `target` arrivals.
+// Work placed between the two calls (staging the next tile) overlaps with the other CTAs' arrival.
+__device__ __forceinline__ void grid_arrive(unsigned int *counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();   // cumulative over the CTA barrier above: every thread's r / field stores are visible gpu-wide
+        atomicAdd(counter, 1u);
+    }
+}
+__device__ __forceinline__ void grid_wait(unsigned int *counter, unsigned int target) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire_gpu_u32(counter) < target) { }
+    }
+    __syncthreads();
+}
+
+struct SiteRaw { int k0, k1, gz; double pd, nobs, S, f; };
+
+// optional in-kernel timeline (development aid, nngp_debug_timeline): CTA 0 stamps %globaltimer at the pipeline stages
+__device__ long long g_timeline[8192];
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define NNGP_STAMP(slot) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0 && tl_n < 4090) { g_timeline[2 * tl_n] = global_ns(); g_timeline[2 * tl_n + 1] = (slot); tl_n++; } } while (0)
+
+#define NNGP_PERSIST_CAP 512   // tiles one CTA may own per sweep (descriptor table in shared memory)
+
+template <int THREADS, int EPT>
+__global__ void __launch_bounds__(THREADS) gibbs_persistent_kernel(
+    const int4 *__restrict__ tiles, const int *__restrict__ tile_ptr, int K, int n_sweeps, unsigned long long sweep_counter0,
+    unsigned long long z_offset0, unsigned long long n_sites, const int *__restrict__ colptr, const int *__restrict__ crow,
+    const double *__restrict__ valT, const double *__restrict__ pd, const double *__restrict__ nobs, const double *__restrict__ S,
+    const int *__restrict__ zpos, const int *__restrict__ gid, const double *__restrict__ zbuf,
+    const SweepParams *__restrict__ spp, double *field, double *r, unsigned int *bar, int dbg) {
+    constexpr int ECAP = THREADS * EPT;
+    __shared__ double sprod[ECAP];
+    __shared__ double sbc[2];
+    int tl_n = 0;
+    // this CTA's tiles of one sweep, colour-major (tile j of colour c is tile_ptr[c] + blockIdx.x + j*gridDim.x), with their
+    // colour: descriptors never cost a dependent global load inside the pipeline
+    __shared__ int4 sdesc[NNGP_PERSIST_CAP];
+    __shared__ short scol[NNGP_PERSIST_CAP];
+    __shared__ int s_cnt[128];
+    const int tid = threadIdx.x;
+    const SweepParams sp = *spp;
+    const int G = (int)gridDim.x, bid = (int)blockIdx.x;
+    unsigned int arrivals = 0;
+
+    // ---- build the per-CTA tile list (host guarantees K <= 128 and list length <= NNGP_PERSIST_CAP) ----
+    for (int col = tid; col < K; col += THREADS) {
+        const int nt = tile_ptr[col + 1] - tile_ptr[col];
+        s_cnt[col] = nt > bid ? (nt - bid + G - 1) / G : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int col = 0; col < K; col++) { const int c = s_cnt[col]; s_cnt[col] = acc; acc += c; }
+        s_cnt[K] = acc;   // K <= 127
+    }
+    __syncthreads();
+    const int n_my = s_cnt[K];
+    for (int col = 0; col < K; col++) {
+        const int base = s_cnt[col], cnt = s_cnt[col + 1] - base;
+        for (int j = tid; j < cnt; j += THREADS) {
+            sdesc[base + j] = tiles[tile_ptr[col] + bid + j * G];
+            scol[base + j] = (short)col;
+        }
+    }
+    __syncthreads();
+
+    // issue every r-independent load of a tile (entry stream + raw per-site data); nothing here waits
+    auto issue_loads = [&](const int4 &d, double (&v)[EPT], int (&rw)[EPT], SiteRaw &sr) {
+        const bool staged = (d.w - d.z) <= ECAP;
+#pragma unroll
+        for (int k = 0; k < EPT; k++) {
+            const int e = d.z + k * THREADS + tid;
+            if (staged && e < d.w) {
+                v[k] = valT[e];
+                rw[k] = crow[e];
+            } else {
+                v[k] = 0.0;
+                rw[k] = -1;
+            }
+        }
+        if (tid < d.y - d.x) {
+            const int q = d.x + tid;
+            sr.k0 = colptr[q] - d.z;
+            sr.k1 = colptr[q + 1] - d.z;
+            sr.pd = pd[q];
+            sr.nobs = nobs[q];
+            sr.S = S[q];
+            sr.gz = (sp.rng_mode == 0) ? zpos[q] : gid[q];
+            sr.f = __ldcg(field + q);   // only this thread ever writes field[q] in this launch (static tile -> CTA map)
+        }
+    };
+    auto make_const = [&](const SiteRaw &sr, unsigned long long sweep_idx) -> SiteConst {
+        const double z = (sp.rng_mode == 0)
+                             ? zbuf[z_offset0 + sweep_idx * n_sites + (unsigned long long)sr.gz]
+                             : philox_normal((uint32_t)sr.gz, (uint32_t)(sweep_counter0 + sweep_idx),
+                                             (uint32_t)((sweep_counter0 + sweep_idx) >> 32), sp.key0, sp.key1);
+        return site_const(sp, sr.f, sr.pd, sr.nobs, sr.S, z);
+    };
+    auto barrier = [&]() {
+        grid_arrive(bar);
+        arrivals += (unsigned int)G;
+        grid_wait(bar, arrivals);
+    };
+
+    if (n_my == 0) {   // cannot happen when G <= max tiles per colour, but stay in step with the grid if it does
+        for (int b = 0; b < n_sweeps * K; b++) barrier();
+        return;
+    }
+    // software pipeline: (val,row,sc,ks0,ks1,td) = current tile; (val2,row2,raw,tdn) = next tile, loads in flight
+    double val[EPT], val2[EPT];
+    int row[EPT], row2[EPT];
+    SiteRaw raw{0, 0, 0, 0.0, 0.0, 0.0, 0.0};
+    SiteConst sc{0.0, 0.0, 0.0};
+    int4 td = sdesc[0];
+    int ccol = scol[0];
+    issue_loads(td, val, row, raw);
+    int ks0 = raw.k0, ks1 = raw.k1;
+    if (tid < td.y - td.x) sc = make_const(raw, 0ull);
+    for (int b = 0; b < ccol; b++) barrier();   // colours before this CTA's first tile
+
+    for (int sweep = 0; sweep < n_sweeps; sweep++) {
+        for (int i = 0; i < n_my; i++) {
+            // next tile of this CTA (same colour, a later colour, or the first tile of the next sweep)
+            int ni = i + 1, nsweep = sweep;
+            if (ni == n_my) { ni = 0; nsweep++; }
+            const bool has_next = nsweep < n_sweeps;
+            const int4 tdn = sdesc[ni];
+            const int ncol = scol[ni];
+            // colour boundaries to cross before the next tile may touch r (K barriers per sweep for every CTA)
+            const int nbar = has_next ? (nsweep == sweep ? ncol - ccol : K - ccol + ncol) : K - ccol;
+            const bool oversize = (td.w - td.z) > ECAP;
+            NNGP_STAMP(0);
+            // 1. the r gathers of the current tile go out first ...
+            double rr[EPT];
+            double f_new_mine = 0.0;
+            if (!oversize) {
+#pragma unroll
+                for (int k = 0; k < EPT; k++)
+                    if (row[k] >= 0) rr[k] = __ldcg(r + row[k]);
+            }
+            // 2. ... then the whole r-independent stream of the NEXT tile: it lands while this tile is finished
+            if (has_next) issue_loads(tdn, val2, row2, raw);
+            // 3. finish the current tile
+            if (oversize) {
+                // a single site whose column does not fit a tile (pathological fan-out): whole-CTA reduction from global
+                double acc[1] = {0.0};
+                for (int e = td.z + tid; e < td.w; e += THREADS) acc[0] += valT[e] * __ldcg(r + crow[e]);
+                block_reduce_sum<1>(acc);
+                if (tid == 0) {
+                    const double f_new = sc.c0 - sc.c1 * acc[0];
+                    sbc[0] = f_new - sc.f_old;
+                    __stcg(field + td.x, f_new);
+                    f_new_mine = f_new;
+                }
+                __syncthreads();
+                const double delta = sbc[0];
+                for (int e = td.z + tid; e < td.w; e += THREADS) {
+                    const int rw = crow[e];
+                    __stcg(r + rw, __ldcg(r + rw) + valT[e] * delta);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < EPT; k++)
+                    if (row[k] >= 0) sprod[k * THREADS + tid] = val[k] * rr[k];
+                __syncthreads();
+                NNGP_STAMP(1);
+                if (tid < td.y - td.x) {
+                    const double a = segment_sum(sprod, ks0, ks1);
+                    const double f_new = sc.c0 - sc.c1 * a;
+                    const double delta = f_new - sc.f_old;
+                    for (int k = ks0; k < ks1; k++) sprod[k] = delta;
+                    __stcg(field + td.x + tid, f_new);
+                    f_new_mine = f_new;
+                }
+                __syncthreads();
+                NNGP_STAMP(2);
+#pragma unroll
+                for (int k = 0; k < EPT; k++)
+                    if (row[k] >= 0) __stcg(r + row[k], rr[k] + val[k] * sprod[k * THREADS + tid]);
+            }
+            // a CTA that owns a single tile stages that same tile again for the next sweep: its field value is the one
+            // just written, not the one read (too early) by issue_loads
+            if (n_my == 1) raw.f = f_new_mine;
+            // 4. publish (if a colour ends here), rotate the pipeline, and do the FP64-heavy r-independent site maths of
+            //    the next tile while the other CTAs arrive
+            if (nbar > 0) grid_arrive(bar); else __syncthreads();   // sprod is rewritten by the next tile
+            NNGP_STAMP(3);
+            td = tdn;
+            ccol = ncol;
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+                val[k] = val2[k];
+                row[k] = row2[k];
+            }
+            ks0 = raw.k0;
+            ks1 = raw.k1;
+            if (has_next && tid < td.y - td.x) sc = make_const(raw, (unsigned long long)nsweep);
+            NNGP_STAMP(4);
+            if (nbar > 0) {
+                arrivals += (unsigned int)G;
+                grid_wait(bar, arrivals);
+                for (int b = 1; b < nbar; b++) barrier();
+            }
+        }
+    }
+    if (dbg && blockIdx.x == 0 && tid == 0) g_timeline[8191] = tl_n;
 }
 
 // tail of the colour sequence: colours [c0, c1) are small; one CTA walks them with a block barrier in between

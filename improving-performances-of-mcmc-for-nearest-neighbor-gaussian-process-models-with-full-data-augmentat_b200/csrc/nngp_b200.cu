@@ -94,12 +94,20 @@ struct Ctx {
     struct Seg { int l0, l1; bool single_block; };
     std::vector<Seg> solve_plan;
     int tail_color = 0;  // colours [tail_color, K) are walked by one CTA
-    // tiles of the sweep: cfg 0 = 256 threads x 8 entries, cfg 1 = 128 threads x 8 entries
-    std::vector<int> tile_ptr[2];          // per colour, into d_tiles[cfg]
-    std::vector<int> color_cfg;            // chosen cfg per colour
-    int sweep_variant = 0;                 // 0 auto tiles, 1 force cfg 0, 2 force cfg 1, 3 thread-per-site kernel
+    // tiles of the sweep: cfg 0 = 256 threads x 8 entries, cfg 1 = 128 x 8, cfg 2 = 256 x 4
+    std::vector<int> tile_ptr[3];          // per colour, into d_tiles[cfg]
+    int max_tiles[3] = {0, 0, 0};          // largest number of tiles in one colour
+    int persistent_grid[3] = {0, 0, 0};    // co-resident grid size of the persistent kernel per cfg
+    bool persistent_ok[3] = {false, false, false};   // per-CTA tile list fits the kernel's shared-memory table
+    // 0 persistent 256x8 | 1 per-colour launches 256x8 | 2 per-colour launches 128x8 | 3 thread-per-site launches
+    // 4 persistent 256x4 | 5 persistent 128x8
+    int sweep_variant = 2;                 // measured fastest at n = 1M (profiles/r01_explore.txt)
     int solve_variant = 0;                 // 0 sync-free single launch, 1 level-scheduled launches
     int n_slots = 0;                       // padded length of the level-ordered row list
+    int solve_ctas_per_sm = 1;             // window of the sync-free solve = n_sm * this * 256 rows
+    int solve_window_ctas = 0;             // if > 0: absolute number of CTAs (overrides the per-SM setting)
+    int solve_sleep_ns = 0;                // back-off between polls
+    bool debug_timeline = false;           // persistent sweep kernel stamps %globaltimer (development aid)
 
     // device structure
     DevBuf<int> d_i2g, d_g2i, d_nn, d_colptr, d_crow, d_csrc, d_zpos, d_lvl_rows, d_lvl_ptr, d_lm, d_optr, d_oidx, d_cstart,
@@ -107,8 +115,10 @@ struct Ctx {
     DevBuf<double> d_locs, d_tl, d_linv[2], d_valT, d_pd, d_nobs, d_ymx, d_S, d_field, d_newfield, d_r, d_tmp1, d_tmp2, d_io,
         d_zbuf, d_partials, d_scalars, d_flush;
     DevBuf<SweepParams> d_sp;
-    DevBuf<int2> d_tiles[2];
+    DevBuf<int4> d_tiles[3];
+    DevBuf<int> d_tile_ptr[3];
     DevBuf<int> d_rows_padded, d_ticket;
+    DevBuf<unsigned int> d_bar;
     double *h_pinned = nullptr;       // 64 doubles of pinned scratch for scalar results
     double *h_stage = nullptr;        // pinned staging for vectors (n doubles at least)
     size_t h_stage_n = 0;
@@ -297,8 +307,9 @@ static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, do
         CK(cudaMemsetAsync(c->d_ticket.p, 0, sizeof(int), c->stream));
         fill_u64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(reinterpret_cast<unsigned long long *>(x), NNGP_SOLVE_SENTINEL, c->n);
         LAUNCHED(c);
-        const int blocks = (c->n_slots + 255) / 256;
-        DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1)));
+        const int want = c->solve_window_ctas > 0 ? c->solve_window_ctas : c->n_sm * c->solve_ctas_per_sm;
+        const int blocks = std::max(1, std::min((c->n_slots + 255) / 256, want));
+        DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns)));
         LAUNCHED(c);
         return;
     }
@@ -326,7 +337,7 @@ static void launch_sweep_colors(Ctx *c) {
             gibbs_color_kernel<<<(q1 - q0 + 255) / 256, 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, q0, q1);
             continue;
         }
-        const int cfg = c->sweep_variant == 1 ? 0 : (c->sweep_variant == 2 ? 1 : c->color_cfg[col]);
+        const int cfg = c->sweep_variant == 1 ? 0 : 1;   // also the fallback when the persistent kernel's table would overflow
         const int t0 = c->tile_ptr[cfg][col], nt = c->tile_ptr[cfg][col + 1] - t0;
         if (cfg == 0)
             gibbs_tile_kernel<256, 8><<<nt, 256, 0, c->stream>>>(c->d_tiles[0].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
@@ -340,25 +351,52 @@ static void launch_sweep_colors(Ctx *c) {
 
 static int sweep_launches(Ctx *c) { return c->tail_color + (c->tail_color < c->K ? 1 : 0) + 1; }
 
-// one sweep over all colours; parameters are read from d_sp
-static void op_sweep_once(Ctx *c) {
-    if (c->use_graph) {
-        if (!c->sweep_graph) {
-            cudaGraph_t g;
-            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-            launch_sweep_colors(c);
-            CK(cudaStreamEndCapture(c->stream, &g));
-            CK(cudaGraphInstantiate(&c->sweep_graph, g, 0));
-            CK(cudaGraphDestroy(g));
-        }
-        CK(cudaGraphLaunch(c->sweep_graph, c->stream));
-    } else {
-        launch_sweep_colors(c);
-        CK(cudaGetLastError());
+static bool sweep_is_persistent(Ctx *c) { return c->sweep_variant == 0 || c->sweep_variant == 4 || c->sweep_variant == 5; }
+
+// n_sweeps sweeps over all colours; scalar parameters are read from d_sp, the sweep counter / normals offset are passed in
+static void op_sweeps(Ctx *c, int n_sweeps, unsigned long long sweep_in_call) {
+    if (n_sweeps <= 0) return;
+    const int pcfg = c->sweep_variant == 0 ? 0 : (c->sweep_variant == 5 ? 1 : 2);
+    if (sweep_is_persistent(c) && c->persistent_ok[pcfg]) {
+        const int cfg = pcfg;
+        CK(cudaMemsetAsync(c->d_bar.p, 0, sizeof(unsigned int), c->stream));
+        const int4 *tiles = c->d_tiles[cfg].p;
+        const int *tile_ptr = c->d_tile_ptr[cfg].p;
+        int K = c->K, ns = n_sweeps;
+        unsigned long long sc0 = c->sweep_counter + sweep_in_call, zoff0 = sweep_in_call * (unsigned long long)c->n, nsites = (unsigned long long)c->n;
+        const int *colptr = c->d_colptr.p, *crow = c->d_crow.p, *zpos = c->d_zpos.p, *gid = c->d_i2g.p;
+        const double *valT = c->d_valT.p, *pd = c->d_pd.p, *nobs = c->d_nobs.p, *S = c->d_S.p, *zbuf = c->d_zbuf.p;
+        const SweepParams *spp = c->d_sp.p;
+        double *field = c->d_field.p, *r = c->d_r.p;
+        unsigned int *bar = c->d_bar.p;
+        int dbg = c->debug_timeline ? 1 : 0;
+        void *args[] = {&tiles, &tile_ptr, &K, &ns, &sc0, &zoff0, &nsites, &colptr, &crow, &valT, &pd, &nobs, &S, &zpos, &gid, &zbuf, &spp, &field, &r, &bar, &dbg};
+        const int grid = c->persistent_grid[cfg];
+        if (cfg == 0) CK(cudaLaunchCooperativeKernel((void *)gibbs_persistent_kernel<256, 8>, dim3(grid), dim3(256), args, 0, c->stream));
+        else if (cfg == 1) CK(cudaLaunchCooperativeKernel((void *)gibbs_persistent_kernel<128, 8>, dim3(grid), dim3(128), args, 0, c->stream));
+        else CK(cudaLaunchCooperativeKernel((void *)gibbs_persistent_kernel<256, 4>, dim3(grid), dim3(256), args, 0, c->stream));
+        LAUNCHED(c);
+        return;
     }
-    const int nl = sweep_launches(c);
-    g_launches.fetch_add(nl, std::memory_order_relaxed);
-    c->launches_in_op += nl;
+    for (int s = 0; s < n_sweeps; s++) {
+        if (c->use_graph) {
+            if (!c->sweep_graph) {
+                cudaGraph_t g;
+                CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                launch_sweep_colors(c);
+                CK(cudaStreamEndCapture(c->stream, &g));
+                CK(cudaGraphInstantiate(&c->sweep_graph, g, 0));
+                CK(cudaGraphDestroy(g));
+            }
+            CK(cudaGraphLaunch(c->sweep_graph, c->stream));
+        } else {
+            launch_sweep_colors(c);
+            CK(cudaGetLastError());
+        }
+        const int nl = sweep_launches(c);
+        g_launches.fetch_add(nl, std::memory_order_relaxed);
+        c->launches_in_op += nl;
+    }
 }
 
 static void set_sweep_params(Ctx *c, double beta0, double log_scale, double log_noise_variance, int rng_mode, double seed) {
@@ -435,7 +473,8 @@ static void destroy_ctx(Ctx *c) {
                             &c->d_scalars, &c->d_flush};
     for (auto *b : db) b->release();
     c->d_sp.release();
-    c->d_tiles[0].release(); c->d_tiles[1].release(); c->d_rows_padded.release(); c->d_ticket.release();
+    for (int k = 0; k < 3; k++) { c->d_tiles[k].release(); c->d_tile_ptr[k].release(); }
+    c->d_rows_padded.release(); c->d_ticket.release(); c->d_bar.release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -563,9 +602,7 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
         for (int i = 0; i < n; i++) zg[i] = next[coloring[i] - 1]++;
         for (int q = 0; q < n; q++) zpos[q] = zg[c->i2g[q]];
     }
-    // colours small enough to be walked by a single CTA form the tail
-    c->tail_color = K;
-    while (c->tail_color > 0 && (c->cstart[c->tail_color] - c->cstart[c->tail_color - 1]) <= 2048) c->tail_color--;
+    c->tail_color = K;   // ncu: the single-CTA tail walk costs more (dependent cold misses) than one small launch per colour
 
     // ---- row structure in internal numbering ----
     const int ld = c->ld;
@@ -630,11 +667,11 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
         while (rows_padded.size() % 32) rows_padded.push_back(-1);
     }
     c->n_slots = (int)rows_padded.size();
-    // ---- sweep tiles: runs of consecutive same-colour sites with <= T sites and <= T*8 CSC entries ----
-    std::vector<int2> tiles[2];
-    const int tcfg_threads[2] = {256, 128};
-    for (int cfg = 0; cfg < 2; cfg++) {
-        const int T = tcfg_threads[cfg], ECAP = T * 8;
+    // ---- sweep tiles: runs of consecutive same-colour sites with <= T sites and <= T*EPT CSC entries ----
+    std::vector<int4> tiles[3];
+    const int tcfg_threads[3] = {256, 128, 256}, tcfg_ept[3] = {8, 8, 4};
+    for (int cfg = 0; cfg < 3; cfg++) {
+        const int T = tcfg_threads[cfg], ECAP = T * tcfg_ept[cfg];
         c->tile_ptr[cfg].assign(K + 1, 0);
         for (int col = 0; col < K; col++) {
             int s0 = c->cstart[col];
@@ -642,15 +679,13 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
             while (s0 < send) {
                 int s1 = s0 + 1;   // at least one site (an oversize column is handled inside the kernel)
                 while (s1 < send && s1 - s0 < T && colptr[s1 + 1] - colptr[s0] <= ECAP) s1++;
-                tiles[cfg].push_back(make_int2(s0, s1));
+                tiles[cfg].push_back(make_int4(s0, s1, colptr[s0], colptr[s1]));
                 s0 = s1;
             }
             c->tile_ptr[cfg][col + 1] = (int)tiles[cfg].size();
+            c->max_tiles[cfg] = std::max(c->max_tiles[cfg], c->tile_ptr[cfg][col + 1] - c->tile_ptr[cfg][col]);
         }
     }
-    c->color_cfg.assign(K, 0);
-    for (int col = 0; col < K; col++)
-        c->color_cfg[col] = (c->tile_ptr[0][col + 1] - c->tile_ptr[0][col] >= 2 * c->n_sm) ? 0 : 1;
     // ---- observations ----
     std::vector<int> lm(n_obs), optr(n + 1, 0), oidx(n_obs);
     for (int o = 0; o < n_obs; o++) {
@@ -675,7 +710,25 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
     CK(cudaMemsetAsync(c->d_nbad.p, 0, 2 * sizeof(int), s));
     c->d_ticket.alloc(1);
     c->d_rows_padded.upload(rows_padded, s);
-    for (int cfg = 0; cfg < 2; cfg++) c->d_tiles[cfg].upload(tiles[cfg], s);
+    for (int cfg = 0; cfg < 3; cfg++) { c->d_tiles[cfg].upload(tiles[cfg], s); c->d_tile_ptr[cfg].upload(c->tile_ptr[cfg], s); }
+    c->d_bar.alloc(1);
+    {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_persistent_kernel<256, 8>, 256, 0));
+        c->persistent_grid[0] = std::max(1, std::min(occ * c->n_sm, c->max_tiles[0]));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_persistent_kernel<128, 8>, 128, 0));
+        c->persistent_grid[1] = std::max(1, std::min(occ * c->n_sm, c->max_tiles[1]));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_persistent_kernel<256, 4>, 256, 0));
+        c->persistent_grid[2] = std::max(1, std::min(occ * c->n_sm, c->max_tiles[2]));
+        for (int cfg = 0; cfg < 3; cfg++) {
+            long long per_cta = 0;
+            for (int col = 0; col < K; col++) {
+                const int nt = c->tile_ptr[cfg][col + 1] - c->tile_ptr[cfg][col];
+                per_cta += (nt + c->persistent_grid[cfg] - 1) / c->persistent_grid[cfg];
+            }
+            c->persistent_ok[cfg] = (K <= 127) && (per_cta <= NNGP_PERSIST_CAP);
+        }
+    }
     c->d_tl.alloc((size_t)n * c->dt);
     for (int k = 0; k < 2; k++) { c->d_linv[k].alloc((size_t)ld * M); CK(cudaMemsetAsync(c->d_linv[k].p, 0, sizeof(double) * ld * M, s)); }
     c->d_valT.alloc(c->nnz); c->d_pd.alloc(n); c->d_ymx.alloc(std::max(n_obs, 1)); c->d_S.alloc(n); c->d_field.alloc(n);
@@ -711,12 +764,28 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
     use(c);
     CK(cudaStreamSynchronize(c->stream));
     switch (*key) {
-        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 3, "sweep variant must be 0..3"); c->sweep_variant = *value; break;
+        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 5, "sweep variant must be 0..5"); c->sweep_variant = *value; break;
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
+        case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;
+        case NNGP_OPT_SOLVE_WINDOW_CTAS: REQUIRE(*value >= 0 && *value <= 4096, "solve window must be 0..4096 CTAs"); c->solve_window_ctas = *value; break;
+        case NNGP_OPT_DEBUG_TIMELINE: c->debug_timeline = (*value != 0); break;
+        case NNGP_OPT_SOLVE_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "solve sleep must be 0..100000 ns"); c->solve_sleep_ns = *value; break;
         default: REQUIRE(false, "unknown option key %d", *key);
     }
     if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; }
+    ABI_END
+}
+
+void nngp_debug_timeline(double *out, const int *n_out, int *n_written, int *status) {
+    ABI_BEGIN
+    REQUIRE(out && n_out && n_written, "nngp_debug_timeline: null argument");
+    std::vector<long long> h(8192);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(h.data(), g_timeline, sizeof(long long) * 8192));
+    const int cnt = (int)std::min<long long>(std::min<long long>(h[8191], 4090), *n_out / 2);
+    for (int i = 0; i < cnt; i++) { out[2 * i] = (double)(h[2 * i] - h[0]); out[2 * i + 1] = (double)h[2 * i + 1]; }
+    *n_written = cnt;
     ABI_END
 }
 
@@ -913,7 +982,7 @@ void nngp_gibbs_sweep(const int *ctx_id, const int *n_sweeps, const double *beta
     }
     set_sweep_params(c, *beta_0, *log_scale, *log_noise_variance, *rng_mode, seed ? *seed : 0.0);
     refresh_r(c, *beta_0);
-    for (int s = 0; s < *n_sweeps; s++) op_sweep_once(c);
+    op_sweeps(c, *n_sweeps, 0);
     c->sweep_counter += (unsigned long long)*n_sweeps;
     CK(cudaStreamSynchronize(c->stream));
     ABI_END
@@ -1133,7 +1202,7 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
         }
         set_sweep_params(c, beta_0, log_scale, lnv, rng_mode, (double)philox_seed);
         refresh_r(c, beta_0);
-        for (int s = 0; s < n_chromatic; s++) op_sweep_once(c);
+        op_sweeps(c, n_chromatic, 0);
         c->sweep_counter += (unsigned long long)n_chromatic;
         // ---- (E) noise variance :281-293 ----
         op_obs_sq(c, c->d_field.p, c->d_field.p, 0);
@@ -1195,12 +1264,12 @@ void nngp_time_op(const int *ctx_id, const int *op_, const int *reps_, const int
         switch (op) {
             case 0: op_factor_build(c, NNGP_SLOT_PROPOSAL, c->last_cc); break;
             case 1: op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, 0); break;
-            case 2: op_sweep_once(c); c->sweep_counter++; break;
+            case 2: op_sweeps(c, 1, 0); c->sweep_counter++; break;
             case 3: op_spmv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, c->d_tmp1.p); break;
             case 4: op_spmv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, c->d_tmp1.p);
                     op_sptrsv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_tmp1.p, c->d_tmp2.p, nullptr, 0.0, 1.0); break;
             case 5: op_commit(c); break;
-            case 6: op_sweep_once(c); c->sweep_counter++;
+            case 6: op_sweeps(c, 1, 0); c->sweep_counter++;
                     op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, 0); break;
             default: REQUIRE(false, "nngp_time_op: unknown op %d", op);
         }

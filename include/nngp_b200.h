@@ -88,13 +88,19 @@ void nngp_ctx_create(const int *n, const int *d, const int *m, const double *loc
                      const int *device, const int *layout, int *ctx_id, int *status);
 void nngp_ctx_destroy(const int *ctx_id, int *status);
 /* performance knobs (results are identical up to FP64 summation order):
- *   NNGP_OPT_SWEEP_VARIANT 0 = tiled kernel, tile shape chosen per colour; 1 = 256x8 tiles; 2 = 128x8 tiles;
- *                          3 = thread-per-site kernel
+ *   NNGP_OPT_SWEEP_VARIANT 2 = one launch per colour, 128-thread CTAs x 8 entries/thread, replayed from a CUDA graph
+ *                          (default); 1 = same with 256x8 tiles; 3 = one launch per colour, thread per site;
+ *                          0 / 4 / 5 = persistent cooperative kernel (grid barrier between colours, next tile prefetched
+ *                          across the barrier) with 256x8 / 256x4 / 128x8 tiles
  *   NNGP_OPT_SOLVE_VARIANT 0 = synchronisation-free single-launch triangular solve; 1 = one launch per DAG level
  *   NNGP_OPT_USE_GRAPH     1 = the colour launches of a sweep are replayed from a captured CUDA graph (default) */
 #define NNGP_OPT_SWEEP_VARIANT 1
 #define NNGP_OPT_SOLVE_VARIANT 2
 #define NNGP_OPT_USE_GRAPH 3
+#define NNGP_OPT_SOLVE_CTAS_PER_SM 4 /* window of the sync-free solve: n_sm * value * 256 rows in flight (default 1) */
+#define NNGP_OPT_SOLVE_SLEEP_NS 5    /* back-off between dependency polls (default 0) */
+#define NNGP_OPT_SOLVE_WINDOW_CTAS 7  /* absolute window of the sync-free solve in CTAs of 256 rows (0 = use per-SM setting) */
+#define NNGP_OPT_DEBUG_TIMELINE 6    /* development aid: the persistent sweep kernel stamps %globaltimer per stage */
 void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);
 /* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,
  * [6]=device, [7]=layout */
@@ -201,6 +207,8 @@ void nngp_predict_sample(const int *ctx_id, const int *slot, const int *n_obs_si
  * per repetition. flush_l2 != 0 writes a 256 MB scratch buffer between repetitions (outside the timed events). */
 void nngp_time_op(const int *ctx_id, const int *op, const int *reps, const int *flush_l2, double *ms_out,
                   int *launches_out, int *status);
+/* development aid: (time ns, stage id) pairs stamped by CTA 0 of the last persistent sweep launch (NNGP_OPT_DEBUG_TIMELINE) */
+void nngp_debug_timeline(double *out, const int *n_out, int *n_written, int *status);
 /* cumulative number of kernels this library has launched in this process (for bench.py's gpu_launches) */
 void nngp_launch_count(double *count);
 

@@ -38,8 +38,8 @@ def main():
         ctx.obs_set(w + np.sqrt(0.1) * rng.standard_normal(a.n))
         ctx.gibbs_sweep(0.0, 0.0, np.log(0.1), 1, seed=1)
         print(f"layout={layout} n={a.n} m={a.m} colors={ctx.n_colors} levels={ctx.n_levels} nnz={ctx.nnz} max_col={ctx.max_col}")
-        for sv in (0, 1, 2, 3):
-            for g in (1, 0):
+        for sv in (0, 4, 5, 1, 2, 3):
+            for g in ((1,) if sv in (0, 4, 5) else (1, 0)):
                 ctx.set_option("sweep_variant", sv)
                 ctx.set_option("use_graph", g)
                 ctx.time_op("gibbs_sweep", reps=3)
@@ -47,11 +47,16 @@ def main():
                 print(f"  sweep variant={sv} graph={g}: mean {ms.mean()*1e3:8.1f} us  min {ms.min()*1e3:8.1f} us  launches {nl}")
         ctx.set_option("sweep_variant", 0)
         ctx.set_option("use_graph", 1)
-        for sv in (0, 1):
+        for sv, win, slp in ((1, 0, 0), (0, 18, 0), (0, 37, 0), (0, 74, 0), (0, 111, 0), (0, 148, 0), (0, 222, 0), (0, 296, 0), (0, 74, 50), (0, 148, 50)):
             ctx.set_option("solve_variant", sv)
+            ctx.set_option("solve_window_ctas", win)
+            ctx.set_option("solve_sleep_ns", slp)
             ctx.time_op("sptrsv", reps=2)
             ms, nl = ctx.time_op("sptrsv", reps=max(3, a.reps // 4))
-            print(f"  spmv+sptrsv variant={sv}: mean {ms.mean()*1e3:8.1f} us  min {ms.min()*1e3:8.1f} us  launches {nl}")
+            print(f"  spmv+sptrsv variant={sv} window_ctas={win} sleep={slp}: mean {ms.mean()*1e3:8.1f} us  min {ms.min()*1e3:8.1f} us  launches {nl}")
+        ctx.set_option("solve_window_ctas", 0)
+        ctx.set_option("solve_ctas_per_sm", 1)
+        ctx.set_option("solve_sleep_ns", 0)
         ctx.set_option("solve_variant", 0)
         for op in ("loglik", "spmv", "factor_build", "commit", "sweep_loglik"):
             ctx.time_op(op, reps=2)
