@@ -395,54 +395,82 @@ __global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restr
     // The grid is a sliding window over the level-ordered rows: each CTA repeatedly takes the next chunk of 256 slots.  A
     // bounded window (gridDim.x * 256 rows, a few DAG levels wide) keeps the number of polling threads -- and the L2 traffic
     // they generate -- small; with one thread per row for the whole DAG in flight ncu showed 1.1 GB of DRAM reads and 3 ms.
+    // Three chunks are in flight per CTA: (A) ticket + row id of chunk i+2, (B) the index / coefficient loads of chunk
+    // i+1, (C) the dependency polls of chunk i -- so the only latency left on a CTA's critical path is the polling itself.
+    // Deadlock freedom: tickets are handed out in order and every CTA works through the chunks it holds in increasing
+    // order, so the lowest unfinished chunk is always being processed and only depends on finished chunks (or on earlier
+    // levels inside itself, which other warps of the same CTA handle).
     __shared__ int s_chunk;
     constexpr int MC = MT > 0 ? MT : 32;
     const int Mr = MT > 0 ? MT : M;
-    for (;;) {
+    const int n_chunks = (n_slots + (int)blockDim.x - 1) / (int)blockDim.x;
+    auto take = [&]() -> int {
         __syncthreads();
         if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1);
         __syncthreads();
-        const int base = s_chunk * (int)blockDim.x;
-        if (base >= n_slots) return;
-        const int t = base + threadIdx.x;
-        const int q = (t < n_slots) ? rows_padded[t] : -1;
-        if (q < 0) continue;
-        int idx[MC];
-        double a[MC];
+        return s_chunk;
+    };
+    auto row_of = [&](int chunk) -> int {
+        const int t = chunk * (int)blockDim.x + (int)threadIdx.x;
+        return (chunk < n_chunks && t < n_slots) ? rows_padded[t] : -1;
+    };
+    int idx[MC], idx1[MC];
+    double a[MC], a1[MC];
+    double bq = 0.0, bq1 = 0.0;
+    auto load_row = [&](int q, int (&id)[MC], double (&av)[MC], double &bv) {
+        if (q < 0) return;
 #pragma unroll
         for (int j = 0; j < MC; j++) {
             if (j < Mr) {
-                idx[j] = nn[(size_t)j * ld + q];
-                a[j] = linv[(size_t)j * ld + q];
+                id[j] = nn[(size_t)j * ld + q];
+                av[j] = linv[(size_t)j * ld + q];
             }
         }
-        double s = b[q];
-        // Poll ALL still-pending parents in every round: the loads of one round are independent and overlap, so a round
-        // costs one L2 round trip however many parents are outstanding (polling them one after the other cost up to m
-        // serial round trips per DAG level: 7 us per level measured, against a 0.38 us flag hop).
-        unsigned long long bits[MC];
+        bv = b[q];
+    };
+    int c0 = take();
+    int q0 = row_of(c0);
+    load_row(q0, idx, a, bq);
+    int c1 = take();
+    int q1 = row_of(c1);
+    while (c0 < n_chunks) {
+        const int c2 = (c1 < n_chunks) ? take() : n_chunks;   // (A) ticket of chunk i+2 ...
+        const int q2 = row_of(c2);                            //     ... and its row id (in flight)
+        load_row(q1, idx1, a1, bq1);                          // (B) loads of chunk i+1 (row id arrived last iteration)
+        if (q0 >= 0) {                                        // (C) chunk i
+            double s = bq;
+            // Poll ALL still-pending parents in every round: the loads of one round are independent and overlap, so a
+            // round costs one L2 round trip however many parents are outstanding (polling them one after the other cost
+            // up to m serial round trips per DAG level: 7 us per level measured, against a 0.38 us flag hop).
+            unsigned long long bits[MC];
 #pragma unroll
-        for (int j = 1; j < MC; j++) bits[j] = (j < Mr && idx[j] >= 0) ? NNGP_SOLVE_SENTINEL : 0ull;
-        unsigned int spins = 0;
-        bool pending = true;
-        while (pending) {
+            for (int j = 1; j < MC; j++) bits[j] = (j < Mr && idx[j] >= 0) ? NNGP_SOLVE_SENTINEL : 0ull;
+            unsigned int spins = 0;
+            bool pending = true;
+            while (pending) {
+#pragma unroll
+                for (int j = 1; j < MC; j++)
+                    if (bits[j] == NNGP_SOLVE_SENTINEL) bits[j] = ld_relaxed_gpu_u64(x + idx[j]);
+                pending = false;
+#pragma unroll
+                for (int j = 1; j < MC; j++) pending = pending || (bits[j] == NNGP_SOLVE_SENTINEL);
+                if (pending) {
+                    if (++spins > (1u << 22)) { atomicExch(err, 1); break; }   // never hang the device on a corrupted structure
+                    if (sleep_ns) __nanosleep(sleep_ns);
+                }
+            }
 #pragma unroll
             for (int j = 1; j < MC; j++)
-                if (bits[j] == NNGP_SOLVE_SENTINEL) bits[j] = ld_relaxed_gpu_u64(x + idx[j]);
-            pending = false;
-#pragma unroll
-            for (int j = 1; j < MC; j++) pending = pending || (bits[j] == NNGP_SOLVE_SENTINEL);
-            if (pending) {
-                if (++spins > (1u << 22)) { atomicExch(err, 1); break; }   // never hang the device on a corrupted structure
-                if (sleep_ns) __nanosleep(sleep_ns);
-            }
+                if (j < Mr && idx[j] >= 0) s -= a[j] * __longlong_as_double((long long)bits[j]);
+            const double xv = s / a[0];
+            st_relaxed_gpu_u64(x + q0, (unsigned long long)__double_as_longlong(xv));
+            if (y) y[q0] = shift + scale * xv;
         }
+        // rotate the pipeline
+        c0 = c1; q0 = q1; bq = bq1;
 #pragma unroll
-        for (int j = 1; j < MC; j++)
-            if (j < Mr && idx[j] >= 0) s -= a[j] * __longlong_as_double((long long)bits[j]);
-        const double xv = s / a[0];
-        st_relaxed_gpu_u64(x + q, (unsigned long long)__double_as_longlong(xv));
-        if (y) y[q] = shift + scale * xv;
+        for (int j = 0; j < MC; j++) { idx[j] = idx1[j]; a[j] = a1[j]; }
+        c1 = c2; q1 = q2;
     }
 }
 

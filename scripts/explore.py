@@ -47,7 +47,7 @@ def main():
                 print(f"  sweep variant={sv} graph={g}: mean {ms.mean()*1e3:8.1f} us  min {ms.min()*1e3:8.1f} us  launches {nl}")
         ctx.set_option("sweep_variant", 0)
         ctx.set_option("use_graph", 1)
-        for sv, win, slp in ((1, 0, 0), (0, 18, 0), (0, 37, 0), (0, 74, 0), (0, 111, 0), (0, 148, 0), (0, 222, 0), (0, 296, 0), (0, 74, 50), (0, 148, 50)):
+        for sv, win, slp in ((0, 18, 0), (0, 37, 0), (0, 74, 0), (0, 111, 0), (0, 148, 0), (0, 222, 0), (0, 296, 0), (0, 74, 50), (0, 148, 50)):
             ctx.set_option("solve_variant", sv)
             ctx.set_option("solve_window_ctas", win)
             ctx.set_option("solve_sleep_ns", slp)

@@ -5,11 +5,15 @@ set -u
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
-tail -1 gpurun_out/plain.log | cut -c1-400
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+tail -1 gpurun_out/plain.log | cut -c1-300
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:gibbs_tile_kernel -s 42 -c 4 -f -o gpurun_out/prof_gibbs $CMD > gpurun_out/ncu_gibbs.log 2>&1
+# one full sweep = K colour launches of gibbs_tile_kernel (K = 22 at n = 1M): skip the first two sweeps
+ncu --set full --clock-control none --import-source on -k regex:gibbs_tile_kernel -s 44 -c 22 -f -o gpurun_out/prof_gibbs $CMD > gpurun_out/ncu_gibbs.log 2>&1
 echo "gibbs full rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"vecchia_factor_reg_kernel|loglik_partial_kernel|transpose_values|sptrsv_syncfree" -s 2 -c 6 -f -o gpurun_out/prof_other $CMD > gpurun_out/ncu_other.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:vecchia_factor_reg_kernel -s 1 -c 1 -f -o gpurun_out/prof_factor $CMD > gpurun_out/ncu_factor.log 2>&1
+echo "factor full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"loglik_partial_kernel" -s 2 -c 1 -f -o gpurun_out/prof_loglik $CMD > gpurun_out/ncu_loglik.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"transpose_values_kernel|sptrsv_syncfree_kernel" -s 1 -c 2 -f -o gpurun_out/prof_other $CMD > gpurun_out/ncu_other.log 2>&1
 echo "other full rc=$?"
 ls -la gpurun_out
