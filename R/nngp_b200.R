@@ -1,0 +1,87 @@
+# R/nngp_b200.R -- thin .C() glue over libnngp_b200.so (C ABI: include/nngp_b200.h).
+#
+# R is not available in the build image, so this file is untested there; it is the binding a maintainer of the reference
+# would add (INTEGRATION.md).  Every ABI function takes only pointers and returns void, so .C() needs no compiled shim.
+# NAOK = TRUE lets NA_integer_ (INT_MIN) in NNarray reach the library unchanged.
+
+nngp_b200_load = function(path = file.path("improving-performances-of-mcmc-for-nearest-neighbor-gaussian-process-models-with-full-data-augmentat_b200", "libnngp_b200.so"))
+{
+  if(!is.loaded("nngp_ctx_create")) dyn.load(path)
+  invisible(TRUE)
+}
+
+nngp_covfun_id = function(stationary_covfun)
+{
+  ids = c(exponential_isotropic = 0L, exponential_sphere = 1L, exponential_scaledim = 2L, exponential_spacetime = 3L,
+          matern_isotropic = 4L, matern_sphere = 5L, matern_scaledim = 6L, matern_spacetime = 7L)
+  if(!stationary_covfun %in% names(ids)) stop(paste("unknown stationary_covfun", stationary_covfun))
+  ids[[stationary_covfun]]
+}
+
+nngp_check = function(res)
+{
+  if(res$status != 0L)
+  {
+    msg = .C("nngp_last_error", buf = paste(rep(" ", 1024), collapse = ""), len = 1024L)$buf
+    stop(paste0("libnngp_b200 status ", res$status, ": ", trimws(msg)))
+  }
+  res
+}
+
+# one context per chain: graph structure of vecchia_approx (Scripts/mcmc_nngp_initialize.R:80-110) uploaded once
+nngp_ctx_create = function(locs, vecchia_approx, stationary_covfun, device = 0L, layout = 2L)
+{
+  locs = as.matrix(locs)
+  res = nngp_check(.C("nngp_ctx_create", n = nrow(locs), d = ncol(locs), m = as.integer(ncol(vecchia_approx$NNarray) - 1L),
+                      locs = as.double(locs), NNarray = as.integer(vecchia_approx$NNarray),
+                      coloring = as.integer(vecchia_approx$coloring), n_obs = as.integer(vecchia_approx$n_obs),
+                      locs_match = as.integer(vecchia_approx$locs_match), covfun_id = nngp_covfun_id(stationary_covfun),
+                      device = as.integer(device), layout = as.integer(layout), ctx_id = integer(1), status = integer(1), NAOK = TRUE))
+  res$ctx_id
+}
+
+nngp_ctx_destroy = function(ctx) invisible(.C("nngp_ctx_destroy", ctx_id = as.integer(ctx), status = integer(1)))
+
+# GpGp::vecchia_Linv replacement; returns the number of non-positive-definite neighbour blocks
+nngp_factor_build = function(ctx, covparms, slot = 0L)
+  nngp_check(.C("nngp_factor_build", ctx_id = as.integer(ctx), slot = as.integer(slot), covparms = as.double(covparms),
+                n_covparms = length(covparms), n_not_pd = integer(1), status = integer(1)))$n_not_pd
+
+nngp_factor_get = function(ctx, n, m, slot = 0L)
+  matrix(nngp_check(.C("nngp_factor_get", ctx_id = as.integer(ctx), slot = as.integer(slot), Linv = double(n * (m + 1)), status = integer(1)))$Linv, n, m + 1)
+
+nngp_field_set = function(ctx, field) invisible(nngp_check(.C("nngp_field_set", ctx_id = as.integer(ctx), field = as.double(field), status = integer(1))))
+nngp_field_get = function(ctx, n) nngp_check(.C("nngp_field_get", ctx_id = as.integer(ctx), field = double(n), status = integer(1)))$field
+nngp_obs_set = function(ctx, y_minus_xb) invisible(nngp_check(.C("nngp_obs_set", ctx_id = as.integer(ctx), y = as.double(y_minus_xb), status = integer(1))))
+
+# ll_compressed_sparse_chol(Linv, field - beta_0, NNarray, log_scale) on the device-resident field
+nngp_loglik = function(ctx, beta_0, log_scale, slot = 0L)
+  nngp_check(.C("nngp_loglik", ctx_id = as.integer(ctx), slot = as.integer(slot), beta_0 = as.double(beta_0), log_scale = as.double(log_scale), ll = double(1), status = integer(1)))$ll
+
+# n_sweeps chromatic sweeps (update_Gaussian.R:257-275); z = NULL uses the on-device Philox generator
+nngp_gibbs_sweep = function(ctx, n_sweeps, beta_0, log_scale, log_noise_variance, z = NULL, seed = 0)
+{
+  rng_mode = if(is.null(z)) 1L else 0L
+  if(is.null(z)) z = 0
+  invisible(nngp_check(.C("nngp_gibbs_sweep", ctx_id = as.integer(ctx), n_sweeps = as.integer(n_sweeps), beta_0 = as.double(beta_0),
+                          log_scale = as.double(log_scale), log_noise_variance = as.double(log_noise_variance), rng_mode = rng_mode,
+                          z = as.double(z), seed = as.double(seed), status = integer(1))))
+}
+
+# initial field draw (initialize.R:201-208) with R's own rnorm stream
+nngp_field_init = function(ctx, beta_0, log_scale, z, slot = 0L)
+  invisible(nngp_check(.C("nngp_field_init", ctx_id = as.integer(ctx), slot = as.integer(slot), beta_0 = as.double(beta_0), log_scale = as.double(log_scale), z = as.double(z), status = integer(1))))
+
+# the whole per-chain loop of mcmc_nngp_update_Gaussian (no regressors) behind one call
+nngp_chain_run = function(ctx, params, transition_kernels, n_iter, field_thinning, n_chromatic, iter_start, chain_index, var_y, n_locs, rng_mode = 1L)
+{
+  k = length(params$shape)
+  p = c(params$beta_0, params$log_scale, params$log_noise_variance, transition_kernels$covariance_params_sufficient$logvar,
+        transition_kernels$covariance_params_ancillary$logvar, params$shape)
+  n_frec = round(n_iter * field_thinning)
+  nngp_check(.C("nngp_chain_run", ctx_id = as.integer(ctx), n_shape = as.integer(k), params_io = as.double(p), n_iter = as.integer(n_iter),
+                thin = as.double(field_thinning), n_chromatic = as.integer(n_chromatic), iter_start = as.integer(iter_start),
+                chain_index = as.integer(chain_index), rng_mode = as.integer(rng_mode), var_y = as.double(var_y),
+                records_out = double(n_iter * (3 + k)), field_records_out = double(max(n_frec, 1) * n_locs), accept_out = integer(2 * n_iter),
+                status = integer(1)))
+}
