@@ -5,10 +5,10 @@ mcmc_nngp_predict_field / mcmc_nngp_estimate) over the C ABI of libnngp_b200.so 
 in this image, so the host side above the ABI is Python; R/ holds the equivalent .C() glue.
 """
 from . import _lib
-from ._lib import (COVFUN_IDS, LAYOUT_COLOR, LAYOUT_COLOR_MORTON, NA_INT, RNG_PHILOX, RNG_SUPPLIED, SLOT_CURRENT,
+from ._lib import (COVFUN_IDS, LAYOUT_COLOR, LAYOUT_COLOR_MORTON, LAYOUT_MORTON, NA_INT, RNG_PHILOX, RNG_SUPPLIED, SLOT_CURRENT,
                    SLOT_PROPOSAL, NNGPError, device_count, launch_count)
 from .context import NNGPContext, find_ordered_nn, greedy_coloring, order_maxmin
 
 __all__ = ["NNGPContext", "find_ordered_nn", "greedy_coloring", "order_maxmin", "NNGPError", "device_count", "launch_count",
            "COVFUN_IDS", "NA_INT", "SLOT_CURRENT", "SLOT_PROPOSAL", "RNG_SUPPLIED", "RNG_PHILOX", "LAYOUT_COLOR",
-           "LAYOUT_COLOR_MORTON"]
+           "LAYOUT_COLOR_MORTON", "LAYOUT_MORTON"]

@@ -20,7 +20,7 @@ COVFUN_IDS = {
 }
 SLOT_CURRENT, SLOT_PROPOSAL = 0, 1
 RNG_SUPPLIED, RNG_PHILOX = 0, 1
-LAYOUT_COLOR, LAYOUT_COLOR_MORTON = 1, 2
+LAYOUT_COLOR, LAYOUT_COLOR_MORTON, LAYOUT_MORTON = 1, 2, 3
 
 # every symbol include/nngp_b200.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [

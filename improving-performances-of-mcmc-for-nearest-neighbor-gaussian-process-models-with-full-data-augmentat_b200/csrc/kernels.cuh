@@ -1,6 +1,13 @@
 // kernels.cuh -- sm_100a kernels of the NNGP hot path.
 //
-// Device layout (all arrays in the INTERNAL site numbering: colour-major, optionally Morton inside a colour):
+// Two internal numberings (both invisible at the ABI):
+//   STORAGE order   -- rows / sites of nn, linv, tl, field, r and every n-vector.  NNGP_LAYOUT_MORTON: pure Z-curve order of
+//                      the coordinates, so that the 8-byte gathers of a row's parents (log-lik, SpMV, factor build) and of a
+//                      site's children (sweep: r) fall into few 32-byte sectors; NNGP_LAYOUT_COLOR[_MORTON]: colour-major.
+//   PROCESSING order -- sites of the Gibbs sweep: colour-major (a colour class is a contiguous range), storage order inside
+//                      a colour.  The CSC (transpose) arrays, the tiles and the per-site constants pd / nobs / S / gid /
+//                      zpos are laid out in processing order; psite[p] is the storage id of processing site p.
+// Device layout:
 //   nn    int32  [M][ld]   neighbour table, slot-major ("column-major" as R stores NNarray): nn[j*ld + q]; -1 = NA
 //   linv  double [M][ld]   compressed factor, same shape: linv[j*ld + q]     (slot 0 = 1/sqrt(F_q), slot j = -B_qj/sqrt(F_q))
 //   tl    double [n][DT]   coordinates after the covariance family's transformation (range-scaled / unit sphere)
@@ -111,7 +118,12 @@ __global__ void __launch_bounds__(128) vecchia_factor_reg_kernel(const int *__re
             for (int c = 0; c < DT; c++) p[k][c] = src[c];
         }
     }
+    // ncu (profiles/r01_factor_full.txt): FP64 pipe 41 % busy, ~2.6 k FP64 instructions per row of which the 66 divisions
+    // and 11 square roots are a third.  One reciprocal square root per pivot replaces them: inv[a] = rsqrt(pivot),
+    // L[a][a] = pivot * inv[a], L[a][b] = s * inv[b], x[a] = s * inv[a]  (<= 2 ulp per operation away from the oracle's
+    // sqrt / divide; the parity tests bound the effect on a factor row at 1e-10).
     double L[M * (M + 1) / 2];
+    double inv[M];
     bool ok = true;
 #pragma unroll
     for (int a = 0; a < M; a++) {
@@ -133,9 +145,10 @@ __global__ void __launch_bounds__(128) vecchia_factor_reg_kernel(const int *__re
             for (int k = 0; k < b; k++) s -= L[a * (a + 1) / 2 + k] * L[b * (b + 1) / 2 + k];
             if (a == b) {
                 ok = ok && (s > 0.0);
-                L[a * (a + 1) / 2 + a] = sqrt(s);
+                inv[a] = rsqrt(s);
+                L[a * (a + 1) / 2 + a] = s * inv[a];
             } else {
-                L[a * (a + 1) / 2 + b] = s / L[b * (b + 1) / 2 + b];
+                L[a * (a + 1) / 2 + b] = s * inv[b];
             }
         }
     }
@@ -145,7 +158,7 @@ __global__ void __launch_bounds__(128) vecchia_factor_reg_kernel(const int *__re
         double s = (a == M - 1) ? 1.0 : 0.0;
 #pragma unroll
         for (int k = a + 1; k < M; k++) s -= L[k * (k + 1) / 2 + a] * x[k];
-        x[a] = s / L[a * (a + 1) / 2 + a];
+        x[a] = s * inv[a];
     }
 #pragma unroll
     for (int j = 0; j < M; j++) linv[(size_t)j * ld + q] = x[M - 1 - j];
@@ -300,13 +313,19 @@ __global__ void __launch_bounds__(256) beta0_partial_kernel(const int *__restric
 
 // t(sparse_chol) %*% u through the transpose map (no atomics)
 __global__ void __launch_bounds__(256) sptmv_kernel(const int *__restrict__ colptr, const int *__restrict__ crow,
-                                                    const int *__restrict__ csrc, const double *__restrict__ linv,
-                                                    const double *__restrict__ u, int n, double *__restrict__ out) {
+                                                    const int *__restrict__ csrc, const int *__restrict__ psite,
+                                                    const double *__restrict__ linv, const double *__restrict__ u, int n,
+                                                    double *__restrict__ out) {
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         double s = 0.0;
         for (int k = colptr[q]; k < colptr[q + 1]; k++) s += linv[csrc[k]] * u[crow[k]];
-        out[q] = s;
+        out[psite[q]] = s;   // CSC columns are in processing order, vectors in storage order
     }
+}
+
+// dst[map[t]] = src[t]
+__global__ void scatter_f64_kernel(double *__restrict__ dst, const double *__restrict__ src, const int *__restrict__ map, int n) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) dst[map[t]] = src[t];
 }
 
 // accept branch: gather the CSC values of the new current factor and its precision_diag in one pass
@@ -322,6 +341,55 @@ __global__ void __launch_bounds__(256) transpose_values_kernel(const int *__rest
             s += v * v;
         }
         pd[q] = s;
+    }
+}
+
+__device__ __forceinline__ double segment_sum(const double *__restrict__ sh, int k0, int k1);
+
+// Tiled form of the same pass (production path): the CSC entry stream of a tile is read flat and coalesced (csrc), values
+// are gathered from the slot-major factor, written back coalesced (valT), and squared into shared memory where one thread per
+// site reduces its segment.  Thread-per-column walking was LSU-wavefront bound (190 us at n = 1M).
+template <int THREADS, int EPT>
+__global__ void __launch_bounds__(THREADS) transpose_tile_kernel(const int4 *__restrict__ tiles, const int *__restrict__ colptr,
+                                                                 const int *__restrict__ csrc, const double *__restrict__ linv,
+                                                                 double *__restrict__ valT, double *__restrict__ pd) {
+    constexpr int ECAP = THREADS * EPT;
+    __shared__ double ssq[ECAP];
+    const int tid = threadIdx.x;
+    const int4 tile = tiles[blockIdx.x];
+    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
+    if (e1 - e0 > ECAP) {   // single site with an oversize column
+        double acc[1] = {0.0};
+        for (int e = e0 + tid; e < e1; e += THREADS) {
+            const double v = linv[csrc[e]];
+            valT[e] = v;
+            acc[0] += v * v;
+        }
+        block_reduce_sum<1>(acc);
+        if (tid == 0) pd[s0] = acc[0];
+        return;
+    }
+    int src[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        const int e = e0 + k * THREADS + tid;
+        src[k] = (e < e1) ? csrc[e] : -1;
+    }
+    double v[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (src[k] >= 0) v[k] = linv[src[k]];
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        if (src[k] >= 0) {
+            valT[e0 + k * THREADS + tid] = v[k];
+            ssq[k * THREADS + tid] = v[k] * v[k];
+        }
+    }
+    __syncthreads();
+    if (tid < s1 - s0) {
+        const int q = s0 + tid;
+        pd[q] = segment_sum(ssq, colptr[q] - e0, colptr[q + 1] - e0);
     }
 }
 
@@ -554,13 +622,15 @@ __global__ void __launch_bounds__(256) gibbs_color_kernel(const int *__restrict_
                                                           const double *__restrict__ valT, const double *__restrict__ pd,
                                                           const double *__restrict__ nobs, const double *__restrict__ S,
                                                           const int *__restrict__ zpos, const int *__restrict__ gid,
+                                                          const int *__restrict__ psite,
                                                           const double *__restrict__ zbuf, const SweepParams *__restrict__ spp,
                                                           double *__restrict__ field, double *__restrict__ r, int q0, int q1) {
     const int q = q0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= q1) return;
     const SweepParams sp = *spp;
     const int k0 = colptr[q], k1 = colptr[q + 1];
-    const double f_old = field[q];
+    const int sq = psite[q];
+    const double f_old = field[sq];
     const double w_old = f_old - sp.beta0;
     double a = 0.0;
     for (int k = k0; k < k1; k++) a += valT[k] * r[crow[k]];
@@ -573,7 +643,7 @@ __global__ void __launch_bounds__(256) gibbs_color_kernel(const int *__restrict_
     const double f_new = mean + z / sqrt(prec);
     const double delta = (f_new - sp.beta0) - w_old;
     for (int k = k0; k < k1; k++) r[crow[k]] += valT[k] * delta;
-    field[q] = f_new;
+    field[sq] = f_new;
 }
 
 // Tiled variant (the production path).  A CTA owns a tile = a run of consecutive same-colour sites whose CSC entries
@@ -584,12 +654,17 @@ __global__ void __launch_bounds__(256) gibbs_color_kernel(const int *__restrict_
 //   phase 3: every thread scatters r[row] = r_old + val*delta for the entries it still holds (no second read of r)
 // Compared with the thread-per-site form this turns 2x(m+1) strided loads per site into coalesced 128/256 B transactions
 // and halves the traffic on r.
-template <int THREADS, int EPT>
+// PDL = true: the launch carries cudaLaunchAttributeProgrammaticStreamSerialization (programmatic dependent launch).
+// The kernel releases its dependents immediately (griddepcontrol.launch_dependents) and does everything that does not
+// depend on r -- entry stream, per-site constants, Philox + Box-Muller -- BEFORE griddepcontrol.wait, i.e. while the
+// previous colour's kernel is still running; only the r gather / segment sum / r scatter remain serialised per colour.
+template <int THREADS, int EPT, bool PDL>
 __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restrict__ tiles, const int *__restrict__ colptr,
                                                              const int *__restrict__ crow, const double *__restrict__ valT,
                                                              const double *__restrict__ pd, const double *__restrict__ nobs,
                                                              const double *__restrict__ S, const int *__restrict__ zpos,
-                                                             const int *__restrict__ gid, const double *__restrict__ zbuf,
+                                                             const int *__restrict__ gid, const int *__restrict__ psite,
+                                                             const double *__restrict__ zbuf,
                                                              const SweepParams *__restrict__ spp, double *__restrict__ field,
                                                              double *__restrict__ r) {
     constexpr int ECAP = THREADS * EPT;
@@ -599,14 +674,17 @@ __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restr
     const int4 tile = tiles[blockIdx.x];
     const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
     const SweepParams sp = *spp;
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (e1 - e0 > ECAP) {
         // a single site whose column does not fit the tile (pathological fan-out): whole-CTA reduction
         const int q = s0;
+        if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
         double acc[1] = {0.0};
         for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * r[crow[e]];
         block_reduce_sum<1>(acc);
         if (tid == 0) {
-            const double w_old = field[q] - sp.beta0;
+            const int sq = psite[q];
+            const double w_old = field[sq] - sp.beta0;
             const double Qss = pd[q], no = nobs[q];
             const double prec = sp.e_ls * Qss + sp.e_ln * no;
             const double t = acc[0] - Qss * w_old;
@@ -614,7 +692,7 @@ __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restr
             const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
             const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
             sbc[0] = (f_new - sp.beta0) - w_old;
-            field[q] = f_new;
+            field[sq] = f_new;
         }
         __syncthreads();
         const double delta = sbc[0];
@@ -634,17 +712,27 @@ __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restr
             row[k] = -1;
         }
     }
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) rr[k] = r[row[k]];
-    // r-independent part of the site update (Philox + Box-Muller, 1/prec, sqrt): overlaps with the gathers in flight
-    int k0 = 0, k1 = 0;
+    int k0 = 0, k1 = 0, sq = 0;
     SiteConst sc{0.0, 0.0, 0.0};
+    if (!PDL) {
+#pragma unroll
+        for (int k = 0; k < EPT; k++)
+            if (row[k] >= 0) rr[k] = r[row[k]];
+    }
+    // r-independent part of the site update (Philox + Box-Muller, 1/prec, sqrt): overlaps with the gathers in flight
+    // (or, under PDL, with the previous colour's kernel)
     if (tid < s1 - s0) {
         const int q = s0 + tid;
         k0 = colptr[q] - e0;
         k1 = colptr[q + 1] - e0;
-        sc = site_const(sp, field[q], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
+        sq = psite[q];
+        sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
+    }
+    if (PDL) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < EPT; k++)
+            if (row[k] >= 0) rr[k] = r[row[k]];
     }
 #pragma unroll
     for (int k = 0; k < EPT; k++)
@@ -655,7 +743,7 @@ __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restr
         const double f_new = sc.c0 - sc.c1 * a;
         const double delta = f_new - sc.f_old;
         for (int k = k0; k < k1; k++) sprod[k] = delta;
-        field[s0 + tid] = f_new;
+        field[sq] = f_new;
     }
     __syncthreads();
 #pragma unroll
@@ -696,7 +784,7 @@ __device__ __forceinline__ void grid_wait(unsigned int *counter, unsigned int ta
     __syncthreads();
 }
 
-struct SiteRaw { int k0, k1, gz; double pd, nobs, S, f; };
+struct SiteRaw { int k0, k1, gz, sq; double pd, nobs, S, f; };
 
 // optional in-kernel timeline (development aid, nngp_debug_timeline): CTA 0 stamps %globaltimer at the pipeline stages
 __device__ long long g_timeline[8192];
@@ -714,7 +802,7 @@ __global__ void __launch_bounds__(THREADS) gibbs_persistent_kernel(
     const int4 *__restrict__ tiles, const int *__restrict__ tile_ptr, int K, int n_sweeps, unsigned long long sweep_counter0,
     unsigned long long z_offset0, unsigned long long n_sites, const int *__restrict__ colptr, const int *__restrict__ crow,
     const double *__restrict__ valT, const double *__restrict__ pd, const double *__restrict__ nobs, const double *__restrict__ S,
-    const int *__restrict__ zpos, const int *__restrict__ gid, const double *__restrict__ zbuf,
+    const int *__restrict__ zpos, const int *__restrict__ gid, const int *__restrict__ psite, const double *__restrict__ zbuf,
     const SweepParams *__restrict__ spp, double *field, double *r, unsigned int *bar, int dbg) {
     constexpr int ECAP = THREADS * EPT;
     __shared__ double sprod[ECAP];
@@ -774,7 +862,8 @@ __global__ void __launch_bounds__(THREADS) gibbs_persistent_kernel(
             sr.nobs = nobs[q];
             sr.S = S[q];
             sr.gz = (sp.rng_mode == 0) ? zpos[q] : gid[q];
-            sr.f = __ldcg(field + q);   // only this thread ever writes field[q] in this launch (static tile -> CTA map)
+            sr.sq = psite[q];
+            sr.f = __ldcg(field + sr.sq);   // only this thread ever writes this field entry in this launch (static tile -> CTA map)
         }
     };
     auto make_const = [&](const SiteRaw &sr, unsigned long long sweep_idx) -> SiteConst {
@@ -797,12 +886,12 @@ __global__ void __launch_bounds__(THREADS) gibbs_persistent_kernel(
     // software pipeline: (val,row,sc,ks0,ks1,td) = current tile; (val2,row2,raw,tdn) = next tile, loads in flight
     double val[EPT], val2[EPT];
     int row[EPT], row2[EPT];
-    SiteRaw raw{0, 0, 0, 0.0, 0.0, 0.0, 0.0};
+    SiteRaw raw{0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0};
     SiteConst sc{0.0, 0.0, 0.0};
     int4 td = sdesc[0];
     int ccol = scol[0];
     issue_loads(td, val, row, raw);
-    int ks0 = raw.k0, ks1 = raw.k1;
+    int ks0 = raw.k0, ks1 = raw.k1, csq = raw.sq;
     if (tid < td.y - td.x) sc = make_const(raw, 0ull);
     for (int b = 0; b < ccol; b++) barrier();   // colours before this CTA's first tile
 
@@ -837,7 +926,7 @@ __global__ void __launch_bounds__(THREADS) gibbs_persistent_kernel(
                 if (tid == 0) {
                     const double f_new = sc.c0 - sc.c1 * acc[0];
                     sbc[0] = f_new - sc.f_old;
-                    __stcg(field + td.x, f_new);
+                    __stcg(field + csq, f_new);
                     f_new_mine = f_new;
                 }
                 __syncthreads();
@@ -857,7 +946,7 @@ __global__ void __launch_bounds__(THREADS) gibbs_persistent_kernel(
                     const double f_new = sc.c0 - sc.c1 * a;
                     const double delta = f_new - sc.f_old;
                     for (int k = ks0; k < ks1; k++) sprod[k] = delta;
-                    __stcg(field + td.x + tid, f_new);
+                    __stcg(field + csq, f_new);
                     f_new_mine = f_new;
                 }
                 __syncthreads();
@@ -882,6 +971,7 @@ __global__ void __launch_bounds__(THREADS) gibbs_persistent_kernel(
             }
             ks0 = raw.k0;
             ks1 = raw.k1;
+            csq = raw.sq;
             if (has_next && tid < td.y - td.x) sc = make_const(raw, (unsigned long long)nsweep);
             NNGP_STAMP(4);
             if (nbar > 0) {
@@ -892,37 +982,6 @@ __global__ void __launch_bounds__(THREADS) gibbs_persistent_kernel(
         }
     }
     if (dbg && blockIdx.x == 0 && tid == 0) g_timeline[8191] = tl_n;
-}
-
-// tail of the colour sequence: colours [c0, c1) are small; one CTA walks them with a block barrier in between
-__global__ void __launch_bounds__(1024) gibbs_tail_kernel(const int *__restrict__ colptr, const int *__restrict__ crow,
-                                                          const double *__restrict__ valT, const double *__restrict__ pd,
-                                                          const double *__restrict__ nobs, const double *__restrict__ S,
-                                                          const int *__restrict__ zpos, const int *__restrict__ gid,
-                                                          const double *__restrict__ zbuf, const SweepParams *__restrict__ spp,
-                                                          double *__restrict__ field, double *__restrict__ r,
-                                                          const int *__restrict__ cstart, int c0, int c1) {
-    const SweepParams sp = *spp;
-    for (int c = c0; c < c1; c++) {
-        const int q0 = cstart[c], q1 = cstart[c + 1];
-        for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
-            const int k0 = colptr[q], k1 = colptr[q + 1];
-            const double w_old = field[q] - sp.beta0;
-            double a = 0.0;
-            for (int k = k0; k < k1; k++) a += valT[k] * r[crow[k]];
-            const double Qss = pd[q], no = nobs[q];
-            const double prec = sp.e_ls * Qss + sp.e_ln * no;
-            const double t = a - Qss * w_old;
-            const double resid = S[q] - no * sp.beta0;
-            const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
-            const double z = sweep_normal(sp, zbuf, zpos, gid, q);
-            const double f_new = mean + z / sqrt(prec);
-            const double delta = (f_new - sp.beta0) - w_old;
-            for (int k = k0; k < k1; k++) r[crow[k]] += valT[k] * delta;
-            field[q] = f_new;
-        }
-        __syncthreads();
-    }
 }
 
 __global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n) {

@@ -81,7 +81,7 @@ struct DevBuf {
 };
 
 struct Ctx {
-    int device = 0, layout = NNGP_LAYOUT_COLOR_MORTON;
+    int device = 0, layout = NNGP_LAYOUT_MORTON;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n = 0, d = 0, m = 0, M = 0, ld = 0, n_obs = 0, covfun = 0, dt = 0, K = 0, n_levels = 0, max_col = 0;
@@ -90,10 +90,9 @@ struct Ctx {
     long long launches_in_op = 0;
 
     // host-side structure
-    std::vector<int> i2g, g2i, cstart, lvl_ptr, partial_rows;
+    std::vector<int> i2g, g2i, cstart, lvl_ptr, partial_rows;   // i2g / g2i: storage id <-> reference (0-based) id
     struct Seg { int l0, l1; bool single_block; };
     std::vector<Seg> solve_plan;
-    int tail_color = 0;  // colours [tail_color, K) are walked by one CTA
     // tiles of the sweep: cfg 0 = 256 threads x 8 entries, cfg 1 = 128 x 8, cfg 2 = 256 x 4
     std::vector<int> tile_ptr[3];          // per colour, into d_tiles[cfg]
     int max_tiles[3] = {0, 0, 0};          // largest number of tiles in one colour
@@ -101,8 +100,9 @@ struct Ctx {
     bool persistent_ok[3] = {false, false, false};   // per-CTA tile list fits the kernel's shared-memory table
     // 0 persistent 256x8 | 1 per-colour launches 256x8 | 2 per-colour launches 128x8 | 3 thread-per-site launches
     // 4 persistent 256x4 | 5 persistent 128x8
-    int sweep_variant = 2;                 // measured fastest at n = 1M (profiles/r01_explore.txt)
+    int sweep_variant = 6;                 // PDL chain of 128x8 tile launches: measured fastest at n = 1M (profiles/)
     int solve_variant = 0;                 // 0 sync-free single launch, 1 level-scheduled launches
+    int commit_variant = 0;                // 0 tiled transposition, 1 thread per column
     int n_slots = 0;                       // padded length of the level-ordered row list
     int solve_ctas_per_sm = 1;             // window of the sync-free solve = n_sm * this * 256 rows
     int solve_window_ctas = 0;             // if > 0: absolute number of CTAs (overrides the per-SM setting)
@@ -110,7 +110,7 @@ struct Ctx {
     bool debug_timeline = false;           // persistent sweep kernel stamps %globaltimer (development aid)
 
     // device structure
-    DevBuf<int> d_i2g, d_g2i, d_nn, d_colptr, d_crow, d_csrc, d_zpos, d_lvl_rows, d_lvl_ptr, d_lm, d_optr, d_oidx, d_cstart,
+    DevBuf<int> d_psite, d_gid, d_i2g, d_g2i, d_nn, d_colptr, d_crow, d_csrc, d_zpos, d_lvl_rows, d_lvl_ptr, d_lm, d_optr, d_oidx, d_cstart,
         d_partial_rows, d_nbad;
     DevBuf<double> d_locs, d_tl, d_linv[2], d_valT, d_pd, d_nobs, d_ymx, d_S, d_field, d_newfield, d_r, d_tmp1, d_tmp2, d_io,
         d_zbuf, d_partials, d_scalars, d_flush;
@@ -325,31 +325,55 @@ static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, do
 }
 
 static void op_commit(Ctx *c) {
-    transpose_values_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, c->n, c->d_valT.p, c->d_pd.p);
+    if (c->commit_variant == 0) {
+        const int nt = c->tile_ptr[1][c->K];   // every tile of every colour (128 x 8 configuration)
+        transpose_tile_kernel<128, 8><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p, c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, c->d_valT.p, c->d_pd.p);
+    } else {
+        transpose_values_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, c->n, c->d_valT.p, c->d_pd.p);
+    }
     LAUNCHED(c);
     c->committed = true;
 }
 
 static void launch_sweep_colors(Ctx *c) {
-    for (int col = 0; col < c->tail_color; col++) {
+    for (int col = 0; col < c->K; col++) {
         const int q0 = c->cstart[col], q1 = c->cstart[col + 1];
         if (c->sweep_variant == 3) {
-            gibbs_color_kernel<<<(q1 - q0 + 255) / 256, 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, q0, q1);
+            gibbs_color_kernel<<<(q1 - q0 + 255) / 256, 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, q0, q1);
             continue;
         }
-        const int cfg = c->sweep_variant == 1 ? 0 : 1;   // also the fallback when the persistent kernel's table would overflow
+        const bool pdl = (c->sweep_variant == 6 || c->sweep_variant == 7);
+        const int cfg = (c->sweep_variant == 1 || c->sweep_variant == 7) ? 0 : 1;   // 128x8 is also the persistent kernel's fallback
         const int t0 = c->tile_ptr[cfg][col], nt = c->tile_ptr[cfg][col + 1] - t0;
-        if (cfg == 0)
-            gibbs_tile_kernel<256, 8><<<nt, 256, 0, c->stream>>>(c->d_tiles[0].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
-        else
-            gibbs_tile_kernel<128, 8><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
+        if (!pdl) {
+            if (cfg == 0)
+                gibbs_tile_kernel<256, 8, false><<<nt, 256, 0, c->stream>>>(c->d_tiles[0].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
+            else
+                gibbs_tile_kernel<128, 8, false><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
+        } else {
+            // programmatic dependent launch: colour c+1 may start its r-independent prologue while colour c is running; the
+            // first colour of a sweep is an ordinary launch (it must see the advance kernel's counter update)
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(nt);
+            lc.blockDim = dim3(cfg == 0 ? 256 : 128);
+            lc.dynamicSmemBytes = 0;
+            lc.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at;
+            lc.numAttrs = (col > 0) ? 1 : 0;
+            const int4 *tl = c->d_tiles[cfg].p + t0;
+            if (cfg == 0)
+                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<256, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
+            else
+                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
+        }
     }
-    if (c->tail_color < c->K)
-        gibbs_tail_kernel<<<1, 1024, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_i2g.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, c->d_cstart.p, c->tail_color, c->K);
     advance_sweep_kernel<<<1, 1, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n);
 }
 
-static int sweep_launches(Ctx *c) { return c->tail_color + (c->tail_color < c->K ? 1 : 0) + 1; }
+static int sweep_launches(Ctx *c) { return c->K + 1; }
 
 static bool sweep_is_persistent(Ctx *c) { return c->sweep_variant == 0 || c->sweep_variant == 4 || c->sweep_variant == 5; }
 
@@ -364,13 +388,13 @@ static void op_sweeps(Ctx *c, int n_sweeps, unsigned long long sweep_in_call) {
         const int *tile_ptr = c->d_tile_ptr[cfg].p;
         int K = c->K, ns = n_sweeps;
         unsigned long long sc0 = c->sweep_counter + sweep_in_call, zoff0 = sweep_in_call * (unsigned long long)c->n, nsites = (unsigned long long)c->n;
-        const int *colptr = c->d_colptr.p, *crow = c->d_crow.p, *zpos = c->d_zpos.p, *gid = c->d_i2g.p;
+        const int *colptr = c->d_colptr.p, *crow = c->d_crow.p, *zpos = c->d_zpos.p, *gid = c->d_gid.p, *psite = c->d_psite.p;
         const double *valT = c->d_valT.p, *pd = c->d_pd.p, *nobs = c->d_nobs.p, *S = c->d_S.p, *zbuf = c->d_zbuf.p;
         const SweepParams *spp = c->d_sp.p;
         double *field = c->d_field.p, *r = c->d_r.p;
         unsigned int *bar = c->d_bar.p;
         int dbg = c->debug_timeline ? 1 : 0;
-        void *args[] = {&tiles, &tile_ptr, &K, &ns, &sc0, &zoff0, &nsites, &colptr, &crow, &valT, &pd, &nobs, &S, &zpos, &gid, &zbuf, &spp, &field, &r, &bar, &dbg};
+        void *args[] = {&tiles, &tile_ptr, &K, &ns, &sc0, &zoff0, &nsites, &colptr, &crow, &valT, &pd, &nobs, &S, &zpos, &gid, &psite, &zbuf, &spp, &field, &r, &bar, &dbg};
         const int grid = c->persistent_grid[cfg];
         if (cfg == 0) CK(cudaLaunchCooperativeKernel((void *)gibbs_persistent_kernel<256, 8>, dim3(grid), dim3(256), args, 0, c->stream));
         else if (cfg == 1) CK(cudaLaunchCooperativeKernel((void *)gibbs_persistent_kernel<128, 8>, dim3(grid), dim3(128), args, 0, c->stream));
@@ -465,7 +489,7 @@ static void destroy_ctx(Ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->sweep_graph) cudaGraphExecDestroy(c->sweep_graph);
-    DevBuf<int> *ib[] = {&c->d_i2g, &c->d_g2i, &c->d_nn, &c->d_colptr, &c->d_crow, &c->d_csrc, &c->d_zpos, &c->d_lvl_rows, &c->d_lvl_ptr,
+    DevBuf<int> *ib[] = {&c->d_psite, &c->d_gid, &c->d_i2g, &c->d_g2i, &c->d_nn, &c->d_colptr, &c->d_crow, &c->d_csrc, &c->d_zpos, &c->d_lvl_rows, &c->d_lvl_ptr,
                          &c->d_lm, &c->d_optr, &c->d_oidx, &c->d_cstart, &c->d_partial_rows, &c->d_nbad};
     for (auto *b : ib) b->release();
     DevBuf<double> *db[] = {&c->d_locs, &c->d_tl, &c->d_linv[0], &c->d_linv[1], &c->d_valT, &c->d_pd, &c->d_nobs, &c->d_ymx, &c->d_S,
@@ -539,7 +563,7 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
 
     c = new Ctx();
     c->device = *device;
-    c->layout = (*layout == NNGP_LAYOUT_COLOR) ? NNGP_LAYOUT_COLOR : NNGP_LAYOUT_COLOR_MORTON;
+    c->layout = (*layout == NNGP_LAYOUT_COLOR || *layout == NNGP_LAYOUT_COLOR_MORTON) ? *layout : NNGP_LAYOUT_MORTON;
     c->n = n; c->d = d; c->m = m; c->M = M; c->n_obs = n_obs; c->covfun = *covfun_id;
     c->dt = (*covfun_id == NNGP_EXPONENTIAL_SPHERE || *covfun_id == NNGP_MATERN_SPHERE) ? 3 : d;
     c->ld = (n + 31) / 32 * 32;
@@ -566,9 +590,11 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
             REQUIRE(v >= 1 && v <= i, "NNarray[%d,%d] = %d is not a previous site", i + 1, j + 1, v);
         }
     }
-    // ---- internal numbering: colour-major; inside a colour reference order or Morton order ----
+    // ---- numberings ----
+    // storage order: NNGP_LAYOUT_MORTON = Z-curve over all sites; NNGP_LAYOUT_COLOR[_MORTON] = colour-major (reference / Z-curve
+    // order inside a colour).  processing order (sweep) = colour-major, storage order inside a colour.
     std::vector<uint32_t> key(n, 0);
-    if (c->layout == NNGP_LAYOUT_COLOR_MORTON) {
+    if (c->layout != NNGP_LAYOUT_COLOR) {
         double lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
         const int dd = std::min(d, 2);
         for (int k = 0; k < dd; k++)
@@ -585,26 +611,31 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
     }
     c->i2g.resize(n);
     std::iota(c->i2g.begin(), c->i2g.end(), 0);
+    const bool color_major_storage = (c->layout != NNGP_LAYOUT_MORTON);
     std::stable_sort(c->i2g.begin(), c->i2g.end(), [&](int a, int b) {
-        if (coloring[a] != coloring[b]) return coloring[a] < coloring[b];
+        if (color_major_storage && coloring[a] != coloring[b]) return coloring[a] < coloring[b];
         return key[a] < key[b];
     });
     c->g2i.resize(n);
     for (int q = 0; q < n; q++) c->g2i[c->i2g[q]] = q;
+    // processing order: storage ids sorted by colour (stable => storage order inside a colour)
+    std::vector<int> psite(n), pof(n);   // psite[p] = storage id of processing site p; pof = inverse
+    std::iota(psite.begin(), psite.end(), 0);
+    std::stable_sort(psite.begin(), psite.end(), [&](int a, int b) { return coloring[c->i2g[a]] < coloring[c->i2g[b]]; });
+    for (int p = 0; p < n; p++) pof[psite[p]] = p;
     c->cstart.assign(K + 1, 0);
     for (int i = 0; i < n; i++) c->cstart[coloring[i]]++;
     for (int k = 0; k < K; k++) c->cstart[k + 1] += c->cstart[k];
     // position of each site inside the reference's rnorm() hand-out order: colour 1..K, ascending reference index
-    std::vector<int> zpos(n);
+    std::vector<int> zpos(n), gid(n);
     {
         std::vector<int> next(c->cstart.begin(), c->cstart.end() - 1);
         std::vector<int> zg(n);
         for (int i = 0; i < n; i++) zg[i] = next[coloring[i] - 1]++;
-        for (int q = 0; q < n; q++) zpos[q] = zg[c->i2g[q]];
+        for (int p = 0; p < n; p++) { gid[p] = c->i2g[psite[p]]; zpos[p] = zg[gid[p]]; }
     }
-    c->tail_color = K;   // ncu: the single-CTA tail walk costs more (dependent cold misses) than one small launch per colour
 
-    // ---- row structure in internal numbering ----
+    // ---- row structure in storage numbering ----
     const int ld = c->ld;
     std::vector<int> nn((size_t)ld * M, -1);
     for (int q = 0; q < n; q++) {
@@ -620,19 +651,19 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
     std::vector<double> locs_int((size_t)n * d);
     for (int q = 0; q < n; q++)
         for (int k = 0; k < d; k++) locs_int[(size_t)q * d + k] = locs[(size_t)c->i2g[q] + (size_t)n * k];
-    // ---- transpose (CSC) structure ----
+    // ---- transpose (CSC) structure: columns in processing order, row ids in storage numbering ----
     std::vector<int> colptr(n + 1, 0);
     for (int q = 0; q < n; q++)
-        for (int j = 0; j < M; j++) { const int v = nn[(size_t)j * ld + q]; if (v >= 0) colptr[v + 1]++; }
-    for (int q = 0; q < n; q++) { c->max_col = std::max(c->max_col, colptr[q + 1]); colptr[q + 1] += colptr[q]; }
+        for (int j = 0; j < M; j++) { const int v = nn[(size_t)j * ld + q]; if (v >= 0) colptr[pof[v] + 1]++; }
+    for (int p = 0; p < n; p++) { c->max_col = std::max(c->max_col, colptr[p + 1]); colptr[p + 1] += colptr[p]; }
     c->nnz = colptr[n];
     std::vector<int> crow(c->nnz), csrc(c->nnz);
     {
         std::vector<int> pos(colptr.begin(), colptr.end() - 1);
-        for (int q = 0; q < n; q++)  // rows ascending => every column's entries are sorted by row
+        for (int q = 0; q < n; q++)  // rows ascending => every column's entries are sorted by (storage) row
             for (int j = 0; j < M; j++) {
                 const int v = nn[(size_t)j * ld + q];
-                if (v >= 0) { crow[pos[v]] = q; csrc[pos[v]] = j * ld + q; pos[v]++; }
+                if (v >= 0) { const int p = pof[v]; crow[pos[p]] = q; csrc[pos[p]] = j * ld + q; pos[p]++; }
             }
     }
     // ---- solve DAG levels ----
@@ -686,21 +717,22 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
             c->max_tiles[cfg] = std::max(c->max_tiles[cfg], c->tile_ptr[cfg][col + 1] - c->tile_ptr[cfg][col]);
         }
     }
-    // ---- observations ----
+    // ---- observations: lm in storage numbering (gathers of field); per-site lists / counts in processing order ----
     std::vector<int> lm(n_obs), optr(n + 1, 0), oidx(n_obs);
     for (int o = 0; o < n_obs; o++) {
         REQUIRE(locs_match[o] >= 1 && locs_match[o] <= n, "locs_match[%d] = %d out of range", o + 1, locs_match[o]);
         lm[o] = c->g2i[locs_match[o] - 1];
-        optr[lm[o] + 1]++;
+        optr[pof[lm[o]] + 1]++;
     }
     std::vector<double> nobs(n);
-    for (int q = 0; q < n; q++) { nobs[q] = optr[q + 1]; optr[q + 1] += optr[q]; }
+    for (int p = 0; p < n; p++) { nobs[p] = optr[p + 1]; optr[p + 1] += optr[p]; }
     {
         std::vector<int> pos(optr.begin(), optr.end() - 1);
-        for (int o = 0; o < n_obs; o++) oidx[pos[lm[o]]++] = o;
+        for (int o = 0; o < n_obs; o++) oidx[pos[pof[lm[o]]]++] = o;
     }
     // ---- upload ----
     cudaStream_t s = c->stream;
+    c->d_psite.upload(psite, s); c->d_gid.upload(gid, s);
     c->d_i2g.upload(c->i2g, s); c->d_g2i.upload(c->g2i, s); c->d_nn.upload(nn, s); c->d_colptr.upload(colptr, s);
     c->d_crow.upload(crow, s); c->d_csrc.upload(csrc, s); c->d_zpos.upload(zpos, s); c->d_lvl_rows.upload(lvl_rows, s);
     c->d_lvl_ptr.upload(c->lvl_ptr, s); c->d_lm.upload(lm, s); c->d_optr.upload(optr, s); c->d_oidx.upload(oidx, s);
@@ -764,10 +796,11 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
     use(c);
     CK(cudaStreamSynchronize(c->stream));
     switch (*key) {
-        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 5, "sweep variant must be 0..5"); c->sweep_variant = *value; break;
+        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 7, "sweep variant must be 0..7"); c->sweep_variant = *value; break;
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;
+        case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "commit variant must be 0..1"); c->commit_variant = *value; break;
         case NNGP_OPT_SOLVE_WINDOW_CTAS: REQUIRE(*value >= 0 && *value <= 4096, "solve window must be 0..4096 CTAs"); c->solve_window_ctas = *value; break;
         case NNGP_OPT_DEBUG_TIMELINE: c->debug_timeline = (*value != 0); break;
         case NNGP_OPT_SOLVE_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "solve sleep must be 0..100000 ns"); c->solve_sleep_ns = *value; break;
@@ -858,7 +891,9 @@ void nngp_precision_diag(const int *ctx_id, double *out, int *status) {
     NEED(c->have_slot(NNGP_SLOT_CURRENT), "nngp_precision_diag: no current factor");
     use(c);
     if (!c->committed) op_commit(c);
-    download_site_vector(c, c->d_pd.p, out);
+    scatter_f64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_tmp1.p, c->d_pd.p, c->d_psite.p, c->n);   // processing -> storage order
+    LAUNCHED(c);
+    download_site_vector(c, c->d_tmp1.p, out);
     ABI_END
 }
 
@@ -945,7 +980,7 @@ void nngp_sptmv(const int *ctx_id, const int *slot, const double *u, double *out
     NEED(c->have_slot(*slot), "nngp_sptmv: that slot holds no factor");
     use(c);
     upload_site_vector(c, u, c->d_tmp1.p);
-    sptmv_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_csrc.p, c->linv_slot(*slot), c->d_tmp1.p, c->n, c->d_tmp2.p);
+    sptmv_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_csrc.p, c->d_psite.p, c->linv_slot(*slot), c->d_tmp1.p, c->n, c->d_tmp2.p);
     LAUNCHED(c);
     download_site_vector(c, c->d_tmp2.p, out);
     ABI_END

@@ -53,8 +53,9 @@ extern "C" {
 #define NNGP_RNG_PHILOX 1   /* counter-based Philox4x32-10 keyed by (seed, sweep counter, global site id) */
 
 /* internal site layout (performance knob; results are layout-independent up to FP64 summation order) */
-#define NNGP_LAYOUT_COLOR 1        /* colour-major, reference order inside a colour */
-#define NNGP_LAYOUT_COLOR_MORTON 2 /* colour-major, Morton (Z-curve) order inside a colour */
+#define NNGP_LAYOUT_COLOR 1        /* vectors stored colour-major, reference order inside a colour */
+#define NNGP_LAYOUT_COLOR_MORTON 2 /* vectors stored colour-major, Morton (Z-curve) order inside a colour */
+#define NNGP_LAYOUT_MORTON 3       /* vectors stored in pure Z-curve order; the sweep walks them colour by colour (default) */
 
 /* ------------------------------------------------------------------------------------------------------------------
  * library / device
@@ -88,10 +89,11 @@ void nngp_ctx_create(const int *n, const int *d, const int *m, const double *loc
                      const int *device, const int *layout, int *ctx_id, int *status);
 void nngp_ctx_destroy(const int *ctx_id, int *status);
 /* performance knobs (results are identical up to FP64 summation order):
- *   NNGP_OPT_SWEEP_VARIANT 2 = one launch per colour, 128-thread CTAs x 8 entries/thread, replayed from a CUDA graph
- *                          (default); 1 = same with 256x8 tiles; 3 = one launch per colour, thread per site;
- *                          0 / 4 / 5 = persistent cooperative kernel (grid barrier between colours, next tile prefetched
- *                          across the barrier) with 256x8 / 256x4 / 128x8 tiles
+ *   NNGP_OPT_SWEEP_VARIANT 6 = one launch per colour, 128-thread CTAs x 8 entries/thread, chained with programmatic
+ *                          dependent launch (the r-independent prologue of colour c+1 overlaps colour c) and replayed from
+ *                          a CUDA graph (default); 7 = same with 256x8 tiles; 2 / 1 = the same tiles without PDL;
+ *                          3 = one launch per colour, thread per site; 0 / 4 / 5 = persistent cooperative kernel (grid
+ *                          barrier between colours, next tile prefetched across the barrier) with 256x8 / 256x4 / 128x8 tiles
  *   NNGP_OPT_SOLVE_VARIANT 0 = synchronisation-free single-launch triangular solve; 1 = one launch per DAG level
  *   NNGP_OPT_USE_GRAPH     1 = the colour launches of a sweep are replayed from a captured CUDA graph (default) */
 #define NNGP_OPT_SWEEP_VARIANT 1
@@ -100,6 +102,7 @@ void nngp_ctx_destroy(const int *ctx_id, int *status);
 #define NNGP_OPT_SOLVE_CTAS_PER_SM 4 /* window of the sync-free solve: n_sm * value * 256 rows in flight (default 1) */
 #define NNGP_OPT_SOLVE_SLEEP_NS 5    /* back-off between dependency polls (default 0) */
 #define NNGP_OPT_SOLVE_WINDOW_CTAS 7  /* absolute window of the sync-free solve in CTAs of 256 rows (0 = use per-SM setting) */
+#define NNGP_OPT_COMMIT_VARIANT 8     /* accept-branch transposition: 0 = tiled (default), 1 = thread per column */
 #define NNGP_OPT_DEBUG_TIMELINE 6    /* development aid: the persistent sweep kernel stamps %globaltimer per stage */
 void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);
 /* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,

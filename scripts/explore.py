@@ -29,7 +29,7 @@ def main():
     col = nb.greedy_coloring(nn)
     lm = np.arange(1, a.n + 1, dtype=np.int32)
     cp = [1.0, 0.05, 0.0] if a.covfun.startswith("exp") else [1.0, 0.05, 0.75, 0.0]
-    for layout in (nb.LAYOUT_COLOR_MORTON, nb.LAYOUT_COLOR):
+    for layout in (nb.LAYOUT_MORTON, nb.LAYOUT_COLOR_MORTON):
         ctx = nb.NNGPContext(locs, nn, col, lm, a.covfun, layout=layout)
         assert ctx.factor_build(cp) == 0
         ctx.factor_commit()
@@ -38,14 +38,14 @@ def main():
         ctx.obs_set(w + np.sqrt(0.1) * rng.standard_normal(a.n))
         ctx.gibbs_sweep(0.0, 0.0, np.log(0.1), 1, seed=1)
         print(f"layout={layout} n={a.n} m={a.m} colors={ctx.n_colors} levels={ctx.n_levels} nnz={ctx.nnz} max_col={ctx.max_col}")
-        for sv in (0, 4, 5, 1, 2, 3):
+        for sv in (0, 5, 1, 2, 6, 7):
             for g in ((1,) if sv in (0, 4, 5) else (1, 0)):
                 ctx.set_option("sweep_variant", sv)
                 ctx.set_option("use_graph", g)
                 ctx.time_op("gibbs_sweep", reps=3)
                 ms, nl = ctx.time_op("gibbs_sweep", reps=a.reps)
                 print(f"  sweep variant={sv} graph={g}: mean {ms.mean()*1e3:8.1f} us  min {ms.min()*1e3:8.1f} us  launches {nl}")
-        ctx.set_option("sweep_variant", 0)
+        ctx.set_option("sweep_variant", 6)
         ctx.set_option("use_graph", 1)
         for sv, win, slp in ((0, 18, 0), (0, 37, 0), (0, 74, 0), (0, 111, 0), (0, 148, 0), (0, 222, 0), (0, 296, 0), (0, 74, 50), (0, 148, 50)):
             ctx.set_option("solve_variant", sv)
@@ -58,6 +58,10 @@ def main():
         ctx.set_option("solve_ctas_per_sm", 1)
         ctx.set_option("solve_sleep_ns", 0)
         ctx.set_option("solve_variant", 0)
+        ctx.set_option("commit_variant", 1)
+        ms, nl = ctx.time_op("commit", reps=a.reps)
+        print(f"  commit (thread per column): mean {ms.mean()*1e3:8.1f} us")
+        ctx.set_option("commit_variant", 0)
         for op in ("loglik", "spmv", "factor_build", "commit", "sweep_loglik"):
             ctx.time_op(op, reps=2)
             ms, nl = ctx.time_op(op, reps=a.reps)

@@ -39,7 +39,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("covfun,d,m,cp", CASES)
-@pytest.mark.parametrize("layout", [nb.LAYOUT_COLOR, nb.LAYOUT_COLOR_MORTON])
+@pytest.mark.parametrize("layout", [nb.LAYOUT_COLOR, nb.LAYOUT_COLOR_MORTON, nb.LAYOUT_MORTON])
 def test_factor_and_products(covfun, d, m, cp, layout):
     P = make_problem(4000, m, d=d, seed=11)
     with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], covfun, layout=layout) as ctx:
@@ -105,7 +105,7 @@ def test_not_positive_definite_is_flagged_not_fatal():
         assert ctx.factor_build([1.0, 0.2, 0.0]) in (0, 1)   # flagged or a huge-but-finite row, never a crash
 
 
-@pytest.mark.parametrize("layout", [nb.LAYOUT_COLOR, nb.LAYOUT_COLOR_MORTON])
+@pytest.mark.parametrize("layout", [nb.LAYOUT_COLOR, nb.LAYOUT_COLOR_MORTON, nb.LAYOUT_MORTON])
 @pytest.mark.parametrize("m,n_extra,drop", [(10, 0, 0.0), (5, 300, 0.0), (10, 200, 0.3)])
 def test_chromatic_sweep_supplied_normals(layout, m, n_extra, drop):
     """Same normals in the reference's hand-out order => same field as update_Gaussian.R:257-275 written literally."""
@@ -253,3 +253,69 @@ def test_error_paths():
     bad[10, 1] = 50                                              # a "neighbour" that is not a previous site
     with pytest.raises(nb.NNGPError):
         nb.NNGPContext(P["locs"], bad, P["coloring"], P["locs_match"])
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("n,m", [(20000, 10), (3000, 5)])
+def test_every_sweep_variant_matches_the_reference_loop(variant, n, m):
+    """All kernel variants of the sweep (tiled launches, persistent cooperative kernel, PDL chain, thread-per-site) are the
+    same map given the same normals; multi-sweep launches included (n = 20000 gives several CTAs per colour)."""
+    P = make_problem(n, m, seed=77, n_extra_obs=n // 20)
+    cp = [1.0, 0.05, 0.0]
+    beta_0, ls, lnv = -0.2, 0.3, -0.9
+    Lo = O.vecchia_Linv(cp, "exponential_isotropic", P["locs"], P["NNarray"])
+    pd = O.precision_diag(Lo, P["NNarray"])
+    mu = np.full(P["n_obs"], beta_0)
+    n_sweeps = 3
+    z = P["rng"].standard_normal(n_sweeps * n)
+    f = P["field"].copy()
+    rs = O.residuals_sum(P["locs_match"], n, P["y"], mu)
+    for s in range(n_sweeps):
+        f = O.chromatic_sweep(Lo, P["NNarray"], P["coloring"], pd, P["obs_per_loc"], rs, beta_0, ls, lnv,
+                              z[s * n:(s + 1) * n], f, form="residual")
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.set_option("sweep_variant", variant)
+        ctx.factor_build(cp)
+        ctx.factor_commit()
+        ctx.field_set(P["field"])
+        ctx.obs_set(P["y"])
+        ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=n_sweeps, z=z)
+        assert rel_vec(ctx.field_get(), f) < TOL
+        # Philox draws are keyed by (seed, sweep counter, site): identical across variants
+        ctx.field_set(P["field"])
+        ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=2, seed=5)
+        a = ctx.field_get()
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], layout=nb.LAYOUT_COLOR) as ctx:
+        ctx.set_option("sweep_variant", 3)
+        ctx.factor_build(cp)
+        ctx.factor_commit()
+        ctx.field_set(P["field"])
+        ctx.obs_set(P["y"])
+        ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=n_sweeps, z=z)     # same per-context sweep counter as above
+        ctx.field_set(P["field"])
+        ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=2, seed=5)
+        assert rel_vec(ctx.field_get(), a) < TOL
+
+
+@pytest.mark.parametrize("solve_variant", [0, 1])
+def test_both_solve_variants(solve_variant):
+    P = make_problem(30000, 10, seed=13)
+    cp = [1.0, 0.05, 0.0]
+    Lo = O.vecchia_Linv(cp, "exponential_isotropic", P["locs"], P["NNarray"])
+    v = P["rng"].standard_normal(P["n"])
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.set_option("solve_variant", solve_variant)
+        ctx.factor_build(cp)
+        assert rel_vec(ctx.sptrsv(v), O.sparse_chol_solve(Lo, P["NNarray"], v)) < 1e-9
+
+
+@pytest.mark.parametrize("commit_variant", [0, 1])
+def test_both_transposition_variants(commit_variant):
+    P = make_problem(20000, 10, seed=14)
+    cp = [1.0, 0.05, 0.0]
+    Lo = O.vecchia_Linv(cp, "exponential_isotropic", P["locs"], P["NNarray"])
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.set_option("commit_variant", commit_variant)
+        ctx.factor_build(cp)
+        ctx.factor_commit()
+        assert rel_vec(ctx.precision_diag(), O.precision_diag(Lo, P["NNarray"])) < TOL
