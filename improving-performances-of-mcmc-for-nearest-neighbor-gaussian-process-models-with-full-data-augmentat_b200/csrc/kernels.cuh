@@ -250,9 +250,11 @@ __device__ __forceinline__ double row_dot(const int *__restrict__ nn, const doub
 template <int MT>
 __global__ void __launch_bounds__(256) loglik_partial_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
                                                              const double *__restrict__ field, double shift, int n, int ld, int M,
+                                                             const unsigned char *__restrict__ row_mask,
                                                              double2 *__restrict__ partials) {
     double acc[2] = {0.0, 0.0};
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        if (row_mask && !row_mask[q]) continue;   // sharded field: ghost rows are summed by the rank that owns them
         const double u = row_dot<MT>(nn, linv, field, shift, q, ld, M);
         acc[0] += log(linv[q]);
         acc[1] += u * u;
@@ -292,9 +294,11 @@ __global__ void __launch_bounds__(256) spmv_rows_kernel(const int *__restrict__ 
 template <int MT>
 __global__ void __launch_bounds__(256) beta0_partial_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
                                                             const double *__restrict__ field, int n, int ld, int M,
+                                                            const unsigned char *__restrict__ row_mask,
                                                             double2 *__restrict__ partials) {
     double acc[2] = {0.0, 0.0};
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        if (row_mask && !row_mask[q]) continue;
         double u = 0.0, v = 0.0;
         for (int j = 0; j < (MT > 0 ? MT : M); j++) {
             const int id = nn[(size_t)j * ld + q];
@@ -331,9 +335,9 @@ __global__ void scatter_f64_kernel(double *__restrict__ dst, const double *__res
 // accept branch: gather the CSC values of the new current factor and its precision_diag in one pass
 // (replaces Matrix::sparseMatrix assembly + the (x^2) %*% indicator product, update_Gaussian.R:73-74,141-142,196-197)
 __global__ void __launch_bounds__(256) transpose_values_kernel(const int *__restrict__ colptr, const int *__restrict__ csrc,
-                                                               const double *__restrict__ linv, int n, double *__restrict__ valT,
-                                                               double *__restrict__ pd) {
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+                                                               const double *__restrict__ linv, int q0, int q1,
+                                                               double *__restrict__ valT, double *__restrict__ pd) {
+    for (int q = q0 + blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += gridDim.x * blockDim.x) {
         double s = 0.0;
         for (int k = colptr[q]; k < colptr[q + 1]; k++) {
             const double v = linv[csrc[k]];
@@ -982,6 +986,30 @@ __global__ void __launch_bounds__(THREADS) gibbs_persistent_kernel(
         }
     }
     if (dbg && blockIdx.x == 0 && tid == 0) g_timeline[8191] = tl_n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// halo exchange of a sharded field, one colour at a time: pack the new values of the owned boundary sites of
+// the colour, (NCCL send/recv between the two kernels), then apply what arrived to the local ghost copies: the ghost value
+// is replaced and r is patched along the ghost site's local column exactly as an owned update would have done.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void halo_pack_kernel(const int *__restrict__ send_storage, const double *__restrict__ field, int k0, int k1,
+                                 double *__restrict__ sendbuf) {
+    const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < k1) sendbuf[k] = field[send_storage[k]];
+}
+
+__global__ void halo_apply_kernel(const int *__restrict__ recv_proc, const double *__restrict__ recvbuf, int k0, int k1,
+                                  const int *__restrict__ colptr, const int *__restrict__ crow, const double *__restrict__ valT,
+                                  const int *__restrict__ psite, double *__restrict__ field, double *__restrict__ r) {
+    const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    const int p = recv_proc[k];
+    const int sq = psite[p];
+    const double f_new = recvbuf[k];
+    const double delta = f_new - field[sq];
+    field[sq] = f_new;
+    for (int e = colptr[p]; e < colptr[p + 1]; e++) r[crow[e]] += valT[e] * delta;   // same-colour sites never share a row
 }
 
 __global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n) {

@@ -4,6 +4,7 @@
 // (current + proposal factor, field, residual r = L^-1 (field - beta_0)).  Only scalars and explicitly requested vectors
 // cross PCIe.  There is no CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -47,6 +48,7 @@ struct CudaFail {};
     } while (0)
 #define LAUNCHED(c) do { nngp::g_launches.fetch_add(1, std::memory_order_relaxed); (c)->launches_in_op++; } while (0)
 
+struct NcclFail {};
 struct ArgFail {};
 #define REQUIRE(cond, ...)                    \
     do {                                      \
@@ -56,6 +58,49 @@ struct ArgFail {};
         }                                     \
     } while (0)
 struct StateFail {};
+
+// ------------------------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (dlopen): the library must not pin a second copy of libnccl.so.2 next to the one a host
+// process (e.g. PyTorch) may already have loaded, so nothing is linked; whichever libnccl.so.2 is resident is used.
+// Only the sharded contexts need it: per-colour halo exchange (ncclSend / ncclRecv) and scalar all-reduces.
+// ------------------------------------------------------------------------------------------------------------------
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    typedef void *Comm;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*Send)(const void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static NcclApi g_nccl;
+static const int kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+static void nccl_load() {
+    if (g_nccl.ok) return;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { set_error("cannot load libnccl.so.2: %s", dlerror()); throw NcclFail(); }
+#define NCCL_SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { set_error("libnccl: missing %s", name); throw NcclFail(); }
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId") NCCL_SYM(CommInitRank, "ncclCommInitRank") NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    NCCL_SYM(Send, "ncclSend") NCCL_SYM(Recv, "ncclRecv") NCCL_SYM(GroupStart, "ncclGroupStart") NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    NCCL_SYM(AllReduce, "ncclAllReduce") NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+    g_nccl.ok = true;
+}
+#define NCK(call)                                                                                              \
+    do {                                                                                                       \
+        int r__ = (call);                                                                                      \
+        if (r__ != 0) {                                                                                        \
+            nngp::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, nngp::g_nccl.GetErrorString(r__));    \
+            throw nngp::NcclFail();                                                                            \
+        }                                                                                                      \
+    } while (0)
 
 // ------------------------------------------------------------------------------------------------------------------
 // context
@@ -85,6 +130,13 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n = 0, d = 0, m = 0, M = 0, ld = 0, n_obs = 0, covfun = 0, dt = 0, K = 0, n_levels = 0, max_col = 0;
+    // ---- sharding (one spatial block of a larger field) ----
+    bool sharded = false;
+    int world = 1, rank = 0, n_owned = 0;
+    long long n_global = 0;            // sites of the whole field (= n on an unsharded context)
+    NcclApi::Comm comm = nullptr;
+    std::vector<int> send_ptr, recv_ptr;   // [(colour, peer)] segments of the packed halo buffers
+    std::vector<int> gstart;               // processing-index range of the ghost sites of each colour
     long long nnz = 0;
     int n_sm = 148;
     long long launches_in_op = 0;
@@ -115,6 +167,9 @@ struct Ctx {
     DevBuf<double> d_locs, d_tl, d_linv[2], d_valT, d_pd, d_nobs, d_ymx, d_S, d_field, d_newfield, d_r, d_tmp1, d_tmp2, d_io,
         d_zbuf, d_partials, d_scalars, d_flush;
     DevBuf<SweepParams> d_sp;
+    DevBuf<int> d_send_storage, d_recv_proc;
+    DevBuf<double> d_sendbuf, d_recvbuf;
+    DevBuf<unsigned char> d_owned;         // per storage id: 1 = owned row (reductions skip ghost rows)
     DevBuf<int4> d_tiles[3];
     DevBuf<int> d_tile_ptr[3];
     DevBuf<int> d_rows_padded, d_ticket;
@@ -287,13 +342,18 @@ static void op_factor_build(Ctx *c, int slot, const CovConst &cc) {
 
 static const int kReduceBlocks = 148 * 8;
 
+// sharded field: every rank holds the partial sums of its owned rows / observations; the scalars are summed over ranks
+static void allreduce_scalars(Ctx *c, int off, int count);
+static void op_halo_exchange(Ctx *c, int col);
+
 // partial sums -> d_scalars[off..off+1]
 static void op_loglik_sums(Ctx *c, const double *linv, const double *field, double shift, int scal_off) {
     const int blocks = std::min(kReduceBlocks, (c->n + 255) / 256);
-    DISPATCH_MT(c->M, (loglik_partial_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, field, shift, c->n, c->ld, c->M, reinterpret_cast<double2 *>(c->d_partials.p))));
+    DISPATCH_MT(c->M, (loglik_partial_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, field, shift, c->n, c->ld, c->M, c->sharded ? c->d_owned.p : nullptr, reinterpret_cast<double2 *>(c->d_partials.p))));
     LAUNCHED(c);
     reduce_partials_kernel<2><<<1, 1024, 0, c->stream>>>(c->d_partials.p, blocks, c->d_scalars.p + scal_off);
     LAUNCHED(c);
+    allreduce_scalars(c, scal_off, 2);
 }
 
 static void op_spmv(Ctx *c, const double *linv, const double *v, double shift, double *out) {
@@ -325,13 +385,21 @@ static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, do
 }
 
 static void op_commit(Ctx *c) {
+    const int n_tiled = c->sharded ? c->n_owned : c->n;   // tiles cover the owned sites; ghost columns follow in processing order
     if (c->commit_variant == 0) {
         const int nt = c->tile_ptr[1][c->K];   // every tile of every colour (128 x 8 configuration)
-        transpose_tile_kernel<128, 8><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p, c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, c->d_valT.p, c->d_pd.p);
+        if (nt > 0) {
+            transpose_tile_kernel<128, 8><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p, c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, c->d_valT.p, c->d_pd.p);
+            LAUNCHED(c);
+        }
     } else {
-        transpose_values_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, c->n, c->d_valT.p, c->d_pd.p);
+        transpose_values_kernel<<<grid_for(c, n_tiled, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, 0, n_tiled, c->d_valT.p, c->d_pd.p);
+        LAUNCHED(c);
     }
-    LAUNCHED(c);
+    if (n_tiled < c->n) {   // values of the ghost sites' local columns (halo_apply_kernel patches r along them)
+        transpose_values_kernel<<<grid_for(c, c->n - n_tiled, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, n_tiled, c->n, c->d_valT.p, c->d_pd.p);
+        LAUNCHED(c);
+    }
     c->committed = true;
 }
 
@@ -370,7 +438,7 @@ static void launch_sweep_colors(Ctx *c) {
                 CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
         }
     }
-    advance_sweep_kernel<<<1, 1, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n);
+    advance_sweep_kernel<<<1, 1, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global);
 }
 
 static int sweep_launches(Ctx *c) { return c->K + 1; }
@@ -380,6 +448,24 @@ static bool sweep_is_persistent(Ctx *c) { return c->sweep_variant == 0 || c->swe
 // n_sweeps sweeps over all colours; scalar parameters are read from d_sp, the sweep counter / normals offset are passed in
 static void op_sweeps(Ctx *c, int n_sweeps, unsigned long long sweep_in_call) {
     if (n_sweeps <= 0) return;
+    if (c->sharded) {
+        // one spatial block of a larger field: per colour, sweep the owned sites, then exchange the boundary values with the
+        // peers that hold them as ghosts (NCCL send/recv over NVLink) and patch the local residual for what arrived
+        for (int s = 0; s < n_sweeps; s++) {
+            for (int col = 0; col < c->K; col++) {
+                const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
+                if (nt > 0) {
+                    gibbs_tile_kernel<128, 8, false><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
+                    LAUNCHED(c);
+                }
+                op_halo_exchange(c, col);
+            }
+            advance_sweep_kernel<<<1, 1, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global);
+            LAUNCHED(c);
+        }
+        CK(cudaGetLastError());
+        return;
+    }
     const int pcfg = c->sweep_variant == 0 ? 0 : (c->sweep_variant == 5 ? 1 : 2);
     if (sweep_is_persistent(c) && c->persistent_ok[pcfg]) {
         const int cfg = pcfg;
@@ -387,7 +473,7 @@ static void op_sweeps(Ctx *c, int n_sweeps, unsigned long long sweep_in_call) {
         const int4 *tiles = c->d_tiles[cfg].p;
         const int *tile_ptr = c->d_tile_ptr[cfg].p;
         int K = c->K, ns = n_sweeps;
-        unsigned long long sc0 = c->sweep_counter + sweep_in_call, zoff0 = sweep_in_call * (unsigned long long)c->n, nsites = (unsigned long long)c->n;
+        unsigned long long sc0 = c->sweep_counter + sweep_in_call, zoff0 = sweep_in_call * (unsigned long long)c->n_global, nsites = (unsigned long long)c->n_global;
         const int *colptr = c->d_colptr.p, *crow = c->d_crow.p, *zpos = c->d_zpos.p, *gid = c->d_gid.p, *psite = c->d_psite.p;
         const double *valT = c->d_valT.p, *pd = c->d_pd.p, *nobs = c->d_nobs.p, *S = c->d_S.p, *zbuf = c->d_zbuf.p;
         const SweepParams *spp = c->d_sp.p;
@@ -452,7 +538,7 @@ static void check_solve_flag(Ctx *c) {
 }
 
 static double ll_from_sums(Ctx *c, double sum_log, double sum_sq, double log_scale) {
-    return sum_log - c->n * 0.5 * log_scale - 0.5 * sum_sq / std::exp(log_scale);
+    return sum_log - (double)c->n_global * 0.5 * log_scale - 0.5 * sum_sq / std::exp(log_scale);
 }
 
 static void op_obs_sq(Ctx *c, const double *fnew, const double *f, int scal_off) {
@@ -461,14 +547,47 @@ static void op_obs_sq(Ctx *c, const double *fnew, const double *f, int scal_off)
     LAUNCHED(c);
     reduce_partials_kernel<2><<<1, 1024, 0, c->stream>>>(c->d_partials.p, blocks, c->d_scalars.p + scal_off);
     LAUNCHED(c);
+    allreduce_scalars(c, scal_off, 2);
 }
 
 static void op_beta0_sums(Ctx *c, int scal_off) {
     const int blocks = std::min(kReduceBlocks, (c->n + 255) / 256);
-    DISPATCH_MT(c->M, (beta0_partial_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, c->d_linv[c->cur].p, c->d_field.p, c->n, c->ld, c->M, reinterpret_cast<double2 *>(c->d_partials.p))));
+    DISPATCH_MT(c->M, (beta0_partial_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, c->d_linv[c->cur].p, c->d_field.p, c->n, c->ld, c->M, c->sharded ? c->d_owned.p : nullptr, reinterpret_cast<double2 *>(c->d_partials.p))));
     LAUNCHED(c);
     reduce_partials_kernel<2><<<1, 1024, 0, c->stream>>>(c->d_partials.p, blocks, c->d_scalars.p + scal_off);
     LAUNCHED(c);
+    allreduce_scalars(c, scal_off, 2);
+}
+
+static void allreduce_scalars(Ctx *c, int off, int count) {
+    if (!c->sharded || c->world == 1 || !c->comm) return;   // without a communicator the caller sums the per-rank partials
+    NCK(g_nccl.AllReduce(c->d_scalars.p + off, c->d_scalars.p + off, (size_t)count, kNcclFloat64, kNcclSum, c->comm, c->stream));
+}
+
+// halo exchange for colour `col` (0-based) of a sharded field
+static void op_halo_exchange(Ctx *c, int col) {
+    if (!c->sharded || c->world == 1) return;
+    if (!c->comm) { set_error("this sharded context has no NCCL communicator: drive it with the nngp_shard_* colour-stepping entry points"); throw StateFail(); }
+    const int W = c->world;
+    const int s0 = c->send_ptr[(size_t)col * W], s1 = c->send_ptr[(size_t)(col + 1) * W];
+    const int r0 = c->recv_ptr[(size_t)col * W], r1 = c->recv_ptr[(size_t)(col + 1) * W];
+    if (s1 > s0) {
+        halo_pack_kernel<<<(s1 - s0 + 255) / 256, 256, 0, c->stream>>>(c->d_send_storage.p, c->d_field.p, s0, s1, c->d_sendbuf.p);
+        LAUNCHED(c);
+    }
+    NCK(g_nccl.GroupStart());
+    for (int h = 0; h < W; h++) {
+        if (h == c->rank) continue;
+        const int a = c->send_ptr[(size_t)col * W + h], b = c->send_ptr[(size_t)col * W + h + 1];
+        const int ra = c->recv_ptr[(size_t)col * W + h], rb = c->recv_ptr[(size_t)col * W + h + 1];
+        if (b > a) NCK(g_nccl.Send(c->d_sendbuf.p + a, (size_t)(b - a), kNcclFloat64, h, c->comm, c->stream));
+        if (rb > ra) NCK(g_nccl.Recv(c->d_recvbuf.p + ra, (size_t)(rb - ra), kNcclFloat64, h, c->comm, c->stream));
+    }
+    NCK(g_nccl.GroupEnd());
+    if (r1 > r0) {
+        halo_apply_kernel<<<(r1 - r0 + 255) / 256, 256, 0, c->stream>>>(c->d_recv_proc.p, c->d_recvbuf.p, r0, r1, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_psite.p, c->d_field.p, c->d_r.p);
+        LAUNCHED(c);
+    }
 }
 
 static void ensure_zbuf(Ctx *c, size_t count) {
@@ -489,6 +608,8 @@ static void destroy_ctx(Ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->sweep_graph) cudaGraphExecDestroy(c->sweep_graph);
+    if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    c->d_send_storage.release(); c->d_recv_proc.release(); c->d_sendbuf.release(); c->d_recvbuf.release(); c->d_owned.release();
     DevBuf<int> *ib[] = {&c->d_psite, &c->d_gid, &c->d_i2g, &c->d_g2i, &c->d_nn, &c->d_colptr, &c->d_crow, &c->d_csrc, &c->d_zpos, &c->d_lvl_rows, &c->d_lvl_ptr,
                          &c->d_lm, &c->d_optr, &c->d_oidx, &c->d_cstart, &c->d_partial_rows, &c->d_nbad};
     for (auto *b : ib) b->release();
@@ -519,6 +640,7 @@ using namespace nngp;
     catch (const nngp::ArgFail &) { if (status) *status = NNGP_ERR_ARG; }     \
     catch (const nngp::CudaFail &) { if (status) *status = NNGP_ERR_CUDA; }   \
     catch (const nngp::StateFail &) { if (status) *status = NNGP_ERR_STATE; } \
+    catch (const nngp::NcclFail &) { if (status) *status = NNGP_ERR_NCCL; } \
     catch (const std::bad_alloc &) { nngp::set_error("host allocation failed"); if (status) *status = NNGP_ERR_ALLOC; } \
     catch (...) { nngp::set_error("unexpected exception"); if (status) *status = NNGP_ERR_ARG; }
 #define NEED(cond, msg) do { if (!(cond)) { nngp::set_error(msg); throw nngp::StateFail(); } } while (0)
@@ -546,12 +668,19 @@ void nngp_device_count(int *count, int *status) {
     ABI_END
 }
 
-void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *locs, const int *NNarray, const int *coloring,
-                     const int *n_obs_, const int *locs_match, const int *covfun_id, const int *device, const int *layout,
-                     int *ctx_id, int *status) {
+struct ShardArgs {
+    const int *owned, *global_id, *global_zpos, *send_site, *send_ptr, *recv_site, *recv_ptr;
+    int n_colors, world, rank;
+    long long n_global;
+    const char *comm_id;
+};
+
+static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const double *locs, const int *NNarray, const int *coloring,
+                            const int *n_obs_, const int *locs_match, const int *covfun_id, const int *device, const int *layout,
+                            const ShardArgs *sh, int *ctx_id, int *status) {
     Ctx *c = nullptr;
     ABI_BEGIN
-    REQUIRE(n_ && d_ && m_ && locs && NNarray && coloring && n_obs_ && locs_match && covfun_id && device && layout && ctx_id, "nngp_ctx_create: null argument");
+    REQUIRE(n_ && d_ && m_ && locs && NNarray && coloring && n_obs_ && (locs_match || *n_obs_ == 0) && covfun_id && device && layout && ctx_id, "nngp_ctx_create: null argument");
     const int n = *n_, d = *d_, m = *m_, M = m + 1, n_obs = *n_obs_;
     REQUIRE(n >= 1 && d >= 1 && d <= 4 && m >= 1 && m <= 31 && n_obs >= 0, "nngp_ctx_create: need n>=1, 1<=d<=4, 1<=m<=31 (got n=%d d=%d m=%d)", n, d, m);
     REQUIRE(*covfun_id >= 0 && *covfun_id <= 7, "unknown covfun_id %d", *covfun_id);
@@ -579,7 +708,15 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
     // ---- validate structure, colour classes ----
     int K = 0;
     for (int i = 0; i < n; i++) { REQUIRE(coloring[i] >= 1, "coloring[%d] = %d (colours are 1..K)", i, coloring[i]); K = std::max(K, coloring[i]); }
+    if (sh) {   // a shard sees only some of the field's colours but must walk all of them in step with its peers
+        REQUIRE(sh->n_colors >= K && sh->world >= 1 && sh->rank >= 0 && sh->rank < sh->world && sh->owned && sh->global_id && sh->global_zpos && sh->send_ptr && sh->recv_ptr && sh->comm_id,
+                "nngp_ctx_create_sharded: bad sharding arguments");
+        K = sh->n_colors;
+        c->sharded = true; c->world = sh->world; c->rank = sh->rank;
+    }
+    c->n_global = sh ? sh->n_global : n;
     c->K = K;
+    auto is_ghost = [&](int ref) { return sh != nullptr && sh->owned[ref] == 0; };
     for (int i = 0; i < n; i++) {
         REQUIRE(NNarray[i] == i + 1, "NNarray[%d,1] must be the row itself", i + 1);
         bool seen_na = false;
@@ -621,18 +758,32 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
     // processing order: storage ids sorted by colour (stable => storage order inside a colour)
     std::vector<int> psite(n), pof(n);   // psite[p] = storage id of processing site p; pof = inverse
     std::iota(psite.begin(), psite.end(), 0);
-    std::stable_sort(psite.begin(), psite.end(), [&](int a, int b) { return coloring[c->i2g[a]] < coloring[c->i2g[b]]; });
+    // (owned sites colour by colour, then -- sharded contexts only -- the ghost sites colour by colour)
+    std::stable_sort(psite.begin(), psite.end(), [&](int a, int b) {
+        const int ra = c->i2g[a], rb = c->i2g[b];
+        const bool ga = is_ghost(ra), gb = is_ghost(rb);
+        if (ga != gb) return gb;
+        return coloring[ra] < coloring[rb];
+    });
     for (int p = 0; p < n; p++) pof[psite[p]] = p;
     c->cstart.assign(K + 1, 0);
-    for (int i = 0; i < n; i++) c->cstart[coloring[i]]++;
+    c->gstart.assign(K + 1, 0);
+    for (int i = 0; i < n; i++) (is_ghost(i) ? c->gstart : c->cstart)[coloring[i]]++;
     for (int k = 0; k < K; k++) c->cstart[k + 1] += c->cstart[k];
+    c->n_owned = c->cstart[K];
+    c->gstart[0] = c->n_owned;
+    for (int k = 0; k < K; k++) c->gstart[k + 1] += c->gstart[k];
     // position of each site inside the reference's rnorm() hand-out order: colour 1..K, ascending reference index
     std::vector<int> zpos(n), gid(n);
     {
-        std::vector<int> next(c->cstart.begin(), c->cstart.end() - 1);
-        std::vector<int> zg(n);
-        for (int i = 0; i < n; i++) zg[i] = next[coloring[i] - 1]++;
-        for (int p = 0; p < n; p++) { gid[p] = c->i2g[psite[p]]; zpos[p] = zg[gid[p]]; }
+        if (sh) {   // Philox keys and the position in the rnorm() hand-out order refer to the WHOLE field
+            for (int p = 0; p < n; p++) { const int ref = c->i2g[psite[p]]; gid[p] = sh->global_id[ref]; zpos[p] = sh->global_zpos[ref]; }
+        } else {
+            std::vector<int> next(c->cstart.begin(), c->cstart.end() - 1);
+            std::vector<int> zg(n);
+            for (int i = 0; i < n; i++) zg[i] = next[coloring[i] - 1]++;
+            for (int p = 0; p < n; p++) { gid[p] = c->i2g[psite[p]]; zpos[p] = zg[gid[p]]; }
+        }
     }
 
     // ---- row structure in storage numbering ----
@@ -767,6 +918,36 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
     c->d_newfield.alloc(n); c->d_r.alloc(n); c->d_tmp1.alloc(n); c->d_tmp2.alloc(n); c->d_io.alloc((size_t)std::max(n, n_obs));
     c->d_zbuf.alloc(n); c->d_partials.alloc((size_t)kReduceBlocks * 4); c->d_scalars.alloc(64); c->d_sp.alloc(1);
     CK(cudaMemsetAsync(c->d_S.p, 0, sizeof(double) * n, s));
+    if (sh) {
+        const int W = sh->world;
+        c->send_ptr.assign(sh->send_ptr, sh->send_ptr + (size_t)K * W + 1);
+        c->recv_ptr.assign(sh->recv_ptr, sh->recv_ptr + (size_t)K * W + 1);
+        std::vector<int> send_storage(c->send_ptr.back()), recv_proc(c->recv_ptr.back());
+        for (size_t k = 0; k < send_storage.size(); k++) {
+            const int ref = sh->send_site[k] - 1;
+            REQUIRE(ref >= 0 && ref < n && sh->owned[ref], "send_site[%d] is not an owned local site", (int)k + 1);
+            send_storage[k] = c->g2i[ref];
+        }
+        for (size_t k = 0; k < recv_proc.size(); k++) {
+            const int ref = sh->recv_site[k] - 1;
+            REQUIRE(ref >= 0 && ref < n && !sh->owned[ref], "recv_site[%d] is not a ghost site", (int)k + 1);
+            recv_proc[k] = pof[c->g2i[ref]];
+        }
+        std::vector<unsigned char> owned_storage(n);
+        for (int q = 0; q < n; q++) owned_storage[q] = sh->owned[c->i2g[q]] ? 1 : 0;
+        c->d_send_storage.upload(send_storage, s);
+        c->d_recv_proc.upload(recv_proc, s);
+        c->d_owned.upload(owned_storage, s);
+        c->d_sendbuf.alloc(std::max<size_t>(send_storage.size(), 1));
+        c->d_recvbuf.alloc(std::max<size_t>(recv_proc.size(), 1));
+        CK(cudaStreamSynchronize(s));
+        if (W > 1 && sh->comm_id[0] != '\0') {   // collective: every rank of the field creates its context at the same time
+            nccl_load();
+            NcclApi::UniqueId id;
+            std::memcpy(id.internal, sh->comm_id, 128);
+            NCK(g_nccl.CommInitRank(&c->comm, W, id, sh->rank));
+        }
+    }
     CK(cudaStreamSynchronize(s));   // host vectors go out of scope below
     {
         std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -779,6 +960,32 @@ void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *
     c = nullptr;
     ABI_END
     if (c) destroy_ctx(c);
+}
+
+void nngp_ctx_create(const int *n_, const int *d_, const int *m_, const double *locs, const int *NNarray, const int *coloring,
+                     const int *n_obs_, const int *locs_match, const int *covfun_id, const int *device, const int *layout,
+                     int *ctx_id, int *status) {
+    create_ctx_impl(n_, d_, m_, locs, NNarray, coloring, n_obs_, locs_match, covfun_id, device, layout, nullptr, ctx_id, status);
+}
+
+void nngp_comm_unique_id(char *id128, int *status) {
+    ABI_BEGIN
+    REQUIRE(id128 != nullptr, "nngp_comm_unique_id: null buffer");
+    nccl_load();
+    NcclApi::UniqueId id;
+    NCK(g_nccl.GetUniqueId(&id));
+    std::memcpy(id128, id.internal, 128);
+    ABI_END
+}
+
+void nngp_ctx_create_sharded(const int *n_, const int *d_, const int *m_, const double *locs, const int *NNarray, const int *coloring,
+                             const int *n_colors, const int *owned, const int *global_id, const int *global_zpos, const double *n_global,
+                             const int *n_obs_, const int *locs_match, const int *covfun_id, const int *device, const int *layout,
+                             const int *world, const int *rank, const int *send_site, const int *send_ptr, const int *recv_site,
+                             const int *recv_ptr, const char *comm_id128, int *ctx_id, int *status) {
+    if (!n_colors || !world || !rank || !n_global) { set_error("nngp_ctx_create_sharded: null argument"); if (status) *status = NNGP_ERR_ARG; return; }
+    ShardArgs sh{owned, global_id, global_zpos, send_site, send_ptr, recv_site, recv_ptr, *n_colors, *world, *rank, (long long)*n_global, comm_id128};
+    create_ctx_impl(n_, d_, m_, locs, NNarray, coloring, n_obs_, locs_match, covfun_id, device, layout, &sh, ctx_id, status);
 }
 
 void nngp_ctx_destroy(const int *ctx_id, int *status) {
@@ -976,6 +1183,7 @@ void nngp_spmv(const int *ctx_id, const int *slot, const double *v, double *out,
 void nngp_sptmv(const int *ctx_id, const int *slot, const double *u, double *out, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
+    NEED(!c->sharded, "nngp_sptmv: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
     REQUIRE(slot && u && out && (*slot == 0 || *slot == 1), "nngp_sptmv: bad argument");
     NEED(c->have_slot(*slot), "nngp_sptmv: that slot holds no factor");
     use(c);
@@ -989,6 +1197,7 @@ void nngp_sptmv(const int *ctx_id, const int *slot, const double *u, double *out
 void nngp_sptrsv(const int *ctx_id, const int *slot, const double *b, double *x, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
+    NEED(!c->sharded, "nngp_sptrsv: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
     REQUIRE(slot && b && x && (*slot == 0 || *slot == 1), "nngp_sptrsv: bad argument");
     NEED(c->have_slot(*slot), "nngp_sptrsv: that slot holds no factor");
     use(c);
@@ -1010,7 +1219,7 @@ void nngp_gibbs_sweep(const int *ctx_id, const int *n_sweeps, const double *beta
     NEED(c->have_field && c->have_obs, "nngp_gibbs_sweep: field and observations must be set first");
     use(c);
     if (!c->committed) op_commit(c);
-    const size_t nz = (size_t)c->n * (size_t)std::max(1, *n_sweeps);
+    const size_t nz = (size_t)c->n_global * (size_t)std::max(1, *n_sweeps);   // normals are indexed by the position in the whole field
     if (*rng_mode == NNGP_RNG_SUPPLIED) {
         ensure_zbuf(c, nz);
         CK(cudaMemcpyAsync(c->d_zbuf.p, z, sizeof(double) * nz, cudaMemcpyHostToDevice, c->stream));
@@ -1023,10 +1232,96 @@ void nngp_gibbs_sweep(const int *ctx_id, const int *n_sweeps, const double *beta
     ABI_END
 }
 
+// ---- colour-stepping form of the sharded sweep: the caller moves the halo (any transport), the library does the rest ----
+void nngp_shard_sweep_begin(const int *ctx_id, const double *beta_0, const double *log_scale, const double *log_noise_variance,
+                            const int *rng_mode, const double *z, const double *seed, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(beta_0 && log_scale && log_noise_variance && rng_mode, "nngp_shard_sweep_begin: bad argument");
+    REQUIRE(*rng_mode == NNGP_RNG_PHILOX || (*rng_mode == NNGP_RNG_SUPPLIED && z != nullptr), "nngp_shard_sweep_begin: rng_mode 0 needs z");
+    NEED(c->sharded, "nngp_shard_sweep_begin: not a sharded context");
+    NEED(c->have_slot(NNGP_SLOT_CURRENT) && c->have_field && c->have_obs, "nngp_shard_sweep_begin: factor, field and observations must be set first");
+    use(c);
+    if (!c->committed) op_commit(c);
+    if (*rng_mode == NNGP_RNG_SUPPLIED) {
+        ensure_zbuf(c, (size_t)c->n_global);
+        CK(cudaMemcpyAsync(c->d_zbuf.p, z, sizeof(double) * (size_t)c->n_global, cudaMemcpyHostToDevice, c->stream));
+    }
+    set_sweep_params(c, *beta_0, *log_scale, *log_noise_variance, *rng_mode, seed ? *seed : 0.0);
+    refresh_r(c, *beta_0);
+    CK(cudaStreamSynchronize(c->stream));
+    ABI_END
+}
+
+void nngp_shard_sweep_colour(const int *ctx_id, const int *colour, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(colour && *colour >= 1 && *colour <= c->K, "nngp_shard_sweep_colour: colour out of range");
+    NEED(c->sharded, "nngp_shard_sweep_colour: not a sharded context");
+    use(c);
+    const int col = *colour - 1;
+    const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
+    if (nt > 0) {
+        gibbs_tile_kernel<128, 8, false><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
+        LAUNCHED(c);
+    }
+    CK(cudaGetLastError());
+    ABI_END
+}
+
+void nngp_shard_halo_get(const int *ctx_id, const int *colour, double *out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(colour && *colour >= 1 && *colour <= c->K, "nngp_shard_halo_get: colour out of range");
+    NEED(c->sharded, "nngp_shard_halo_get: not a sharded context");
+    use(c);
+    const int W = c->world, col = *colour - 1;
+    const int s0 = c->send_ptr[(size_t)col * W], s1 = c->send_ptr[(size_t)(col + 1) * W];
+    if (s1 > s0) {
+        REQUIRE(out != nullptr, "nngp_shard_halo_get: null buffer");
+        halo_pack_kernel<<<(s1 - s0 + 255) / 256, 256, 0, c->stream>>>(c->d_send_storage.p, c->d_field.p, s0, s1, c->d_sendbuf.p);
+        LAUNCHED(c);
+        CK(cudaMemcpyAsync(out, c->d_sendbuf.p + s0, sizeof(double) * (size_t)(s1 - s0), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    ABI_END
+}
+
+void nngp_shard_halo_put(const int *ctx_id, const int *colour, const double *in, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(colour && *colour >= 1 && *colour <= c->K, "nngp_shard_halo_put: colour out of range");
+    NEED(c->sharded, "nngp_shard_halo_put: not a sharded context");
+    use(c);
+    const int W = c->world, col = *colour - 1;
+    const int r0 = c->recv_ptr[(size_t)col * W], r1 = c->recv_ptr[(size_t)(col + 1) * W];
+    if (r1 > r0) {
+        REQUIRE(in != nullptr, "nngp_shard_halo_put: null buffer");
+        CK(cudaMemcpyAsync(c->d_recvbuf.p + r0, in, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyHostToDevice, c->stream));
+        halo_apply_kernel<<<(r1 - r0 + 255) / 256, 256, 0, c->stream>>>(c->d_recv_proc.p, c->d_recvbuf.p, r0, r1, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_psite.p, c->d_field.p, c->d_r.p);
+        LAUNCHED(c);
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    ABI_END
+}
+
+void nngp_shard_sweep_end(const int *ctx_id, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    NEED(c->sharded, "nngp_shard_sweep_end: not a sharded context");
+    use(c);
+    advance_sweep_kernel<<<1, 1, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global);
+    LAUNCHED(c);
+    c->sweep_counter += 1ull;
+    CK(cudaStreamSynchronize(c->stream));
+    ABI_END
+}
+
 void nngp_ancillary_propose(const int *ctx_id, const double *beta_0, const double *delta_log_scale,
                             const double *log_noise_variance, double *field_response_ratio, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
+    NEED(!c->sharded, "nngp_ancillary_propose: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
     REQUIRE(beta_0 && delta_log_scale && log_noise_variance && field_response_ratio, "nngp_ancillary_propose: bad argument");
     NEED(c->have_slot(NNGP_SLOT_CURRENT) && c->have_slot(NNGP_SLOT_PROPOSAL), "nngp_ancillary_propose: needs current and proposal factors");
     NEED(c->have_field && c->have_obs, "nngp_ancillary_propose: field and observations must be set first");
@@ -1086,6 +1381,7 @@ void nngp_ssr(const int *ctx_id, double *ssr, int *status) {
 void nngp_field_init(const int *ctx_id, const int *slot, const double *beta_0, const double *log_scale, const double *z, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
+    NEED(!c->sharded, "nngp_field_init: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
     REQUIRE(slot && beta_0 && log_scale && z && (*slot == 0 || *slot == 1), "nngp_field_init: bad argument");
     NEED(c->have_slot(*slot), "nngp_field_init: that slot holds no factor");
     use(c);
@@ -1101,6 +1397,7 @@ void nngp_predict_sample(const int *ctx_id, const int *slot, const int *n_obs_si
                          const double *log_scale, const double *z_pred, double *out, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
+    NEED(!c->sharded, "nngp_predict_sample: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
     REQUIRE(slot && n_obs_sites && field && beta_0 && log_scale && z_pred && out && (*slot == 0 || *slot == 1), "nngp_predict_sample: bad argument");
     REQUIRE(*n_obs_sites >= 0 && *n_obs_sites <= c->n, "nngp_predict_sample: n_obs_sites out of range");
     NEED(c->have_slot(*slot), "nngp_predict_sample: that slot holds no factor");
@@ -1130,6 +1427,7 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
                     const double *var_y_, double *records_out, double *field_records_out, int *accept_out, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
+    NEED(!c->sharded, "nngp_chain_run: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
     REQUIRE(n_shape_ && params_io && n_iter_ && thin_ && n_chromatic_ && iter_start_ && chain_index_ && rng_mode_ && var_y_, "nngp_chain_run: null argument");
     const int ns = *n_shape_, n_iter = *n_iter_, n_chromatic = *n_chromatic_, iter_start = *iter_start_, rng_mode = *rng_mode_;
     const double thin = *thin_, var_y = *var_y_;
@@ -1278,6 +1576,7 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
 void nngp_time_op(const int *ctx_id, const int *op_, const int *reps_, const int *flush_l2_, double *ms_out, int *launches_out, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
+    NEED(!c->sharded || (*op_ == 0 || *op_ == 1 || *op_ == 2 || *op_ == 3 || *op_ == 5 || *op_ == 6), "nngp_time_op: that op is not available on a sharded context");
     REQUIRE(op_ && reps_ && flush_l2_ && ms_out && *reps_ >= 1, "nngp_time_op: bad argument");
     const int op = *op_;
     use(c);

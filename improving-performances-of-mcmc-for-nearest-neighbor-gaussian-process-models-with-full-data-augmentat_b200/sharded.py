@@ -1,0 +1,125 @@
+"""Sharded contexts: one latent field split over the GPUs of a box by spatial blocks."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .context import NNGPContext
+from .partition import shard_plan, spatial_blocks
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    st = C.c_int(0)
+    L.load().nngp_comm_unique_id(buf, C.byref(st))
+    L.check(st)
+    return buf.raw
+
+
+class ShardedContext(NNGPContext):
+    """Context over the LOCAL site set of one rank (owned + ghost sites).  Vectors passed to field_set / field_get have
+    plan["local_sites"].size entries; observations are those of the owned sites (plan["obs_index"])."""
+
+    def __init__(self, plan: dict, covfun_name="exponential_isotropic", device=0, comm_id: bytes | None = None,
+                 layout=L.LAYOUT_MORTON):
+        self.plan = plan
+        locs = np.asarray(plan["locs"], dtype=np.float64)
+        self.n, self.d = locs.shape
+        self.m = plan["NNarray"].shape[1] - 1
+        self.covfun_name = covfun_name
+        lm = L.i32(plan["locs_match"])
+        self.n_obs = lm.size
+        self.world, self.rank = plan["world"], plan["rank"]
+        self._id = None
+        cid, st = C.c_int(-1), C.c_int(0)
+        idbuf = C.create_string_buffer(comm_id if comm_id else b"\0" * 128, 128)
+        lib = L.load()
+        lib.nngp_ctx_create_sharded(
+            L.ci(self.n), L.ci(self.d), L.ci(self.m), L.dptr(L.f64(locs)), L.iptr(L.i32(plan["NNarray"])),
+            L.iptr(L.i32(plan["coloring"])), L.ci(plan["n_colors"]), L.iptr(L.i32(plan["owned"])), L.iptr(L.i32(plan["global_id"])),
+            L.iptr(L.i32(plan["global_zpos"])), L.cd(plan["n_global"]), L.ci(self.n_obs), L.iptr(lm), L.ci(L.COVFUN_IDS[covfun_name]),
+            L.ci(device), L.ci(layout), L.ci(self.world), L.ci(self.rank), L.iptr(L.i32(plan["send_site"])), L.iptr(L.i32(plan["send_ptr"])),
+            L.iptr(L.i32(plan["recv_site"])), L.iptr(L.i32(plan["recv_ptr"])), idbuf, C.byref(cid), C.byref(st))
+        L.check(st)
+        self._id = cid.value
+        info = (C.c_int * 8)()
+        lib.nngp_ctx_info(L.ci(self._id), info, C.byref(st))
+        L.check(st)
+        self.n_colors, self.n_levels, self.nnz, self.max_col = info[2], info[3], info[4], info[5]
+        self.device, self.layout = info[6], info[7]
+
+    # ---- colour-stepping sweep (caller-moved halo)
+    def sweep_begin(self, beta_0, log_scale, log_noise_variance, z=None, seed=0):
+        if z is None:
+            self._call("nngp_shard_sweep_begin", L.cd(beta_0), L.cd(log_scale), L.cd(log_noise_variance), L.ci(L.RNG_PHILOX), None, L.cd(seed))
+        else:
+            zz = L.f64(z)
+            assert zz.size == self.plan["n_global"]
+            self._call("nngp_shard_sweep_begin", L.cd(beta_0), L.cd(log_scale), L.cd(log_noise_variance), L.ci(L.RNG_SUPPLIED), L.dptr(zz), L.cd(seed))
+
+    def sweep_colour(self, colour: int):
+        self._call("nngp_shard_sweep_colour", L.ci(colour))
+
+    def halo_get(self, colour: int) -> np.ndarray:
+        W = self.world
+        sp = self.plan["send_ptr"]
+        out = np.zeros(max(int(sp[colour * W] - sp[(colour - 1) * W]), 1))
+        self._call("nngp_shard_halo_get", L.ci(colour), L.dptr(out))
+        return out[: int(sp[colour * W] - sp[(colour - 1) * W])]
+
+    def halo_put(self, colour: int, values: np.ndarray):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        if v.size == 0:
+            v = np.zeros(1)
+        self._call("nngp_shard_halo_put", L.ci(colour), L.dptr(v))
+
+    def sweep_end(self):
+        self._call("nngp_shard_sweep_end")
+
+    def send_segment(self, colour: int, peer: int):
+        W, sp = self.world, self.plan["send_ptr"]
+        base = sp[(colour - 1) * W]
+        return int(sp[(colour - 1) * W + peer] - base), int(sp[(colour - 1) * W + peer + 1] - base)
+
+    def recv_segment(self, colour: int, peer: int):
+        W, rp = self.world, self.plan["recv_ptr"]
+        base = rp[(colour - 1) * W]
+        return int(rp[(colour - 1) * W + peer] - base), int(rp[(colour - 1) * W + peer + 1] - base)
+
+
+def host_routed_sweep(contexts, beta_0, log_scale, log_noise_variance, z=None, seed=0):
+    """One sweep of a sharded field whose shards live in ONE process (any devices): the halo is routed through the host.
+    This is the reference driver for the colour-stepping ABI and the way the sharded arithmetic is tested on one GPU."""
+    K = contexts[0].plan["n_colors"]
+    for c in contexts:
+        c.sweep_begin(beta_0, log_scale, log_noise_variance, z=z, seed=seed)
+    for colour in range(1, K + 1):
+        for c in contexts:
+            c.sweep_colour(colour)
+        outs = [c.halo_get(colour) for c in contexts]
+        for h, dst in enumerate(contexts):
+            r0, r1 = 0, dst.plan["recv_ptr"][colour * dst.world] - dst.plan["recv_ptr"][(colour - 1) * dst.world]
+            buf = np.zeros(int(r1))
+            for g, src in enumerate(contexts):
+                if g == h:
+                    continue
+                a, b = src.send_segment(colour, h)
+                ra, rb = dst.recv_segment(colour, g)
+                assert b - a == rb - ra
+                buf[ra:rb] = outs[g][a:b]
+            dst.halo_put(colour, buf)
+    for c in contexts:
+        c.sweep_end()
+
+
+def create_sharded_distributed(locs, NNarray, coloring, locs_match, covfun_name, device, dist):
+    """torch.distributed driver: every rank calls this with the same (replicated) global structure; rank 0's NCCL id is
+    broadcast; returns (ShardedContext, plan)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    owner = spatial_blocks(locs, world)
+    plan = shard_plan(locs, NNarray, coloring, locs_match, owner, rank, world)
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return ShardedContext(plan, covfun_name, device=device, comm_id=box[0]), plan

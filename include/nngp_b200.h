@@ -88,6 +88,37 @@ void nngp_ctx_create(const int *n, const int *d, const int *m, const double *loc
                      const int *coloring, const int *n_obs, const int *locs_match, const int *covfun_id,
                      const int *device, const int *layout, int *ctx_id, int *status);
 void nngp_ctx_destroy(const int *ctx_id, int *status);
+
+/* ---- one latent field sharded over the GPUs of a box by spatial blocks (BASELINE.json config 4) ----
+ * One process per GPU.  Rank 0 obtains a communicator id (128 bytes) and hands it to its peers by any means (the Python
+ * mirror uses torch.distributed, R would use its own sockets); every rank then creates its context at the same time.
+ * The context covers the rank's LOCAL site set (owned sites + ghost sites, numbered in the field's order; see
+ * <package>/partition.py for how it is derived from NNarray and the block owner of every site):
+ *   owned[n]        1 = this rank updates the site, 0 = ghost copy kept current by the halo exchange
+ *   global_id[n]    0-based id of the site in the whole field (Philox key, so that results do not depend on the sharding)
+ *   global_zpos[n]  position of the site in the whole field's rnorm() hand-out order (NNGP_RNG_SUPPLIED mode)
+ *   send_site / send_ptr   owned boundary sites per (colour, peer): segment [send_ptr[c*world+h], send_ptr[c*world+h+1])
+ *   recv_site / recv_ptr   ghost sites per (colour, peer), in the same order as the owner sends them
+ * On such a context nngp_gibbs_sweep exchanges the boundary values after every colour (ncclSend/ncclRecv) and
+ * nngp_loglik / nngp_ssr / nngp_beta0_moments all-reduce their partial sums; observations are those of the owned sites.
+ * Triangular solves (ancillary step, initial draw, prediction) are not available on a sharded context. */
+void nngp_comm_unique_id(char *id128, int *status);
+void nngp_ctx_create_sharded(const int *n, const int *d, const int *m, const double *locs, const int *NNarray,
+                             const int *coloring, const int *n_colors, const int *owned, const int *global_id,
+                             const int *global_zpos, const double *n_global, const int *n_obs, const int *locs_match,
+                             const int *covfun_id, const int *device, const int *layout, const int *world, const int *rank,
+                             const int *send_site, const int *send_ptr, const int *recv_site, const int *recv_ptr,
+                             const char *comm_id128, int *ctx_id, int *status);
+/* Colour-stepping form of one sharded sweep for callers that move the halo themselves (any transport; also how the sharded
+ * arithmetic is tested on a single GPU).  Create the contexts with an empty comm_id (first byte 0) to skip NCCL.
+ * begin -> for colour in 1..K: sweep_colour; halo_get (packed send buffer of that colour, all peers, send_ptr order);
+ * [caller routes the segments]; halo_put (packed receive buffer, recv_ptr order) -> end. */
+void nngp_shard_sweep_begin(const int *ctx_id, const double *beta_0, const double *log_scale, const double *log_noise_variance,
+                            const int *rng_mode, const double *z, const double *seed, int *status);
+void nngp_shard_sweep_colour(const int *ctx_id, const int *colour, int *status);
+void nngp_shard_halo_get(const int *ctx_id, const int *colour, double *out, int *status);
+void nngp_shard_halo_put(const int *ctx_id, const int *colour, const double *in, int *status);
+void nngp_shard_sweep_end(const int *ctx_id, int *status);
 /* performance knobs (results are identical up to FP64 summation order):
  *   NNGP_OPT_SWEEP_VARIANT 6 = one launch per colour, 128-thread CTAs x 8 entries/thread, chained with programmatic
  *                          dependent launch (the r-independent prologue of colour c+1 overlaps colour c) and replayed from

@@ -1,0 +1,168 @@
+"""A spatially sharded field must reproduce the unsharded one: same sweep given the same normals, same Philox draws
+(keyed by global site id), same log-likelihood.  On one GPU the shards live in one process and the halo is routed through the
+host (colour-stepping ABI); with >= 2 GPUs the NCCL path is run as well."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import nngp_b200 as nb
+from problems import make_problem
+
+pytestmark = pytest.mark.gpu
+CP = [1.0, 0.05, 0.0]
+B0, LS, LNV = 0.2, 0.1, -1.0
+
+
+def reference(P, n_sweeps, z=None, seed=3):
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.factor_build(CP)
+        ctx.factor_commit()
+        ctx.field_set(P["field"])
+        ctx.obs_set(P["y"])
+        ll = ctx.loglik(B0, LS)
+        ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=n_sweeps, z=z, seed=seed)
+        return ctx.field_get(), ll, ctx.loglik(B0, LS), ctx.ssr(), ctx.precision_diag()
+
+
+def shard_contexts(P, parts):
+    owner = nb.spatial_blocks(P["locs"], parts)
+    ctxs = []
+    for r in range(parts):
+        plan = nb.shard_plan(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], owner, r, parts)
+        c = nb.ShardedContext(plan, device=0, comm_id=None)
+        c.factor_build(CP)
+        c.factor_commit()
+        c.field_set(P["field"][plan["local_sites"]])
+        c.obs_set(P["y"][plan["obs_index"]])
+        ctxs.append(c)
+    return ctxs
+
+
+def gather_owned(ctxs, n):
+    out = np.full(n, np.nan)
+    for c in ctxs:
+        f = c.field_get()
+        own = c.plan["owned"] == 1
+        out[c.plan["local_sites"][own]] = f[own]
+    return out
+
+
+@pytest.mark.parametrize("parts", [2, 4])
+def test_host_routed_sharded_sweep_equals_unsharded(parts):
+    P = make_problem(30000, 10, seed=5, n_extra_obs=500)
+    n = P["n"]
+    z = P["rng"].standard_normal(2 * n)
+    f_ref, ll0_ref, ll1_ref, ssr_ref, pd_ref = reference(P, 2, z=z)
+    ctxs = shard_contexts(P, parts)
+    try:
+        # log-likelihood: partial sums of the owned rows add up to the whole (each context reports ll with n_global)
+        parts_ll = [c.loglik(B0, LS) for c in ctxs]
+        const = -n * 0.5 * LS
+        assert abs(sum(l - const for l in parts_ll) + const - ll0_ref) < 1e-10 * abs(ll0_ref)
+        for s in range(2):
+            nb.host_routed_sweep(ctxs, B0, LS, LNV, z=z[s * n:(s + 1) * n])
+        f = gather_owned(ctxs, n)
+        assert np.max(np.abs(f - f_ref)) < 1e-10 * np.max(np.abs(f_ref))
+        # ghosts carry the owners' values after the sweep
+        for c in ctxs:
+            assert np.max(np.abs(c.field_get() - f_ref[c.plan["local_sites"]])) < 1e-10 * np.max(np.abs(f_ref))
+        assert abs(sum(c.ssr() for c in ctxs) - ssr_ref) < 1e-10 * ssr_ref
+        for c in ctxs:
+            own = c.plan["owned"] == 1
+            assert np.allclose(c.precision_diag()[own], pd_ref[c.plan["local_sites"][own]], rtol=1e-12)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_philox_draws_do_not_depend_on_the_sharding():
+    P = make_problem(20000, 10, seed=6)
+    f_ref, *_ = reference(P, 1, z=None, seed=9)
+    ctxs = shard_contexts(P, 3)
+    try:
+        nb.host_routed_sweep(ctxs, B0, LS, LNV, z=None, seed=9)
+        f = gather_owned(ctxs, P["n"])
+        assert np.max(np.abs(f - f_ref)) < 1e-10 * np.max(np.abs(f_ref))
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_single_rank_sharded_context_is_the_plain_one():
+    P = make_problem(5000, 10, seed=7)
+    z = P["rng"].standard_normal(P["n"])
+    f_ref, ll0, ll1, *_ = reference(P, 1, z=z)
+    plan = nb.shard_plan(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], nb.spatial_blocks(P["locs"], 1), 0, 1)
+    with nb.ShardedContext(plan) as c:
+        c.factor_build(CP)
+        c.factor_commit()
+        c.field_set(P["field"])
+        c.obs_set(P["y"])
+        assert abs(c.loglik(B0, LS) - ll0) < 1e-10 * abs(ll0)
+        c.gibbs_sweep(B0, LS, LNV, n_sweeps=1, z=z)              # world = 1: the ordinary entry point works
+        assert np.max(np.abs(c.field_get() - f_ref)) < 1e-10
+        with pytest.raises(nb.NNGPError):
+            c.sptrsv(z)                                          # not available on sharded contexts
+
+
+def _nccl_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        P = make_problem(40000, 10, seed=8)
+        n = P["n"]
+        z = np.random.default_rng(1).standard_normal(2 * n)
+        ctx, plan = nb.create_sharded_distributed(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], "exponential_isotropic", rank, dist)
+        ctx.factor_build(CP)
+        ctx.factor_commit()
+        ctx.field_set(P["field"][plan["local_sites"]])
+        ctx.obs_set(P["y"][plan["obs_index"]])
+        ll = ctx.loglik(B0, LS)                                   # all-reduced inside the library
+        ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=2, z=z)             # halo exchange over NCCL after every colour
+        ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=1, seed=4)
+        f = ctx.field_get()
+        own = plan["owned"] == 1
+        q.put((rank, ll, plan["local_sites"][own], f[own], ctx.ssr()))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_sharded_sweep_on_two_gpus():
+    if nb.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    P = make_problem(40000, 10, seed=8)
+    n = P["n"]
+    z = np.random.default_rng(1).standard_normal(2 * n)
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.factor_build(CP)
+        ctx.factor_commit()
+        ctx.field_set(P["field"])
+        ctx.obs_set(P["y"])
+        ll_ref = ctx.loglik(B0, LS)
+        ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=2, z=z)
+        ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=1, seed=4)
+        f_ref, ssr_ref = ctx.field_get(), ctx.ssr()
+    f = np.full(n, np.nan)
+    for rank, ll, sites, vals, ssr in res:
+        assert abs(ll - ll_ref) < 1e-10 * abs(ll_ref)
+        assert abs(ssr - ssr_ref) < 1e-10 * ssr_ref
+        f[sites] = vals
+    assert np.max(np.abs(f - f_ref)) < 1e-10 * np.max(np.abs(f_ref))
