@@ -9,8 +9,10 @@ stream.  `e2e` = the same step through the C ABI with HOST buffers (field in, fi
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 1000000] [--m 10]
 
-N > 1 (torchrun, one rank per GPU): one independent chain per GPU (the reference's own parallelism, mclapply over chains,
-Scripts/mcmc_nngp_update_Gaussian.R:25); no data-path collective; scaling = "weak".
+N > 1 (torchrun, one rank per GPU), default --mode chains: one independent chain per GPU (the reference's own parallelism,
+mclapply over chains, Scripts/mcmc_nngp_update_Gaussian.R:25); no data-path collective; scaling = "weak".
+--mode sharded: ONE field of --n sites split over the N GPUs by spatial blocks, per-colour halo exchange of boundary values
+(ncclSend/ncclRecv) and an all-reduce for the log-lik scalars; scaling = "strong".
 """
 from __future__ import annotations
 
@@ -300,19 +302,89 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_sharded(a):
+    """One field over all ranks.  Every rank builds the (replicated) host-side structure, keeps its block."""
+    import torch
+    import torch.distributed as dist
+    import nngp_b200 as nb
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, m = a.n, a.m
+    t_setup = time.perf_counter()
+    rng, locs, nn, coloring, locs_match = build_problem(n, m, seed=1)       # same seed everywhere: replicated structure
+    ctx, plan = nb.create_sharded_distributed(locs, nn, coloring, locs_match, "exponential_isotropic", local, dist)
+    t_setup = time.perf_counter() - t_setup
+    assert ctx.factor_build([1.0, RANGE, 0.0]) == 0
+    ctx.factor_commit()
+    w = np.random.default_rng(7).standard_normal(n) * 0.5                    # any field will do for throughput; same on all ranks
+    y = w + np.sqrt(TAU2) * np.random.default_rng(8).standard_normal(n)
+    ctx.field_set(w[plan["local_sites"]])
+    ctx.obs_set(y[plan["obs_index"]])
+    beta_0, ls, lnv = 0.0, float(np.log(SIGMA2)), float(np.log(TAU2))
+    ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=1, seed=1)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx.time_op("sweep_loglik", reps=max(a.warmup, 3))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = nb.launch_count()
+    barrier()
+    ms_steps, launches_per_step = ctx.time_op("sweep_loglik", reps=a.steps)
+    barrier()
+    launches = nb.launch_count() - launches0
+    ms_sweep, _ = ctx.time_op("gibbs_sweep", reps=max(10, a.steps))
+    ms_ll, _ = ctx.time_op("loglik", reps=max(10, a.steps))
+    ms_fac, _ = ctx.time_op("factor_build", reps=5)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([float(ms_steps.sum()), float(ms_sweep.mean()), float(ms_ll.mean()), float(ms_fac.mean())], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, sweep_ms, ll_ms, fac_ms = [float(v) for v in t.tolist()]
+    halo = torch.tensor([float(plan["send_ptr"][-1]), float(plan["n_ghost"]), float(plan["n_owned"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(halo, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ab = algorithmic_bytes(n, m)
+        achieved = ab["gibbs_sweep"] / (sweep_ms * 1e-3) / 1e9
+        line = {
+            "metric": "gibbs_sweep_plus_vecchia_loglik_per_sec", "value": a.steps / (total_ms * 1e-3), "unit": "steps/s", "n_gpus": world,
+            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"one field, U(0,1)^2, n={n}, m={m}, exponential_isotropic range {RANGE}, reordering=random",
+                       "step": "1 chromatic Gibbs sweep of the whole field (per-colour NCCL halo exchange) + 1 Vecchia log-lik (all-reduce)",
+                       "parallelism": f"field sharded over {world} GPUs by spatial blocks", "n_colors": ctx.n_colors,
+                       "halo_values_per_sweep": int(halo[0].item()), "ghost_sites_total": int(halo[1].item()), "setup_s": t_setup},
+            "gibbs_sweeps_per_sec": 1e3 / sweep_ms, "loglik_evals_per_sec": 1e3 / ll_ms, "factor_builds_per_sec": 1e3 / fac_ms,
+            "ms": {"sweep": sweep_ms, "loglik": ll_ms, "factor_build": fac_ms},
+            "roofline": {"bound": "hbm", "kernel": "gibbs_tile_kernel + halo exchange (whole-field sweep, all ranks)", "achieved": achieved,
+                         "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
+            "e2e": None, "gpu_launches": int(launches), "launches_per_step": int(launches_per_step), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
-    ap.add_argument("--m", type=int, default=10)
+    ap.add_argument("--sites", "--n", dest="n", type=int, default=1_000_000)
+    ap.add_argument("--nbrs", "--m", dest="m", type=int, default=10)
     ap.add_argument("--ref-n", type=int, default=None, help="reference arm: run on a smaller n and scale (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="chains", choices=["chains", "sharded"])
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.mode == "sharded":
+        run_sharded(a)
     else:
         run_ours(a)
 

@@ -143,7 +143,7 @@ class NNGPContext:
                        L.ci(L.RNG_PHILOX), None, L.cd(seed))
         else:
             zz = L.f64(z)
-            assert zz.size == self.n * n_sweeps
+            assert zz.size == getattr(self, "n_z", self.n) * n_sweeps   # sharded contexts index the whole field's normals
             self._call("nngp_gibbs_sweep", L.ci(n_sweeps), L.cd(beta_0), L.cd(log_scale), L.cd(log_noise_variance),
                        L.ci(L.RNG_SUPPLIED), L.dptr(zz), L.cd(seed))
 

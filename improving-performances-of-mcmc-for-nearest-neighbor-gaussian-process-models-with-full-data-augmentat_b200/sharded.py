@@ -32,6 +32,7 @@ class ShardedContext(NNGPContext):
         lm = L.i32(plan["locs_match"])
         self.n_obs = lm.size
         self.world, self.rank = plan["world"], plan["rank"]
+        self.n_z = int(plan["n_global"])
         self._id = None
         cid, st = C.c_int(-1), C.c_int(0)
         idbuf = C.create_string_buffer(comm_id if comm_id else b"\0" * 128, 128)

@@ -129,6 +129,9 @@ def _nccl_worker(rank, world, port, q):
         own = plan["owned"] == 1
         q.put((rank, ll, plan["local_sites"][own], f[own], ctx.ssr()))
         ctx.close()
+    except Exception as e:   # report instead of leaving the parent waiting on the queue
+        q.put((rank, repr(e)))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -145,9 +148,10 @@ def test_nccl_sharded_sweep_on_two_gpus():
     procs = [mpc.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
+    res = [q.get(timeout=240) for _ in procs]
     for p in procs:
         p.join(timeout=60)
+    assert all(len(r) == 5 for r in res), res
     P = make_problem(40000, 10, seed=8)
     n = P["n"]
     z = np.random.default_rng(1).standard_normal(2 * n)
