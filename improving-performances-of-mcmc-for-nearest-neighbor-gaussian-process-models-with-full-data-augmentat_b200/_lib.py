@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "nngp_factor_get", "nngp_factor_accept", "nngp_factor_commit", "nngp_precision_diag", "nngp_field_set",
     "nngp_field_get", "nngp_obs_set", "nngp_loglik", "nngp_loglik_host", "nngp_spmv", "nngp_sptmv", "nngp_sptrsv",
     "nngp_gibbs_sweep", "nngp_ancillary_propose", "nngp_ancillary_accept", "nngp_beta0_moments", "nngp_ssr",
-    "nngp_field_init", "nngp_chain_run", "nngp_predict_sample", "nngp_time_op", "nngp_launch_count", "nngp_debug_timeline",
+    "nngp_field_init", "nngp_chain_run", "nngp_predict_sample", "nngp_time_op", "nngp_launch_count", "nngp_debug_timeline", "nngp_host_alloc", "nngp_host_free",
 ]
 
 
@@ -88,6 +88,29 @@ def dptr(a: np.ndarray):
 
 def iptr(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class PinnedArray:
+    """float64 numpy array over page-locked host memory (nngp_host_alloc): vectors passed from it skip the staging copy."""
+
+    def __init__(self, n: int):
+        self._ptr = C.c_void_p(None)
+        st = C.c_int(0)
+        load().nngp_host_alloc(C.byref(C.c_double(8.0 * n)), C.byref(self._ptr), C.byref(st))
+        check(st)
+        self.array = np.ctypeslib.as_array(C.cast(self._ptr, C.POINTER(C.c_double)), shape=(n,))
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            st = C.c_int(0)
+            load().nngp_host_free(C.byref(self._ptr), C.byref(st))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def launch_count() -> int:

@@ -63,7 +63,7 @@ class NNGPContext:
         getattr(L.load(), name)(L.ci(self._id), *args, C.byref(st))
         L.check(st)
 
-    OPTIONS = {"sweep_variant": 1, "solve_variant": 2, "use_graph": 3, "solve_ctas_per_sm": 4, "solve_sleep_ns": 5, "debug_timeline": 6, "solve_window_ctas": 7, "commit_variant": 8}
+    OPTIONS = {"sweep_variant": 1, "solve_variant": 2, "use_graph": 3, "solve_ctas_per_sm": 4, "solve_sleep_ns": 5, "debug_timeline": 6, "solve_window_ctas": 7, "commit_variant": 8, "matern_table": 9}
 
     def set_option(self, name: str, value: int):
         self._call("nngp_ctx_set_option", L.ci(self.OPTIONS[name]), L.ci(value))
@@ -97,8 +97,11 @@ class NNGPContext:
         assert f.size == self.n
         self._call("nngp_field_set", L.dptr(f))
 
-    def field_get(self) -> np.ndarray:
-        out = np.empty(self.n)
+    def field_get(self, out: np.ndarray | None = None) -> np.ndarray:
+        """`out` may be a pinned buffer (L.PinnedArray(n).array): the download then lands in it without a staging copy"""
+        if out is None:
+            out = np.empty(self.n)
+        assert out.dtype == np.float64 and out.size == self.n and out.flags.c_contiguous
         self._call("nngp_field_get", L.dptr(out))
         return out
 

@@ -73,7 +73,8 @@ __device__ __forceinline__ double philox_normal(uint32_t site, uint32_t sweep_lo
 // cancellation of (1/Gamma(1-mu) - 1/Gamma(1+mu)) / (2 mu) near mu = 0.  Checked against std::cyl_bessel_k (oracle) and
 // scipy.special.kv to ~1e-13 relative.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ double bessel_k_real(double nu, double x) {
+// scaled = true returns K_nu(x) * exp(x) (no underflow for large x)
+__device__ __noinline__ double bessel_k_real(double nu, double x, bool scaled = false) {
     const double EPS = 1.0e-16, PI = 3.14159265358979323846;
     const int MAXIT = 10000;
     const int nl = (int)(nu + 0.5);
@@ -135,8 +136,13 @@ __device__ __noinline__ double bessel_k_real(double nu, double x) {
             if (fabs(dels / s) < EPS) break;
         }
         h = a1 * h;
-        rkmu = sqrt(PI / (2.0 * x)) * exp(-x) / s;
+        rkmu = sqrt(PI / (2.0 * x)) * (scaled ? 1.0 : exp(-x)) / s;
         rk1 = rkmu * (xmu + x + 0.5 - h) * xi;
+    }
+    if (scaled && x < 2.0) {
+        const double ex = exp(x);
+        rkmu *= ex;
+        rk1 *= ex;
     }
     for (int i = 1; i <= nl; i++) {
         const double t = (xmu + i) * xi2 * rk1 + rkmu;

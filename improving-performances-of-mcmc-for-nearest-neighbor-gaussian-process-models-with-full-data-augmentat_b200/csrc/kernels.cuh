@@ -27,7 +27,61 @@ struct CovConst {
     int covfun;       // NNGP_* id
     int d;            // raw coordinate dimension
     int dt;           // transformed dimension
+    const double *mtab;   // Matern families: piecewise-polynomial table of the kernel (nullptr = evaluate K_nu directly)
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Matern kernel table.  Inside one factor build the smoothness nu is fixed, so  q(x) = normcon * x^nu * K_nu(x) * e^x  is a
+// fixed smooth function of the scaled distance x; evaluating K_nu directly (Temme series / continued fraction, ~2.7 k FP64
+// instructions per call, 55 calls per row at m = 10) made the Matern factor build 26x slower than the exponential one.
+// The table holds, for every binary octave [2^e, 2^(e+1)), e in [MT_EMIN, MT_EMAX), MT_S sub-intervals (uniform in the
+// mantissa) with a degree-7 Newton interpolant on Chebyshev nodes.  The segment and the local coordinate come straight from
+// the exponent / mantissa bits of x; the kernel value is p(u) * exp(-x).  Interpolation error < 1e-13 relative (checked
+// against scipy's kve and, through the factor parity tests, against std::cyl_bessel_k).  Outside the table range the exact
+// routine is used.
+// ---------------------------------------------------------------------------------------------------------------
+#define MT_EMIN (-40)
+#define MT_EMAX 10
+#define MT_S 16
+#define MT_SEGS ((MT_EMAX - MT_EMIN) * MT_S)
+
+__device__ __forceinline__ double mt_node(int k) {   // Chebyshev nodes on [0, 1]
+    const double nodes[8] = {0.99039264020161522, 0.91573480615127262, 0.77778511650980109, 0.59754516100806417,
+                             0.40245483899193590, 0.22221488349019886, 0.08426519384872738, 0.00960735979838478};
+    return nodes[k];
+}
+
+__global__ void __launch_bounds__(128) matern_table_kernel(double *__restrict__ tab, double nu, double normcon) {
+    __shared__ double f[128];
+    const int seg = blockIdx.x * 16 + (threadIdx.x >> 3), k = threadIdx.x & 7;
+    if (seg < MT_SEGS) {
+        const int e = MT_EMIN + seg / MT_S, msub = seg % MT_S;
+        const double x = ldexp(1.0 + ((double)msub + mt_node(k)) / MT_S, e);
+        f[threadIdx.x] = normcon * pow(x, nu) * bessel_k_real(nu, x, true);
+    }
+    __syncthreads();
+    if (seg < MT_SEGS && k == 0) {
+        double c[8];
+        for (int j = 0; j < 8; j++) c[j] = f[threadIdx.x + j];
+        for (int j = 1; j < 8; j++)
+            for (int i = 7; i >= j; i--) c[i] = (c[i] - c[i - 1]) / (mt_node(i) - mt_node(i - j));
+        for (int j = 0; j < 8; j++) tab[(size_t)seg * 8 + j] = c[j];
+    }
+}
+
+__device__ __forceinline__ double matern_from_table(const double *__restrict__ tab, double x, double &out_ok) {
+    const long long bits = __double_as_longlong(x);
+    const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    if (e < MT_EMIN || e >= MT_EMAX) { out_ok = 0.0; return 0.0; }
+    const int seg = (e - MT_EMIN) * MT_S + (int)((bits >> 48) & 0xF);
+    const double u = (double)(bits & 0xFFFFFFFFFFFFll) * 3.5527136788005009e-15;   // 2^-48
+    const double *c = tab + (size_t)seg * 8;
+    double p = c[7];
+#pragma unroll
+    for (int k = 6; k >= 0; k--) p = p * (u - mt_node(k)) + c[k];
+    out_ok = 1.0;
+    return p * exp(-x);
+}
 
 // parameters of the sweep that change between launches live in device memory so that the captured graph is static
 struct SweepParams {
@@ -81,6 +135,11 @@ template <bool MATERN>
 __device__ __forceinline__ double kernel_value(const CovConst &cc, double dist) {
     if (!MATERN) return cc.variance * exp(-dist);
     if (dist == 0.0) return cc.variance;
+    if (cc.mtab) {
+        double ok;
+        const double v = matern_from_table(cc.mtab, dist, ok);
+        if (ok != 0.0) return v;
+    }
     return cc.normcon * pow(dist, cc.smooth) * bessel_k_real(cc.smooth, dist);
 }
 

@@ -164,6 +164,8 @@ struct Ctx {
     // device structure
     DevBuf<int> d_psite, d_gid, d_i2g, d_g2i, d_nn, d_colptr, d_crow, d_csrc, d_zpos, d_lvl_rows, d_lvl_ptr, d_lm, d_optr, d_oidx, d_cstart,
         d_partial_rows, d_nbad;
+    DevBuf<double> d_mtab;
+    bool matern_table = true;              // tabulate the Matern kernel per factor build (false: evaluate K_nu per pair)
     DevBuf<double> d_locs, d_tl, d_linv[2], d_valT, d_pd, d_nobs, d_ymx, d_S, d_field, d_newfield, d_r, d_tmp1, d_tmp2, d_io,
         d_zbuf, d_partials, d_scalars, d_flush;
     DevBuf<SweepParams> d_sp;
@@ -222,23 +224,53 @@ static void ensure_stage(Ctx *c, size_t count) {
     c->h_stage_n = count;
 }
 
+// Is `p` page-locked host memory (cudaMallocHost / nngp_host_alloc / cudaHostRegister)?  Then the DMA engine can read or
+// write it directly and the staging copy is skipped.
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// multi-threaded memcpy between pageable caller memory and the pinned staging buffer (a single thread moves ~8 GB/s,
+// which made the staging copy of an 8 MB vector the largest term of an end-to-end step)
+static void par_memcpy(void *dst, const void *src, size_t bytes) {
+    const size_t chunk = (size_t)1 << 20;
+    const long long nchunks = (long long)((bytes + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static) if (nchunks >= 4)
+    for (long long k = 0; k < nchunks; k++) {
+        const size_t off = (size_t)k * chunk;
+        std::memcpy((char *)dst + off, (const char *)src + off, std::min(chunk, bytes - off));
+    }
+}
+
 // host vector (reference order) -> device vector (internal order)
 static void upload_site_vector(Ctx *c, const double *host, double *dev) {
-    ensure_stage(c, c->n);
-    std::memcpy(c->h_stage, host, sizeof(double) * c->n);
-    CK(cudaMemcpyAsync(c->d_io.p, c->h_stage, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+    if (is_pinned(host)) {
+        CK(cudaMemcpyAsync(c->d_io.p, host, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        ensure_stage(c, c->n);
+        par_memcpy(c->h_stage, host, sizeof(double) * c->n);
+        CK(cudaMemcpyAsync(c->d_io.p, c->h_stage, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+    }
     gather_f64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(dev, c->d_io.p, c->d_i2g.p, c->n);
     LAUNCHED(c);
+    if (is_pinned(host)) CK(cudaStreamSynchronize(c->stream));   // the caller may reuse its buffer as soon as we return
 }
 
 // device vector (internal order) -> host vector (reference order)
 static void download_site_vector(Ctx *c, const double *dev, double *host) {
-    ensure_stage(c, c->n);
     gather_f64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_io.p, dev, c->d_g2i.p, c->n);
     LAUNCHED(c);
+    if (is_pinned(host)) {
+        CK(cudaMemcpyAsync(host, c->d_io.p, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return;
+    }
+    ensure_stage(c, c->n);
     CK(cudaMemcpyAsync(c->h_stage, c->d_io.p, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    std::memcpy(host, c->h_stage, sizeof(double) * c->n);
+    par_memcpy(host, c->h_stage, sizeof(double) * c->n);
 }
 
 static uint32_t morton2(uint32_t x, uint32_t y) {
@@ -255,6 +287,7 @@ static uint32_t morton2(uint32_t x, uint32_t y) {
 
 static CovConst make_cov(Ctx *c, const double *cp, int ncp) {
     CovConst cc{};
+    cc.mtab = nullptr;
     cc.covfun = c->covfun;
     cc.d = c->d;
     cc.dt = c->dt;
@@ -303,12 +336,13 @@ static void launch_factor(Ctx *c, double *linv, const CovConst &cc) {
     FACTOR_CASE(6, 3)
     FACTOR_CASE(11, 2)
     FACTOR_CASE(11, 3)
+    FACTOR_CASE(21, 2)
 #undef FACTOR_CASE
     if (specialised) {
         LAUNCHED(c);
         const int np = (int)c->partial_rows.size();
         if (np > 0) {
-            vecchia_factor_generic_kernel<16, MATERN><<<(np + blk - 1) / blk, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, c->d_partial_rows.p, np, ld, M, cc, c->d_nbad.p);
+            vecchia_factor_generic_kernel<24, MATERN><<<(np + blk - 1) / blk, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, c->d_partial_rows.p, np, ld, M, cc, c->d_nbad.p);
             LAUNCHED(c);
         }
         return;
@@ -320,7 +354,15 @@ static void launch_factor(Ctx *c, double *linv, const CovConst &cc) {
     LAUNCHED(c);
 }
 
-static void op_factor_build(Ctx *c, int slot, const CovConst &cc) {
+static void op_factor_build(Ctx *c, int slot, const CovConst &cc_in) {
+    CovConst cc = cc_in;
+    cc.mtab = nullptr;
+    if (c->covfun >= NNGP_MATERN_ISOTROPIC && c->matern_table) {
+        if (c->d_mtab.n == 0) c->d_mtab.alloc((size_t)MT_SEGS * 8);
+        matern_table_kernel<<<(MT_SEGS + 15) / 16, 128, 0, c->stream>>>(c->d_mtab.p, cc.smooth, cc.normcon);
+        LAUNCHED(c);
+        cc.mtab = c->d_mtab.p;
+    }
     CK(cudaMemsetAsync(c->d_nbad.p, 0, 2 * sizeof(int), c->stream));
     transform_locs_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_locs.p, c->d_tl.p, c->n, cc);
     LAUNCHED(c);
@@ -617,6 +659,7 @@ static void destroy_ctx(Ctx *c) {
                             &c->d_field, &c->d_newfield, &c->d_r, &c->d_tmp1, &c->d_tmp2, &c->d_io, &c->d_zbuf, &c->d_partials,
                             &c->d_scalars, &c->d_flush};
     for (auto *b : db) b->release();
+    c->d_mtab.release();
     c->d_sp.release();
     for (int k = 0; k < 3; k++) { c->d_tiles[k].release(); c->d_tile_ptr[k].release(); }
     c->d_rows_padded.release(); c->d_ticket.release(); c->d_bar.release();
@@ -654,6 +697,23 @@ void nngp_last_error(char *buf, const int *len) {
     std::lock_guard<std::mutex> lk(g_err_mu);
     std::strncpy(buf, g_err, (size_t)*len - 1);
     buf[*len - 1] = '\0';
+}
+
+void nngp_host_alloc(const double *n_bytes, void **ptr, int *status) {
+    ABI_BEGIN
+    REQUIRE(n_bytes && ptr && *n_bytes >= 0, "nngp_host_alloc: bad argument");
+    void *p = nullptr;
+    CK(cudaMallocHost(&p, (size_t)std::max(*n_bytes, 8.0)));
+    *ptr = p;
+    ABI_END
+}
+
+void nngp_host_free(void **ptr, int *status) {
+    ABI_BEGIN
+    REQUIRE(ptr != nullptr, "nngp_host_free: null argument");
+    if (*ptr) CK(cudaFreeHost(*ptr));
+    *ptr = nullptr;
+    ABI_END
 }
 
 void nngp_launch_count(double *count) { if (count) *count = (double)g_launches.load(); }
@@ -1007,6 +1067,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;
+        case NNGP_OPT_MATERN_TABLE: c->matern_table = (*value != 0); break;
         case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "commit variant must be 0..1"); c->commit_variant = *value; break;
         case NNGP_OPT_SOLVE_WINDOW_CTAS: REQUIRE(*value >= 0 && *value <= 4096, "solve window must be 0..4096 CTAs"); c->solve_window_ctas = *value; break;
         case NNGP_OPT_DEBUG_TIMELINE: c->debug_timeline = (*value != 0); break;

@@ -134,6 +134,7 @@ void nngp_shard_sweep_end(const int *ctx_id, int *status);
 #define NNGP_OPT_SOLVE_SLEEP_NS 5    /* back-off between dependency polls (default 0) */
 #define NNGP_OPT_SOLVE_WINDOW_CTAS 7  /* absolute window of the sync-free solve in CTAs of 256 rows (0 = use per-SM setting) */
 #define NNGP_OPT_COMMIT_VARIANT 8     /* accept-branch transposition: 0 = tiled (default), 1 = thread per column */
+#define NNGP_OPT_MATERN_TABLE 9       /* Matern families: 1 = per-build interpolation table of the kernel (default), 0 = K_nu per pair */
 #define NNGP_OPT_DEBUG_TIMELINE 6    /* development aid: the persistent sweep kernel stamps %globaltimer per stage */
 void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);
 /* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,
@@ -243,6 +244,11 @@ void nngp_time_op(const int *ctx_id, const int *op, const int *reps, const int *
                   int *launches_out, int *status);
 /* development aid: (time ns, stage id) pairs stamped by CTA 0 of the last persistent sweep launch (NNGP_OPT_DEBUG_TIMELINE) */
 void nngp_debug_timeline(double *out, const int *n_out, int *n_written, int *status);
+/* Page-locked host buffers.  Vectors handed to the library from such a buffer are DMA-ed directly (no staging copy); any other
+ * host pointer is staged through an internal pinned buffer with a multi-threaded copy.  n_bytes is a double so that .C() can
+ * pass sizes beyond 2^31. */
+void nngp_host_alloc(const double *n_bytes, void **ptr, int *status);
+void nngp_host_free(void **ptr, int *status);
 /* cumulative number of kernels this library has launched in this process (for bench.py's gpu_launches) */
 void nngp_launch_count(double *count);
 
