@@ -325,8 +325,21 @@ def run_sharded(a):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, m = a.n, a.m
     t_setup = time.perf_counter()
-    rng, locs, nn, coloring, locs_match = build_problem(n, m, seed=1)       # same seed everywhere: replicated structure
-    ctx, plan = nb.create_sharded_distributed(locs, nn, coloring, locs_match, "exponential_isotropic", local, dist)
+    # the (replicated) host-side structure is built once, by rank 0 with all host cores, and shared through /dev/shm
+    shm = f"/dev/shm/nngp_bench_{os.environ.get('MASTER_PORT', '0')}_{n}_{m}"
+    if rank == 0:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)           # torchrun pins it to 1; the library is not loaded yet
+        rng, locs, nn, coloring, locs_match = build_problem(n, m, seed=1)
+        np.save(shm + "_locs.npy", locs); np.save(shm + "_nn.npy", nn); np.save(shm + "_col.npy", coloring)
+    dist.barrier()
+    if rank != 0:
+        locs, nn, coloring = np.load(shm + "_locs.npy"), np.load(shm + "_nn.npy"), np.load(shm + "_col.npy")
+        locs_match = np.arange(1, n + 1, dtype=np.int32)
+    dist.barrier()
+    if rank == 0:
+        for suffix in ("_locs.npy", "_nn.npy", "_col.npy"):
+            os.remove(shm + suffix)
+    ctx, plan = nb.create_sharded_distributed(locs, nn, coloring, locs_match, "exponential_isotropic", local, dist, transport=a.transport)
     t_setup = time.perf_counter() - t_setup
     assert ctx.factor_build([1.0, RANGE, 0.0]) == 0
     ctx.factor_commit()
@@ -369,7 +382,7 @@ def run_sharded(a):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"one field, U(0,1)^2, n={n}, m={m}, exponential_isotropic range {RANGE}, reordering=random",
                        "step": "1 chromatic Gibbs sweep of the whole field (per-colour NCCL halo exchange) + 1 Vecchia log-lik (all-reduce)",
-                       "parallelism": f"field sharded over {world} GPUs by spatial blocks", "n_colors": ctx.n_colors,
+                       "parallelism": f"field sharded over {world} GPUs by spatial blocks", "transport": a.transport, "n_colors": ctx.n_colors,
                        "halo_values_per_sweep": int(halo[0].item()), "ghost_sites_total": int(halo[1].item()), "setup_s": t_setup},
             "gibbs_sweeps_per_sec": 1e3 / sweep_ms, "loglik_evals_per_sec": 1e3 / ll_ms, "factor_builds_per_sec": 1e3 / fac_ms,
             "ms": {"sweep": sweep_ms, "loglik": ll_ms, "factor_build": fac_ms},
@@ -393,6 +406,7 @@ def main():
     ap.add_argument("--ref-n", type=int, default=None, help="reference arm: run on a smaller n and scale (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="chains", choices=["chains", "sharded"])
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="sharded mode: halo transport")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

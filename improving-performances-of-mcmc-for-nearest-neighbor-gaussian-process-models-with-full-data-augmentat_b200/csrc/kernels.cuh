@@ -1071,6 +1071,174 @@ __global__ void halo_apply_kernel(const int *__restrict__ recv_proc, const doubl
     for (int e = colptr[p]; e < colptr[p + 1]; e++) r[crow[e]] += valT[e] * delta;   // same-colour sites never share a row
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Peer-to-peer halo exchange (the production transport between the GPUs of one box): every rank maps its peers' receive
+// areas (CUDA IPC over NVLink / NVSwitch).  After a colour's sweep kernel, halo_push_kernel stores the new boundary values
+// STRAIGHT into the peers' ghost buffers, fences system-wide and raises this rank's flag on every peer; the peer's
+// halo_wait_apply_kernel spins (bounded) on the flags of all its peers and then patches its residual.  One NCCL
+// send/recv group per colour cost ~43 us; a flag hop over NVLink is a few microseconds.
+// Area layout (doubles; the header is the same on every rank): [ 16 halo flags (u64) | 16 reduction flags | 2 x 32
+// reduction slots | receive values ... ].
+// ---------------------------------------------------------------------------------------------------------------
+struct PeerTable { double *area[8]; };   // peers' mapped areas (own entry = own area)
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// one CTA; segments [send_ptr[h], send_ptr[h+1]) of this colour go to peer h at offset peer_base[h] of its receive area
+__global__ void __launch_bounds__(1024) halo_push_kernel(PeerTable peers, const int *__restrict__ send_storage,
+                                                         const double *__restrict__ field, const int *__restrict__ send_ptr_col,
+                                                         const int *__restrict__ peer_base_col, int world, int rank,
+                                                         size_t flag_off, size_t val_off, unsigned long long *epoch_ctr) {
+    // the exchange counter lives in device memory so that the whole sweep (all colours) is one static CUDA graph
+    __shared__ unsigned long long s_epoch;
+    if (threadIdx.x == 0) s_epoch = ++(*epoch_ctr);
+    for (int h = 0; h < world; h++) {
+        if (h == rank) continue;
+        const int a = send_ptr_col[h], b = send_ptr_col[h + 1];
+        double *dst = peers.area[h] + val_off + peer_base_col[h];
+        for (int k = a + (int)threadIdx.x; k < b; k += (int)blockDim.x) dst[k - a] = field[send_storage[k]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world && (int)threadIdx.x != rank)
+        st_release_sys_u64(reinterpret_cast<unsigned long long *>(peers.area[threadIdx.x] + flag_off) + rank, s_epoch);
+}
+
+// wait for every peer's flag of this colour, then apply what arrived (see halo_apply_kernel)
+__global__ void __launch_bounds__(256) halo_wait_apply_kernel(const unsigned long long *flags, int world, int rank,
+                                                              const unsigned long long *epoch_ctr, int *err,
+                                                              const int *__restrict__ recv_proc, const double *recvbuf, int k0,
+                                                              int k1, const int *__restrict__ colptr, const int *__restrict__ crow,
+                                                              const double *__restrict__ valT, const int *__restrict__ psite,
+                                                              double *__restrict__ field, double *__restrict__ r) {
+    if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+        const unsigned long long epoch = *epoch_ctr;   // set by this colour's halo_push_kernel, earlier on the same stream
+        unsigned int spins = 0;
+        while (ld_acquire_sys_u64(flags + threadIdx.x) < epoch) {
+            if (++spins > (1u << 24)) { atomicExch(err, 2); break; }   // a peer died: report instead of hanging the box
+        }
+    }
+    __syncthreads();
+    const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    const int p = recv_proc[k];
+    const int sq = psite[p];
+    const double f_new = __ldcv(recvbuf + k);   // written by a peer over NVLink: never from a stale cache line
+    const double delta = f_new - field[sq];
+    field[sq] = f_new;
+    for (int e = colptr[p]; e < colptr[p + 1]; e++) r[crow[e]] += valT[e] * delta;
+}
+
+// Fused exchange of one colour (the production path): CTA 0 first pushes this rank's boundary values into the peers'
+// receive areas and raises its flag there; every CTA then waits for the peers' flags and applies the ghost values that
+// arrived.  Launched with programmatic dependent launch between the colour kernels: griddepcontrol.launch_dependents lets the
+// next colour's sweep kernel run its r-independent prologue meanwhile, griddepcontrol.wait orders this kernel after the
+// sweep kernel whose boundary values it publishes.  epoch_ctr[0] counts completed exchanges (bumped by the last CTA to
+// leave, so every CTA of a launch reads the same value), epoch_ctr[1] is the departure counter.
+__global__ void __launch_bounds__(256) halo_exchange_kernel(PeerTable peers, const int *__restrict__ send_storage,
+                                                            const int *__restrict__ send_ptr_col, const int *__restrict__ peer_base_col,
+                                                            int world, int rank, size_t flag_off, size_t val_off,
+                                                            unsigned long long *epoch_ctr, int *err,
+                                                            const int *__restrict__ recv_proc, int k0, int k1,
+                                                            const int *__restrict__ colptr, const int *__restrict__ crow,
+                                                            const double *__restrict__ valT, const int *__restrict__ psite,
+                                                            double *field, double *r, int dbg) {
+#define EX_STAMP(slot) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = g_timeline[8191]; if (n_ < 4090) { g_timeline[2 * n_] = global_ns(); g_timeline[2 * n_ + 1] = (slot); g_timeline[8191] = n_ + 1; } } } while (0)
+    EX_STAMP(0);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    EX_STAMP(1);
+    const unsigned long long target = *reinterpret_cast<volatile unsigned long long *>(epoch_ctr) + 1ull;
+    if (blockIdx.x == 0) {
+        for (int h = 0; h < world; h++) {
+            if (h == rank) continue;
+            const int a = send_ptr_col[h], b = send_ptr_col[h + 1];
+            double *dst = peers.area[h] + val_off + peer_base_col[h];
+            for (int k = a + (int)threadIdx.x; k < b; k += (int)blockDim.x) dst[k - a] = field[send_storage[k]];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();   // cumulative over the CTA barrier: every thread's peer stores are visible system-wide
+            for (int h = 0; h < world; h++)
+                if (h != rank) st_release_sys_u64(reinterpret_cast<unsigned long long *>(peers.area[h] + flag_off) + rank, target);
+        }
+    }
+    EX_STAMP(2);
+    if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+        const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(peers.area[rank] + flag_off);
+        unsigned int spins = 0;
+        while (ld_acquire_sys_u64(flags + threadIdx.x) < target) {
+            if (++spins > (1u << 24)) { atomicExch(err, 2); break; }   // a peer died: report instead of hanging the box
+        }
+    }
+    __syncthreads();
+    EX_STAMP(3);
+    // one WARP per ghost site: the lanes stride over the site's local column, so all its r patches are in flight at once
+    // (a thread walking the column alone paid three dependent memory round trips per entry: 18 us per colour in the
+    // %globaltimer timeline)
+    const int k = k0 + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (k < k1) {
+        const int p = recv_proc[k];
+        const int sq = psite[p];
+        const double f_new = __ldcv(peers.area[rank] + val_off + k);   // written by a peer over NVLink
+        const double delta = f_new - field[sq];
+        __syncwarp();
+        if (lane == 0) field[sq] = f_new;
+        for (int e = colptr[p] + lane; e < colptr[p + 1]; e += 32) r[crow[e]] += valT[e] * delta;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long left = atomicAdd(epoch_ctr + 1, 1ull) + 1ull;
+        if (left == gridDim.x) {   // last CTA out: this exchange is complete
+            epoch_ctr[1] = 0ull;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned long long *>(epoch_ctr) = target;
+        }
+    }
+    EX_STAMP(4);
+#undef EX_STAMP
+}
+
+// all-reduce (sum) of `count` <= 4 scalars over the ranks: push the partials to every peer, then sum in rank order
+__global__ void allreduce_push_kernel(PeerTable peers, const double *__restrict__ partial, int count, int world, int rank,
+                                      size_t slot_off, size_t flag_off, unsigned long long epoch) {
+    const int h = threadIdx.x;
+    if (h < world) {
+        // two slot sets alternate with the epoch: a fast rank may already push reduction e+1 while a peer still sums e
+        double *slots = peers.area[h] + slot_off + (size_t)(epoch & 1ull) * 32 + (size_t)rank * 4;
+        for (int k = 0; k < count; k++) slots[k] = partial[k];
+        __threadfence_system();
+        st_release_sys_u64(reinterpret_cast<unsigned long long *>(peers.area[h] + flag_off) + rank, epoch);
+    }
+}
+__global__ void allreduce_wait_sum_kernel(const double *area, int count, int world, size_t slot_off, size_t flag_off,
+                                          unsigned long long epoch, int *err, double *__restrict__ out) {
+    const int h = threadIdx.x;
+    if (h < world) {
+        const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(area + flag_off);
+        unsigned int spins = 0;
+        while (ld_acquire_sys_u64(flags + h) < epoch) {
+            if (++spins > (1u << 24)) { atomicExch(err, 2); break; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < count; k++) {
+            double s = 0.0;
+            for (int g = 0; g < world; g++) s += __ldcv(area + slot_off + (size_t)(epoch & 1ull) * 32 + (size_t)g * 4 + k);   // fixed order: deterministic
+            out[k] = s;
+        }
+    }
+}
+
 __global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n) {
     spp->sweep_counter += 1ull;
     spp->z_offset += n;

@@ -137,6 +137,16 @@ struct Ctx {
     NcclApi::Comm comm = nullptr;
     std::vector<int> send_ptr, recv_ptr;   // [(colour, peer)] segments of the packed halo buffers
     std::vector<int> gstart;               // processing-index range of the ghost sites of each colour
+    // peer-to-peer transport (CUDA IPC): own area + the peers' mapped areas
+    bool p2p = false;
+    double *p2p_area = nullptr;            // [recv values | W halo flags | W reduction flags | W*4 reduction slots]
+    size_t p2p_flag_off = 0, p2p_rflag_off = 16, p2p_slot_off = 32, p2p_val_off = 96, p2p_doubles = 0;
+    PeerTable peers{};
+    void *peer_mapped[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long red_epoch = 0;
+    int graph_launches = 0;
+    DevBuf<unsigned long long> d_halo_epoch;
+    DevBuf<int> d_send_ptr, d_peer_base;   // per colour: [W+1] send offsets, [W] offsets inside the peers' receive areas
     long long nnz = 0;
     int n_sm = 148;
     long long launches_in_op = 0;
@@ -492,18 +502,53 @@ static void op_sweeps(Ctx *c, int n_sweeps, unsigned long long sweep_in_call) {
     if (n_sweeps <= 0) return;
     if (c->sharded) {
         // one spatial block of a larger field: per colour, sweep the owned sites, then exchange the boundary values with the
-        // peers that hold them as ghosts (NCCL send/recv over NVLink) and patch the local residual for what arrived
-        for (int s = 0; s < n_sweeps; s++) {
+        // peers that hold them as ghosts and patch the local residual for what arrived.  With the peer-to-peer transport
+        // nothing in the sequence depends on host-side values, so one sweep is captured once and replayed as a CUDA graph
+        // (66 plain launches per sweep were CPU-submission bound: ~40 us per colour).
+        auto one_sweep = [&]() {
             for (int col = 0; col < c->K; col++) {
                 const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
-                if (nt > 0) {
+                if (nt > 0 && c->p2p && c->world > 1) {
+                    // PDL chain: sweep(c) -> exchange(c) -> sweep(c+1) ...; the first sweep kernel is an ordinary launch
+                    cudaLaunchConfig_t lc = {};
+                    lc.gridDim = dim3(nt);
+                    lc.blockDim = dim3(128);
+                    lc.stream = c->stream;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[0].val.programmaticStreamSerializationAllowed = 1;
+                    lc.attrs = at;
+                    lc.numAttrs = (col > 0) ? 1 : 0;
+                    CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true>, (const int4 *)(c->d_tiles[1].p + t0), (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
+                } else if (nt > 0) {
                     gibbs_tile_kernel<128, 8, false><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
-                    LAUNCHED(c);
                 }
                 op_halo_exchange(c, col);
             }
             advance_sweep_kernel<<<1, 1, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global);
-            LAUNCHED(c);
+        };
+        const bool graphable = c->use_graph && (c->world == 1 || c->p2p);
+        for (int s = 0; s < n_sweeps; s++) {
+            if (graphable) {
+                if (!c->sweep_graph) {
+                    cudaGraph_t g;
+                    const long long l0 = c->launches_in_op;
+                    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                    one_sweep();
+                    CK(cudaStreamEndCapture(c->stream, &g));
+                    CK(cudaGraphInstantiate(&c->sweep_graph, g, 0));
+                    CK(cudaGraphDestroy(g));
+                    c->graph_launches = (int)(c->launches_in_op - l0) + c->K + 1;
+                    c->launches_in_op = l0;
+                }
+                CK(cudaGraphLaunch(c->sweep_graph, c->stream));
+                g_launches.fetch_add(c->graph_launches, std::memory_order_relaxed);
+                c->launches_in_op += c->graph_launches;
+            } else {
+                one_sweep();
+                g_launches.fetch_add(c->K + 1, std::memory_order_relaxed);
+                c->launches_in_op += c->K + 1;
+            }
         }
         CK(cudaGetLastError());
         return;
@@ -576,6 +621,7 @@ static void check_solve_flag(Ctx *c) {
     CK(cudaMemcpyAsync(c->h_pinned + 9, c->d_nbad.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     std::memcpy(&flag, c->h_pinned + 9, sizeof(int));
+    if (flag == 2) { set_error("sharded field: timed out waiting for a peer's halo / reduction flag (a rank died or fell out of step)"); throw NcclFail(); }
     if (flag) { set_error("triangular solve: dependency wait timed out (corrupted neighbour structure?)"); throw CudaFail(); }
 }
 
@@ -602,6 +648,14 @@ static void op_beta0_sums(Ctx *c, int scal_off) {
 }
 
 static void allreduce_scalars(Ctx *c, int off, int count) {
+    if (c->sharded && c->world > 1 && c->p2p) {
+        c->red_epoch++;
+        allreduce_push_kernel<<<1, 32, 0, c->stream>>>(c->peers, c->d_scalars.p + off, count, c->world, c->rank, c->p2p_slot_off, c->p2p_rflag_off, c->red_epoch);
+        LAUNCHED(c);
+        allreduce_wait_sum_kernel<<<1, 32, 0, c->stream>>>(c->p2p_area, count, c->world, c->p2p_slot_off, c->p2p_rflag_off, c->red_epoch, c->d_nbad.p + 1, c->d_scalars.p + off);
+        LAUNCHED(c);
+        return;
+    }
     if (!c->sharded || c->world == 1 || !c->comm) return;   // without a communicator the caller sums the per-rank partials
     NCK(g_nccl.AllReduce(c->d_scalars.p + off, c->d_scalars.p + off, (size_t)count, kNcclFloat64, kNcclSum, c->comm, c->stream));
 }
@@ -609,6 +663,25 @@ static void allreduce_scalars(Ctx *c, int off, int count) {
 // halo exchange for colour `col` (0-based) of a sharded field
 static void op_halo_exchange(Ctx *c, int col) {
     if (!c->sharded || c->world == 1) return;
+    if (c->p2p) {
+        const int W = c->world;
+        const int r0 = c->recv_ptr[(size_t)col * W], r1 = c->recv_ptr[(size_t)(col + 1) * W];
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(std::max(1, (r1 - r0 + 7) / 8));   // one warp per ghost site, 8 warps per CTA
+        lc.blockDim = dim3(256);
+        lc.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&lc, halo_exchange_kernel, c->peers, (const int *)c->d_send_storage.p, (const int *)(c->d_send_ptr.p + (size_t)col * W),
+                              (const int *)(c->d_peer_base.p + (size_t)col * W), W, c->rank, c->p2p_flag_off, c->p2p_val_off, c->d_halo_epoch.p,
+                              c->d_nbad.p + 1, (const int *)c->d_recv_proc.p, r0, r1, (const int *)c->d_colptr.p, (const int *)c->d_crow.p,
+                              (const double *)c->d_valT.p, (const int *)c->d_psite.p, c->d_field.p, c->d_r.p, c->debug_timeline ? 1 : 0));
+        LAUNCHED(c);
+        return;
+    }
     if (!c->comm) { set_error("this sharded context has no NCCL communicator: drive it with the nngp_shard_* colour-stepping entry points"); throw StateFail(); }
     const int W = c->world;
     const int s0 = c->send_ptr[(size_t)col * W], s1 = c->send_ptr[(size_t)(col + 1) * W];
@@ -651,7 +724,11 @@ static void destroy_ctx(Ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->sweep_graph) cudaGraphExecDestroy(c->sweep_graph);
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
-    c->d_send_storage.release(); c->d_recv_proc.release(); c->d_sendbuf.release(); c->d_recvbuf.release(); c->d_owned.release();
+    for (int h = 0; h < 8; h++) if (c->peer_mapped[h]) cudaIpcCloseMemHandle(c->peer_mapped[h]);
+    c->d_recvbuf.p = nullptr;
+    if (c->p2p_area) cudaFree(c->p2p_area);
+    c->d_send_ptr.release(); c->d_peer_base.release(); c->d_halo_epoch.release();
+    c->d_send_storage.release(); c->d_recv_proc.release(); c->d_sendbuf.release(); c->d_owned.release();
     DevBuf<int> *ib[] = {&c->d_psite, &c->d_gid, &c->d_i2g, &c->d_g2i, &c->d_nn, &c->d_colptr, &c->d_crow, &c->d_csrc, &c->d_zpos, &c->d_lvl_rows, &c->d_lvl_ptr,
                          &c->d_lm, &c->d_optr, &c->d_oidx, &c->d_cstart, &c->d_partial_rows, &c->d_nbad};
     for (auto *b : ib) b->release();
@@ -999,7 +1076,23 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         c->d_recv_proc.upload(recv_proc, s);
         c->d_owned.upload(owned_storage, s);
         c->d_sendbuf.alloc(std::max<size_t>(send_storage.size(), 1));
-        c->d_recvbuf.alloc(std::max<size_t>(recv_proc.size(), 1));
+        // the receive values live at the head of one plain cudaMalloc area that peers can map through CUDA IPC
+        REQUIRE(W <= 8, "at most 8 ranks per field");
+        // fixed header so that every rank knows where its peers' flags are: [16 halo flags | 16 reduction flags |
+        // 2 x 32 reduction slots | receive values ...]
+        const size_t nrecv = std::max<size_t>(recv_proc.size(), 1);
+        c->p2p_flag_off = 0;
+        c->p2p_rflag_off = 16;
+        c->p2p_slot_off = 32;
+        c->p2p_val_off = 96;
+        c->p2p_doubles = std::max<size_t>(c->p2p_val_off + nrecv, (size_t)1 << 18);   // >= 2 MB: a whole allocation of its own
+        CK(cudaMalloc(&c->p2p_area, c->p2p_doubles * sizeof(double)));
+        CK(cudaMemsetAsync(c->p2p_area, 0, c->p2p_doubles * sizeof(double), s));
+        c->d_recvbuf.p = c->p2p_area + c->p2p_val_off;      // not owned by the DevBuf (released with the area)
+        c->d_recvbuf.n = 0;
+        c->d_send_ptr.upload(c->send_ptr, s);
+        c->d_halo_epoch.alloc(2);
+        CK(cudaMemsetAsync(c->d_halo_epoch.p, 0, 2 * sizeof(unsigned long long), s));
         CK(cudaStreamSynchronize(s));
         if (W > 1 && sh->comm_id[0] != '\0') {   // collective: every rank of the field creates its context at the same time
             nccl_load();
@@ -1070,7 +1163,11 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         case NNGP_OPT_MATERN_TABLE: c->matern_table = (*value != 0); break;
         case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "commit variant must be 0..1"); c->commit_variant = *value; break;
         case NNGP_OPT_SOLVE_WINDOW_CTAS: REQUIRE(*value >= 0 && *value <= 4096, "solve window must be 0..4096 CTAs"); c->solve_window_ctas = *value; break;
-        case NNGP_OPT_DEBUG_TIMELINE: c->debug_timeline = (*value != 0); break;
+        case NNGP_OPT_DEBUG_TIMELINE: {
+            c->debug_timeline = (*value != 0);
+            long long zero = 0;
+            if (c->debug_timeline) CK(cudaMemcpyToSymbol(g_timeline, &zero, sizeof(long long), sizeof(long long) * 8191));
+        } break;
         case NNGP_OPT_SOLVE_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "solve sleep must be 0..100000 ns"); c->solve_sleep_ns = *value; break;
         default: REQUIRE(false, "unknown option key %d", *key);
     }
@@ -1290,6 +1387,43 @@ void nngp_gibbs_sweep(const int *ctx_id, const int *n_sweeps, const double *beta
     op_sweeps(c, *n_sweeps, 0);
     c->sweep_counter += (unsigned long long)*n_sweeps;
     CK(cudaStreamSynchronize(c->stream));
+    if (c->p2p) check_solve_flag(c);
+    ABI_END
+}
+
+void nngp_shard_p2p_export(const int *ctx_id, char *handle64, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(handle64 != nullptr, "nngp_shard_p2p_export: null buffer");
+    NEED(c->sharded && c->p2p_area, "nngp_shard_p2p_export: not a sharded context");
+    use(c);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->p2p_area));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    std::memcpy(handle64, &h, 64);
+    ABI_END
+}
+
+void nngp_shard_p2p_connect(const int *ctx_id, const char *all_handles, const int *peer_recv_base, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(all_handles && peer_recv_base, "nngp_shard_p2p_connect: null argument");
+    NEED(c->sharded && c->p2p_area, "nngp_shard_p2p_connect: not a sharded context");
+    use(c);
+    const int W = c->world;
+    for (int h = 0; h < W; h++) {
+        if (h == c->rank) { c->peers.area[h] = c->p2p_area; continue; }
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, all_handles + (size_t)h * 64, 64);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_mapped[h] = p;
+        c->peers.area[h] = static_cast<double *>(p);
+    }
+    std::vector<int> base(peer_recv_base, peer_recv_base + (size_t)c->K * W);
+    c->d_peer_base.upload(base, c->stream);
+    CK(cudaStreamSynchronize(c->stream));
+    c->p2p = true;
     ABI_END
 }
 

@@ -51,6 +51,22 @@ class ShardedContext(NNGPContext):
         self.n_colors, self.n_levels, self.nnz, self.max_col = info[2], info[3], info[4], info[5]
         self.device, self.layout = info[6], info[7]
 
+    # ---- peer-to-peer transport (CUDA IPC over NVLink)
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._call("nngp_shard_p2p_export", buf)
+        return buf.raw
+
+    def p2p_connect(self, all_handles: list, all_recv_ptr: list):
+        W, K = self.world, self.plan["n_colors"]
+        base = np.zeros(K * W, dtype=np.int32)
+        for c in range(K):
+            for h in range(W):
+                if h != self.rank:
+                    base[c * W + h] = all_recv_ptr[h][c * W + self.rank]
+        blob = C.create_string_buffer(b"".join(all_handles), 64 * W)
+        self._call("nngp_shard_p2p_connect", blob, L.iptr(base))
+
     # ---- colour-stepping sweep (caller-moved halo)
     def sweep_begin(self, beta_0, log_scale, log_noise_variance, z=None, seed=0):
         if z is None:
@@ -115,12 +131,19 @@ def host_routed_sweep(contexts, beta_0, log_scale, log_noise_variance, z=None, s
         c.sweep_end()
 
 
-def create_sharded_distributed(locs, NNarray, coloring, locs_match, covfun_name, device, dist):
-    """torch.distributed driver: every rank calls this with the same (replicated) global structure; rank 0's NCCL id is
-    broadcast; returns (ShardedContext, plan)."""
+def create_sharded_distributed(locs, NNarray, coloring, locs_match, covfun_name, device, dist, transport="p2p"):
+    """torch.distributed driver: every rank calls this with the same (replicated) global structure.  transport "p2p" maps the
+    peers' receive areas through CUDA IPC (halo values are stored straight into the peers' memory over NVLink); "nccl"
+    uses ncclSend/ncclRecv per colour (rank 0's NCCL id is broadcast).  Returns (ShardedContext, plan)."""
     rank, world = dist.get_rank(), dist.get_world_size()
     owner = spatial_blocks(locs, world)
     plan = shard_plan(locs, NNarray, coloring, locs_match, owner, rank, world)
-    box = [comm_unique_id() if rank == 0 else None]
+    box = [comm_unique_id() if (rank == 0 and transport == "nccl") else None]
     dist.broadcast_object_list(box, src=0)
-    return ShardedContext(plan, covfun_name, device=device, comm_id=box[0]), plan
+    ctx = ShardedContext(plan, covfun_name, device=device, comm_id=box[0])
+    if transport == "p2p" and world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, (ctx.p2p_export(), plan["recv_ptr"]))
+        ctx.p2p_connect([h[0] for h in handles], [h[1] for h in handles])
+        dist.barrier()   # nobody pushes before everybody has mapped everybody
+    return ctx, plan

@@ -109,6 +109,13 @@ void nngp_ctx_create_sharded(const int *n, const int *d, const int *m, const dou
                              const int *covfun_id, const int *device, const int *layout, const int *world, const int *rank,
                              const int *send_site, const int *send_ptr, const int *recv_site, const int *recv_ptr,
                              const char *comm_id128, int *ctx_id, int *status);
+/* Peer-to-peer transport for the halo and the scalar all-reduces (preferred inside one NVLink box): every rank exports the
+ * CUDA IPC handle (64 bytes) of its receive area, the handles are gathered by the caller, and every rank connects with the
+ * table of all handles (world * 64 bytes, rank order) plus peer_recv_base[c*world + h] = offset of this rank's colour-c
+ * segment inside peer h's receive area (= peer h's recv_ptr[c*world + this rank]).  Afterwards the sweep kernels' boundary
+ * values are stored directly into the peers' ghost buffers over NVLink and flags replace the NCCL calls. */
+void nngp_shard_p2p_export(const int *ctx_id, char *handle64, int *status);
+void nngp_shard_p2p_connect(const int *ctx_id, const char *all_handles, const int *peer_recv_base, int *status);
 /* Colour-stepping form of one sharded sweep for callers that move the halo themselves (any transport; also how the sharded
  * arithmetic is tested on a single GPU).  Create the contexts with an empty comm_id (first byte 0) to skip NCCL.
  * begin -> for colour in 1..K: sweep_colour; halo_get (packed send buffer of that colour, all peers, send_ptr order);

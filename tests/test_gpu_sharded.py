@@ -107,7 +107,7 @@ def test_single_rank_sharded_context_is_the_plain_one():
             c.sptrsv(z)                                          # not available on sharded contexts
 
 
-def _nccl_worker(rank, world, port, q):
+def _nccl_worker(rank, world, port, q, transport="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch
     import torch.distributed as dist
@@ -117,7 +117,7 @@ def _nccl_worker(rank, world, port, q):
         P = make_problem(40000, 10, seed=8)
         n = P["n"]
         z = np.random.default_rng(1).standard_normal(2 * n)
-        ctx, plan = nb.create_sharded_distributed(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], "exponential_isotropic", rank, dist)
+        ctx, plan = nb.create_sharded_distributed(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], "exponential_isotropic", rank, dist, transport=transport)
         ctx.factor_build(CP)
         ctx.factor_commit()
         ctx.field_set(P["field"][plan["local_sites"]])
@@ -136,7 +136,8 @@ def _nccl_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_nccl_sharded_sweep_on_two_gpus():
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+def test_nccl_sharded_sweep_on_two_gpus(transport):
     if nb.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
@@ -145,7 +146,7 @@ def test_nccl_sharded_sweep_on_two_gpus():
         port = s.getsockname()[1]
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
-    procs = [mpc.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [mpc.Process(target=_nccl_worker, args=(r, 2, port, q, transport)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
