@@ -74,3 +74,41 @@ def test_config1b_no_regressor_chain_and_prediction():
     assert pred["predicted_field_summary"].shape == (300, 5)
     assert np.corrcoef(pred["predicted_field_summary"][:, 0], w[:300])[0, 1] > 0.85
     nb.release_contexts(lst)
+
+
+def test_config2_heavy_metals_subset_runs_end_to_end():
+    """config 2 (Heavy_metals/run_script.R:8-15): real lon/lat data, exponential_sphere, m = 5, 3 chains, field_thinning .5,
+    11 numeric + 3 factor location regressors (tests/golden/heavy_metals_subset.npz: 12 000 of the 64 274 observations,
+    written by tests/golden/make_heavy_metals_fixture.py).  The reference ships no outputs for this run (myfit.RDS is not in
+    the repo), so this is an acceptance run: schema, finiteness, variance budget, chains agreeing."""
+    import os
+    import pandas as pd
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "heavy_metals_subset.npz"), allow_pickle=False)
+    df = pd.DataFrame(z["X_numeric"], columns=[str(s) for s in z["numeric_names"]])
+    for k in ("minotype", "glwd31", "MAJOR1"):
+        lv = z[f"levels_{k}"]
+        df[k] = pd.Categorical(lv[z[f"factor_{k}"] - 1])          # observed levels only (model.matrix drops nothing else)
+    lst = nb.mcmc_nngp_initialize(z["observed_locs"], z["observed_field"], X_locs=df, stationary_covfun="exponential_sphere", m=5, n_chains=3, seed=1)
+    va = lst["vecchia_approx"]
+    assert va["n_obs"] == 12000 and va["n_locs"] <= 12000
+    assert lst["space_time_model"]["covfun"]["shape_params"] == ["log_range"]
+    assert lst["X"]["locs"] == list(range(14))                     # quirk: X$locs = seq(ncol(X_locs)) before factor expansion
+    lst = nb.mcmc_nngp_run(lst, n_cycles=3, n_iterations_update=100, field_thinning=.5, Gelman_Rubin_Brooks_stop=(1.0, 1.0), verbose=False)
+    for name, ch in lst["records"].items():
+        assert ch["params"]["beta"].shape == (300, lst["X"]["X"].shape[1])
+        assert ch["params"]["field"].shape == (150, va["n_locs"])
+        for k in ("beta_0", "log_scale", "log_noise_variance", "shape", "beta", "field"):
+            assert np.all(np.isfinite(ch["params"][k])), (name, k)
+    assert len(lst["diagnostics"]["Gelman_Rubin_Brooks"]) == 3
+    est = nb.mcmc_nngp_estimate(lst, burn_in=.5)
+    g = dict(zip(est["covariance_params"]["GpGp_covparams"]["names"], est["covariance_params"]["GpGp_covparams"]["summary"][:, 0]))
+    # variance budget: spatial scale + noise variance explain the residual variance left by the regressors (same order)
+    D = np.column_stack([np.ones(12000), lst["X"]["X"]])
+    resid = z["observed_field"] - D @ np.linalg.lstsq(D, z["observed_field"], rcond=None)[0]
+    vr = float(np.var(resid, ddof=1))
+    assert 0.3 * vr < g["noise_variance"] + g["scale"] < 3.0 * vr, (g, vr)
+    assert g["noise_variance"] > 0.02 * vr and g["scale"] > 0.02 * vr, (g, vr)
+    assert 1e-5 < g["range"] < 1.0, g                              # chordal range in units of the sphere radius
+    last = np.array([ch["params"]["log_noise_variance"][-50:].mean() for ch in lst["records"].values()])
+    assert np.ptp(last) < 0.5                                      # the three chains sit in the same region
+    nb.release_contexts(lst)
