@@ -322,6 +322,96 @@ __global__ void __launch_bounds__(256) loglik_partial_kernel(const int *__restri
     if (threadIdx.x == 0) partials[blockIdx.x] = make_double2(acc[0], acc[1]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-staged variant of the log-likelihood pass.  The slot-major tables make a tile of TR rows M contiguous segments of
+// nn (TR*4 B each) and M of linv (TR*8 B each); one elected thread fetches them with cp.async.bulk (the TMA engine's 1-D
+// bulk copy, SASS UBLKCP) into a STAGES-deep shared-memory ring, completion is tracked by an mbarrier per stage
+// (complete_tx::bytes), and the 256 consumer threads -- one row each -- read their indices / coefficients from shared
+// memory and gather the field from L2.  The plain kernel keeps ~22 coalesced loads per thread in flight behind the
+// gathers and reached 49 % of DRAM peak in ncu (latency bound); here the streaming part runs ahead of the consumers
+// with no register cost, so DRAM stays busy while the gathers of the previous tile resolve.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned int bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
+    unsigned int done, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();   // a lost completion must surface as an error, never as a hung device
+    } while (!done);
+}
+
+template <int MT, int STAGES>
+__global__ void __launch_bounds__(256) loglik_tma_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
+                                                         const double *__restrict__ field, double shift, int n, int ld,
+                                                         const unsigned char *__restrict__ row_mask,
+                                                         double2 *__restrict__ partials) {
+    constexpr int TR = 256;
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    double *lin_s = reinterpret_cast<double *>(tma_smem);                                   // [STAGES][MT][TR]
+    int *nn_s = reinterpret_cast<int *>(tma_smem + (size_t)STAGES * MT * TR * 8);           // [STAGES][MT][TR]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(tma_smem + (size_t)STAGES * MT * TR * 12);
+    const int tid = threadIdx.x;
+    const int n_tiles = (n + TR - 1) / TR;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    auto issue = [&](int i) {   // elected thread: fetch this CTA's i-th tile into stage i % STAGES
+        const int stage = i % STAGES;
+        const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * TR;
+        const int rows = min(TR, ld - row0);   // ld is a multiple of 32: every segment is a multiple of 128 B
+        mbar_arrive_expect_tx(full + stage, (unsigned int)(MT * rows * 12));
+#pragma unroll
+        for (int j = 0; j < MT; j++) {
+            tma_bulk_g2s(lin_s + ((size_t)stage * MT + j) * TR, linv + (size_t)j * ld + row0, (unsigned int)(rows * 8), full + stage);
+            tma_bulk_g2s(nn_s + ((size_t)stage * MT + j) * TR, nn + (size_t)j * ld + row0, (unsigned int)(rows * 4), full + stage);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 0; i < STAGES && i < my_tiles; i++) issue(i);
+
+    double acc[2] = {0.0, 0.0};
+    for (int i = 0; i < my_tiles; i++) {
+        const int stage = i % STAGES;
+        mbar_wait(full + stage, (unsigned int)((i / STAGES) & 1));
+        const int q = ((int)blockIdx.x + i * (int)gridDim.x) * TR + tid;
+        if (q < n && (!row_mask || row_mask[q])) {
+            int idx[MT];
+            double a[MT];
+#pragma unroll
+            for (int j = 0; j < MT; j++) {
+                idx[j] = nn_s[((size_t)stage * MT + j) * TR + tid];
+                a[j] = lin_s[((size_t)stage * MT + j) * TR + tid];
+            }
+            double u = 0.0;
+#pragma unroll
+            for (int j = 0; j < MT; j++)
+                if (idx[j] >= 0) u += a[j] * (field[idx[j]] - shift);
+            acc[0] += log(a[0]);
+            acc[1] += u * u;
+        }
+        __syncthreads();                                   // every consumer is done with this stage ...
+        if (tid == 0 && i + STAGES < my_tiles) issue(i + STAGES);   // ... so the TMA engine may refill it
+    }
+    block_reduce_sum<2>(acc);
+    if (tid == 0) partials[blockIdx.x] = make_double2(acc[0], acc[1]);
+}
+
 // generic final reduction of NV-vectors of per-block partials: out[k] = sum_b partials[b*NV + k]
 template <int NV>
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__restrict__ partials, int n_blocks, double *__restrict__ out) {

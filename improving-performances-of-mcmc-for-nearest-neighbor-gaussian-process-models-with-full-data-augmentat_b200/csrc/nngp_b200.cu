@@ -165,6 +165,10 @@ struct Ctx {
     int sweep_variant = 6;                 // PDL chain of 128x8 tile launches: measured fastest at n = 1M (profiles/)
     int solve_variant = 0;                 // 0 sync-free single launch, 1 level-scheduled launches
     int commit_variant = 0;                // 0 tiled transposition, 1 thread per column
+    // 1 plain coalesced loads (default), 0 TMA-staged ring.  Measured on B200 (profiles/r01_explore_final.txt): the TMA ring is
+    // SLOWER (44.7 vs 37.3 us at n = 1M, 128 vs 100 us at 4M, 96 vs 55 us at m = 20): the pass is bound by the latency of
+    // the 8-byte field gathers, which wants 2048 resident threads per SM; a 100 KB ring leaves room for 512.
+    int loglik_variant = 1;
     int n_slots = 0;                       // padded length of the level-ordered row list
     int solve_ctas_per_sm = 1;             // window of the sync-free solve = n_sm * this * 256 rows
     int solve_window_ctas = 0;             // if > 0: absolute number of CTAs (overrides the per-SM setting)
@@ -398,10 +402,29 @@ static const int kReduceBlocks = 148 * 8;
 static void allreduce_scalars(Ctx *c, int off, int count);
 static void op_halo_exchange(Ctx *c, int col);
 
+template <int MT, int STAGES>
+static bool launch_loglik_tma(Ctx *c, const double *linv, const double *field, double shift, int *blocks_out) {
+    const size_t smem = (size_t)STAGES * MT * 256 * 12 + 64;
+    CK(cudaFuncSetAttribute(loglik_tma_kernel<MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
+    const int per_sm = std::max(1, (int)((size_t)220 * 1024 / smem));
+    const int blocks = std::max(1, std::min(c->n_sm * per_sm, (c->n + 255) / 256));
+    loglik_tma_kernel<MT, STAGES><<<blocks, 256, smem, c->stream>>>(c->d_nn.p, linv, field, shift, c->n, c->ld, c->sharded ? c->d_owned.p : nullptr, reinterpret_cast<double2 *>(c->d_partials.p));
+    *blocks_out = blocks;
+    return true;
+}
+
 // partial sums -> d_scalars[off..off+1]
 static void op_loglik_sums(Ctx *c, const double *linv, const double *field, double shift, int scal_off) {
-    const int blocks = std::min(kReduceBlocks, (c->n + 255) / 256);
-    DISPATCH_MT(c->M, (loglik_partial_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, field, shift, c->n, c->ld, c->M, c->sharded ? c->d_owned.p : nullptr, reinterpret_cast<double2 *>(c->d_partials.p))));
+    int blocks = std::min(kReduceBlocks, (c->n + 255) / 256);
+    bool done = false;
+    if (c->loglik_variant == 0) {   // TMA-staged ring (specialised neighbour counts only)
+        if (c->M == 6) done = launch_loglik_tma<6, 4>(c, linv, field, shift, &blocks);
+        else if (c->M == 11) done = launch_loglik_tma<11, 3>(c, linv, field, shift, &blocks);
+        else if (c->M == 21) done = launch_loglik_tma<21, 2>(c, linv, field, shift, &blocks);
+    }
+    if (!done) {
+        DISPATCH_MT(c->M, (loglik_partial_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, field, shift, c->n, c->ld, c->M, c->sharded ? c->d_owned.p : nullptr, reinterpret_cast<double2 *>(c->d_partials.p))));
+    }
     LAUNCHED(c);
     reduce_partials_kernel<2><<<1, 1024, 0, c->stream>>>(c->d_partials.p, blocks, c->d_scalars.p + scal_off);
     LAUNCHED(c);
@@ -1160,6 +1183,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;
+        case NNGP_OPT_LOGLIK_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "loglik variant must be 0..1"); c->loglik_variant = *value; break;
         case NNGP_OPT_MATERN_TABLE: c->matern_table = (*value != 0); break;
         case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "commit variant must be 0..1"); c->commit_variant = *value; break;
         case NNGP_OPT_SOLVE_WINDOW_CTAS: REQUIRE(*value >= 0 && *value <= 4096, "solve window must be 0..4096 CTAs"); c->solve_window_ctas = *value; break;

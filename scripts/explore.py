@@ -62,6 +62,11 @@ def main():
         ms, nl = ctx.time_op("commit", reps=a.reps)
         print(f"  commit (thread per column): mean {ms.mean()*1e3:8.1f} us")
         ctx.set_option("commit_variant", 0)
+        ctx.set_option("loglik_variant", 0)
+        ms, nl = ctx.time_op("loglik", reps=a.reps)
+        ms2, _ = ctx.time_op("loglik", reps=a.reps, flush_l2=True)
+        print(f"  loglik (TMA-staged ring)  : mean {ms.mean()*1e3:8.1f} us  min {ms.min()*1e3:8.1f} us  (L2 flushed: {ms2.mean()*1e3:8.1f} us)")
+        ctx.set_option("loglik_variant", 1)
         for op in ("loglik", "spmv", "factor_build", "commit", "sweep_loglik"):
             ctx.time_op(op, reps=2)
             ms, nl = ctx.time_op(op, reps=a.reps)

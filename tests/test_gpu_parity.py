@@ -337,3 +337,18 @@ def test_matern_table_matches_direct_bessel_and_oracle(nu, m):
     assert rel_rows(Lt, Lo) < TOL
     assert rel_rows(Ld, Lo) < TOL
     assert rel_rows(Lt, Ld) < TOL      # smoother kernels have worse-conditioned blocks: 1e-15 kernel differences show up at 1e-11
+
+
+@pytest.mark.parametrize("m", [5, 10, 20])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_both_loglik_variants(variant, m):
+    """plain coalesced loads vs the TMA-staged ring (cp.async.bulk + mbarrier): same partial sums, ragged last tile included"""
+    P = make_problem(10007, m, seed=23)
+    cp = [1.0, 0.05, 0.0]
+    Lo = O.vecchia_Linv(cp, "exponential_isotropic", P["locs"], P["NNarray"])
+    ll_o = O.ll_compressed_sparse_chol(Lo, P["field"] - 0.3, P["NNarray"], 0.2)
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.set_option("loglik_variant", variant)
+        ctx.factor_build(cp)
+        ctx.field_set(P["field"])
+        assert abs(ctx.loglik(0.3, 0.2) - ll_o) < TOL * abs(ll_o)
