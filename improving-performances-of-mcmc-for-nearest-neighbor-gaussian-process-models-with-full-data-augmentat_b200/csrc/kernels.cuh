@@ -150,8 +150,8 @@ __device__ __forceinline__ double kernel_value(const CovConst &cc, double dist) 
 // Operation order = oracle_vecchia_linv (oracle/nngp_oracle.c): neighbours farthest-first, self last; row-by-row Cholesky;
 // back-substitution for the last row of L^-1.
 // ---------------------------------------------------------------------------------------------------------------
-template <int M, int DT, bool MATERN>
-__global__ void __launch_bounds__(128) vecchia_factor_reg_kernel(const int *__restrict__ nn, const double *__restrict__ tl,
+template <int M, int DT, bool MATERN, int MINB = 3>
+__global__ void __launch_bounds__(128, MINB) vecchia_factor_reg_kernel(const int *__restrict__ nn, const double *__restrict__ tl,
                                                                  double *__restrict__ linv, int n, int ld, CovConst cc,
                                                                  int *__restrict__ n_bad) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;

@@ -169,6 +169,7 @@ struct Ctx {
     // SLOWER (44.7 vs 37.3 us at n = 1M, 128 vs 100 us at 4M, 96 vs 55 us at m = 20): the pass is bound by the latency of
     // the 8-byte field gathers, which wants 2048 resident threads per SM; a 100 KB ring leaves room for 512.
     int loglik_variant = 1;
+    int factor_variant = 0;                // m = 10, d = 2: 0 = 3 CTAs/SM (162 registers), 1 = capped at 128, 2 = capped at 96
     int n_slots = 0;                       // padded length of the level-ordered row list
     int solve_ctas_per_sm = 1;             // window of the sync-free solve = n_sm * this * 256 rows
     int solve_window_ctas = 0;             // if > 0: absolute number of CTAs (overrides the per-SM setting)
@@ -342,15 +343,25 @@ static void launch_factor(Ctx *c, double *linv, const CovConst &cc) {
     bool specialised = false;
     const int blk = 128, grd = (n + blk - 1) / blk;
 #define FACTOR_CASE(MM, DD)                                                                                              \
-    if (M == MM && c->dt == DD) {                                                                                        \
+    if (!specialised && M == MM && c->dt == DD) {                                                                                        \
         vecchia_factor_reg_kernel<MM, DD, MATERN><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p); \
         specialised = true;                                                                                              \
     }
+    if (M == 11 && c->dt == 2 && c->factor_variant == 1) {   // occupancy experiment: cap at 128 registers (4 CTAs / SM)
+        vecchia_factor_reg_kernel<11, 2, MATERN, 4><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
+        specialised = true;
+    } else if (M == 11 && c->dt == 2 && c->factor_variant == 2) {   // ... or at 96 registers (5 CTAs / SM)
+        vecchia_factor_reg_kernel<11, 2, MATERN, 5><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
+        specialised = true;
+    } else
     FACTOR_CASE(6, 2)
     FACTOR_CASE(6, 3)
     FACTOR_CASE(11, 2)
     FACTOR_CASE(11, 3)
-    FACTOR_CASE(21, 2)
+    if (!specialised && M == 21 && c->dt == 2) {   // 231-entry triangle: let ptxas use all 255 registers (spills to L1 beyond)
+        vecchia_factor_reg_kernel<21, 2, MATERN, 1><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
+        specialised = true;
+    }
 #undef FACTOR_CASE
     if (specialised) {
         LAUNCHED(c);
@@ -1183,6 +1194,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;
+        case NNGP_OPT_FACTOR_VARIANT: REQUIRE(*value >= 0 && *value <= 2, "factor variant must be 0..2"); c->factor_variant = *value; break;
         case NNGP_OPT_LOGLIK_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "loglik variant must be 0..1"); c->loglik_variant = *value; break;
         case NNGP_OPT_MATERN_TABLE: c->matern_table = (*value != 0); break;
         case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "commit variant must be 0..1"); c->commit_variant = *value; break;
@@ -1676,8 +1688,10 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
     op_factor_build(c, NNGP_SLOT_CURRENT, to_covparms(shape));                   // :72
     op_commit(c);                                                                // :73-74
     std::vector<double> zhost;
-    if (rng_mode == NNGP_RNG_SUPPLIED) { zhost.resize(n); rs.rnorm(zhost.data(), n); }   // :75 current_p consumes n normals
-    else for (int i = 0; i < n; i++) (void)rs.norm_rand();
+    // :75 current_p = rnorm(n_locs) is dead code in the reference but consumes n draws of R's stream.  In NNGP_RNG_SUPPLIED mode
+    // (bit-comparable with R) they are consumed too; in Philox mode the field draws differ from R's anyway, so the 15-20 ms of
+    // host RNG per call (n = 1M) are skipped and the scalar draws simply continue from the seeded state.
+    if (rng_mode == NNGP_RNG_SUPPLIED) { zhost.resize(n); rs.rnorm(zhost.data(), n); }
     std::vector<int> acc_anc(n_iter + 1, 0), acc_suf(n_iter + 1, 0);
     const int n_frec = (int)std::nearbyint(n_iter * thin);
     const unsigned long long philox_seed = ((unsigned long long)(uint32_t)iter_start << 20) ^ (unsigned long long)(uint32_t)*chain_index_;

@@ -143,6 +143,7 @@ void nngp_shard_sweep_end(const int *ctx_id, int *status);
 #define NNGP_OPT_COMMIT_VARIANT 8     /* accept-branch transposition: 0 = tiled (default), 1 = thread per column */
 #define NNGP_OPT_MATERN_TABLE 9       /* Matern families: 1 = per-build interpolation table of the kernel (default), 0 = K_nu per pair */
 #define NNGP_OPT_LOGLIK_VARIANT 10    /* log-lik pass: 1 = plain coalesced loads (default, faster); 0 = TMA-staged shared-memory ring (cp.async.bulk + mbarrier) */
+#define NNGP_OPT_FACTOR_VARIANT 11    /* m = 10, d = 2 factor kernel register cap: 0 = none (default), 1 = 128, 2 = 96 registers */
 #define NNGP_OPT_DEBUG_TIMELINE 6    /* development aid: the persistent sweep kernel stamps %globaltimer per stage */
 void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);
 /* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,

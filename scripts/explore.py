@@ -62,6 +62,11 @@ def main():
         ms, nl = ctx.time_op("commit", reps=a.reps)
         print(f"  commit (thread per column): mean {ms.mean()*1e3:8.1f} us")
         ctx.set_option("commit_variant", 0)
+        for fv in (1, 2, 0):
+            ctx.set_option("factor_variant", fv)
+            ctx.time_op("factor_build", reps=2)
+            ms, nl = ctx.time_op("factor_build", reps=a.reps)
+            print(f"  factor_build variant={fv}: mean {ms.mean()*1e3:8.1f} us  min {ms.min()*1e3:8.1f} us")
         ctx.set_option("loglik_variant", 0)
         ms, nl = ctx.time_op("loglik", reps=a.reps)
         ms2, _ = ctx.time_op("loglik", reps=a.reps, flush_l2=True)
