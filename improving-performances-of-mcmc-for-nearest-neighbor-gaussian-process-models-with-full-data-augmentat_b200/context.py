@@ -193,6 +193,13 @@ class NNGPContext:
         frec_m = frec[: n_frec * self.n].reshape((n_frec, self.n), order="F") if keep_field else None
         return out, rec.reshape((n_iter, 3 + shape.size), order="F"), frec_m, acc.reshape((n_iter, 2), order="F")
 
+    def records_summary(self, first_row: int, n_rows: int, offsets=None) -> np.ndarray:
+        """get_summary (estimate.R:1-6) of the field samples kept on the device by the last chain_run; n x 5"""
+        out = np.empty(self.n * 5)
+        off = None if offsets is None else L.f64(offsets)
+        self._call("nngp_records_summary", L.ci(first_row), L.ci(n_rows), None if off is None else L.dptr(off), L.dptr(out))
+        return out.reshape((self.n, 5), order="F")
+
     def predict_sample(self, n_obs_sites, field, beta_0, log_scale, z_pred, slot=L.SLOT_CURRENT):
         f = L.f64(field)
         z = L.f64(z_pred)

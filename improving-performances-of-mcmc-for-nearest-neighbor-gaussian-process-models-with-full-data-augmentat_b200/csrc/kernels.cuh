@@ -108,6 +108,50 @@ __global__ void linv_to_host_order_kernel(double *__restrict__ dst, const double
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// device-side record store (records$field of update_Gaussian.R:56,311): stored samples are written
+// straight into the final R layout (n_rec x n, column-major, reference site order) in HBM and leave the device in one copy
+// at the end of the cycle, instead of one download + strided host scatter per stored sample.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void record_field_kernel(double *__restrict__ rec, const double *__restrict__ field, const int *__restrict__ g2i,
+                                    int row, int n_rec, int n) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+        rec[(size_t)row + (size_t)n_rec * t] = field[g2i[t]];
+}
+
+// Posterior summary of the stored samples of every site, on the device (get_summary, Scripts/mcmc_nngp_estimate.R:1-6 applied
+// to records$field as in :88-94): mean, quantiles 2.5 / 50 / 97.5 % (R's default type 7), sd (n-1), after subtracting a
+// per-sample offset (beta_0 of the same iteration).  One thread per site; its samples are contiguous in the record store.
+__global__ void __launch_bounds__(128) records_summary_kernel(const double *__restrict__ rec, int n_rec_total, int row0, int n_rows,
+                                                              const double *__restrict__ offsets, int n, double *__restrict__ out,
+                                                              double *__restrict__ scratch) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double *v = scratch + (size_t)t * n_rows;   // per-site workspace
+    double mean = 0.0;
+    for (int k = 0; k < n_rows; k++) {
+        const double x = rec[(size_t)(row0 + k) + (size_t)n_rec_total * t] - (offsets ? offsets[k] : 0.0);
+        mean += x;
+        int j = k;                               // insertion sort (n_rows is a few hundred at most)
+        while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; j--; }
+        v[j] = x;
+    }
+    mean /= n_rows;
+    double ss = 0.0;
+    for (int k = 0; k < n_rows; k++) { const double d = v[k] - mean; ss += d * d; }
+    auto quantile = [&](double p) {              // type 7: h = (n-1) p, linear interpolation between order statistics
+        const double h = (n_rows - 1) * p;
+        const int lo = (int)floor(h);
+        const int hi = min(lo + 1, n_rows - 1);
+        return v[lo] + (h - lo) * (v[hi] - v[lo]);
+    };
+    out[t] = mean;
+    out[(size_t)n + t] = quantile(0.025);
+    out[(size_t)2 * n + t] = quantile(0.5);
+    out[(size_t)3 * n + t] = quantile(0.975);
+    out[(size_t)4 * n + t] = n_rows > 1 ? sqrt(ss / (n_rows - 1)) : 0.0;
+}
+
 __global__ void fill_f64_kernel(double *__restrict__ dst, double v, size_t n) {
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) dst[t] = v;
 }

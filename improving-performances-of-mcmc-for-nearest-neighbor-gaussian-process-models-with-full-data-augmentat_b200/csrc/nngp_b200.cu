@@ -179,6 +179,8 @@ struct Ctx {
     // device structure
     DevBuf<int> d_psite, d_gid, d_i2g, d_g2i, d_nn, d_colptr, d_crow, d_csrc, d_zpos, d_lvl_rows, d_lvl_ptr, d_lm, d_optr, d_oidx, d_cstart,
         d_partial_rows, d_nbad;
+    DevBuf<double> d_frec;                 // device-side record store of the last chain_run: n_frec x n, column-major
+    int frec_rows = 0;
     DevBuf<double> d_mtab;
     bool matern_table = true;              // tabulate the Matern kernel per factor build (false: evaluate K_nu per pair)
     DevBuf<double> d_locs, d_tl, d_linv[2], d_valT, d_pd, d_nobs, d_ymx, d_S, d_field, d_newfield, d_r, d_tmp1, d_tmp2, d_io,
@@ -771,6 +773,7 @@ static void destroy_ctx(Ctx *c) {
                             &c->d_scalars, &c->d_flush};
     for (auto *b : db) b->release();
     c->d_mtab.release();
+    c->d_frec.release();
     c->d_sp.release();
     for (int k = 0; k < 3; k++) { c->d_tiles[k].release(); c->d_tile_ptr[k].release(); }
     c->d_rows_padded.release(); c->d_ticket.release(); c->d_bar.release();
@@ -1694,6 +1697,18 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
     if (rng_mode == NNGP_RNG_SUPPLIED) { zhost.resize(n); rs.rnorm(zhost.data(), n); }
     std::vector<int> acc_anc(n_iter + 1, 0), acc_suf(n_iter + 1, 0);
     const int n_frec = (int)std::nearbyint(n_iter * thin);
+    // stored field samples stay in HBM, already in R's n_frec x n column-major layout, and leave in one copy at the end
+    bool frec_on_device = false;
+    if (field_records_out && n_frec > 0) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (size_t)n_frec * n * sizeof(double);
+        if (c->d_frec.n >= (size_t)n_frec * n || need + ((size_t)2 << 30) < free_b + c->d_frec.n * sizeof(double)) {
+            if (c->d_frec.n < (size_t)n_frec * n) c->d_frec.alloc((size_t)n_frec * n);
+            frec_on_device = true;
+            c->frec_rows = n_frec;
+        }
+    }
     const unsigned long long philox_seed = ((unsigned long long)(uint32_t)iter_start << 20) ^ (unsigned long long)(uint32_t)*chain_index_;
     for (int iter = 1; iter <= n_iter; iter++) {
         // ---- (A) ancillary :113-157 ----
@@ -1792,17 +1807,43 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
             if (std::nearbyint(t) == t) {
                 const int row = (int)t - 1;
                 if (row >= 0 && row < n_frec) {
-                    std::vector<double> f(n);
-                    download_site_vector(c, c->d_field.p, f.data());
-                    for (int s = 0; s < n; s++) field_records_out[(size_t)row + (size_t)n_frec * s] = f[s];
+                    if (frec_on_device) {
+                        record_field_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->d_frec.p, c->d_field.p, c->d_g2i.p, row, n_frec, n);
+                        LAUNCHED(c);
+                    } else {   // record store does not fit next to the model: one download per stored sample
+                        std::vector<double> f(n);
+                        download_site_vector(c, c->d_field.p, f.data());
+                        for (int s = 0; s < n; s++) field_records_out[(size_t)row + (size_t)n_frec * s] = f[s];
+                    }
                 }
             }
         }
         if (accept_out) { accept_out[iter - 1] = acc_anc[iter]; accept_out[n_iter + iter - 1] = acc_suf[iter]; }
     }
+    if (frec_on_device) CK(cudaMemcpyAsync(field_records_out, c->d_frec.p, (size_t)n_frec * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     params_io[0] = beta_0; params_io[1] = log_scale; params_io[2] = lnv; params_io[3] = logvar_suf; params_io[4] = logvar_anc;
     for (int k = 0; k < ns; k++) params_io[5 + k] = shape[k];
+    ABI_END
+}
+
+void nngp_records_summary(const int *ctx_id, const int *first_row, const int *n_rows, const double *offsets, double *out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(first_row && n_rows && out && *first_row >= 1 && *n_rows >= 1, "nngp_records_summary: bad argument");
+    NEED(c->frec_rows > 0 && c->d_frec.p, "nngp_records_summary: no device-resident field records (run nngp_chain_run with field records first)");
+    REQUIRE(*first_row - 1 + *n_rows <= c->frec_rows, "nngp_records_summary: rows %d..%d exceed the %d stored samples", *first_row, *first_row + *n_rows - 1, c->frec_rows);
+    use(c);
+    const int n = c->n, k = *n_rows;
+    DevBuf<double> scratch, dout, doff;
+    scratch.alloc((size_t)n * k);
+    dout.alloc((size_t)n * 5);
+    if (offsets) { doff.alloc(k); CK(cudaMemcpyAsync(doff.p, offsets, sizeof(double) * k, cudaMemcpyHostToDevice, c->stream)); }
+    records_summary_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_frec.p, c->frec_rows, *first_row - 1, k, offsets ? doff.p : nullptr, n, dout.p, scratch.p);
+    LAUNCHED(c);
+    CK(cudaMemcpyAsync(out, dout.p, sizeof(double) * (size_t)n * 5, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    scratch.release(); dout.release(); doff.release();
     ABI_END
 }
 

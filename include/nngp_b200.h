@@ -233,6 +233,13 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape, double *params_io, co
                     const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode,
                     const double *var_y, double *records_out, double *field_records_out, int *accept_out, int *status);
 
+/* Posterior summary of the field samples stored by the last nngp_chain_run, computed on the device from the record store
+ * that stays in HBM: get_summary (Scripts/mcmc_nngp_estimate.R:1-6) of rows first_row .. first_row +
+ * n_rows - 1 (1-based) of records$field minus offsets[k] (beta_0 of the same iteration, estimate.R:90-92; NULL = none).
+ * out: n x 5 column-major (mean, q0.025, median, q0.975, sd), sites in reference order. */
+void nngp_records_summary(const int *ctx_id, const int *first_row, const int *n_rows, const double *offsets, double *out,
+                          int *status);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * prediction  (mcmc_nngp_predict_field, Scripts/mcmc_nngp_predict.R:25-54)
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -352,3 +352,23 @@ def test_both_loglik_variants(variant, m):
         ctx.factor_build(cp)
         ctx.field_set(P["field"])
         assert abs(ctx.loglik(0.3, 0.2) - ll_o) < TOL * abs(ll_o)
+
+
+def test_device_record_store_and_summary():
+    """Field records come back in R's layout from the device-side store, and nngp_records_summary reproduces get_summary
+    (estimate.R:1-6: mean, type-7 quantiles, sd with n-1) of records$field minus beta_0."""
+    n, m = 3000, 5
+    P = make_problem(n, m, seed=51)
+    lm = np.arange(1, n + 1, dtype=np.int32)
+    y = 0.5 + P["rng"].standard_normal(n)
+    p0 = dict(shape=[np.log(0.1)], beta_0=0.4, log_scale=0.0, log_noise_variance=-0.5)
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], lm) as ctx:
+        ctx.field_set(P["field"])
+        ctx.obs_set(y)
+        _, rec, frec, _ = ctx.chain_run(p0, 40, float(np.var(y, ddof=1)), thin=0.5, n_chromatic=2, iter_start=0, chain_index=1)
+        assert frec.shape == (20, n) and np.all(np.isfinite(frec))
+        assert np.max(np.abs(frec[-1] - ctx.field_get())) == 0.0          # iteration 40 is stored in the last row
+        b0 = rec[1::2, 0][10:]                                            # beta_0 of iterations 22, 24, ..., 40
+        got = ctx.records_summary(11, 10, offsets=b0)
+    want = nb.get_summary(frec[10:] - b0[:, None])
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
