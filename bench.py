@@ -273,6 +273,21 @@ def run_ours(a):
     chain_it_per_s = world * n_chain_it / (time.perf_counter() - t0)
     ctx.field_set(w)
 
+    # ---- config 5 flavour: mcmc_nngp_predict_field at n new sites (joint context over 2n sites; only the new rows are solved) ----
+    pred_per_s = None
+    if world == 1 and not a.no_predict:
+        new_locs = np.random.default_rng(99).random((n, 2))
+        joint = np.vstack([locs, new_locs])
+        nn_j = nb.find_ordered_nn(joint, m)
+        with nb.NNGPContext(joint, nn_j, np.ones(2 * n, dtype=np.int32), np.zeros(0, dtype=np.int32), "exponential_isotropic", device=local) as pctx:
+            pctx.factor_build([1.0, RANGE, 0.0])
+            zp = np.random.default_rng(5).standard_normal(n)
+            pctx.predict_sample(n, w, beta_0, ls, zp)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                pctx.predict_sample(n, w, beta_0, ls, zp)
+            pred_per_s = 5 / (time.perf_counter() - t0)
+
     pinned = nb.PinnedArray(n)
     pinned.array[:] = ctx.field_get()
     e2e_value = timed_e2e(pinned.array)
@@ -304,6 +319,8 @@ def run_ours(a):
         "gibbs_sweeps_per_sec": world * 1e3 / sweep_ms, "loglik_evals_per_sec": world * 1e3 / float(np.mean(ms_ll)),
         "factor_builds_per_sec": world * 1e3 / float(np.mean(ms_fac)),
         "chain_iterations_per_sec": chain_it_per_s,
+        "predicted_field_samples_per_sec": pred_per_s,
+        "predicted_field_sample": f"nngp_predict_sample through the C ABI with host buffers: one stored sample conditionally simulated at {n} new sites",
         "chain_iteration": "nngp_chain_run: reference loop update_Gaussian.R:101-314 (2 factor rebuilds, ancillary SpMV+SpTRSV, 2 log-liks, beta_0, 10 sweeps, noise steps), whole job",
         "ms": {"sweep": sweep_ms, "loglik": float(np.mean(ms_ll)), "factor_build": float(np.mean(ms_fac)),
                "spmv_plus_sptrsv": float(np.mean(ms_solve)), "accept_transpose_precision_diag": float(np.mean(ms_commit)),
@@ -419,6 +436,7 @@ def main():
     ap.add_argument("--nbrs", "--m", dest="m", type=int, default=10)
     ap.add_argument("--ref-n", type=int, default=None, help="reference arm: run on a smaller n and scale (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-predict", action="store_true")
     ap.add_argument("--mode", default="chains", choices=["chains", "sharded"])
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="sharded mode: halo transport")
     a = ap.parse_args()

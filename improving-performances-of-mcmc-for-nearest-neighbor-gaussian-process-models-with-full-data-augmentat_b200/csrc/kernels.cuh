@@ -638,6 +638,14 @@ __global__ void __launch_bounds__(1024) sptrsv_multilevel_kernel(const int *__re
 // loads of all levels are in flight at once; only the chain of x dependencies (DAG depth ~200 L2 round trips) serialises.
 #define NNGP_SOLVE_SENTINEL 0xFFF8DEADBEEF0001ull
 
+// conditional simulation at new sites: rows of the observed sites are known (x = (field - beta_0)/sd), rows of the new sites
+// are marked pending for the sync-free solve, which then only walks the new rows
+__global__ void predict_prepare_kernel(unsigned long long *__restrict__ x, const double *__restrict__ known, const int *__restrict__ i2g,
+                                       int n0, int n) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
+        x[q] = (i2g[q] >= n0) ? NNGP_SOLVE_SENTINEL : (unsigned long long)__double_as_longlong(known[q]);
+}
+
 __global__ void fill_u64_kernel(unsigned long long *__restrict__ dst, unsigned long long v, int n) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) dst[t] = v;
 }

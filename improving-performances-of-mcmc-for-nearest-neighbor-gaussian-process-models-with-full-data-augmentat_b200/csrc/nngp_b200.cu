@@ -179,6 +179,9 @@ struct Ctx {
     // device structure
     DevBuf<int> d_psite, d_gid, d_i2g, d_g2i, d_nn, d_colptr, d_crow, d_csrc, d_zpos, d_lvl_rows, d_lvl_ptr, d_lm, d_optr, d_oidx, d_cstart,
         d_partial_rows, d_nbad;
+    // prediction (new sites appended after n0 observed ones): level-ordered, warp-padded list of the NEW rows only
+    int pred_n0 = -1, pred_slots = 0, pred_levels = 0;
+    DevBuf<int> d_pred_rows;
     DevBuf<double> d_frec;                 // device-side record store of the last chain_run: n_frec x n, column-major
     int frec_rows = 0;
     DevBuf<double> d_mtab;
@@ -774,6 +777,7 @@ static void destroy_ctx(Ctx *c) {
     for (auto *b : db) b->release();
     c->d_mtab.release();
     c->d_frec.release();
+    c->d_pred_rows.release();
     c->d_sp.release();
     for (int k = 0; k < 3; k++) { c->d_tiles[k].release(); c->d_tile_ptr[k].release(); }
     c->d_rows_padded.release(); c->d_ticket.release(); c->d_bar.release();
@@ -1636,22 +1640,53 @@ void nngp_predict_sample(const int *ctx_id, const int *slot, const int *n_obs_si
     REQUIRE(*n_obs_sites >= 0 && *n_obs_sites <= c->n, "nngp_predict_sample: n_obs_sites out of range");
     NEED(c->have_slot(*slot), "nngp_predict_sample: that slot holds no factor");
     use(c);
-    // rhs (reference order) = c( sparse_chol[1:n,1:n] %*% (field - beta_0) / sd , z_pred ); the first n rows of the solve then
-    // return (field - beta_0)/sd exactly, so build rhs by spmv over the joint factor with x_pred = 0 on the new rows.
-    const int n0 = *n_obs_sites, np = c->n - n0;
+    // predict.R:43-53 solves the joint system with rhs c(sparse_chol[1:n,1:n] %*% (field - beta_0)/sd, z): its first n0 unknowns
+    // are (field - beta_0)/sd again, so only the new rows are solved:  x_i = (z_i - sum_j Linv[i,j] x[nn(i,j)]) / Linv[i,1].
+    const int n0 = *n_obs_sites, np = c->n - n0, n = c->n;
     const double sd = std::exp(0.5 * *log_scale);
-    std::vector<double> host(c->n);
+    if (c->pred_n0 != n0) {   // level schedule of the new rows (a new row waits only for new-site parents)
+        std::vector<int> nn((size_t)c->ld * c->M);
+        CK(cudaMemcpy(nn.data(), c->d_nn.p, sizeof(int) * nn.size(), cudaMemcpyDeviceToHost));
+        std::vector<int> lvl(n, -1);
+        int depth = 0;
+        for (int i = n0; i < n; i++) {
+            const int q = c->g2i[i];
+            int l = 0;
+            for (int j = 1; j < c->M; j++) {
+                const int p = nn[(size_t)j * c->ld + q];
+                if (p >= 0 && lvl[p] >= 0) l = std::max(l, lvl[p] + 1);
+            }
+            lvl[q] = l;
+            depth = std::max(depth, l + 1);
+        }
+        std::vector<std::vector<int>> by_level(depth);
+        for (int q = 0; q < n; q++) if (lvl[q] >= 0) by_level[lvl[q]].push_back(q);
+        std::vector<int> rows;
+        rows.reserve((size_t)np + 32 * (size_t)depth);
+        for (auto &v : by_level) { for (int q : v) rows.push_back(q); while (rows.size() % 32) rows.push_back(-1); }
+        c->d_pred_rows.upload(rows, c->stream);
+        CK(cudaStreamSynchronize(c->stream));
+        c->pred_slots = (int)rows.size();
+        c->pred_levels = depth;
+        c->pred_n0 = n0;
+    }
+    std::vector<double> host(n);
     for (int i = 0; i < n0; i++) host[i] = (field[i] - *beta_0) / sd;
-    for (int i = 0; i < np; i++) host[n0 + i] = 0.0;
-    upload_site_vector(c, host.data(), c->d_tmp1.p);
-    op_spmv(c, c->linv_slot(*slot), c->d_tmp1.p, 0.0, c->d_tmp2.p);   // rows < n0 only involve observed sites
-    // overwrite the rhs of the new rows with z_pred
-    download_site_vector(c, c->d_tmp2.p, host.data());
     for (int i = 0; i < np; i++) host[n0 + i] = z_pred[i];
-    upload_site_vector(c, host.data(), c->d_tmp1.p);
-    op_sptrsv(c, c->linv_slot(*slot), c->d_tmp1.p, c->d_tmp2.p, nullptr, 0.0, 1.0);
+    upload_site_vector(c, host.data(), c->d_tmp1.p);     // known x on the observed rows, rhs z on the new rows
+    predict_prepare_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(reinterpret_cast<unsigned long long *>(c->d_tmp2.p), c->d_tmp1.p, c->d_i2g.p, n0, n);
+    LAUNCHED(c);
+    if (c->pred_slots > 0) {
+        CK(cudaMemsetAsync(c->d_ticket.p, 0, sizeof(int), c->stream));
+        const int want = c->solve_window_ctas > 0 ? c->solve_window_ctas : c->n_sm * c->solve_ctas_per_sm;
+        const int blocks = std::max(1, std::min((c->pred_slots + 255) / 256, want));
+        const double *linv = c->linv_slot(*slot);
+        DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_pred_rows.p, c->pred_slots, c->d_tmp1.p, reinterpret_cast<unsigned long long *>(c->d_tmp2.p), nullptr, 0.0, 1.0, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns)));
+        LAUNCHED(c);
+    }
     CK(cudaGetLastError());
     download_site_vector(c, c->d_tmp2.p, host.data());
+    check_solve_flag(c);
     for (int i = 0; i < np; i++) out[i] = sd * host[n0 + i];
     ABI_END
 }
