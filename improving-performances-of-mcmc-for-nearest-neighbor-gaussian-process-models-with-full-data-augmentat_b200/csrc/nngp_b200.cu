@@ -156,8 +156,8 @@ struct Ctx {
     struct Seg { int l0, l1; bool single_block; };
     std::vector<Seg> solve_plan;
     // tiles of the sweep: cfg 0 = 256 threads x 8 entries, cfg 1 = 128 x 8, cfg 2 = 256 x 4
-    std::vector<int> tile_ptr[3];          // per colour, into d_tiles[cfg]
-    int max_tiles[3] = {0, 0, 0};          // largest number of tiles in one colour
+    std::vector<int> tile_ptr[4];          // per colour, into d_tiles[cfg]
+    int max_tiles[4] = {0, 0, 0, 0};       // largest number of tiles in one colour
     int persistent_grid[3] = {0, 0, 0};    // co-resident grid size of the persistent kernel per cfg
     bool persistent_ok[3] = {false, false, false};   // per-CTA tile list fits the kernel's shared-memory table
     // 0 persistent 256x8 | 1 per-colour launches 256x8 | 2 per-colour launches 128x8 | 3 thread-per-site launches
@@ -192,8 +192,8 @@ struct Ctx {
     DevBuf<int> d_send_storage, d_recv_proc;
     DevBuf<double> d_sendbuf, d_recvbuf;
     DevBuf<unsigned char> d_owned;         // per storage id: 1 = owned row (reductions skip ghost rows)
-    DevBuf<int4> d_tiles[3];
-    DevBuf<int> d_tile_ptr[3];
+    DevBuf<int4> d_tiles[4];
+    DevBuf<int> d_tile_ptr[4];
     DevBuf<int> d_rows_padded, d_ticket;
     DevBuf<unsigned int> d_bar;
     double *h_pinned = nullptr;       // 64 doubles of pinned scratch for scalar results
@@ -501,8 +501,8 @@ static void launch_sweep_colors(Ctx *c) {
             gibbs_color_kernel<<<(q1 - q0 + 255) / 256, 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, q0, q1);
             continue;
         }
-        const bool pdl = (c->sweep_variant == 6 || c->sweep_variant == 7);
-        const int cfg = (c->sweep_variant == 1 || c->sweep_variant == 7) ? 0 : 1;   // 128x8 is also the persistent kernel's fallback
+        const bool pdl = (c->sweep_variant == 6 || c->sweep_variant == 7 || c->sweep_variant == 8);
+        const int cfg = (c->sweep_variant == 1 || c->sweep_variant == 7) ? 0 : (c->sweep_variant == 8 ? 3 : 1);   // 128x8 is also the persistent kernel's fallback
         const int t0 = c->tile_ptr[cfg][col], nt = c->tile_ptr[cfg][col + 1] - t0;
         if (!pdl) {
             if (cfg == 0)
@@ -514,7 +514,7 @@ static void launch_sweep_colors(Ctx *c) {
             // first colour of a sweep is an ordinary launch (it must see the advance kernel's counter update)
             cudaLaunchConfig_t lc = {};
             lc.gridDim = dim3(nt);
-            lc.blockDim = dim3(cfg == 0 ? 256 : 128);
+            lc.blockDim = dim3(cfg == 0 ? 256 : (cfg == 3 ? 64 : 128));
             lc.dynamicSmemBytes = 0;
             lc.stream = c->stream;
             cudaLaunchAttribute at[1];
@@ -523,7 +523,9 @@ static void launch_sweep_colors(Ctx *c) {
             lc.attrs = at;
             lc.numAttrs = (col > 0) ? 1 : 0;
             const int4 *tl = c->d_tiles[cfg].p + t0;
-            if (cfg == 0)
+            if (cfg == 3)
+                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<64, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
+            else if (cfg == 0)
                 CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<256, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
             else
                 CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
@@ -779,7 +781,7 @@ static void destroy_ctx(Ctx *c) {
     c->d_frec.release();
     c->d_pred_rows.release();
     c->d_sp.release();
-    for (int k = 0; k < 3; k++) { c->d_tiles[k].release(); c->d_tile_ptr[k].release(); }
+    for (int k = 0; k < 4; k++) { c->d_tiles[k].release(); c->d_tile_ptr[k].release(); }
     c->d_rows_padded.release(); c->d_ticket.release(); c->d_bar.release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -1028,9 +1030,9 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     }
     c->n_slots = (int)rows_padded.size();
     // ---- sweep tiles: runs of consecutive same-colour sites with <= T sites and <= T*EPT CSC entries ----
-    std::vector<int4> tiles[3];
-    const int tcfg_threads[3] = {256, 128, 256}, tcfg_ept[3] = {8, 8, 4};
-    for (int cfg = 0; cfg < 3; cfg++) {
+    std::vector<int4> tiles[4];
+    const int tcfg_threads[4] = {256, 128, 256, 64}, tcfg_ept[4] = {8, 8, 4, 8};
+    for (int cfg = 0; cfg < 4; cfg++) {
         const int T = tcfg_threads[cfg], ECAP = T * tcfg_ept[cfg];
         c->tile_ptr[cfg].assign(K + 1, 0);
         for (int col = 0; col < K; col++) {
@@ -1071,7 +1073,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     CK(cudaMemsetAsync(c->d_nbad.p, 0, 2 * sizeof(int), s));
     c->d_ticket.alloc(1);
     c->d_rows_padded.upload(rows_padded, s);
-    for (int cfg = 0; cfg < 3; cfg++) { c->d_tiles[cfg].upload(tiles[cfg], s); c->d_tile_ptr[cfg].upload(c->tile_ptr[cfg], s); }
+    for (int cfg = 0; cfg < 4; cfg++) { c->d_tiles[cfg].upload(tiles[cfg], s); c->d_tile_ptr[cfg].upload(c->tile_ptr[cfg], s); }
     c->d_bar.alloc(1);
     {
         int occ = 0;
@@ -1197,7 +1199,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
     use(c);
     CK(cudaStreamSynchronize(c->stream));
     switch (*key) {
-        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 7, "sweep variant must be 0..7"); c->sweep_variant = *value; break;
+        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 8, "sweep variant must be 0..8"); c->sweep_variant = *value; break;
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;

@@ -15,7 +15,9 @@ PAREN = re.compile(r"\(.*")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 SRC = os.path.join(ROOT, "gpurun_out")
-METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "dram__bytes.sum.per_second",
+           "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+           "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
@@ -65,9 +67,13 @@ def launch_list(tag):
 
 def full(tag, rep, label):
     path = os.path.join(SRC, rep)
-    if not os.path.exists(path):
+    csv_path = path.replace(".ncu-rep", "_raw.csv")
+    if os.path.exists(csv_path):
+        raw = open(csv_path).read()
+    elif os.path.exists(path):
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     if len(rows) < 3:
         return
@@ -84,9 +90,17 @@ def full(tag, rep, label):
                     f.write(f"  {m:62s} {r[idx[m]]:>14s} {units[idx[m]]}\n")
             st = sorted([(float(r[idx[h]]), h) for h in stall if r[idx[h]] not in ("", "n/a")], reverse=True)[:5]
             f.write("  top stalls (warp cycles per issued instruction): " + ", ".join(f"{h.split('issue_stalled_')[1].replace('_per_issue_active.ratio', '')}={v:.1f}" for v, h in st) + "\n")
-            tot_r += to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
-            tot_w += to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
-            tot_t += to_us(r[idx["gpu__time_duration.sum"]], units[idx["gpu__time_duration.sum"]])
+            us = to_us(r[idx["gpu__time_duration.sum"]], units[idx["gpu__time_duration.sum"]])
+            tot_t += us
+            if "dram__bytes_read.sum" in idx:
+                tot_r += to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
+                tot_w += to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+            elif "dram__bytes.sum.per_second" in idx:   # section-limited capture: bytes = rate x duration (read + write together)
+                u = units[idx["dram__bytes.sum.per_second"]]
+                rate = float(r[idx["dram__bytes.sum.per_second"]].replace(",", "")) * {"byte/s": 1, "Kbyte/s": 1e3, "Mbyte/s": 1e6, "Gbyte/s": 1e9, "Tbyte/s": 1e12}.get(u, 1)
+                b = rate * us * 1e-6
+                tot_r += b
+                f.write(f"  dram bytes (rate x duration)                                   {b / 1e6:14.3f} MB\n")
         f.write(f"\n# totals over the {len(rows) - 2} captured launches: dram read {tot_r / 1e6:.1f} MB, dram write {tot_w / 1e6:.1f} MB, "
                 f"time {tot_t:.1f} us (cold cache, serialised)\n")
     return tot_r + tot_w
@@ -98,7 +112,7 @@ if __name__ == "__main__":
     launch_list(tag)
     import json
     traffic = {}
-    for rep, label in (("prof_gibbs.ncu-rep", "gibbs_sweep_full"), ("prof_factor.ncu-rep", "factor_full"),
+    for rep, label in (("prof_gibbs.ncu-rep", "gibbs_sweep_full"), ("prof_gibbs_first.ncu-rep", "gibbs_first_colour_full"), ("prof_factor.ncu-rep", "factor_full"),
                        ("prof_loglik.ncu-rep", "loglik_full"), ("prof_other.ncu-rep", "transpose_sptrsv_full")):
         t = full(tag, rep, label)
         if t:

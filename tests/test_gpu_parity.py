@@ -255,7 +255,7 @@ def test_error_paths():
         nb.NNGPContext(P["locs"], bad, P["coloring"], P["locs_match"])
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("n,m", [(20000, 10), (3000, 5)])
 def test_every_sweep_variant_matches_the_reference_loop(variant, n, m):
     """All kernel variants of the sweep (tiled launches, persistent cooperative kernel, PDL chain, thread-per-site) are the
