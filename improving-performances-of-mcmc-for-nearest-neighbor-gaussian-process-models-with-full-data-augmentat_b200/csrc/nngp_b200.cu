@@ -907,6 +907,21 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
             REQUIRE(v >= 1 && v <= i, "NNarray[%d,%d] = %d is not a previous site", i + 1, j + 1, v);
         }
     }
+    // The sweep kernels update all sites of a colour concurrently and patch r without atomics: that is only race-free if no
+    // two sites of one colour appear in the same row (= the colouring is proper for the moral graph, initialize.R:103-110).
+    // Checked here, once, instead of trusting the caller (compute-sanitizer's racecheck is not available on this pool).
+    {
+        std::vector<int> seen(K + 1, -1);
+        for (int i = 0; i < n; i++) {
+            for (int j = 0; j < M; j++) {
+                const int v = NNarray[(size_t)i + (size_t)n * j];
+                if (v == NNGP_NA_INT) continue;
+                const int col = coloring[v - 1];
+                REQUIRE(seen[col] != i, "coloring is not proper: row %d contains two sites of colour %d (they would be updated concurrently)", i + 1, col);
+                seen[col] = i;
+            }
+        }
+    }
     // ---- numberings ----
     // storage order: NNGP_LAYOUT_MORTON = Z-curve over all sites; NNGP_LAYOUT_COLOR[_MORTON] = colour-major (reference / Z-curve
     // order inside a colour).  processing order (sweep) = colour-major, storage order inside a colour.

@@ -253,6 +253,11 @@ def test_error_paths():
     bad[10, 1] = 50                                              # a "neighbour" that is not a previous site
     with pytest.raises(nb.NNGPError):
         nb.NNGPContext(P["locs"], bad, P["coloring"], P["locs_match"])
+    improper = P["coloring"].copy()
+    improper[P["NNarray"][150, 1] - 1] = improper[150]           # a site and one of its parents share a colour: racy sweep
+    with pytest.raises(nb.NNGPError) as e:
+        nb.NNGPContext(P["locs"], P["NNarray"], improper, P["locs_match"])
+    assert "not proper" in str(e.value)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
