@@ -325,9 +325,9 @@ def run_ours(a):
         "ms": {"sweep": sweep_ms, "loglik": float(np.mean(ms_ll)), "factor_build": float(np.mean(ms_fac)),
                "spmv_plus_sptrsv": float(np.mean(ms_solve)), "accept_transpose_precision_diag": float(np.mean(ms_commit)),
                "wall_timed_region": wall * 1e3},
-        "roofline": {"bound": "hbm", "kernel": "gibbs_tile_kernel (the K colour launches of one sweep, replayed from one CUDA graph)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "gibbs_tile2_kernel (the K colour launches of one sweep, PDL-chained, replayed from one CUDA graph)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the colour launches of one sweep)",
+                     "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the colour launches of one sweep, --cache-control none)",
                      "algorithmic_bytes_per_sweep": ab["gibbs_sweep"],
                      "loglik_GBps": ab["loglik"] / (float(np.mean(ms_ll)) * 1e-3) / 1e9,
                      "factor_build_GBps": ab["factor_build"] / (float(np.mean(ms_fac)) * 1e-3) / 1e9},
@@ -417,7 +417,7 @@ def run_sharded(a):
                        "halo_values_per_sweep": int(halo[0].item()), "ghost_sites_total": int(halo[1].item()), "setup_s": t_setup},
             "gibbs_sweeps_per_sec": 1e3 / sweep_ms, "loglik_evals_per_sec": 1e3 / ll_ms, "factor_builds_per_sec": 1e3 / fac_ms,
             "ms": {"sweep": sweep_ms, "loglik": ll_ms, "factor_build": fac_ms},
-            "roofline": {"bound": "hbm", "kernel": "gibbs_tile_kernel + halo exchange (whole-field sweep, all ranks)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "gibbs_tile2_kernel + halo exchange (whole-field sweep, all ranks)", "achieved": achieved,
                          "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
             "e2e": None, "gpu_launches": int(launches), "launches_per_step": int(launches_per_step), "clocks": clocks,
         }

@@ -863,15 +863,16 @@ __global__ void __launch_bounds__(256) gibbs_color_kernel(const int *__restrict_
 // The kernel releases its dependents immediately (griddepcontrol.launch_dependents) and does everything that does not
 // depend on r -- entry stream, per-site constants, Philox + Box-Muller -- BEFORE griddepcontrol.wait, i.e. while the
 // previous colour's kernel is still running; only the r gather / segment sum / r scatter remain serialised per colour.
-template <int THREADS, int EPT, bool PDL>
-__global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restrict__ tiles, const int *__restrict__ colptr,
+__device__ __forceinline__ long long global_ns();
+template <int THREADS, int EPT, bool PDL, int MINB = 0, bool DBG = false>
+__global__ void __launch_bounds__(THREADS, MINB) gibbs_tile_kernel(const int4 *__restrict__ tiles, const int *__restrict__ colptr,
                                                              const int *__restrict__ crow, const double *__restrict__ valT,
                                                              const double *__restrict__ pd, const double *__restrict__ nobs,
                                                              const double *__restrict__ S, const int *__restrict__ zpos,
                                                              const int *__restrict__ gid, const int *__restrict__ psite,
                                                              const double *__restrict__ zbuf,
                                                              const SweepParams *__restrict__ spp, double *__restrict__ field,
-                                                             double *__restrict__ r) {
+                                                             double *__restrict__ r, long long *ts = nullptr, int col = 0) {
     constexpr int ECAP = THREADS * EPT;
     __shared__ double sprod[ECAP];
     __shared__ double sbc[2];
@@ -879,6 +880,12 @@ __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restr
     const int4 tile = tiles[blockIdx.x];
     const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
     const SweepParams sp = *spp;
+    long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tqa = 0, tqb = 0, tqc = 0;   // DBG: per-CTA phase clock (thread 0)
+    if (DBG) {
+        tq0 = global_ns();
+        asm volatile("" ::"r"(s0), "r"(s1), "r"(e0), "r"(e1), "d"(sp.beta0) : "memory");   // descriptor + parameters landed
+        tqa = global_ns();
+    }
     if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (e1 - e0 > ECAP) {
         // a single site whose column does not fit the tile (pathological fan-out): whole-CTA reduction
@@ -926,7 +933,21 @@ __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restr
     }
     // r-independent part of the site update (Philox + Box-Muller, 1/prec, sqrt): overlaps with the gathers in flight
     // (or, under PDL, with the previous colour's kernel)
-    if (tid < s1 - s0) {
+    if (DBG) {
+        if (tid < s1 - s0) {
+            const int q = s0 + tid;
+            k0 = colptr[q] - e0;
+            k1 = colptr[q + 1] - e0;
+            sq = psite[q];
+            const double f_old = field[sq], pdq = pd[q], nq = nobs[q], Sq = S[q];
+            const int gq = gid[q];
+            asm volatile("" ::"r"(k0), "r"(k1), "d"(f_old), "d"(pdq), "d"(nq), "d"(Sq), "r"(gq) : "memory");   // site loads landed
+            tqb = global_ns();
+            sc = site_const(sp, f_old, pdq, nq, Sq, sweep_normal(sp, zbuf, zpos, gid, q));
+            asm volatile("" ::"d"(sc.c0), "d"(sc.c1) : "memory");   // draw + constants computed
+            tqc = global_ns();
+        }
+    } else if (tid < s1 - s0) {
         const int q = s0 + tid;
         k0 = colptr[q] - e0;
         k1 = colptr[q + 1] - e0;
@@ -934,11 +955,569 @@ __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restr
         sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
     }
     if (PDL) {
+        if (DBG) {   // force the stream loads to land before the stamp (debug build only)
+            int chk = 0;
+#pragma unroll
+            for (int k = 0; k < EPT; k++) chk ^= row[k] ^ (int)__double_as_longlong(val[k]);
+            if (chk == 0x7ffffff1 && sc.c0 == 123.456) sbc[1] = 1.0;
+            tq1 = global_ns();
+        }
+        if (DBG && tid == 0) atomicMax((unsigned long long *)ts + col * 4 + 0, (unsigned long long)global_ns());   // last CTA ready to wait
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (DBG) tq2 = global_ns();
+        if (DBG && tid == 0) atomicMin((unsigned long long *)ts + col * 4 + 1, (unsigned long long)global_ns());   // first CTA released
 #pragma unroll
         for (int k = 0; k < EPT; k++)
             if (row[k] >= 0) rr[k] = r[row[k]];
     }
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) sprod[k * THREADS + tid] = val[k] * rr[k];
+    __syncthreads();
+    if (DBG) tq3 = global_ns();
+    if (tid < s1 - s0) {
+        const double a = segment_sum(sprod, k0, k1);
+        const double f_new = sc.c0 - sc.c1 * a;
+        const double delta = f_new - sc.f_old;
+        for (int k = k0; k < k1; k++) sprod[k] = delta;
+        field[sq] = f_new;
+    }
+    __syncthreads();
+    if (DBG) tq4 = global_ns();
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) r[row[k]] = rr[k] + val[k] * sprod[k * THREADS + tid];
+    if (DBG && tid == 0) {   // development aid (NNGP_OPT_DEBUG_TIMELINE): first / last CTA past its scatter
+        const unsigned long long t = (unsigned long long)global_ns();
+        atomicMin((unsigned long long *)ts + col * 4 + 2, t);
+        atomicMax((unsigned long long *)ts + col * 4 + 3, t);
+        // per-CTA phase durations, summed over the colour's CTAs: [stream+consts, wait, gather+products, reduce, scatter issue, n]
+        unsigned long long *acc = (unsigned long long *)ts + 4096 + col * 16;
+        atomicAdd(acc + 8, (unsigned long long)(tqa - tq0));
+        atomicAdd(acc + 9, (unsigned long long)(tqb - tqa));
+        atomicAdd(acc + 10, (unsigned long long)(tqc - tqb));
+        atomicAdd(acc + 11, (unsigned long long)(tq1 - tqc));
+        atomicAdd(acc + 0, (unsigned long long)(tq1 - tq0));
+        atomicAdd(acc + 1, (unsigned long long)(tq2 - tq1));
+        atomicAdd(acc + 2, (unsigned long long)(tq3 - tq2));
+        atomicAdd(acc + 3, (unsigned long long)(tq4 - tq3));
+        atomicAdd(acc + 4, (unsigned long long)((long long)t - tq4));
+        atomicAdd(acc + 7, 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tile kernel with a BLOCKED segmented reduction (production path since the L1 data-pipe analysis in profiles/):
+// gibbs_tile_kernel is bound by L1 data-pipe wavefronts, and more than half of them (920 of 1620 per tile, ncu
+// l1tex__data_pipe_lsu_wavefronts_mem_shared vs _mem_lgds) are SHARED-memory traffic of the per-site segment sums: one thread
+// per site walks its column with a stride of ~11 doubles (2-way bank conflicts on top of the 2 wavefronts a 64-bit request
+// needs) and then writes delta once per ENTRY.  Here
+//   * products go to shared memory once, padded by one double per 8 (position e + e/8);
+//   * thread t reads back the 8 CONTIGUOUS products [8t, 8t+8) -- stride 9 doubles, conflict-free -- and reduces them by
+//     runs of equal site (the local site id of every entry is a byte stream, cloc, laid out per tile and padded to the tile
+//     capacity so that the 8 ids of a thread are one aligned 64-bit load).  A run that starts inside the thread belongs to
+//     a site whose column starts there: its sum goes to sstart[site] (single writer).  A run that continues the previous
+//     thread's last run goes to shead[t];
+//   * the site's owner adds sstart[site] and the shead[] of the threads its column runs through (1.4 on average): a fixed
+//     order, so the result does not depend on scheduling;
+//   * delta is written once per SITE; the scatter phase looks it up by the entry's local site id (a broadcast read).
+// Shared-memory wavefronts per tile: ~270 instead of ~920.
+// ---------------------------------------------------------------------------------------------------------------
+#define NNGP_PADPOS(e) ((e) + ((e) >> 3))
+
+// reduces the padded product array by runs; must be called by all THREADS threads between two __syncthreads()
+template <int THREADS>
+__device__ __forceinline__ void blocked_run_sums(const double *__restrict__ sprod, unsigned long long sid, unsigned int prev_last,
+                                                 double *__restrict__ sstart, double *__restrict__ shead) {
+    const int t = threadIdx.x;
+    unsigned int cur = (unsigned int)(sid & 0xffull);
+    bool cont = (cur == prev_last);
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const unsigned int sj = (unsigned int)((sid >> (8 * j)) & 0xffull);
+        if (sj != cur) {
+            if (cur != 255u) { if (cont) shead[t] = acc; else sstart[cur] = acc; }
+            cur = sj;
+            cont = false;
+            acc = 0.0;
+        }
+        acc += sprod[9 * t + j];
+    }
+    if (cur != 255u) { if (cont) shead[t] = acc; else sstart[cur] = acc; }
+}
+
+__device__ __forceinline__ double blocked_site_sum(const double *__restrict__ sstart, const double *__restrict__ shead, int site,
+                                                   int k0, int k1) {
+    double a = sstart[site];
+    const int t1 = (k1 - 1) >> 3;
+    for (int t = (k0 >> 3) + 1; t <= t1; t++) a += shead[t];
+    return a;
+}
+
+// one-touch streams (factor values, row ids, local ids): do not allocate in L1 and mark the L2 line evict-first, so that the
+// re-used vectors (r, field: 8n bytes each) are what stays resident in the 126 MB L2 while ~13 bytes per entry stream through
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double ld_keep_f64(const double *p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_keep_f64(double *p, double v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+template <int HINT> __device__ __forceinline__ double ld_stream_f64(const double *p, unsigned long long pol) {
+    if (!HINT) return *p;
+    double v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+template <int HINT> __device__ __forceinline__ int ld_stream_s32(const int *p, unsigned long long pol) {
+    if (!HINT) return *p;
+    int v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+template <int HINT> __device__ __forceinline__ unsigned int ld_stream_u8(const unsigned char *p, unsigned long long pol) {
+    if (!HINT) return *p;
+    unsigned int v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+template <int THREADS, bool PDL, int MINB, int HINT = 0, bool DBG = false>
+__global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *__restrict__ tiles, int tile_base,
+                                                              const int *__restrict__ colptr, const int *__restrict__ crow,
+                                                              const unsigned char *__restrict__ cloc,
+                                                              const double *__restrict__ valT, const double *__restrict__ pd,
+                                                              const double *__restrict__ nobs, const double *__restrict__ S,
+                                                              const int *__restrict__ zpos, const int *__restrict__ gid,
+                                                              const int *__restrict__ psite, const double *__restrict__ zbuf,
+                                                              const SweepParams *__restrict__ spp, double *__restrict__ field,
+                                                              double *__restrict__ r, long long *ts, int col) {
+    constexpr int EPT = 8;
+    constexpr int ECAP = THREADS * EPT;
+    __shared__ double sprod[ECAP + ECAP / 8];
+    __shared__ double sstart[THREADS], shead[THREADS];
+    __shared__ double sbc[2];
+    const int tid = threadIdx.x;
+    const int4 tile = tiles[blockIdx.x];
+    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
+    const SweepParams sp = *spp;
+    long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq5 = 0;   // DBG: per-CTA phase clock
+    if (DBG) tq0 = global_ns();
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
+        const int q = s0;
+        if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+        double acc[1] = {0.0};
+        for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * r[crow[e]];
+        block_reduce_sum<1>(acc);
+        if (tid == 0) {
+            const int sq = psite[q];
+            const double w_old = field[sq] - sp.beta0;
+            const double Qss = pd[q], no = nobs[q];
+            const double prec = sp.e_ls * Qss + sp.e_ln * no;
+            const double t = acc[0] - Qss * w_old;
+            const double resid = S[q] - no * sp.beta0;
+            const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
+            const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
+            sbc[0] = (f_new - sp.beta0) - w_old;
+            field[sq] = f_new;
+        }
+        __syncthreads();
+        const double delta = sbc[0];
+        for (int e = e0 + tid; e < e1; e += THREADS) r[crow[e]] += valT[e] * delta;
+        return;
+    }
+    const unsigned char *tloc = cloc + (size_t)(tile_base + blockIdx.x) * ECAP;   // this tile's local site ids (255 = padding)
+    const unsigned long long pol = HINT ? l2_evict_first_policy() : 0ull;
+    const unsigned long long keep = HINT >= 2 ? l2_evict_last_policy() : 0ull;
+    double val[EPT], rr[EPT];
+    int row[EPT];
+    unsigned int loc[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        const int e = e0 + k * THREADS + tid;
+        loc[k] = ld_stream_u8<(HINT > 0)>(tloc + k * THREADS + tid, pol);
+        if (e < e1) {
+            val[k] = ld_stream_f64<(HINT > 0)>(valT + e, pol);
+            row[k] = ld_stream_s32<(HINT > 0)>(crow + e, pol);
+        } else {
+            val[k] = 0.0;
+            row[k] = -1;
+        }
+    }
+    const unsigned long long sid = reinterpret_cast<const unsigned long long *>(tloc)[tid];
+    const unsigned int prev_last = tid > 0 ? (unsigned int)tloc[8 * tid - 1] : 255u;
+    int k0 = 0, k1 = 0, sq = 0;
+    SiteConst sc{0.0, 0.0, 0.0};
+    if (!PDL) {
+#pragma unroll
+        for (int k = 0; k < EPT; k++)
+            if (row[k] >= 0) rr[k] = r[row[k]];
+    }
+    if (tid < s1 - s0) {
+        const int q = s0 + tid;
+        if (HINT == 3) {   // the per-site constants are one-touch streams too
+            k0 = ld_stream_s32<1>(colptr + q, pol) - e0;
+            k1 = ld_stream_s32<1>(colptr + q + 1, pol) - e0;
+            sq = ld_stream_s32<1>(psite + q, pol);
+            sc = site_const(sp, field[sq], ld_stream_f64<1>(pd + q, pol), ld_stream_f64<1>(nobs + q, pol), ld_stream_f64<1>(S + q, pol),
+                            sweep_normal(sp, zbuf, zpos, gid, q));
+        } else {
+            k0 = colptr[q] - e0;
+            k1 = colptr[q + 1] - e0;
+            sq = psite[q];
+            sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
+        }
+    }
+    if (PDL) {
+        if (DBG) {   // force the prologue to finish before the stamp (debug build only)
+            int chk = 0;
+#pragma unroll
+            for (int k = 0; k < EPT; k++) chk ^= row[k] ^ (int)__double_as_longlong(val[k]) ^ (int)loc[k];
+            asm volatile("" ::"r"(chk), "d"(sc.c0), "d"(sc.c1), "l"(sid) : "memory");
+            tq1 = global_ns();
+            if (tid == 0) atomicMax((unsigned long long *)ts + col * 4 + 0, (unsigned long long)tq1);   // last CTA ready to wait
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (DBG) {
+            tq2 = global_ns();
+            if (tid == 0) atomicMin((unsigned long long *)ts + col * 4 + 1, (unsigned long long)tq2);   // first CTA released
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; k++)
+            if (row[k] >= 0) rr[k] = (HINT >= 2) ? ld_keep_f64(r + row[k], keep) : r[row[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < EPT; k++) sprod[NNGP_PADPOS(k * THREADS + tid)] = (row[k] >= 0) ? val[k] * rr[k] : 0.0;
+    __syncthreads();
+    if (DBG) tq3 = global_ns();
+    blocked_run_sums<THREADS>(sprod, sid, prev_last, sstart, shead);
+    __syncthreads();
+    if (DBG) tq4 = global_ns();
+    if (tid < s1 - s0) {
+        const double a = blocked_site_sum(sstart, shead, tid, k0, k1);
+        const double f_new = sc.c0 - sc.c1 * a;
+        sstart[tid] = f_new - sc.f_old;   // delta, once per site (sstart[tid] was read by this thread only)
+        field[sq] = f_new;
+    }
+    __syncthreads();
+    if (DBG) tq5 = global_ns();
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) {
+            const double rn = rr[k] + val[k] * sstart[loc[k]];
+            if (HINT >= 2) st_keep_f64(r + row[k], rn, keep); else r[row[k]] = rn;
+        }
+    if (DBG && tid == 0) {
+        const unsigned long long t = (unsigned long long)global_ns();
+        atomicMin((unsigned long long *)ts + col * 4 + 2, t);
+        atomicMax((unsigned long long *)ts + col * 4 + 3, t);
+        unsigned long long *acc = (unsigned long long *)ts + 4096 + col * 16;
+        atomicAdd(acc + 0, (unsigned long long)(tq1 - tq0));   // prologue
+        atomicAdd(acc + 1, (unsigned long long)(tq2 - tq1));   // wait
+        atomicAdd(acc + 2, (unsigned long long)(tq3 - tq2));   // gather + products
+        atomicAdd(acc + 3, (unsigned long long)(tq5 - tq3));   // run sums + site update
+        atomicAdd(acc + 4, (unsigned long long)((long long)t - tq5));   // scatter issue
+        atomicAdd(acc + 8, (unsigned long long)(tq4 - tq3));   // run sums alone
+        atomicAdd(acc + 7, 1ull);
+    }
+}
+
+// transposition + precision_diag with the same blocked reduction (see gibbs_tile2_kernel); csrc / linv are one-touch streams
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) transpose_tile2_kernel(const int4 *__restrict__ tiles, const int *__restrict__ colptr,
+                                                                  const int *__restrict__ csrc, const unsigned char *__restrict__ cloc,
+                                                                  const double *__restrict__ linv, double *__restrict__ valT,
+                                                                  double *__restrict__ pd) {
+    constexpr int EPT = 8;
+    constexpr int ECAP = THREADS * EPT;
+    __shared__ double ssq[ECAP + ECAP / 8];
+    __shared__ double sstart[THREADS], shead[THREADS];
+    const int tid = threadIdx.x;
+    const int4 tile = tiles[blockIdx.x];
+    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
+    if (e1 - e0 > ECAP) {   // single site with an oversize column
+        double acc[1] = {0.0};
+        for (int e = e0 + tid; e < e1; e += THREADS) {
+            const double v = linv[csrc[e]];
+            valT[e] = v;
+            acc[0] += v * v;
+        }
+        block_reduce_sum<1>(acc);
+        if (tid == 0) pd[s0] = acc[0];
+        return;
+    }
+    const unsigned long long pol = l2_evict_first_policy();
+    const unsigned char *tloc = cloc + (size_t)blockIdx.x * ECAP;
+    int src[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        const int e = e0 + k * THREADS + tid;
+        src[k] = (e < e1) ? ld_stream_s32<1>(csrc + e, pol) : -1;
+    }
+    const unsigned long long sid = reinterpret_cast<const unsigned long long *>(tloc)[tid];
+    const unsigned int prev_last = tid > 0 ? (unsigned int)tloc[8 * tid - 1] : 255u;
+    int k0 = 0, k1 = 0;
+    if (tid < s1 - s0) { k0 = colptr[s0 + tid] - e0; k1 = colptr[s0 + tid + 1] - e0; }
+    double v[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (src[k] >= 0) v[k] = linv[src[k]];
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        if (src[k] >= 0) valT[e0 + k * THREADS + tid] = v[k];
+        ssq[NNGP_PADPOS(k * THREADS + tid)] = (src[k] >= 0) ? v[k] * v[k] : 0.0;
+    }
+    __syncthreads();
+    blocked_run_sums<THREADS>(ssq, sid, prev_last, sstart, shead);
+    __syncthreads();
+    if (tid < s1 - s0) pd[s0 + tid] = blocked_site_sum(sstart, shead, tid, k0, k1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two-pass sweep: site_prepare_kernel + gibbs_tile3_kernel.
+// The %globaltimer phase profile of gibbs_tile_kernel (profiles/r01_pdl_phases_*.txt) shows a CTA living 6.4 us, of which 3.4 us
+// are the r-INDEPENDENT prologue: 1.6 us for the dependent loads colptr/psite -> field[psite] and 1.8 us for the serial FP64
+// chain of the draw (Philox, log, sincospi, sqrt, 1/prec, sqrt) -- executed by 93 of 128 threads while the CTA's registers
+// and its slot sit idle.  With 5 CTAs/SM this occupancy x latency product, not bandwidth, bounds the sweep.  All of that
+// work depends only on the state at the START of the sweep (a site's own field value does not change before its update),
+// so it moves to a full-occupancy streaming pass over all sites; the tile kernel then loads three doubles per site.
+//   c0, c1 as in SiteConst; f_old = field at the start of the sweep.
+// Chain: prepare -> tile(colour 1) -> tile(colour 2) ...  The first tile kernel triggers its dependents only AFTER its own
+// griddepcontrol.wait, so no later colour can start (and read c0/c1/f_old in its prologue) before the prepare pass is
+// complete and visible.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) site_prepare_kernel(const double *__restrict__ pd, const double *__restrict__ nobs,
+                                                           const double *__restrict__ S, const int *__restrict__ zpos,
+                                                           const int *__restrict__ gid, const int *__restrict__ psite,
+                                                           const double *__restrict__ zbuf, const SweepParams *__restrict__ spp,
+                                                           const double *__restrict__ field, int n_sites,
+                                                           double *__restrict__ pc0, double *__restrict__ pc1,
+                                                           double *__restrict__ pf) {
+    const SweepParams sp = *spp;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_sites; q += gridDim.x * blockDim.x) {
+        const SiteConst sc = site_const(sp, field[psite[q]], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
+        pc0[q] = sc.c0;
+        pc1[q] = sc.c1;
+        pf[q] = sc.f_old;
+    }
+}
+
+template <int THREADS, bool FIRST, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) gibbs_tile3_kernel(const int4 *__restrict__ tiles, int tile_base,
+                                                                    const int *__restrict__ colptr, const int *__restrict__ crow,
+                                                                    const unsigned char *__restrict__ cloc,
+                                                                    const double *__restrict__ valT, const int *__restrict__ psite,
+                                                                    const double *pc0, const double *pc1, const double *pf,
+                                                                    double *__restrict__ field, double *__restrict__ r) {
+    constexpr int EPT = 8;
+    constexpr int ECAP = THREADS * EPT;
+    __shared__ double sprod[ECAP + ECAP / 8];
+    __shared__ double sstart[THREADS], shead[THREADS];
+    __shared__ double sbc[2];
+    const int tid = threadIdx.x;
+    const int4 tile = tiles[blockIdx.x];
+    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
+    if (!FIRST) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (FIRST) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        double acc[1] = {0.0};
+        for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * r[crow[e]];
+        block_reduce_sum<1>(acc);
+        if (tid == 0) {
+            const double f_new = pc0[s0] - pc1[s0] * acc[0];
+            sbc[0] = f_new - pf[s0];
+            field[psite[s0]] = f_new;
+        }
+        __syncthreads();
+        const double delta = sbc[0];
+        for (int e = e0 + tid; e < e1; e += THREADS) r[crow[e]] += valT[e] * delta;
+        return;
+    }
+    const unsigned char *tloc = cloc + (size_t)(tile_base + blockIdx.x) * ECAP;   // this tile's local site ids (255 = padding)
+    double val[EPT], rr[EPT];
+    int row[EPT];
+    unsigned int locp[2] = {0u, 0u};   // local site ids of this thread's entries, one byte each
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        const int e = e0 + k * THREADS + tid;
+        locp[k >> 2] |= (unsigned int)tloc[k * THREADS + tid] << (8 * (k & 3));
+        if (e < e1) {
+            val[k] = valT[e];
+            row[k] = crow[e];
+        } else {
+            val[k] = 0.0;
+            row[k] = -1;
+        }
+    }
+    const unsigned long long sid = reinterpret_cast<const unsigned long long *>(tloc)[tid];
+    const unsigned int prev_last = tid > 0 ? (unsigned int)tloc[8 * tid - 1] : 255u;
+    int k0 = 0, k1 = 0, sq = 0;
+    double c0 = 0.0, c1 = 0.0, f_old = 0.0;
+    const bool owner = tid < s1 - s0;
+    if (owner) {
+        const int q = s0 + tid;
+        k0 = colptr[q] - e0;
+        k1 = colptr[q + 1] - e0;
+        sq = psite[q];
+        if (!FIRST) { c0 = pc0[q]; c1 = pc1[q]; f_old = pf[q]; }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (FIRST) {   // the prepare pass is complete only now
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (owner) { const int q = s0 + tid; c0 = pc0[q]; c1 = pc1[q]; f_old = pf[q]; }
+    }
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) rr[k] = r[row[k]];
+#pragma unroll
+    for (int k = 0; k < EPT; k++) sprod[NNGP_PADPOS(k * THREADS + tid)] = (row[k] >= 0) ? val[k] * rr[k] : 0.0;
+    __syncthreads();
+    blocked_run_sums<THREADS>(sprod, sid, prev_last, sstart, shead);
+    __syncthreads();
+    if (owner) {
+        const double a = blocked_site_sum(sstart, shead, tid, k0, k1);
+        const double f_new = c0 - c1 * a;
+        sstart[tid] = f_new - f_old;   // delta, once per site
+        field[sq] = f_new;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) r[row[k]] = rr[k] + val[k] * sstart[(locp[k >> 2] >> (8 * (k & 3))) & 0xffu];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Flag-chained variant of the tile kernel.  The launches are still one per colour and still carry the programmatic
+// stream serialisation attribute, but the kernel NEVER executes griddepcontrol.wait: colour c+1 learns that colour c is
+// finished from a device counter instead of from the completion of the previous grid.
+//   * every CTA of colour c, after its last r store:  bar.sync ; red.release.gpu  cdone[c] += 1
+//   * every CTA of colour c+1, before its first r load: thread 0 spins on ld.acquire.gpu cdone[c] until it equals the
+//     number of tiles of colour c, then bar.sync
+// The hand-off therefore costs one L2 flag hop (0.4 us measured, scripts/microbench) instead of grid drain + memory flush +
+// dependent release (the ~6.7 us/colour floor of the griddepcontrol.wait chain).  No deadlock: the hardware starts grid
+// c+1 only after EVERY CTA of grid c has executed griddepcontrol.launch_dependents, i.e. is resident, so whatever a
+// spinning CTA waits for is always able to run.  r is read with ld.global.cg and written with st.global.cg: CTAs of two
+// colours share an SM, and there is no grid boundary between them to invalidate L1.  The counters are zeroed by the
+// ordinary launch that closes a sweep (advance_sweep_kernel).  A bounded spin raises *stuck instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------------------------
+#define NNGP_CHAIN_STRIDE 32   // one 128-byte line per colour counter
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p);
+__device__ __forceinline__ long long global_ns();
+
+// two_line = false: pollers spin on the arrival counter itself.  two_line = true: the CTA whose arrival completes the count
+// raises a separate "go" word (another 128-byte line), so that the ~10^3 spinning readers do not queue on the line the
+// arrivals' read-modify-writes are serialised on; costs the last arriver one extra L2 round trip.
+__device__ __forceinline__ void chain_wait(const unsigned int *cnt, unsigned int need, unsigned int sleep_ns, int *stuck) {
+    if (threadIdx.x == 0 && need > 0) {
+        if (ld_acquire_gpu_u32(cnt) < need) {
+            const long long t0 = global_ns();
+            unsigned int it = 0;
+            while (ld_acquire_gpu_u32(cnt) < need) {
+                if (sleep_ns) __nanosleep(sleep_ns);
+                if ((++it & 1023u) == 0 && global_ns() - t0 > 2000000000ll) { *stuck = 3; break; }
+            }
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void chain_arrive(unsigned int *cnt, unsigned int *go, unsigned int n_tiles, bool two_line) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!two_line) {
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+        } else {
+            unsigned int old;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(cnt) : "memory");
+            if (old + 1u == n_tiles) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(n_tiles) : "memory");
+        }
+    }
+}
+
+template <int THREADS, int EPT>
+__global__ void __launch_bounds__(THREADS) gibbs_chain_kernel(const int4 *__restrict__ tiles, const int *__restrict__ colptr,
+                                                              const int *__restrict__ crow, const double *__restrict__ valT,
+                                                              const double *__restrict__ pd, const double *__restrict__ nobs,
+                                                              const double *__restrict__ S, const int *__restrict__ zpos,
+                                                              const int *__restrict__ gid, const int *__restrict__ psite,
+                                                              const double *__restrict__ zbuf,
+                                                              const SweepParams *__restrict__ spp, double *__restrict__ field,
+                                                              double *r, unsigned int *cdone, int col, int K, unsigned int need_prev,
+                                                              unsigned int sleep_ns, int two_line, int *stuck) {
+    constexpr int ECAP = THREADS * EPT;
+    __shared__ double sprod[ECAP];
+    __shared__ double sbc[2];
+    const int tid = threadIdx.x;
+    const int4 tile = tiles[blockIdx.x];
+    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
+    const SweepParams sp = *spp;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // cdone[c * STRIDE] = arrivals of colour c; cdone[(K + c) * STRIDE] = its "go" word (two-line mode)
+    const unsigned int *prev = cdone + ((two_line ? K : 0) + (col > 0 ? col - 1 : 0)) * NNGP_CHAIN_STRIDE;
+    if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
+        const int q = s0;
+        chain_wait(prev, need_prev, sleep_ns, stuck);
+        double acc[1] = {0.0};
+        for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * __ldcg(r + crow[e]);
+        block_reduce_sum<1>(acc);
+        if (tid == 0) {
+            const int sq = psite[q];
+            const double w_old = field[sq] - sp.beta0;
+            const double Qss = pd[q], no = nobs[q];
+            const double prec = sp.e_ls * Qss + sp.e_ln * no;
+            const double t = acc[0] - Qss * w_old;
+            const double resid = S[q] - no * sp.beta0;
+            const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
+            const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
+            sbc[0] = (f_new - sp.beta0) - w_old;
+            field[sq] = f_new;
+        }
+        __syncthreads();
+        const double delta = sbc[0];
+        for (int e = e0 + tid; e < e1; e += THREADS) __stcg(r + crow[e], __ldcg(r + crow[e]) + valT[e] * delta);
+        chain_arrive(cdone + col * NNGP_CHAIN_STRIDE, cdone + (K + col) * NNGP_CHAIN_STRIDE, gridDim.x, two_line != 0);
+        return;
+    }
+    double val[EPT], rr[EPT];
+    int row[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        const int e = e0 + k * THREADS + tid;
+        if (e < e1) {
+            val[k] = valT[e];
+            row[k] = crow[e];
+        } else {
+            val[k] = 0.0;
+            row[k] = -1;
+        }
+    }
+    int k0 = 0, k1 = 0, sq = 0;
+    SiteConst sc{0.0, 0.0, 0.0};
+    if (tid < s1 - s0) {
+        const int q = s0 + tid;
+        k0 = colptr[q] - e0;
+        k1 = colptr[q + 1] - e0;
+        sq = psite[q];
+        sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
+    }
+    chain_wait(prev, need_prev, sleep_ns, stuck);
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) rr[k] = __ldcg(r + row[k]);
 #pragma unroll
     for (int k = 0; k < EPT; k++)
         if (row[k] >= 0) sprod[k * THREADS + tid] = val[k] * rr[k];
@@ -953,7 +1532,8 @@ __global__ void __launch_bounds__(THREADS) gibbs_tile_kernel(const int4 *__restr
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) r[row[k]] = rr[k] + val[k] * sprod[k * THREADS + tid];
+        if (row[k] >= 0) __stcg(r + row[k], rr[k] + val[k] * sprod[k * THREADS + tid]);
+    chain_arrive(cdone + col * NNGP_CHAIN_STRIDE, cdone + (K + col) * NNGP_CHAIN_STRIDE, gridDim.x, two_line != 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1381,9 +1961,13 @@ __global__ void allreduce_wait_sum_kernel(const double *area, int count, int wor
     }
 }
 
-__global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n) {
-    spp->sweep_counter += 1ull;
-    spp->z_offset += n;
+__global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n, unsigned int *cdone, int K) {
+    if (threadIdx.x == 0) {
+        spp->sweep_counter += 1ull;
+        spp->z_offset += n;
+    }
+    if (cdone)   // flag-chained sweep: the colour counters start every sweep at zero
+        for (int k = threadIdx.x; k < 2 * K; k += blockDim.x) cdone[k * NNGP_CHAIN_STRIDE] = 0u;
 }
 
 }  // namespace nngp

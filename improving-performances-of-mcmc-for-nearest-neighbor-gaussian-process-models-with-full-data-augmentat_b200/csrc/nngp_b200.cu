@@ -162,7 +162,7 @@ struct Ctx {
     bool persistent_ok[3] = {false, false, false};   // per-CTA tile list fits the kernel's shared-memory table
     // 0 persistent 256x8 | 1 per-colour launches 256x8 | 2 per-colour launches 128x8 | 3 thread-per-site launches
     // 4 persistent 256x4 | 5 persistent 128x8
-    int sweep_variant = 6;                 // PDL chain of 128x8 tile launches: measured fastest at n = 1M (profiles/)
+    int sweep_variant = 22;                // PDL chain of 128x8 tiles, blocked segmented reduction, L2 eviction hints: fastest (profiles/)
     int solve_variant = 0;                 // 0 sync-free single launch, 1 level-scheduled launches
     int commit_variant = 0;                // 0 tiled transposition, 1 thread per column
     // 1 plain coalesced loads (default), 0 TMA-staged ring.  Measured on B200 (profiles/r01_explore_final.txt): the TMA ring is
@@ -193,9 +193,13 @@ struct Ctx {
     DevBuf<double> d_sendbuf, d_recvbuf;
     DevBuf<unsigned char> d_owned;         // per storage id: 1 = owned row (reductions skip ghost rows)
     DevBuf<int4> d_tiles[4];
+    DevBuf<unsigned char> d_cloc;          // per tile (128x8 configuration, padded to 1024): local site id of every CSC entry, 255 = padding
     DevBuf<int> d_tile_ptr[4];
     DevBuf<int> d_rows_padded, d_ticket;
     DevBuf<unsigned int> d_bar;
+    DevBuf<double> d_pc0, d_pc1, d_pf;     // two-pass sweep: per-site constants of the current sweep (site_prepare_kernel)
+    DevBuf<unsigned int> d_cdone;          // flag-chained sweep: arrivals per colour (one 128-byte line each)
+    int chain_sleep_ns = 0;
     double *h_pinned = nullptr;       // 64 doubles of pinned scratch for scalar results
     double *h_stage = nullptr;        // pinned staging for vectors (n doubles at least)
     size_t h_stage_n = 0;
@@ -477,10 +481,11 @@ static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, do
 
 static void op_commit(Ctx *c) {
     const int n_tiled = c->sharded ? c->n_owned : c->n;   // tiles cover the owned sites; ghost columns follow in processing order
-    if (c->commit_variant == 0) {
+    if (c->commit_variant == 0 || c->commit_variant == 2) {
         const int nt = c->tile_ptr[1][c->K];   // every tile of every colour (128 x 8 configuration)
         if (nt > 0) {
-            transpose_tile_kernel<128, 8><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p, c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, c->d_valT.p, c->d_pd.p);
+            if (c->commit_variant == 2) transpose_tile_kernel<128, 8><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p, c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, c->d_valT.p, c->d_pd.p);
+            else transpose_tile2_kernel<128><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p, c->d_colptr.p, c->d_csrc.p, c->d_cloc.p, c->d_linv[c->cur].p, c->d_valT.p, c->d_pd.p);
             LAUNCHED(c);
         }
     } else {
@@ -494,14 +499,102 @@ static void op_commit(Ctx *c) {
     c->committed = true;
 }
 
+static long long *timeline_ptr() {
+    long long *p = nullptr;
+    CK(cudaGetSymbolAddress((void **)&p, g_timeline));
+    return p;
+}
+
+static bool sweep_is_two_pass(Ctx *c) { return c->sweep_variant >= 18 && c->sweep_variant <= 20; }
+
 static void launch_sweep_colors(Ctx *c) {
+    if (sweep_is_two_pass(c)) {
+        // pass 1: r-independent per-site constants (draw included) for every tiled site, full occupancy
+        const int n_tiled = c->sharded ? c->n_owned : c->n;
+        site_prepare_kernel<<<std::min((n_tiled + 255) / 256, c->n_sm * 8), 256, 0, c->stream>>>(c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, n_tiled, c->d_pc0.p, c->d_pc1.p, c->d_pf.p);
+        // pass 2: one PDL-chained launch per colour
+        for (int col = 0; col < c->K; col++) {
+            const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(nt);
+            lc.blockDim = dim3(128);
+            lc.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at;
+            lc.numAttrs = 1;
+            const int4 *tl = c->d_tiles[1].p + t0;
+#define NNGP_T3_ARGS tl, t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const int *)c->d_psite.p, (const double *)c->d_pc0.p, (const double *)c->d_pc1.p, (const double *)c->d_pf.p, c->d_field.p, c->d_r.p
+            if (c->sweep_variant == 18) {
+                if (col == 0) CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, true, 6>, NNGP_T3_ARGS));
+                else CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, false, 6>, NNGP_T3_ARGS));
+            } else if (c->sweep_variant == 19) {
+                if (col == 0) CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, true, 8>, NNGP_T3_ARGS));
+                else CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, false, 8>, NNGP_T3_ARGS));
+            } else {
+                if (col == 0) CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, true, 5>, NNGP_T3_ARGS));
+                else CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, false, 5>, NNGP_T3_ARGS));
+            }
+#undef NNGP_T3_ARGS
+        }
+        advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, c->d_cdone.p, c->K);
+        return;
+    }
     for (int col = 0; col < c->K; col++) {
         const int q0 = c->cstart[col], q1 = c->cstart[col + 1];
         if (c->sweep_variant == 3) {
             gibbs_color_kernel<<<(q1 - q0 + 255) / 256, 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, q0, q1);
             continue;
         }
-        const bool pdl = (c->sweep_variant == 6 || c->sweep_variant == 7 || c->sweep_variant == 8);
+        if (c->sweep_variant >= 9 && c->sweep_variant <= 12) {
+            // flag-chained PDL launches: no griddepcontrol.wait, the colour hand-off is a device counter (gibbs_chain_kernel)
+            // 9 = 128x8 tiles, 10 = 256x8, 11 = 64x8, 12 = 128x8 with a separate "go" word
+            const int cfg = c->sweep_variant == 10 ? 0 : (c->sweep_variant == 11 ? 3 : 1);
+            const int two_line = c->sweep_variant == 12 ? 1 : 0;
+            const int t0 = c->tile_ptr[cfg][col], nt = c->tile_ptr[cfg][col + 1] - t0;
+            const unsigned int need = col > 0 ? (unsigned int)(c->tile_ptr[cfg][col] - c->tile_ptr[cfg][col - 1]) : 0u;
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(nt);
+            lc.blockDim = dim3(cfg == 0 ? 256 : (cfg == 3 ? 64 : 128));
+            lc.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at;
+            lc.numAttrs = (col > 0) ? 1 : 0;
+            const int4 *tl = c->d_tiles[cfg].p + t0;
+#define NNGP_CHAIN_ARGS tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, c->d_cdone.p, col, c->K, need, (unsigned int)c->chain_sleep_ns, two_line, c->d_nbad.p + 1
+            if (cfg == 0) CK(cudaLaunchKernelEx(&lc, gibbs_chain_kernel<256, 8>, NNGP_CHAIN_ARGS));
+            else if (cfg == 3) CK(cudaLaunchKernelEx(&lc, gibbs_chain_kernel<64, 8>, NNGP_CHAIN_ARGS));
+            else CK(cudaLaunchKernelEx(&lc, gibbs_chain_kernel<128, 8>, NNGP_CHAIN_ARGS));
+#undef NNGP_CHAIN_ARGS
+            continue;
+        }
+        if ((c->sweep_variant >= 15 && c->sweep_variant <= 17) || (c->sweep_variant >= 21 && c->sweep_variant <= 23)) {   // blocked segmented reduction (gibbs_tile2_kernel), 128x8 tiles
+            const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(nt);
+            lc.blockDim = dim3(128);
+            lc.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at;
+            lc.numAttrs = (col > 0 && c->sweep_variant != 16) ? 1 : 0;
+            const int4 *tl = c->d_tiles[1].p + t0;
+#define NNGP_T2_ARGS tl, t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, c->debug_timeline ? timeline_ptr() : (long long *)nullptr, col
+            if (c->debug_timeline) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2, true>, NNGP_T2_ARGS));
+            else if (c->sweep_variant == 15) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5>, NNGP_T2_ARGS));
+            else if (c->sweep_variant == 17) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6>, NNGP_T2_ARGS));
+            else if (c->sweep_variant == 21) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 1>, NNGP_T2_ARGS));
+            else if (c->sweep_variant == 22) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, NNGP_T2_ARGS));
+            else if (c->sweep_variant == 23) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 3>, NNGP_T2_ARGS));
+            else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, false, 5>, NNGP_T2_ARGS));
+#undef NNGP_T2_ARGS
+            continue;
+        }
+        const bool pdl = (c->sweep_variant == 6 || c->sweep_variant == 7 || c->sweep_variant == 8 || c->sweep_variant == 13 || c->sweep_variant == 14);
         const int cfg = (c->sweep_variant == 1 || c->sweep_variant == 7) ? 0 : (c->sweep_variant == 8 ? 3 : 1);   // 128x8 is also the persistent kernel's fallback
         const int t0 = c->tile_ptr[cfg][col], nt = c->tile_ptr[cfg][col + 1] - t0;
         if (!pdl) {
@@ -523,18 +616,25 @@ static void launch_sweep_colors(Ctx *c) {
             lc.attrs = at;
             lc.numAttrs = (col > 0) ? 1 : 0;
             const int4 *tl = c->d_tiles[cfg].p + t0;
-            if (cfg == 3)
-                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<64, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
+            if (c->sweep_variant == 13 || c->sweep_variant == 14) {   // occupancy experiments: 128x8 capped at 64 / 80 registers
+                if (c->sweep_variant == 13)
+                    CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true, 8>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
+                else
+                    CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true, 6>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
+            } else if (cfg == 3)
+                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<64, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
             else if (cfg == 0)
-                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<256, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
+                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<256, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
+            else if (c->debug_timeline)
+                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true, 0, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, timeline_ptr(), col));
             else
-                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
+                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
         }
     }
-    advance_sweep_kernel<<<1, 1, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global);
+    advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, c->d_cdone.p, c->K);
 }
 
-static int sweep_launches(Ctx *c) { return c->K + 1; }
+static int sweep_launches(Ctx *c) { return c->K + 1 + (sweep_is_two_pass(c) ? 1 : 0); }
 
 static bool sweep_is_persistent(Ctx *c) { return c->sweep_variant == 0 || c->sweep_variant == 4 || c->sweep_variant == 5; }
 
@@ -560,13 +660,13 @@ static void op_sweeps(Ctx *c, int n_sweeps, unsigned long long sweep_in_call) {
                     at[0].val.programmaticStreamSerializationAllowed = 1;
                     lc.attrs = at;
                     lc.numAttrs = (col > 0) ? 1 : 0;
-                    CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true>, (const int4 *)(c->d_tiles[1].p + t0), (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p));
+                    CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, (const int4 *)(c->d_tiles[1].p + t0), t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
                 } else if (nt > 0) {
-                    gibbs_tile_kernel<128, 8, false><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
+                    gibbs_tile2_kernel<128, false, 5, 2><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, t0, c->d_colptr.p, c->d_crow.p, c->d_cloc.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0);
                 }
                 op_halo_exchange(c, col);
             }
-            advance_sweep_kernel<<<1, 1, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global);
+            advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, c->d_cdone.p, c->K);
         };
         const bool graphable = c->use_graph && (c->world == 1 || c->p2p);
         for (int s = 0; s < n_sweeps; s++) {
@@ -617,6 +717,13 @@ static void op_sweeps(Ctx *c, int n_sweeps, unsigned long long sweep_in_call) {
         return;
     }
     for (int s = 0; s < n_sweeps; s++) {
+        if (c->debug_timeline && c->K * 16 <= 4096) {   // per-colour stamps of the PDL chain: [last ready, first released, first done, last done]
+            std::vector<long long> init((size_t)c->K * 4);
+            for (int k = 0; k < c->K; k++) { init[4 * k] = 0; init[4 * k + 1] = -1; init[4 * k + 2] = -1; init[4 * k + 3] = 0; }
+            CK(cudaMemcpyAsync(timeline_ptr(), init.data(), init.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemsetAsync(timeline_ptr() + 4096, 0, 4096 * sizeof(long long), c->stream));   // per-CTA phase accumulators
+            CK(cudaStreamSynchronize(c->stream));
+        }
         if (c->use_graph) {
             if (!c->sweep_graph) {
                 cudaGraph_t g;
@@ -782,7 +889,7 @@ static void destroy_ctx(Ctx *c) {
     c->d_pred_rows.release();
     c->d_sp.release();
     for (int k = 0; k < 4; k++) { c->d_tiles[k].release(); c->d_tile_ptr[k].release(); }
-    c->d_rows_padded.release(); c->d_ticket.release(); c->d_bar.release();
+    c->d_rows_padded.release(); c->d_ticket.release(); c->d_bar.release(); c->d_cdone.release(); c->d_cloc.release(); c->d_pc0.release(); c->d_pc1.release(); c->d_pf.release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1063,6 +1170,15 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
             c->max_tiles[cfg] = std::max(c->max_tiles[cfg], c->tile_ptr[cfg][col + 1] - c->tile_ptr[cfg][col]);
         }
     }
+    // local site id of every entry of the 128x8 tiles, one padded block of 1024 bytes per tile (blocked reduction of
+    // gibbs_tile2_kernel); an oversize single-site tile does not use it
+    std::vector<unsigned char> cloc((size_t)tiles[1].size() * 1024, (unsigned char)255);
+    for (size_t t = 0; t < tiles[1].size(); t++) {
+        const int4 tl = tiles[1][t];
+        if (tl.w - tl.z > 1024) continue;
+        for (int q = tl.x; q < tl.y; q++)
+            for (int e = colptr[q]; e < colptr[q + 1]; e++) cloc[t * 1024 + (size_t)(e - tl.z)] = (unsigned char)(q - tl.x);
+    }
     // ---- observations: lm in storage numbering (gathers of field); per-site lists / counts in processing order ----
     std::vector<int> lm(n_obs), optr(n + 1, 0), oidx(n_obs);
     for (int o = 0; o < n_obs; o++) {
@@ -1089,7 +1205,11 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     c->d_ticket.alloc(1);
     c->d_rows_padded.upload(rows_padded, s);
     for (int cfg = 0; cfg < 4; cfg++) { c->d_tiles[cfg].upload(tiles[cfg], s); c->d_tile_ptr[cfg].upload(c->tile_ptr[cfg], s); }
+    c->d_cloc.upload(cloc, s);
+    c->d_pc0.alloc((size_t)n); c->d_pc1.alloc((size_t)n); c->d_pf.alloc((size_t)n);
     c->d_bar.alloc(1);
+    c->d_cdone.alloc((size_t)std::max(1, c->K) * 2 * NNGP_CHAIN_STRIDE);
+    CK(cudaMemsetAsync(c->d_cdone.p, 0, c->d_cdone.n * sizeof(unsigned int), s));
     {
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_persistent_kernel<256, 8>, 256, 0));
@@ -1214,20 +1334,21 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
     use(c);
     CK(cudaStreamSynchronize(c->stream));
     switch (*key) {
-        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 8, "sweep variant must be 0..8"); c->sweep_variant = *value; break;
+        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 23, "sweep variant must be 0..23"); c->sweep_variant = *value; break;
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;
         case NNGP_OPT_FACTOR_VARIANT: REQUIRE(*value >= 0 && *value <= 2, "factor variant must be 0..2"); c->factor_variant = *value; break;
         case NNGP_OPT_LOGLIK_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "loglik variant must be 0..1"); c->loglik_variant = *value; break;
         case NNGP_OPT_MATERN_TABLE: c->matern_table = (*value != 0); break;
-        case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "commit variant must be 0..1"); c->commit_variant = *value; break;
+        case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 2, "commit variant must be 0..2"); c->commit_variant = *value; break;
         case NNGP_OPT_SOLVE_WINDOW_CTAS: REQUIRE(*value >= 0 && *value <= 4096, "solve window must be 0..4096 CTAs"); c->solve_window_ctas = *value; break;
         case NNGP_OPT_DEBUG_TIMELINE: {
             c->debug_timeline = (*value != 0);
             long long zero = 0;
             if (c->debug_timeline) CK(cudaMemcpyToSymbol(g_timeline, &zero, sizeof(long long), sizeof(long long) * 8191));
         } break;
+        case NNGP_OPT_CHAIN_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "chain sleep must be 0..100000 ns"); c->chain_sleep_ns = *value; break;
         case NNGP_OPT_SOLVE_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "solve sleep must be 0..100000 ns"); c->solve_sleep_ns = *value; break;
         default: REQUIRE(false, "unknown option key %d", *key);
     }
@@ -1244,6 +1365,30 @@ void nngp_debug_timeline(double *out, const int *n_out, int *n_written, int *sta
     const int cnt = (int)std::min<long long>(std::min<long long>(h[8191], 4090), *n_out / 2);
     for (int i = 0; i < cnt; i++) { out[2 * i] = (double)(h[2 * i] - h[0]); out[2 * i + 1] = (double)h[2 * i + 1]; }
     *n_written = cnt;
+    ABI_END
+}
+
+void nngp_debug_colour_phases(const int *ctx_id, double *out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(out != nullptr && c->K * 16 <= 4096, "nngp_debug_colour_phases: bad argument");
+    std::vector<long long> h((size_t)c->K * 16);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(h.data(), g_timeline, sizeof(long long) * h.size(), sizeof(long long) * 4096));
+    for (size_t i = 0; i < h.size(); i++) out[i] = (double)h[i];
+    ABI_END
+}
+
+void nngp_debug_colour_times(const int *ctx_id, double *out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(out != nullptr && c->K * 4 <= 4096, "nngp_debug_colour_times: bad argument");
+    std::vector<long long> h((size_t)c->K * 4);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(h.data(), g_timeline, sizeof(long long) * h.size()));
+    long long t0 = h[2];
+    for (size_t i = 0; i < h.size(); i++) if (h[i] > 0 && h[i] < t0) t0 = h[i];
+    for (size_t i = 0; i < h.size(); i++) out[i] = (double)(h[i] - t0);
     ABI_END
 }
 
@@ -1517,7 +1662,7 @@ void nngp_shard_sweep_colour(const int *ctx_id, const int *colour, int *status) 
     const int col = *colour - 1;
     const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
     if (nt > 0) {
-        gibbs_tile_kernel<128, 8, false><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
+        gibbs_tile2_kernel<128, false, 5, 2><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, t0, c->d_colptr.p, c->d_crow.p, c->d_cloc.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0);
         LAUNCHED(c);
     }
     CK(cudaGetLastError());
@@ -1565,7 +1710,7 @@ void nngp_shard_sweep_end(const int *ctx_id, int *status) {
     Ctx *c = get_ctx(ctx_id);
     NEED(c->sharded, "nngp_shard_sweep_end: not a sharded context");
     use(c);
-    advance_sweep_kernel<<<1, 1, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global);
+    advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, c->d_cdone.p, c->K);
     LAUNCHED(c);
     c->sweep_counter += 1ull;
     CK(cudaStreamSynchronize(c->stream));

@@ -131,7 +131,9 @@ void nngp_shard_sweep_end(const int *ctx_id, int *status);
  *                          dependent launch (the r-independent prologue of colour c+1 overlaps colour c) and replayed from
  *                          a CUDA graph (default); 7 = same with 256x8 tiles; 2 / 1 = the same tiles without PDL;
  *                          3 = one launch per colour, thread per site; 0 / 4 / 5 = persistent cooperative kernel (grid
- *                          barrier between colours, next tile prefetched across the barrier) with 256x8 / 256x4 / 128x8 tiles
+ *                          barrier between colours, next tile prefetched across the barrier) with 256x8 / 256x4 / 128x8 tiles;
+ *                          9 / 10 = flag-chained launches (128x8 / 256x8 tiles): programmatic dependent launches that never
+ *                          wait on the previous grid, the colour hand-off is a device counter (release / acquire)
  *   NNGP_OPT_SOLVE_VARIANT 0 = synchronisation-free single-launch triangular solve; 1 = one launch per DAG level
  *   NNGP_OPT_USE_GRAPH     1 = the colour launches of a sweep are replayed from a captured CUDA graph (default) */
 #define NNGP_OPT_SWEEP_VARIANT 1
@@ -140,12 +142,21 @@ void nngp_shard_sweep_end(const int *ctx_id, int *status);
 #define NNGP_OPT_SOLVE_CTAS_PER_SM 4 /* window of the sync-free solve: n_sm * value * 256 rows in flight (default 1) */
 #define NNGP_OPT_SOLVE_SLEEP_NS 5    /* back-off between dependency polls (default 0) */
 #define NNGP_OPT_SOLVE_WINDOW_CTAS 7  /* absolute window of the sync-free solve in CTAs of 256 rows (0 = use per-SM setting) */
-#define NNGP_OPT_COMMIT_VARIANT 8     /* accept-branch transposition: 0 = tiled (default), 1 = thread per column */
+#define NNGP_OPT_COMMIT_VARIANT 8     /* accept-branch transposition: 0 = tiled, blocked reduction (default), 1 = thread per column, 2 = tiled, segment sums */
 #define NNGP_OPT_MATERN_TABLE 9       /* Matern families: 1 = per-build interpolation table of the kernel (default), 0 = K_nu per pair */
 #define NNGP_OPT_LOGLIK_VARIANT 10    /* log-lik pass: 1 = plain coalesced loads (default, faster); 0 = TMA-staged shared-memory ring (cp.async.bulk + mbarrier) */
 #define NNGP_OPT_FACTOR_VARIANT 11    /* m = 10, d = 2 factor kernel register cap: 0 = none (default), 1 = 128, 2 = 96 registers */
+#define NNGP_OPT_CHAIN_SLEEP_NS 12     /* flag-chained sweep: back-off between polls of the colour counter (default 0) */
 #define NNGP_OPT_DEBUG_TIMELINE 6    /* development aid: the persistent sweep kernel stamps %globaltimer per stage */
 void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);
+/* development aid: with NNGP_OPT_DEBUG_TIMELINE and the PDL chain (sweep variant 6), per colour c of the last sweep
+ * out[4c..4c+3] = ns (relative) at which [the last CTA reached griddepcontrol.wait, the first CTA was released,
+ * the first CTA finished its scatter, the last CTA finished its scatter] */
+void nngp_debug_colour_times(const int *ctx_id, double *out, int *status);
+/* same run: out[16c..16c+4] = ns summed over the CTAs of colour c spent in [entry stream + site constants, griddepcontrol.wait,
+ * r gather + products, segment sums + draw, scatter issue]; out[16c+7] = number of CTAs; out[16c+8..11] = the first phase
+ * split (thread 0) into [tile descriptor, per-site loads, draw + constants, rest of the entry stream] */
+void nngp_debug_colour_phases(const int *ctx_id, double *out, int *status);
 /* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,
  * [6]=device, [7]=layout */
 void nngp_ctx_info(const int *ctx_id, int *info8, int *status);

@@ -8,15 +8,16 @@ $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_ou
 tail -1 gpurun_out/plain.log | cut -c1-300
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-# one full sweep = K colour launches of gibbs_tile_kernel (K = 22 at n = 1M): skip the first two sweeps
+# one full sweep = K colour launches of gibbs_tile2_kernel (K = 22 at n = 1M): skip the first two sweeps.
+# --cache-control none: the sweep's DRAM traffic is reported warm (L2 as the previous launches left it), like the timed run
 rm -f gpurun_out/*.ncu-rep   # the whole directory must stay below 64 MiB to be copied back
-ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section Occupancy --section LaunchStats --clock-control none -k regex:gibbs_tile_kernel -s 44 -c 22 -f -o gpurun_out/prof_gibbs $CMD > gpurun_out/ncu_gibbs.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gibbs_tile_kernel -s 44 -c 1 -f -o gpurun_out/prof_gibbs_first $CMD > gpurun_out/ncu_gibbs_first.log 2>&1
+ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section Occupancy --section LaunchStats --clock-control none --cache-control none -k regex:gibbs_tile2_kernel -s 44 -c 22 -f -o gpurun_out/prof_gibbs $CMD > gpurun_out/ncu_gibbs.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gibbs_tile2_kernel -s 44 -c 1 -f -o gpurun_out/prof_gibbs_first $CMD > gpurun_out/ncu_gibbs_first.log 2>&1
 echo "gibbs full rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:vecchia_factor_reg_kernel -s 1 -c 1 -f -o gpurun_out/prof_factor $CMD > gpurun_out/ncu_factor.log 2>&1
 echo "factor full rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"loglik_partial_kernel" -s 2 -c 1 -f -o gpurun_out/prof_loglik $CMD > gpurun_out/ncu_loglik.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"transpose_tile_kernel|sptrsv_syncfree_kernel" -s 1 -c 2 -f -o gpurun_out/prof_other $CMD > gpurun_out/ncu_other.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"transpose_tile2_kernel|sptrsv_syncfree_kernel" -s 1 -c 2 -f -o gpurun_out/prof_other $CMD > gpurun_out/ncu_other.log 2>&1
 echo "other full rc=$?"
 # gpurun copies back at most 64 MiB and every .ncu-rep carries ~14 MB of module image: keep the raw CSV pages instead
 for r in gpurun_out/*.ncu-rep; do
