@@ -1537,6 +1537,317 @@ __global__ void __launch_bounds__(THREADS) gibbs_chain_kernel(const int4 *__rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Dataflow sweep: ONE launch per sweep, no barrier between colours.  The colour order of the reference
+// (update_Gaussian.R:261) only constrains pairs of sites that are moral neighbours, i.e. pairs of TILES that touch a common
+// row of the factor.  ctx_create computes, for every tile, the earlier tiles it shares a row with and removes the pairs that
+// are implied by a two-step path (tile_dependencies, nngp_b200.cu): at n = 1M, m = 10 that leaves 6.9 predecessors per tile
+// (maximum 19), 99.8 % of them in the previous colour and a median of 660 tiles back in launch order.  A tile
+//   * streams its entries / per-site constants / draws exactly like gibbs_tile2_kernel (nothing there depends on r),
+//   * one thread per predecessor spins on that tile's flag (ld.acquire.gpu) until it carries this sweep's epoch,
+//   * gathers r (ld.global.cg: L1 is not coherent and there is no launch boundary any more), reduces, writes field,
+//     scatters r (st.global.cg), and publishes its own flag (bar.sync; fence; st.release.gpu).
+// Every pair of tiles that share a row is ordered by these flags (directly or through a chain), so RAW, WAR and WAW hazards
+// on r are all covered and the result is bit-identical to the colour-by-colour kernels.  Forward progress: tiles are
+// numbered colour-major and a tile only waits for lower-numbered tiles; with TICKET the tile number is drawn from a device
+// counter at CTA start (every lower number belongs to a CTA that is already resident), without it the kernel relies on the
+// hardware dispatching CTAs in blockIdx order (as the decoupled look-back scans do).  A bounded spin raises *stuck.
+// The epoch lives in flow[0] and is advanced by advance_sweep_kernel, so flags never need clearing.
+// ---------------------------------------------------------------------------------------------------------------
+#define NNGP_FLOW_STRIDE 8    // one 32-byte sector per tile flag
+#define NNGP_FLOW_HEADER 32   // flow[0] = epoch of the last completed sweep, flow[1] = ticket; flags start at flow[32]
+__device__ __forceinline__ double ld_cg_keep_f64(const double *p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cg_keep_f64(double *p, double v, unsigned long long pol) {
+    asm volatile("st.global.cg.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void flow_wait(const unsigned int *flags, const int *__restrict__ dep_idx, int d0, int d1,
+                                          unsigned int epoch, int *stuck) {
+    for (int k = d0 + (int)threadIdx.x; k < d1; k += (int)blockDim.x) {
+        const unsigned int *f = flags + (size_t)dep_idx[k] * NNGP_FLOW_STRIDE;
+        if (ld_acquire_gpu_u32(f) != epoch) {
+            const long long t0 = global_ns();
+            unsigned int it = 0;
+            while (ld_acquire_gpu_u32(f) != epoch)
+                if ((++it & 1023u) == 0 && global_ns() - t0 > 2000000000ll) { *stuck = 4; break; }
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void flow_publish(unsigned int *flag, unsigned int epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    }
+}
+
+template <int THREADS, int MINB, bool TICKET>
+__global__ void __launch_bounds__(THREADS, MINB) gibbs_flow_kernel(const int4 *__restrict__ tiles, const int *__restrict__ dep_ptr,
+                                                             const int *__restrict__ dep_idx, unsigned int *flow,
+                                                             const int *__restrict__ colptr, const int *__restrict__ crow,
+                                                             const unsigned char *__restrict__ cloc,
+                                                             const double *__restrict__ valT, const double *__restrict__ pd,
+                                                             const double *__restrict__ nobs, const double *__restrict__ S,
+                                                             const int *__restrict__ zpos, const int *__restrict__ gid,
+                                                             const int *__restrict__ psite, const double *__restrict__ zbuf,
+                                                             const SweepParams *__restrict__ spp, double *__restrict__ field,
+                                                             double *r, int *stuck) {
+    constexpr int EPT = 8;
+    constexpr int ECAP = THREADS * EPT;
+    __shared__ double sprod[ECAP + ECAP / 8];
+    __shared__ double sstart[THREADS], shead[THREADS];
+    __shared__ double sbc[2];
+    __shared__ int sticket;
+    const int tid = threadIdx.x;
+    int t = blockIdx.x;
+    if (TICKET) {
+        if (tid == 0) sticket = (int)atomicAdd(flow + 1, 1u);
+        __syncthreads();
+        t = sticket;
+    }
+    const int4 tile = tiles[t];
+    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
+    const SweepParams sp = *spp;
+    const unsigned int epoch = flow[0] + 1u;
+    unsigned int *flags = flow + NNGP_FLOW_HEADER;
+    const int d0 = dep_ptr[t], d1 = dep_ptr[t + 1];
+    if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
+        const int q = s0;
+        flow_wait(flags, dep_idx, d0, d1, epoch, stuck);
+        double acc[1] = {0.0};
+        for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * __ldcg(r + crow[e]);
+        block_reduce_sum<1>(acc);
+        if (tid == 0) {
+            const int sq = psite[q];
+            const double w_old = field[sq] - sp.beta0;
+            const double Qss = pd[q], no = nobs[q];
+            const double prec = sp.e_ls * Qss + sp.e_ln * no;
+            const double tt = acc[0] - Qss * w_old;
+            const double resid = S[q] - no * sp.beta0;
+            const double mean = sp.beta0 - (1.0 / prec) * (tt * sp.e_ls - sp.e_ln * resid);
+            const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
+            sbc[0] = (f_new - sp.beta0) - w_old;
+            field[sq] = f_new;
+        }
+        __syncthreads();
+        const double delta = sbc[0];
+        for (int e = e0 + tid; e < e1; e += THREADS) __stcg(r + crow[e], __ldcg(r + crow[e]) + valT[e] * delta);
+        flow_publish(flags + (size_t)t * NNGP_FLOW_STRIDE, epoch);
+        return;
+    }
+    const unsigned char *tloc = cloc + (size_t)t * ECAP;   // this tile's local site ids (255 = padding)
+    const unsigned long long pol = l2_evict_first_policy();
+    const unsigned long long keep = l2_evict_last_policy();
+    double val[EPT], rr[EPT];
+    int row[EPT];
+    unsigned int loc[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; k++) {
+        const int e = e0 + k * THREADS + tid;
+        loc[k] = ld_stream_u8<true>(tloc + k * THREADS + tid, pol);
+        if (e < e1) {
+            val[k] = ld_stream_f64<true>(valT + e, pol);
+            row[k] = ld_stream_s32<true>(crow + e, pol);
+        } else {
+            val[k] = 0.0;
+            row[k] = -1;
+        }
+    }
+    const unsigned long long sid = reinterpret_cast<const unsigned long long *>(tloc)[tid];
+    const unsigned int prev_last = tid > 0 ? (unsigned int)tloc[8 * tid - 1] : 255u;
+    int k0 = 0, k1 = 0, sq = 0;
+    SiteConst sc{0.0, 0.0, 0.0};
+    if (tid < s1 - s0) {
+        const int q = s0 + tid;
+        k0 = colptr[q] - e0;
+        k1 = colptr[q + 1] - e0;
+        sq = psite[q];
+        sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
+    }
+    flow_wait(flags, dep_idx, d0, d1, epoch, stuck);
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) rr[k] = ld_cg_keep_f64(r + row[k], keep);
+#pragma unroll
+    for (int k = 0; k < EPT; k++) sprod[NNGP_PADPOS(k * THREADS + tid)] = (row[k] >= 0) ? val[k] * rr[k] : 0.0;
+    __syncthreads();
+    blocked_run_sums<THREADS>(sprod, sid, prev_last, sstart, shead);
+    __syncthreads();
+    if (tid < s1 - s0) {
+        const double a = blocked_site_sum(sstart, shead, tid, k0, k1);
+        const double f_new = sc.c0 - sc.c1 * a;
+        sstart[tid] = f_new - sc.f_old;   // delta, once per site (sstart[tid] was read by this thread only)
+        field[sq] = f_new;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (row[k] >= 0) st_cg_keep_f64(r + row[k], rr[k] + val[k] * sstart[loc[k]], keep);
+    flow_publish(flags + (size_t)t * NNGP_FLOW_STRIDE, epoch);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dataflow sweep, persistent form with a TMA ring (gibbs_flow2_kernel).  gibbs_flow_kernel holds a tile's 1024 entries in
+// registers from the moment the CTA starts, so only 5 tiles per SM are in flight and ~4 us of every tile's 9 us life is the
+// dependent load chain descriptor -> entry stream (measured: scripts/timeline_pdl.py).  Here the grid is co-resident
+// (G = n_sm x CTAs/SM), CTA b owns tiles b, b+G, b+2G, ... of the colour-major list, and the one-touch streams of its next
+// STAGES tiles (factor values, row ids, local site ids: contiguous, 13 bytes per entry) are fetched by cp.async.bulk into a
+// shared-memory ring while the current tile is processed; registers hold only the 8 gathered r values per thread.  The
+// r-independent per-site constants of the NEXT tile are computed while the current tile's r gather is in flight.
+// Dependencies, flags, epoch and memory ordering are those of gibbs_flow_kernel.  Forward progress: every CTA works through
+// its tiles in increasing order and all CTAs are resident, so the lowest unfinished tile is always being worked on.
+// ---------------------------------------------------------------------------------------------------------------
+struct FlowSite { double c0, c1, f_old; int k0, k1, sq; };
+
+template <int THREADS, int STAGES, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) gibbs_flow2_kernel(const int4 *__restrict__ tiles, int n_tiles,
+                                                              const int *__restrict__ dep_ptr, const int *__restrict__ dep_idx,
+                                                              unsigned int *flow, const int *__restrict__ colptr,
+                                                              const int *__restrict__ crow, const unsigned char *__restrict__ cloc,
+                                                              const double *__restrict__ valT, const double *__restrict__ pd,
+                                                              const double *__restrict__ nobs, const double *__restrict__ S,
+                                                              const int *__restrict__ zpos, const int *__restrict__ gid,
+                                                              const int *__restrict__ psite, const double *__restrict__ zbuf,
+                                                              const SweepParams *__restrict__ spp, double *__restrict__ field,
+                                                              double *r, int *stuck) {
+    constexpr int EPT = 8;
+    constexpr int ECAP = THREADS * EPT;
+    constexpr int VAL_B = (ECAP + 2) * 8, ROW_B = (ECAP + 4) * 4, LOC_B = ECAP;   // one stage: values, rows, local ids
+    constexpr int STAGE_B = VAL_B + ROW_B + LOC_B;
+    extern __shared__ __align__(128) unsigned char flow_smem[];
+    double *sprod = reinterpret_cast<double *>(flow_smem + (size_t)STAGES * STAGE_B);       // [ECAP + ECAP / 8]
+    double *sstart = sprod + ECAP + ECAP / 8;                                                // [THREADS]
+    double *shead = sstart + THREADS;                                                        // [THREADS]
+    double *sbc = shead + THREADS;                                                           // [2]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(sbc + 2);             // [STAGES]
+    const int tid = threadIdx.x;
+    const int G = (int)gridDim.x;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + G - 1) / G : 0;
+    const SweepParams sp = *spp;
+    const unsigned int epoch = flow[0] + 1u;
+    unsigned int *flags = flow + NNGP_FLOW_HEADER;
+    const unsigned long long keep = l2_evict_last_policy();
+
+    auto issue = [&](int i, const int4 tl) {   // elected thread: stream tile i of this CTA into stage i % STAGES
+        const int stage = i % STAGES;
+        unsigned char *base = flow_smem + (size_t)stage * STAGE_B;
+        const int e0 = tl.z, e1 = tl.w;
+        if (e1 - e0 > ECAP) { mbar_arrive_expect_tx(full + stage, 0u); return; }   // oversize column: read straight from global
+        const int t = (int)blockIdx.x + i * G;
+        const int ev = e0 & ~1, er = e0 & ~3;   // 16-byte aligned starts; the arrays are padded past nnz
+        const unsigned int bv = (unsigned int)(((e1 - ev) * 8 + 15) & ~15), br = (unsigned int)(((e1 - er) * 4 + 15) & ~15);
+        mbar_arrive_expect_tx(full + stage, bv + br + (unsigned int)LOC_B);
+        tma_bulk_g2s(base, valT + ev, bv, full + stage);
+        tma_bulk_g2s(base + VAL_B, crow + er, br, full + stage);
+        tma_bulk_g2s(base + VAL_B + ROW_B, cloc + (size_t)t * ECAP, (unsigned int)LOC_B, full + stage);
+    };
+    auto site_part = [&](const int4 tl) {
+        FlowSite fs{0.0, 0.0, 0.0, 0, 0, 0};
+        if (tid < tl.y - tl.x && tl.w - tl.z <= ECAP) {
+            const int q = tl.x + tid;
+            fs.k0 = colptr[q] - tl.z;
+            fs.k1 = colptr[q + 1] - tl.z;
+            fs.sq = psite[q];
+            const SiteConst sc = site_const(sp, field[fs.sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
+            fs.c0 = sc.c0; fs.c1 = sc.c1; fs.f_old = sc.f_old;
+        }
+        return fs;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (my_tiles == 0) return;
+    if (tid == 0)
+        for (int i = 0; i < STAGES && i < my_tiles; i++) issue(i, tiles[(int)blockIdx.x + i * G]);
+    int4 tile = tiles[blockIdx.x];
+    FlowSite cur = site_part(tile);
+
+    for (int i = 0; i < my_tiles; i++) {
+        const int stage = i % STAGES;
+        const int t = (int)blockIdx.x + i * G;
+        const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
+        // descriptors needed later in this iteration: the next tile (site constants) and the tile that refills this stage
+        const bool has_next = i + 1 < my_tiles, has_refill = i + STAGES < my_tiles;
+        int4 tile_next = make_int4(0, 0, 0, 0), tile_refill = make_int4(0, 0, 0, 0);
+        if (has_next) tile_next = tiles[t + G];
+        if (tid == 0 && has_refill) tile_refill = tiles[t + STAGES * G];
+        const int d0 = dep_ptr[t], d1 = dep_ptr[t + 1];
+        FlowSite nxt{0.0, 0.0, 0.0, 0, 0, 0};
+        mbar_wait(full + stage, (unsigned int)((i / STAGES) & 1));
+        if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction from global memory
+            const int q = s0;
+            flow_wait(flags, dep_idx, d0, d1, epoch, stuck);
+            double acc[1] = {0.0};
+            for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * __ldcg(r + crow[e]);
+            block_reduce_sum<1>(acc);
+            if (tid == 0) {
+                const int sq = psite[q];
+                const double w_old = field[sq] - sp.beta0;
+                const double Qss = pd[q], no = nobs[q];
+                const double prec = sp.e_ls * Qss + sp.e_ln * no;
+                const double tt = acc[0] - Qss * w_old;
+                const double resid = S[q] - no * sp.beta0;
+                const double mean = sp.beta0 - (1.0 / prec) * (tt * sp.e_ls - sp.e_ln * resid);
+                const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
+                sbc[0] = (f_new - sp.beta0) - w_old;
+                field[sq] = f_new;
+            }
+            __syncthreads();
+            const double delta = sbc[0];
+            for (int e = e0 + tid; e < e1; e += THREADS) __stcg(r + crow[e], __ldcg(r + crow[e]) + valT[e] * delta);
+            if (has_next) nxt = site_part(tile_next);
+        } else {
+            const unsigned char *base = flow_smem + (size_t)stage * STAGE_B;
+            const double *s_val = reinterpret_cast<const double *>(base) + (e0 & 1);
+            const int *s_row = reinterpret_cast<const int *>(base + VAL_B) + (e0 & 3);
+            const unsigned char *s_loc = base + VAL_B + ROW_B;
+            const int ne = e1 - e0;
+            flow_wait(flags, dep_idx, d0, d1, epoch, stuck);
+            double rr[EPT];
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+                const int e = k * THREADS + tid;
+                rr[k] = (e < ne) ? ld_cg_keep_f64(r + s_row[e], keep) : 0.0;
+            }
+            if (has_next) nxt = site_part(tile_next);   // its loads travel with the gather
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+                const int e = k * THREADS + tid;
+                sprod[NNGP_PADPOS(e)] = (e < ne) ? s_val[e] * rr[k] : 0.0;
+            }
+            const unsigned long long sid = reinterpret_cast<const unsigned long long *>(s_loc)[tid];
+            const unsigned int prev_last = tid > 0 ? (unsigned int)s_loc[8 * tid - 1] : 255u;
+            __syncthreads();
+            blocked_run_sums<THREADS>(sprod, sid, prev_last, sstart, shead);
+            __syncthreads();
+            if (tid < s1 - s0) {
+                const double a = blocked_site_sum(sstart, shead, tid, cur.k0, cur.k1);
+                const double f_new = cur.c0 - cur.c1 * a;
+                sstart[tid] = f_new - cur.f_old;   // delta, once per site (sstart[tid] was read by this thread only)
+                field[cur.sq] = f_new;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+                const int e = k * THREADS + tid;
+                if (e < ne) st_cg_keep_f64(r + s_row[e], rr[k] + s_val[e] * sstart[s_loc[e]], keep);
+            }
+        }
+        flow_publish(flags + (size_t)t * NNGP_FLOW_STRIDE, epoch);   // bar.sync inside: every thread is done with this stage
+        if (tid == 0 && has_refill) issue(i + STAGES, tile_refill);
+        tile = tile_next;
+        cur = nxt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Persistent sweep kernel (the production path): ONE cooperative launch runs n_sweeps full sweeps.  The grid is
 // co-resident (cudaLaunchCooperativeKernel); colour classes are separated by a hand-rolled grid barrier (one atomic
 // arrival per CTA + acquire polling), not by kernel boundaries.  Every per-colour kernel launch cost ~10 us of pure latency
@@ -1961,10 +2272,14 @@ __global__ void allreduce_wait_sum_kernel(const double *area, int count, int wor
     }
 }
 
-__global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n, unsigned int *cdone, int K) {
+__global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n, unsigned int *cdone, int K, unsigned int *flow = nullptr) {
     if (threadIdx.x == 0) {
         spp->sweep_counter += 1ull;
         spp->z_offset += n;
+        if (flow) {   // dataflow sweep: next epoch, ticket back to zero
+            flow[0] += 1u;
+            flow[1] = 0u;
+        }
     }
     if (cdone)   // flag-chained sweep: the colour counters start every sweep at zero
         for (int k = threadIdx.x; k < 2 * K; k += blockDim.x) cdone[k * NNGP_CHAIN_STRIDE] = 0u;

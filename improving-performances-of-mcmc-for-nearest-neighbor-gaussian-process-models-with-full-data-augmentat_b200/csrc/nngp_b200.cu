@@ -199,6 +199,13 @@ struct Ctx {
     DevBuf<unsigned int> d_bar;
     DevBuf<double> d_pc0, d_pc1, d_pf;     // two-pass sweep: per-site constants of the current sweep (site_prepare_kernel)
     DevBuf<unsigned int> d_cdone;          // flag-chained sweep: arrivals per colour (one 128-byte line each)
+    // dataflow sweep (gibbs_flow_kernel): per tile the earlier tiles it must wait for (transitively reduced), epoch + flags
+    DevBuf<int> d_dep_ptr, d_dep_idx;
+    DevBuf<unsigned int> d_flow;
+    bool flow_ok = false;
+    int flow2_grid[6] = {0, 0, 0, 0, 0, 0};
+    long long flow_edges = 0, flow_edges_direct = 0;
+    int flow_max_deps = 0;
     int chain_sleep_ns = 0;
     double *h_pinned = nullptr;       // 64 doubles of pinned scratch for scalar results
     double *h_stage = nullptr;        // pinned staging for vectors (n doubles at least)
@@ -507,7 +514,47 @@ static long long *timeline_ptr() {
 
 static bool sweep_is_two_pass(Ctx *c) { return c->sweep_variant >= 18 && c->sweep_variant <= 20; }
 
+static bool sweep_is_flow(Ctx *c) { return c->sweep_variant >= 24 && c->sweep_variant <= 33 && c->flow_ok; }
+
+// persistent dataflow sweep: stages / CTAs per SM per variant; the grid must be co-resident (occupancy query, cached)
+template <int STAGES, int MINB>
+static void launch_flow2(Ctx *c, int slot) {
+    constexpr int ECAP = 1024;
+    constexpr size_t smem = (size_t)STAGES * ((ECAP + 2) * 8 + (ECAP + 4) * 4 + ECAP) + (size_t)(ECAP + ECAP / 8 + 2 * 128 + 2) * 8 + (size_t)STAGES * 8;
+    auto kern = gibbs_flow2_kernel<128, STAGES, MINB>;
+    if (c->flow2_grid[slot] == 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem));
+        REQUIRE(occ >= 1, "gibbs_flow2_kernel does not fit an SM");
+        c->flow2_grid[slot] = occ * c->n_sm;
+    }
+    const int nt = c->tile_ptr[1][c->K];
+    const int grid = std::min(c->flow2_grid[slot], nt);
+    kern<<<grid, 128, smem, c->stream>>>(c->d_tiles[1].p, nt, c->d_dep_ptr.p, c->d_dep_idx.p, c->d_flow.p, c->d_colptr.p, c->d_crow.p, c->d_cloc.p,
+                                          c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p,
+                                          c->d_sp.p, c->d_field.p, c->d_r.p, c->d_nbad.p + 1);
+}
+
 static void launch_sweep_colors(Ctx *c) {
+    if (sweep_is_flow(c)) {
+        // dataflow sweep: one launch over all tiles in colour-major order, per-tile dependency flags instead of colour barriers
+        const int nt = c->tile_ptr[1][c->K];
+#define NNGP_FLOW_ARGS c->d_tiles[1].p, c->d_dep_ptr.p, c->d_dep_idx.p, c->d_flow.p, c->d_colptr.p, c->d_crow.p, c->d_cloc.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, c->d_nbad.p + 1
+        if (c->sweep_variant == 24) gibbs_flow_kernel<128, 5, false><<<nt, 128, 0, c->stream>>>(NNGP_FLOW_ARGS);
+        else if (c->sweep_variant == 25) gibbs_flow_kernel<128, 5, true><<<nt, 128, 0, c->stream>>>(NNGP_FLOW_ARGS);
+        else if (c->sweep_variant == 26) gibbs_flow_kernel<128, 6, false><<<nt, 128, 0, c->stream>>>(NNGP_FLOW_ARGS);
+        else if (c->sweep_variant == 27) gibbs_flow_kernel<128, 4, false><<<nt, 128, 0, c->stream>>>(NNGP_FLOW_ARGS);
+        else if (c->sweep_variant == 28) launch_flow2<3, 4>(c, 0);
+        else if (c->sweep_variant == 29) launch_flow2<2, 5>(c, 1);
+        else if (c->sweep_variant == 30) launch_flow2<4, 3>(c, 2);
+        else if (c->sweep_variant == 31) launch_flow2<2, 6>(c, 3);
+        else if (c->sweep_variant == 32) launch_flow2<1, 8>(c, 4);
+        else launch_flow2<6, 2>(c, 5);
+#undef NNGP_FLOW_ARGS
+        advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, nullptr, c->K, c->d_flow.p);
+        return;
+    }
     if (sweep_is_two_pass(c)) {
         // pass 1: r-independent per-site constants (draw included) for every tiled site, full occupancy
         const int n_tiled = c->sharded ? c->n_owned : c->n;
@@ -634,7 +681,7 @@ static void launch_sweep_colors(Ctx *c) {
     advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, c->d_cdone.p, c->K);
 }
 
-static int sweep_launches(Ctx *c) { return c->K + 1 + (sweep_is_two_pass(c) ? 1 : 0); }
+static int sweep_launches(Ctx *c) { return sweep_is_flow(c) ? 2 : c->K + 1 + (sweep_is_two_pass(c) ? 1 : 0); }
 
 static bool sweep_is_persistent(Ctx *c) { return c->sweep_variant == 0 || c->sweep_variant == 4 || c->sweep_variant == 5; }
 
@@ -889,7 +936,7 @@ static void destroy_ctx(Ctx *c) {
     c->d_pred_rows.release();
     c->d_sp.release();
     for (int k = 0; k < 4; k++) { c->d_tiles[k].release(); c->d_tile_ptr[k].release(); }
-    c->d_rows_padded.release(); c->d_ticket.release(); c->d_bar.release(); c->d_cdone.release(); c->d_cloc.release(); c->d_pc0.release(); c->d_pc1.release(); c->d_pf.release();
+    c->d_rows_padded.release(); c->d_ticket.release(); c->d_bar.release(); c->d_cdone.release(); c->d_cloc.release(); c->d_dep_ptr.release(); c->d_dep_idx.release(); c->d_flow.release(); c->d_pc0.release(); c->d_pc1.release(); c->d_pf.release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -961,6 +1008,57 @@ struct ShardArgs {
     long long n_global;
     const char *comm_id;
 };
+
+// Tile dependency graph of the dataflow sweep.  Two tiles conflict when a row of the factor has an entry in a column of each
+// (their sites are moral neighbours); the reference's colour order (update_Gaussian.R:261) says the lower-numbered tile goes
+// first (tiles are numbered colour-major and same-colour sites never share a row).  preds[t] = every lower-numbered tile in
+// conflict with t; an edge u -> t is dropped when some v in preds[t] has u in preds[v] (a subset of the transitive reduction
+// that already brings 62 predecessors per tile down to 7 at n = 1M, m = 10).  nn: slot-major [M][ld], storage numbering.
+static void tile_dependencies(const std::vector<int4> &tiles, const std::vector<int> &colptr, const std::vector<int> &crow,
+                              const std::vector<int> &nn, int ld, int M, const std::vector<int> &pof, int n,
+                              std::vector<int> &dep_ptr, std::vector<int> &dep_idx, long long &n_direct, int &max_deps) {
+    const int nt = (int)tiles.size();
+    std::vector<int> tile_of(n, -1);   // by processing id
+    for (int t = 0; t < nt; t++)
+        for (int q = tiles[t].x; q < tiles[t].y; q++) tile_of[q] = t;
+    std::vector<std::vector<int>> preds(nt), kept(nt);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int t = 0; t < nt; t++) {
+        std::vector<int> &v = preds[t];
+        for (int e = tiles[t].z; e < tiles[t].w; e++) {
+            const int row = crow[e];
+            for (int j = 0; j < M; j++) {
+                const int s = nn[(size_t)j * ld + row];
+                if (s < 0) continue;
+                const int u = tile_of[pof[s]];
+                if (u >= 0 && u < t && (v.empty() || v.back() != u)) v.push_back(u);
+            }
+            if (v.size() > (size_t)1 << 16) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+        }
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    }
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int t = 0; t < nt; t++) {
+        const std::vector<int> &v = preds[t];
+        if (v.size() > 4096) { kept[t] = v; continue; }   // quadratic check not worth it: keep the full list (still correct)
+        for (size_t a = 0; a < v.size(); a++) {
+            bool implied = false;
+            for (size_t b = v.size(); b-- > a + 1 && !implied;) implied = std::binary_search(preds[v[b]].begin(), preds[v[b]].end(), v[a]);
+            if (!implied) kept[t].push_back(v[a]);
+        }
+    }
+    dep_ptr.assign(nt + 1, 0);
+    n_direct = 0;
+    max_deps = 0;
+    for (int t = 0; t < nt; t++) {
+        dep_ptr[t + 1] = dep_ptr[t] + (int)kept[t].size();
+        n_direct += (long long)preds[t].size();
+        max_deps = std::max(max_deps, (int)kept[t].size());
+    }
+    dep_idx.resize((size_t)dep_ptr[nt]);
+    for (int t = 0; t < nt; t++) std::copy(kept[t].begin(), kept[t].end(), dep_idx.begin() + dep_ptr[t]);
+}
 
 static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const double *locs, const int *NNarray, const int *coloring,
                             const int *n_obs_, const int *locs_match, const int *covfun_id, const int *device, const int *layout,
@@ -1196,7 +1294,8 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     cudaStream_t s = c->stream;
     c->d_psite.upload(psite, s); c->d_gid.upload(gid, s);
     c->d_i2g.upload(c->i2g, s); c->d_g2i.upload(c->g2i, s); c->d_nn.upload(nn, s); c->d_colptr.upload(colptr, s);
-    c->d_crow.upload(crow, s); c->d_csrc.upload(csrc, s); c->d_zpos.upload(zpos, s); c->d_lvl_rows.upload(lvl_rows, s);
+    { std::vector<int> crow_padded(crow); crow_padded.resize(crow.size() + 4, 0); c->d_crow.upload(crow_padded, s); }   // + 4: see d_valT
+    c->d_csrc.upload(csrc, s); c->d_zpos.upload(zpos, s); c->d_lvl_rows.upload(lvl_rows, s);
     c->d_lvl_ptr.upload(c->lvl_ptr, s); c->d_lm.upload(lm, s); c->d_optr.upload(optr, s); c->d_oidx.upload(oidx, s);
     c->d_cstart.upload(c->cstart, s); c->d_locs.upload(locs_int, s); c->d_nobs.upload(nobs, s);
     if (!c->partial_rows.empty()) c->d_partial_rows.upload(c->partial_rows, s);
@@ -1206,6 +1305,17 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     c->d_rows_padded.upload(rows_padded, s);
     for (int cfg = 0; cfg < 4; cfg++) { c->d_tiles[cfg].upload(tiles[cfg], s); c->d_tile_ptr[cfg].upload(c->tile_ptr[cfg], s); }
     c->d_cloc.upload(cloc, s);
+    if (!c->sharded) {   // dataflow sweep: tile dependency lists, epoch word + ticket + one flag sector per tile
+        std::vector<int> dep_ptr, dep_idx;
+        tile_dependencies(tiles[1], colptr, crow, nn, ld, M, pof, n, dep_ptr, dep_idx, c->flow_edges_direct, c->flow_max_deps);
+        c->flow_edges = (long long)dep_idx.size();
+        if (dep_idx.empty()) dep_idx.push_back(0);
+        c->d_dep_ptr.upload(dep_ptr, s);
+        c->d_dep_idx.upload(dep_idx, s);
+        c->d_flow.alloc((size_t)NNGP_FLOW_HEADER + tiles[1].size() * NNGP_FLOW_STRIDE);
+        CK(cudaMemsetAsync(c->d_flow.p, 0, c->d_flow.n * sizeof(unsigned int), s));
+        c->flow_ok = true;
+    }
     c->d_pc0.alloc((size_t)n); c->d_pc1.alloc((size_t)n); c->d_pf.alloc((size_t)n);
     c->d_bar.alloc(1);
     c->d_cdone.alloc((size_t)std::max(1, c->K) * 2 * NNGP_CHAIN_STRIDE);
@@ -1229,7 +1339,9 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     }
     c->d_tl.alloc((size_t)n * c->dt);
     for (int k = 0; k < 2; k++) { c->d_linv[k].alloc((size_t)ld * M); CK(cudaMemsetAsync(c->d_linv[k].p, 0, sizeof(double) * ld * M, s)); }
-    c->d_valT.alloc(c->nnz); c->d_pd.alloc(n); c->d_ymx.alloc(std::max(n_obs, 1)); c->d_S.alloc(n); c->d_field.alloc(n);
+    c->d_valT.alloc((size_t)c->nnz + 2);   // + 2: the bulk copies of gibbs_flow2_kernel are 16-byte granular
+    CK(cudaMemsetAsync(c->d_valT.p + c->nnz, 0, 2 * sizeof(double), s));
+    c->d_pd.alloc(n); c->d_ymx.alloc(std::max(n_obs, 1)); c->d_S.alloc(n); c->d_field.alloc(n);
     c->d_newfield.alloc(n); c->d_r.alloc(n); c->d_tmp1.alloc(n); c->d_tmp2.alloc(n); c->d_io.alloc((size_t)std::max(n, n_obs));
     c->d_zbuf.alloc(n); c->d_partials.alloc((size_t)kReduceBlocks * 4); c->d_scalars.alloc(64); c->d_sp.alloc(1);
     CK(cudaMemsetAsync(c->d_S.p, 0, sizeof(double) * n, s));
@@ -1334,7 +1446,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
     use(c);
     CK(cudaStreamSynchronize(c->stream));
     switch (*key) {
-        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 23, "sweep variant must be 0..23"); c->sweep_variant = *value; break;
+        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 33, "sweep variant must be 0..33"); c->sweep_variant = *value; break;
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;
