@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "nngp_factor_get", "nngp_factor_accept", "nngp_factor_commit", "nngp_precision_diag", "nngp_field_set",
     "nngp_field_get", "nngp_obs_set", "nngp_loglik", "nngp_loglik_host", "nngp_spmv", "nngp_sptmv", "nngp_sptrsv",
     "nngp_gibbs_sweep", "nngp_ancillary_propose", "nngp_ancillary_accept", "nngp_beta0_moments", "nngp_ssr",
-    "nngp_field_init", "nngp_chain_run", "nngp_records_summary", "nngp_predict_sample", "nngp_time_op", "nngp_launch_count", "nngp_debug_timeline", "nngp_debug_colour_times", "nngp_debug_colour_phases", "nngp_host_alloc", "nngp_host_free",
+    "nngp_field_init", "nngp_chain_run", "nngp_regressors_set", "nngp_chain_run_regressors", "nngp_records_summary", "nngp_predict_sample", "nngp_time_op", "nngp_launch_count", "nngp_debug_timeline", "nngp_debug_colour_times", "nngp_debug_colour_phases", "nngp_host_alloc", "nngp_host_free",
 ]
 
 

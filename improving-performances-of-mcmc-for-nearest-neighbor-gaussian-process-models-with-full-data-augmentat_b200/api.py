@@ -226,9 +226,11 @@ def release_contexts(mcmc_nngp_list):
 
 def mcmc_nngp_update_Gaussian(locs, X, observed_field, space_time_model, vecchia_approx, states, n_iterations_update,
                               n_cores=None, field_thinning=1, ancillary=True, n_chromatic=10, iterations=None, n_gpus=None,
-                              rng="philox"):
+                              rng="philox", regressor_engine="device"):
     """Returns [ {"state": ..., "records": ...} per chain ] like the reference (:315).  `ancillary` is accepted and ignored,
-    as in the reference (quirk 1).  Chains are not forked: chain i runs on GPU i mod n_gpus inside this process."""
+    as in the reference (quirk 1).  Chains are not forked: chain i runs on GPU i mod n_gpus inside this process.
+    regressor_engine (models with X): "device" = the whole loop behind nngp_chain_run_regressors (X resident in HBM);
+    "host" = the loop driven from Python over the device primitives (kept as a cross-check of the former)."""
     n_dev = L.device_count()
     if n_dev < 1:
         raise L.NNGPError(2, "no CUDA device: libnngp_b200 has no CPU fallback")
@@ -244,9 +246,12 @@ def mcmc_nngp_update_Gaussian(locs, X, observed_field, space_time_model, vecchia
         if X["X"] is None:
             out.append(_update_chain_device(ctx, state, observed_field, shape_params, var_y, n_iterations_update, field_thinning,
                                             n_chromatic, iter_start, i + 1, rng))
-        else:
+        elif regressor_engine == "host":
             out.append(_update_chain_regressors(ctx, state, X, observed_field, vecchia_approx, shape_params, var_y, n_iterations_update,
                                                 field_thinning, n_chromatic, iter_start, i + 1))
+        else:
+            out.append(_update_chain_regressors_device(ctx, state, X, observed_field, vecchia_approx, shape_params, var_y,
+                                                       n_iterations_update, field_thinning, n_chromatic, iter_start, i + 1, rng))
     return out
 
 
@@ -276,6 +281,28 @@ def _update_chain_device(ctx, state, observed_field, shape_params, var_y, n_iter
                  "params": {"shape": po["shape"], "beta_0": po["beta_0"], "log_scale": po["log_scale"],
                             "log_noise_variance": po["log_noise_variance"], "field": ctx.field_get()}}
     return {"state": new_state, "records": _records_dict(rec, shape_params, frec)}
+
+
+def _update_chain_regressors_device(ctx, state, X, y, va, shape_params, var_y, n_iter, thin, n_chromatic, iter_start, chain_index, rng):
+    """Regressor model: the whole loop (:101-314 including the regression block :226-250) behind nngp_chain_run_regressors.
+    X$X, X$X[hctam_scol_1, X$locs] and the observations are uploaded once per context and stay in HBM."""
+    p = state["params"]
+    tk = state["transition_kernels"]
+    if not getattr(ctx, "_regressors_loaded", False):
+        ctx.regressors_set(X["X"], y, xlocs=[int(c) + 1 for c in X["locs"]], first_obs=va["hctam_scol_1"])
+        ctx._regressors_loaded = True
+    ctx.field_set(p["field"])
+    params = {"shape": p["shape"], "beta_0": p["beta_0"], "log_scale": p["log_scale"], "log_noise_variance": p["log_noise_variance"],
+              "logvar_sufficient": tk["covariance_params_sufficient"]["logvar"], "logvar_ancillary": tk["covariance_params_ancillary"]["logvar"]}
+    po, rec, brec, frec, _ = ctx.chain_run_regressors(params, p["beta"], X["solve_1XT1X"], X["chol_solve_1XT1X"], n_iter, var_y, thin=thin,
+                                                      n_chromatic=n_chromatic, iter_start=iter_start, chain_index=chain_index,
+                                                      rng_mode=L.RNG_SUPPLIED if rng == "R" else L.RNG_PHILOX)
+    new_state = {"transition_kernels": {"covariance_params_sufficient": {"logvar": po["logvar_sufficient"]},
+                                        "covariance_params_ancillary": {"logvar": po["logvar_ancillary"]},
+                                        "log_noise_variance": dict(tk["log_noise_variance"])},
+                 "params": {**p, "shape": po["shape"], "beta_0": po["beta_0"], "beta": po["beta"], "log_scale": po["log_scale"],
+                            "log_noise_variance": po["log_noise_variance"], "field": ctx.field_get()}}
+    return {"state": new_state, "records": _records_dict(rec, shape_params, frec, beta=brec, beta_names=X["names"])}
 
 
 def _update_chain_regressors(ctx, state, X, y, va, shape_params, var_y, n_iter, thin, n_chromatic, iter_start, chain_index):

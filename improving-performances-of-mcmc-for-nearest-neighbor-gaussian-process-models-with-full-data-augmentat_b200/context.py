@@ -206,6 +206,45 @@ class NNGPContext:
         frec_m = frec[: n_frec * self.n].reshape((n_frec, self.n), order="F") if keep_field else None
         return out, rec.reshape((n_iter, 3 + shape.size), order="F"), frec_m, acc.reshape((n_iter, 2), order="F")
 
+    def regressors_set(self, X, observed_field, xlocs=(), first_obs=None):
+        """nngp_regressors_set: X$X (n_obs x p, centred, no intercept), observed_field, X$locs (1-based columns) and
+        hctam_scol_1 stay resident on the device for chain_run_regressors."""
+        Xf = np.asfortranarray(X, dtype=np.float64)
+        y = L.f64(observed_field)
+        xl = np.ascontiguousarray(xlocs, dtype=np.int32)
+        fo = None if first_obs is None else np.ascontiguousarray(first_obs, dtype=np.int32)
+        self._reg_p = Xf.shape[1]
+        self._call("nngp_regressors_set", L.ci(Xf.shape[1]), Xf.ctypes.data_as(C.POINTER(C.c_double)), L.dptr(y), L.ci(xl.size),
+                   L.iptr(xl) if xl.size else None, L.iptr(fo) if fo is not None else None)
+
+    def chain_run_regressors(self, params: dict, beta, solve_1XT1X, chol_solve_1XT1X, n_iter, var_y, thin=1.0, n_chromatic=10,
+                             iter_start=0, chain_index=1, rng_mode=L.RNG_PHILOX, keep_field=True):
+        """nngp_chain_run_regressors: the reference loop with the regression updates (update_Gaussian.R:226-250) behind the ABI."""
+        shape = np.atleast_1d(np.asarray(params["shape"], dtype=np.float64))
+        p = np.concatenate([[params["beta_0"], params["log_scale"], params["log_noise_variance"],
+                             params.get("logvar_sufficient", -2.0), params.get("logvar_ancillary", -2.0)], shape])
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        b = np.array(beta, dtype=np.float64).ravel().copy()
+        P1 = b.size + 1
+        S = np.asfortranarray(solve_1XT1X, dtype=np.float64)
+        Ch = np.asfortranarray(chol_solve_1XT1X, dtype=np.float64)
+        assert S.shape == (P1, P1) and Ch.shape == (P1, P1) and b.size == getattr(self, "_reg_p", -1)
+        n_iter = int(n_iter)
+        rec = np.zeros(n_iter * (3 + shape.size))
+        brec = np.zeros(max(n_iter * b.size, 1))
+        n_frec = int(round(n_iter * thin))
+        frec = np.zeros(max(n_frec, 1) * self.n) if keep_field else None
+        acc = np.zeros(2 * n_iter, dtype=np.int32)
+        self._call("nngp_chain_run_regressors", L.ci(shape.size), L.dptr(p), L.dptr(b), S.ctypes.data_as(C.POINTER(C.c_double)),
+                   Ch.ctypes.data_as(C.POINTER(C.c_double)), L.ci(n_iter), L.cd(thin), L.ci(n_chromatic), L.ci(iter_start),
+                   L.ci(chain_index), L.ci(rng_mode), L.cd(var_y), L.dptr(rec), L.dptr(brec),
+                   L.dptr(frec) if keep_field else None, L.iptr(acc))
+        out = dict(beta_0=p[0], log_scale=p[1], log_noise_variance=p[2], logvar_sufficient=p[3], logvar_ancillary=p[4],
+                   shape=p[5:].copy(), beta=b)
+        frec_m = frec[: n_frec * self.n].reshape((n_frec, self.n), order="F") if keep_field else None
+        return (out, rec.reshape((n_iter, 3 + shape.size), order="F"), brec[: n_iter * b.size].reshape((n_iter, b.size), order="F"),
+                frec_m, acc.reshape((n_iter, 2), order="F"))
+
     def records_summary(self, first_row: int, n_rows: int, offsets=None) -> np.ndarray:
         """get_summary (estimate.R:1-6) of the field samples kept on the device by the last chain_run; n x 5"""
         out = np.empty(self.n * 5)

@@ -2285,4 +2285,78 @@ __global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n, uns
         for (int k = threadIdx.x; k < 2 * K; k += blockDim.x) cdone[k * NNGP_CHAIN_STRIDE] = 0u;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// regression coefficients (Scripts/mcmc_nngp_update_Gaussian.R:226-250): the only dense algebra on the path.  X$X
+// (n_obs x p, column-major) and the site-level design cbind(1, X$X[hctam_scol_1, X$locs]) stay resident in HBM; every
+// product with them is a streaming pass (HBM-bound, FP64), the (p+1)-dimensional solves are host scalars.
+// ---------------------------------------------------------------------------------------------------------------
+// out_o = observed_field_o - field[locs_match_o] + beta_0      (:229, left factor of the crossprod)
+__global__ void __launch_bounds__(256) obs_resid_kernel(const int *__restrict__ lm, const double *__restrict__ y,
+                                                        const double *__restrict__ field, double beta0, int n_obs,
+                                                        double *__restrict__ out) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) out[o] = y[o] - field[lm[o]] + beta0;
+}
+
+// ymx_o = observed_field_o - sum_k X[o,k] beta_k  (= observed_field - mu + beta_0, :249 and its uses :129,260,281);
+// X is the block of columns 1..p of cbind(1, X$X)
+__global__ void __launch_bounds__(256) obs_minus_xb_kernel(const double *__restrict__ X, const double *__restrict__ beta, int p,
+                                                           const double *__restrict__ y, int n_obs, double *__restrict__ ymx) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < p; k++) s += X[(size_t)k * n_obs + o] * __ldg(beta + k);
+        ymx[o] = y[o] - s;
+    }
+}
+
+// out_q = in_q + sign * sum_{l=1..q_cols-1} Xl[q,l] coef_l    (:240 other_field, :245 back; column 0 of Xl is the intercept)
+__global__ void __launch_bounds__(256) site_design_axpy_kernel(const double *__restrict__ Xl, const double *__restrict__ coef, int q_cols,
+                                                               int n, double sign, const double *__restrict__ in, double *__restrict__ out) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int l = 1; l < q_cols; l++) s += Xl[(size_t)l * n + q] * __ldg(coef + l);
+        out[q] = in[q] + sign * s;
+    }
+}
+
+// v_q = (v_q - sub) + add      (:232 field - beta_0 + innovation[1], evaluated in R's order)
+__global__ void __launch_bounds__(256) shift_kernel(double *__restrict__ v, int n, double sub, double add) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) v[q] = (v[q] - sub) + add;
+}
+
+// C = A^T B for tall column-major A (rows x qa) and B (rows x qb): crossprod() of :78,81,229,241.
+// grid (ceil(qa/16), ceil(qb/16), chunks); a CTA owns a 16 x 16 tile of C over one chunk of rows, staged 64 rows at a time
+// through shared memory (row-contiguous, i.e. coalesced, loads); per-chunk partials are summed in chunk order by
+// atb_reduce_kernel, so the result does not depend on the launch geometry's scheduling (no atomics).
+#define NNGP_ATB_ROWS 64
+__global__ void __launch_bounds__(256) atb_partial_kernel(const double *__restrict__ A, int qa, const double *__restrict__ B, int qb,
+                                                          int rows, int rows_per_chunk, double *__restrict__ part) {
+    __shared__ double As[16][NNGP_ATB_ROWS + 1], Bs[16][NNGP_ATB_ROWS + 1];
+    const int ta = threadIdx.x & 15, tb = threadIdx.x >> 4;
+    const int ja0 = blockIdx.x * 16, jb0 = blockIdx.y * 16;
+    const int r_begin = blockIdx.z * rows_per_chunk, r_end = min(rows, r_begin + rows_per_chunk);
+    double acc = 0.0;
+    for (int r0 = r_begin; r0 < r_end; r0 += NNGP_ATB_ROWS) {
+        for (int e = threadIdx.x; e < 16 * NNGP_ATB_ROWS; e += 256) {
+            const int col = e / NNGP_ATB_ROWS, rr = e % NNGP_ATB_ROWS, r = r0 + rr;
+            As[col][rr] = (r < r_end && ja0 + col < qa) ? A[(size_t)(ja0 + col) * rows + r] : 0.0;
+            Bs[col][rr] = (r < r_end && jb0 + col < qb) ? B[(size_t)(jb0 + col) * rows + r] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int rr = 0; rr < NNGP_ATB_ROWS; rr++) acc += As[ta][rr] * Bs[tb][rr];
+        __syncthreads();
+    }
+    if (ja0 + ta < qa && jb0 + tb < qb) part[(size_t)blockIdx.z * qa * qb + (size_t)(jb0 + tb) * qa + (ja0 + ta)] = acc;
+}
+
+// C[e] = sum over chunks (ascending) of part[chunk][e]; C is qa x qb column-major
+__global__ void __launch_bounds__(256) atb_reduce_kernel(const double *__restrict__ part, int n_chunks, int qaqb, double *__restrict__ C) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < qaqb; e += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < n_chunks; k++) s += part[(size_t)k * qaqb + e];
+        C[e] = s;
+    }
+}
+
+
 }  // namespace nngp

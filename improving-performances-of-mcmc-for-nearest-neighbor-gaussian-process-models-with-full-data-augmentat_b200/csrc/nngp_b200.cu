@@ -183,6 +183,13 @@ struct Ctx {
     int pred_n0 = -1, pred_slots = 0, pred_levels = 0;
     DevBuf<int> d_pred_rows;
     DevBuf<double> d_frec;                 // device-side record store of the last chain_run: n_frec x n, column-major
+    // regressors of the Gaussian model (nngp_regressors_set): design matrices resident in HBM
+    int reg_p = -1, reg_q = 0;             // ncol(X$X) (-1 = none set); 1 + length(X$locs) (0 = no location-level regressors)
+    std::vector<int> reg_xlocs;            // 0-based columns of X$X listed in X$locs
+    DevBuf<double> d_Xa;                   // cbind(1, X$X): n_obs x (p+1), column-major, observation order
+    DevBuf<double> d_Xl;                   // cbind(1, X$X[hctam_scol_1, X$locs]): n x q, column-major, storage order
+    DevBuf<double> d_B;                    // sparse_chol %*% d_Xl of the current factor (sparse_chol_X_locs)
+    DevBuf<double> d_yobs, d_robs, d_coef, d_atb_part, d_atb_out;
     int frec_rows = 0;
     DevBuf<double> d_mtab;
     bool matern_table = true;              // tabulate the Matern kernel per factor build (false: evaluate K_nu per pair)
@@ -909,6 +916,91 @@ static void ensure_zbuf(Ctx *c, size_t count) {
 
 static void refresh_r(Ctx *c, double beta0) { op_spmv(c, c->d_linv[c->cur].p, c->d_field.p, beta0, c->d_r.p); }
 
+// ---- dense products with the resident design matrices (update_Gaussian.R:226-246) ----
+static const int kAtbRowsPerChunk = 4096;
+
+// host_out (qa x qb, column-major) = A^T B over `rows` rows; returns after the result is on the host
+static void op_atb(Ctx *c, const double *A, int qa, const double *B, int qb, int rows, double *host_out) {
+    const int chunks = std::max(1, (rows + kAtbRowsPerChunk - 1) / kAtbRowsPerChunk);
+    const size_t qq = (size_t)qa * qb;
+    if (c->d_atb_part.n < qq * chunks) c->d_atb_part.alloc(qq * chunks);
+    if (c->d_atb_out.n < qq) c->d_atb_out.alloc(qq);
+    dim3 grid((qa + 15) / 16, (qb + 15) / 16, chunks);
+    atb_partial_kernel<<<grid, 256, 0, c->stream>>>(A, qa, B, qb, rows, kAtbRowsPerChunk, c->d_atb_part.p);
+    LAUNCHED(c);
+    atb_reduce_kernel<<<grid_for(c, (long long)qq, 256), 256, 0, c->stream>>>(c->d_atb_part.p, chunks, (int)qq, c->d_atb_out.p);
+    LAUNCHED(c);
+    CK(cudaMemcpyAsync(host_out, c->d_atb_out.p, qq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+}
+
+// in place: lower Cholesky factor of the symmetric positive definite q x q matrix A (column-major), upper part zeroed;
+// false when a pivot falls below 1e-13 of its diagonal entry
+static bool dense_chol_lower(std::vector<double> &A, int q) {
+    for (int j = 0; j < q; j++) {
+        const double ajj = A[(size_t)j + (size_t)q * j];
+        double dj = ajj;
+        for (int k = 0; k < j; k++) dj -= A[(size_t)j + (size_t)q * k] * A[(size_t)j + (size_t)q * k];
+        if (!(dj > 1e-13 * ajj)) return false;                        // numerically singular (e.g. collinear regressors)
+        dj = std::sqrt(dj);
+        A[(size_t)j + (size_t)q * j] = dj;
+        for (int i = j + 1; i < q; i++) {
+            double v = A[(size_t)i + (size_t)q * j];
+            for (int k = 0; k < j; k++) v -= A[(size_t)i + (size_t)q * k] * A[(size_t)j + (size_t)q * k];
+            A[(size_t)i + (size_t)q * j] = v / dj;
+        }
+        for (int i = 0; i < j; i++) A[(size_t)i + (size_t)q * j] = 0.0;
+    }
+    return true;
+}
+
+// inverse of a symmetric positive definite matrix through its Cholesky factor: P = L L^T, P^-1 = L^-T L^-1
+static bool dense_spd_inverse(const std::vector<double> &P, int q, std::vector<double> &inv) {
+    std::vector<double> L(P);
+    if (!dense_chol_lower(L, q)) return false;
+    std::vector<double> Li((size_t)q * q, 0.0);                       // L^-1, lower triangular, column by column
+    for (int j = 0; j < q; j++) {
+        Li[(size_t)j + (size_t)q * j] = 1.0 / L[(size_t)j + (size_t)q * j];
+        for (int i = j + 1; i < q; i++) {
+            double v = 0.0;
+            for (int k = j; k < i; k++) v -= L[(size_t)i + (size_t)q * k] * Li[(size_t)k + (size_t)q * j];
+            Li[(size_t)i + (size_t)q * j] = v / L[(size_t)i + (size_t)q * i];
+        }
+    }
+    inv.assign((size_t)q * q, 0.0);
+    for (int a = 0; a < q; a++)
+        for (int b = 0; b <= a; b++) {
+            double v = 0.0;
+            for (int k = a; k < q; k++) v += Li[(size_t)k + (size_t)q * a] * Li[(size_t)k + (size_t)q * b];
+            inv[(size_t)a + (size_t)q * b] = v;
+            inv[(size_t)b + (size_t)q * a] = v;
+        }
+    return true;
+}
+
+// mu = beta_0 + X$X %*% beta (:249) enters every later step as observed_field - mu + beta_0 = y - X beta: refresh d_ymx and
+// the per-site sums residuals_sum (:260)
+static void op_set_beta(Ctx *c, const double *beta) {
+    CK(cudaMemcpyAsync(c->d_coef.p, beta, sizeof(double) * c->reg_p, cudaMemcpyHostToDevice, c->stream));
+    obs_minus_xb_kernel<<<grid_for(c, c->n_obs, 256), 256, 0, c->stream>>>(c->d_Xa.p + c->n_obs, c->d_coef.p, c->reg_p, c->d_yobs.p, c->n_obs, c->d_ymx.p);
+    LAUNCHED(c);
+    site_obs_sum_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_optr.p, c->d_oidx.p, c->d_ymx.p, c->n, c->d_S.p);
+    LAUNCHED(c);
+    CK(cudaStreamSynchronize(c->stream));                              // `beta` may live on the caller's stack
+}
+
+// :77-83 (and after every accepted proposal :145-151, :200-206): sparse_chol_X_locs = sparse_chol %*% cbind(1, X_locs),
+// beta_interweaved_covmat = solve(crossprod(.)), and the lower Cholesky factor of the latter (= t(chol(.)) in R)
+static void op_interweave(Ctx *c, std::vector<double> &cov, std::vector<double> &chol_lower) {
+    const int q = c->reg_q, n = c->n;
+    for (int l = 0; l < q; l++) op_spmv(c, c->d_linv[c->cur].p, c->d_Xl.p + (size_t)l * n, 0.0, c->d_B.p + (size_t)l * n);
+    std::vector<double> prec((size_t)q * q);
+    op_atb(c, c->d_B.p, q, c->d_B.p, q, n, prec.data());
+    if (!dense_spd_inverse(prec, q, cov)) { set_error("interweaving: crossprod(sparse_chol %%*%% cbind(1, X_locs)) is not positive definite (collinear location regressors?)"); throw StateFail(); }
+    chol_lower = cov;
+    if (!dense_chol_lower(chol_lower, q)) { set_error("interweaving: beta_interweaved_covmat is not positive definite"); throw StateFail(); }
+}
+
 static void flush_l2(Ctx *c) {
     if (c->d_flush.n == 0) c->d_flush.alloc((size_t)32 << 20);  // 256 MB of doubles
     fill_f64_kernel<<<c->n_sm * 8, 256, 0, c->stream>>>(c->d_flush.p, 1.0, c->d_flush.n);
@@ -933,6 +1025,7 @@ static void destroy_ctx(Ctx *c) {
     for (auto *b : db) b->release();
     c->d_mtab.release();
     c->d_frec.release();
+    c->d_Xa.release(); c->d_Xl.release(); c->d_B.release(); c->d_yobs.release(); c->d_robs.release(); c->d_coef.release(); c->d_atb_part.release(); c->d_atb_out.release();
     c->d_pred_rows.release();
     c->d_sp.release();
     for (int k = 0; k < 4; k++) { c->d_tiles[k].release(); c->d_tile_ptr[k].release(); }
@@ -1965,18 +2058,32 @@ void nngp_predict_sample(const int *ctx_id, const int *slot, const int *n_obs_si
     ABI_END
 }
 
-void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, const int *n_iter_, const double *thin_,
-                    const int *n_chromatic_, const int *iter_start_, const int *chain_index_, const int *rng_mode_,
-                    const double *var_y_, double *records_out, double *field_records_out, int *accept_out, int *status) {
-    ABI_BEGIN
-    Ctx *c = get_ctx(ctx_id);
-    NEED(!c->sharded, "nngp_chain_run: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
-    REQUIRE(n_shape_ && params_io && n_iter_ && thin_ && n_chromatic_ && iter_start_ && chain_index_ && rng_mode_ && var_y_, "nngp_chain_run: null argument");
+}  // extern "C"
+
+// regression part of one chain (nngp_chain_run_regressors); nullptr = the no-regressor model
+struct RegRun {
+    double *beta_io;              // p: state$params$beta in, out
+    const double *solve_1XT1X;    // (p+1) x (p+1): X$solve_1XT1X      (initialize.R:135)
+    const double *chol_1XT1X;     // (p+1) x (p+1): X$chol_solve_1XT1X (initialize.R:136; upper factor)
+    double *beta_records;         // n_iter x p column-major, or NULL
+};
+
+// The loop of Scripts/mcmc_nngp_update_Gaussian.R:101-314 for one chain, entirely on the device side of the ABI.
+static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const int *n_iter_, const double *thin_,
+                           const int *n_chromatic_, const int *iter_start_, const int *chain_index_, const int *rng_mode_,
+                           const double *var_y_, double *records_out, double *field_records_out, int *accept_out, const RegRun *reg) {
     const int ns = *n_shape_, n_iter = *n_iter_, n_chromatic = *n_chromatic_, iter_start = *iter_start_, rng_mode = *rng_mode_;
     const double thin = *thin_, var_y = *var_y_;
     REQUIRE(ns >= 1 && ns <= 5 && n_iter >= 0 && n_chromatic >= 0, "nngp_chain_run: bad sizes");
-    NEED(c->have_field && c->have_obs, "nngp_chain_run: field and observations must be set first");
     use(c);
+    // regressors: beta, the interweaving matrices (:77-83) and scratch for the (p+1)- and q-vectors
+    const int reg_p = reg ? c->reg_p : 0, reg_q = reg ? c->reg_q : 0, P1 = reg_p + 1;
+    std::vector<double> beta, iw_cov, iw_chol, gvec, bmean, zz, innov, coefl;
+    if (reg) {
+        beta.assign(reg->beta_io, reg->beta_io + reg_p);
+        const size_t w = (size_t)std::max(P1, reg_q);
+        gvec.resize(w); bmean.resize(w); zz.resize(w); innov.resize(w); coefl.resize(w);
+    }
     const int n = c->n, n_obs = c->n_obs;
     const bool matern = c->covfun >= NNGP_MATERN_ISOTROPIC;
     double beta_0 = params_io[0], log_scale = params_io[1], lnv = params_io[2], logvar_suf = params_io[3], logvar_anc = params_io[4];
@@ -2005,6 +2112,8 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
     // host RNG per call (n = 1M) are skipped and the scalar draws simply continue from the seeded state.
     if (rng_mode == NNGP_RNG_SUPPLIED) { zhost.resize(n); rs.rnorm(zhost.data(), n); }
     std::vector<int> acc_anc(n_iter + 1, 0), acc_suf(n_iter + 1, 0);
+    if (reg_q > 0) op_interweave(c, iw_cov, iw_chol);                            // :77-83
+    if (reg) op_set_beta(c, beta.data());                                        // :85
     const int n_frec = (int)std::nearbyint(n_iter * thin);
     // stored field samples stay in HBM, already in R's n_frec x n column-major layout, and leave in one copy at the end
     bool frec_on_device = false;
@@ -2039,6 +2148,7 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
             c->cur = 1 - c->cur;
             op_commit(c);
             acc_anc[iter] = 1;
+            if (reg_q > 0) op_interweave(c, iw_cov, iw_chol);                    // :145-151
         }
         if (iter_start >= 0 && iter_start <= 2000 && iter % 25 == 0) {           // :153-157
             int a = 0;
@@ -2066,6 +2176,7 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
                 c->cur = 1 - c->cur;
                 op_commit(c);
                 acc_suf[iter] = 1;
+                if (reg_q > 0) op_interweave(c, iw_cov, iw_chol);                // :200-206
             }
         }
         if (iter_start >= 0 && iter_start <= 2000 && iter % 25 == 0) {           // :209-213
@@ -2075,13 +2186,64 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
             if (mean_acc < .05) logvar_suf -= (.2 + .05 * rs.norm_rand());
             if (mean_acc > .15) logvar_suf += (.2 + .05 * rs.norm_rand());
         }
-        // ---- (C) beta_0 :219-224 ----
-        op_beta0_sums(c, 0);
-        fetch_scalars(c, 2);
-        {
+        // ---- (C) beta_0 :219-224 (no location-level regressors) ----
+        if (reg_q == 0) {
+            op_beta0_sums(c, 0);
+            fetch_scalars(c, 2);
             const double bvar = (1.0 / c->h_pinned[0]) * std::exp(log_scale);
-            const double bmean = std::exp(-log_scale) * c->h_pinned[1] * bvar;
-            beta_0 = bmean + std::sqrt(bvar) * rs.norm_rand();
+            const double b0mean = std::exp(-log_scale) * c->h_pinned[1] * bvar;
+            beta_0 = b0mean + std::sqrt(bvar) * rs.norm_rand();
+        }
+        // ---- (C') regression coefficients :226-250 ----
+        if (reg) {
+            // :229 beta_mean = crossprod(observed_field - field[locs_match] + beta_0, cbind(1, X$X)) %*% X$solve_1XT1X
+            obs_resid_kernel<<<grid_for(c, n_obs, 256), 256, 0, c->stream>>>(c->d_lm.p, c->d_yobs.p, c->d_field.p, beta_0, n_obs, c->d_robs.p);
+            LAUNCHED(c);
+            op_atb(c, c->d_Xa.p, P1, c->d_robs.p, 1, n_obs, gvec.data());
+            for (int j = 0; j < P1; j++) {
+                double v = 0.0;
+                for (int k = 0; k < P1; k++) v += gvec[k] * reg->solve_1XT1X[(size_t)k + (size_t)P1 * j];
+                bmean[j] = v;
+            }
+            for (int k = 0; k < P1; k++) zz[k] = rs.norm_rand();                 // :231 rnorm(ncol(X$X) + 1)
+            const double sd_noise = std::exp(.5 * lnv);
+            for (int j = 0; j < P1; j++) {                                       // t(chol) %*% z
+                double v = 0.0;
+                for (int k = 0; k <= j; k++) v += reg->chol_1XT1X[(size_t)k + (size_t)P1 * j] * zz[k];
+                innov[j] = bmean[j] + sd_noise * v;
+            }
+            shift_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->d_field.p, n, beta_0, innov[0]);   // :232
+            LAUNCHED(c);
+            beta_0 = innov[0];
+            for (int k = 0; k < reg_p; k++) beta[k] = innov[1 + k];
+            if (reg_q > 0) {                                                     // :237-246 interweaving
+                coefl[0] = 0.0;
+                for (int l = 1; l < reg_q; l++) coefl[l] = beta[c->reg_xlocs[l - 1]];
+                CK(cudaMemcpyAsync(c->d_coef.p, coefl.data(), sizeof(double) * reg_q, cudaMemcpyHostToDevice, c->stream));
+                site_design_axpy_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->d_Xl.p, c->d_coef.p, reg_q, n, 1.0, c->d_field.p, c->d_tmp1.p);   // other_field
+                LAUNCHED(c);
+                op_spmv(c, c->d_linv[c->cur].p, c->d_tmp1.p, 0.0, c->d_tmp2.p);
+                op_atb(c, c->d_B.p, reg_q, c->d_tmp2.p, 1, n, gvec.data());      // crossprod(sparse_chol %*% other_field, sparse_chol_X_locs)
+                for (int j = 0; j < reg_q; j++) {
+                    double v = 0.0;
+                    for (int k = 0; k < reg_q; k++) v += iw_cov[(size_t)j + (size_t)reg_q * k] * gvec[k];
+                    bmean[j] = v;
+                }
+                for (int k = 0; k < reg_q; k++) zz[k] = rs.norm_rand();          // :242 rnorm(length(X$locs) + 1)
+                const double sd_scale = std::exp(.5 * log_scale);
+                for (int j = 0; j < reg_q; j++) {                                // t(beta_interweaved_covmat_chol) %*% z
+                    double v = 0.0;
+                    for (int k = 0; k <= j; k++) v += iw_chol[(size_t)j + (size_t)reg_q * k] * zz[k];
+                    innov[j] = bmean[j] + sd_scale * v;
+                }
+                beta_0 = innov[0];
+                for (int l = 1; l < reg_q; l++) { beta[c->reg_xlocs[l - 1]] = innov[l]; coefl[l] = innov[l]; }
+                CK(cudaMemcpyAsync(c->d_coef.p, coefl.data(), sizeof(double) * reg_q, cudaMemcpyHostToDevice, c->stream));
+                site_design_axpy_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>(c->d_Xl.p, c->d_coef.p, reg_q, n, -1.0, c->d_tmp1.p, c->d_field.p);  // :245
+                LAUNCHED(c);
+                CK(cudaStreamSynchronize(c->stream));                            // coefl is reused by the next iteration
+            }
+            op_set_beta(c, beta.data());                                         // :249 mu
         }
         // ---- (D) chromatic sweeps :257-275 ----
         if (rng_mode == NNGP_RNG_SUPPLIED) {
@@ -2111,6 +2273,8 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
             records_out[(size_t)(iter - 1) + (size_t)n_iter * 2] = lnv;
             for (int k = 0; k < ns; k++) records_out[(size_t)(iter - 1) + (size_t)n_iter * (3 + k)] = shape[k];
         }
+        if (reg && reg->beta_records)
+            for (int k = 0; k < reg_p; k++) reg->beta_records[(size_t)(iter - 1) + (size_t)n_iter * k] = beta[k];
         if (field_records_out) {
             const double t = iter * thin;
             if (std::nearbyint(t) == t) {
@@ -2133,6 +2297,89 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
     CK(cudaStreamSynchronize(c->stream));
     params_io[0] = beta_0; params_io[1] = log_scale; params_io[2] = lnv; params_io[3] = logvar_suf; params_io[4] = logvar_anc;
     for (int k = 0; k < ns; k++) params_io[5 + k] = shape[k];
+    if (reg) std::memcpy(reg->beta_io, beta.data(), sizeof(double) * reg_p);
+}
+
+extern "C" {
+
+void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, const int *n_iter_, const double *thin_,
+                    const int *n_chromatic_, const int *iter_start_, const int *chain_index_, const int *rng_mode_,
+                    const double *var_y_, double *records_out, double *field_records_out, int *accept_out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    NEED(!c->sharded, "nngp_chain_run: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
+    REQUIRE(n_shape_ && params_io && n_iter_ && thin_ && n_chromatic_ && iter_start_ && chain_index_ && rng_mode_ && var_y_, "nngp_chain_run: null argument");
+    NEED(c->have_field && c->have_obs, "nngp_chain_run: field and observations must be set first");
+    chain_run_impl(c, n_shape_, params_io, n_iter_, thin_, n_chromatic_, iter_start_, chain_index_, rng_mode_, var_y_, records_out,
+                   field_records_out, accept_out, nullptr);
+    ABI_END
+}
+
+void nngp_regressors_set(const int *ctx_id, const int *p_, const double *X, const double *observed_field, const int *n_xlocs_,
+                         const int *xlocs, const int *first_obs, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    NEED(!c->sharded, "nngp_regressors_set: not available on a sharded context");
+    REQUIRE(p_ && X && observed_field && n_xlocs_, "nngp_regressors_set: null argument");
+    const int p = *p_, nx = *n_xlocs_, n = c->n, n_obs = c->n_obs;
+    REQUIRE(p >= 1 && nx >= 0 && nx <= p, "nngp_regressors_set: need p >= 1 and 0 <= n_xlocs <= p (got p=%d n_xlocs=%d)", p, nx);
+    REQUIRE(n_obs >= 1, "nngp_regressors_set: the context has no observations");
+    REQUIRE(nx == 0 || (xlocs && first_obs), "nngp_regressors_set: X$locs given without xlocs / first_obs");
+    for (int l = 0; l < nx; l++) REQUIRE(xlocs[l] >= 1 && xlocs[l] <= p, "nngp_regressors_set: xlocs[%d] = %d outside 1..%d", l, xlocs[l], p);
+    if (nx > 0)
+        for (int i = 0; i < n; i++) REQUIRE(first_obs[i] >= 1 && first_obs[i] <= n_obs, "nngp_regressors_set: first_obs[%d] = %d outside 1..%d", i, first_obs[i], n_obs);
+    use(c);
+    c->reg_p = -1;
+    const size_t P1 = (size_t)p + 1;
+    c->d_Xa.alloc(P1 * n_obs);
+    {
+        std::vector<double> ones((size_t)n_obs, 1.0);
+        CK(cudaMemcpyAsync(c->d_Xa.p, ones.data(), sizeof(double) * n_obs, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_Xa.p + n_obs, X, sizeof(double) * (size_t)p * n_obs, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->d_yobs.alloc(n_obs);
+    CK(cudaMemcpyAsync(c->d_yobs.p, observed_field, sizeof(double) * n_obs, cudaMemcpyHostToDevice, c->stream));
+    c->d_robs.alloc(n_obs);
+    c->d_coef.alloc(P1 + 1);
+    c->reg_xlocs.clear();
+    if (nx > 0) {
+        const int q = nx + 1;
+        std::vector<double> Xl((size_t)n * q);
+        for (int s = 0; s < n; s++) {
+            const size_t row = (size_t)first_obs[c->i2g[s]] - 1;
+            Xl[s] = 1.0;
+            for (int l = 1; l < q; l++) Xl[(size_t)l * n + s] = X[row + (size_t)n_obs * (xlocs[l - 1] - 1)];
+        }
+        c->d_Xl.alloc((size_t)n * q);
+        CK(cudaMemcpyAsync(c->d_Xl.p, Xl.data(), sizeof(double) * (size_t)n * q, cudaMemcpyHostToDevice, c->stream));
+        c->d_B.alloc((size_t)n * q);
+        CK(cudaStreamSynchronize(c->stream));
+        for (int l = 0; l < nx; l++) c->reg_xlocs.push_back(xlocs[l] - 1);
+        c->reg_q = q;
+    } else {
+        c->reg_q = 0;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    c->reg_p = p;
+    ABI_END
+}
+
+void nngp_chain_run_regressors(const int *ctx_id, const int *n_shape_, double *params_io, double *beta_io, const double *solve_1XT1X,
+                               const double *chol_solve_1XT1X, const int *n_iter_, const double *thin_, const int *n_chromatic_,
+                               const int *iter_start_, const int *chain_index_, const int *rng_mode_, const double *var_y_,
+                               double *records_out, double *beta_records_out, double *field_records_out, int *accept_out, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    NEED(!c->sharded, "nngp_chain_run_regressors: not available on a sharded context");
+    REQUIRE(n_shape_ && params_io && beta_io && solve_1XT1X && chol_solve_1XT1X && n_iter_ && thin_ && n_chromatic_ && iter_start_ && chain_index_ && rng_mode_ && var_y_,
+            "nngp_chain_run_regressors: null argument");
+    NEED(c->reg_p >= 1, "nngp_chain_run_regressors: nngp_regressors_set must be called first");
+    NEED(c->have_field, "nngp_chain_run_regressors: the field must be set first");
+    RegRun reg{beta_io, solve_1XT1X, chol_solve_1XT1X, beta_records_out};
+    chain_run_impl(c, n_shape_, params_io, n_iter_, thin_, n_chromatic_, iter_start_, chain_index_, rng_mode_, var_y_, records_out,
+                   field_records_out, accept_out, &reg);
+    c->have_obs = true;                                                          // d_ymx / residuals_sum now hold y - X beta of the final state
     ABI_END
 }
 

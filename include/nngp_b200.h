@@ -244,6 +244,26 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape, double *params_io, co
                     const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode,
                     const double *var_y, double *records_out, double *field_records_out, int *accept_out, int *status);
 
+/* Regressors of the Gaussian model, kept resident in HBM for nngp_chain_run_regressors (X$X, X$locs of
+ * Scripts/mcmc_nngp_initialize.R:116-137).  X: n_obs x p column-major, the centred model-matrix columns without the
+ * intercept (X$X); observed_field: n_obs; xlocs: the n_xlocs 1-based columns of X that vary with the site only (X$locs;
+ * n_xlocs = 0 and NULL when X_locs was not given); first_obs: vecchia_approx$hctam_scol_1 (n, 1-based; used only when
+ * n_xlocs > 0: X$X[hctam_scol_1, X$locs], update_Gaussian.R:78). */
+void nngp_regressors_set(const int *ctx_id, const int *p, const double *X, const double *observed_field, const int *n_xlocs,
+                         const int *xlocs, const int *first_obs, int *status);
+/* nngp_chain_run for the model with regressors: additionally the block update of (beta_0, beta) given the field
+ * (update_Gaussian.R:226-235) and, with location-level regressors, the interweaved centred update (:237-246) with
+ * sparse_chol_X_locs / beta_interweaved_covmat refreshed after every accepted covariance proposal (:77-83,145-151,200-206).
+ * X, its products and the field stay on the device; per iteration only (p+1)- and (n_xlocs+1)-vectors cross PCIe.
+ * beta_io: p (state$params$beta); solve_1XT1X, chol_solve_1XT1X: (p+1) x (p+1) column-major as stored in X by
+ * mcmc_nngp_initialize (:135-136; chol() = upper factor); beta_records_out: n_iter x p column-major or NULL.
+ * The R stream is consumed exactly as the reference does: ... rnorm(p+1) (:231), rnorm(n_xlocs+1) (:242) ... */
+void nngp_chain_run_regressors(const int *ctx_id, const int *n_shape, double *params_io, double *beta_io,
+                               const double *solve_1XT1X, const double *chol_solve_1XT1X, const int *n_iter, const double *thin,
+                               const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode,
+                               const double *var_y, double *records_out, double *beta_records_out, double *field_records_out,
+                               int *accept_out, int *status);
+
 /* Posterior summary of the field samples stored by the last nngp_chain_run, computed on the device from the record store
  * that stays in HBM: get_summary (Scripts/mcmc_nngp_estimate.R:1-6) of rows first_row .. first_row +
  * n_rows - 1 (1-based) of records$field minus offsets[k] (beta_0 of the same iteration, estimate.R:90-92; NULL = none).

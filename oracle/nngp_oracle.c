@@ -505,12 +505,95 @@ static double sample_var(const double *x, int n)
     return s / (n - 1);
 }
 
+/* ---- small dense helpers for the regression block (R: solve(), chol(); column-major q x q) ---- */
+static int dense_chol_lower(double *A, int q)
+{
+    for (int j = 0; j < q; j++) {
+        double dj = A[j + (size_t)q * j];
+        for (int k = 0; k < j; k++) dj -= A[j + (size_t)q * k] * A[j + (size_t)q * k];
+        if (!(dj > 0.0)) return 1;
+        dj = sqrt(dj);
+        A[j + (size_t)q * j] = dj;
+        for (int i = j + 1; i < q; i++) {
+            double v = A[i + (size_t)q * j];
+            for (int k = 0; k < j; k++) v -= A[i + (size_t)q * k] * A[j + (size_t)q * k];
+            A[i + (size_t)q * j] = v / dj;
+        }
+        for (int i = 0; i < j; i++) A[i + (size_t)q * j] = 0.0;
+    }
+    return 0;
+}
+
+/* inv = P^-1 for symmetric positive definite P, by Gauss-Jordan elimination with partial pivoting (what solve() does
+ * up to the order of operations) */
+static int dense_inverse(const double *P, int q, double *inv)
+{
+    double *A = (double *)malloc(sizeof(double) * (size_t)q * q);
+    memcpy(A, P, sizeof(double) * (size_t)q * q);
+    for (int i = 0; i < q; i++) for (int j = 0; j < q; j++) inv[i + (size_t)q * j] = (i == j) ? 1.0 : 0.0;
+    for (int c = 0; c < q; c++) {
+        int piv = c;
+        for (int r = c + 1; r < q; r++) if (fabs(A[r + (size_t)q * c]) > fabs(A[piv + (size_t)q * c])) piv = r;
+        if (A[piv + (size_t)q * c] == 0.0) { free(A); return 1; }
+        if (piv != c)
+            for (int j = 0; j < q; j++) {
+                double t = A[c + (size_t)q * j]; A[c + (size_t)q * j] = A[piv + (size_t)q * j]; A[piv + (size_t)q * j] = t;
+                t = inv[c + (size_t)q * j]; inv[c + (size_t)q * j] = inv[piv + (size_t)q * j]; inv[piv + (size_t)q * j] = t;
+            }
+        double dinv = 1.0 / A[c + (size_t)q * c];
+        for (int j = 0; j < q; j++) { A[c + (size_t)q * j] *= dinv; inv[c + (size_t)q * j] *= dinv; }
+        for (int r = 0; r < q; r++) {
+            if (r == c) continue;
+            double f = A[r + (size_t)q * c];
+            if (f == 0.0) continue;
+            for (int j = 0; j < q; j++) { A[r + (size_t)q * j] -= f * A[c + (size_t)q * j]; inv[r + (size_t)q * j] -= f * inv[c + (size_t)q * j]; }
+        }
+    }
+    free(A);
+    return 0;
+}
+
+/* update_Gaussian.R:77-83: sparse_chol_X_locs = sparse_chol %*% cbind(1, X$X[hctam_scol_1, X$locs]) (n x q),
+ * beta_interweaved_covmat = solve(crossprod(.)), chol_lower = t(chol(covmat)) */
+static int interweave_matrices(const double *Linv, const int *NNarray, int n, int m, const double *Xl, int q,
+                               double *scXl, double *cov, double *chol_lower)
+{
+    for (int l = 0; l < q; l++) oracle_linv_mult(Linv, Xl + (size_t)l * n, NNarray, n, m, scXl + (size_t)l * n);
+    double *prec = (double *)malloc(sizeof(double) * (size_t)q * q);
+    for (int a = 0; a < q; a++)
+        for (int b = 0; b < q; b++) {
+            double v = 0.0;
+            for (int s = 0; s < n; s++) v += scXl[(size_t)a * n + s] * scXl[(size_t)b * n + s];
+            prec[a + (size_t)q * b] = v;
+        }
+    int bad = dense_inverse(prec, q, cov);
+    free(prec);
+    if (bad) return 1;
+    for (int a = 0; a < q; a++)                               /* symmetrise the rounding of the elimination */
+        for (int b = 0; b < a; b++) { double v = 0.5 * (cov[a + (size_t)q * b] + cov[b + (size_t)q * a]); cov[a + (size_t)q * b] = v; cov[b + (size_t)q * a] = v; }
+    memcpy(chol_lower, cov, sizeof(double) * (size_t)q * q);
+    return dense_chol_lower(chol_lower, q);
+}
+
 int oracle_update_gaussian_chain(const double *locs, int n, int d, const int *NNarray, int m, const int *coloring,
                                  int n_colors, const int *locs_match, int n_obs, const double *obs_per_loc,
                                  const double *observed_field, int covfun, oracle_chain_params *p, double *field,
                                  int n_iterations_update, double field_thinning, int n_chromatic, int iter_start,
                                  int chain_index, int sweep_form, double *records, double *field_records,
                                  int *accept_records)
+{
+    return oracle_update_gaussian_chain_x(locs, n, d, NNarray, m, coloring, n_colors, locs_match, n_obs, obs_per_loc,
+                                          observed_field, covfun, p, field, n_iterations_update, field_thinning, n_chromatic,
+                                          iter_start, chain_index, sweep_form, records, field_records, accept_records, NULL);
+}
+
+/* the same loop with the regression block update_Gaussian.R:226-250 when reg != NULL */
+int oracle_update_gaussian_chain_x(const double *locs, int n, int d, const int *NNarray, int m, const int *coloring,
+                                   int n_colors, const int *locs_match, int n_obs, const double *obs_per_loc,
+                                   const double *observed_field, int covfun, oracle_chain_params *p, double *field,
+                                   int n_iterations_update, double field_thinning, int n_chromatic, int iter_start,
+                                   int chain_index, int sweep_form, double *records, double *field_records,
+                                   int *accept_records, const oracle_regressors *reg)
 {
     const int M = m + 1, n_iter = n_iterations_update, ns = p->n_shape;
     size_t lsz = (size_t)n * M;
@@ -534,9 +617,36 @@ int oracle_update_gaussian_chain(const double *locs, int n, int d, const int *NN
     oracle_vecchia_linv(cp, ncp, covfun, locs, n, d, NNarray, m, Linv);                          /* :72 */
     oracle_precision_diag(Linv, NNarray, n, m, precision_diag);                                  /* :74 */
     for (int i = 0; i < n; i++) (void)r_norm_rand();                                             /* :75 current_p (dead, but consumes the stream) */
-    for (int o = 0; o < n_obs; o++) mu[o] = p->beta_0;                                           /* :86 */
+    /* regression state: X$X (n_obs x P), site-level design Xl = cbind(1, X$X[hctam_scol_1, X$locs]) (n x q) */
+    const int P = reg ? reg->p : 0, P1 = P + 1, q = (reg && reg->n_xlocs > 0) ? reg->n_xlocs + 1 : 0;
+    const int wlen = P1 > q ? P1 : q;
+    double *Xl = NULL, *scXl = NULL, *iw_cov = NULL, *iw_chol = NULL, *other = NULL;
+    double *gvec = (double *)malloc(sizeof(double) * (size_t)wlen), *bmean = (double *)malloc(sizeof(double) * (size_t)wlen),
+           *zz = (double *)malloc(sizeof(double) * (size_t)wlen), *innov = (double *)malloc(sizeof(double) * (size_t)wlen);
+    int status = 0;
+    if (q > 0) {
+        Xl = (double *)malloc(sizeof(double) * (size_t)n * q);
+        scXl = (double *)malloc(sizeof(double) * (size_t)n * q);
+        iw_cov = (double *)malloc(sizeof(double) * (size_t)q * q);
+        iw_chol = (double *)malloc(sizeof(double) * (size_t)q * q);
+        other = (double *)malloc(sizeof(double) * (size_t)n);
+        for (int s = 0; s < n; s++) {
+            Xl[s] = 1.0;
+            for (int l = 1; l < q; l++)
+                Xl[(size_t)l * n + s] = reg->X[(size_t)(reg->first_obs[s] - 1) + (size_t)n_obs * (reg->xlocs[l - 1] - 1)];
+        }
+        status = interweave_matrices(Linv, NNarray, n, m, Xl, q, scXl, iw_cov, iw_chol);         /* :77-83 */
+    }
+#define ORACLE_SET_MU()                                                                            \
+    for (int o = 0; o < n_obs; o++) {                                                              \
+        double xb = 0.0;                                                                           \
+        for (int k = 0; k < P; k++) xb += reg->X[(size_t)o + (size_t)n_obs * k] * reg->beta[k];    \
+        mu[o] = p->beta_0 + xb;                                                                    \
+    }
+    if (reg) { ORACLE_SET_MU() }                                                                 /* :85 */
+    else for (int o = 0; o < n_obs; o++) mu[o] = p->beta_0;                                      /* :86 */
 
-    for (int iter = 1; iter <= n_iter; iter++) {
+    for (int iter = 1; iter <= n_iter && status == 0; iter++) {
         /* ---- ancillary step :113-157 ---- */
         double sd_anc = exp(.5 * p->logvar_ancillary);
         for (int k = 0; k < ns + 1; k++) innovation[k] = 0.0 + sd_anc * r_norm_rand();
@@ -564,6 +674,7 @@ int oracle_update_gaussian_chain(const double *locs, int n, int d, const int *NN
             memcpy(Linv, new_Linv, sizeof(double) * lsz);
             oracle_precision_diag(Linv, NNarray, n, m, precision_diag);
             acc_anc[iter] = 1;
+            if (q > 0) status |= interweave_matrices(Linv, NNarray, n, m, Xl, q, scXl, iw_cov, iw_chol);   /* :145-151 */
         }
         if (iter_start >= 0 && iter_start <= 2000 && iter % 25 == 0) {                           /* :153-157 */
             int a = 0;
@@ -589,6 +700,7 @@ int oracle_update_gaussian_chain(const double *locs, int n, int d, const int *NN
                 memcpy(Linv, new_Linv, sizeof(double) * lsz);
                 oracle_precision_diag(Linv, NNarray, n, m, precision_diag);
                 acc_suf[iter] = 1;
+                if (q > 0) status |= interweave_matrices(Linv, NNarray, n, m, Xl, q, scXl, iw_cov, iw_chol);   /* :200-206 */
             }
         }
         if (iter_start >= 0 && iter_start <= 2000 && iter % 25 == 0) {                           /* :209-213 */
@@ -598,13 +710,71 @@ int oracle_update_gaussian_chain(const double *locs, int n, int d, const int *NN
             if (mean_acc < .05) p->logvar_sufficient -= (.2 + .05 * r_norm_rand());
             if (mean_acc > .15) p->logvar_sufficient += (.2 + .05 * r_norm_rand());
         }
-        /* ---- beta_0 :219-224 ---- */
-        {
-            double bmean, bvar;
-            oracle_beta0_moments(Linv, NNarray, n, m, field, p->log_scale, &bmean, &bvar);
-            p->beta_0 = bmean + sqrt(bvar) * r_norm_rand();
+        /* ---- beta_0 :219-224: if(length(X$locs) == 0 | is.null(X$X)) ---- */
+        if (q == 0) {
+            double b0mean, bvar;
+            oracle_beta0_moments(Linv, NNarray, n, m, field, p->log_scale, &b0mean, &bvar);
+            p->beta_0 = b0mean + sqrt(bvar) * r_norm_rand();
         }
-        for (int o = 0; o < n_obs; o++) mu[o] = p->beta_0;                                        /* :250 */
+        /* ---- regression coefficients :226-247 ---- */
+        if (reg) {
+            for (int k = 0; k < P1; k++) gvec[k] = 0.0;                                          /* :229 crossprod(resid, cbind(1, X$X)) */
+            for (int o = 0; o < n_obs; o++) {
+                double e = observed_field[o] - field[locs_match[o] - 1] + p->beta_0;
+                gvec[0] += e;
+                for (int k = 0; k < P; k++) gvec[1 + k] += e * reg->X[(size_t)o + (size_t)n_obs * k];
+            }
+            for (int j = 0; j < P1; j++) {                                                       /* ... %*% X$solve_1XT1X */
+                double v = 0.0;
+                for (int k = 0; k < P1; k++) v += gvec[k] * reg->solve_1XT1X[k + (size_t)P1 * j];
+                bmean[j] = v;
+            }
+            for (int k = 0; k < P1; k++) zz[k] = r_norm_rand();                                  /* :231 */
+            double sd_noise = exp(.5 * p->log_noise_variance);
+            for (int j = 0; j < P1; j++) {                                                       /* t(X$chol_solve_1XT1X) %*% z */
+                double v = 0.0;
+                for (int k = 0; k < P1; k++) v += reg->chol_solve_1XT1X[k + (size_t)P1 * j] * zz[k];
+                innov[j] = bmean[j] + sd_noise * v;
+            }
+            for (int s = 0; s < n; s++) field[s] = field[s] - p->beta_0 + innov[0];              /* :232 */
+            p->beta_0 = innov[0];                                                                /* :233 */
+            for (int k = 0; k < P; k++) reg->beta[k] = innov[1 + k];                             /* :234 */
+            if (q > 0) {                                                                         /* :237-246 interweaving */
+                for (int s = 0; s < n; s++) {                                                    /* :240 other_field */
+                    double xb = 0.0;
+                    for (int l = 1; l < q; l++) xb += Xl[(size_t)l * n + s] * reg->beta[reg->xlocs[l - 1] - 1];
+                    other[s] = field[s] + xb;
+                }
+                oracle_linv_mult(Linv, other, NNarray, n, m, tmp);                               /* sparse_chol %*% other_field */
+                for (int j = 0; j < q; j++) {
+                    double v = 0.0;
+                    for (int s = 0; s < n; s++) v += tmp[s] * scXl[(size_t)j * n + s];
+                    gvec[j] = v;
+                }
+                for (int j = 0; j < q; j++) {                                                    /* :241 */
+                    double v = 0.0;
+                    for (int k = 0; k < q; k++) v += iw_cov[j + (size_t)q * k] * gvec[k];
+                    bmean[j] = v;
+                }
+                for (int k = 0; k < q; k++) zz[k] = r_norm_rand();                               /* :242 */
+                double sd_scale = exp(.5 * p->log_scale);
+                for (int j = 0; j < q; j++) {
+                    double v = 0.0;
+                    for (int k = 0; k < q; k++) v += iw_chol[j + (size_t)q * k] * zz[k];
+                    innov[j] = bmean[j] + sd_scale * v;
+                }
+                p->beta_0 = innov[0];                                                            /* :243 */
+                for (int l = 1; l < q; l++) reg->beta[reg->xlocs[l - 1] - 1] = innov[l];         /* :244 */
+                for (int s = 0; s < n; s++) {                                                    /* :245 */
+                    double xb = 0.0;
+                    for (int l = 1; l < q; l++) xb += Xl[(size_t)l * n + s] * reg->beta[reg->xlocs[l - 1] - 1];
+                    field[s] = other[s] - xb;
+                }
+            }
+            ORACLE_SET_MU()                                                                      /* :249 */
+        } else {
+            for (int o = 0; o < n_obs; o++) mu[o] = p->beta_0;                                    /* :250 */
+        }
         /* ---- chromatic sweeps :257-275 ---- */
         for (int ic = 0; ic < n_chromatic; ic++) {
             oracle_residuals_sum(locs_match, n_obs, n, observed_field, mu, residuals_sum);       /* :260 */
@@ -636,6 +806,8 @@ int oracle_update_gaussian_chain(const double *locs, int n, int d, const int *NN
             records[(size_t)(iter - 1) + (size_t)n_iter * 2] = p->log_noise_variance;
             for (int k = 0; k < ns; k++) records[(size_t)(iter - 1) + (size_t)n_iter * (3 + k)] = p->shape[k];
         }
+        if (reg && reg->beta_records)                                                            /* :305 */
+            for (int k = 0; k < P; k++) reg->beta_records[(size_t)(iter - 1) + (size_t)n_iter * k] = reg->beta[k];
         if (field_records) {
             double t = iter * field_thinning;
             if (nearbyint(t) == t) {
@@ -648,6 +820,8 @@ int oracle_update_gaussian_chain(const double *locs, int n, int d, const int *NN
     }
     free(Linv); free(new_Linv); free(precision_diag); free(tmp); free(tmp2); free(new_field); free(mu);
     free(residuals_sum); free(z); free(acc_suf); free(acc_anc); free(order); free(cptr);
+    free(Xl); free(scXl); free(iw_cov); free(iw_chol); free(other); free(gvec); free(bmean); free(zz); free(innov);
     csc_free(&csc);
-    return 0;
+#undef ORACLE_SET_MU
+    return status;
 }

@@ -123,6 +123,27 @@ int oracle_update_gaussian_chain(const double *locs, int n, int d, const int *NN
                                  int chain_index, int sweep_form, double *records, double *field_records,
                                  int *accept_records);
 
+/* ---- the same chain with regressors (update_Gaussian.R:226-250; X as prepared by mcmc_nngp_initialize.R:116-137) ---- */
+typedef struct {
+    int p;                          /* ncol(X$X) */
+    const double *X;                /* X$X: n_obs x p column-major, centred, no intercept column */
+    int n_xlocs;                    /* length(X$locs); 0 = no location-level regressors */
+    const int *xlocs;               /* X$locs, 1-based columns of X$X */
+    const int *first_obs;           /* vecchia_approx$hctam_scol_1: n, 1-based (used when n_xlocs > 0) */
+    const double *solve_1XT1X;      /* (p+1) x (p+1), initialize.R:135 */
+    const double *chol_solve_1XT1X; /* (p+1) x (p+1) upper factor, initialize.R:136 */
+    double *beta;                   /* p: state$params$beta, in/out */
+    double *beta_records;           /* n_iter x p column-major, or NULL */
+} oracle_regressors;
+
+/* reg == NULL: identical to oracle_update_gaussian_chain. Returns non-zero if an interweaving matrix is singular. */
+int oracle_update_gaussian_chain_x(const double *locs, int n, int d, const int *NNarray, int m, const int *coloring,
+                                   int n_colors, const int *locs_match, int n_obs, const double *obs_per_loc,
+                                   const double *observed_field, int covfun, oracle_chain_params *p, double *field,
+                                   int n_iterations_update, double field_thinning, int n_chromatic, int iter_start,
+                                   int chain_index, int sweep_form, double *records, double *field_records,
+                                   int *accept_records, const oracle_regressors *reg);
+
 #ifdef __cplusplus
 }
 #endif

@@ -238,10 +238,20 @@ class ChainParams(C.Structure):
                 ("log_noise_variance", C.c_double), ("logvar_sufficient", C.c_double), ("logvar_ancillary", C.c_double)]
 
 
+class Regressors(C.Structure):
+    _fields_ = [("p", C.c_int), ("X", C.POINTER(C.c_double)), ("n_xlocs", C.c_int), ("xlocs", C.POINTER(C.c_int)),
+                ("first_obs", C.POINTER(C.c_int)), ("solve_1XT1X", C.POINTER(C.c_double)),
+                ("chol_solve_1XT1X", C.POINTER(C.c_double)), ("beta", C.POINTER(C.c_double)),
+                ("beta_records", C.POINTER(C.c_double))]
+
+
 def update_gaussian_chain(locs, NNarray, coloring, locs_match, obs_per_loc, observed_field, covfun_name, params: dict,
                           field, n_iterations_update, field_thinning=1.0, n_chromatic=10, iter_start=0, chain_index=1,
-                          sweep_form=0):
-    """One chain of mcmc_nngp_update_Gaussian (no regressors). Returns (params, field, records, field_records, accept)."""
+                          sweep_form=0, regressors: dict | None = None):
+    """One chain of mcmc_nngp_update_Gaussian. Returns (params, field, records, field_records, accept).
+    regressors = dict(X, xlocs (1-based), first_obs (1-based), solve_1XT1X, chol_solve_1XT1X, beta): the model with
+    regression coefficients (update_Gaussian.R:226-250); params then also carries "beta" and the tuple gets a sixth
+    element, the beta records."""
     locs = np.asarray(locs, dtype=np.float64)
     n, d = locs.shape
     M = NNarray.shape[1]
@@ -263,14 +273,37 @@ def update_gaussian_chain(locs, NNarray, coloring, locs_match, obs_per_loc, obse
     n_frec = int(round(n_iter * field_thinning))
     frec = np.zeros(max(n_frec, 1) * n)
     acc = np.zeros(2 * n_iter, dtype=np.int32)
-    rc = lib().oracle_update_gaussian_chain(
+    reg_ref, keep = None, []
+    if regressors is not None:
+        X = np.asfortranarray(regressors["X"], dtype=np.float64)
+        P = X.shape[1]
+        xl = _i32(np.atleast_1d(np.asarray(regressors.get("xlocs", []), dtype=np.int32)))
+        fo = _i32(regressors["first_obs"]) if xl.size else np.zeros(1, dtype=np.int32)
+        S = np.asfortranarray(regressors["solve_1XT1X"], dtype=np.float64)
+        Ch = np.asfortranarray(regressors["chol_solve_1XT1X"], dtype=np.float64)
+        beta = np.array(regressors["beta"], dtype=np.float64).ravel().copy()
+        brec = np.zeros(max(n_iter * P, 1))
+        assert X.shape[0] == lm.size and S.shape == (P + 1, P + 1) and Ch.shape == (P + 1, P + 1) and beta.size == P
+        pd_ = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        r = Regressors(P, pd_(X), int(xl.size), xl.ctypes.data_as(C.POINTER(C.c_int)), fo.ctypes.data_as(C.POINTER(C.c_int)),
+                       pd_(S), pd_(Ch), pd_(beta), pd_(brec))
+        keep = [X, xl, fo, S, Ch, beta, brec]
+        reg_ref = C.byref(r)
+    fn = lib().oracle_update_gaussian_chain_x
+    fn.restype = C.c_int
+    rc = fn(
         _d(_f64(locs)), C.c_int(n), C.c_int(d), _i(_i32(NNarray)), C.c_int(M - 1), _i(coloring),
         C.c_int(int(coloring.max())), _i(lm), C.c_int(lm.size), _d(_f64(obs_per_loc)), _d(_f64(observed_field)),
         C.c_int(COVFUN_IDS[covfun_name]), C.byref(p), _d(f), C.c_int(n_iter), C.c_double(field_thinning),
-        C.c_int(n_chromatic), C.c_int(iter_start), C.c_int(chain_index), C.c_int(sweep_form), _d(rec), _d(frec), _i(acc))
+        C.c_int(n_chromatic), C.c_int(iter_start), C.c_int(chain_index), C.c_int(sweep_form), _d(rec), _d(frec), _i(acc),
+        reg_ref)
     assert rc == 0
     out = dict(shape=np.array([p.shape[k] for k in range(shape.size)]), beta_0=p.beta_0, log_scale=p.log_scale,
                log_noise_variance=p.log_noise_variance, logvar_sufficient=p.logvar_sufficient,
                logvar_ancillary=p.logvar_ancillary)
-    return (out, f, rec.reshape((n_iter, 3 + shape.size), order="F"),
-            frec[: n_frec * n].reshape((n_frec, n), order="F"), acc.reshape((n_iter, 2), order="F"))
+    res = (out, f, rec.reshape((n_iter, 3 + shape.size), order="F"),
+           frec[: n_frec * n].reshape((n_frec, n), order="F"), acc.reshape((n_iter, 2), order="F"))
+    if regressors is not None:
+        out["beta"] = keep[5]
+        res = res + (keep[6][: n_iter * keep[5].size].reshape((n_iter, keep[5].size), order="F"),)
+    return res

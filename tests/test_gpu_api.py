@@ -49,6 +49,28 @@ def test_config1a_vignette_toy_posterior_bands(golden):
     nb.release_contexts(lst)
 
 
+def test_regressor_engines_agree_in_distribution():
+    """The device engine (nngp_chain_run_regressors) and the host-driven loop over the device primitives sample the same
+    posterior: slopes of two strong regressors agree within Monte-Carlo error on a small model."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from problems import make_regression_problem
+    P = make_regression_problem(1500, 5, seed=5, n_extra_obs=0, p_locs=1, p_obs=1)
+    means = {}
+    for engine in ("device", "host"):
+        lst = nb.mcmc_nngp_initialize(P["locs"], P["y"], X_locs=P["X"][:, :1], X_obs=P["X"][:, 1:], m=5, reordering="none", n_chains=1, seed=1)
+        for _ in range(3):
+            res = nb.mcmc_nngp_update_Gaussian(lst["locs"], lst["X"], lst["observed_field"], lst["space_time_model"], lst["vecchia_approx"],
+                                               lst["states"], 150, field_thinning=0.0, n_chromatic=5,
+                                               iterations=lst["records"]["chain_1"]["iterations"], regressor_engine=engine)
+            lst["states"]["chain_1"] = res[0]["state"]
+        means[engine] = res[0]["records"]["beta"].mean(axis=0)
+        assert np.all(np.isfinite(res[0]["records"]["beta"]))
+        nb.release_contexts(lst)
+    assert np.max(np.abs(means["device"] - means["host"])) < 0.15, means
+    assert abs(means["device"][1] - P["beta_true"][1]) < 0.1      # the observation-level regressor is sharply identified
+
+
 def test_config1b_no_regressor_chain_and_prediction():
     """config 1b: 2-D, n = 5000, m = 10, one chain through nngp_chain_run; then mcmc_nngp_predict_field."""
     rng = np.random.default_rng(3)

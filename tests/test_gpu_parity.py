@@ -240,6 +240,66 @@ def test_chain_run_matches_oracle_chain_with_r_stream(covfun, shape):
     assert abs(pg["logvar_ancillary"] - po["logvar_ancillary"]) < 1e-12
 
 
+@pytest.mark.parametrize("p_locs,p_obs,extra,covfun,shape", [(2, 1, 300, "exponential_isotropic", [np.log(0.1)]),
+                                                             (0, 3, 0, "exponential_isotropic", [np.log(0.1)]),
+                                                             (3, 0, 100, "matern_isotropic", [np.log(0.1), 0.3]),
+                                                             (20, 4, 50, "exponential_isotropic", [np.log(0.1)])])
+def test_chain_run_regressors_matches_oracle_chain_with_r_stream(p_locs, p_obs, extra, covfun, shape):
+    """nngp_chain_run_regressors (update_Gaussian.R:101-314 with the regression block :226-250 on the device: X resident in
+    HBM, crossprod()s as streaming A^T B kernels, interweaving matrices refreshed on every accept) against the oracle chain
+    (itself checked against the dense transcription of the R loop, tests/test_oracle_golden.py), both driven by R's stream."""
+    from problems import make_regression_problem
+    n, m, n_iter = 1500, 5, 50
+    P = make_regression_problem(n, m, seed=23, n_extra_obs=extra, p_locs=p_locs, p_obs=p_obs)
+    p0 = dict(shape=shape, beta_0=0.5, log_scale=-0.2, log_noise_variance=np.log(0.15), logvar_sufficient=-2.0, logvar_ancillary=-2.0)
+    beta0 = 0.1 * np.ones(P["X"].shape[1])
+    field0 = 0.5 + P["w"]
+    reg = dict(X=P["X"], xlocs=P["xlocs"], first_obs=P["first_obs"], solve_1XT1X=P["solve_1XT1X"],
+               chol_solve_1XT1X=P["chol_solve_1XT1X"], beta=beta0)
+    po, fo, reco, freco, acco, breco = O.update_gaussian_chain(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], P["obs_per_loc"],
+                                                               P["y"], covfun, p0, field0, n_iter, 0.5, 2, 0, 3, 1, regressors=reg)
+    var_y = float(np.var(P["y"], ddof=1))
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], covfun) as ctx:
+        ctx.regressors_set(P["X"], P["y"], xlocs=P["xlocs"], first_obs=P["first_obs"])
+        ctx.field_set(field0)
+        pg, recg, brecg, frecg, accg = ctx.chain_run_regressors(p0, beta0, P["solve_1XT1X"], P["chol_solve_1XT1X"], n_iter, var_y, thin=0.5,
+                                                                n_chromatic=2, iter_start=0, chain_index=3, rng_mode=nb.RNG_SUPPLIED)
+        fg = ctx.field_get()
+        ssr_g = ctx.ssr()                                      # the context's y - X beta corresponds to the final beta
+    assert np.array_equal(accg, acco)
+    assert accg.sum() > 0
+    assert np.max(np.abs(recg - reco)) < 1e-8
+    assert np.max(np.abs(brecg - breco)) < 1e-8
+    assert np.max(np.abs(fg - fo)) < 1e-7
+    assert np.max(np.abs(frecg - freco)) < 1e-7
+    assert np.max(np.abs(pg["beta"] - po["beta"])) < 1e-8
+    assert abs(pg["logvar_sufficient"] - po["logvar_sufficient"]) < 1e-12
+    lm = P["locs_match"] - 1
+    ssr_o = float(np.sum((P["y"] - P["X"] @ po["beta"] - fo[lm]) ** 2))
+    assert abs(ssr_g - ssr_o) < 1e-7 * ssr_o
+
+
+def test_regressor_error_paths():
+    from problems import make_regression_problem
+    P = make_regression_problem(300, 5, seed=2, p_locs=1, p_obs=1)
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.field_set(P["field"])
+        with pytest.raises(nb.NNGPError) as e:                  # no regressors on the device yet
+            ctx._reg_p = 2
+            ctx.chain_run_regressors(dict(shape=[0.0], beta_0=0.0, log_scale=0.0, log_noise_variance=0.0), np.zeros(2), P["solve_1XT1X"],
+                                     P["chol_solve_1XT1X"], 1, 1.0)
+        assert e.value.status == 4
+        with pytest.raises(nb.NNGPError) as e:                  # X$locs names a column that does not exist
+            ctx.regressors_set(P["X"], P["y"], xlocs=[3], first_obs=P["first_obs"])
+        assert e.value.status == 1
+        # collinear location-level regressors: the interweaving precision is singular -> an error, not garbage
+        Xc = np.column_stack([P["X"][:, 0], P["X"][:, 0]])
+        ctx.regressors_set(Xc, P["y"], xlocs=[1, 2], first_obs=P["first_obs"])
+        with pytest.raises(nb.NNGPError):
+            ctx.chain_run_regressors(dict(shape=[np.log(0.1)], beta_0=0.0, log_scale=0.0, log_noise_variance=0.0), np.zeros(2), np.eye(3),
+                                     np.eye(3), 1, 1.0)
+
+
 def test_error_paths():
     P = make_problem(200, 5, seed=1)
     with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:

@@ -269,3 +269,54 @@ def test_chain_forms_agree_and_are_sane():
     assert np.allclose(a[1], b[1], rtol=1e-7, atol=1e-7)          # final field
     assert a[3].shape == (15, n)
     assert np.all(np.isfinite(a[2]))
+
+
+@pytest.mark.parametrize("p_locs,p_obs,extra", [(2, 1, 25), (0, 2, 0), (3, 0, 10)])
+def test_chain_with_regressors_matches_dense_transcription(p_locs, p_obs, extra):
+    """The C oracle's chain with the regression block (update_Gaussian.R:226-250: block update of (beta_0, beta), interweaved
+    centred update for location-level regressors, interweaving matrices refreshed on every accept) against the line-by-line
+    dense numpy transcription of the R loop driven by the same R random stream: same accept/reject decisions, same records."""
+    import dense_transcription as T
+    from problems import make_regression_problem
+    n, m, n_iter = 90, 4, 30
+    P = make_regression_problem(n, m, seed=17, n_extra_obs=extra, p_locs=p_locs, p_obs=p_obs)
+    p0 = dict(shape=[np.log(0.12)], beta_0=0.5, log_scale=-0.2, log_noise_variance=np.log(0.15), logvar_sufficient=-1.0,
+              logvar_ancillary=-1.0)
+    beta0 = 0.1 * np.ones(P["X"].shape[1])
+    field0 = 0.5 + P["w"]
+    reg = dict(X=P["X"], xlocs=P["xlocs"], first_obs=P["first_obs"], solve_1XT1X=P["solve_1XT1X"],
+               chol_solve_1XT1X=P["chol_solve_1XT1X"], beta=beta0)
+    for form in (0, 1):
+        po, fo, reco, freco, acco, breco = O.update_gaussian_chain(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], P["obs_per_loc"],
+                                                                   P["y"], "exponential_isotropic", p0, field0, n_iter, 0.5, 2, 0, 2, form,
+                                                                   regressors=reg)
+        st, rec, rec_beta, rec_field, acc = T.update_gaussian_chain(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], P["y"],
+                                                                    "exponential_isotropic", p0, field0, n_iter, 0.5, 2, 0, 2, X=P["X"],
+                                                                    X_locs_cols=list(P["xlocs"]), beta=beta0, solve_1XT1X=P["solve_1XT1X"],
+                                                                    chol_solve_1XT1X=P["chol_solve_1XT1X"])
+        assert np.array_equal(acc, acco)
+        assert acc.sum() > 0                                      # some proposals were accepted: the refresh paths ran
+        assert np.max(np.abs(rec - reco)) < 1e-8
+        assert np.max(np.abs(rec_beta - breco)) < 1e-8
+        assert np.max(np.abs(st["field"] - fo)) < 1e-7
+        assert np.max(np.abs(rec_field - freco)) < 1e-7
+        assert abs(st["logvar_ancillary"] - po["logvar_ancillary"]) < 1e-12
+        assert np.max(np.abs(st["beta"] - po["beta"])) < 1e-8
+
+
+def test_chain_without_regressors_matches_dense_transcription():
+    """Same check for the no-regressor loop (the path nngp_chain_run implements)."""
+    import dense_transcription as T
+    from problems import make_regression_problem
+    n, m, n_iter = 90, 4, 50
+    P = make_regression_problem(n, m, seed=3, n_extra_obs=15, p_locs=1, p_obs=0)
+    p0 = dict(shape=[np.log(0.12)], beta_0=0.5, log_scale=-0.2, log_noise_variance=np.log(0.15), logvar_sufficient=-1.0,
+              logvar_ancillary=-1.0)
+    field0 = 0.5 + P["w"]
+    po, fo, reco, freco, acco = O.update_gaussian_chain(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], P["obs_per_loc"], P["y"],
+                                                        "exponential_isotropic", p0, field0, n_iter, 1.0, 2, 0, 1, 0)
+    st, rec, _, rec_field, acc = T.update_gaussian_chain(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], P["y"],
+                                                         "exponential_isotropic", p0, field0, n_iter, 1.0, 2, 0, 1)
+    assert np.array_equal(acc, acco)
+    assert np.max(np.abs(rec - reco)) < 1e-8
+    assert np.max(np.abs(rec_field - freco)) < 1e-7
