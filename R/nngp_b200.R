@@ -85,3 +85,28 @@ nngp_chain_run = function(ctx, params, transition_kernels, n_iter, field_thinnin
                 records_out = double(n_iter * (3 + k)), field_records_out = double(max(n_frec, 1) * n_locs), accept_out = integer(2 * n_iter),
                 status = integer(1)))
 }
+
+# regressors of the Gaussian model (X as prepared by mcmc_nngp_initialize.R:116-137) uploaded once per context
+nngp_regressors_set = function(ctx, X, observed_field, vecchia_approx)
+{
+  xl = as.integer(X$locs)
+  invisible(nngp_check(.C("nngp_regressors_set", ctx_id = as.integer(ctx), p = as.integer(ncol(X$X)), X = as.double(X$X),
+                          observed_field = as.double(observed_field), n_xlocs = length(xl), xlocs = if(length(xl)) xl else integer(1),
+                          first_obs = as.integer(vecchia_approx$hctam_scol_1), status = integer(1))))
+}
+
+# the whole per-chain loop with the regression block (update_Gaussian.R:226-250) behind one call
+nngp_chain_run_regressors = function(ctx, params, transition_kernels, X, n_iter, field_thinning, n_chromatic, iter_start, chain_index, var_y,
+                                     n_locs, rng_mode = 1L)
+{
+  k = length(params$shape)
+  p = c(params$beta_0, params$log_scale, params$log_noise_variance, transition_kernels$covariance_params_sufficient$logvar,
+        transition_kernels$covariance_params_ancillary$logvar, params$shape)
+  n_frec = round(n_iter * field_thinning)
+  nngp_check(.C("nngp_chain_run_regressors", ctx_id = as.integer(ctx), n_shape = as.integer(k), params_io = as.double(p),
+                beta_io = as.double(params$beta), solve_1XT1X = as.double(X$solve_1XT1X), chol_solve_1XT1X = as.double(X$chol_solve_1XT1X),
+                n_iter = as.integer(n_iter), thin = as.double(field_thinning), n_chromatic = as.integer(n_chromatic),
+                iter_start = as.integer(iter_start), chain_index = as.integer(chain_index), rng_mode = as.integer(rng_mode),
+                var_y = as.double(var_y), records_out = double(n_iter * (3 + k)), beta_records_out = double(n_iter * ncol(X$X)),
+                field_records_out = double(max(n_frec, 1) * n_locs), accept_out = integer(2 * n_iter), status = integer(1)))
+}

@@ -279,7 +279,7 @@ def run_ours(a):
         new_locs = np.random.default_rng(99).random((n, 2))
         joint = np.vstack([locs, new_locs])
         nn_j = nb.find_ordered_nn(joint, m)
-        with nb.NNGPContext(joint, nn_j, np.ones(2 * n, dtype=np.int32), np.zeros(0, dtype=np.int32), "exponential_isotropic", device=local) as pctx:
+        with nb.NNGPContext(joint, nn_j, np.zeros(2 * n, dtype=np.int32), np.zeros(0, dtype=np.int32), "exponential_isotropic", device=local) as pctx:
             pctx.factor_build([1.0, RANGE, 0.0])
             zp = np.random.default_rng(5).standard_normal(n)
             pctx.predict_sample(n, w, beta_0, ls, zp)

@@ -589,7 +589,7 @@ def mcmc_nngp_predict_field(mcmc_nngp_list, predicted_locs, burn_in=.5, n_cores=
     stored = stored[stored > burn_in * stored.max()].astype(int)                                      # :13-14
     rng = np.random.default_rng(seed)
     out = {}
-    with NNGPContext(locs, NN, np.ones(n + n_pred, dtype=np.int32), np.zeros(0, dtype=np.int32), stm["covfun"]["stationary_covfun"], device=device) as ctx:
+    with NNGPContext(locs, NN, np.zeros(n + n_pred, dtype=np.int32), np.zeros(0, dtype=np.int32), stm["covfun"]["stationary_covfun"], device=device) as ctx:
         for name, chain in mcmc_nngp_list["records"].items():
             samples = np.zeros((stored.size, n_pred))
             prev_shape = None

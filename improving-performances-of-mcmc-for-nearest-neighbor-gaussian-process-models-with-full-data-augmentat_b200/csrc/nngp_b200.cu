@@ -8,9 +8,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -222,6 +224,7 @@ struct Ctx {
     bool have_factor[2] = {false, false};
     bool committed = false;           // valT / pd correspond to linv[cur]
     bool have_field = false, have_obs = false, have_newfield = false;
+    bool can_sweep = true;            // false: created without a colouring (prediction context)
     CovConst last_cc{};
     bool have_cc = false;
     unsigned long long sweep_counter = 0;
@@ -1184,8 +1187,16 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     CK(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
 
     // ---- validate structure, colour classes ----
+    // coloring all zero = "no colouring": a context that never sweeps (the joint observed ++ predicted site set of
+    // mcmc_nngp_predict_field, predict.R:4-8, has none).  Internally one colour class; every sweep entry point refuses.
+    std::vector<int> no_colour;
+    if (!sh) {
+        bool all_zero = true;
+        for (int i = 0; i < n && all_zero; i++) all_zero = coloring[i] == 0;
+        if (all_zero) { no_colour.assign(n, 1); coloring = no_colour.data(); c->can_sweep = false; }
+    }
     int K = 0;
-    for (int i = 0; i < n; i++) { REQUIRE(coloring[i] >= 1, "coloring[%d] = %d (colours are 1..K)", i, coloring[i]); K = std::max(K, coloring[i]); }
+    for (int i = 0; i < n; i++) { REQUIRE(coloring[i] >= 1, "coloring[%d] = %d (colours are 1..K; all zero = context without sweeps)", i, coloring[i]); K = std::max(K, coloring[i]); }
     if (sh) {   // a shard sees only some of the field's colours but must walk all of them in step with its peers
         REQUIRE(sh->n_colors >= K && sh->world >= 1 && sh->rank >= 0 && sh->rank < sh->world && sh->owned && sh->global_id && sh->global_zpos && sh->send_ptr && sh->recv_ptr && sh->comm_id,
                 "nngp_ctx_create_sharded: bad sharding arguments");
@@ -1208,7 +1219,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     // The sweep kernels update all sites of a colour concurrently and patch r without atomics: that is only race-free if no
     // two sites of one colour appear in the same row (= the colouring is proper for the moral graph, initialize.R:103-110).
     // Checked here, once, instead of trusting the caller (compute-sanitizer's racecheck is not available on this pool).
-    {
+    if (c->can_sweep) {
         std::vector<int> seen(K + 1, -1);
         for (int i = 0; i < n; i++) {
             for (int j = 0; j < M; j++) {
@@ -1398,7 +1409,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     c->d_rows_padded.upload(rows_padded, s);
     for (int cfg = 0; cfg < 4; cfg++) { c->d_tiles[cfg].upload(tiles[cfg], s); c->d_tile_ptr[cfg].upload(c->tile_ptr[cfg], s); }
     c->d_cloc.upload(cloc, s);
-    if (!c->sharded) {   // dataflow sweep: tile dependency lists, epoch word + ticket + one flag sector per tile
+    if (!c->sharded && c->can_sweep) {   // dataflow sweep: tile dependency lists, epoch word + ticket + one flag sector per tile
         std::vector<int> dep_ptr, dep_idx;
         tile_dependencies(tiles[1], colptr, crow, nn, ld, M, pof, n, dep_ptr, dep_idx, c->flow_edges_direct, c->flow_max_deps);
         c->flow_edges = (long long)dep_idx.size();
@@ -1783,6 +1794,7 @@ void nngp_gibbs_sweep(const int *ctx_id, const int *n_sweeps, const double *beta
     Ctx *c = get_ctx(ctx_id);
     REQUIRE(n_sweeps && beta_0 && log_scale && log_noise_variance && rng_mode && *n_sweeps >= 0, "nngp_gibbs_sweep: bad argument");
     REQUIRE(*rng_mode == NNGP_RNG_PHILOX || (*rng_mode == NNGP_RNG_SUPPLIED && z != nullptr), "nngp_gibbs_sweep: rng_mode 0 needs z");
+    NEED(c->can_sweep, "this context was created without a colouring (all-zero coloring): it cannot run Gibbs sweeps");
     NEED(c->have_slot(NNGP_SLOT_CURRENT), "nngp_gibbs_sweep: no current factor");
     NEED(c->have_field && c->have_obs, "nngp_gibbs_sweep: field and observations must be set first");
     use(c);
@@ -2075,6 +2087,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
     const int ns = *n_shape_, n_iter = *n_iter_, n_chromatic = *n_chromatic_, iter_start = *iter_start_, rng_mode = *rng_mode_;
     const double thin = *thin_, var_y = *var_y_;
     REQUIRE(ns >= 1 && ns <= 5 && n_iter >= 0 && n_chromatic >= 0, "nngp_chain_run: bad sizes");
+    NEED(c->can_sweep, "this context was created without a colouring (all-zero coloring): it cannot run Gibbs sweeps");
     use(c);
     // regressors: beta, the interweaving matrices (:77-83) and scratch for the (p+1)- and q-vectors
     const int reg_p = reg ? c->reg_p : 0, reg_q = reg ? c->reg_q : 0, P1 = reg_p + 1;
@@ -2128,6 +2141,18 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
         }
     }
     const unsigned long long philox_seed = ((unsigned long long)(uint32_t)iter_start << 20) ^ (unsigned long long)(uint32_t)*chain_index_;
+    // development aid: NNGP_CHAIN_PROFILE=1 synchronises at the phase boundaries and prints host wall-clock per phase
+    const bool prof = std::getenv("NNGP_CHAIN_PROFILE") != nullptr;
+    double phase_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](int k) {
+        if (!prof) return;
+        CK(cudaStreamSynchronize(c->stream));
+        const auto t = std::chrono::steady_clock::now();
+        phase_s[k] += std::chrono::duration<double>(t - t_last).count();
+        t_last = t;
+    };
+    if (prof) { CK(cudaStreamSynchronize(c->stream)); t_last = std::chrono::steady_clock::now(); }
     for (int iter = 1; iter <= n_iter; iter++) {
         // ---- (A) ancillary :113-157 ----
         const double sd_anc = std::exp(.5 * logvar_anc);
@@ -2157,6 +2182,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
             if (mean_acc < .05) logvar_anc -= (.4 + .05 * rs.norm_rand());
             if (mean_acc > .15) logvar_anc += (.4 + .05 * rs.norm_rand());
         }
+        mark(0);
         // ---- (B) sufficient :165-213 ----
         const double sd_suf = std::exp(.5 * logvar_suf);
         for (int k = 0; k < ns + 1; k++) innovation[k] = 0.0 + sd_suf * rs.norm_rand();
@@ -2186,6 +2212,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
             if (mean_acc < .05) logvar_suf -= (.2 + .05 * rs.norm_rand());
             if (mean_acc > .15) logvar_suf += (.2 + .05 * rs.norm_rand());
         }
+        mark(1);
         // ---- (C) beta_0 :219-224 (no location-level regressors) ----
         if (reg_q == 0) {
             op_beta0_sums(c, 0);
@@ -2245,6 +2272,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
             }
             op_set_beta(c, beta.data());                                         // :249 mu
         }
+        mark(2);
         // ---- (D) chromatic sweeps :257-275 ----
         if (rng_mode == NNGP_RNG_SUPPLIED) {
             ensure_zbuf(c, (size_t)n * std::max(1, n_chromatic));
@@ -2256,6 +2284,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
         refresh_r(c, beta_0);
         op_sweeps(c, n_chromatic, 0);
         c->sweep_counter += (unsigned long long)n_chromatic;
+        mark(3);
         // ---- (E) noise variance :281-293 ----
         op_obs_sq(c, c->d_field.p, c->d_field.p, 0);
         fetch_scalars(c, 2);
@@ -2266,6 +2295,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
                 if (-.5 * n_obs * inn - .5 * ssr * (std::exp(-lnv - inn) - std::exp(-lnv)) > std::log(rs.unif_rand())) lnv += inn;
             }
         }
+        mark(4);
         // ---- (F) records :305-311 ----
         if (records_out) {
             records_out[(size_t)(iter - 1)] = beta_0;
@@ -2292,7 +2322,12 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
             }
         }
         if (accept_out) { accept_out[iter - 1] = acc_anc[iter]; accept_out[n_iter + iter - 1] = acc_suf[iter]; }
+        mark(5);
     }
+    if (prof && n_iter > 0)
+        std::fprintf(stderr, "[nngp chain profile] per iteration, us: ancillary %.1f  sufficient %.1f  mean-params %.1f  sweeps(%d) %.1f  noise %.1f  records %.1f\n",
+                     1e6 * phase_s[0] / n_iter, 1e6 * phase_s[1] / n_iter, 1e6 * phase_s[2] / n_iter, n_chromatic, 1e6 * phase_s[3] / n_iter,
+                     1e6 * phase_s[4] / n_iter, 1e6 * phase_s[5] / n_iter);
     if (frec_on_device) CK(cudaMemcpyAsync(field_records_out, c->d_frec.p, (size_t)n_frec * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     params_io[0] = beta_0; params_io[1] = log_scale; params_io[2] = lnv; params_io[3] = logvar_suf; params_io[4] = logvar_anc;
@@ -2414,6 +2449,7 @@ void nngp_time_op(const int *ctx_id, const int *op_, const int *reps_, const int
     if (!c->committed) op_commit(c);
     if (op == 0) NEED(c->have_cc, "nngp_time_op(factor): call nngp_factor_build once first");
     if (op == 2 || op == 6) {
+        NEED(c->can_sweep, "this context was created without a colouring (all-zero coloring): it cannot run Gibbs sweeps");
         NEED(c->have_field && c->have_obs, "nngp_time_op(sweep): field and observations must be set first");
         const SweepParams *sp = reinterpret_cast<SweepParams *>(c->h_pinned + 32);
         set_sweep_params(c, sp->beta0, -std::log(sp->e_ls > 0 ? sp->e_ls : 1.0), -std::log(sp->e_ln > 0 ? sp->e_ln : 1.0), NNGP_RNG_PHILOX, 12345.0);

@@ -82,7 +82,9 @@ void nngp_host_order_maxmin(const double *locs, const int *n, const int *d, int 
 /* ------------------------------------------------------------------------------------------------------------------
  * context: graph structure uploaded once (vecchia_approx, Scripts/mcmc_nngp_initialize.R:80-110)
  * ------------------------------------------------------------------------------------------------------------------ */
-/* locs n x d; NNarray n x (m+1); coloring n (1..K); locs_match n_obs (1-based site of each observation);
+/* locs n x d; NNarray n x (m+1); coloring n (1..K, verified to be proper for the moral graph; ALL ZERO = no colouring:
+ * a context that never sweeps, e.g. the joint observed ++ predicted site set of mcmc_nngp_predict_field, predict.R:4-8 --
+ * its sweep entry points return NNGP_ERR_STATE); locs_match n_obs (1-based site of each observation);
  * device: CUDA ordinal; layout: NNGP_LAYOUT_*.  Returns a context id. */
 void nngp_ctx_create(const int *n, const int *d, const int *m, const double *locs, const int *NNarray,
                      const int *coloring, const int *n_obs, const int *locs_match, const int *covfun_id,

@@ -205,9 +205,12 @@ def test_predict_sample():
     field = 0.3 + rng.standard_normal(n)
     z = rng.standard_normal(n_pred)
     want = O.predict_field_sample(Lo, nn, n, field, 0.3, 0.5, z)
-    with nb.NNGPContext(locs, nn, np.ones(n + n_pred, dtype=np.int32), np.zeros(0, dtype=np.int32)) as ctx:
+    with nb.NNGPContext(locs, nn, np.zeros(n + n_pred, dtype=np.int32), np.zeros(0, dtype=np.int32)) as ctx:   # all-zero colouring = no sweeps
         ctx.factor_build(cp)
         got = ctx.predict_sample(n, field, 0.3, 0.5, z)
+        with pytest.raises(nb.NNGPError) as e:                  # a context without a colouring refuses to sweep
+            ctx.gibbs_sweep(0.0, 0.0, 0.0, n_sweeps=1, seed=1)
+        assert e.value.status == 4
     assert rel_vec(got, want) < 1e-9
 
 
