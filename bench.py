@@ -325,7 +325,7 @@ def run_ours(a):
         "ms": {"sweep": sweep_ms, "loglik": float(np.mean(ms_ll)), "factor_build": float(np.mean(ms_fac)),
                "spmv_plus_sptrsv": float(np.mean(ms_solve)), "accept_transpose_precision_diag": float(np.mean(ms_commit)),
                "wall_timed_region": wall * 1e3},
-        "roofline": {"bound": "hbm", "kernel": "gibbs_tile2_kernel (the K colour launches of one sweep, PDL-chained, replayed from one CUDA graph)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "gibbs_tile2_kernel (the K colour launches of one sweep, PDL-chained, replayed from one CUDA graph; 6 CTAs/SM build for colours that would not fit one wave at 5)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the colour launches of one sweep, --cache-control none)",
                      "algorithmic_bytes_per_sweep": ab["gibbs_sweep"],

@@ -1094,7 +1094,35 @@ template <int HINT> __device__ __forceinline__ unsigned int ld_stream_u8(const u
     return v;
 }
 
-template <int THREADS, bool PDL, int MINB, int HINT = 0, bool DBG = false>
+// PF: the CTA first asks the L2 for tile(s) of the NEXT colour (prefetch.global.L2 of the entry streams and per-site
+// constants).  With 5 CTAs/SM a large colour fills every slot of the chip, so the next colour's CTAs only become resident -- and
+// only then start streaming their ~13 KB of one-touch data from DRAM -- when this colour's CTAs exit: programmatic dependent
+// launch cannot overlap that prologue.  The prefetch moves the DRAM latency + transfer of colour c+1 under colour c's
+// gather / reduce / scatter phases, during which DRAM is idle (r and field are L2-resident).
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int THREADS>
+__device__ __forceinline__ void prefetch_tile(const int4 t, const unsigned char *__restrict__ tloc, const int *__restrict__ colptr,
+                                              const int *__restrict__ crow, const double *__restrict__ valT, const double *__restrict__ pd,
+                                              const double *__restrict__ nobs, const double *__restrict__ S, const int *__restrict__ psite,
+                                              const int *__restrict__ gid) {
+    const int tid = threadIdx.x;
+    const int ne = t.w - t.z, ns = t.y - t.x;
+    if (ne > THREADS * 8) return;                                   // oversize single-site tile: not worth it
+    for (int o = tid * 16; o < ne + 15; o += THREADS * 16) prefetch_l2(valT + t.z + min(o, ne - 1));      // 128-byte lines of doubles
+    for (int o = tid * 32; o < ne + 31; o += THREADS * 32) prefetch_l2(crow + t.z + min(o, ne - 1));
+    if (tid < 8) prefetch_l2(tloc + tid * 128);
+    for (int o = tid * 16; o < ns + 15; o += THREADS * 16) {
+        const int q = t.x + min(o, ns - 1);
+        prefetch_l2(pd + q); prefetch_l2(nobs + q); prefetch_l2(S + q);
+    }
+    for (int o = tid * 32; o < ns + 31; o += THREADS * 32) {
+        const int q = t.x + min(o, ns - 1);
+        prefetch_l2(colptr + q); prefetch_l2(psite + q); prefetch_l2(gid + q);
+    }
+}
+
+template <int THREADS, bool PDL, int MINB, int HINT = 0, bool DBG = false, bool PF = false>
 __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *__restrict__ tiles, int tile_base,
                                                               const int *__restrict__ colptr, const int *__restrict__ crow,
                                                               const unsigned char *__restrict__ cloc,
@@ -1103,7 +1131,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
                                                               const int *__restrict__ zpos, const int *__restrict__ gid,
                                                               const int *__restrict__ psite, const double *__restrict__ zbuf,
                                                               const SweepParams *__restrict__ spp, double *__restrict__ field,
-                                                              double *__restrict__ r, long long *ts, int col) {
+                                                              double *__restrict__ r, long long *ts, int col, int n_next = 0) {
     constexpr int EPT = 8;
     constexpr int ECAP = THREADS * EPT;
     __shared__ double sprod[ECAP + ECAP / 8];
@@ -1116,6 +1144,10 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
     long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq5 = 0;   // DBG: per-CTA phase clock
     if (DBG) tq0 = global_ns();
     if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (PF) {   // the next colour's tiles follow this colour's in the tile array: tiles[gridDim.x + j], j < n_next
+        for (int j = blockIdx.x; j < n_next; j += gridDim.x)
+            prefetch_tile<THREADS>(tiles[gridDim.x + j], cloc + (size_t)(tile_base + gridDim.x + j) * ECAP, colptr, crow, valT, pd, nobs, S, psite, gid);
+    }
     if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
         const int q = s0;
         if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1232,6 +1264,135 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
         atomicAdd(acc + 4, (unsigned long long)((long long)t - tq5));   // scatter issue
         atomicAdd(acc + 8, (unsigned long long)(tq4 - tq3));   // run sums alone
         atomicAdd(acc + 7, 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused tail of the sweep.  First-fit colour classes decay geometrically: the last few colours of a sweep hold a handful of
+// tiles (16, 1 and 1 at n = 1M, m = 10) yet each costs a full dependent stage of the PDL chain (~5 us: hand-off, gather,
+// sums, scatter drain).  All trailing colours with at most CLUSTER tiles run here in ONE launch of ONE thread-block cluster:
+// CTA j of the cluster owns tile j of every fused colour, colours are separated by the hardware cluster barrier
+// (barrier.cluster arrive.release / wait.acquire, a few hundred ns) instead of a kernel boundary, and the r-independent
+// prologue of the next colour (entry stream, per-site constants, draw) is issued between arrive and wait.  Because several
+// colours now share one kernel, r is gathered with ld.global.cg (L2 only: L1 lines from an earlier colour would be stale).
+// The kernel also advances the sweep counter (what advance_sweep_kernel does), saving that launch as well.
+// Arithmetic per tile is that of gibbs_tile2_kernel, so the results are bit-identical to the one-launch-per-colour chain.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ld_cg_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int cluster_ctarank() {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+template <int THREADS, bool PDL>
+__global__ void __launch_bounds__(THREADS) gibbs_tail_kernel(const int4 *__restrict__ tiles, const int *__restrict__ tile_ptr, int col_first,
+                                                             int K, const int *__restrict__ colptr, const int *__restrict__ crow,
+                                                             const unsigned char *__restrict__ cloc, const double *__restrict__ valT,
+                                                             const double *__restrict__ pd, const double *__restrict__ nobs,
+                                                             const double *__restrict__ S, const int *__restrict__ zpos,
+                                                             const int *__restrict__ gid, const int *__restrict__ psite,
+                                                             const double *__restrict__ zbuf, SweepParams *__restrict__ spp,
+                                                             double *__restrict__ field, double *__restrict__ r, unsigned long long n_advance) {
+    constexpr int EPT = 8;
+    constexpr int ECAP = THREADS * EPT;
+    __shared__ double sprod[ECAP + ECAP / 8];
+    __shared__ double sstart[THREADS], shead[THREADS];
+    __shared__ double sbc[2];
+    const int tid = threadIdx.x;
+    const int rank = (int)cluster_ctarank();
+    const SweepParams sp = *spp;
+    for (int col = col_first; col < K; col++) {
+        const int t = tile_ptr[col] + rank;
+        const bool has = t < tile_ptr[col + 1];          // uniform over the CTA
+        int s0 = 0, s1 = 0, e0 = 0, e1 = 0;
+        if (has) { const int4 tile = tiles[t]; s0 = tile.x; s1 = tile.y; e0 = tile.z; e1 = tile.w; }
+        const bool big = has && (e1 - e0 > ECAP);        // a single site whose column does not fit the tile
+        // ---- r-independent prologue (overlaps the previous colour's tail / the wait) ----
+        const unsigned char *tloc = cloc + (size_t)t * ECAP;
+        double val[EPT], rr[EPT];
+        int row[EPT];
+        unsigned int loc[EPT];
+        unsigned long long sid = 0ull;
+        unsigned int prev_last = 255u;
+        int k0 = 0, k1 = 0, sq = 0;
+        SiteConst sc{0.0, 0.0, 0.0};
+        if (has && !big) {
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+                const int e = e0 + k * THREADS + tid;
+                loc[k] = tloc[k * THREADS + tid];
+                if (e < e1) { val[k] = valT[e]; row[k] = crow[e]; } else { val[k] = 0.0; row[k] = -1; }
+            }
+            sid = reinterpret_cast<const unsigned long long *>(tloc)[tid];
+            prev_last = tid > 0 ? (unsigned int)tloc[8 * tid - 1] : 255u;
+            if (tid < s1 - s0) {
+                const int q = s0 + tid;
+                k0 = colptr[q] - e0;
+                k1 = colptr[q + 1] - e0;
+                sq = psite[q];
+                sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
+            }
+        }
+        // ---- wait for the previous colour: the preceding launch (first fused colour) or the cluster barrier ----
+        if (col == col_first) {
+            if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+        } else {
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+        if (big) {
+            const int q = s0;
+            double acc[1] = {0.0};
+            for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * ld_cg_f64(r + crow[e]);
+            block_reduce_sum<1>(acc);
+            if (tid == 0) {
+                const int sq1 = psite[q];
+                const double w_old = field[sq1] - sp.beta0;
+                const double Qss = pd[q], no = nobs[q];
+                const double prec = sp.e_ls * Qss + sp.e_ln * no;
+                const double tt = acc[0] - Qss * w_old;
+                const double resid = S[q] - no * sp.beta0;
+                const double mean = sp.beta0 - (1.0 / prec) * (tt * sp.e_ls - sp.e_ln * resid);
+                const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
+                sbc[0] = (f_new - sp.beta0) - w_old;
+                field[sq1] = f_new;
+            }
+            __syncthreads();
+            const double delta = sbc[0];
+            for (int e = e0 + tid; e < e1; e += THREADS) r[crow[e]] = ld_cg_f64(r + crow[e]) + valT[e] * delta;
+            __syncthreads();                              // sbc is reused by a later colour
+        } else if (has) {
+#pragma unroll
+            for (int k = 0; k < EPT; k++)
+                if (row[k] >= 0) rr[k] = ld_cg_f64(r + row[k]);
+#pragma unroll
+            for (int k = 0; k < EPT; k++) sprod[NNGP_PADPOS(k * THREADS + tid)] = (row[k] >= 0) ? val[k] * rr[k] : 0.0;
+            __syncthreads();
+            blocked_run_sums<THREADS>(sprod, sid, prev_last, sstart, shead);
+            __syncthreads();
+            if (tid < s1 - s0) {
+                const double a = blocked_site_sum(sstart, shead, tid, k0, k1);
+                const double f_new = sc.c0 - sc.c1 * a;
+                sstart[tid] = f_new - sc.f_old;
+                field[sq] = f_new;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < EPT; k++)
+                if (row[k] >= 0) r[row[k]] = rr[k] + val[k] * sstart[loc[k]];
+            __syncthreads();                              // sstart / sprod are rewritten by the next colour's reduction
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // every CTA copied *spp before its first arrive and all of them have arrived: advance the counter / normals offset
+    if (rank == 0 && tid == 0 && n_advance != 0ull) {
+        spp->sweep_counter = sp.sweep_counter + 1ull;
+        spp->z_offset = sp.z_offset + n_advance;
     }
 }
 

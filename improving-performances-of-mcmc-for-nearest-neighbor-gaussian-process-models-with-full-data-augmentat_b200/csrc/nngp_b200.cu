@@ -164,7 +164,12 @@ struct Ctx {
     bool persistent_ok[3] = {false, false, false};   // per-CTA tile list fits the kernel's shared-memory table
     // 0 persistent 256x8 | 1 per-colour launches 256x8 | 2 per-colour launches 128x8 | 3 thread-per-site launches
     // 4 persistent 256x4 | 5 persistent 128x8
-    int sweep_variant = 22;                // PDL chain of 128x8 tiles, blocked segmented reduction, L2 eviction hints: fastest (profiles/)
+    int tail_first = -1, tail_cluster = 0; // fused tail (gibbs_tail_kernel): first fused colour, cluster size (0 = unavailable)
+    // 34 = PDL chain of 128x8 tiles, blocked segmented reduction, L2 eviction hints, and the 6-CTAs/SM build for colours whose
+    // tile count would otherwise spill into a second wave: fastest (profiles/r01_explore_sweep_occupancy.txt).  Measured and
+    // kept as options: 22 (5 CTAs/SM everywhere, +6 %), 36 (trailing small colours fused into one cluster launch, +2 %),
+    // 37 (L2 prefetch of the next colour's tiles, +3 % at n = 1M, +10 % at 4M)
+    int sweep_variant = 34;
     int solve_variant = 0;                 // 0 sync-free single launch, 1 level-scheduled launches
     int commit_variant = 0;                // 0 tiled transposition, 1 thread per column
     // 1 plain coalesced loads (default), 0 TMA-staged ring.  Measured on B200 (profiles/r01_explore_final.txt): the TMA ring is
@@ -628,8 +633,27 @@ static void launch_sweep_colors(Ctx *c) {
 #undef NNGP_CHAIN_ARGS
             continue;
         }
-        if ((c->sweep_variant >= 15 && c->sweep_variant <= 17) || (c->sweep_variant >= 21 && c->sweep_variant <= 23)) {   // blocked segmented reduction (gibbs_tile2_kernel), 128x8 tiles
+        if ((c->sweep_variant >= 15 && c->sweep_variant <= 17) || (c->sweep_variant >= 21 && c->sweep_variant <= 23) || (c->sweep_variant >= 34 && c->sweep_variant <= 37)) {   // blocked segmented reduction (gibbs_tile2_kernel), 128x8 tiles
             const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
+            if (c->sweep_variant == 36 && c->tail_cluster > 0 && col == c->tail_first) {
+                // all remaining colours (each <= tail_cluster tiles) + the counter update: one cluster launch
+                cudaLaunchConfig_t lt = {};
+                lt.gridDim = dim3(c->tail_cluster);
+                lt.blockDim = dim3(128);
+                lt.stream = c->stream;
+                cudaLaunchAttribute att[2];
+                att[0].id = cudaLaunchAttributeClusterDimension;
+                att[0].val.clusterDim.x = c->tail_cluster; att[0].val.clusterDim.y = 1; att[0].val.clusterDim.z = 1;
+                att[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                att[1].val.programmaticStreamSerializationAllowed = 1;
+                lt.attrs = att;
+                lt.numAttrs = col > 0 ? 2 : 1;
+#define NNGP_TAIL_ARGS (const int4 *)c->d_tiles[1].p, (const int *)c->d_tile_ptr[1].p, col, c->K, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, (unsigned long long)c->n_global
+                if (col > 0) CK(cudaLaunchKernelEx(&lt, gibbs_tail_kernel<128, true>, NNGP_TAIL_ARGS));
+                else CK(cudaLaunchKernelEx(&lt, gibbs_tail_kernel<128, false>, NNGP_TAIL_ARGS));
+#undef NNGP_TAIL_ARGS
+                return;                                   // the tail kernel also advanced the sweep counter
+            }
             cudaLaunchConfig_t lc = {};
             lc.gridDim = dim3(nt);
             lc.blockDim = dim3(128);
@@ -640,12 +664,25 @@ static void launch_sweep_colors(Ctx *c) {
             lc.attrs = at;
             lc.numAttrs = (col > 0 && c->sweep_variant != 16) ? 1 : 0;
             const int4 *tl = c->d_tiles[1].p + t0;
-#define NNGP_T2_ARGS tl, t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, c->debug_timeline ? timeline_ptr() : (long long *)nullptr, col
+#define NNGP_T2_ARGS tl, t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, c->debug_timeline ? timeline_ptr() : (long long *)nullptr, col, n_next
+            const int n_next = (col + 1 < c->K && !(c->sweep_variant == 36 && c->tail_cluster > 0 && col + 1 >= c->tail_first)) ? c->tile_ptr[1][col + 2] - c->tile_ptr[1][col + 1] : 0;
             if (c->debug_timeline) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2, true>, NNGP_T2_ARGS));
             else if (c->sweep_variant == 15) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5>, NNGP_T2_ARGS));
             else if (c->sweep_variant == 17) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6>, NNGP_T2_ARGS));
             else if (c->sweep_variant == 21) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 1>, NNGP_T2_ARGS));
             else if (c->sweep_variant == 22) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, NNGP_T2_ARGS));
+            // 34: as 22, but a colour with more tiles than 5 CTAs/SM can hold (a 6 % tail wave that costs a whole extra
+            // gather -> sum -> scatter round) runs the 6-CTAs/SM build (80 registers) so that all its tiles are co-resident
+            else if (c->sweep_variant == 34 || c->sweep_variant == 36) {
+                if (nt > 5 * c->n_sm && nt <= 6 * c->n_sm) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2>, NNGP_T2_ARGS));
+                else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, NNGP_T2_ARGS));
+            }
+            else if (c->sweep_variant == 35) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2>, NNGP_T2_ARGS));
+            // 37: as 34, and every CTA prefetches tile(s) of the next colour into L2 before its own prologue
+            else if (c->sweep_variant == 37) {
+                if (nt > 5 * c->n_sm && nt <= 6 * c->n_sm) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2, false, true>, NNGP_T2_ARGS));
+                else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2, false, true>, NNGP_T2_ARGS));
+            }
             else if (c->sweep_variant == 23) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 3>, NNGP_T2_ARGS));
             else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, false, 5>, NNGP_T2_ARGS));
 #undef NNGP_T2_ARGS
@@ -691,7 +728,10 @@ static void launch_sweep_colors(Ctx *c) {
     advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, c->d_cdone.p, c->K);
 }
 
-static int sweep_launches(Ctx *c) { return sweep_is_flow(c) ? 2 : c->K + 1 + (sweep_is_two_pass(c) ? 1 : 0); }
+static int sweep_launches(Ctx *c) {
+    if (c->sweep_variant == 36 && c->tail_cluster > 0 && !c->sharded) return c->tail_first + 1;   // leading colours + fused tail
+    return sweep_is_flow(c) ? 2 : c->K + 1 + (sweep_is_two_pass(c) ? 1 : 0);
+}
 
 static bool sweep_is_persistent(Ctx *c) { return c->sweep_variant == 0 || c->sweep_variant == 4 || c->sweep_variant == 5; }
 
@@ -717,7 +757,7 @@ static void op_sweeps(Ctx *c, int n_sweeps, unsigned long long sweep_in_call) {
                     at[0].val.programmaticStreamSerializationAllowed = 1;
                     lc.attrs = at;
                     lc.numAttrs = (col > 0) ? 1 : 0;
-                    CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, (const int4 *)(c->d_tiles[1].p + t0), t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
+                    CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, (const int4 *)(c->d_tiles[1].p + t0), t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0, 0));
                 } else if (nt > 0) {
                     gibbs_tile2_kernel<128, false, 5, 2><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, t0, c->d_colptr.p, c->d_crow.p, c->d_cloc.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0);
                 }
@@ -1409,6 +1449,34 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     c->d_rows_padded.upload(rows_padded, s);
     for (int cfg = 0; cfg < 4; cfg++) { c->d_tiles[cfg].upload(tiles[cfg], s); c->d_tile_ptr[cfg].upload(c->tile_ptr[cfg], s); }
     c->d_cloc.upload(cloc, s);
+    if (!c->sharded && c->can_sweep) {   // fused tail of the sweep: the largest cluster the device can place, the colours it covers
+        for (int cl : {16, 8}) {
+            cudaLaunchConfig_t lt = {};
+            lt.gridDim = dim3(cl);
+            lt.blockDim = dim3(128);
+            cudaLaunchAttribute att[1];
+            att[0].id = cudaLaunchAttributeClusterDimension;
+            att[0].val.clusterDim.x = cl; att[0].val.clusterDim.y = 1; att[0].val.clusterDim.z = 1;
+            lt.attrs = att;
+            lt.numAttrs = 1;
+            int n_clusters = 0;
+            bool ok = true;
+            if (cl > 8) {
+                ok = cudaFuncSetAttribute(gibbs_tail_kernel<128, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                     cudaFuncSetAttribute(gibbs_tail_kernel<128, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+            }
+            if (ok && cudaOccupancyMaxActiveClusters(&n_clusters, gibbs_tail_kernel<128, true>, &lt) == cudaSuccess && n_clusters >= 1) {
+                c->tail_cluster = cl;
+                break;
+            }
+            cudaGetLastError();
+        }
+        if (c->tail_cluster > 0) {
+            c->tail_first = c->K;
+            while (c->tail_first > 0 && c->tile_ptr[1][c->tail_first] - c->tile_ptr[1][c->tail_first - 1] <= c->tail_cluster) c->tail_first--;
+            if (c->tail_first == c->K) c->tail_cluster = 0;   // even the last colour is too large: nothing to fuse
+        }
+    }
     if (!c->sharded && c->can_sweep) {   // dataflow sweep: tile dependency lists, epoch word + ticket + one flag sector per tile
         std::vector<int> dep_ptr, dep_idx;
         tile_dependencies(tiles[1], colptr, crow, nn, ld, M, pof, n, dep_ptr, dep_idx, c->flow_edges_direct, c->flow_max_deps);
@@ -1550,7 +1618,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
     use(c);
     CK(cudaStreamSynchronize(c->stream));
     switch (*key) {
-        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 33, "sweep variant must be 0..33"); c->sweep_variant = *value; break;
+        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 37, "sweep variant must be 0..37"); c->sweep_variant = *value; break;
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;

@@ -112,6 +112,10 @@ if __name__ == "__main__":
     launch_list(tag)
     import json
     traffic = {}
+    tj = os.path.join(OUT, "traffic.json")
+    if os.path.exists(tj):                      # captures that were not re-taken keep their earlier value
+        with open(tj) as f:
+            traffic = json.load(f).get("bytes", {})
     for rep, label in (("prof_gibbs.ncu-rep", "gibbs_sweep_full"), ("prof_gibbs_first.ncu-rep", "gibbs_first_colour_full"), ("prof_factor.ncu-rep", "factor_full"),
                        ("prof_loglik.ncu-rep", "loglik_full"), ("prof_other.ncu-rep", "transpose_sptrsv_full")):
         t = full(tag, rep, label)

@@ -323,7 +323,7 @@ def test_error_paths():
     assert "not proper" in str(e.value)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37])
 @pytest.mark.parametrize("n,m", [(20000, 10), (3000, 5)])
 def test_every_sweep_variant_matches_the_reference_loop(variant, n, m):
     """All kernel variants of the sweep (tiled launches, persistent cooperative kernel, PDL chain, dataflow launch, thread-per-site) are the
