@@ -69,18 +69,80 @@ __global__ void __launch_bounds__(128) matern_table_kernel(double *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// exp(-sqrt(d2)) for the register-resident factor kernel.  SASS of the first version (cuobjdump, m = 10): 3.5 k
+// instructions per row of which only 1.4 k were FP64 math -- 870 UMOV + 730 (I)MAD/MOV re-materialised the 64-bit
+// polynomial coefficients of libdevice's exp() for each of the 55 pairs (an FP64 immediate cannot be encoded in DFMA), and
+// every sqrt() carried a slow-path CALL.  Here the coefficients are constant-bank operands of the DFMAs (no moves), the
+// argument is known to be <= 0 and finite (no special cases), a 32-entry table of 2^(j/32) shortens the polynomial to
+// degree 6, and the distance comes from the MUFU seed + one Goldschmidt step + one Newton correction (no slow path).
+// ---------------------------------------------------------------------------------------------------------------
+// exp(x) = 2^n * 2^(j/32) * P(r),  x = (32 n + j) ln2/32 + r,  |r| <= ln2/64: degree-6 Taylor (remainder 4e-18),
+// table of 2^(j/32) correctly rounded (L1-resident 256 bytes), the power of two is added into the table entry's exponent
+__device__ const double g_exp2_tab32[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0, 0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0,
+    0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0, 0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0, 0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0,
+    0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0, 0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0, 0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0,
+    0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+__constant__ double c_exp_red[4] = {0x1.71547652b82fep+5 /* 32 / ln2 */, 6755399441055744.0 /* 1.5 * 2^52 */,
+                                    0x1.62e42fee00000p-6 /* ln2 / 32, high part (21 trailing zero bits) */, 0x1.a39ef35793c76p-38 /* low part */};
+__constant__ double c_exp_taylor[4] = {1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720};
+
+// sqrt(d2), d2 >= 0: MUFU.RSQ64H seed (>= 20 bits), one coupled Goldschmidt step (g -> sqrt, h -> 1/(2 sqrt)), one Newton
+// correction; no special-case slow path (libdevice's sqrt()/rsqrt() carry a CALL each).  <= 1 ulp; a coincident pair
+// (d2 = 0) comes out as 1e-150, whose covariance is exactly the variance.
+__device__ __forceinline__ double fast_sqrt_nonneg(double d2) {
+    const double a = fmax(d2, 1e-300);
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double g = a * r, h = 0.5 * r;
+    double e = fma(-g, h, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    e = fma(-g, g, a);
+    return fma(e, h, g);
+}
+
+// exp(x) for -745 < x <= 0 (returns 0 below -708: the result would be subnormal)
+__device__ __forceinline__ double fast_exp_nonpos(double x) {
+    const double kd = fma(x, c_exp_red[0], c_exp_red[1]);
+    const int ki = __double2loint(kd);
+    const double nd = kd - c_exp_red[1];
+    double r = fma(nd, -c_exp_red[2], x);
+    r = fma(nd, -c_exp_red[3], r);
+    double p = fma(c_exp_taylor[3], r, c_exp_taylor[2]);
+    p = fma(p, r, c_exp_taylor[1]);
+    p = fma(p, r, c_exp_taylor[0]);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double t = __ldg(g_exp2_tab32 + (ki & 31));
+    const double scale = __hiloint2double(__double2hiint(t) + ((ki >> 5) << 20), __double2loint(t));
+    return x < -708.0 ? 0.0 : p * scale;
+}
+
 __device__ __forceinline__ double matern_from_table(const double *__restrict__ tab, double x, double &out_ok) {
     const long long bits = __double_as_longlong(x);
     const int e = (int)((bits >> 52) & 0x7ff) - 1023;
     if (e < MT_EMIN || e >= MT_EMAX) { out_ok = 0.0; return 0.0; }
     const int seg = (e - MT_EMIN) * MT_S + (int)((bits >> 48) & 0xF);
-    const double u = (double)(bits & 0xFFFFFFFFFFFFll) * 3.5527136788005009e-15;   // 2^-48
-    const double *c = tab + (size_t)seg * 8;
-    double p = c[7];
-#pragma unroll
-    for (int k = 6; k >= 0; k--) p = p * (u - mt_node(k)) + c[k];
+    // position inside the segment, exactly: y = 1.mantissa, yb = y with the low 48 mantissa bits cleared, u = 16 (y - yb)
+    const long long mant = (bits & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll;
+    const double u = (__longlong_as_double(mant) - __longlong_as_double(mant & (long long)0xFFFF000000000000ull)) * 16.0;
+    const double2 *c2 = reinterpret_cast<const double2 *>(tab + (size_t)seg * 8);   // 64-byte aligned: four 128-bit loads
+    const double2 c01 = c2[0], c23 = c2[1], c45 = c2[2], c67 = c2[3];
+    double p = c67.y;
+    p = p * (u - mt_node(6)) + c67.x;
+    p = p * (u - mt_node(5)) + c45.y;
+    p = p * (u - mt_node(4)) + c45.x;
+    p = p * (u - mt_node(3)) + c23.y;
+    p = p * (u - mt_node(2)) + c23.x;
+    p = p * (u - mt_node(1)) + c01.y;
+    p = p * (u - mt_node(0)) + c01.x;
     out_ok = 1.0;
-    return p * exp(-x);
+    return p * fast_exp_nonpos(-x);
 }
 
 // parameters of the sweep that change between launches live in device memory so that the captured graph is static
@@ -176,6 +238,19 @@ __global__ void transform_locs_kernel(const double *__restrict__ locs /* [n][d] 
 }
 
 template <bool MATERN>
+__device__ __forceinline__ double kernel_value_fast(const CovConst &cc, double d2) {
+    if (!MATERN) return cc.variance * fast_exp_nonpos(-fast_sqrt_nonneg(d2));
+    if (d2 == 0.0) return cc.variance;
+    const double dist = fast_sqrt_nonneg(d2);
+    if (cc.mtab) {
+        double ok;
+        const double v = matern_from_table(cc.mtab, dist, ok);
+        if (ok != 0.0) return v;
+    }
+    return cc.normcon * pow(dist, cc.smooth) * bessel_k_real(cc.smooth, dist);
+}
+
+template <bool MATERN>
 __device__ __forceinline__ double kernel_value(const CovConst &cc, double dist) {
     if (!MATERN) return cc.variance * exp(-dist);
     if (dist == 0.0) return cc.variance;
@@ -187,97 +262,12 @@ __device__ __forceinline__ double kernel_value(const CovConst &cc, double dist) 
     return cc.normcon * pow(dist, cc.smooth) * bessel_k_real(cc.smooth, dist);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Vecchia factor build, register-resident: one thread per row, M = m+1 and DT compile-time, the (M x M) lower triangle
-// lives in registers, all loops fully unrolled.  Rows with fewer than m neighbours (at most m of them) are skipped here and
-// done by the generic kernel.  FP64-pipe bound: ~M(M-1)/2 exp + sqrt, M^3/6 FMA, M(M+1)/2 div.
-// Operation order = oracle_vecchia_linv (oracle/nngp_oracle.c): neighbours farthest-first, self last; row-by-row Cholesky;
-// back-substitution for the last row of L^-1.
-// ---------------------------------------------------------------------------------------------------------------
-template <int M, int DT, bool MATERN, int MINB = 3>
-__global__ void __launch_bounds__(128, MINB) vecchia_factor_reg_kernel(const int *__restrict__ nn, const double *__restrict__ tl,
-                                                                 double *__restrict__ linv, int n, int ld, CovConst cc,
-                                                                 int *__restrict__ n_bad) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    int idx[M];
-    bool full = true;
-#pragma unroll
-    for (int j = 0; j < M; j++) {
-        idx[j] = nn[(size_t)j * ld + q];
-        full = full && (idx[j] >= 0);
-    }
-    if (!full) return;
-    double p[M][DT];
-#pragma unroll
-    for (int k = 0; k < M; k++) {
-        const double *src = tl + (size_t)idx[M - 1 - k] * DT;
-        if (DT == 2) {
-            const double2 v = *reinterpret_cast<const double2 *>(src);
-            p[k][0] = v.x;
-            p[k][1] = v.y;
-        } else {
-#pragma unroll
-            for (int c = 0; c < DT; c++) p[k][c] = src[c];
-        }
-    }
-    // ncu (profiles/r01_factor_full.txt): FP64 pipe 41 % busy, ~2.6 k FP64 instructions per row of which the 66 divisions
-    // and 11 square roots are a third.  One reciprocal square root per pivot replaces them: inv[a] = rsqrt(pivot),
-    // L[a][a] = pivot * inv[a], L[a][b] = s * inv[b], x[a] = s * inv[a]  (<= 2 ulp per operation away from the oracle's
-    // sqrt / divide; the parity tests bound the effect on a factor row at 1e-10).
-    double L[M * (M + 1) / 2];
-    double inv[M];
-    bool ok = true;
-#pragma unroll
-    for (int a = 0; a < M; a++) {
-#pragma unroll
-        for (int b = 0; b <= a; b++) {
-            double s;
-            if (a == b) {
-                s = cc.variance + cc.nugget;
-            } else {
-                double d2 = 0.0;
-#pragma unroll
-                for (int c = 0; c < DT; c++) {
-                    const double t = p[a][c] - p[b][c];
-                    d2 += t * t;
-                }
-                s = kernel_value<MATERN>(cc, sqrt(d2));
-            }
-#pragma unroll
-            for (int k = 0; k < b; k++) s -= L[a * (a + 1) / 2 + k] * L[b * (b + 1) / 2 + k];
-            if (a == b) {
-                ok = ok && (s > 0.0);
-                inv[a] = rsqrt(s);
-                L[a * (a + 1) / 2 + a] = s * inv[a];
-            } else {
-                L[a * (a + 1) / 2 + b] = s * inv[b];
-            }
-        }
-    }
-    double x[M];
-#pragma unroll
-    for (int a = M - 1; a >= 0; a--) {
-        double s = (a == M - 1) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = a + 1; k < M; k++) s -= L[k * (k + 1) / 2 + a] * x[k];
-        x[a] = s * inv[a];
-    }
-#pragma unroll
-    for (int j = 0; j < M; j++) linv[(size_t)j * ld + q] = x[M - 1 - j];
-    if (!ok) atomicAdd(n_bad, 1);
-}
-
-// Generic factor build: any M <= MCAP, any DT <= 4, rows listed in `rows` (or all rows when rows == nullptr); handles
-// partial rows (fewer than m neighbours).  Triangle in local memory.
+// One row of the factor with the triangle in local memory: any M <= MCAP, any DT <= 4, any number of valid neighbours.
+// Deliberately not inlined: the register-resident kernel calls it for the (at most m) rows that have fewer than m
+// neighbours, so that those rows ride along with the main launch instead of costing a serial 40 us launch of their own.
 template <int MCAP, bool MATERN>
-__global__ void __launch_bounds__(128) vecchia_factor_generic_kernel(const int *__restrict__ nn, const double *__restrict__ tl,
-                                                                     double *__restrict__ linv, const int *__restrict__ rows,
-                                                                     int n_rows, int ld, int M, CovConst cc,
-                                                                     int *__restrict__ n_bad) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_rows) return;
-    const int q = rows ? rows[t] : t;
+__device__ __noinline__ void factor_row_generic(int q, const int *__restrict__ nn, const double *__restrict__ tl,
+                                                double *__restrict__ linv, int ld, int M, const CovConst &cc, int *__restrict__ n_bad) {
     const int DT = cc.dt;
     int idx[MCAP];
     int bsize = 0;
@@ -319,6 +309,102 @@ __global__ void __launch_bounds__(128) vecchia_factor_generic_kernel(const int *
     }
     for (int j = 0; j < M; j++) linv[(size_t)j * ld + q] = (j < bsize) ? x[bsize - 1 - j] : 0.0;
     if (!ok) atomicAdd(n_bad, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Vecchia factor build, register-resident: one thread per row, M = m+1 and DT compile-time, the (M x M) lower triangle
+// lives in registers, all loops fully unrolled.  Rows with fewer than m neighbours (at most m of them) take the generic
+// local-memory path (factor_row_generic) inside the same launch (PARTIAL; M <= 24).  FP64-pipe bound: ~M(M-1)/2 exp + sqrt, M^3/6 FMA, M(M+1)/2 div.
+// Operation order = oracle_vecchia_linv (oracle/nngp_oracle.c): neighbours farthest-first, self last; row-by-row Cholesky;
+// back-substitution for the last row of L^-1.
+// ---------------------------------------------------------------------------------------------------------------
+template <int M, int DT, bool MATERN, int MINB = 3, bool FAST = true, bool PARTIAL = true>
+__global__ void __launch_bounds__(128, MINB) vecchia_factor_reg_kernel(const int *__restrict__ nn, const double *__restrict__ tl,
+                                                                 double *__restrict__ linv, int n, int ld, CovConst cc,
+                                                                 int *__restrict__ n_bad) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int idx[M];
+    bool full = true;
+#pragma unroll
+    for (int j = 0; j < M; j++) {
+        idx[j] = nn[(size_t)j * ld + q];
+        full = full && (idx[j] >= 0);
+    }
+    if (!full) {   // one of the first m rows: generic path, concurrently with the rest of this launch
+        if (PARTIAL) factor_row_generic<24, MATERN>(q, nn, tl, linv, ld, M, cc, n_bad);
+        return;
+    }
+    double p[M][DT];
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+        const double *src = tl + (size_t)idx[M - 1 - k] * DT;
+        if (DT == 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(src);
+            p[k][0] = v.x;
+            p[k][1] = v.y;
+        } else {
+#pragma unroll
+            for (int c = 0; c < DT; c++) p[k][c] = src[c];
+        }
+    }
+    // ncu (profiles/r01_factor_full.txt): FP64 pipe 41 % busy, ~2.6 k FP64 instructions per row of which the 66 divisions
+    // and 11 square roots are a third.  One reciprocal square root per pivot replaces them: inv[a] = rsqrt(pivot),
+    // L[a][a] = pivot * inv[a], L[a][b] = s * inv[b], x[a] = s * inv[a]  (<= 2 ulp per operation away from the oracle's
+    // sqrt / divide; the parity tests bound the effect on a factor row at 1e-10).
+    double L[M * (M + 1) / 2];
+    double inv[M];
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+            double s;
+            if (a == b) {
+                s = cc.variance + cc.nugget;
+            } else {
+                double d2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < DT; c++) {
+                    const double t = p[a][c] - p[b][c];
+                    d2 += t * t;
+                }
+                s = FAST ? kernel_value_fast<MATERN>(cc, d2) : kernel_value<MATERN>(cc, sqrt(d2));
+            }
+#pragma unroll
+            for (int k = 0; k < b; k++) s -= L[a * (a + 1) / 2 + k] * L[b * (b + 1) / 2 + k];
+            if (a == b) {
+                ok = ok && (s > 0.0);
+                inv[a] = rsqrt(s);
+                L[a * (a + 1) / 2 + a] = s * inv[a];
+            } else {
+                L[a * (a + 1) / 2 + b] = s * inv[b];
+            }
+        }
+    }
+    double x[M];
+#pragma unroll
+    for (int a = M - 1; a >= 0; a--) {
+        double s = (a == M - 1) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = a + 1; k < M; k++) s -= L[k * (k + 1) / 2 + a] * x[k];
+        x[a] = s * inv[a];
+    }
+#pragma unroll
+    for (int j = 0; j < M; j++) linv[(size_t)j * ld + q] = x[M - 1 - j];
+    if (!ok) atomicAdd(n_bad, 1);
+}
+
+// Generic factor build: any M <= MCAP, any DT <= 4, rows listed in `rows` (or all rows when rows == nullptr); handles
+// partial rows (fewer than m neighbours).  Triangle in local memory (factor_row_generic).
+template <int MCAP, bool MATERN>
+__global__ void __launch_bounds__(128) vecchia_factor_generic_kernel(const int *__restrict__ nn, const double *__restrict__ tl,
+                                                                     double *__restrict__ linv, const int *__restrict__ rows,
+                                                                     int n_rows, int ld, int M, CovConst cc,
+                                                                     int *__restrict__ n_bad) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows) return;
+    factor_row_generic<MCAP, MATERN>(rows ? rows[t] : t, nn, tl, linv, ld, M, cc, n_bad);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

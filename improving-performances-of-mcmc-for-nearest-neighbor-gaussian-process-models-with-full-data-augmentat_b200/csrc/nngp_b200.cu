@@ -384,6 +384,9 @@ static void launch_factor(Ctx *c, double *linv, const CovConst &cc) {
     } else if (M == 11 && c->dt == 2 && c->factor_variant == 2) {   // ... or at 96 registers (5 CTAs / SM)
         vecchia_factor_reg_kernel<11, 2, MATERN, 5><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
         specialised = true;
+    } else if (M == 11 && c->dt == 2 && c->factor_variant == 3) {   // libdevice sqrt() / exp() instead of the constant-bank versions
+        vecchia_factor_reg_kernel<11, 2, MATERN, 3, false, false><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
+        specialised = true;
     } else
     FACTOR_CASE(6, 2)
     FACTOR_CASE(6, 3)
@@ -396,7 +399,7 @@ static void launch_factor(Ctx *c, double *linv, const CovConst &cc) {
 #undef FACTOR_CASE
     if (specialised) {
         LAUNCHED(c);
-        const int np = (int)c->partial_rows.size();
+        const int np = (M <= 24 && c->factor_variant != 3) ? 0 : (int)c->partial_rows.size();   // partial rows ride along in the main launch
         if (np > 0) {
             vecchia_factor_generic_kernel<24, MATERN><<<(np + blk - 1) / blk, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, c->d_partial_rows.p, np, ld, M, cc, c->d_nbad.p);
             LAUNCHED(c);
@@ -1622,7 +1625,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;
-        case NNGP_OPT_FACTOR_VARIANT: REQUIRE(*value >= 0 && *value <= 2, "factor variant must be 0..2"); c->factor_variant = *value; break;
+        case NNGP_OPT_FACTOR_VARIANT: REQUIRE(*value >= 0 && *value <= 3, "factor variant must be 0..3"); c->factor_variant = *value; break;
         case NNGP_OPT_LOGLIK_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "loglik variant must be 0..1"); c->loglik_variant = *value; break;
         case NNGP_OPT_MATERN_TABLE: c->matern_table = (*value != 0); break;
         case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 2, "commit variant must be 0..2"); c->commit_variant = *value; break;
