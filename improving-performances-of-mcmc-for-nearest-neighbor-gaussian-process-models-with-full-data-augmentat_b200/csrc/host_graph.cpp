@@ -205,12 +205,19 @@ int greedy_coloring(const int *NNarray, int n, int m, int *coloring) {
     std::vector<int> stamp(64, -1);
     int K = 0;
     for (int i = 0; i < n; i++) coloring[i] = 0;
+    // row-major copy of the neighbour table: the loop below reads whole rows at random, and in R's column-major layout the
+    // m+1 members of a row sit n ints apart (one cache miss each instead of one per row)
+    const int M = m + 1;
+    std::vector<int> nn_rm((size_t)n * M);
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < n; r++)
+        for (int j = 0; j < M; j++) nn_rm[(size_t)r * M + j] = NNarray[(size_t)r + (size_t)n * j];
     for (int i = 0; i < n; i++) {
         // moral neighbours of i = members of every row that contains i (Scripts/mcmc_nngp_initialize.R:103)
         for (int64_t k = ptr[i]; k < ptr[i + 1]; k++) {
-            int r = rows[k];
+            const int *row = nn_rm.data() + (size_t)rows[k] * M;
             for (int j = 0; j <= m; j++) {
-                int v = NNarray[(size_t)r + (size_t)n * j];
+                int v = row[j];
                 if (v == NNGP_NA_INT) continue;
                 int c = coloring[v - 1];
                 if (c > 0) {
