@@ -153,7 +153,7 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 8))
+    procs = max(1, min(cores, a.ref_procs))
     # bounded sample: the reference-form sweep costs K full mat-vecs, ~1 s/step/chain at n = 1M
     n = a.n if a.ref_n is None else a.ref_n
     steps = max(1, min(a.steps, 3))
@@ -435,6 +435,7 @@ def main():
     ap.add_argument("--sites", "--n", dest="n", type=int, default=1_000_000)
     ap.add_argument("--nbrs", "--m", dest="m", type=int, default=10)
     ap.add_argument("--ref-n", type=int, default=None, help="reference arm: run on a smaller n and scale (bounded sample)")
+    ap.add_argument("--ref-procs", type=int, default=32, help="reference arm: at most this many independent chains (one per host core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
     ap.add_argument("--mode", default="chains", choices=["chains", "sharded"])
