@@ -5,6 +5,7 @@
 // hot path.  Semantics (and the reference lines they replace) are documented in the header.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <queue>
@@ -199,6 +200,64 @@ void build_csc(const int *NNarray, int n, int m, std::vector<int64_t> &ptr, std:
         }
 }
 
+// Exact first-fit colouring in index order, in parallel.  colour(i) = smallest colour not used by a moral neighbour j < i, so
+// the sites of a block [b0, b1) of consecutive indices can all scan their neighbourhoods at once: colours of neighbours
+// j < b0 are final and go into a 64-bit "forbidden" mask, neighbours inside the block with b0 <= j < i are only recorded.
+// A cheap sequential pass over the block then resolves the recorded dependencies in index order.  The result is identical
+// to the sequential loop (Coloring.R:2-20) by construction; the expensive part -- ~ (m+1)^2 random reads per site -- is
+// spread over the host cores.  Returns 0 when a colour >= 63 shows up (caller falls back to the sequential loop).
+static int greedy_coloring_blocked(const int *nn_rm, int n, int M, const std::vector<int64_t> &ptr, const std::vector<int> &rows, int *coloring) {
+    const int B = 8192, CAP = 24;
+    const char *lim_env = std::getenv("NNGP_COLORING_MASK_COLOURS");   // testing hook: pretend the mask is narrower than 63 colours
+    const int limit = lim_env ? std::max(1, std::min(63, std::atoi(lim_env))) : 63;
+    std::vector<uint64_t> mask(B);
+    std::vector<int> ndep(B), dep((size_t)B * CAP);
+    int K = 0;
+    for (int b0 = 0; b0 < n; b0 += B) {
+        const int b1 = std::min(n, b0 + B);
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int i = b0; i < b1; i++) {
+            uint64_t mk = 0;
+            int nd = 0;
+            for (int64_t k = ptr[i]; k < ptr[i + 1]; k++) {
+                const int *row = nn_rm + (size_t)rows[k] * M;
+                for (int j = 0; j < M; j++) {
+                    const int v = row[j];
+                    if (v == NNGP_NA_INT) continue;
+                    const int s = v - 1;
+                    if (s >= i) continue;
+                    if (s < b0) mk |= (uint64_t)1 << coloring[s];
+                    else if (nd < CAP) dep[(size_t)(i - b0) * CAP + nd++] = s;
+                    else nd = CAP + 1;                 // too many in-block neighbours: rescan in the sequential pass
+                }
+            }
+            mask[i - b0] = mk;
+            ndep[i - b0] = nd;
+        }
+        for (int i = b0; i < b1; i++) {
+            uint64_t mk = mask[i - b0];
+            const int nd = ndep[i - b0];
+            if (nd <= CAP) {
+                for (int k = 0; k < nd; k++) mk |= (uint64_t)1 << coloring[dep[(size_t)(i - b0) * CAP + k]];
+            } else {
+                for (int64_t k = ptr[i]; k < ptr[i + 1]; k++) {
+                    const int *row = nn_rm + (size_t)rows[k] * M;
+                    for (int j = 0; j < M; j++) {
+                        const int v = row[j];
+                        if (v != NNGP_NA_INT && v - 1 < i && v - 1 >= b0) mk |= (uint64_t)1 << coloring[v - 1];
+                    }
+                }
+            }
+            mk |= 1;                                    // bit 0 is not a colour
+            const int c = __builtin_ctzll(~mk);
+            if (c >= limit) return 0;
+            coloring[i] = c;
+            if (c > K) K = c;
+        }
+    }
+    return K;
+}
+
 int greedy_coloring(const int *NNarray, int n, int m, int *coloring) {
     std::vector<int64_t> ptr; std::vector<int> rows, slots;
     build_csc(NNarray, n, m, ptr, rows, slots);
@@ -212,6 +271,11 @@ int greedy_coloring(const int *NNarray, int n, int m, int *coloring) {
 #pragma omp parallel for schedule(static)
     for (int r = 0; r < n; r++)
         for (int j = 0; j < M; j++) nn_rm[(size_t)r * M + j] = NNarray[(size_t)r + (size_t)n * j];
+    if (std::getenv("NNGP_COLORING_SEQUENTIAL") == nullptr) {
+        K = greedy_coloring_blocked(nn_rm.data(), n, M, ptr, rows, coloring);
+        if (K > 0 || n == 0) return K;
+        for (int i = 0; i < n; i++) coloring[i] = 0;    // 63 colours or more: the mask is too narrow, use the sequential loop
+    }
     for (int i = 0; i < n; i++) {
         // moral neighbours of i = members of every row that contains i (Scripts/mcmc_nngp_initialize.R:103)
         for (int64_t k = ptr[i]; k < ptr[i + 1]; k++) {

@@ -94,3 +94,23 @@ def test_bad_arguments_are_reported_not_crashed():
     assert st.value == 1
     L.load().nngp_ctx_destroy(L.ci(12345), C.byref(st))
     assert st.value == 1 and "unknown context" in L.last_error()
+
+
+@pytest.mark.parametrize("n,m,d,order", [(120000, 10, 2, "random"), (30000, 20, 2, "random"), (20000, 10, 2, "maxmin"), (20000, 31, 2, "random")])
+def test_parallel_coloring_equals_the_sequential_first_fit(n, m, d, order, monkeypatch):
+    """The blocked-parallel colouring (mask of final colours + in-block dependencies resolved in index order) is the
+    sequential first-fit loop of Coloring.R:2-20 bit for bit, including the fall-back when 63 colours do not suffice
+    (m = 31) and a max-min ordering, whose first sites are moral neighbours of almost everything."""
+    rng = np.random.default_rng(n + m)
+    locs = rng.random((n, d))
+    if order == "maxmin":
+        locs = locs[nb.order_maxmin(locs) - 1]
+    nn = nb.find_ordered_nn(locs, m)
+    par = nb.greedy_coloring(nn)
+    monkeypatch.setenv("NNGP_COLORING_MASK_COLOURS", "12")       # fewer mask bits than colours: the fall-back path
+    fb = nb.greedy_coloring(nn)
+    monkeypatch.delenv("NNGP_COLORING_MASK_COLOURS")
+    monkeypatch.setenv("NNGP_COLORING_SEQUENTIAL", "1")
+    seq = nb.greedy_coloring(nn)
+    assert np.array_equal(par, seq) and np.array_equal(fb, seq)
+    assert par.min() == 1
