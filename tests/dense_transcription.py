@@ -6,7 +6,7 @@ is numpy.linalg.solve, crossprod(a, b) is a.T @ b, ...) and R's own random strea
 against the vignette in test_oracle_golden.py).  The only call that is not transcribed is GpGp::vecchia_Linv (third-party,
 restated in oracle/ and pinned by the dense-GP identities).  It exists to check the C oracle's chain -- in particular the
 regression block :226-250 -- against an independently written form; it is O(n^2)-O(n^3) per iteration and only usable for
-n of a few hundred.  Only log-parametrised shapes (the exponential families) are transcribed.
+n of a few hundred.
 """
 from __future__ import annotations
 
@@ -54,7 +54,12 @@ def update_gaussian_chain(locs, NNarray, coloring, locs_match, observed_field, c
     rec_beta = None if X is None else np.zeros((n_iterations_update, X.shape[1]))
     rec_field = np.zeros((int(round(n_iterations_update * field_thinning)), n_locs))
     acc_suf, acc_anc = np.zeros(n_iterations_update), np.zeros(n_iterations_update)
-    vecchia = lambda shape: O.vecchia_Linv(np.concatenate([[1.0], np.exp(shape), [0.0]]), covfun, locs, NNarray)   # :67-72
+    def vecchia(shape):                                                                                # :67-72
+        # shape_params "log_*" -> exp, "qlogis_*" (the Matern smoothness, last) -> .5 + .5 plogis
+        sh = np.exp(shape)
+        if covfun.startswith("matern"):
+            sh[-1] = .5 + .5 / (1.0 + np.exp(-shape[-1]))
+        return O.vecchia_Linv(np.concatenate([[1.0], sh, [0.0]]), covfun, locs, NNarray)
     compressed = vecchia(st["shape"])
     sparse_chol = sparse_matrix(compressed, NNarray)                                                   # :73
     precision_diag = (sparse_chol ** 2).sum(axis=0)                                                    # :74

@@ -304,19 +304,20 @@ def test_chain_with_regressors_matches_dense_transcription(p_locs, p_obs, extra)
         assert np.max(np.abs(st["beta"] - po["beta"])) < 1e-8
 
 
-def test_chain_without_regressors_matches_dense_transcription():
-    """Same check for the no-regressor loop (the path nngp_chain_run implements)."""
+@pytest.mark.parametrize("covfun,shape", [("exponential_isotropic", [np.log(0.12)]), ("matern_isotropic", [np.log(0.12), 0.4])])
+def test_chain_without_regressors_matches_dense_transcription(covfun, shape):
+    """Same check for the no-regressor loop (the path nngp_chain_run implements), exponential and Matern (qlogis smoothness)."""
     import dense_transcription as T
     from problems import make_regression_problem
     n, m, n_iter = 90, 4, 50
     P = make_regression_problem(n, m, seed=3, n_extra_obs=15, p_locs=1, p_obs=0)
-    p0 = dict(shape=[np.log(0.12)], beta_0=0.5, log_scale=-0.2, log_noise_variance=np.log(0.15), logvar_sufficient=-1.0,
+    p0 = dict(shape=shape, beta_0=0.5, log_scale=-0.2, log_noise_variance=np.log(0.15), logvar_sufficient=-1.0,
               logvar_ancillary=-1.0)
     field0 = 0.5 + P["w"]
     po, fo, reco, freco, acco = O.update_gaussian_chain(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], P["obs_per_loc"], P["y"],
-                                                        "exponential_isotropic", p0, field0, n_iter, 1.0, 2, 0, 1, 0)
+                                                        covfun, p0, field0, n_iter, 1.0, 2, 0, 1, 0)
     st, rec, _, rec_field, acc = T.update_gaussian_chain(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], P["y"],
-                                                         "exponential_isotropic", p0, field0, n_iter, 1.0, 2, 0, 1)
+                                                         covfun, p0, field0, n_iter, 1.0, 2, 0, 1)
     assert np.array_equal(acc, acco)
     assert np.max(np.abs(rec - reco)) < 1e-8
     assert np.max(np.abs(rec_field - freco)) < 1e-7
