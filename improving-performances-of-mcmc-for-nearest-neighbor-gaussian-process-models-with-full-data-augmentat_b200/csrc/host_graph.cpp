@@ -324,9 +324,27 @@ void order_maxmin(const double *locs_cm, int n, int d, int *order) {
         pos_of[s] = q;
         for (int k = 0; k < d; k++) Ps[(size_t)q * d + k] = P[(size_t)s * d + k];
     }
-    // heap entries carry the position; ties are broken by the ORIGINAL index (lower first), as before
-    struct HE { double d2; int idx; int pos; bool operator<(const HE &o) const { return d2 < o.d2 || (d2 == o.d2 && idx > o.idx); } };
-    std::priority_queue<HE> heap;
+    // Indexed max-heap with one node per unselected site (key = (distance to the selected set, lower original index
+    // first)); a relaxation lowers a key in place (sift-down) instead of pushing a fresh entry -- the lazy heap of the first
+    // version grew to ~14 M mostly stale entries at n = 1M and its cache misses were most of the run time.
+    struct Node { double d2; int idx; int pos; };
+    auto before = [](const Node &a, const Node &b) { return a.d2 > b.d2 || (a.d2 == b.d2 && a.idx < b.idx); };   // a leaves the heap first
+    std::vector<Node> heap;
+    std::vector<int> where(n, -1);
+    int hn = 0;
+    auto sift_down = [&](int h) {
+        Node t = heap[h];
+        for (;;) {
+            int c = 2 * h + 1;
+            if (c >= hn) break;
+            if (c + 1 < hn && before(heap[c + 1], heap[c])) c++;
+            if (!before(heap[c], t)) break;
+            heap[h] = heap[c]; where[heap[h].pos] = h;
+            h = c;
+        }
+        heap[h] = t; where[t.pos] = h;
+    };
+    bool heap_ready = false;
     auto relax_around = [&](int pq, double r2) {
         // every unselected q with |q-p|^2 < dist[q] has dist[q] <= r2, hence lies within radius sqrt(r2) of p
         double r = std::sqrt(r2);
@@ -343,16 +361,28 @@ void order_maxmin(const double *locs_cm, int n, int d, int *order) {
                 for (int q = g.start[ca]; q < g.start[cb + 1]; q++) {
                     if (done[q]) continue;
                     double dd = dist2(Ps.data(), d, q, pq);
-                    if (dd < dist[q]) { dist[q] = dd; heap.push(HE{dd, g.pts[q], q}); }
+                    if (dd < dist[q]) {
+                        dist[q] = dd;
+                        if (heap_ready) { heap[where[q]].d2 = dd; sift_down(where[q]); }
+                    }
                 }
             }
     };
     int cnt = 0;
     done[pos_of[first]] = 1; order[cnt++] = first + 1;
-    relax_around(pos_of[first], INFINITY);
-    while (cnt < n) {
-        HE t = heap.top(); heap.pop();
-        if (done[t.pos] || t.d2 != dist[t.pos]) continue;   // stale entry
+    relax_around(pos_of[first], INFINITY);             // every other site now has a finite distance
+    heap.reserve(n);
+    for (int q = 0; q < n; q++)
+        if (!done[q]) { heap.push_back(Node{dist[q], g.pts[q], q}); }
+    hn = (int)heap.size();
+    for (int h = 0; h < hn; h++) where[heap[h].pos] = h;
+    for (int h = hn / 2 - 1; h >= 0; h--) sift_down(h);
+    heap_ready = true;
+    while (hn > 0) {
+        const Node t = heap[0];
+        hn--;
+        if (hn > 0) { heap[0] = heap[hn]; sift_down(0); }
+        where[t.pos] = -1;
         done[t.pos] = 1; order[cnt++] = t.idx + 1;
         relax_around(t.pos, t.d2);
     }
