@@ -110,3 +110,31 @@ nngp_chain_run_regressors = function(ctx, params, transition_kernels, X, n_iter,
                 var_y = as.double(var_y), records_out = double(n_iter * (3 + k)), beta_records_out = double(n_iter * ncol(X$X)),
                 field_records_out = double(max(n_frec, 1) * n_locs), accept_out = integer(2 * n_iter), status = integer(1)))
 }
+
+# GpGp::find_ordered_nn replacement (exact m nearest previous sites, ties by lower index; initialize.R:93, predict.R:5)
+nngp_find_ordered_nn = function(locs, m)
+{
+  locs = as.matrix(locs)
+  res = nngp_check(.C("nngp_host_find_ordered_nn", locs = as.double(locs), n = nrow(locs), d = ncol(locs), m = as.integer(m),
+                      NNarray = integer(nrow(locs) * (m + 1)), status = integer(1), NAOK = TRUE))
+  NNarray = matrix(res$NNarray, nrow(locs), m + 1)
+  NNarray[NNarray == -2147483647L - 1L] = NA   # unreachable in practice: .C hands INT_MIN back as NA_integer_ already
+  NNarray
+}
+
+# context over the joint (observed ++ predicted) site set of mcmc_nngp_predict_field: no colouring (all zero), no observations
+nngp_ctx_create_predict = function(locs, NNarray, stationary_covfun, device = 0L, layout = 2L)
+{
+  locs = as.matrix(locs)
+  res = nngp_check(.C("nngp_ctx_create", n = nrow(locs), d = ncol(locs), m = as.integer(ncol(NNarray) - 1L), locs = as.double(locs),
+                      NNarray = as.integer(NNarray), coloring = integer(nrow(locs)), n_obs = 0L, locs_match = integer(1),
+                      covfun_id = nngp_covfun_id(stationary_covfun), device = as.integer(device), layout = as.integer(layout),
+                      ctx_id = integer(1), status = integer(1), NAOK = TRUE))
+  res$ctx_id
+}
+
+# one stored sample conditionally simulated at the new sites (predict.R:43-53); z = rnorm(n_pred)
+nngp_predict_sample = function(ctx, n_obs_sites, field, beta_0, log_scale, z, slot = 0L)
+  nngp_check(.C("nngp_predict_sample", ctx_id = as.integer(ctx), slot = as.integer(slot), n_obs_sites = as.integer(n_obs_sites),
+                field = as.double(field), beta_0 = as.double(beta_0), log_scale = as.double(log_scale), z_pred = as.double(z),
+                out = double(length(z)), status = integer(1)))$out
