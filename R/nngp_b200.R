@@ -117,9 +117,7 @@ nngp_find_ordered_nn = function(locs, m)
   locs = as.matrix(locs)
   res = nngp_check(.C("nngp_host_find_ordered_nn", locs = as.double(locs), n = nrow(locs), d = ncol(locs), m = as.integer(m),
                       NNarray = integer(nrow(locs) * (m + 1)), status = integer(1), NAOK = TRUE))
-  NNarray = matrix(res$NNarray, nrow(locs), m + 1)
-  NNarray[NNarray == -2147483647L - 1L] = NA   # unreachable in practice: .C hands INT_MIN back as NA_integer_ already
-  NNarray
+  matrix(res$NNarray, nrow(locs), m + 1)   # INT_MIN comes back as NA_integer_, exactly like GpGp's NA slots
 }
 
 # context over the joint (observed ++ predicted) site set of mcmc_nngp_predict_field: no colouring (all zero), no observations
