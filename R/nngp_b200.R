@@ -136,3 +136,18 @@ nngp_predict_sample = function(ctx, n_obs_sites, field, beta_0, log_scale, z, sl
   nngp_check(.C("nngp_predict_sample", ctx_id = as.integer(ctx), slot = as.integer(slot), n_obs_sites = as.integer(n_obs_sites),
                 field = as.double(field), beta_0 = as.double(beta_0), log_scale = as.double(log_scale), z_pred = as.double(z),
                 out = double(length(z)), status = integer(1)))$out
+
+# Replaces the crossprod() moral graph + naive_greedy_coloring of mcmc_nngp_initialize.R:103-110 / Coloring.R:2-20 (the R loop
+# needs an (n+1) x maxdeg double scratch: 2.2 GB at n = 1M, ~47 GB at n = 10M): identical colours, O(nnz) memory.
+# In mcmc_nngp_initialize:   vecchia_approx$coloring = nngp_greedy_coloring(vecchia_approx$NNarray)
+nngp_greedy_coloring = function(NNarray)
+  nngp_check(.C("nngp_host_greedy_coloring", NNarray = as.integer(NNarray), n = nrow(NNarray), m = as.integer(ncol(NNarray) - 1L),
+                coloring = integer(nrow(NNarray)), n_colors = integer(1), status = integer(1), NAOK = TRUE))$coloring
+
+# exact farthest-point ("max-min") ordering; GpGp::order_maxmin (initialize.R:29) is a randomised approximation of it, so the
+# two orderings differ -- any ordering is valid for the model, and an ordering computed by GpGp can be used unchanged
+nngp_order_maxmin = function(locs)
+{
+  locs = as.matrix(locs)
+  nngp_check(.C("nngp_host_order_maxmin", locs = as.double(locs), n = nrow(locs), d = ncol(locs), order = integer(nrow(locs)), status = integer(1)))$order
+}
