@@ -52,7 +52,7 @@ nngp_factor_get = function(ctx, n, m, slot = 0L)
 
 nngp_field_set = function(ctx, field) invisible(nngp_check(.C("nngp_field_set", ctx_id = as.integer(ctx), field = as.double(field), status = integer(1))))
 nngp_field_get = function(ctx, n) nngp_check(.C("nngp_field_get", ctx_id = as.integer(ctx), field = double(n), status = integer(1)))$field
-nngp_obs_set = function(ctx, y_minus_xb) invisible(nngp_check(.C("nngp_obs_set", ctx_id = as.integer(ctx), y = as.double(y_minus_xb), status = integer(1))))
+nngp_obs_set = function(ctx, y_minus_xb) invisible(nngp_check(.C("nngp_obs_set", ctx_id = as.integer(ctx), y_minus_xb = as.double(y_minus_xb), status = integer(1))))
 
 # ll_compressed_sparse_chol(Linv, field - beta_0, NNarray, log_scale) on the device-resident field
 nngp_loglik = function(ctx, beta_0, log_scale, slot = 0L)
