@@ -12,7 +12,7 @@ import numpy as np
 
 NA_INT = -2147483648
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(PKG_DIR, "libnngp_b200.so")
+SO_PATH = os.path.join(os.path.dirname(PKG_DIR), "lib", "libnngp_b200.so")   # built in-tree by build.py
 
 COVFUN_IDS = {
     "exponential_isotropic": 0, "exponential_sphere": 1, "exponential_scaledim": 2, "exponential_spacetime": 3,
@@ -29,7 +29,9 @@ ABI_SYMBOLS = [
     "nngp_factor_get", "nngp_factor_accept", "nngp_factor_commit", "nngp_precision_diag", "nngp_field_set",
     "nngp_field_get", "nngp_obs_set", "nngp_loglik", "nngp_loglik_host", "nngp_spmv", "nngp_sptmv", "nngp_sptrsv",
     "nngp_gibbs_sweep", "nngp_ancillary_propose", "nngp_ancillary_accept", "nngp_beta0_moments", "nngp_ssr",
-    "nngp_field_init", "nngp_chain_run", "nngp_regressors_set", "nngp_chain_run_regressors", "nngp_records_summary", "nngp_predict_sample", "nngp_time_op", "nngp_launch_count", "nngp_debug_timeline", "nngp_debug_colour_times", "nngp_debug_colour_phases", "nngp_host_alloc", "nngp_host_free",
+    "nngp_field_init", "nngp_chain_run", "nngp_regressors_set", "nngp_chain_run_regressors", "nngp_records_summary", "nngp_predict_sample", "nngp_time_op", "nngp_launch_count", "nngp_host_alloc", "nngp_host_free",
+    "nngp_host_spatial_blocks", "nngp_host_shard_plan_build", "nngp_host_shard_plan_get", "nngp_shard_connect_local", "nngp_shard_group_sweep",
+    "nngp_shard_group_loglik",
 ]
 
 
@@ -51,6 +53,9 @@ def load():
                 f"{SO_PATH} is missing: build it with `python {os.path.join(PKG_DIR, 'build.py')}` "
                 "(the NNGP hot path has no CPU fallback)")
         _lib = C.CDLL(SO_PATH)
+        if os.environ.get("NNGP_QUIET") is None:   # one line so that a run's log shows which native library served it
+            import sys
+            print(f"[nngp_b200] loaded {os.path.realpath(SO_PATH)}", file=sys.stderr, flush=True)
     return _lib
 
 

@@ -63,20 +63,8 @@ class NNGPContext:
         getattr(L.load(), name)(L.ci(self._id), *args, C.byref(st))
         L.check(st)
 
-    OPTIONS = {"sweep_variant": 1, "solve_variant": 2, "use_graph": 3, "solve_ctas_per_sm": 4, "solve_sleep_ns": 5, "debug_timeline": 6, "solve_window_ctas": 7, "commit_variant": 8, "matern_table": 9, "loglik_variant": 10, "factor_variant": 11, "chain_sleep_ns": 12}
-
-    def debug_colour_times(self) -> np.ndarray:
-        """[K][4] ns stamps of the last PDL-chain sweep (debug_timeline = 1, sweep_variant = 6): last CTA at the wait,
-        first CTA released, first CTA done, last CTA done."""
-        out = np.zeros(4 * self.n_colors)
-        self._call("nngp_debug_colour_times", L.dptr(out))
-        return out.reshape(-1, 4)
-
-    def debug_colour_phases(self) -> np.ndarray:
-        """[K][8]: ns summed over a colour's CTAs in [stream, wait, gather, reduce, scatter, -, -, n_ctas] (same run as above)."""
-        out = np.zeros(16 * self.n_colors)
-        self._call("nngp_debug_colour_phases", L.dptr(out))
-        return out.reshape(-1, 16)
+    OPTIONS = {"sweep_variant": 1, "solve_variant": 2, "use_graph": 3, "solve_ctas_per_sm": 4, "solve_sleep_ns": 5,
+               "solve_window_ctas": 7, "commit_variant": 8, "matern_table": 9, "loglik_variant": 10}
 
     def set_option(self, name: str, value: int):
         self._call("nngp_ctx_set_option", L.ci(self.OPTIONS[name]), L.ci(value))
@@ -270,16 +258,6 @@ class NNGPContext:
         return ms, nl.value
 
 
-def debug_timeline():
-    """(time_ns, stage) stamps of CTA 0 from the last persistent sweep launch (development aid)."""
-    out = np.zeros(2 * 8190)
-    nw, st = C.c_int(0), C.c_int(0)
-    L.load().nngp_debug_timeline(L.dptr(out), L.ci(out.size), C.byref(nw), C.byref(st))
-    L.check(st)
-    return out[: 2 * nw.value].reshape(-1, 2)
-
-
-# ---- host set-up utilities (init-time code of the reference)
 def find_ordered_nn(locs, m) -> np.ndarray:
     """GpGp::find_ordered_nn replacement (Scripts/mcmc_nngp_initialize.R:93): exact, ties by lower index."""
     locs = np.asarray(locs, dtype=np.float64)

@@ -627,55 +627,6 @@ __global__ void __launch_bounds__(256) transpose_values_kernel(const int *__rest
     }
 }
 
-__device__ __forceinline__ double segment_sum(const double *__restrict__ sh, int k0, int k1);
-
-// Tiled form of the same pass (production path): the CSC entry stream of a tile is read flat and coalesced (csrc), values
-// are gathered from the slot-major factor, written back coalesced (valT), and squared into shared memory where one thread per
-// site reduces its segment.  Thread-per-column walking was LSU-wavefront bound (190 us at n = 1M).
-template <int THREADS, int EPT>
-__global__ void __launch_bounds__(THREADS) transpose_tile_kernel(const int4 *__restrict__ tiles, const int *__restrict__ colptr,
-                                                                 const int *__restrict__ csrc, const double *__restrict__ linv,
-                                                                 double *__restrict__ valT, double *__restrict__ pd) {
-    constexpr int ECAP = THREADS * EPT;
-    __shared__ double ssq[ECAP];
-    const int tid = threadIdx.x;
-    const int4 tile = tiles[blockIdx.x];
-    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
-    if (e1 - e0 > ECAP) {   // single site with an oversize column
-        double acc[1] = {0.0};
-        for (int e = e0 + tid; e < e1; e += THREADS) {
-            const double v = linv[csrc[e]];
-            valT[e] = v;
-            acc[0] += v * v;
-        }
-        block_reduce_sum<1>(acc);
-        if (tid == 0) pd[s0] = acc[0];
-        return;
-    }
-    int src[EPT];
-#pragma unroll
-    for (int k = 0; k < EPT; k++) {
-        const int e = e0 + k * THREADS + tid;
-        src[k] = (e < e1) ? csrc[e] : -1;
-    }
-    double v[EPT];
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (src[k] >= 0) v[k] = linv[src[k]];
-#pragma unroll
-    for (int k = 0; k < EPT; k++) {
-        if (src[k] >= 0) {
-            valT[e0 + k * THREADS + tid] = v[k];
-            ssq[k * THREADS + tid] = v[k] * v[k];
-        }
-    }
-    __syncthreads();
-    if (tid < s1 - s0) {
-        const int q = s0 + tid;
-        pd[q] = segment_sum(ssq, colptr[q] - e0, colptr[q + 1] - e0);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // level-scheduled sparse triangular solve: rows of one level (or, single-block variant, of a run of narrow levels)
 //   x_q = (b_q - sum_{j>=1} linv[j,q] x[nn[j,q]]) / linv[0,q]
@@ -881,22 +832,6 @@ __device__ __forceinline__ double sweep_normal(const SweepParams &sp, const doub
 // (algebraically identical to update_Gaussian.R:264-273; differs from the literal order of operations by FP64 rounding)
 struct SiteConst { double c0, c1, f_old; };
 
-// sum of a contiguous shared-memory segment with four independent accumulators: the per-site loop is a chain of dependent
-// LDS (29 cycles) + DADD; at a column length of 30-40 (the longest lane of a warp sets the pace) the plain loop cost 1.4 us
-// per tile in the %globaltimer timeline of the persistent kernel
-__device__ __forceinline__ double segment_sum(const double *__restrict__ sh, int k0, int k1) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int k = k0;
-    for (; k + 4 <= k1; k += 4) {
-        a0 += sh[k];
-        a1 += sh[k + 1];
-        a2 += sh[k + 2];
-        a3 += sh[k + 3];
-    }
-    for (; k < k1; k++) a0 += sh[k];
-    return (a0 + a1) + (a2 + a3);
-}
-
 __device__ __forceinline__ SiteConst site_const(const SweepParams &sp, double f_old, double Qss, double no, double Sq, double z) {
     SiteConst sc;
     const double w_old = f_old - sp.beta0;
@@ -935,161 +870,6 @@ __global__ void __launch_bounds__(256) gibbs_color_kernel(const int *__restrict_
     const double delta = (f_new - sp.beta0) - w_old;
     for (int k = k0; k < k1; k++) r[crow[k]] += valT[k] * delta;
     field[sq] = f_new;
-}
-
-// Tiled variant (the production path).  A CTA owns a tile = a run of consecutive same-colour sites whose CSC entries
-// [e0, e1) are contiguous; the host packs tiles with <= THREADS sites and <= THREADS*EPT entries.
-//   phase 1: every thread loads EPT entries of the flat entry stream (val, row: fully coalesced), gathers r[row] and leaves
-//            val*r in shared memory;  val / row / r stay in registers
-//   phase 2: one thread per site sums its segment of shared memory, draws the site, overwrites the segment with delta
-//   phase 3: every thread scatters r[row] = r_old + val*delta for the entries it still holds (no second read of r)
-// Compared with the thread-per-site form this turns 2x(m+1) strided loads per site into coalesced 128/256 B transactions
-// and halves the traffic on r.
-// PDL = true: the launch carries cudaLaunchAttributeProgrammaticStreamSerialization (programmatic dependent launch).
-// The kernel releases its dependents immediately (griddepcontrol.launch_dependents) and does everything that does not
-// depend on r -- entry stream, per-site constants, Philox + Box-Muller -- BEFORE griddepcontrol.wait, i.e. while the
-// previous colour's kernel is still running; only the r gather / segment sum / r scatter remain serialised per colour.
-__device__ __forceinline__ long long global_ns();
-template <int THREADS, int EPT, bool PDL, int MINB = 0, bool DBG = false>
-__global__ void __launch_bounds__(THREADS, MINB) gibbs_tile_kernel(const int4 *__restrict__ tiles, const int *__restrict__ colptr,
-                                                             const int *__restrict__ crow, const double *__restrict__ valT,
-                                                             const double *__restrict__ pd, const double *__restrict__ nobs,
-                                                             const double *__restrict__ S, const int *__restrict__ zpos,
-                                                             const int *__restrict__ gid, const int *__restrict__ psite,
-                                                             const double *__restrict__ zbuf,
-                                                             const SweepParams *__restrict__ spp, double *__restrict__ field,
-                                                             double *__restrict__ r, long long *ts = nullptr, int col = 0) {
-    constexpr int ECAP = THREADS * EPT;
-    __shared__ double sprod[ECAP];
-    __shared__ double sbc[2];
-    const int tid = threadIdx.x;
-    const int4 tile = tiles[blockIdx.x];
-    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
-    const SweepParams sp = *spp;
-    long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tqa = 0, tqb = 0, tqc = 0;   // DBG: per-CTA phase clock (thread 0)
-    if (DBG) {
-        tq0 = global_ns();
-        asm volatile("" ::"r"(s0), "r"(s1), "r"(e0), "r"(e1), "d"(sp.beta0) : "memory");   // descriptor + parameters landed
-        tqa = global_ns();
-    }
-    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (e1 - e0 > ECAP) {
-        // a single site whose column does not fit the tile (pathological fan-out): whole-CTA reduction
-        const int q = s0;
-        if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
-        double acc[1] = {0.0};
-        for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * r[crow[e]];
-        block_reduce_sum<1>(acc);
-        if (tid == 0) {
-            const int sq = psite[q];
-            const double w_old = field[sq] - sp.beta0;
-            const double Qss = pd[q], no = nobs[q];
-            const double prec = sp.e_ls * Qss + sp.e_ln * no;
-            const double t = acc[0] - Qss * w_old;
-            const double resid = S[q] - no * sp.beta0;
-            const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
-            const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
-            sbc[0] = (f_new - sp.beta0) - w_old;
-            field[sq] = f_new;
-        }
-        __syncthreads();
-        const double delta = sbc[0];
-        for (int e = e0 + tid; e < e1; e += THREADS) r[crow[e]] += valT[e] * delta;
-        return;
-    }
-    double val[EPT], rr[EPT];
-    int row[EPT];
-#pragma unroll
-    for (int k = 0; k < EPT; k++) {
-        const int e = e0 + k * THREADS + tid;
-        if (e < e1) {
-            val[k] = valT[e];
-            row[k] = crow[e];
-        } else {
-            val[k] = 0.0;
-            row[k] = -1;
-        }
-    }
-    int k0 = 0, k1 = 0, sq = 0;
-    SiteConst sc{0.0, 0.0, 0.0};
-    if (!PDL) {
-#pragma unroll
-        for (int k = 0; k < EPT; k++)
-            if (row[k] >= 0) rr[k] = r[row[k]];
-    }
-    // r-independent part of the site update (Philox + Box-Muller, 1/prec, sqrt): overlaps with the gathers in flight
-    // (or, under PDL, with the previous colour's kernel)
-    if (DBG) {
-        if (tid < s1 - s0) {
-            const int q = s0 + tid;
-            k0 = colptr[q] - e0;
-            k1 = colptr[q + 1] - e0;
-            sq = psite[q];
-            const double f_old = field[sq], pdq = pd[q], nq = nobs[q], Sq = S[q];
-            const int gq = gid[q];
-            asm volatile("" ::"r"(k0), "r"(k1), "d"(f_old), "d"(pdq), "d"(nq), "d"(Sq), "r"(gq) : "memory");   // site loads landed
-            tqb = global_ns();
-            sc = site_const(sp, f_old, pdq, nq, Sq, sweep_normal(sp, zbuf, zpos, gid, q));
-            asm volatile("" ::"d"(sc.c0), "d"(sc.c1) : "memory");   // draw + constants computed
-            tqc = global_ns();
-        }
-    } else if (tid < s1 - s0) {
-        const int q = s0 + tid;
-        k0 = colptr[q] - e0;
-        k1 = colptr[q + 1] - e0;
-        sq = psite[q];
-        sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
-    }
-    if (PDL) {
-        if (DBG) {   // force the stream loads to land before the stamp (debug build only)
-            int chk = 0;
-#pragma unroll
-            for (int k = 0; k < EPT; k++) chk ^= row[k] ^ (int)__double_as_longlong(val[k]);
-            if (chk == 0x7ffffff1 && sc.c0 == 123.456) sbc[1] = 1.0;
-            tq1 = global_ns();
-        }
-        if (DBG && tid == 0) atomicMax((unsigned long long *)ts + col * 4 + 0, (unsigned long long)global_ns());   // last CTA ready to wait
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (DBG) tq2 = global_ns();
-        if (DBG && tid == 0) atomicMin((unsigned long long *)ts + col * 4 + 1, (unsigned long long)global_ns());   // first CTA released
-#pragma unroll
-        for (int k = 0; k < EPT; k++)
-            if (row[k] >= 0) rr[k] = r[row[k]];
-    }
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) sprod[k * THREADS + tid] = val[k] * rr[k];
-    __syncthreads();
-    if (DBG) tq3 = global_ns();
-    if (tid < s1 - s0) {
-        const double a = segment_sum(sprod, k0, k1);
-        const double f_new = sc.c0 - sc.c1 * a;
-        const double delta = f_new - sc.f_old;
-        for (int k = k0; k < k1; k++) sprod[k] = delta;
-        field[sq] = f_new;
-    }
-    __syncthreads();
-    if (DBG) tq4 = global_ns();
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) r[row[k]] = rr[k] + val[k] * sprod[k * THREADS + tid];
-    if (DBG && tid == 0) {   // development aid (NNGP_OPT_DEBUG_TIMELINE): first / last CTA past its scatter
-        const unsigned long long t = (unsigned long long)global_ns();
-        atomicMin((unsigned long long *)ts + col * 4 + 2, t);
-        atomicMax((unsigned long long *)ts + col * 4 + 3, t);
-        // per-CTA phase durations, summed over the colour's CTAs: [stream+consts, wait, gather+products, reduce, scatter issue, n]
-        unsigned long long *acc = (unsigned long long *)ts + 4096 + col * 16;
-        atomicAdd(acc + 8, (unsigned long long)(tqa - tq0));
-        atomicAdd(acc + 9, (unsigned long long)(tqb - tqa));
-        atomicAdd(acc + 10, (unsigned long long)(tqc - tqb));
-        atomicAdd(acc + 11, (unsigned long long)(tq1 - tqc));
-        atomicAdd(acc + 0, (unsigned long long)(tq1 - tq0));
-        atomicAdd(acc + 1, (unsigned long long)(tq2 - tq1));
-        atomicAdd(acc + 2, (unsigned long long)(tq3 - tq2));
-        atomicAdd(acc + 3, (unsigned long long)(tq4 - tq3));
-        atomicAdd(acc + 4, (unsigned long long)((long long)t - tq4));
-        atomicAdd(acc + 7, 1ull);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1180,35 +960,103 @@ template <int HINT> __device__ __forceinline__ unsigned int ld_stream_u8(const u
     return v;
 }
 
-// PF: the CTA first asks the L2 for tile(s) of the NEXT colour (prefetch.global.L2 of the entry streams and per-site
-// constants).  With 5 CTAs/SM a large colour fills every slot of the chip, so the next colour's CTAs only become resident -- and
-// only then start streaming their ~13 KB of one-touch data from DRAM -- when this colour's CTAs exit: programmatic dependent
-// launch cannot overlap that prologue.  The prefetch moves the DRAM latency + transfer of colour c+1 under colour c's
-// gather / reduce / scatter phases, during which DRAM is idle (r and field are L2-resident).
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// ---------------------------------------------------------------------------------------------------------------
+// Sharded field: peers' receive areas, mapped through CUDA IPC (one process per GPU) or addressed directly
+// (several contexts in one process).  Area layout (doubles; the header is the same on every rank):
+//   [ 16 halo flags (u64) | 16 reduction flags | 2 x 32 reduction slots | receive values, parity 0 | receive values, parity 1 ]
+// ---------------------------------------------------------------------------------------------------------------
+struct PeerTable { double *area[8]; };   // peers' areas (own entry = own area)
 
-template <int THREADS>
-__device__ __forceinline__ void prefetch_tile(const int4 t, const unsigned char *__restrict__ tloc, const int *__restrict__ colptr,
-                                              const int *__restrict__ crow, const double *__restrict__ valT, const double *__restrict__ pd,
-                                              const double *__restrict__ nobs, const double *__restrict__ S, const int *__restrict__ psite,
-                                              const int *__restrict__ gid) {
-    const int tid = threadIdx.x;
-    const int ne = t.w - t.z, ns = t.y - t.x;
-    if (ne > THREADS * 8) return;                                   // oversize single-site tile: not worth it
-    for (int o = tid * 16; o < ne + 15; o += THREADS * 16) prefetch_l2(valT + t.z + min(o, ne - 1));      // 128-byte lines of doubles
-    for (int o = tid * 32; o < ne + 31; o += THREADS * 32) prefetch_l2(crow + t.z + min(o, ne - 1));
-    if (tid < 8) prefetch_l2(tloc + tid * 128);
-    for (int o = tid * 16; o < ns + 15; o += THREADS * 16) {
-        const int q = t.x + min(o, ns - 1);
-        prefetch_l2(pd + q); prefetch_l2(nobs + q); prefetch_l2(S + q);
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// per-context constants of a sharded sweep
+struct ShardConst {
+    PeerTable peers;
+    const int *bptr;              // [n_owned + 1] by processing id: destinations of a boundary site's value (empty for interior sites)
+    const int2 *bdst;             // (peer, offset inside the peer's receive values of one parity)
+    const int *gsite;             // ghost sites (processing ids) in receive order
+    unsigned long long *state;    // [0] sweeps completed since the peers were connected; [1 + colour] boundary tiles done
+    int *err;
+    int world, rank, K;
+    unsigned int flag_off, val_off, parity_stride;   // in doubles
+};
+// per-colour launch parameters of a sharded sweep
+struct ShardColour {
+    int n_tiles, n_btiles;        // tiles of the colour on this rank; the first n_btiles hold its boundary sites
+    int g0, g1;                   // this colour's ghost sites: [g0, g1) of the receive order
+    unsigned int send_mask, recv_mask;   // peers that ghost sites of this rank / own ghosts of this rank in this colour
+    int col;
+};
+
+// Ghost CTAs of the sweep kernel (blockIdx.x >= n_tiles): wait for the flags of the peers that own ghost sites of this colour,
+// then replace the ghost values and patch r along the ghost sites' local columns, one warp per ghost site.  Ghost sites of
+// colour c never share a row with owned sites of colour c (the colouring is proper), so this runs concurrently with the tiles.
+template <bool PDL>
+__device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const ShardColour &cl, const int *__restrict__ colptr,
+                                                  const int *__restrict__ crow, const double *__restrict__ valT,
+                                                  const int *__restrict__ psite, double *field, double *r) {
+    const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(sc.state);
+    const unsigned long long target = epoch * (unsigned long long)sc.K + (unsigned long long)cl.col + 1ull;
+    if ((int)threadIdx.x < sc.world && ((cl.recv_mask >> threadIdx.x) & 1u)) {
+        const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(sc.peers.area[sc.rank] + sc.flag_off);
+        unsigned int spins = 0;
+        while (ld_acquire_sys_u64(flags + threadIdx.x) < target) {
+            if (++spins > (1u << 24)) { atomicExch(sc.err, 2); break; }   // a peer died: report instead of hanging the box
+        }
     }
-    for (int o = tid * 32; o < ns + 31; o += THREADS * 32) {
-        const int q = t.x + min(o, ns - 1);
-        prefetch_l2(colptr + q); prefetch_l2(psite + q); prefetch_l2(gid + q);
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");   // r / field of the previous colour are complete
+    __syncthreads();
+    const double *vals = sc.peers.area[sc.rank] + sc.val_off + (size_t)(epoch & 1ull) * sc.parity_stride;
+    const int warps = (int)(blockDim.x >> 5), lane = threadIdx.x & 31;
+    const int n_gcta = (int)gridDim.x - cl.n_tiles;
+    for (int k = cl.g0 + ((int)blockIdx.x - cl.n_tiles) * warps + (int)(threadIdx.x >> 5); k < cl.g1; k += n_gcta * warps) {
+        const int p = sc.gsite[k];
+        const int sq = psite[p];
+        const double f_new = __ldcv(vals + k);   // written by a peer over NVLink: never from a stale cache line
+        const double delta = f_new - field[sq];
+        __syncwarp();
+        if (lane == 0) field[sq] = f_new;
+        for (int e = colptr[p] + lane; e < colptr[p + 1]; e += 32) r[crow[e]] += valT[e] * delta;
     }
 }
 
-template <int THREADS, bool PDL, int MINB, int HINT = 0, bool DBG = false, bool PF = false>
+// a boundary site's new value goes straight into the ghost slots of the peers that hold it (NVLink peer stores)
+__device__ __forceinline__ void shard_push_site(const ShardConst &sc, unsigned long long epoch, int q, double f_new) {
+    const size_t base = sc.val_off + (size_t)(epoch & 1ull) * sc.parity_stride;
+    for (int k = sc.bptr[q]; k < sc.bptr[q + 1]; k++) {
+        const int2 d = sc.bdst[k];
+        sc.peers.area[d.x][base + d.y] = f_new;
+    }
+}
+
+// called by thread 0 of a boundary tile after a CTA barrier that follows the tile's pushes: publish them system-wide, count the
+// tile, and -- last boundary tile of the colour -- raise this rank's flag on every peer that receives from it in this colour
+__device__ __forceinline__ void shard_tile_done(const ShardConst &sc, const ShardColour &cl, unsigned long long epoch) {
+    __threadfence_system();   // cumulative over the CTA barrier: every thread's peer stores are visible system-wide
+    unsigned long long *cnt = sc.state + 1 + cl.col;
+    const unsigned long long done = atomicAdd(cnt, 1ull) + 1ull;
+    if (done == (unsigned long long)cl.n_btiles) {
+        *cnt = 0ull;          // next sweep starts from zero (no tile of this colour touches it before then)
+        __threadfence_system();
+        const unsigned long long target = epoch * (unsigned long long)sc.K + (unsigned long long)cl.col + 1ull;
+        for (int h = 0; h < sc.world; h++)
+            if ((cl.send_mask >> h) & 1u)
+                st_release_sys_u64(reinterpret_cast<unsigned long long *>(sc.peers.area[h] + sc.flag_off) + sc.rank, target);
+    }
+}
+
+// SHARD: one spatial block of a larger field with the peer-to-peer transport.  The grid is [boundary tiles | interior tiles |
+// ghost CTAs]: boundary tiles come first, store their sites' new values directly into the peers' ghost slots and the last of
+// them raises this rank's flag there, so the NVLink hop overlaps the interior tiles; the ghost CTAs at the end of the grid
+// wait for the peers' flags and apply what arrived.  One launch per colour, same PDL chain as the unsharded sweep.
+template <int THREADS, bool PDL, int MINB, int HINT = 0, bool SHARD = false>
 __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *__restrict__ tiles, int tile_base,
                                                               const int *__restrict__ colptr, const int *__restrict__ crow,
                                                               const unsigned char *__restrict__ cloc,
@@ -1217,23 +1065,23 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
                                                               const int *__restrict__ zpos, const int *__restrict__ gid,
                                                               const int *__restrict__ psite, const double *__restrict__ zbuf,
                                                               const SweepParams *__restrict__ spp, double *__restrict__ field,
-                                                              double *__restrict__ r, long long *ts, int col, int n_next = 0) {
+                                                              double *__restrict__ r, const __grid_constant__ ShardConst sc, const __grid_constant__ ShardColour cl) {
     constexpr int EPT = 8;
     constexpr int ECAP = THREADS * EPT;
     __shared__ double sprod[ECAP + ECAP / 8];
     __shared__ double sstart[THREADS], shead[THREADS];
     __shared__ double sbc[2];
     const int tid = threadIdx.x;
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (SHARD && (int)blockIdx.x >= cl.n_tiles) {
+        shard_ghost_apply<PDL>(sc, cl, colptr, crow, valT, psite, field, r);
+        return;
+    }
+    const bool btile = SHARD && (int)blockIdx.x < cl.n_btiles;
+    const unsigned long long epoch = btile ? *reinterpret_cast<volatile unsigned long long *>(sc.state) : 0ull;
     const int4 tile = tiles[blockIdx.x];
     const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
     const SweepParams sp = *spp;
-    long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq5 = 0;   // DBG: per-CTA phase clock
-    if (DBG) tq0 = global_ns();
-    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (PF) {   // the next colour's tiles follow this colour's in the tile array: tiles[gridDim.x + j], j < n_next
-        for (int j = blockIdx.x; j < n_next; j += gridDim.x)
-            prefetch_tile<THREADS>(tiles[gridDim.x + j], cloc + (size_t)(tile_base + gridDim.x + j) * ECAP, colptr, crow, valT, pd, nobs, S, psite, gid);
-    }
     if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
         const int q = s0;
         if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1251,8 +1099,10 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
             const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
             sbc[0] = (f_new - sp.beta0) - w_old;
             field[sq] = f_new;
+            if (btile) shard_push_site(sc, epoch, q, f_new);
         }
         __syncthreads();
+        if (btile && tid == 0) shard_tile_done(sc, cl, epoch);
         const double delta = sbc[0];
         for (int e = e0 + tid; e < e1; e += THREADS) r[crow[e]] += valT[e] * delta;
         return;
@@ -1278,7 +1128,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
     const unsigned long long sid = reinterpret_cast<const unsigned long long *>(tloc)[tid];
     const unsigned int prev_last = tid > 0 ? (unsigned int)tloc[8 * tid - 1] : 255u;
     int k0 = 0, k1 = 0, sq = 0;
-    SiteConst sc{0.0, 0.0, 0.0};
+    SiteConst scn{0.0, 0.0, 0.0};
     if (!PDL) {
 #pragma unroll
         for (int k = 0; k < EPT; k++)
@@ -1286,33 +1136,13 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
     }
     if (tid < s1 - s0) {
         const int q = s0 + tid;
-        if (HINT == 3) {   // the per-site constants are one-touch streams too
-            k0 = ld_stream_s32<1>(colptr + q, pol) - e0;
-            k1 = ld_stream_s32<1>(colptr + q + 1, pol) - e0;
-            sq = ld_stream_s32<1>(psite + q, pol);
-            sc = site_const(sp, field[sq], ld_stream_f64<1>(pd + q, pol), ld_stream_f64<1>(nobs + q, pol), ld_stream_f64<1>(S + q, pol),
-                            sweep_normal(sp, zbuf, zpos, gid, q));
-        } else {
-            k0 = colptr[q] - e0;
-            k1 = colptr[q + 1] - e0;
-            sq = psite[q];
-            sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
-        }
+        k0 = colptr[q] - e0;
+        k1 = colptr[q + 1] - e0;
+        sq = psite[q];
+        scn = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
     }
     if (PDL) {
-        if (DBG) {   // force the prologue to finish before the stamp (debug build only)
-            int chk = 0;
-#pragma unroll
-            for (int k = 0; k < EPT; k++) chk ^= row[k] ^ (int)__double_as_longlong(val[k]) ^ (int)loc[k];
-            asm volatile("" ::"r"(chk), "d"(sc.c0), "d"(sc.c1), "l"(sid) : "memory");
-            tq1 = global_ns();
-            if (tid == 0) atomicMax((unsigned long long *)ts + col * 4 + 0, (unsigned long long)tq1);   // last CTA ready to wait
-        }
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (DBG) {
-            tq2 = global_ns();
-            if (tid == 0) atomicMin((unsigned long long *)ts + col * 4 + 1, (unsigned long long)tq2);   // first CTA released
-        }
 #pragma unroll
         for (int k = 0; k < EPT; k++)
             if (row[k] >= 0) rr[k] = (HINT >= 2) ? ld_keep_f64(r + row[k], keep) : r[row[k]];
@@ -1320,166 +1150,23 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
 #pragma unroll
     for (int k = 0; k < EPT; k++) sprod[NNGP_PADPOS(k * THREADS + tid)] = (row[k] >= 0) ? val[k] * rr[k] : 0.0;
     __syncthreads();
-    if (DBG) tq3 = global_ns();
     blocked_run_sums<THREADS>(sprod, sid, prev_last, sstart, shead);
     __syncthreads();
-    if (DBG) tq4 = global_ns();
     if (tid < s1 - s0) {
         const double a = blocked_site_sum(sstart, shead, tid, k0, k1);
-        const double f_new = sc.c0 - sc.c1 * a;
-        sstart[tid] = f_new - sc.f_old;   // delta, once per site (sstart[tid] was read by this thread only)
+        const double f_new = scn.c0 - scn.c1 * a;
+        sstart[tid] = f_new - scn.f_old;   // delta, once per site (sstart[tid] was read by this thread only)
         field[sq] = f_new;
+        if (btile) shard_push_site(sc, epoch, s0 + tid, f_new);
     }
     __syncthreads();
-    if (DBG) tq5 = global_ns();
+    if (btile && tid == 0) shard_tile_done(sc, cl, epoch);   // the flag leaves while the other threads scatter
 #pragma unroll
     for (int k = 0; k < EPT; k++)
         if (row[k] >= 0) {
             const double rn = rr[k] + val[k] * sstart[loc[k]];
             if (HINT >= 2) st_keep_f64(r + row[k], rn, keep); else r[row[k]] = rn;
         }
-    if (DBG && tid == 0) {
-        const unsigned long long t = (unsigned long long)global_ns();
-        atomicMin((unsigned long long *)ts + col * 4 + 2, t);
-        atomicMax((unsigned long long *)ts + col * 4 + 3, t);
-        unsigned long long *acc = (unsigned long long *)ts + 4096 + col * 16;
-        atomicAdd(acc + 0, (unsigned long long)(tq1 - tq0));   // prologue
-        atomicAdd(acc + 1, (unsigned long long)(tq2 - tq1));   // wait
-        atomicAdd(acc + 2, (unsigned long long)(tq3 - tq2));   // gather + products
-        atomicAdd(acc + 3, (unsigned long long)(tq5 - tq3));   // run sums + site update
-        atomicAdd(acc + 4, (unsigned long long)((long long)t - tq5));   // scatter issue
-        atomicAdd(acc + 8, (unsigned long long)(tq4 - tq3));   // run sums alone
-        atomicAdd(acc + 7, 1ull);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Fused tail of the sweep.  First-fit colour classes decay geometrically: the last few colours of a sweep hold a handful of
-// tiles (16, 1 and 1 at n = 1M, m = 10) yet each costs a full dependent stage of the PDL chain (~5 us: hand-off, gather,
-// sums, scatter drain).  All trailing colours with at most CLUSTER tiles run here in ONE launch of ONE thread-block cluster:
-// CTA j of the cluster owns tile j of every fused colour, colours are separated by the hardware cluster barrier
-// (barrier.cluster arrive.release / wait.acquire, a few hundred ns) instead of a kernel boundary, and the r-independent
-// prologue of the next colour (entry stream, per-site constants, draw) is issued between arrive and wait.  Because several
-// colours now share one kernel, r is gathered with ld.global.cg (L2 only: L1 lines from an earlier colour would be stale).
-// The kernel also advances the sweep counter (what advance_sweep_kernel does), saving that launch as well.
-// Arithmetic per tile is that of gibbs_tile2_kernel, so the results are bit-identical to the one-launch-per-colour chain.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double ld_cg_f64(const double *p) {
-    double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned int cluster_ctarank() {
-    unsigned int r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-
-template <int THREADS, bool PDL>
-__global__ void __launch_bounds__(THREADS) gibbs_tail_kernel(const int4 *__restrict__ tiles, const int *__restrict__ tile_ptr, int col_first,
-                                                             int K, const int *__restrict__ colptr, const int *__restrict__ crow,
-                                                             const unsigned char *__restrict__ cloc, const double *__restrict__ valT,
-                                                             const double *__restrict__ pd, const double *__restrict__ nobs,
-                                                             const double *__restrict__ S, const int *__restrict__ zpos,
-                                                             const int *__restrict__ gid, const int *__restrict__ psite,
-                                                             const double *__restrict__ zbuf, SweepParams *__restrict__ spp,
-                                                             double *__restrict__ field, double *__restrict__ r, unsigned long long n_advance) {
-    constexpr int EPT = 8;
-    constexpr int ECAP = THREADS * EPT;
-    __shared__ double sprod[ECAP + ECAP / 8];
-    __shared__ double sstart[THREADS], shead[THREADS];
-    __shared__ double sbc[2];
-    const int tid = threadIdx.x;
-    const int rank = (int)cluster_ctarank();
-    const SweepParams sp = *spp;
-    for (int col = col_first; col < K; col++) {
-        const int t = tile_ptr[col] + rank;
-        const bool has = t < tile_ptr[col + 1];          // uniform over the CTA
-        int s0 = 0, s1 = 0, e0 = 0, e1 = 0;
-        if (has) { const int4 tile = tiles[t]; s0 = tile.x; s1 = tile.y; e0 = tile.z; e1 = tile.w; }
-        const bool big = has && (e1 - e0 > ECAP);        // a single site whose column does not fit the tile
-        // ---- r-independent prologue (overlaps the previous colour's tail / the wait) ----
-        const unsigned char *tloc = cloc + (size_t)t * ECAP;
-        double val[EPT], rr[EPT];
-        int row[EPT];
-        unsigned int loc[EPT];
-        unsigned long long sid = 0ull;
-        unsigned int prev_last = 255u;
-        int k0 = 0, k1 = 0, sq = 0;
-        SiteConst sc{0.0, 0.0, 0.0};
-        if (has && !big) {
-#pragma unroll
-            for (int k = 0; k < EPT; k++) {
-                const int e = e0 + k * THREADS + tid;
-                loc[k] = tloc[k * THREADS + tid];
-                if (e < e1) { val[k] = valT[e]; row[k] = crow[e]; } else { val[k] = 0.0; row[k] = -1; }
-            }
-            sid = reinterpret_cast<const unsigned long long *>(tloc)[tid];
-            prev_last = tid > 0 ? (unsigned int)tloc[8 * tid - 1] : 255u;
-            if (tid < s1 - s0) {
-                const int q = s0 + tid;
-                k0 = colptr[q] - e0;
-                k1 = colptr[q + 1] - e0;
-                sq = psite[q];
-                sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
-            }
-        }
-        // ---- wait for the previous colour: the preceding launch (first fused colour) or the cluster barrier ----
-        if (col == col_first) {
-            if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
-        } else {
-            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-        }
-        if (big) {
-            const int q = s0;
-            double acc[1] = {0.0};
-            for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * ld_cg_f64(r + crow[e]);
-            block_reduce_sum<1>(acc);
-            if (tid == 0) {
-                const int sq1 = psite[q];
-                const double w_old = field[sq1] - sp.beta0;
-                const double Qss = pd[q], no = nobs[q];
-                const double prec = sp.e_ls * Qss + sp.e_ln * no;
-                const double tt = acc[0] - Qss * w_old;
-                const double resid = S[q] - no * sp.beta0;
-                const double mean = sp.beta0 - (1.0 / prec) * (tt * sp.e_ls - sp.e_ln * resid);
-                const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
-                sbc[0] = (f_new - sp.beta0) - w_old;
-                field[sq1] = f_new;
-            }
-            __syncthreads();
-            const double delta = sbc[0];
-            for (int e = e0 + tid; e < e1; e += THREADS) r[crow[e]] = ld_cg_f64(r + crow[e]) + valT[e] * delta;
-            __syncthreads();                              // sbc is reused by a later colour
-        } else if (has) {
-#pragma unroll
-            for (int k = 0; k < EPT; k++)
-                if (row[k] >= 0) rr[k] = ld_cg_f64(r + row[k]);
-#pragma unroll
-            for (int k = 0; k < EPT; k++) sprod[NNGP_PADPOS(k * THREADS + tid)] = (row[k] >= 0) ? val[k] * rr[k] : 0.0;
-            __syncthreads();
-            blocked_run_sums<THREADS>(sprod, sid, prev_last, sstart, shead);
-            __syncthreads();
-            if (tid < s1 - s0) {
-                const double a = blocked_site_sum(sstart, shead, tid, k0, k1);
-                const double f_new = sc.c0 - sc.c1 * a;
-                sstart[tid] = f_new - sc.f_old;
-                field[sq] = f_new;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < EPT; k++)
-                if (row[k] >= 0) r[row[k]] = rr[k] + val[k] * sstart[loc[k]];
-            __syncthreads();                              // sstart / sprod are rewritten by the next colour's reduction
-        }
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    }
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    // every CTA copied *spp before its first arrive and all of them have arrived: advance the counter / normals offset
-    if (rank == 0 && tid == 0 && n_advance != 0ull) {
-        spp->sweep_counter = sp.sweep_counter + 1ull;
-        spp->z_offset = sp.z_offset + n_advance;
-    }
 }
 
 // transposition + precision_diag with the same blocked reduction (see gibbs_tile2_kernel); csrc / linv are one-touch streams
@@ -1534,800 +1221,6 @@ __global__ void __launch_bounds__(THREADS) transpose_tile2_kernel(const int4 *__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Two-pass sweep: site_prepare_kernel + gibbs_tile3_kernel.
-// The %globaltimer phase profile of gibbs_tile_kernel (profiles/r01_pdl_phases_*.txt) shows a CTA living 6.4 us, of which 3.4 us
-// are the r-INDEPENDENT prologue: 1.6 us for the dependent loads colptr/psite -> field[psite] and 1.8 us for the serial FP64
-// chain of the draw (Philox, log, sincospi, sqrt, 1/prec, sqrt) -- executed by 93 of 128 threads while the CTA's registers
-// and its slot sit idle.  With 5 CTAs/SM this occupancy x latency product, not bandwidth, bounds the sweep.  All of that
-// work depends only on the state at the START of the sweep (a site's own field value does not change before its update),
-// so it moves to a full-occupancy streaming pass over all sites; the tile kernel then loads three doubles per site.
-//   c0, c1 as in SiteConst; f_old = field at the start of the sweep.
-// Chain: prepare -> tile(colour 1) -> tile(colour 2) ...  The first tile kernel triggers its dependents only AFTER its own
-// griddepcontrol.wait, so no later colour can start (and read c0/c1/f_old in its prologue) before the prepare pass is
-// complete and visible.
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) site_prepare_kernel(const double *__restrict__ pd, const double *__restrict__ nobs,
-                                                           const double *__restrict__ S, const int *__restrict__ zpos,
-                                                           const int *__restrict__ gid, const int *__restrict__ psite,
-                                                           const double *__restrict__ zbuf, const SweepParams *__restrict__ spp,
-                                                           const double *__restrict__ field, int n_sites,
-                                                           double *__restrict__ pc0, double *__restrict__ pc1,
-                                                           double *__restrict__ pf) {
-    const SweepParams sp = *spp;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_sites; q += gridDim.x * blockDim.x) {
-        const SiteConst sc = site_const(sp, field[psite[q]], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
-        pc0[q] = sc.c0;
-        pc1[q] = sc.c1;
-        pf[q] = sc.f_old;
-    }
-}
-
-template <int THREADS, bool FIRST, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) gibbs_tile3_kernel(const int4 *__restrict__ tiles, int tile_base,
-                                                                    const int *__restrict__ colptr, const int *__restrict__ crow,
-                                                                    const unsigned char *__restrict__ cloc,
-                                                                    const double *__restrict__ valT, const int *__restrict__ psite,
-                                                                    const double *pc0, const double *pc1, const double *pf,
-                                                                    double *__restrict__ field, double *__restrict__ r) {
-    constexpr int EPT = 8;
-    constexpr int ECAP = THREADS * EPT;
-    __shared__ double sprod[ECAP + ECAP / 8];
-    __shared__ double sstart[THREADS], shead[THREADS];
-    __shared__ double sbc[2];
-    const int tid = threadIdx.x;
-    const int4 tile = tiles[blockIdx.x];
-    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
-    if (!FIRST) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        if (FIRST) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        double acc[1] = {0.0};
-        for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * r[crow[e]];
-        block_reduce_sum<1>(acc);
-        if (tid == 0) {
-            const double f_new = pc0[s0] - pc1[s0] * acc[0];
-            sbc[0] = f_new - pf[s0];
-            field[psite[s0]] = f_new;
-        }
-        __syncthreads();
-        const double delta = sbc[0];
-        for (int e = e0 + tid; e < e1; e += THREADS) r[crow[e]] += valT[e] * delta;
-        return;
-    }
-    const unsigned char *tloc = cloc + (size_t)(tile_base + blockIdx.x) * ECAP;   // this tile's local site ids (255 = padding)
-    double val[EPT], rr[EPT];
-    int row[EPT];
-    unsigned int locp[2] = {0u, 0u};   // local site ids of this thread's entries, one byte each
-#pragma unroll
-    for (int k = 0; k < EPT; k++) {
-        const int e = e0 + k * THREADS + tid;
-        locp[k >> 2] |= (unsigned int)tloc[k * THREADS + tid] << (8 * (k & 3));
-        if (e < e1) {
-            val[k] = valT[e];
-            row[k] = crow[e];
-        } else {
-            val[k] = 0.0;
-            row[k] = -1;
-        }
-    }
-    const unsigned long long sid = reinterpret_cast<const unsigned long long *>(tloc)[tid];
-    const unsigned int prev_last = tid > 0 ? (unsigned int)tloc[8 * tid - 1] : 255u;
-    int k0 = 0, k1 = 0, sq = 0;
-    double c0 = 0.0, c1 = 0.0, f_old = 0.0;
-    const bool owner = tid < s1 - s0;
-    if (owner) {
-        const int q = s0 + tid;
-        k0 = colptr[q] - e0;
-        k1 = colptr[q + 1] - e0;
-        sq = psite[q];
-        if (!FIRST) { c0 = pc0[q]; c1 = pc1[q]; f_old = pf[q]; }
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (FIRST) {   // the prepare pass is complete only now
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        if (owner) { const int q = s0 + tid; c0 = pc0[q]; c1 = pc1[q]; f_old = pf[q]; }
-    }
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) rr[k] = r[row[k]];
-#pragma unroll
-    for (int k = 0; k < EPT; k++) sprod[NNGP_PADPOS(k * THREADS + tid)] = (row[k] >= 0) ? val[k] * rr[k] : 0.0;
-    __syncthreads();
-    blocked_run_sums<THREADS>(sprod, sid, prev_last, sstart, shead);
-    __syncthreads();
-    if (owner) {
-        const double a = blocked_site_sum(sstart, shead, tid, k0, k1);
-        const double f_new = c0 - c1 * a;
-        sstart[tid] = f_new - f_old;   // delta, once per site
-        field[sq] = f_new;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) r[row[k]] = rr[k] + val[k] * sstart[(locp[k >> 2] >> (8 * (k & 3))) & 0xffu];
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Flag-chained variant of the tile kernel.  The launches are still one per colour and still carry the programmatic
-// stream serialisation attribute, but the kernel NEVER executes griddepcontrol.wait: colour c+1 learns that colour c is
-// finished from a device counter instead of from the completion of the previous grid.
-//   * every CTA of colour c, after its last r store:  bar.sync ; red.release.gpu  cdone[c] += 1
-//   * every CTA of colour c+1, before its first r load: thread 0 spins on ld.acquire.gpu cdone[c] until it equals the
-//     number of tiles of colour c, then bar.sync
-// The hand-off therefore costs one L2 flag hop (0.4 us measured, scripts/microbench) instead of grid drain + memory flush +
-// dependent release (the ~6.7 us/colour floor of the griddepcontrol.wait chain).  No deadlock: the hardware starts grid
-// c+1 only after EVERY CTA of grid c has executed griddepcontrol.launch_dependents, i.e. is resident, so whatever a
-// spinning CTA waits for is always able to run.  r is read with ld.global.cg and written with st.global.cg: CTAs of two
-// colours share an SM, and there is no grid boundary between them to invalidate L1.  The counters are zeroed by the
-// ordinary launch that closes a sweep (advance_sweep_kernel).  A bounded spin raises *stuck instead of hanging the GPU.
-// ---------------------------------------------------------------------------------------------------------------
-#define NNGP_CHAIN_STRIDE 32   // one 128-byte line per colour counter
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p);
-__device__ __forceinline__ long long global_ns();
-
-// two_line = false: pollers spin on the arrival counter itself.  two_line = true: the CTA whose arrival completes the count
-// raises a separate "go" word (another 128-byte line), so that the ~10^3 spinning readers do not queue on the line the
-// arrivals' read-modify-writes are serialised on; costs the last arriver one extra L2 round trip.
-__device__ __forceinline__ void chain_wait(const unsigned int *cnt, unsigned int need, unsigned int sleep_ns, int *stuck) {
-    if (threadIdx.x == 0 && need > 0) {
-        if (ld_acquire_gpu_u32(cnt) < need) {
-            const long long t0 = global_ns();
-            unsigned int it = 0;
-            while (ld_acquire_gpu_u32(cnt) < need) {
-                if (sleep_ns) __nanosleep(sleep_ns);
-                if ((++it & 1023u) == 0 && global_ns() - t0 > 2000000000ll) { *stuck = 3; break; }
-            }
-        }
-    }
-    __syncthreads();
-}
-__device__ __forceinline__ void chain_arrive(unsigned int *cnt, unsigned int *go, unsigned int n_tiles, bool two_line) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (!two_line) {
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
-        } else {
-            unsigned int old;
-            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(cnt) : "memory");
-            if (old + 1u == n_tiles) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(n_tiles) : "memory");
-        }
-    }
-}
-
-template <int THREADS, int EPT>
-__global__ void __launch_bounds__(THREADS) gibbs_chain_kernel(const int4 *__restrict__ tiles, const int *__restrict__ colptr,
-                                                              const int *__restrict__ crow, const double *__restrict__ valT,
-                                                              const double *__restrict__ pd, const double *__restrict__ nobs,
-                                                              const double *__restrict__ S, const int *__restrict__ zpos,
-                                                              const int *__restrict__ gid, const int *__restrict__ psite,
-                                                              const double *__restrict__ zbuf,
-                                                              const SweepParams *__restrict__ spp, double *__restrict__ field,
-                                                              double *r, unsigned int *cdone, int col, int K, unsigned int need_prev,
-                                                              unsigned int sleep_ns, int two_line, int *stuck) {
-    constexpr int ECAP = THREADS * EPT;
-    __shared__ double sprod[ECAP];
-    __shared__ double sbc[2];
-    const int tid = threadIdx.x;
-    const int4 tile = tiles[blockIdx.x];
-    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
-    const SweepParams sp = *spp;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    // cdone[c * STRIDE] = arrivals of colour c; cdone[(K + c) * STRIDE] = its "go" word (two-line mode)
-    const unsigned int *prev = cdone + ((two_line ? K : 0) + (col > 0 ? col - 1 : 0)) * NNGP_CHAIN_STRIDE;
-    if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
-        const int q = s0;
-        chain_wait(prev, need_prev, sleep_ns, stuck);
-        double acc[1] = {0.0};
-        for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * __ldcg(r + crow[e]);
-        block_reduce_sum<1>(acc);
-        if (tid == 0) {
-            const int sq = psite[q];
-            const double w_old = field[sq] - sp.beta0;
-            const double Qss = pd[q], no = nobs[q];
-            const double prec = sp.e_ls * Qss + sp.e_ln * no;
-            const double t = acc[0] - Qss * w_old;
-            const double resid = S[q] - no * sp.beta0;
-            const double mean = sp.beta0 - (1.0 / prec) * (t * sp.e_ls - sp.e_ln * resid);
-            const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
-            sbc[0] = (f_new - sp.beta0) - w_old;
-            field[sq] = f_new;
-        }
-        __syncthreads();
-        const double delta = sbc[0];
-        for (int e = e0 + tid; e < e1; e += THREADS) __stcg(r + crow[e], __ldcg(r + crow[e]) + valT[e] * delta);
-        chain_arrive(cdone + col * NNGP_CHAIN_STRIDE, cdone + (K + col) * NNGP_CHAIN_STRIDE, gridDim.x, two_line != 0);
-        return;
-    }
-    double val[EPT], rr[EPT];
-    int row[EPT];
-#pragma unroll
-    for (int k = 0; k < EPT; k++) {
-        const int e = e0 + k * THREADS + tid;
-        if (e < e1) {
-            val[k] = valT[e];
-            row[k] = crow[e];
-        } else {
-            val[k] = 0.0;
-            row[k] = -1;
-        }
-    }
-    int k0 = 0, k1 = 0, sq = 0;
-    SiteConst sc{0.0, 0.0, 0.0};
-    if (tid < s1 - s0) {
-        const int q = s0 + tid;
-        k0 = colptr[q] - e0;
-        k1 = colptr[q + 1] - e0;
-        sq = psite[q];
-        sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
-    }
-    chain_wait(prev, need_prev, sleep_ns, stuck);
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) rr[k] = __ldcg(r + row[k]);
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) sprod[k * THREADS + tid] = val[k] * rr[k];
-    __syncthreads();
-    if (tid < s1 - s0) {
-        const double a = segment_sum(sprod, k0, k1);
-        const double f_new = sc.c0 - sc.c1 * a;
-        const double delta = f_new - sc.f_old;
-        for (int k = k0; k < k1; k++) sprod[k] = delta;
-        field[sq] = f_new;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) __stcg(r + row[k], rr[k] + val[k] * sprod[k * THREADS + tid]);
-    chain_arrive(cdone + col * NNGP_CHAIN_STRIDE, cdone + (K + col) * NNGP_CHAIN_STRIDE, gridDim.x, two_line != 0);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Dataflow sweep: ONE launch per sweep, no barrier between colours.  The colour order of the reference
-// (update_Gaussian.R:261) only constrains pairs of sites that are moral neighbours, i.e. pairs of TILES that touch a common
-// row of the factor.  ctx_create computes, for every tile, the earlier tiles it shares a row with and removes the pairs that
-// are implied by a two-step path (tile_dependencies, nngp_b200.cu): at n = 1M, m = 10 that leaves 6.9 predecessors per tile
-// (maximum 19), 99.8 % of them in the previous colour and a median of 660 tiles back in launch order.  A tile
-//   * streams its entries / per-site constants / draws exactly like gibbs_tile2_kernel (nothing there depends on r),
-//   * one thread per predecessor spins on that tile's flag (ld.acquire.gpu) until it carries this sweep's epoch,
-//   * gathers r (ld.global.cg: L1 is not coherent and there is no launch boundary any more), reduces, writes field,
-//     scatters r (st.global.cg), and publishes its own flag (bar.sync; fence; st.release.gpu).
-// Every pair of tiles that share a row is ordered by these flags (directly or through a chain), so RAW, WAR and WAW hazards
-// on r are all covered and the result is bit-identical to the colour-by-colour kernels.  Forward progress: tiles are
-// numbered colour-major and a tile only waits for lower-numbered tiles; with TICKET the tile number is drawn from a device
-// counter at CTA start (every lower number belongs to a CTA that is already resident), without it the kernel relies on the
-// hardware dispatching CTAs in blockIdx order (as the decoupled look-back scans do).  A bounded spin raises *stuck.
-// The epoch lives in flow[0] and is advanced by advance_sweep_kernel, so flags never need clearing.
-// ---------------------------------------------------------------------------------------------------------------
-#define NNGP_FLOW_STRIDE 8    // one 32-byte sector per tile flag
-#define NNGP_FLOW_HEADER 32   // flow[0] = epoch of the last completed sweep, flow[1] = ticket; flags start at flow[32]
-__device__ __forceinline__ double ld_cg_keep_f64(const double *p, unsigned long long pol) {
-    double v;
-    asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_cg_keep_f64(double *p, double v, unsigned long long pol) {
-    asm volatile("st.global.cg.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void flow_wait(const unsigned int *flags, const int *__restrict__ dep_idx, int d0, int d1,
-                                          unsigned int epoch, int *stuck) {
-    for (int k = d0 + (int)threadIdx.x; k < d1; k += (int)blockDim.x) {
-        const unsigned int *f = flags + (size_t)dep_idx[k] * NNGP_FLOW_STRIDE;
-        if (ld_acquire_gpu_u32(f) != epoch) {
-            const long long t0 = global_ns();
-            unsigned int it = 0;
-            while (ld_acquire_gpu_u32(f) != epoch)
-                if ((++it & 1023u) == 0 && global_ns() - t0 > 2000000000ll) { *stuck = 4; break; }
-        }
-    }
-    __syncthreads();
-}
-__device__ __forceinline__ void flow_publish(unsigned int *flag, unsigned int epoch) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-    }
-}
-
-template <int THREADS, int MINB, bool TICKET>
-__global__ void __launch_bounds__(THREADS, MINB) gibbs_flow_kernel(const int4 *__restrict__ tiles, const int *__restrict__ dep_ptr,
-                                                             const int *__restrict__ dep_idx, unsigned int *flow,
-                                                             const int *__restrict__ colptr, const int *__restrict__ crow,
-                                                             const unsigned char *__restrict__ cloc,
-                                                             const double *__restrict__ valT, const double *__restrict__ pd,
-                                                             const double *__restrict__ nobs, const double *__restrict__ S,
-                                                             const int *__restrict__ zpos, const int *__restrict__ gid,
-                                                             const int *__restrict__ psite, const double *__restrict__ zbuf,
-                                                             const SweepParams *__restrict__ spp, double *__restrict__ field,
-                                                             double *r, int *stuck) {
-    constexpr int EPT = 8;
-    constexpr int ECAP = THREADS * EPT;
-    __shared__ double sprod[ECAP + ECAP / 8];
-    __shared__ double sstart[THREADS], shead[THREADS];
-    __shared__ double sbc[2];
-    __shared__ int sticket;
-    const int tid = threadIdx.x;
-    int t = blockIdx.x;
-    if (TICKET) {
-        if (tid == 0) sticket = (int)atomicAdd(flow + 1, 1u);
-        __syncthreads();
-        t = sticket;
-    }
-    const int4 tile = tiles[t];
-    const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
-    const SweepParams sp = *spp;
-    const unsigned int epoch = flow[0] + 1u;
-    unsigned int *flags = flow + NNGP_FLOW_HEADER;
-    const int d0 = dep_ptr[t], d1 = dep_ptr[t + 1];
-    if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
-        const int q = s0;
-        flow_wait(flags, dep_idx, d0, d1, epoch, stuck);
-        double acc[1] = {0.0};
-        for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * __ldcg(r + crow[e]);
-        block_reduce_sum<1>(acc);
-        if (tid == 0) {
-            const int sq = psite[q];
-            const double w_old = field[sq] - sp.beta0;
-            const double Qss = pd[q], no = nobs[q];
-            const double prec = sp.e_ls * Qss + sp.e_ln * no;
-            const double tt = acc[0] - Qss * w_old;
-            const double resid = S[q] - no * sp.beta0;
-            const double mean = sp.beta0 - (1.0 / prec) * (tt * sp.e_ls - sp.e_ln * resid);
-            const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
-            sbc[0] = (f_new - sp.beta0) - w_old;
-            field[sq] = f_new;
-        }
-        __syncthreads();
-        const double delta = sbc[0];
-        for (int e = e0 + tid; e < e1; e += THREADS) __stcg(r + crow[e], __ldcg(r + crow[e]) + valT[e] * delta);
-        flow_publish(flags + (size_t)t * NNGP_FLOW_STRIDE, epoch);
-        return;
-    }
-    const unsigned char *tloc = cloc + (size_t)t * ECAP;   // this tile's local site ids (255 = padding)
-    const unsigned long long pol = l2_evict_first_policy();
-    const unsigned long long keep = l2_evict_last_policy();
-    double val[EPT], rr[EPT];
-    int row[EPT];
-    unsigned int loc[EPT];
-#pragma unroll
-    for (int k = 0; k < EPT; k++) {
-        const int e = e0 + k * THREADS + tid;
-        loc[k] = ld_stream_u8<true>(tloc + k * THREADS + tid, pol);
-        if (e < e1) {
-            val[k] = ld_stream_f64<true>(valT + e, pol);
-            row[k] = ld_stream_s32<true>(crow + e, pol);
-        } else {
-            val[k] = 0.0;
-            row[k] = -1;
-        }
-    }
-    const unsigned long long sid = reinterpret_cast<const unsigned long long *>(tloc)[tid];
-    const unsigned int prev_last = tid > 0 ? (unsigned int)tloc[8 * tid - 1] : 255u;
-    int k0 = 0, k1 = 0, sq = 0;
-    SiteConst sc{0.0, 0.0, 0.0};
-    if (tid < s1 - s0) {
-        const int q = s0 + tid;
-        k0 = colptr[q] - e0;
-        k1 = colptr[q + 1] - e0;
-        sq = psite[q];
-        sc = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
-    }
-    flow_wait(flags, dep_idx, d0, d1, epoch, stuck);
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) rr[k] = ld_cg_keep_f64(r + row[k], keep);
-#pragma unroll
-    for (int k = 0; k < EPT; k++) sprod[NNGP_PADPOS(k * THREADS + tid)] = (row[k] >= 0) ? val[k] * rr[k] : 0.0;
-    __syncthreads();
-    blocked_run_sums<THREADS>(sprod, sid, prev_last, sstart, shead);
-    __syncthreads();
-    if (tid < s1 - s0) {
-        const double a = blocked_site_sum(sstart, shead, tid, k0, k1);
-        const double f_new = sc.c0 - sc.c1 * a;
-        sstart[tid] = f_new - sc.f_old;   // delta, once per site (sstart[tid] was read by this thread only)
-        field[sq] = f_new;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (row[k] >= 0) st_cg_keep_f64(r + row[k], rr[k] + val[k] * sstart[loc[k]], keep);
-    flow_publish(flags + (size_t)t * NNGP_FLOW_STRIDE, epoch);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Dataflow sweep, persistent form with a TMA ring (gibbs_flow2_kernel).  gibbs_flow_kernel holds a tile's 1024 entries in
-// registers from the moment the CTA starts, so only 5 tiles per SM are in flight and ~4 us of every tile's 9 us life is the
-// dependent load chain descriptor -> entry stream (measured: scripts/timeline_pdl.py).  Here the grid is co-resident
-// (G = n_sm x CTAs/SM), CTA b owns tiles b, b+G, b+2G, ... of the colour-major list, and the one-touch streams of its next
-// STAGES tiles (factor values, row ids, local site ids: contiguous, 13 bytes per entry) are fetched by cp.async.bulk into a
-// shared-memory ring while the current tile is processed; registers hold only the 8 gathered r values per thread.  The
-// r-independent per-site constants of the NEXT tile are computed while the current tile's r gather is in flight.
-// Dependencies, flags, epoch and memory ordering are those of gibbs_flow_kernel.  Forward progress: every CTA works through
-// its tiles in increasing order and all CTAs are resident, so the lowest unfinished tile is always being worked on.
-// ---------------------------------------------------------------------------------------------------------------
-struct FlowSite { double c0, c1, f_old; int k0, k1, sq; };
-
-template <int THREADS, int STAGES, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) gibbs_flow2_kernel(const int4 *__restrict__ tiles, int n_tiles,
-                                                              const int *__restrict__ dep_ptr, const int *__restrict__ dep_idx,
-                                                              unsigned int *flow, const int *__restrict__ colptr,
-                                                              const int *__restrict__ crow, const unsigned char *__restrict__ cloc,
-                                                              const double *__restrict__ valT, const double *__restrict__ pd,
-                                                              const double *__restrict__ nobs, const double *__restrict__ S,
-                                                              const int *__restrict__ zpos, const int *__restrict__ gid,
-                                                              const int *__restrict__ psite, const double *__restrict__ zbuf,
-                                                              const SweepParams *__restrict__ spp, double *__restrict__ field,
-                                                              double *r, int *stuck) {
-    constexpr int EPT = 8;
-    constexpr int ECAP = THREADS * EPT;
-    constexpr int VAL_B = (ECAP + 2) * 8, ROW_B = (ECAP + 4) * 4, LOC_B = ECAP;   // one stage: values, rows, local ids
-    constexpr int STAGE_B = VAL_B + ROW_B + LOC_B;
-    extern __shared__ __align__(128) unsigned char flow_smem[];
-    double *sprod = reinterpret_cast<double *>(flow_smem + (size_t)STAGES * STAGE_B);       // [ECAP + ECAP / 8]
-    double *sstart = sprod + ECAP + ECAP / 8;                                                // [THREADS]
-    double *shead = sstart + THREADS;                                                        // [THREADS]
-    double *sbc = shead + THREADS;                                                           // [2]
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(sbc + 2);             // [STAGES]
-    const int tid = threadIdx.x;
-    const int G = (int)gridDim.x;
-    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + G - 1) / G : 0;
-    const SweepParams sp = *spp;
-    const unsigned int epoch = flow[0] + 1u;
-    unsigned int *flags = flow + NNGP_FLOW_HEADER;
-    const unsigned long long keep = l2_evict_last_policy();
-
-    auto issue = [&](int i, const int4 tl) {   // elected thread: stream tile i of this CTA into stage i % STAGES
-        const int stage = i % STAGES;
-        unsigned char *base = flow_smem + (size_t)stage * STAGE_B;
-        const int e0 = tl.z, e1 = tl.w;
-        if (e1 - e0 > ECAP) { mbar_arrive_expect_tx(full + stage, 0u); return; }   // oversize column: read straight from global
-        const int t = (int)blockIdx.x + i * G;
-        const int ev = e0 & ~1, er = e0 & ~3;   // 16-byte aligned starts; the arrays are padded past nnz
-        const unsigned int bv = (unsigned int)(((e1 - ev) * 8 + 15) & ~15), br = (unsigned int)(((e1 - er) * 4 + 15) & ~15);
-        mbar_arrive_expect_tx(full + stage, bv + br + (unsigned int)LOC_B);
-        tma_bulk_g2s(base, valT + ev, bv, full + stage);
-        tma_bulk_g2s(base + VAL_B, crow + er, br, full + stage);
-        tma_bulk_g2s(base + VAL_B + ROW_B, cloc + (size_t)t * ECAP, (unsigned int)LOC_B, full + stage);
-    };
-    auto site_part = [&](const int4 tl) {
-        FlowSite fs{0.0, 0.0, 0.0, 0, 0, 0};
-        if (tid < tl.y - tl.x && tl.w - tl.z <= ECAP) {
-            const int q = tl.x + tid;
-            fs.k0 = colptr[q] - tl.z;
-            fs.k1 = colptr[q + 1] - tl.z;
-            fs.sq = psite[q];
-            const SiteConst sc = site_const(sp, field[fs.sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
-            fs.c0 = sc.c0; fs.c1 = sc.c1; fs.f_old = sc.f_old;
-        }
-        return fs;
-    };
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) mbar_init(full + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    if (my_tiles == 0) return;
-    if (tid == 0)
-        for (int i = 0; i < STAGES && i < my_tiles; i++) issue(i, tiles[(int)blockIdx.x + i * G]);
-    int4 tile = tiles[blockIdx.x];
-    FlowSite cur = site_part(tile);
-
-    for (int i = 0; i < my_tiles; i++) {
-        const int stage = i % STAGES;
-        const int t = (int)blockIdx.x + i * G;
-        const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
-        // descriptors needed later in this iteration: the next tile (site constants) and the tile that refills this stage
-        const bool has_next = i + 1 < my_tiles, has_refill = i + STAGES < my_tiles;
-        int4 tile_next = make_int4(0, 0, 0, 0), tile_refill = make_int4(0, 0, 0, 0);
-        if (has_next) tile_next = tiles[t + G];
-        if (tid == 0 && has_refill) tile_refill = tiles[t + STAGES * G];
-        const int d0 = dep_ptr[t], d1 = dep_ptr[t + 1];
-        FlowSite nxt{0.0, 0.0, 0.0, 0, 0, 0};
-        mbar_wait(full + stage, (unsigned int)((i / STAGES) & 1));
-        if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction from global memory
-            const int q = s0;
-            flow_wait(flags, dep_idx, d0, d1, epoch, stuck);
-            double acc[1] = {0.0};
-            for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * __ldcg(r + crow[e]);
-            block_reduce_sum<1>(acc);
-            if (tid == 0) {
-                const int sq = psite[q];
-                const double w_old = field[sq] - sp.beta0;
-                const double Qss = pd[q], no = nobs[q];
-                const double prec = sp.e_ls * Qss + sp.e_ln * no;
-                const double tt = acc[0] - Qss * w_old;
-                const double resid = S[q] - no * sp.beta0;
-                const double mean = sp.beta0 - (1.0 / prec) * (tt * sp.e_ls - sp.e_ln * resid);
-                const double f_new = mean + sweep_normal(sp, zbuf, zpos, gid, q) / sqrt(prec);
-                sbc[0] = (f_new - sp.beta0) - w_old;
-                field[sq] = f_new;
-            }
-            __syncthreads();
-            const double delta = sbc[0];
-            for (int e = e0 + tid; e < e1; e += THREADS) __stcg(r + crow[e], __ldcg(r + crow[e]) + valT[e] * delta);
-            if (has_next) nxt = site_part(tile_next);
-        } else {
-            const unsigned char *base = flow_smem + (size_t)stage * STAGE_B;
-            const double *s_val = reinterpret_cast<const double *>(base) + (e0 & 1);
-            const int *s_row = reinterpret_cast<const int *>(base + VAL_B) + (e0 & 3);
-            const unsigned char *s_loc = base + VAL_B + ROW_B;
-            const int ne = e1 - e0;
-            flow_wait(flags, dep_idx, d0, d1, epoch, stuck);
-            double rr[EPT];
-#pragma unroll
-            for (int k = 0; k < EPT; k++) {
-                const int e = k * THREADS + tid;
-                rr[k] = (e < ne) ? ld_cg_keep_f64(r + s_row[e], keep) : 0.0;
-            }
-            if (has_next) nxt = site_part(tile_next);   // its loads travel with the gather
-#pragma unroll
-            for (int k = 0; k < EPT; k++) {
-                const int e = k * THREADS + tid;
-                sprod[NNGP_PADPOS(e)] = (e < ne) ? s_val[e] * rr[k] : 0.0;
-            }
-            const unsigned long long sid = reinterpret_cast<const unsigned long long *>(s_loc)[tid];
-            const unsigned int prev_last = tid > 0 ? (unsigned int)s_loc[8 * tid - 1] : 255u;
-            __syncthreads();
-            blocked_run_sums<THREADS>(sprod, sid, prev_last, sstart, shead);
-            __syncthreads();
-            if (tid < s1 - s0) {
-                const double a = blocked_site_sum(sstart, shead, tid, cur.k0, cur.k1);
-                const double f_new = cur.c0 - cur.c1 * a;
-                sstart[tid] = f_new - cur.f_old;   // delta, once per site (sstart[tid] was read by this thread only)
-                field[cur.sq] = f_new;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < EPT; k++) {
-                const int e = k * THREADS + tid;
-                if (e < ne) st_cg_keep_f64(r + s_row[e], rr[k] + s_val[e] * sstart[s_loc[e]], keep);
-            }
-        }
-        flow_publish(flags + (size_t)t * NNGP_FLOW_STRIDE, epoch);   // bar.sync inside: every thread is done with this stage
-        if (tid == 0 && has_refill) issue(i + STAGES, tile_refill);
-        tile = tile_next;
-        cur = nxt;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Persistent sweep kernel (the production path): ONE cooperative launch runs n_sweeps full sweeps.  The grid is
-// co-resident (cudaLaunchCooperativeKernel); colour classes are separated by a hand-rolled grid barrier (one atomic
-// arrival per CTA + acquire polling), not by kernel boundaries.  Every per-colour kernel launch cost ~10 us of pure latency
-// (descriptor -> colptr -> entry stream -> r gather, each a dependent DRAM/L2 round trip, ncu: 0.8 waves, 15 % DRAM);
-// here the stream of the NEXT colour's tile (descriptor, values, row ids, per-site constants: everything that does not
-// depend on r) is issued BEFORE the barrier and lands while the CTA waits, so that after the barrier only the r gather, the
-// per-site draw and the r scatter remain on the critical path.
-// r and field are accessed with ld.global.cg / st.global.cg (L2 only): L1 is not coherent across SMs and, unlike the
-// multi-launch form, there is no launch boundary to invalidate it.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// split grid barrier over a co-resident grid: arrive publishes this CTA's stores, wait blocks until `target` arrivals.
-// Work placed between the two calls (staging the next tile) overlaps with the other CTAs' arrival.
-__device__ __forceinline__ void grid_arrive(unsigned int *counter) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();   // cumulative over the CTA barrier above: every thread's r / field stores are visible gpu-wide
-        atomicAdd(counter, 1u);
-    }
-}
-__device__ __forceinline__ void grid_wait(unsigned int *counter, unsigned int target) {
-    if (threadIdx.x == 0) {
-        while (ld_acquire_gpu_u32(counter) < target) { }
-    }
-    __syncthreads();
-}
-
-struct SiteRaw { int k0, k1, gz, sq; double pd, nobs, S, f; };
-
-// optional in-kernel timeline (development aid, nngp_debug_timeline): CTA 0 stamps %globaltimer at the pipeline stages
-__device__ long long g_timeline[8192];
-__device__ __forceinline__ long long global_ns() {
-    long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-#define NNGP_STAMP(slot) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0 && tl_n < 4090) { g_timeline[2 * tl_n] = global_ns(); g_timeline[2 * tl_n + 1] = (slot); tl_n++; } } while (0)
-
-#define NNGP_PERSIST_CAP 512   // tiles one CTA may own per sweep (descriptor table in shared memory)
-
-template <int THREADS, int EPT>
-__global__ void __launch_bounds__(THREADS) gibbs_persistent_kernel(
-    const int4 *__restrict__ tiles, const int *__restrict__ tile_ptr, int K, int n_sweeps, unsigned long long sweep_counter0,
-    unsigned long long z_offset0, unsigned long long n_sites, const int *__restrict__ colptr, const int *__restrict__ crow,
-    const double *__restrict__ valT, const double *__restrict__ pd, const double *__restrict__ nobs, const double *__restrict__ S,
-    const int *__restrict__ zpos, const int *__restrict__ gid, const int *__restrict__ psite, const double *__restrict__ zbuf,
-    const SweepParams *__restrict__ spp, double *field, double *r, unsigned int *bar, int dbg) {
-    constexpr int ECAP = THREADS * EPT;
-    __shared__ double sprod[ECAP];
-    __shared__ double sbc[2];
-    int tl_n = 0;
-    // this CTA's tiles of one sweep, colour-major (tile j of colour c is tile_ptr[c] + blockIdx.x + j*gridDim.x), with their
-    // colour: descriptors never cost a dependent global load inside the pipeline
-    __shared__ int4 sdesc[NNGP_PERSIST_CAP];
-    __shared__ short scol[NNGP_PERSIST_CAP];
-    __shared__ int s_cnt[128];
-    const int tid = threadIdx.x;
-    const SweepParams sp = *spp;
-    const int G = (int)gridDim.x, bid = (int)blockIdx.x;
-    unsigned int arrivals = 0;
-
-    // ---- build the per-CTA tile list (host guarantees K <= 128 and list length <= NNGP_PERSIST_CAP) ----
-    for (int col = tid; col < K; col += THREADS) {
-        const int nt = tile_ptr[col + 1] - tile_ptr[col];
-        s_cnt[col] = nt > bid ? (nt - bid + G - 1) / G : 0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        for (int col = 0; col < K; col++) { const int c = s_cnt[col]; s_cnt[col] = acc; acc += c; }
-        s_cnt[K] = acc;   // K <= 127
-    }
-    __syncthreads();
-    const int n_my = s_cnt[K];
-    for (int col = 0; col < K; col++) {
-        const int base = s_cnt[col], cnt = s_cnt[col + 1] - base;
-        for (int j = tid; j < cnt; j += THREADS) {
-            sdesc[base + j] = tiles[tile_ptr[col] + bid + j * G];
-            scol[base + j] = (short)col;
-        }
-    }
-    __syncthreads();
-
-    // issue every r-independent load of a tile (entry stream + raw per-site data); nothing here waits
-    auto issue_loads = [&](const int4 &d, double (&v)[EPT], int (&rw)[EPT], SiteRaw &sr) {
-        const bool staged = (d.w - d.z) <= ECAP;
-#pragma unroll
-        for (int k = 0; k < EPT; k++) {
-            const int e = d.z + k * THREADS + tid;
-            if (staged && e < d.w) {
-                v[k] = valT[e];
-                rw[k] = crow[e];
-            } else {
-                v[k] = 0.0;
-                rw[k] = -1;
-            }
-        }
-        if (tid < d.y - d.x) {
-            const int q = d.x + tid;
-            sr.k0 = colptr[q] - d.z;
-            sr.k1 = colptr[q + 1] - d.z;
-            sr.pd = pd[q];
-            sr.nobs = nobs[q];
-            sr.S = S[q];
-            sr.gz = (sp.rng_mode == 0) ? zpos[q] : gid[q];
-            sr.sq = psite[q];
-            sr.f = __ldcg(field + sr.sq);   // only this thread ever writes this field entry in this launch (static tile -> CTA map)
-        }
-    };
-    auto make_const = [&](const SiteRaw &sr, unsigned long long sweep_idx) -> SiteConst {
-        const double z = (sp.rng_mode == 0)
-                             ? zbuf[z_offset0 + sweep_idx * n_sites + (unsigned long long)sr.gz]
-                             : philox_normal((uint32_t)sr.gz, (uint32_t)(sweep_counter0 + sweep_idx),
-                                             (uint32_t)((sweep_counter0 + sweep_idx) >> 32), sp.key0, sp.key1);
-        return site_const(sp, sr.f, sr.pd, sr.nobs, sr.S, z);
-    };
-    auto barrier = [&]() {
-        grid_arrive(bar);
-        arrivals += (unsigned int)G;
-        grid_wait(bar, arrivals);
-    };
-
-    if (n_my == 0) {   // cannot happen when G <= max tiles per colour, but stay in step with the grid if it does
-        for (int b = 0; b < n_sweeps * K; b++) barrier();
-        return;
-    }
-    // software pipeline: (val,row,sc,ks0,ks1,td) = current tile; (val2,row2,raw,tdn) = next tile, loads in flight
-    double val[EPT], val2[EPT];
-    int row[EPT], row2[EPT];
-    SiteRaw raw{0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0};
-    SiteConst sc{0.0, 0.0, 0.0};
-    int4 td = sdesc[0];
-    int ccol = scol[0];
-    issue_loads(td, val, row, raw);
-    int ks0 = raw.k0, ks1 = raw.k1, csq = raw.sq;
-    if (tid < td.y - td.x) sc = make_const(raw, 0ull);
-    for (int b = 0; b < ccol; b++) barrier();   // colours before this CTA's first tile
-
-    for (int sweep = 0; sweep < n_sweeps; sweep++) {
-        for (int i = 0; i < n_my; i++) {
-            // next tile of this CTA (same colour, a later colour, or the first tile of the next sweep)
-            int ni = i + 1, nsweep = sweep;
-            if (ni == n_my) { ni = 0; nsweep++; }
-            const bool has_next = nsweep < n_sweeps;
-            const int4 tdn = sdesc[ni];
-            const int ncol = scol[ni];
-            // colour boundaries to cross before the next tile may touch r (K barriers per sweep for every CTA)
-            const int nbar = has_next ? (nsweep == sweep ? ncol - ccol : K - ccol + ncol) : K - ccol;
-            const bool oversize = (td.w - td.z) > ECAP;
-            NNGP_STAMP(0);
-            // 1. the r gathers of the current tile go out first ...
-            double rr[EPT];
-            double f_new_mine = 0.0;
-            if (!oversize) {
-#pragma unroll
-                for (int k = 0; k < EPT; k++)
-                    if (row[k] >= 0) rr[k] = __ldcg(r + row[k]);
-            }
-            // 2. ... then the whole r-independent stream of the NEXT tile: it lands while this tile is finished
-            if (has_next) issue_loads(tdn, val2, row2, raw);
-            // 3. finish the current tile
-            if (oversize) {
-                // a single site whose column does not fit a tile (pathological fan-out): whole-CTA reduction from global
-                double acc[1] = {0.0};
-                for (int e = td.z + tid; e < td.w; e += THREADS) acc[0] += valT[e] * __ldcg(r + crow[e]);
-                block_reduce_sum<1>(acc);
-                if (tid == 0) {
-                    const double f_new = sc.c0 - sc.c1 * acc[0];
-                    sbc[0] = f_new - sc.f_old;
-                    __stcg(field + csq, f_new);
-                    f_new_mine = f_new;
-                }
-                __syncthreads();
-                const double delta = sbc[0];
-                for (int e = td.z + tid; e < td.w; e += THREADS) {
-                    const int rw = crow[e];
-                    __stcg(r + rw, __ldcg(r + rw) + valT[e] * delta);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < EPT; k++)
-                    if (row[k] >= 0) sprod[k * THREADS + tid] = val[k] * rr[k];
-                __syncthreads();
-                NNGP_STAMP(1);
-                if (tid < td.y - td.x) {
-                    const double a = segment_sum(sprod, ks0, ks1);
-                    const double f_new = sc.c0 - sc.c1 * a;
-                    const double delta = f_new - sc.f_old;
-                    for (int k = ks0; k < ks1; k++) sprod[k] = delta;
-                    __stcg(field + csq, f_new);
-                    f_new_mine = f_new;
-                }
-                __syncthreads();
-                NNGP_STAMP(2);
-#pragma unroll
-                for (int k = 0; k < EPT; k++)
-                    if (row[k] >= 0) __stcg(r + row[k], rr[k] + val[k] * sprod[k * THREADS + tid]);
-            }
-            // a CTA that owns a single tile stages that same tile again for the next sweep: its field value is the one
-            // just written, not the one read (too early) by issue_loads
-            if (n_my == 1) raw.f = f_new_mine;
-            // 4. publish (if a colour ends here), rotate the pipeline, and do the FP64-heavy r-independent site maths of
-            //    the next tile while the other CTAs arrive
-            if (nbar > 0) grid_arrive(bar); else __syncthreads();   // sprod is rewritten by the next tile
-            NNGP_STAMP(3);
-            td = tdn;
-            ccol = ncol;
-#pragma unroll
-            for (int k = 0; k < EPT; k++) {
-                val[k] = val2[k];
-                row[k] = row2[k];
-            }
-            ks0 = raw.k0;
-            ks1 = raw.k1;
-            csq = raw.sq;
-            if (has_next && tid < td.y - td.x) sc = make_const(raw, (unsigned long long)nsweep);
-            NNGP_STAMP(4);
-            if (nbar > 0) {
-                arrivals += (unsigned int)G;
-                grid_wait(bar, arrivals);
-                for (int b = 1; b < nbar; b++) barrier();
-            }
-        }
-    }
-    if (dbg && blockIdx.x == 0 && tid == 0) g_timeline[8191] = tl_n;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // halo exchange of a sharded field, one colour at a time: pack the new values of the owned boundary sites of
 // the colour, (NCCL send/recv between the two kernels), then apply what arrived to the local ghost copies: the ghost value
 // is replaced and r is patched along the ghost site's local column exactly as an owned update would have done.
@@ -2351,185 +1244,41 @@ __global__ void halo_apply_kernel(const int *__restrict__ recv_proc, const doubl
     for (int e = colptr[p]; e < colptr[p + 1]; e++) r[crow[e]] += valT[e] * delta;   // same-colour sites never share a row
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Peer-to-peer halo exchange (the production transport between the GPUs of one box): every rank maps its peers' receive
-// areas (CUDA IPC over NVLink / NVSwitch).  After a colour's sweep kernel, halo_push_kernel stores the new boundary values
-// STRAIGHT into the peers' ghost buffers, fences system-wide and raises this rank's flag on every peer; the peer's
-// halo_wait_apply_kernel spins (bounded) on the flags of all its peers and then patches its residual.  One NCCL
-// send/recv group per colour cost ~43 us; a flag hop over NVLink is a few microseconds.
-// Area layout (doubles; the header is the same on every rank): [ 16 halo flags (u64) | 16 reduction flags | 2 x 32
-// reduction slots | receive values ... ].
-// ---------------------------------------------------------------------------------------------------------------
-struct PeerTable { double *area[8]; };   // peers' mapped areas (own entry = own area)
-
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// one CTA; segments [send_ptr[h], send_ptr[h+1]) of this colour go to peer h at offset peer_base[h] of its receive area
-__global__ void __launch_bounds__(1024) halo_push_kernel(PeerTable peers, const int *__restrict__ send_storage,
-                                                         const double *__restrict__ field, const int *__restrict__ send_ptr_col,
-                                                         const int *__restrict__ peer_base_col, int world, int rank,
-                                                         size_t flag_off, size_t val_off, unsigned long long *epoch_ctr) {
-    // the exchange counter lives in device memory so that the whole sweep (all colours) is one static CUDA graph
-    __shared__ unsigned long long s_epoch;
-    if (threadIdx.x == 0) s_epoch = ++(*epoch_ctr);
-    for (int h = 0; h < world; h++) {
-        if (h == rank) continue;
-        const int a = send_ptr_col[h], b = send_ptr_col[h + 1];
-        double *dst = peers.area[h] + val_off + peer_base_col[h];
-        for (int k = a + (int)threadIdx.x; k < b; k += (int)blockDim.x) dst[k - a] = field[send_storage[k]];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < world && (int)threadIdx.x != rank)
-        st_release_sys_u64(reinterpret_cast<unsigned long long *>(peers.area[threadIdx.x] + flag_off) + rank, s_epoch);
-}
-
-// wait for every peer's flag of this colour, then apply what arrived (see halo_apply_kernel)
-__global__ void __launch_bounds__(256) halo_wait_apply_kernel(const unsigned long long *flags, int world, int rank,
-                                                              const unsigned long long *epoch_ctr, int *err,
-                                                              const int *__restrict__ recv_proc, const double *recvbuf, int k0,
-                                                              int k1, const int *__restrict__ colptr, const int *__restrict__ crow,
-                                                              const double *__restrict__ valT, const int *__restrict__ psite,
-                                                              double *__restrict__ field, double *__restrict__ r) {
-    if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
-        const unsigned long long epoch = *epoch_ctr;   // set by this colour's halo_push_kernel, earlier on the same stream
-        unsigned int spins = 0;
-        while (ld_acquire_sys_u64(flags + threadIdx.x) < epoch) {
-            if (++spins > (1u << 24)) { atomicExch(err, 2); break; }   // a peer died: report instead of hanging the box
-        }
-    }
-    __syncthreads();
-    const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= k1) return;
-    const int p = recv_proc[k];
-    const int sq = psite[p];
-    const double f_new = __ldcv(recvbuf + k);   // written by a peer over NVLink: never from a stale cache line
-    const double delta = f_new - field[sq];
-    field[sq] = f_new;
-    for (int e = colptr[p]; e < colptr[p + 1]; e++) r[crow[e]] += valT[e] * delta;
-}
-
-// Fused exchange of one colour (the production path): CTA 0 first pushes this rank's boundary values into the peers'
-// receive areas and raises its flag there; every CTA then waits for the peers' flags and applies the ghost values that
-// arrived.  Launched with programmatic dependent launch between the colour kernels: griddepcontrol.launch_dependents lets the
-// next colour's sweep kernel run its r-independent prologue meanwhile, griddepcontrol.wait orders this kernel after the
-// sweep kernel whose boundary values it publishes.  epoch_ctr[0] counts completed exchanges (bumped by the last CTA to
-// leave, so every CTA of a launch reads the same value), epoch_ctr[1] is the departure counter.
-__global__ void __launch_bounds__(256) halo_exchange_kernel(PeerTable peers, const int *__restrict__ send_storage,
-                                                            const int *__restrict__ send_ptr_col, const int *__restrict__ peer_base_col,
-                                                            int world, int rank, size_t flag_off, size_t val_off,
-                                                            unsigned long long *epoch_ctr, int *err,
-                                                            const int *__restrict__ recv_proc, int k0, int k1,
-                                                            const int *__restrict__ colptr, const int *__restrict__ crow,
-                                                            const double *__restrict__ valT, const int *__restrict__ psite,
-                                                            double *field, double *r, int dbg) {
-#define EX_STAMP(slot) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = g_timeline[8191]; if (n_ < 4090) { g_timeline[2 * n_] = global_ns(); g_timeline[2 * n_ + 1] = (slot); g_timeline[8191] = n_ + 1; } } } while (0)
-    EX_STAMP(0);
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    EX_STAMP(1);
-    const unsigned long long target = *reinterpret_cast<volatile unsigned long long *>(epoch_ctr) + 1ull;
-    if (blockIdx.x == 0) {
-        for (int h = 0; h < world; h++) {
-            if (h == rank) continue;
-            const int a = send_ptr_col[h], b = send_ptr_col[h + 1];
-            double *dst = peers.area[h] + val_off + peer_base_col[h];
-            for (int k = a + (int)threadIdx.x; k < b; k += (int)blockDim.x) dst[k - a] = field[send_storage[k]];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();   // cumulative over the CTA barrier: every thread's peer stores are visible system-wide
-            for (int h = 0; h < world; h++)
-                if (h != rank) st_release_sys_u64(reinterpret_cast<unsigned long long *>(peers.area[h] + flag_off) + rank, target);
-        }
-    }
-    EX_STAMP(2);
-    if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
-        const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(peers.area[rank] + flag_off);
-        unsigned int spins = 0;
-        while (ld_acquire_sys_u64(flags + threadIdx.x) < target) {
-            if (++spins > (1u << 24)) { atomicExch(err, 2); break; }   // a peer died: report instead of hanging the box
-        }
-    }
-    __syncthreads();
-    EX_STAMP(3);
-    // one WARP per ghost site: the lanes stride over the site's local column, so all its r patches are in flight at once
-    // (a thread walking the column alone paid three dependent memory round trips per entry: 18 us per colour in the
-    // %globaltimer timeline)
-    const int k = k0 + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (k < k1) {
-        const int p = recv_proc[k];
-        const int sq = psite[p];
-        const double f_new = __ldcv(peers.area[rank] + val_off + k);   // written by a peer over NVLink
-        const double delta = f_new - field[sq];
-        __syncwarp();
-        if (lane == 0) field[sq] = f_new;
-        for (int e = colptr[p] + lane; e < colptr[p + 1]; e += 32) r[crow[e]] += valT[e] * delta;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long left = atomicAdd(epoch_ctr + 1, 1ull) + 1ull;
-        if (left == gridDim.x) {   // last CTA out: this exchange is complete
-            epoch_ctr[1] = 0ull;
-            __threadfence();
-            *reinterpret_cast<volatile unsigned long long *>(epoch_ctr) = target;
-        }
-    }
-    EX_STAMP(4);
-#undef EX_STAMP
-}
-
-// all-reduce (sum) of `count` <= 4 scalars over the ranks: push the partials to every peer, then sum in rank order
-__global__ void allreduce_push_kernel(PeerTable peers, const double *__restrict__ partial, int count, int world, int rank,
-                                      size_t slot_off, size_t flag_off, unsigned long long epoch) {
+// all-reduce (sum) of `count` <= 4 scalars over the ranks, one launch: lane h pushes this rank's partials into peer h's slots
+// and raises its flag there, then waits for peer h's flag; lane 0 sums the slots in rank order (deterministic, identical on
+// every rank).  Two slot sets alternate with the epoch: a fast rank may already push reduction e+1 while a peer still sums e.
+__global__ void allreduce_p2p_kernel(PeerTable peers, const double *__restrict__ partial, int count, int world, int rank,
+                                     size_t slot_off, size_t flag_off, unsigned long long epoch, int *err, double *out) {
     const int h = threadIdx.x;
     if (h < world) {
-        // two slot sets alternate with the epoch: a fast rank may already push reduction e+1 while a peer still sums e
         double *slots = peers.area[h] + slot_off + (size_t)(epoch & 1ull) * 32 + (size_t)rank * 4;
         for (int k = 0; k < count; k++) slots[k] = partial[k];
         __threadfence_system();
         st_release_sys_u64(reinterpret_cast<unsigned long long *>(peers.area[h] + flag_off) + rank, epoch);
-    }
-}
-__global__ void allreduce_wait_sum_kernel(const double *area, int count, int world, size_t slot_off, size_t flag_off,
-                                          unsigned long long epoch, int *err, double *__restrict__ out) {
-    const int h = threadIdx.x;
-    if (h < world) {
-        const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(area + flag_off);
+        const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(peers.area[rank] + flag_off);
         unsigned int spins = 0;
         while (ld_acquire_sys_u64(flags + h) < epoch) {
             if (++spins > (1u << 24)) { atomicExch(err, 2); break; }
         }
     }
-    __syncthreads();
+    __syncwarp();
     if (threadIdx.x == 0) {
+        const double *area = peers.area[rank];
         for (int k = 0; k < count; k++) {
             double s = 0.0;
-            for (int g = 0; g < world; g++) s += __ldcv(area + slot_off + (size_t)(epoch & 1ull) * 32 + (size_t)g * 4 + k);   // fixed order: deterministic
+            for (int g = 0; g < world; g++) s += __ldcv(area + slot_off + (size_t)(epoch & 1ull) * 32 + (size_t)g * 4 + k);
             out[k] = s;
         }
     }
 }
 
-__global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n, unsigned int *cdone, int K, unsigned int *flow = nullptr) {
+// closes a sweep: next Philox counter / next block of supplied normals; a sharded field also counts the sweep for its flags
+__global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n, unsigned long long *shard_state) {
     if (threadIdx.x == 0) {
         spp->sweep_counter += 1ull;
         spp->z_offset += n;
-        if (flow) {   // dataflow sweep: next epoch, ticket back to zero
-            flow[0] += 1u;
-            flow[1] = 0u;
-        }
+        if (shard_state) shard_state[0] += 1ull;
     }
-    if (cdone)   // flag-chained sweep: the colour counters start every sweep at zero
-        for (int k = threadIdx.x; k < 2 * K; k += blockDim.x) cdone[k * NNGP_CHAIN_STRIDE] = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -139,16 +139,20 @@ struct Ctx {
     NcclApi::Comm comm = nullptr;
     std::vector<int> send_ptr, recv_ptr;   // [(colour, peer)] segments of the packed halo buffers
     std::vector<int> gstart;               // processing-index range of the ghost sites of each colour
-    // peer-to-peer transport (CUDA IPC): own area + the peers' mapped areas
+    // peer-to-peer transport: own area + the peers' areas (CUDA IPC mappings, or direct pointers inside one process)
     bool p2p = false;
-    double *p2p_area = nullptr;            // [recv values | W halo flags | W reduction flags | W*4 reduction slots]
-    size_t p2p_flag_off = 0, p2p_rflag_off = 16, p2p_slot_off = 32, p2p_val_off = 96, p2p_doubles = 0;
+    double *p2p_area = nullptr;            // [16 halo flags | 16 reduction flags | 2 x 32 reduction slots | recv values x 2 parities]
+    size_t p2p_flag_off = 0, p2p_rflag_off = 16, p2p_slot_off = 32, p2p_val_off = 96, p2p_doubles = 0, p2p_parity_stride = 0;
     PeerTable peers{};
     void *peer_mapped[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned long long red_epoch = 0;
     int graph_launches = 0;
-    DevBuf<unsigned long long> d_halo_epoch;
-    DevBuf<int> d_send_ptr, d_peer_base;   // per colour: [W+1] send offsets, [W] offsets inside the peers' receive areas
+    std::vector<int> send_proc;            // processing id of every entry of the send lists
+    std::vector<int> btile_count;          // per colour: tiles that hold boundary sites (they come first inside the colour)
+    std::vector<unsigned int> send_mask, recv_mask;   // per colour: peers this rank sends to / receives from
+    DevBuf<unsigned long long> d_shard_state;         // [0] sweeps since connect, [1 + colour] boundary tiles done
+    DevBuf<int> d_bptr;
+    DevBuf<int2> d_bdst;
     long long nnz = 0;
     int n_sm = 148;
     long long launches_in_op = 0;
@@ -157,31 +161,22 @@ struct Ctx {
     std::vector<int> i2g, g2i, cstart, lvl_ptr, partial_rows;   // i2g / g2i: storage id <-> reference (0-based) id
     struct Seg { int l0, l1; bool single_block; };
     std::vector<Seg> solve_plan;
-    // tiles of the sweep: cfg 0 = 256 threads x 8 entries, cfg 1 = 128 x 8, cfg 2 = 256 x 4
-    std::vector<int> tile_ptr[4];          // per colour, into d_tiles[cfg]
-    int max_tiles[4] = {0, 0, 0, 0};       // largest number of tiles in one colour
-    int persistent_grid[3] = {0, 0, 0};    // co-resident grid size of the persistent kernel per cfg
-    bool persistent_ok[3] = {false, false, false};   // per-CTA tile list fits the kernel's shared-memory table
-    // 0 persistent 256x8 | 1 per-colour launches 256x8 | 2 per-colour launches 128x8 | 3 thread-per-site launches
-    // 4 persistent 256x4 | 5 persistent 128x8
-    int tail_first = -1, tail_cluster = 0; // fused tail (gibbs_tail_kernel): first fused colour, cluster size (0 = unavailable)
-    // 34 = PDL chain of 128x8 tiles, blocked segmented reduction, L2 eviction hints, and the 6-CTAs/SM build for colours whose
-    // tile count would otherwise spill into a second wave: fastest (profiles/r01_explore_sweep_occupancy.txt).  Measured and
-    // kept as options: 22 (5 CTAs/SM everywhere, +6 %), 36 (trailing small colours fused into one cluster launch, +2 %),
-    // 37 (L2 prefetch of the next colour's tiles, +3 % at n = 1M, +10 % at 4M)
-    int sweep_variant = 34;
+    // tiles of the sweep: runs of consecutive same-colour sites with <= 128 sites and <= 1024 CSC entries
+    std::vector<int> tile_ptr;             // per colour, into d_tiles
+    // 0 = PDL chain of 128x8 tiles (blocked segmented reduction, L2 eviction hints), 5 CTAs/SM, and the 6-CTAs/SM build for
+    //     colours whose tile count would otherwise spill into a second wave (default; profiles/r01_explore_sweep_occupancy.txt)
+    // 1 = the same chain with 5 CTAs/SM everywhere; 2 = the same tiles as plain launches (no PDL); 3 = thread per site
+    int sweep_variant = 0;
     int solve_variant = 0;                 // 0 sync-free single launch, 1 level-scheduled launches
     int commit_variant = 0;                // 0 tiled transposition, 1 thread per column
     // 1 plain coalesced loads (default), 0 TMA-staged ring.  Measured on B200 (profiles/r01_explore_final.txt): the TMA ring is
     // SLOWER (44.7 vs 37.3 us at n = 1M, 128 vs 100 us at 4M, 96 vs 55 us at m = 20): the pass is bound by the latency of
     // the 8-byte field gathers, which wants 2048 resident threads per SM; a 100 KB ring leaves room for 512.
     int loglik_variant = 1;
-    int factor_variant = 0;                // m = 10, d = 2: 0 = 3 CTAs/SM (162 registers), 1 = capped at 128, 2 = capped at 96
     int n_slots = 0;                       // padded length of the level-ordered row list
     int solve_ctas_per_sm = 1;             // window of the sync-free solve = n_sm * this * 256 rows
     int solve_window_ctas = 0;             // if > 0: absolute number of CTAs (overrides the per-SM setting)
     int solve_sleep_ns = 0;                // back-off between polls
-    bool debug_timeline = false;           // persistent sweep kernel stamps %globaltimer (development aid)
 
     // device structure
     DevBuf<int> d_psite, d_gid, d_i2g, d_g2i, d_nn, d_colptr, d_crow, d_csrc, d_zpos, d_lvl_rows, d_lvl_ptr, d_lm, d_optr, d_oidx, d_cstart,
@@ -206,21 +201,9 @@ struct Ctx {
     DevBuf<int> d_send_storage, d_recv_proc;
     DevBuf<double> d_sendbuf, d_recvbuf;
     DevBuf<unsigned char> d_owned;         // per storage id: 1 = owned row (reductions skip ghost rows)
-    DevBuf<int4> d_tiles[4];
-    DevBuf<unsigned char> d_cloc;          // per tile (128x8 configuration, padded to 1024): local site id of every CSC entry, 255 = padding
-    DevBuf<int> d_tile_ptr[4];
+    DevBuf<int4> d_tiles;
+    DevBuf<unsigned char> d_cloc;          // per tile (padded to 1024): local site id of every CSC entry, 255 = padding
     DevBuf<int> d_rows_padded, d_ticket;
-    DevBuf<unsigned int> d_bar;
-    DevBuf<double> d_pc0, d_pc1, d_pf;     // two-pass sweep: per-site constants of the current sweep (site_prepare_kernel)
-    DevBuf<unsigned int> d_cdone;          // flag-chained sweep: arrivals per colour (one 128-byte line each)
-    // dataflow sweep (gibbs_flow_kernel): per tile the earlier tiles it must wait for (transitively reduced), epoch + flags
-    DevBuf<int> d_dep_ptr, d_dep_idx;
-    DevBuf<unsigned int> d_flow;
-    bool flow_ok = false;
-    int flow2_grid[6] = {0, 0, 0, 0, 0, 0};
-    long long flow_edges = 0, flow_edges_direct = 0;
-    int flow_max_deps = 0;
-    int chain_sleep_ns = 0;
     double *h_pinned = nullptr;       // 64 doubles of pinned scratch for scalar results
     double *h_stage = nullptr;        // pinned staging for vectors (n doubles at least)
     size_t h_stage_n = 0;
@@ -378,16 +361,6 @@ static void launch_factor(Ctx *c, double *linv, const CovConst &cc) {
         vecchia_factor_reg_kernel<MM, DD, MATERN><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p); \
         specialised = true;                                                                                              \
     }
-    if (M == 11 && c->dt == 2 && c->factor_variant == 1) {   // occupancy experiment: cap at 128 registers (4 CTAs / SM)
-        vecchia_factor_reg_kernel<11, 2, MATERN, 4><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
-        specialised = true;
-    } else if (M == 11 && c->dt == 2 && c->factor_variant == 2) {   // ... or at 96 registers (5 CTAs / SM)
-        vecchia_factor_reg_kernel<11, 2, MATERN, 5><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
-        specialised = true;
-    } else if (M == 11 && c->dt == 2 && c->factor_variant == 3) {   // libdevice sqrt() / exp() instead of the constant-bank versions
-        vecchia_factor_reg_kernel<11, 2, MATERN, 3, false, false><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
-        specialised = true;
-    } else
     FACTOR_CASE(6, 2)
     FACTOR_CASE(6, 3)
     FACTOR_CASE(11, 2)
@@ -399,7 +372,7 @@ static void launch_factor(Ctx *c, double *linv, const CovConst &cc) {
 #undef FACTOR_CASE
     if (specialised) {
         LAUNCHED(c);
-        const int np = (M <= 24 && c->factor_variant != 3) ? 0 : (int)c->partial_rows.size();   // partial rows ride along in the main launch
+        const int np = M <= 24 ? 0 : (int)c->partial_rows.size();   // partial rows ride along in the main launch
         if (np > 0) {
             vecchia_factor_generic_kernel<24, MATERN><<<(np + blk - 1) / blk, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, c->d_partial_rows.p, np, ld, M, cc, c->d_nbad.p);
             LAUNCHED(c);
@@ -445,7 +418,7 @@ static const int kReduceBlocks = 148 * 8;
 
 // sharded field: every rank holds the partial sums of its owned rows / observations; the scalars are summed over ranks
 static void allreduce_scalars(Ctx *c, int off, int count);
-static void op_halo_exchange(Ctx *c, int col);
+static int op_halo_exchange(Ctx *c, int col);
 
 template <int MT, int STAGES>
 static bool launch_loglik_tma(Ctx *c, const double *linv, const double *field, double shift, int *blocks_out) {
@@ -506,339 +479,123 @@ static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, do
 
 static void op_commit(Ctx *c) {
     const int n_tiled = c->sharded ? c->n_owned : c->n;   // tiles cover the owned sites; ghost columns follow in processing order
-    if (c->commit_variant == 0 || c->commit_variant == 2) {
-        const int nt = c->tile_ptr[1][c->K];   // every tile of every colour (128 x 8 configuration)
+    if (c->commit_variant == 0) {
+        const int nt = c->tile_ptr[c->K];   // every tile of every colour
         if (nt > 0) {
-            if (c->commit_variant == 2) transpose_tile_kernel<128, 8><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p, c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, c->d_valT.p, c->d_pd.p);
-            else transpose_tile2_kernel<128><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p, c->d_colptr.p, c->d_csrc.p, c->d_cloc.p, c->d_linv[c->cur].p, c->d_valT.p, c->d_pd.p);
+            transpose_tile2_kernel<128><<<nt, 128, 0, c->stream>>>(c->d_tiles.p, c->d_colptr.p, c->d_csrc.p, c->d_cloc.p, c->d_linv[c->cur].p, c->d_valT.p, c->d_pd.p);
             LAUNCHED(c);
         }
     } else {
         transpose_values_kernel<<<grid_for(c, n_tiled, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, 0, n_tiled, c->d_valT.p, c->d_pd.p);
         LAUNCHED(c);
     }
-    if (n_tiled < c->n) {   // values of the ghost sites' local columns (halo_apply_kernel patches r along them)
+    if (n_tiled < c->n) {   // values of the ghost sites' local columns (the halo apply patches r along them)
         transpose_values_kernel<<<grid_for(c, c->n - n_tiled, 256), 256, 0, c->stream>>>(c->d_colptr.p, c->d_csrc.p, c->d_linv[c->cur].p, n_tiled, c->n, c->d_valT.p, c->d_pd.p);
         LAUNCHED(c);
     }
     c->committed = true;
 }
 
-static long long *timeline_ptr() {
-    long long *p = nullptr;
-    CK(cudaGetSymbolAddress((void **)&p, g_timeline));
-    return p;
+static ShardConst shard_const(Ctx *c) {
+    ShardConst sc{};
+    sc.peers = c->peers;
+    sc.bptr = c->d_bptr.p;
+    sc.bdst = c->d_bdst.p;
+    sc.gsite = c->d_recv_proc.p;
+    sc.state = c->d_shard_state.p;
+    sc.err = c->d_nbad.p + 1;
+    sc.world = c->world; sc.rank = c->rank; sc.K = c->K;
+    sc.flag_off = (unsigned int)c->p2p_flag_off; sc.val_off = (unsigned int)c->p2p_val_off; sc.parity_stride = (unsigned int)c->p2p_parity_stride;
+    return sc;
 }
 
-static bool sweep_is_two_pass(Ctx *c) { return c->sweep_variant >= 18 && c->sweep_variant <= 20; }
-
-static bool sweep_is_flow(Ctx *c) { return c->sweep_variant >= 24 && c->sweep_variant <= 33 && c->flow_ok; }
-
-// persistent dataflow sweep: stages / CTAs per SM per variant; the grid must be co-resident (occupancy query, cached)
-template <int STAGES, int MINB>
-static void launch_flow2(Ctx *c, int slot) {
-    constexpr int ECAP = 1024;
-    constexpr size_t smem = (size_t)STAGES * ((ECAP + 2) * 8 + (ECAP + 4) * 4 + ECAP) + (size_t)(ECAP + ECAP / 8 + 2 * 128 + 2) * 8 + (size_t)STAGES * 8;
-    auto kern = gibbs_flow2_kernel<128, STAGES, MINB>;
-    if (c->flow2_grid[slot] == 0) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem));
-        REQUIRE(occ >= 1, "gibbs_flow2_kernel does not fit an SM");
-        c->flow2_grid[slot] = occ * c->n_sm;
-    }
-    const int nt = c->tile_ptr[1][c->K];
-    const int grid = std::min(c->flow2_grid[slot], nt);
-    kern<<<grid, 128, smem, c->stream>>>(c->d_tiles[1].p, nt, c->d_dep_ptr.p, c->d_dep_idx.p, c->d_flow.p, c->d_colptr.p, c->d_crow.p, c->d_cloc.p,
-                                          c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p,
-                                          c->d_sp.p, c->d_field.p, c->d_r.p, c->d_nbad.p + 1);
-}
-
-static void launch_sweep_colors(Ctx *c) {
-    if (sweep_is_flow(c)) {
-        // dataflow sweep: one launch over all tiles in colour-major order, per-tile dependency flags instead of colour barriers
-        const int nt = c->tile_ptr[1][c->K];
-#define NNGP_FLOW_ARGS c->d_tiles[1].p, c->d_dep_ptr.p, c->d_dep_idx.p, c->d_flow.p, c->d_colptr.p, c->d_crow.p, c->d_cloc.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, c->d_nbad.p + 1
-        if (c->sweep_variant == 24) gibbs_flow_kernel<128, 5, false><<<nt, 128, 0, c->stream>>>(NNGP_FLOW_ARGS);
-        else if (c->sweep_variant == 25) gibbs_flow_kernel<128, 5, true><<<nt, 128, 0, c->stream>>>(NNGP_FLOW_ARGS);
-        else if (c->sweep_variant == 26) gibbs_flow_kernel<128, 6, false><<<nt, 128, 0, c->stream>>>(NNGP_FLOW_ARGS);
-        else if (c->sweep_variant == 27) gibbs_flow_kernel<128, 4, false><<<nt, 128, 0, c->stream>>>(NNGP_FLOW_ARGS);
-        else if (c->sweep_variant == 28) launch_flow2<3, 4>(c, 0);
-        else if (c->sweep_variant == 29) launch_flow2<2, 5>(c, 1);
-        else if (c->sweep_variant == 30) launch_flow2<4, 3>(c, 2);
-        else if (c->sweep_variant == 31) launch_flow2<2, 6>(c, 3);
-        else if (c->sweep_variant == 32) launch_flow2<1, 8>(c, 4);
-        else launch_flow2<6, 2>(c, 5);
-#undef NNGP_FLOW_ARGS
-        advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, nullptr, c->K, c->d_flow.p);
-        return;
-    }
-    if (sweep_is_two_pass(c)) {
-        // pass 1: r-independent per-site constants (draw included) for every tiled site, full occupancy
-        const int n_tiled = c->sharded ? c->n_owned : c->n;
-        site_prepare_kernel<<<std::min((n_tiled + 255) / 256, c->n_sm * 8), 256, 0, c->stream>>>(c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, n_tiled, c->d_pc0.p, c->d_pc1.p, c->d_pf.p);
-        // pass 2: one PDL-chained launch per colour
-        for (int col = 0; col < c->K; col++) {
-            const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
-            cudaLaunchConfig_t lc = {};
-            lc.gridDim = dim3(nt);
-            lc.blockDim = dim3(128);
-            lc.stream = c->stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            lc.attrs = at;
-            lc.numAttrs = 1;
-            const int4 *tl = c->d_tiles[1].p + t0;
-#define NNGP_T3_ARGS tl, t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const int *)c->d_psite.p, (const double *)c->d_pc0.p, (const double *)c->d_pc1.p, (const double *)c->d_pf.p, c->d_field.p, c->d_r.p
-            if (c->sweep_variant == 18) {
-                if (col == 0) CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, true, 6>, NNGP_T3_ARGS));
-                else CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, false, 6>, NNGP_T3_ARGS));
-            } else if (c->sweep_variant == 19) {
-                if (col == 0) CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, true, 8>, NNGP_T3_ARGS));
-                else CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, false, 8>, NNGP_T3_ARGS));
-            } else {
-                if (col == 0) CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, true, 5>, NNGP_T3_ARGS));
-                else CK(cudaLaunchKernelEx(&lc, gibbs_tile3_kernel<128, false, 5>, NNGP_T3_ARGS));
-            }
-#undef NNGP_T3_ARGS
-        }
-        advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, c->d_cdone.p, c->K);
-        return;
-    }
+// One launch per colour.  Unsharded field or a sharded one with the peer-to-peer transport: a chain of programmatic
+// dependent launches (colour c+1's r-independent prologue overlaps colour c); with the peer-to-peer transport the same kernel
+// also pushes the boundary values to the peers and applies the ghost values that arrive (gibbs_tile2_kernel<.., SHARD>).
+// Returns the number of kernels launched.
+static int launch_sweep_colors(Ctx *c) {
+    const bool fused_halo = c->sharded && c->p2p && c->world > 1;
+    const ShardConst sc = fused_halo ? shard_const(c) : ShardConst{};
+    int launched = 0;
     for (int col = 0; col < c->K; col++) {
-        const int q0 = c->cstart[col], q1 = c->cstart[col + 1];
-        if (c->sweep_variant == 3) {
-            gibbs_color_kernel<<<(q1 - q0 + 255) / 256, 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, q0, q1);
+        if (c->sweep_variant == 3 && !c->sharded) {
+            const int q0 = c->cstart[col], q1 = c->cstart[col + 1];
+            if (q1 > q0) {
+                gibbs_color_kernel<<<(q1 - q0 + 255) / 256, 256, 0, c->stream>>>(c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, q0, q1);
+                launched++;
+            }
             continue;
         }
-        if (c->sweep_variant >= 9 && c->sweep_variant <= 12) {
-            // flag-chained PDL launches: no griddepcontrol.wait, the colour hand-off is a device counter (gibbs_chain_kernel)
-            // 9 = 128x8 tiles, 10 = 256x8, 11 = 64x8, 12 = 128x8 with a separate "go" word
-            const int cfg = c->sweep_variant == 10 ? 0 : (c->sweep_variant == 11 ? 3 : 1);
-            const int two_line = c->sweep_variant == 12 ? 1 : 0;
-            const int t0 = c->tile_ptr[cfg][col], nt = c->tile_ptr[cfg][col + 1] - t0;
-            const unsigned int need = col > 0 ? (unsigned int)(c->tile_ptr[cfg][col] - c->tile_ptr[cfg][col - 1]) : 0u;
-            cudaLaunchConfig_t lc = {};
-            lc.gridDim = dim3(nt);
-            lc.blockDim = dim3(cfg == 0 ? 256 : (cfg == 3 ? 64 : 128));
-            lc.stream = c->stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            lc.attrs = at;
-            lc.numAttrs = (col > 0) ? 1 : 0;
-            const int4 *tl = c->d_tiles[cfg].p + t0;
-#define NNGP_CHAIN_ARGS tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, c->d_cdone.p, col, c->K, need, (unsigned int)c->chain_sleep_ns, two_line, c->d_nbad.p + 1
-            if (cfg == 0) CK(cudaLaunchKernelEx(&lc, gibbs_chain_kernel<256, 8>, NNGP_CHAIN_ARGS));
-            else if (cfg == 3) CK(cudaLaunchKernelEx(&lc, gibbs_chain_kernel<64, 8>, NNGP_CHAIN_ARGS));
-            else CK(cudaLaunchKernelEx(&lc, gibbs_chain_kernel<128, 8>, NNGP_CHAIN_ARGS));
-#undef NNGP_CHAIN_ARGS
-            continue;
+        const int t0 = c->tile_ptr[col], nt = c->tile_ptr[col + 1] - t0;
+        ShardColour cl{};
+        int grid = nt;
+        if (fused_halo) {
+            const int W = c->world;
+            cl.n_tiles = nt;
+            cl.n_btiles = c->btile_count[col];
+            cl.g0 = c->recv_ptr[(size_t)col * W];
+            cl.g1 = c->recv_ptr[(size_t)(col + 1) * W];
+            cl.send_mask = c->send_mask[col];
+            cl.recv_mask = c->recv_mask[col];
+            cl.col = col;
+            const int ng = cl.g1 - cl.g0;
+            if (ng > 0) grid += std::min(16, (ng + 3) / 4);   // ghost CTAs: one warp per ghost site, 4 warps per CTA
         }
-        if ((c->sweep_variant >= 15 && c->sweep_variant <= 17) || (c->sweep_variant >= 21 && c->sweep_variant <= 23) || (c->sweep_variant >= 34 && c->sweep_variant <= 37)) {   // blocked segmented reduction (gibbs_tile2_kernel), 128x8 tiles
-            const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
-            if (c->sweep_variant == 36 && c->tail_cluster > 0 && col == c->tail_first) {
-                // all remaining colours (each <= tail_cluster tiles) + the counter update: one cluster launch
-                cudaLaunchConfig_t lt = {};
-                lt.gridDim = dim3(c->tail_cluster);
-                lt.blockDim = dim3(128);
-                lt.stream = c->stream;
-                cudaLaunchAttribute att[2];
-                att[0].id = cudaLaunchAttributeClusterDimension;
-                att[0].val.clusterDim.x = c->tail_cluster; att[0].val.clusterDim.y = 1; att[0].val.clusterDim.z = 1;
-                att[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                att[1].val.programmaticStreamSerializationAllowed = 1;
-                lt.attrs = att;
-                lt.numAttrs = col > 0 ? 2 : 1;
-#define NNGP_TAIL_ARGS (const int4 *)c->d_tiles[1].p, (const int *)c->d_tile_ptr[1].p, col, c->K, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, (unsigned long long)c->n_global
-                if (col > 0) CK(cudaLaunchKernelEx(&lt, gibbs_tail_kernel<128, true>, NNGP_TAIL_ARGS));
-                else CK(cudaLaunchKernelEx(&lt, gibbs_tail_kernel<128, false>, NNGP_TAIL_ARGS));
-#undef NNGP_TAIL_ARGS
-                return;                                   // the tail kernel also advanced the sweep counter
-            }
-            cudaLaunchConfig_t lc = {};
-            lc.gridDim = dim3(nt);
-            lc.blockDim = dim3(128);
-            lc.stream = c->stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            lc.attrs = at;
-            lc.numAttrs = (col > 0 && c->sweep_variant != 16) ? 1 : 0;
-            const int4 *tl = c->d_tiles[1].p + t0;
-#define NNGP_T2_ARGS tl, t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, c->debug_timeline ? timeline_ptr() : (long long *)nullptr, col, n_next
-            const int n_next = (col + 1 < c->K && !(c->sweep_variant == 36 && c->tail_cluster > 0 && col + 1 >= c->tail_first)) ? c->tile_ptr[1][col + 2] - c->tile_ptr[1][col + 1] : 0;
-            if (c->debug_timeline) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2, true>, NNGP_T2_ARGS));
-            else if (c->sweep_variant == 15) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5>, NNGP_T2_ARGS));
-            else if (c->sweep_variant == 17) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6>, NNGP_T2_ARGS));
-            else if (c->sweep_variant == 21) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 1>, NNGP_T2_ARGS));
-            else if (c->sweep_variant == 22) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, NNGP_T2_ARGS));
-            // 34: as 22, but a colour with more tiles than 5 CTAs/SM can hold (a 6 % tail wave that costs a whole extra
-            // gather -> sum -> scatter round) runs the 6-CTAs/SM build (80 registers) so that all its tiles are co-resident
-            else if (c->sweep_variant == 34 || c->sweep_variant == 36) {
-                if (nt > 5 * c->n_sm && nt <= 6 * c->n_sm) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2>, NNGP_T2_ARGS));
-                else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, NNGP_T2_ARGS));
-            }
-            else if (c->sweep_variant == 35) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2>, NNGP_T2_ARGS));
-            // 37: as 34, and every CTA prefetches tile(s) of the next colour into L2 before its own prologue
-            else if (c->sweep_variant == 37) {
-                if (nt > 5 * c->n_sm && nt <= 6 * c->n_sm) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2, false, true>, NNGP_T2_ARGS));
-                else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2, false, true>, NNGP_T2_ARGS));
-            }
-            else if (c->sweep_variant == 23) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 3>, NNGP_T2_ARGS));
-            else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, false, 5>, NNGP_T2_ARGS));
-#undef NNGP_T2_ARGS
-            continue;
-        }
-        const bool pdl = (c->sweep_variant == 6 || c->sweep_variant == 7 || c->sweep_variant == 8 || c->sweep_variant == 13 || c->sweep_variant == 14);
-        const int cfg = (c->sweep_variant == 1 || c->sweep_variant == 7) ? 0 : (c->sweep_variant == 8 ? 3 : 1);   // 128x8 is also the persistent kernel's fallback
-        const int t0 = c->tile_ptr[cfg][col], nt = c->tile_ptr[cfg][col + 1] - t0;
-        if (!pdl) {
-            if (cfg == 0)
-                gibbs_tile_kernel<256, 8, false><<<nt, 256, 0, c->stream>>>(c->d_tiles[0].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
-            else
-                gibbs_tile_kernel<128, 8, false><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p);
+        if (grid == 0) continue;
+        const bool pdl = c->sweep_variant != 2 && !(c->sharded && !fused_halo);
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(grid);
+        lc.blockDim = dim3(128);
+        lc.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = (pdl && launched > 0) ? 1 : 0;   // the first colour of a sweep is an ordinary launch: it must see the counter update
+#define NNGP_T2_ARGS (const int4 *)(c->d_tiles.p + t0), t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, sc, cl
+        // a colour with slightly more tiles than 5 CTAs/SM can hold (a 6 % tail wave that costs a whole extra gather -> sum ->
+        // scatter round) runs the 6-CTAs/SM build (80 registers) so that all its tiles are co-resident
+        const bool six = c->sweep_variant == 0 && nt > 5 * c->n_sm && nt <= 6 * c->n_sm;
+        if (fused_halo) {
+            if (six) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2, true>, NNGP_T2_ARGS));
+            else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2, true>, NNGP_T2_ARGS));
+        } else if (!pdl) {
+            CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, false, 5, 2>, NNGP_T2_ARGS));
         } else {
-            // programmatic dependent launch: colour c+1 may start its r-independent prologue while colour c is running; the
-            // first colour of a sweep is an ordinary launch (it must see the advance kernel's counter update)
-            cudaLaunchConfig_t lc = {};
-            lc.gridDim = dim3(nt);
-            lc.blockDim = dim3(cfg == 0 ? 256 : (cfg == 3 ? 64 : 128));
-            lc.dynamicSmemBytes = 0;
-            lc.stream = c->stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            lc.attrs = at;
-            lc.numAttrs = (col > 0) ? 1 : 0;
-            const int4 *tl = c->d_tiles[cfg].p + t0;
-            if (c->sweep_variant == 13 || c->sweep_variant == 14) {   // occupancy experiments: 128x8 capped at 64 / 80 registers
-                if (c->sweep_variant == 13)
-                    CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true, 8>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
-                else
-                    CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true, 6>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
-            } else if (cfg == 3)
-                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<64, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
-            else if (cfg == 0)
-                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<256, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
-            else if (c->debug_timeline)
-                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true, 0, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, timeline_ptr(), col));
-            else
-                CK(cudaLaunchKernelEx(&lc, gibbs_tile_kernel<128, 8, true>, tl, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0));
+            if (six) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2>, NNGP_T2_ARGS));
+            else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, NNGP_T2_ARGS));
         }
+#undef NNGP_T2_ARGS
+        launched++;
+        if (c->sharded && !fused_halo) launched += op_halo_exchange(c, col);
     }
-    advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, c->d_cdone.p, c->K);
+    advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, fused_halo ? c->d_shard_state.p : nullptr);
+    return launched + 1;
 }
 
-static int sweep_launches(Ctx *c) {
-    if (c->sweep_variant == 36 && c->tail_cluster > 0 && !c->sharded) return c->tail_first + 1;   // leading colours + fused tail
-    return sweep_is_flow(c) ? 2 : c->K + 1 + (sweep_is_two_pass(c) ? 1 : 0);
-}
-
-static bool sweep_is_persistent(Ctx *c) { return c->sweep_variant == 0 || c->sweep_variant == 4 || c->sweep_variant == 5; }
-
-// n_sweeps sweeps over all colours; scalar parameters are read from d_sp, the sweep counter / normals offset are passed in
-static void op_sweeps(Ctx *c, int n_sweeps, unsigned long long sweep_in_call) {
+// n_sweeps sweeps over all colours; scalar parameters are read from d_sp.  Nothing in the sequence depends on host-side values
+// (the NCCL transport excepted), so one sweep is captured once and replayed as a CUDA graph: K + 1 plain launches per sweep were
+// CPU-submission bound.
+static void op_sweeps(Ctx *c, int n_sweeps) {
     if (n_sweeps <= 0) return;
-    if (c->sharded) {
-        // one spatial block of a larger field: per colour, sweep the owned sites, then exchange the boundary values with the
-        // peers that hold them as ghosts and patch the local residual for what arrived.  With the peer-to-peer transport
-        // nothing in the sequence depends on host-side values, so one sweep is captured once and replayed as a CUDA graph
-        // (66 plain launches per sweep were CPU-submission bound: ~40 us per colour).
-        auto one_sweep = [&]() {
-            for (int col = 0; col < c->K; col++) {
-                const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
-                if (nt > 0 && c->p2p && c->world > 1) {
-                    // PDL chain: sweep(c) -> exchange(c) -> sweep(c+1) ...; the first sweep kernel is an ordinary launch
-                    cudaLaunchConfig_t lc = {};
-                    lc.gridDim = dim3(nt);
-                    lc.blockDim = dim3(128);
-                    lc.stream = c->stream;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                    at[0].val.programmaticStreamSerializationAllowed = 1;
-                    lc.attrs = at;
-                    lc.numAttrs = (col > 0) ? 1 : 0;
-                    CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, (const int4 *)(c->d_tiles[1].p + t0), t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0, 0));
-                } else if (nt > 0) {
-                    gibbs_tile2_kernel<128, false, 5, 2><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, t0, c->d_colptr.p, c->d_crow.p, c->d_cloc.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0);
-                }
-                op_halo_exchange(c, col);
-            }
-            advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, c->d_cdone.p, c->K);
-        };
-        const bool graphable = c->use_graph && (c->world == 1 || c->p2p);
-        for (int s = 0; s < n_sweeps; s++) {
-            if (graphable) {
-                if (!c->sweep_graph) {
-                    cudaGraph_t g;
-                    const long long l0 = c->launches_in_op;
-                    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                    one_sweep();
-                    CK(cudaStreamEndCapture(c->stream, &g));
-                    CK(cudaGraphInstantiate(&c->sweep_graph, g, 0));
-                    CK(cudaGraphDestroy(g));
-                    c->graph_launches = (int)(c->launches_in_op - l0) + c->K + 1;
-                    c->launches_in_op = l0;
-                }
-                CK(cudaGraphLaunch(c->sweep_graph, c->stream));
-                g_launches.fetch_add(c->graph_launches, std::memory_order_relaxed);
-                c->launches_in_op += c->graph_launches;
-            } else {
-                one_sweep();
-                g_launches.fetch_add(c->K + 1, std::memory_order_relaxed);
-                c->launches_in_op += c->K + 1;
-            }
-        }
-        CK(cudaGetLastError());
-        return;
-    }
-    const int pcfg = c->sweep_variant == 0 ? 0 : (c->sweep_variant == 5 ? 1 : 2);
-    if (sweep_is_persistent(c) && c->persistent_ok[pcfg]) {
-        const int cfg = pcfg;
-        CK(cudaMemsetAsync(c->d_bar.p, 0, sizeof(unsigned int), c->stream));
-        const int4 *tiles = c->d_tiles[cfg].p;
-        const int *tile_ptr = c->d_tile_ptr[cfg].p;
-        int K = c->K, ns = n_sweeps;
-        unsigned long long sc0 = c->sweep_counter + sweep_in_call, zoff0 = sweep_in_call * (unsigned long long)c->n_global, nsites = (unsigned long long)c->n_global;
-        const int *colptr = c->d_colptr.p, *crow = c->d_crow.p, *zpos = c->d_zpos.p, *gid = c->d_gid.p, *psite = c->d_psite.p;
-        const double *valT = c->d_valT.p, *pd = c->d_pd.p, *nobs = c->d_nobs.p, *S = c->d_S.p, *zbuf = c->d_zbuf.p;
-        const SweepParams *spp = c->d_sp.p;
-        double *field = c->d_field.p, *r = c->d_r.p;
-        unsigned int *bar = c->d_bar.p;
-        int dbg = c->debug_timeline ? 1 : 0;
-        void *args[] = {&tiles, &tile_ptr, &K, &ns, &sc0, &zoff0, &nsites, &colptr, &crow, &valT, &pd, &nobs, &S, &zpos, &gid, &psite, &zbuf, &spp, &field, &r, &bar, &dbg};
-        const int grid = c->persistent_grid[cfg];
-        if (cfg == 0) CK(cudaLaunchCooperativeKernel((void *)gibbs_persistent_kernel<256, 8>, dim3(grid), dim3(256), args, 0, c->stream));
-        else if (cfg == 1) CK(cudaLaunchCooperativeKernel((void *)gibbs_persistent_kernel<128, 8>, dim3(grid), dim3(128), args, 0, c->stream));
-        else CK(cudaLaunchCooperativeKernel((void *)gibbs_persistent_kernel<256, 4>, dim3(grid), dim3(256), args, 0, c->stream));
-        LAUNCHED(c);
-        return;
-    }
+    const bool graphable = c->use_graph && !(c->sharded && c->world > 1 && !c->p2p);
     for (int s = 0; s < n_sweeps; s++) {
-        if (c->debug_timeline && c->K * 16 <= 4096) {   // per-colour stamps of the PDL chain: [last ready, first released, first done, last done]
-            std::vector<long long> init((size_t)c->K * 4);
-            for (int k = 0; k < c->K; k++) { init[4 * k] = 0; init[4 * k + 1] = -1; init[4 * k + 2] = -1; init[4 * k + 3] = 0; }
-            CK(cudaMemcpyAsync(timeline_ptr(), init.data(), init.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-            CK(cudaMemsetAsync(timeline_ptr() + 4096, 0, 4096 * sizeof(long long), c->stream));   // per-CTA phase accumulators
-            CK(cudaStreamSynchronize(c->stream));
-        }
-        if (c->use_graph) {
+        int nl;
+        if (graphable) {
             if (!c->sweep_graph) {
                 cudaGraph_t g;
                 CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                launch_sweep_colors(c);
+                c->graph_launches = launch_sweep_colors(c);
                 CK(cudaStreamEndCapture(c->stream, &g));
                 CK(cudaGraphInstantiate(&c->sweep_graph, g, 0));
                 CK(cudaGraphDestroy(g));
             }
             CK(cudaGraphLaunch(c->sweep_graph, c->stream));
+            nl = c->graph_launches;
         } else {
-            launch_sweep_colors(c);
+            nl = launch_sweep_colors(c);
             CK(cudaGetLastError());
         }
-        const int nl = sweep_launches(c);
         g_launches.fetch_add(nl, std::memory_order_relaxed);
         c->launches_in_op += nl;
     }
@@ -898,9 +655,7 @@ static void op_beta0_sums(Ctx *c, int scal_off) {
 static void allreduce_scalars(Ctx *c, int off, int count) {
     if (c->sharded && c->world > 1 && c->p2p) {
         c->red_epoch++;
-        allreduce_push_kernel<<<1, 32, 0, c->stream>>>(c->peers, c->d_scalars.p + off, count, c->world, c->rank, c->p2p_slot_off, c->p2p_rflag_off, c->red_epoch);
-        LAUNCHED(c);
-        allreduce_wait_sum_kernel<<<1, 32, 0, c->stream>>>(c->p2p_area, count, c->world, c->p2p_slot_off, c->p2p_rflag_off, c->red_epoch, c->d_nbad.p + 1, c->d_scalars.p + off);
+        allreduce_p2p_kernel<<<1, 32, 0, c->stream>>>(c->peers, c->d_scalars.p + off, count, c->world, c->rank, c->p2p_slot_off, c->p2p_rflag_off, c->red_epoch, c->d_nbad.p + 1, c->d_scalars.p + off);
         LAUNCHED(c);
         return;
     }
@@ -908,35 +663,18 @@ static void allreduce_scalars(Ctx *c, int off, int count) {
     NCK(g_nccl.AllReduce(c->d_scalars.p + off, c->d_scalars.p + off, (size_t)count, kNcclFloat64, kNcclSum, c->comm, c->stream));
 }
 
-// halo exchange for colour `col` (0-based) of a sharded field
-static void op_halo_exchange(Ctx *c, int col) {
-    if (!c->sharded || c->world == 1) return;
-    if (c->p2p) {
-        const int W = c->world;
-        const int r0 = c->recv_ptr[(size_t)col * W], r1 = c->recv_ptr[(size_t)(col + 1) * W];
-        cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3(std::max(1, (r1 - r0 + 7) / 8));   // one warp per ghost site, 8 warps per CTA
-        lc.blockDim = dim3(256);
-        lc.stream = c->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at;
-        lc.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&lc, halo_exchange_kernel, c->peers, (const int *)c->d_send_storage.p, (const int *)(c->d_send_ptr.p + (size_t)col * W),
-                              (const int *)(c->d_peer_base.p + (size_t)col * W), W, c->rank, c->p2p_flag_off, c->p2p_val_off, c->d_halo_epoch.p,
-                              c->d_nbad.p + 1, (const int *)c->d_recv_proc.p, r0, r1, (const int *)c->d_colptr.p, (const int *)c->d_crow.p,
-                              (const double *)c->d_valT.p, (const int *)c->d_psite.p, c->d_field.p, c->d_r.p, c->debug_timeline ? 1 : 0));
-        LAUNCHED(c);
-        return;
-    }
-    if (!c->comm) { set_error("this sharded context has no NCCL communicator: drive it with the nngp_shard_* colour-stepping entry points"); throw StateFail(); }
+// halo exchange for colour `col` (0-based) of a sharded field over NCCL (the fallback transport; the peer-to-peer transport is
+// fused into the sweep kernel): pack, one send/recv group, apply.  Returns the number of kernels launched.
+static int op_halo_exchange(Ctx *c, int col) {
+    if (!c->sharded || c->world == 1) return 0;
+    if (!c->comm) { set_error("this sharded context has no transport: connect its peers (nngp_shard_p2p_connect / nngp_shard_connect_local), give it an NCCL id, or drive it with the nngp_shard_* colour-stepping entry points"); throw StateFail(); }
     const int W = c->world;
     const int s0 = c->send_ptr[(size_t)col * W], s1 = c->send_ptr[(size_t)(col + 1) * W];
     const int r0 = c->recv_ptr[(size_t)col * W], r1 = c->recv_ptr[(size_t)(col + 1) * W];
+    int launched = 0;
     if (s1 > s0) {
         halo_pack_kernel<<<(s1 - s0 + 255) / 256, 256, 0, c->stream>>>(c->d_send_storage.p, c->d_field.p, s0, s1, c->d_sendbuf.p);
-        LAUNCHED(c);
+        launched++;
     }
     NCK(g_nccl.GroupStart());
     for (int h = 0; h < W; h++) {
@@ -949,8 +687,9 @@ static void op_halo_exchange(Ctx *c, int col) {
     NCK(g_nccl.GroupEnd());
     if (r1 > r0) {
         halo_apply_kernel<<<(r1 - r0 + 255) / 256, 256, 0, c->stream>>>(c->d_recv_proc.p, c->d_recvbuf.p, r0, r1, c->d_colptr.p, c->d_crow.p, c->d_valT.p, c->d_psite.p, c->d_field.p, c->d_r.p);
-        LAUNCHED(c);
+        launched++;
     }
+    return launched;
 }
 
 static void ensure_zbuf(Ctx *c, size_t count) {
@@ -1060,7 +799,7 @@ static void destroy_ctx(Ctx *c) {
     for (int h = 0; h < 8; h++) if (c->peer_mapped[h]) cudaIpcCloseMemHandle(c->peer_mapped[h]);
     c->d_recvbuf.p = nullptr;
     if (c->p2p_area) cudaFree(c->p2p_area);
-    c->d_send_ptr.release(); c->d_peer_base.release(); c->d_halo_epoch.release();
+    c->d_shard_state.release(); c->d_bptr.release(); c->d_bdst.release();
     c->d_send_storage.release(); c->d_recv_proc.release(); c->d_sendbuf.release(); c->d_owned.release();
     DevBuf<int> *ib[] = {&c->d_psite, &c->d_gid, &c->d_i2g, &c->d_g2i, &c->d_nn, &c->d_colptr, &c->d_crow, &c->d_csrc, &c->d_zpos, &c->d_lvl_rows, &c->d_lvl_ptr,
                          &c->d_lm, &c->d_optr, &c->d_oidx, &c->d_cstart, &c->d_partial_rows, &c->d_nbad};
@@ -1074,8 +813,8 @@ static void destroy_ctx(Ctx *c) {
     c->d_Xa.release(); c->d_Xl.release(); c->d_B.release(); c->d_yobs.release(); c->d_robs.release(); c->d_coef.release(); c->d_atb_part.release(); c->d_atb_out.release();
     c->d_pred_rows.release();
     c->d_sp.release();
-    for (int k = 0; k < 4; k++) { c->d_tiles[k].release(); c->d_tile_ptr[k].release(); }
-    c->d_rows_padded.release(); c->d_ticket.release(); c->d_bar.release(); c->d_cdone.release(); c->d_cloc.release(); c->d_dep_ptr.release(); c->d_dep_idx.release(); c->d_flow.release(); c->d_pc0.release(); c->d_pc1.release(); c->d_pf.release();
+    c->d_tiles.release();
+    c->d_rows_padded.release(); c->d_ticket.release(); c->d_cloc.release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1147,57 +886,6 @@ struct ShardArgs {
     long long n_global;
     const char *comm_id;
 };
-
-// Tile dependency graph of the dataflow sweep.  Two tiles conflict when a row of the factor has an entry in a column of each
-// (their sites are moral neighbours); the reference's colour order (update_Gaussian.R:261) says the lower-numbered tile goes
-// first (tiles are numbered colour-major and same-colour sites never share a row).  preds[t] = every lower-numbered tile in
-// conflict with t; an edge u -> t is dropped when some v in preds[t] has u in preds[v] (a subset of the transitive reduction
-// that already brings 62 predecessors per tile down to 7 at n = 1M, m = 10).  nn: slot-major [M][ld], storage numbering.
-static void tile_dependencies(const std::vector<int4> &tiles, const std::vector<int> &colptr, const std::vector<int> &crow,
-                              const std::vector<int> &nn, int ld, int M, const std::vector<int> &pof, int n,
-                              std::vector<int> &dep_ptr, std::vector<int> &dep_idx, long long &n_direct, int &max_deps) {
-    const int nt = (int)tiles.size();
-    std::vector<int> tile_of(n, -1);   // by processing id
-    for (int t = 0; t < nt; t++)
-        for (int q = tiles[t].x; q < tiles[t].y; q++) tile_of[q] = t;
-    std::vector<std::vector<int>> preds(nt), kept(nt);
-#pragma omp parallel for schedule(dynamic, 16)
-    for (int t = 0; t < nt; t++) {
-        std::vector<int> &v = preds[t];
-        for (int e = tiles[t].z; e < tiles[t].w; e++) {
-            const int row = crow[e];
-            for (int j = 0; j < M; j++) {
-                const int s = nn[(size_t)j * ld + row];
-                if (s < 0) continue;
-                const int u = tile_of[pof[s]];
-                if (u >= 0 && u < t && (v.empty() || v.back() != u)) v.push_back(u);
-            }
-            if (v.size() > (size_t)1 << 16) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
-        }
-        std::sort(v.begin(), v.end());
-        v.erase(std::unique(v.begin(), v.end()), v.end());
-    }
-#pragma omp parallel for schedule(dynamic, 16)
-    for (int t = 0; t < nt; t++) {
-        const std::vector<int> &v = preds[t];
-        if (v.size() > 4096) { kept[t] = v; continue; }   // quadratic check not worth it: keep the full list (still correct)
-        for (size_t a = 0; a < v.size(); a++) {
-            bool implied = false;
-            for (size_t b = v.size(); b-- > a + 1 && !implied;) implied = std::binary_search(preds[v[b]].begin(), preds[v[b]].end(), v[a]);
-            if (!implied) kept[t].push_back(v[a]);
-        }
-    }
-    dep_ptr.assign(nt + 1, 0);
-    n_direct = 0;
-    max_deps = 0;
-    for (int t = 0; t < nt; t++) {
-        dep_ptr[t + 1] = dep_ptr[t] + (int)kept[t].size();
-        n_direct += (long long)preds[t].size();
-        max_deps = std::max(max_deps, (int)kept[t].size());
-    }
-    dep_idx.resize((size_t)dep_ptr[nt]);
-    for (int t = 0; t < nt; t++) std::copy(kept[t].begin(), kept[t].end(), dep_idx.begin() + dep_ptr[t]);
-}
 
 static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const double *locs, const int *NNarray, const int *coloring,
                             const int *n_obs_, const int *locs_match, const int *covfun_id, const int *device, const int *layout,
@@ -1305,12 +993,21 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     // processing order: storage ids sorted by colour (stable => storage order inside a colour)
     std::vector<int> psite(n), pof(n);   // psite[p] = storage id of processing site p; pof = inverse
     std::iota(psite.begin(), psite.end(), 0);
-    // (owned sites colour by colour, then -- sharded contexts only -- the ghost sites colour by colour)
+    // (owned sites colour by colour -- inside a colour of a sharded field the boundary sites, i.e. those some peer ghosts, come
+    // first so that their tiles run, and push their values to the peers, before the interior tiles; then the ghost sites)
+    std::vector<unsigned char> is_boundary(n, 0);   // by reference id
+    if (sh)
+        for (int k = 0; k < sh->send_ptr[(size_t)K * sh->world]; k++) {
+            const int ref = sh->send_site[k] - 1;
+            REQUIRE(ref >= 0 && ref < n && sh->owned[ref], "send_site[%d] is not an owned local site", k + 1);
+            is_boundary[ref] = 1;
+        }
     std::stable_sort(psite.begin(), psite.end(), [&](int a, int b) {
         const int ra = c->i2g[a], rb = c->i2g[b];
         const bool ga = is_ghost(ra), gb = is_ghost(rb);
         if (ga != gb) return gb;
-        return coloring[ra] < coloring[rb];
+        if (coloring[ra] != coloring[rb]) return coloring[ra] < coloring[rb];
+        return is_boundary[ra] > is_boundary[rb];
     });
     for (int p = 0; p < n; p++) pof[psite[p]] = p;
     c->cstart.assign(K + 1, 0);
@@ -1396,33 +1093,38 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         while (rows_padded.size() % 32) rows_padded.push_back(-1);
     }
     c->n_slots = (int)rows_padded.size();
-    // ---- sweep tiles: runs of consecutive same-colour sites with <= T sites and <= T*EPT CSC entries ----
-    std::vector<int4> tiles[4];
-    const int tcfg_threads[4] = {256, 128, 256, 64}, tcfg_ept[4] = {8, 8, 4, 8};
-    for (int cfg = 0; cfg < 4; cfg++) {
-        const int T = tcfg_threads[cfg], ECAP = T * tcfg_ept[cfg];
-        c->tile_ptr[cfg].assign(K + 1, 0);
+    // ---- sweep tiles: runs of consecutive same-colour sites with <= 128 sites and <= 1024 CSC entries; a tile never mixes
+    // boundary and interior sites ----
+    std::vector<int4> tiles;
+    {
+        const int T = 128, ECAP = 1024;
+        c->tile_ptr.assign(K + 1, 0);
+        c->btile_count.assign(K, 0);
         for (int col = 0; col < K; col++) {
             int s0 = c->cstart[col];
             const int send = c->cstart[col + 1];
+            int bend = s0;   // end of the colour's boundary sites
+            while (bend < send && is_boundary[c->i2g[psite[bend]]]) bend++;
             while (s0 < send) {
+                const int lim = s0 < bend ? bend : send;
                 int s1 = s0 + 1;   // at least one site (an oversize column is handled inside the kernel)
-                while (s1 < send && s1 - s0 < T && colptr[s1 + 1] - colptr[s0] <= ECAP) s1++;
-                tiles[cfg].push_back(make_int4(s0, s1, colptr[s0], colptr[s1]));
+                while (s1 < lim && s1 - s0 < T && colptr[s1 + 1] - colptr[s0] <= ECAP) s1++;
+                tiles.push_back(make_int4(s0, s1, colptr[s0], colptr[s1]));
+                if (s0 < bend) c->btile_count[col]++;
                 s0 = s1;
             }
-            c->tile_ptr[cfg][col + 1] = (int)tiles[cfg].size();
-            c->max_tiles[cfg] = std::max(c->max_tiles[cfg], c->tile_ptr[cfg][col + 1] - c->tile_ptr[cfg][col]);
+            c->tile_ptr[col + 1] = (int)tiles.size();
         }
     }
-    // local site id of every entry of the 128x8 tiles, one padded block of 1024 bytes per tile (blocked reduction of
+    // local site id of every entry of a tile, one padded block of 1024 bytes per tile (blocked reduction of
     // gibbs_tile2_kernel); an oversize single-site tile does not use it
-    std::vector<unsigned char> cloc((size_t)tiles[1].size() * 1024, (unsigned char)255);
-    for (size_t t = 0; t < tiles[1].size(); t++) {
-        const int4 tl = tiles[1][t];
+    std::vector<unsigned char> cloc((size_t)tiles.size() * 1024, (unsigned char)255);
+#pragma omp parallel for schedule(static)
+    for (long long t = 0; t < (long long)tiles.size(); t++) {
+        const int4 tl = tiles[t];
         if (tl.w - tl.z > 1024) continue;
         for (int q = tl.x; q < tl.y; q++)
-            for (int e = colptr[q]; e < colptr[q + 1]; e++) cloc[t * 1024 + (size_t)(e - tl.z)] = (unsigned char)(q - tl.x);
+            for (int e = colptr[q]; e < colptr[q + 1]; e++) cloc[(size_t)t * 1024 + (size_t)(e - tl.z)] = (unsigned char)(q - tl.x);
     }
     // ---- observations: lm in storage numbering (gathers of field); per-site lists / counts in processing order ----
     std::vector<int> lm(n_obs), optr(n + 1, 0), oidx(n_obs);
@@ -1450,71 +1152,11 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     CK(cudaMemsetAsync(c->d_nbad.p, 0, 2 * sizeof(int), s));
     c->d_ticket.alloc(1);
     c->d_rows_padded.upload(rows_padded, s);
-    for (int cfg = 0; cfg < 4; cfg++) { c->d_tiles[cfg].upload(tiles[cfg], s); c->d_tile_ptr[cfg].upload(c->tile_ptr[cfg], s); }
+    c->d_tiles.upload(tiles, s);
     c->d_cloc.upload(cloc, s);
-    if (!c->sharded && c->can_sweep) {   // fused tail of the sweep: the largest cluster the device can place, the colours it covers
-        for (int cl : {16, 8}) {
-            cudaLaunchConfig_t lt = {};
-            lt.gridDim = dim3(cl);
-            lt.blockDim = dim3(128);
-            cudaLaunchAttribute att[1];
-            att[0].id = cudaLaunchAttributeClusterDimension;
-            att[0].val.clusterDim.x = cl; att[0].val.clusterDim.y = 1; att[0].val.clusterDim.z = 1;
-            lt.attrs = att;
-            lt.numAttrs = 1;
-            int n_clusters = 0;
-            bool ok = true;
-            if (cl > 8) {
-                ok = cudaFuncSetAttribute(gibbs_tail_kernel<128, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-                     cudaFuncSetAttribute(gibbs_tail_kernel<128, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-            }
-            if (ok && cudaOccupancyMaxActiveClusters(&n_clusters, gibbs_tail_kernel<128, true>, &lt) == cudaSuccess && n_clusters >= 1) {
-                c->tail_cluster = cl;
-                break;
-            }
-            cudaGetLastError();
-        }
-        if (c->tail_cluster > 0) {
-            c->tail_first = c->K;
-            while (c->tail_first > 0 && c->tile_ptr[1][c->tail_first] - c->tile_ptr[1][c->tail_first - 1] <= c->tail_cluster) c->tail_first--;
-            if (c->tail_first == c->K) c->tail_cluster = 0;   // even the last colour is too large: nothing to fuse
-        }
-    }
-    if (!c->sharded && c->can_sweep) {   // dataflow sweep: tile dependency lists, epoch word + ticket + one flag sector per tile
-        std::vector<int> dep_ptr, dep_idx;
-        tile_dependencies(tiles[1], colptr, crow, nn, ld, M, pof, n, dep_ptr, dep_idx, c->flow_edges_direct, c->flow_max_deps);
-        c->flow_edges = (long long)dep_idx.size();
-        if (dep_idx.empty()) dep_idx.push_back(0);
-        c->d_dep_ptr.upload(dep_ptr, s);
-        c->d_dep_idx.upload(dep_idx, s);
-        c->d_flow.alloc((size_t)NNGP_FLOW_HEADER + tiles[1].size() * NNGP_FLOW_STRIDE);
-        CK(cudaMemsetAsync(c->d_flow.p, 0, c->d_flow.n * sizeof(unsigned int), s));
-        c->flow_ok = true;
-    }
-    c->d_pc0.alloc((size_t)n); c->d_pc1.alloc((size_t)n); c->d_pf.alloc((size_t)n);
-    c->d_bar.alloc(1);
-    c->d_cdone.alloc((size_t)std::max(1, c->K) * 2 * NNGP_CHAIN_STRIDE);
-    CK(cudaMemsetAsync(c->d_cdone.p, 0, c->d_cdone.n * sizeof(unsigned int), s));
-    {
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_persistent_kernel<256, 8>, 256, 0));
-        c->persistent_grid[0] = std::max(1, std::min(occ * c->n_sm, c->max_tiles[0]));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_persistent_kernel<128, 8>, 128, 0));
-        c->persistent_grid[1] = std::max(1, std::min(occ * c->n_sm, c->max_tiles[1]));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_persistent_kernel<256, 4>, 256, 0));
-        c->persistent_grid[2] = std::max(1, std::min(occ * c->n_sm, c->max_tiles[2]));
-        for (int cfg = 0; cfg < 3; cfg++) {
-            long long per_cta = 0;
-            for (int col = 0; col < K; col++) {
-                const int nt = c->tile_ptr[cfg][col + 1] - c->tile_ptr[cfg][col];
-                per_cta += (nt + c->persistent_grid[cfg] - 1) / c->persistent_grid[cfg];
-            }
-            c->persistent_ok[cfg] = (K <= 127) && (per_cta <= NNGP_PERSIST_CAP);
-        }
-    }
     c->d_tl.alloc((size_t)n * c->dt);
     for (int k = 0; k < 2; k++) { c->d_linv[k].alloc((size_t)ld * M); CK(cudaMemsetAsync(c->d_linv[k].p, 0, sizeof(double) * ld * M, s)); }
-    c->d_valT.alloc((size_t)c->nnz + 2);   // + 2: the bulk copies of gibbs_flow2_kernel are 16-byte granular
+    c->d_valT.alloc((size_t)c->nnz + 2);
     CK(cudaMemsetAsync(c->d_valT.p + c->nnz, 0, 2 * sizeof(double), s));
     c->d_pd.alloc(n); c->d_ymx.alloc(std::max(n_obs, 1)); c->d_S.alloc(n); c->d_field.alloc(n);
     c->d_newfield.alloc(n); c->d_r.alloc(n); c->d_tmp1.alloc(n); c->d_tmp2.alloc(n); c->d_io.alloc((size_t)std::max(n, n_obs));
@@ -1525,39 +1167,47 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         c->send_ptr.assign(sh->send_ptr, sh->send_ptr + (size_t)K * W + 1);
         c->recv_ptr.assign(sh->recv_ptr, sh->recv_ptr + (size_t)K * W + 1);
         std::vector<int> send_storage(c->send_ptr.back()), recv_proc(c->recv_ptr.back());
+        c->send_proc.resize(send_storage.size());
         for (size_t k = 0; k < send_storage.size(); k++) {
-            const int ref = sh->send_site[k] - 1;
-            REQUIRE(ref >= 0 && ref < n && sh->owned[ref], "send_site[%d] is not an owned local site", (int)k + 1);
+            const int ref = sh->send_site[k] - 1;   // (range and ownership were checked when the boundary sites were marked)
             send_storage[k] = c->g2i[ref];
+            c->send_proc[k] = pof[send_storage[k]];
         }
         for (size_t k = 0; k < recv_proc.size(); k++) {
             const int ref = sh->recv_site[k] - 1;
             REQUIRE(ref >= 0 && ref < n && !sh->owned[ref], "recv_site[%d] is not a ghost site", (int)k + 1);
             recv_proc[k] = pof[c->g2i[ref]];
         }
+        REQUIRE(W <= 8, "at most 8 ranks per field");
+        c->send_mask.assign(K, 0u);
+        c->recv_mask.assign(K, 0u);
+        for (int col = 0; col < K; col++)
+            for (int h = 0; h < W; h++) {
+                if (c->send_ptr[(size_t)col * W + h + 1] > c->send_ptr[(size_t)col * W + h]) c->send_mask[col] |= 1u << h;
+                if (c->recv_ptr[(size_t)col * W + h + 1] > c->recv_ptr[(size_t)col * W + h]) c->recv_mask[col] |= 1u << h;
+            }
         std::vector<unsigned char> owned_storage(n);
         for (int q = 0; q < n; q++) owned_storage[q] = sh->owned[c->i2g[q]] ? 1 : 0;
         c->d_send_storage.upload(send_storage, s);
         c->d_recv_proc.upload(recv_proc, s);
         c->d_owned.upload(owned_storage, s);
         c->d_sendbuf.alloc(std::max<size_t>(send_storage.size(), 1));
-        // the receive values live at the head of one plain cudaMalloc area that peers can map through CUDA IPC
-        REQUIRE(W <= 8, "at most 8 ranks per field");
-        // fixed header so that every rank knows where its peers' flags are: [16 halo flags | 16 reduction flags |
-        // 2 x 32 reduction slots | receive values ...]
-        const size_t nrecv = std::max<size_t>(recv_proc.size(), 1);
+        // the receive values live in one plain cudaMalloc area that peers can map through CUDA IPC.  Fixed header so that every
+        // rank knows where its peers' flags are: [16 halo flags | 16 reduction flags | 2 x 32 reduction slots | receive values of
+        // even sweeps | receive values of odd sweeps] (two parities: a peer one sweep ahead never overwrites unread values)
+        const size_t nrecv = (std::max<size_t>(recv_proc.size(), 1) + 15) / 16 * 16;
         c->p2p_flag_off = 0;
         c->p2p_rflag_off = 16;
         c->p2p_slot_off = 32;
         c->p2p_val_off = 96;
-        c->p2p_doubles = std::max<size_t>(c->p2p_val_off + nrecv, (size_t)1 << 18);   // >= 2 MB: a whole allocation of its own
+        c->p2p_parity_stride = nrecv;
+        c->p2p_doubles = std::max<size_t>(c->p2p_val_off + 2 * nrecv, (size_t)1 << 18);   // >= 2 MB: a whole allocation of its own
         CK(cudaMalloc(&c->p2p_area, c->p2p_doubles * sizeof(double)));
         CK(cudaMemsetAsync(c->p2p_area, 0, c->p2p_doubles * sizeof(double), s));
         c->d_recvbuf.p = c->p2p_area + c->p2p_val_off;      // not owned by the DevBuf (released with the area)
         c->d_recvbuf.n = 0;
-        c->d_send_ptr.upload(c->send_ptr, s);
-        c->d_halo_epoch.alloc(2);
-        CK(cudaMemsetAsync(c->d_halo_epoch.p, 0, 2 * sizeof(unsigned long long), s));
+        c->d_shard_state.alloc((size_t)K + 1);
+        CK(cudaMemsetAsync(c->d_shard_state.p, 0, ((size_t)K + 1) * sizeof(unsigned long long), s));
         CK(cudaStreamSynchronize(s));
         if (W > 1 && sh->comm_id[0] != '\0') {   // collective: every rank of the field creates its context at the same time
             nccl_load();
@@ -1621,61 +1271,18 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
     use(c);
     CK(cudaStreamSynchronize(c->stream));
     switch (*key) {
-        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 37, "sweep variant must be 0..37"); c->sweep_variant = *value; break;
+        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 3, "sweep variant must be 0..3"); c->sweep_variant = *value; break;
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;
-        case NNGP_OPT_FACTOR_VARIANT: REQUIRE(*value >= 0 && *value <= 3, "factor variant must be 0..3"); c->factor_variant = *value; break;
         case NNGP_OPT_LOGLIK_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "loglik variant must be 0..1"); c->loglik_variant = *value; break;
         case NNGP_OPT_MATERN_TABLE: c->matern_table = (*value != 0); break;
-        case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 2, "commit variant must be 0..2"); c->commit_variant = *value; break;
+        case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "commit variant must be 0..1"); c->commit_variant = *value; break;
         case NNGP_OPT_SOLVE_WINDOW_CTAS: REQUIRE(*value >= 0 && *value <= 4096, "solve window must be 0..4096 CTAs"); c->solve_window_ctas = *value; break;
-        case NNGP_OPT_DEBUG_TIMELINE: {
-            c->debug_timeline = (*value != 0);
-            long long zero = 0;
-            if (c->debug_timeline) CK(cudaMemcpyToSymbol(g_timeline, &zero, sizeof(long long), sizeof(long long) * 8191));
-        } break;
-        case NNGP_OPT_CHAIN_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "chain sleep must be 0..100000 ns"); c->chain_sleep_ns = *value; break;
         case NNGP_OPT_SOLVE_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "solve sleep must be 0..100000 ns"); c->solve_sleep_ns = *value; break;
         default: REQUIRE(false, "unknown option key %d", *key);
     }
     if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; }
-    ABI_END
-}
-
-void nngp_debug_timeline(double *out, const int *n_out, int *n_written, int *status) {
-    ABI_BEGIN
-    REQUIRE(out && n_out && n_written, "nngp_debug_timeline: null argument");
-    std::vector<long long> h(8192);
-    CK(cudaDeviceSynchronize());
-    CK(cudaMemcpyFromSymbol(h.data(), g_timeline, sizeof(long long) * 8192));
-    const int cnt = (int)std::min<long long>(std::min<long long>(h[8191], 4090), *n_out / 2);
-    for (int i = 0; i < cnt; i++) { out[2 * i] = (double)(h[2 * i] - h[0]); out[2 * i + 1] = (double)h[2 * i + 1]; }
-    *n_written = cnt;
-    ABI_END
-}
-
-void nngp_debug_colour_phases(const int *ctx_id, double *out, int *status) {
-    ABI_BEGIN
-    Ctx *c = get_ctx(ctx_id);
-    REQUIRE(out != nullptr && c->K * 16 <= 4096, "nngp_debug_colour_phases: bad argument");
-    std::vector<long long> h((size_t)c->K * 16);
-    CK(cudaDeviceSynchronize());
-    CK(cudaMemcpyFromSymbol(h.data(), g_timeline, sizeof(long long) * h.size(), sizeof(long long) * 4096));
-    for (size_t i = 0; i < h.size(); i++) out[i] = (double)h[i];
-    ABI_END
-}
-
-void nngp_debug_colour_times(const int *ctx_id, double *out, int *status) {
-    ABI_BEGIN
-    Ctx *c = get_ctx(ctx_id);
-    REQUIRE(out != nullptr && c->K * 4 <= 4096, "nngp_debug_colour_times: bad argument");
-    std::vector<long long> h((size_t)c->K * 4);
-    CK(cudaDeviceSynchronize());
-    CK(cudaMemcpyFromSymbol(h.data(), g_timeline, sizeof(long long) * h.size()));
-    long long t0 = h[2];
-    for (size_t i = 0; i < h.size(); i++) if (h[i] > 0 && h[i] < t0) t0 = h[i];
-    for (size_t i = 0; i < h.size(); i++) out[i] = (double)(h[i] - t0);
     ABI_END
 }
 
@@ -1877,7 +1484,7 @@ void nngp_gibbs_sweep(const int *ctx_id, const int *n_sweeps, const double *beta
     }
     set_sweep_params(c, *beta_0, *log_scale, *log_noise_variance, *rng_mode, seed ? *seed : 0.0);
     refresh_r(c, *beta_0);
-    op_sweeps(c, *n_sweeps, 0);
+    op_sweeps(c, *n_sweeps);
     c->sweep_counter += (unsigned long long)*n_sweeps;
     CK(cudaStreamSynchronize(c->stream));
     if (c->p2p) check_solve_flag(c);
@@ -1897,6 +1504,27 @@ void nngp_shard_p2p_export(const int *ctx_id, char *handle64, int *status) {
     ABI_END
 }
 
+// after the peers' areas are known: destinations of every boundary site's value (peer, slot inside the peer's receive values)
+static void finish_p2p_connect(Ctx *c, const int *peer_recv_base) {
+    const int W = c->world, K = c->K;
+    std::vector<int> bptr((size_t)c->n_owned + 1, 0);
+    for (size_t k = 0; k < c->send_proc.size(); k++) bptr[(size_t)c->send_proc[k] + 1]++;
+    for (int q = 0; q < c->n_owned; q++) bptr[q + 1] += bptr[q];
+    std::vector<int2> bdst(std::max<size_t>(c->send_proc.size(), 1));
+    std::vector<int> pos(bptr.begin(), bptr.end() - 1);
+    for (int col = 0; col < K; col++)
+        for (int h = 0; h < W; h++) {
+            const int a = c->send_ptr[(size_t)col * W + h], b = c->send_ptr[(size_t)col * W + h + 1];
+            for (int k = a; k < b; k++) bdst[pos[c->send_proc[k]]++] = make_int2(h, peer_recv_base[(size_t)col * W + h] + (k - a));
+        }
+    c->d_bptr.upload(bptr, c->stream);
+    c->d_bdst.upload(bdst, c->stream);
+    CK(cudaMemsetAsync(c->d_shard_state.p, 0, ((size_t)K + 1) * sizeof(unsigned long long), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; }
+    c->p2p = true;
+}
+
 void nngp_shard_p2p_connect(const int *ctx_id, const char *all_handles, const int *peer_recv_base, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
@@ -1913,10 +1541,105 @@ void nngp_shard_p2p_connect(const int *ctx_id, const char *all_handles, const in
         c->peer_mapped[h] = p;
         c->peers.area[h] = static_cast<double *>(p);
     }
-    std::vector<int> base(peer_recv_base, peer_recv_base + (size_t)c->K * W);
-    c->d_peer_base.upload(base, c->stream);
-    CK(cudaStreamSynchronize(c->stream));
-    c->p2p = true;
+    finish_p2p_connect(c, peer_recv_base);
+    ABI_END
+}
+
+// single-process form: the W contexts of the field live in this process (one per GPU -- what an R session with several GPUs
+// has -- or several on one GPU); their areas are addressed directly, peer access is enabled between distinct devices
+void nngp_shard_connect_local(const int *ctx_ids, const int *world, int *status) {
+    ABI_BEGIN
+    REQUIRE(ctx_ids && world && *world >= 1 && *world <= 8, "nngp_shard_connect_local: bad argument");
+    const int W = *world;
+    std::vector<Ctx *> cs(W);
+    for (int h = 0; h < W; h++) {
+        cs[h] = get_ctx(ctx_ids + h);
+        NEED(cs[h]->sharded && cs[h]->p2p_area && cs[h]->world == W && cs[h]->rank == h, "nngp_shard_connect_local: context h must be rank h of a W-rank sharded field");
+        NEED(cs[h]->K == cs[0]->K, "nngp_shard_connect_local: the contexts belong to different fields");
+    }
+    for (int g = 0; g < W; g++) {
+        Ctx *c = cs[g];
+        use(c);
+        std::vector<int> base((size_t)c->K * W, 0);
+        for (int h = 0; h < W; h++) {
+            c->peers.area[h] = cs[h]->p2p_area;
+            if (h == g) continue;
+            if (cs[h]->device != c->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, c->device, cs[h]->device));
+                REQUIRE(can, "device %d cannot access device %d", c->device, cs[h]->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(cs[h]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+                cudaGetLastError();
+            }
+            for (int col = 0; col < c->K; col++) {
+                const int mine = c->send_ptr[(size_t)col * W + h + 1] - c->send_ptr[(size_t)col * W + h];
+                const int theirs = cs[h]->recv_ptr[(size_t)col * W + g + 1] - cs[h]->recv_ptr[(size_t)col * W + g];
+                REQUIRE(mine == theirs, "nngp_shard_connect_local: rank %d sends %d values of colour %d to rank %d, which expects %d", g, mine, col + 1, h, theirs);
+                base[(size_t)col * W + h] = cs[h]->recv_ptr[(size_t)col * W + g];
+            }
+        }
+        finish_p2p_connect(c, base.data());
+    }
+    ABI_END
+}
+
+// enqueues n_sweeps sweeps on every member of a locally connected field, then waits for all of them (the members exchange
+// their halos among themselves while they run)
+void nngp_shard_group_sweep(const int *ctx_ids, const int *world, const int *n_sweeps, const double *beta_0, const double *log_scale,
+                            const double *log_noise_variance, const int *rng_mode, const double *z, const double *seed, int *status) {
+    ABI_BEGIN
+    REQUIRE(ctx_ids && world && n_sweeps && beta_0 && log_scale && log_noise_variance && rng_mode && *world >= 1 && *world <= 8 && *n_sweeps >= 0, "nngp_shard_group_sweep: bad argument");
+    REQUIRE(*rng_mode == NNGP_RNG_PHILOX || (*rng_mode == NNGP_RNG_SUPPLIED && z != nullptr), "nngp_shard_group_sweep: rng_mode 0 needs z");
+    const int W = *world;
+    std::vector<Ctx *> cs(W);
+    for (int h = 0; h < W; h++) {
+        cs[h] = get_ctx(ctx_ids + h);
+        NEED(cs[h]->sharded && (cs[h]->p2p || W == 1), "nngp_shard_group_sweep: the contexts are not connected (nngp_shard_connect_local)");
+        NEED(cs[h]->have_slot(NNGP_SLOT_CURRENT) && cs[h]->have_field && cs[h]->have_obs, "nngp_shard_group_sweep: factor, field and observations must be set first");
+    }
+    for (Ctx *c : cs) {
+        use(c);
+        if (!c->committed) op_commit(c);
+        const size_t nz = (size_t)c->n_global * (size_t)std::max(1, *n_sweeps);
+        if (*rng_mode == NNGP_RNG_SUPPLIED) {
+            ensure_zbuf(c, nz);
+            CK(cudaMemcpyAsync(c->d_zbuf.p, z, sizeof(double) * nz, cudaMemcpyHostToDevice, c->stream));
+        }
+        set_sweep_params(c, *beta_0, *log_scale, *log_noise_variance, *rng_mode, seed ? *seed : 0.0);
+        refresh_r(c, *beta_0);
+    }
+    for (int s = 0; s < *n_sweeps; s++)       // sweep by sweep over the members: no stream runs far ahead of its peers
+        for (Ctx *c : cs) { use(c); op_sweeps(c, 1); }
+    for (Ctx *c : cs) {
+        use(c);
+        c->sweep_counter += (unsigned long long)*n_sweeps;
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    for (Ctx *c : cs) { use(c); check_solve_flag(c); }
+    ABI_END
+}
+
+// all-reduced scalars of a locally connected field: [sum log diag, sum u^2] of the log-likelihood -> ll (identical on every member)
+void nngp_shard_group_loglik(const int *ctx_ids, const int *world, const int *slot, const double *beta_0, const double *log_scale,
+                             double *ll, int *status) {
+    ABI_BEGIN
+    REQUIRE(ctx_ids && world && slot && beta_0 && log_scale && ll && *world >= 1 && *world <= 8 && (*slot == 0 || *slot == 1), "nngp_shard_group_loglik: bad argument");
+    const int W = *world;
+    std::vector<Ctx *> cs(W);
+    for (int h = 0; h < W; h++) {
+        cs[h] = get_ctx(ctx_ids + h);
+        NEED(cs[h]->sharded && (cs[h]->p2p || W == 1), "nngp_shard_group_loglik: the contexts are not connected (nngp_shard_connect_local)");
+        NEED(cs[h]->have_slot(*slot) && cs[h]->have_field, "nngp_shard_group_loglik: factor and field must be set first");
+    }
+    for (Ctx *c : cs) { use(c); op_loglik_sums(c, c->linv_slot(*slot), c->d_field.p, *beta_0, 0); }
+    for (int h = 0; h < W; h++) {
+        Ctx *c = cs[h];
+        use(c);
+        fetch_scalars(c, 2);
+        ll[h] = ll_from_sums(c, c->h_pinned[0], c->h_pinned[1], *log_scale);
+    }
+    for (Ctx *c : cs) { use(c); check_solve_flag(c); }
     ABI_END
 }
 
@@ -1948,9 +1671,9 @@ void nngp_shard_sweep_colour(const int *ctx_id, const int *colour, int *status) 
     NEED(c->sharded, "nngp_shard_sweep_colour: not a sharded context");
     use(c);
     const int col = *colour - 1;
-    const int t0 = c->tile_ptr[1][col], nt = c->tile_ptr[1][col + 1] - t0;
+    const int t0 = c->tile_ptr[col], nt = c->tile_ptr[col + 1] - t0;
     if (nt > 0) {
-        gibbs_tile2_kernel<128, false, 5, 2><<<nt, 128, 0, c->stream>>>(c->d_tiles[1].p + t0, t0, c->d_colptr.p, c->d_crow.p, c->d_cloc.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, (long long *)nullptr, 0);
+        gibbs_tile2_kernel<128, false, 5, 2><<<nt, 128, 0, c->stream>>>(c->d_tiles.p + t0, t0, c->d_colptr.p, c->d_crow.p, c->d_cloc.p, c->d_valT.p, c->d_pd.p, c->d_nobs.p, c->d_S.p, c->d_zpos.p, c->d_gid.p, c->d_psite.p, c->d_zbuf.p, c->d_sp.p, c->d_field.p, c->d_r.p, ShardConst{}, ShardColour{});
         LAUNCHED(c);
     }
     CK(cudaGetLastError());
@@ -1998,7 +1721,7 @@ void nngp_shard_sweep_end(const int *ctx_id, int *status) {
     Ctx *c = get_ctx(ctx_id);
     NEED(c->sharded, "nngp_shard_sweep_end: not a sharded context");
     use(c);
-    advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, c->d_cdone.p, c->K);
+    advance_sweep_kernel<<<1, 32, 0, c->stream>>>(c->d_sp.p, (unsigned long long)c->n_global, nullptr);
     LAUNCHED(c);
     c->sweep_counter += 1ull;
     CK(cudaStreamSynchronize(c->stream));
@@ -2353,7 +2076,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
         }
         set_sweep_params(c, beta_0, log_scale, lnv, rng_mode, (double)philox_seed);
         refresh_r(c, beta_0);
-        op_sweeps(c, n_chromatic, 0);
+        op_sweeps(c, n_chromatic);
         c->sweep_counter += (unsigned long long)n_chromatic;
         mark(3);
         // ---- (E) noise variance :281-293 ----
@@ -2535,12 +2258,12 @@ void nngp_time_op(const int *ctx_id, const int *op_, const int *reps_, const int
         switch (op) {
             case 0: op_factor_build(c, NNGP_SLOT_PROPOSAL, c->last_cc); break;
             case 1: op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, 0); break;
-            case 2: op_sweeps(c, 1, 0); c->sweep_counter++; break;
+            case 2: op_sweeps(c, 1); c->sweep_counter++; break;
             case 3: op_spmv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, c->d_tmp1.p); break;
             case 4: op_spmv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, c->d_tmp1.p);
                     op_sptrsv(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_tmp1.p, c->d_tmp2.p, nullptr, 0.0, 1.0); break;
             case 5: op_commit(c); break;
-            case 6: op_sweeps(c, 1, 0); c->sweep_counter++;
+            case 6: op_sweeps(c, 1); c->sweep_counter++;
                     op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, 0); break;
             default: REQUIRE(false, "nngp_time_op: unknown op %d", op);
         }

@@ -131,6 +131,38 @@ def host_routed_sweep(contexts, beta_0, log_scale, log_noise_variance, z=None, s
         c.sweep_end()
 
 
+def connect_local(contexts):
+    """Connects the shards of one field that live in this process (one per GPU, or several on one GPU): afterwards
+    group_sweep / group_loglik run the fused peer-to-peer halo exchange between them."""
+    ids = (C.c_int * len(contexts))(*[c._id for c in contexts])
+    st = C.c_int(0)
+    L.load().nngp_shard_connect_local(ids, L.ci(len(contexts)), C.byref(st))
+    L.check(st)
+
+
+def group_sweep(contexts, beta_0, log_scale, log_noise_variance, n_sweeps=1, z=None, seed=0):
+    ids = (C.c_int * len(contexts))(*[c._id for c in contexts])
+    st = C.c_int(0)
+    if z is None:
+        L.load().nngp_shard_group_sweep(ids, L.ci(len(contexts)), L.ci(n_sweeps), L.cd(beta_0), L.cd(log_scale), L.cd(log_noise_variance),
+                                        L.ci(L.RNG_PHILOX), None, L.cd(seed), C.byref(st))
+    else:
+        zz = L.f64(z)
+        assert zz.size == n_sweeps * contexts[0].plan["n_global"]
+        L.load().nngp_shard_group_sweep(ids, L.ci(len(contexts)), L.ci(n_sweeps), L.cd(beta_0), L.cd(log_scale), L.cd(log_noise_variance),
+                                        L.ci(L.RNG_SUPPLIED), L.dptr(zz), L.cd(seed), C.byref(st))
+    L.check(st)
+
+
+def group_loglik(contexts, beta_0, log_scale, slot=L.SLOT_CURRENT) -> np.ndarray:
+    ids = (C.c_int * len(contexts))(*[c._id for c in contexts])
+    st = C.c_int(0)
+    out = np.zeros(len(contexts))
+    L.load().nngp_shard_group_loglik(ids, L.ci(len(contexts)), L.ci(slot), L.cd(beta_0), L.cd(log_scale), L.dptr(out), C.byref(st))
+    L.check(st)
+    return out
+
+
 def create_sharded_distributed(locs, NNarray, coloring, locs_match, covfun_name, device, dist, transport="p2p"):
     """torch.distributed driver: every rank calls this with the same (replicated) global structure.  transport "p2p" maps the
     peers' receive areas through CUDA IPC (halo values are stored straight into the peers' memory over NVLink); "nccl"
@@ -138,6 +170,7 @@ def create_sharded_distributed(locs, NNarray, coloring, locs_match, covfun_name,
     rank, world = dist.get_rank(), dist.get_world_size()
     owner = spatial_blocks(locs, world)
     plan = shard_plan(locs, NNarray, coloring, locs_match, owner, rank, world)
+    del owner
     box = [comm_unique_id() if (rank == 0 and transport == "nccl") else None]
     dist.broadcast_object_list(box, src=0)
     ctx = ShardedContext(plan, covfun_name, device=device, comm_id=box[0])

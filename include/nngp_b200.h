@@ -85,7 +85,8 @@ void nngp_host_order_maxmin(const double *locs, const int *n, const int *d, int 
 /* locs n x d; NNarray n x (m+1); coloring n (1..K, verified to be proper for the moral graph; ALL ZERO = no colouring:
  * a context that never sweeps, e.g. the joint observed ++ predicted site set of mcmc_nngp_predict_field, predict.R:4-8 --
  * its sweep entry points return NNGP_ERR_STATE); locs_match n_obs (1-based site of each observation);
- * device: CUDA ordinal; layout: NNGP_LAYOUT_*.  Returns a context id. */
+ * device: CUDA ordinal; layout: NNGP_LAYOUT_*.  Returns a context id.
+ * Limits: 1 <= d <= 4, 1 <= m <= 31, n * (m + 1) < 2^31 (entry positions are int32; n <= 195M at m = 10, 102M at m = 20). */
 void nngp_ctx_create(const int *n, const int *d, const int *m, const double *locs, const int *NNarray,
                      const int *coloring, const int *n_obs, const int *locs_match, const int *covfun_id,
                      const int *device, const int *layout, int *ctx_id, int *status);
@@ -101,8 +102,9 @@ void nngp_ctx_destroy(const int *ctx_id, int *status);
  *   global_zpos[n]  position of the site in the whole field's rnorm() hand-out order (NNGP_RNG_SUPPLIED mode)
  *   send_site / send_ptr   owned boundary sites per (colour, peer): segment [send_ptr[c*world+h], send_ptr[c*world+h+1])
  *   recv_site / recv_ptr   ghost sites per (colour, peer), in the same order as the owner sends them
- * On such a context nngp_gibbs_sweep exchanges the boundary values after every colour (ncclSend/ncclRecv) and
- * nngp_loglik / nngp_ssr / nngp_beta0_moments all-reduce their partial sums; observations are those of the owned sites.
+ * On such a context nngp_gibbs_sweep exchanges the boundary values of every colour (peer-to-peer transport below: fused into
+ * the sweep kernel; NCCL: ncclSend/ncclRecv after it) and nngp_loglik / nngp_ssr / nngp_beta0_moments all-reduce their partial
+ * sums; observations are those of the owned sites.  Limits: at most 8 ranks per field.
  * Triangular solves (ancillary step, initial draw, prediction) are not available on a sharded context. */
 void nngp_comm_unique_id(char *id128, int *status);
 void nngp_ctx_create_sharded(const int *n, const int *d, const int *m, const double *locs, const int *NNarray,
@@ -114,8 +116,10 @@ void nngp_ctx_create_sharded(const int *n, const int *d, const int *m, const dou
 /* Peer-to-peer transport for the halo and the scalar all-reduces (preferred inside one NVLink box): every rank exports the
  * CUDA IPC handle (64 bytes) of its receive area, the handles are gathered by the caller, and every rank connects with the
  * table of all handles (world * 64 bytes, rank order) plus peer_recv_base[c*world + h] = offset of this rank's colour-c
- * segment inside peer h's receive area (= peer h's recv_ptr[c*world + this rank]).  Afterwards the sweep kernels' boundary
- * values are stored directly into the peers' ghost buffers over NVLink and flags replace the NCCL calls. */
+ * segment inside peer h's receive area (= peer h's recv_ptr[c*world + this rank]).  Afterwards the sweep kernel of a colour
+ * stores the new values of its boundary sites (their tiles run first) directly into the peers' ghost slots over NVLink and
+ * raises a flag there; the ghost values that arrive are applied by trailing CTAs of the same launch, which wait only for the
+ * peers that actually send in that colour.  Scalar all-reduces use the same mapped areas. */
 void nngp_shard_p2p_export(const int *ctx_id, char *handle64, int *status);
 void nngp_shard_p2p_connect(const int *ctx_id, const char *all_handles, const int *peer_recv_base, int *status);
 /* Colour-stepping form of one sharded sweep for callers that move the halo themselves (any transport; also how the sharded
@@ -128,14 +132,37 @@ void nngp_shard_sweep_colour(const int *ctx_id, const int *colour, int *status);
 void nngp_shard_halo_get(const int *ctx_id, const int *colour, double *out, int *status);
 void nngp_shard_halo_put(const int *ctx_id, const int *colour, const double *in, int *status);
 void nngp_shard_sweep_end(const int *ctx_id, int *status);
+/* single-process form of the same transport: the W contexts of the field live in this process (one per GPU -- what an R
+ * session on a multi-GPU box has -- or several on one GPU); ctx_ids[h] must be rank h.  Their receive areas are addressed
+ * directly (peer access is enabled between distinct devices), no IPC handles are needed. */
+void nngp_shard_connect_local(const int *ctx_ids, const int *world, int *status);
+/* n_sweeps sweeps of a locally connected field: enqueued on every member, then all are waited for (the members exchange their
+ * halos among themselves while they run).  z (NNGP_RNG_SUPPLIED): n_sweeps * n_global normals in the whole field's hand-out order */
+void nngp_shard_group_sweep(const int *ctx_ids, const int *world, const int *n_sweeps, const double *beta_0, const double *log_scale,
+                            const double *log_noise_variance, const int *rng_mode, const double *z, const double *seed, int *status);
+/* Vecchia log-likelihood of a locally connected field (partial sums all-reduced between the members): ll[h] for every member h,
+ * all equal */
+void nngp_shard_group_loglik(const int *ctx_ids, const int *world, const int *slot, const double *beta_0, const double *log_scale,
+                             double *ll, int *status);
+/* host-side set-up of a sharded field (replaces nothing in the reference, which has no multi-GPU path):
+ * owner[n] = spatial block (0..n_parts-1) of every site by recursive coordinate bisection into equal counts */
+void nngp_host_spatial_blocks(const double *locs, const int *n, const int *d, const int *n_parts, int *owner, int *status);
+/* everything rank `rank` needs for nngp_ctx_create_sharded, derived from the whole field's structure in O(n (m+1)):
+ * build returns a plan id and sizes6 = [n_local, n_obs_local, n_send, n_recv, n_colors, n_owned]; get copies the arrays into
+ * caller-allocated buffers (locs n_local x d; NNarray n_local x (m+1); coloring / owned / global_id / global_zpos n_local;
+ * obs_index (0-based index into the field's observations) / locs_match n_obs_local; send_site n_send; recv_site n_recv;
+ * send_ptr / recv_ptr n_colors * world + 1) and frees the plan.  At most 8 ranks. */
+void nngp_host_shard_plan_build(const double *locs, const int *NNarray, const int *coloring, const int *n, const int *d, const int *m,
+                                const int *n_obs, const int *locs_match, const int *owner, const int *rank, const int *world,
+                                int *plan_id, int *sizes6, int *status);
+void nngp_host_shard_plan_get(const int *plan_id, double *locs, int *NNarray, int *coloring, int *owned, int *global_id, int *global_zpos,
+                              int *obs_index, int *locs_match, int *send_site, int *send_ptr, int *recv_site, int *recv_ptr, int *status);
 /* performance knobs (results are identical up to FP64 summation order):
- *   NNGP_OPT_SWEEP_VARIANT 6 = one launch per colour, 128-thread CTAs x 8 entries/thread, chained with programmatic
- *                          dependent launch (the r-independent prologue of colour c+1 overlaps colour c) and replayed from
- *                          a CUDA graph (default); 7 = same with 256x8 tiles; 2 / 1 = the same tiles without PDL;
- *                          3 = one launch per colour, thread per site; 0 / 4 / 5 = persistent cooperative kernel (grid
- *                          barrier between colours, next tile prefetched across the barrier) with 256x8 / 256x4 / 128x8 tiles;
- *                          9 / 10 = flag-chained launches (128x8 / 256x8 tiles): programmatic dependent launches that never
- *                          wait on the previous grid, the colour hand-off is a device counter (release / acquire)
+ *   NNGP_OPT_SWEEP_VARIANT 0 = one launch per colour, tiles of <= 128 sites / 1024 factor entries per CTA, blocked segmented
+ *                          reduction, chained with programmatic dependent launch (the r-independent prologue of colour c+1
+ *                          overlaps colour c), replayed from a CUDA graph; colours that would spill into a second wave at
+ *                          5 CTAs/SM run a 6-CTAs/SM build (default); 1 = the same chain with 5 CTAs/SM everywhere;
+ *                          2 = the same tiles as plain launches; 3 = thread per site (unsharded contexts)
  *   NNGP_OPT_SOLVE_VARIANT 0 = synchronisation-free single-launch triangular solve; 1 = one launch per DAG level
  *   NNGP_OPT_USE_GRAPH     1 = the colour launches of a sweep are replayed from a captured CUDA graph (default) */
 #define NNGP_OPT_SWEEP_VARIANT 1
@@ -144,21 +171,10 @@ void nngp_shard_sweep_end(const int *ctx_id, int *status);
 #define NNGP_OPT_SOLVE_CTAS_PER_SM 4 /* window of the sync-free solve: n_sm * value * 256 rows in flight (default 1) */
 #define NNGP_OPT_SOLVE_SLEEP_NS 5    /* back-off between dependency polls (default 0) */
 #define NNGP_OPT_SOLVE_WINDOW_CTAS 7  /* absolute window of the sync-free solve in CTAs of 256 rows (0 = use per-SM setting) */
-#define NNGP_OPT_COMMIT_VARIANT 8     /* accept-branch transposition: 0 = tiled, blocked reduction (default), 1 = thread per column, 2 = tiled, segment sums */
+#define NNGP_OPT_COMMIT_VARIANT 8     /* accept-branch transposition: 0 = tiled, blocked reduction (default), 1 = thread per column */
 #define NNGP_OPT_MATERN_TABLE 9       /* Matern families: 1 = per-build interpolation table of the kernel (default), 0 = K_nu per pair */
 #define NNGP_OPT_LOGLIK_VARIANT 10    /* log-lik pass: 1 = plain coalesced loads (default, faster); 0 = TMA-staged shared-memory ring (cp.async.bulk + mbarrier) */
-#define NNGP_OPT_FACTOR_VARIANT 11    /* m = 10, d = 2 factor kernel register cap: 0 = none (default), 1 = 128, 2 = 96 registers */
-#define NNGP_OPT_CHAIN_SLEEP_NS 12     /* flag-chained sweep: back-off between polls of the colour counter (default 0) */
-#define NNGP_OPT_DEBUG_TIMELINE 6    /* development aid: the persistent sweep kernel stamps %globaltimer per stage */
 void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);
-/* development aid: with NNGP_OPT_DEBUG_TIMELINE and the PDL chain (sweep variant 6), per colour c of the last sweep
- * out[4c..4c+3] = ns (relative) at which [the last CTA reached griddepcontrol.wait, the first CTA was released,
- * the first CTA finished its scatter, the last CTA finished its scatter] */
-void nngp_debug_colour_times(const int *ctx_id, double *out, int *status);
-/* same run: out[16c..16c+4] = ns summed over the CTAs of colour c spent in [entry stream + site constants, griddepcontrol.wait,
- * r gather + products, segment sums + draw, scatter issue]; out[16c+7] = number of CTAs; out[16c+8..11] = the first phase
- * split (thread 0) into [tile descriptor, per-site loads, draw + constants, rest of the entry stream] */
-void nngp_debug_colour_phases(const int *ctx_id, double *out, int *status);
 /* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,
  * [6]=device, [7]=layout */
 void nngp_ctx_info(const int *ctx_id, int *info8, int *status);
@@ -291,8 +307,6 @@ void nngp_predict_sample(const int *ctx_id, const int *slot, const int *n_obs_si
  * per repetition. flush_l2 != 0 writes a 256 MB scratch buffer between repetitions (outside the timed events). */
 void nngp_time_op(const int *ctx_id, const int *op, const int *reps, const int *flush_l2, double *ms_out,
                   int *launches_out, int *status);
-/* development aid: (time ns, stage id) pairs stamped by CTA 0 of the last persistent sweep launch (NNGP_OPT_DEBUG_TIMELINE) */
-void nngp_debug_timeline(double *out, const int *n_out, int *n_written, int *status);
 /* Page-locked host buffers.  Vectors handed to the library from such a buffer are DMA-ed directly (no staging copy); any other
  * host pointer is staged through an internal pinned buffer with a multi-threaded copy.  n_bytes is a double so that .C() can
  * pass sizes beyond 2^31. */

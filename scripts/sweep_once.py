@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 import nngp_b200 as nb
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-variant = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 sweeps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 m = 10
 rng = np.random.default_rng(1)

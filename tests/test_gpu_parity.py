@@ -323,11 +323,11 @@ def test_error_paths():
     assert "not proper" in str(e.value)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("n,m", [(20000, 10), (3000, 5)])
 def test_every_sweep_variant_matches_the_reference_loop(variant, n, m):
-    """All kernel variants of the sweep (tiled launches, persistent cooperative kernel, PDL chain, dataflow launch, thread-per-site) are the
-    same map given the same normals; multi-sweep launches included (n = 20000 gives several CTAs per colour)."""
+    """All kernel variants of the sweep (PDL chain of tiles with and without the 6-CTAs/SM build, plain tiled launches, thread-per-site)
+    are the same map given the same normals; multi-sweep launches included (n = 20000 gives several CTAs per colour)."""
     P = make_problem(n, m, seed=77, n_extra_obs=n // 20)
     cp = [1.0, 0.05, 0.0]
     beta_0, ls, lnv = -0.2, 0.3, -0.9
@@ -377,7 +377,7 @@ def test_both_solve_variants(solve_variant):
         assert rel_vec(ctx.sptrsv(v), O.sparse_chol_solve(Lo, P["NNarray"], v)) < 1e-9
 
 
-@pytest.mark.parametrize("commit_variant", [0, 1, 2])
+@pytest.mark.parametrize("commit_variant", [0, 1])
 def test_both_transposition_variants(commit_variant):
     P = make_problem(20000, 10, seed=14)
     cp = [1.0, 0.05, 0.0]

@@ -77,6 +77,46 @@ def test_host_routed_sharded_sweep_equals_unsharded(parts):
             c.close()
 
 
+@pytest.mark.parametrize("parts,n", [(2, 30000), (3, 20000), (4, 60000), (8, 40000)])
+def test_fused_peer_to_peer_sweep_on_one_gpu_equals_unsharded(parts, n):
+    """The production transport -- boundary tiles push into the peers' ghost slots from inside the sweep kernel, trailing ghost
+    CTAs wait on the peers' flags and apply -- with every shard in this process on one GPU (nngp_shard_connect_local): the
+    flag / epoch / parity protocol, the per-colour peer masks and the PDL chain are exactly those of the multi-GPU run."""
+    P = make_problem(n, 10, seed=15, n_extra_obs=300)
+    n_sweeps = 3
+    z = P["rng"].standard_normal(n_sweeps * n)
+    f_ref, ll0_ref, ll1_ref, ssr_ref, _ = reference(P, n_sweeps, z=z)
+    ctxs = shard_contexts(P, parts)
+    try:
+        nb.connect_local(ctxs)
+        ll = nb.group_loglik(ctxs, B0, LS)
+        assert np.all(np.abs(ll - ll0_ref) < 1e-10 * abs(ll0_ref)) and np.all(ll == ll[0])   # rank-ordered sum: identical on every member
+        nb.group_sweep(ctxs, B0, LS, LNV, n_sweeps=n_sweeps, z=z)
+        f = gather_owned(ctxs, n)
+        assert np.max(np.abs(f - f_ref)) < 1e-10 * np.max(np.abs(f_ref))
+        for c in ctxs:   # ghosts carry the owners' values
+            assert np.max(np.abs(c.field_get() - f_ref[c.plan["local_sites"]])) < 1e-10 * np.max(np.abs(f_ref))
+        ll = nb.group_loglik(ctxs, B0, LS)
+        assert np.all(np.abs(ll - ll1_ref) < 1e-10 * abs(ll1_ref))
+        # Philox sweeps, several calls (epochs keep counting across calls, parities alternate)
+        with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+            ctx.factor_build(CP)
+            ctx.factor_commit()
+            ctx.field_set(P["field"])
+            ctx.obs_set(P["y"])
+            ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=n_sweeps, z=z)   # same per-context sweep counter (part of the Philox key) as the shards
+            for s in range(3):
+                ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=1 + s, seed=21)
+            f_ref2 = ctx.field_get()
+        for s in range(3):
+            nb.group_sweep(ctxs, B0, LS, LNV, n_sweeps=1 + s, seed=21)
+        f2 = gather_owned(ctxs, n)
+        assert np.max(np.abs(f2 - f_ref2)) < 1e-10 * np.max(np.abs(f_ref2))
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_philox_draws_do_not_depend_on_the_sharding():
     P = make_problem(20000, 10, seed=6)
     f_ref, *_ = reference(P, 1, z=None, seed=9)

@@ -27,6 +27,24 @@ def test_blocks_are_balanced_and_cover_everything(P):
     assert counts.sum() == locs.shape[0] and counts.max() - counts.min() <= P
 
 
+@pytest.mark.parametrize("P", [1, 2, 3, 8])
+def test_native_plan_equals_the_numpy_prototype(P):
+    """nngp_host_shard_plan_build (O(n (m+1)), csrc/host_shard.cpp) against the straightforward numpy derivation"""
+    import partition_reference as PR
+    locs, nn, col, lm = problem(5000, 7, seed=11)
+    owner = spatial_blocks(locs, P)
+    for r in range(P):
+        a = shard_plan(locs, nn, col, lm, owner, r, P)
+        b = PR.shard_plan(locs, nn, col, lm, owner, r, P)
+        for k, vb in b.items():
+            if k == "n_rows_needed":
+                continue
+            if isinstance(vb, np.ndarray):
+                assert a[k].shape == vb.shape and np.array_equal(a[k], vb), k
+            else:
+                assert a[k] == vb, k
+
+
 @pytest.mark.parametrize("P", [2, 4])
 def test_plans_are_closed_and_mutually_consistent(P):
     locs, nn, col, lm = problem()
