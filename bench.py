@@ -2,17 +2,19 @@
 """bench.py -- headline benchmark of the NNGP hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
 Metric (BASELINE.json): Gibbs sweeps/sec + Vecchia log-lik evals/sec at n = 1M, m = 10.  One STEP = one full chromatic
-Gibbs sweep of the latent field (all colour classes, Philox normals) + one Vecchia log-likelihood evaluation, on
-config 3 (synthetic U(0,1)^2 sites, n = 1 000 000, m = 10, exponential_isotropic, range 0.05, sigma^2 = 1, tau^2 = 0.1,
-reordering = "random").  `value` = steps/s, whole job, inputs resident in HBM, timed with CUDA events on the library's
-stream.  `e2e` = the same step through the C ABI with HOST buffers (field in, field out, host field for the log-lik).
+Gibbs sweep of the latent field (all colour classes, Philox normals) + one Vecchia log-likelihood evaluation.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 1000000] [--m 10]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N > 1 (torchrun, one rank per GPU), default --mode chains: one independent chain per GPU (the reference's own parallelism,
-mclapply over chains, Scripts/mcmc_nngp_update_Gaussian.R:25); no data-path collective; scaling = "weak".
---mode sharded: ONE field of --n sites split over the N GPUs by spatial blocks, per-colour halo exchange of boundary values
-(ncclSend/ncclRecv) and an all-reduce for the log-lik scalars; scaling = "strong".
+N = 1: config 3 (synthetic U(0,1)^2 sites, n = 1 000 000, m = 10, exponential_isotropic, range 0.05, sigma^2 = 1, tau^2 = 0.1).
+  `value` = steps/s, inputs resident in HBM, CUDA events on the library's stream; `e2e` = the same step through the C ABI with
+  pinned HOST buffers (field in, field out, host field for the log-lik).
+N > 1 (torchrun, one rank per GPU): ONE field of N x 1M sites sharded over the N GPUs by spatial blocks (the
+  north_star's multi-GPU split): boundary values pushed into the peers' ghost slots over NVLink from inside the sweep kernel,
+  scalar all-reduce for the log-lik.  scaling = "weak" (1M sites per GPU); value = N x (steps/s of the whole field), i.e. steps/s
+  counted in 1M-site blocks, so value_N / (N value_1) is the weak-scaling efficiency.  Extra keys: the same n = 1M field sharded
+  over the N GPUs (strong scaling) and N independent replicas (one chain per GPU, no collective).
+--mode sharded --sites 10000000 --nbrs 20 --covfun matern_isotropic : config 4.
 """
 from __future__ import annotations
 
@@ -30,16 +32,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-RANGE, SIGMA2, TAU2 = 0.05, 1.0, 0.1
+RANGE, SIGMA2, TAU2, NU = 0.05, 1.0, 0.1, 0.75
 
 
-def algorithmic_bytes(n, m, d=2):
+def algorithmic(n, m, d=2):
     """FP64 = 8 B, int32 = 4 B, each gathered operand counted once per use, no cache credit."""
     M = m + 1
     return {
         "gibbs_sweep": n * (M * 48 + 40),
         "loglik": n * M * 20,
         "factor_build": n * M * (4 + 8 * d + 8),
+        "factor_build_flops": n * (M * (M + 1) / 2 * (3 * d + 35) + M ** 3 / 3 + M ** 2),
         "spmv": n * M * 20 + 8 * n,
     }
 
@@ -48,8 +51,24 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def covparms(covfun, range_):
+    return [1.0, range_, 0.0] if covfun.startswith("exponential") else [1.0, range_, NU, 0.0]
+
+
+def stats(ms):
+    ms = np.asarray(ms, dtype=np.float64)
+    return {"median": float(np.median(ms)), "min": float(ms.min()), "mean": float(ms.mean()), "reps": int(ms.size)}
+
+
+def git_sha():
+    try:
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True, timeout=5).stdout.strip() or None
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -96,25 +115,58 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem(n, m, seed):
-    """config 3 generator: sites, exact ordered NN, first-fit colouring; w ~ NNGP prior is drawn on the device."""
+def pin_to_gpu_numa(local):
+    """best effort: run this rank on the CPUs of the GPU's NUMA node, so that its pinned buffers and staging copies are local to
+    the GPU's PCIe root (r01: 8 ranks all on NUMA 0 gave an 8-GPU e2e efficiency of 0.61)"""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                             text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except Exception:
+        pass
+    return None
+
+
+def build_problem(n, m, seed, reordering="random"):
+    """config 3 / 4 generator: U(0,1)^2 sites, ordering, exact ordered NN, first-fit colouring (host utilities of the library)"""
     import nngp_b200 as nb
     rng = np.random.default_rng(seed)
     locs = rng.random((n, 2))
+    t = {}
+    t0 = time.perf_counter()
+    if reordering == "maxmin":
+        locs = locs[nb.order_maxmin(locs) - 1]
+    t["ordering_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     nn = nb.find_ordered_nn(locs, m)
+    t["neighbours_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     coloring = nb.greedy_coloring(nn)
+    t["colouring_s"] = time.perf_counter() - t0
     locs_match = np.arange(1, n + 1, dtype=np.int32)
-    return rng, locs, nn, coloring, locs_match
+    return rng, locs, nn, coloring, locs_match, t
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle restatement of the reference's CPU path (R + GpGp + Matrix are not in this image)
 # ---------------------------------------------------------------------------------------------------------------------
 def _oracle_chain_worker(args):
-    n, m, seed, steps, warmup = args
+    n, m, seed, steps, warmup, form = args
     from oracle import oracle as O
     rng = np.random.default_rng(seed)
     locs = rng.random((n, 2))
+    os.environ["NNGP_QUIET"] = "1"
     import nngp_b200 as nb   # host set-up utilities only (no CUDA call is made in this process)
     nn = nb.find_ordered_nn(locs, m)
     coloring = nb.greedy_coloring(nn)
@@ -129,16 +181,16 @@ def _oracle_chain_worker(args):
     for s in range(warmup + steps):
         z = rng.standard_normal(n)
         t0 = time.perf_counter()
-        field = O.chromatic_sweep(Linv, nn, coloring, pd, np.ones(n), rs, 0.0, np.log(SIGMA2), np.log(TAU2), z, field, form="reference")
+        field = O.chromatic_sweep(Linv, nn, coloring, pd, np.ones(n), rs, 0.0, np.log(SIGMA2), np.log(TAU2), z, field, form=form)
         ll = O.ll_compressed_sparse_chol(Linv, field, nn, np.log(SIGMA2))
         times.append(time.perf_counter() - t0)
     assert np.isfinite(ll)
     return times[warmup:]
 
 
-def oracle_steps_per_sec(n, m, steps, warmup, procs):
+def oracle_steps_per_sec(n, m, steps, warmup, procs, form="reference"):
     import multiprocessing as mp
-    args = [(n, m, 100 + k, steps, warmup) for k in range(procs)]
+    args = [(n, m, 100 + k, steps, warmup, form) for k in range(procs)]
     if procs == 1:
         res = [_oracle_chain_worker(args[0])]
     else:
@@ -148,139 +200,170 @@ def oracle_steps_per_sec(n, m, steps, warmup, procs):
     return float(sum(per_chain)), float(np.mean([np.mean(t) for t in res]) * 1e3)
 
 
+def workload_string(n, m, covfun, reordering, n_gpus):
+    base = f"U(0,1)^2, n={n}, m={m}, {covfun} range {RANGE}" + (f" nu {NU}" if covfun.startswith("matern") else "") + f", sigma2 {SIGMA2}, tau2 {TAU2}, reordering={reordering}"
+    if n_gpus == 1:
+        return "config3: " + base
+    return f"one field sharded over {n_gpus} GPUs by spatial blocks ({n // n_gpus} sites per GPU): " + base
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, a.ref_procs))
-    # bounded sample: the reference-form sweep costs K full mat-vecs, ~1 s/step/chain at n = 1M
-    n = a.n if a.ref_n is None else a.ref_n
+    # bounded sample: the reference-form sweep costs K full mat-vecs, ~1 s/step/chain at n = 1M.  The reference's only
+    # parallelism is one chain per core (mclapply): `procs` independent chains of the 1M-site problem, aggregate steps/s.
+    n = a.sites_per_gpu if a.ref_n is None else a.ref_n
     steps = max(1, min(a.steps, 3))
     warmup = min(a.warmup, 1)
     value, ms = oracle_steps_per_sec(n, a.m, steps, warmup, procs)
-    scale = n / a.n
+    scale = n / a.sites_per_gpu
+    n_total = a.sites_per_gpu * a.gpus if a.n is None else a.n
     line = {
-        "impl": "reference", "metric": "gibbs_sweep_plus_vecchia_loglik_per_sec", "value": value * scale, "unit": "steps/s",
+        "impl": "reference", "metric": "gibbs_sweep_plus_vecchia_loglik_per_sec", "value": value * scale, "unit": "steps/s (1M-site blocks)",
         "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms / scale, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config3: U(0,1)^2, n={a.n}, m={a.m}, exponential_isotropic range {RANGE}, reordering=random",
-                   "step": "1 chromatic Gibbs sweep (reference form: one sparse mat-vec per colour) + 1 Vecchia log-lik"},
-        "cpu_baseline": {"value": value * scale, "unit": "steps/s", "cores": procs, "kind": "port",
+        "config": {"workload": workload_string(n_total, a.m, a.covfun, a.reordering, a.gpus),
+                   "step": "1 chromatic Gibbs sweep (reference form: one sparse mat-vec per colour, update_Gaussian.R:257-275) + 1 Vecchia log-lik",
+                   "reference_parallelism": f"{procs} independent chains of a {n}-site field, one per host core (mclapply, update_Gaussian.R:25); "
+                                            "the reference has no way to split one field over cores"},
+        "cpu_baseline": {"value": value * scale, "unit": "steps/s (1M-site blocks)", "cores": procs, "kind": "port",
                          "sample": f"oracle restatement (not R/GpGp): {procs} independent chains (one per core, as mclapply does), "
-                                   f"n={n}, {steps} steps each" + ("" if scale == 1 else f", scaled by n/{a.n}")},
-        "e2e": {"value": value * scale, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                                   f"n={n}, {steps} steps each" + ("" if scale == 1 else f", scaled by n/{a.sites_per_gpu}")},
+        "e2e": {"value": value * scale, "unit": "steps/s (1M-site blocks)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# our arm
+# our arm, one GPU
 # ---------------------------------------------------------------------------------------------------------------------
-def run_ours(a):
+def run_single(a):
     import torch
     import nngp_b200 as nb
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the NNGP hot path has no CPU fallback)")
+    local = 0
     torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    n, m = a.n, a.m
-    rng, locs, nn, coloring, locs_match = build_problem(n, m, seed=1 + rank)
-    ctx = nb.NNGPContext(locs, nn, coloring, locs_match, "exponential_isotropic", device=local)
-    assert ctx.factor_build([SIGMA2 * 0 + 1.0, RANGE, 0.0]) == 0
+    n, m = (a.sites_per_gpu if a.n is None else a.n), a.m
+    cp = covparms(a.covfun, RANGE)
+    rng, locs, nn, coloring, locs_match, t_setup = build_problem(n, m, seed=1, reordering=a.reordering)
+    t0 = time.perf_counter()
+    ctx = nb.NNGPContext(locs, nn, coloring, locs_match, a.covfun, device=local)
+    t_setup["ctx_create_s"] = time.perf_counter() - t0
+    assert ctx.factor_build(cp) == 0
     ctx.factor_commit()
     ctx.field_init(0.0, np.log(SIGMA2), rng.standard_normal(n))          # w ~ NNGP prior by a triangular solve
     w = ctx.field_get()
     y = w + np.sqrt(TAU2) * rng.standard_normal(n)
     ctx.obs_set(y)
     beta_0, ls, lnv = 0.0, float(np.log(SIGMA2)), float(np.log(TAU2))
-    ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=1, seed=rank)               # sets the sweep parameters used by time_op
+    ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=1, seed=0)                  # sets the sweep parameters used by time_op
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps, CUDA events on the library's stream ----
-    ctx.time_op("sweep_loglik", reps=max(a.warmup, 3))
+    warm = max(a.warmup, 3)
+    ctx.time_op("sweep_loglik", reps=warm)
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     launches0 = nb.launch_count()
-    barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     ms_steps, launches_per_step = ctx.time_op("sweep_loglik", reps=a.steps)
-    barrier()
+    torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     launches = nb.launch_count() - launches0
     total_ms = float(ms_steps.sum())
-    # component timings (same stream, same events)
-    ms_sweep, nl_sweep = ctx.time_op("gibbs_sweep", reps=max(10, a.steps))
-    ms_ll, _ = ctx.time_op("loglik", reps=max(10, a.steps))
-    ms_fac, _ = ctx.time_op("factor_build", reps=max(5, a.steps // 2))
-    ms_solve, _ = ctx.time_op("sptrsv", reps=5)
-    ms_commit, _ = ctx.time_op("commit", reps=5)
-    clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    value = world * a.steps / (total_ms * 1e-3)
+    value = a.steps / (total_ms * 1e-3)
+    # component timings (same stream, same events; >= 50 repetitions, median and min -- SURVEY.md 8d)
+    reps = max(50, min(a.steps, 200))
+    comp = {}
+    for key, op in (("sweep", "gibbs_sweep"), ("loglik", "loglik"), ("factor_build", "factor_build"), ("spmv_plus_sptrsv", "sptrsv"),
+                    ("spmv", "spmv"), ("accept_transpose_precision_diag", "commit")):
+        ctx.time_op(op, reps=3)
+        comp[key] = stats(ctx.time_op(op, reps=reps)[0])
+    clocks = sampler.stop()
+    fp64_gflops = nb.fp64_peak(local)
 
     # ---- end to end through the C ABI with host buffers: field in -> sweep -> field out, host field -> log-lik ----
-    # The host side of every step is a page-locked buffer (nngp_host_alloc), as the contract asks; the same loop with
-    # ordinary numpy arrays (staged through the library's pinned buffer by a multi-threaded copy) is reported next to it.
     def e2e_loop(field_h, steps):
         ll = 0.0
         for _ in range(steps):
             ctx.field_set(field_h)                            # H2D 8n bytes
-            ctx.gibbs_sweep(beta_0, ls, lnv, 1, seed=rank)
+            ctx.gibbs_sweep(beta_0, ls, lnv, 1, seed=0)
             ctx.field_get(out=field_h)                        # D2H 8n bytes
             ll = ctx.loglik_host(field_h, ls)                 # H2D 8n bytes, D2H 2 scalars
         return ll
 
-    def timed_e2e(field_h):
-        e2e_loop(field_h, 2)
-        barrier()
+    def timed_e2e(field_h, steps):
+        e2e_loop(field_h, 3)
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ll = e2e_loop(field_h, a.steps)
-        barrier()
+        ll = e2e_loop(field_h, steps)
+        torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
         assert np.isfinite(ll)
-        return world * a.steps / dt
+        return steps / dt
 
-    # ---- config 5 flavour: the full reference iteration (2 factor rebuilds, ancillary solve, 10 sweeps, ...) behind one call ----
+    # ---- the full reference iteration (2 factor rebuilds, ancillary solve, 10 sweeps, ...) behind one call; iter_start = 0 is the
+    # adaptive phase in which proposals ARE accepted (the accept branch -- transposition + precision_diag, field copy -- is in) ----
     var_y = float(np.var(y, ddof=1))
-    chain_params = {"shape": [np.log(RANGE)], "beta_0": 0.0, "log_scale": ls, "log_noise_variance": lnv}
-    ctx.chain_run(chain_params, 3, var_y, thin=0.0, n_chromatic=10, iter_start=5000, chain_index=1 + rank, keep_field=False)
-    n_chain_it = 20
-    barrier()
+    chain_params = {"shape": [np.log(RANGE)] + ([0.0] if a.covfun.startswith("matern") else []), "beta_0": 0.0, "log_scale": ls, "log_noise_variance": lnv}
+    n_chain_it = 50
+    ctx.chain_run(chain_params, 3, var_y, thin=0.0, n_chromatic=10, iter_start=0, chain_index=1, keep_field=False)
     t0 = time.perf_counter()
-    ctx.chain_run(chain_params, n_chain_it, var_y, thin=0.0, n_chromatic=10, iter_start=5000, chain_index=1 + rank, keep_field=False)
-    barrier()
-    chain_it_per_s = world * n_chain_it / (time.perf_counter() - t0)
+    _, _, _, acc = ctx.chain_run(chain_params, n_chain_it, var_y, thin=0.0, n_chromatic=10, iter_start=0, chain_index=1, keep_field=False)
+    chain_it_per_s = n_chain_it / (time.perf_counter() - t0)
+    chain_accepts = [int(acc[:, 0].sum()), int(acc[:, 1].sum())]
     ctx.field_set(w)
+    ctx.factor_build(cp)
+    ctx.factor_commit()
 
-    # ---- config 5 flavour: mcmc_nngp_predict_field at n new sites (joint context over 2n sites; only the new rows are solved) ----
+    # ---- several chains per GPU (the reference's default is n_chains = 3, advanced concurrently): a sweep is a chain of
+    # latency-bound colour stages, so co-scheduled chains fill each other's gaps ----
+    multi = None
+    if not a.no_multichain:
+        others = []
+        try:
+            for k in range(2):
+                c2 = nb.NNGPContext(locs, nn, coloring, locs_match, a.covfun, device=local)
+                c2.factor_build(cp)
+                c2.factor_commit()
+                c2.field_set(w)
+                c2.obs_set(y)
+                c2.gibbs_sweep(beta_0, ls, lnv, 1, seed=k + 1)
+                others.append(c2)
+            r = 100
+            one = nb.time_op_group([ctx], "gibbs_sweep", reps=r)
+            two = nb.time_op_group([ctx, others[0]], "gibbs_sweep", reps=r)
+            three = nb.time_op_group([ctx] + others, "gibbs_sweep", reps=r)
+            three_step = nb.time_op_group([ctx] + others, "sweep_loglik", reps=r)
+            t0 = time.perf_counter()
+            res = nb.chains_run([ctx] + others, [chain_params] * 3, 20, var_y, thin=0.0, n_chromatic=10, iter_start=0,
+                                chain_indices=[1, 2, 3], keep_field=False)
+            chains3 = 3 * 20 / (time.perf_counter() - t0)
+            multi = {"chains_per_gpu": 3, "sweeps_per_sec_1_chain": 1e3 * r / one, "sweeps_per_sec_2_chains": 2e3 * r / two,
+                     "sweeps_per_sec_3_chains": 3e3 * r / three, "steps_per_sec_3_chains": 3e3 * r / three_step,
+                     "chain_iterations_per_sec_3_chains": chains3,
+                     "what": "aggregate over chains co-scheduled on ONE GPU (one context, stream and host thread per chain; nngp_time_op_group / nngp_chains_run)"}
+            del res
+        finally:
+            for c2 in others:
+                c2.close()
+        ctx.field_set(w)
+        ctx.factor_build(cp)
+        ctx.factor_commit()
+
+    # ---- mcmc_nngp_predict_field at n new sites (joint context over 2n sites; only the new rows are solved) ----
     pred_per_s = None
-    if world == 1 and not a.no_predict:
+    if not a.no_predict:
         new_locs = np.random.default_rng(99).random((n, 2))
         joint = np.vstack([locs, new_locs])
         nn_j = nb.find_ordered_nn(joint, m)
-        with nb.NNGPContext(joint, nn_j, np.zeros(2 * n, dtype=np.int32), np.zeros(0, dtype=np.int32), "exponential_isotropic", device=local) as pctx:
-            pctx.factor_build([1.0, RANGE, 0.0])
+        with nb.NNGPContext(joint, nn_j, np.zeros(2 * n, dtype=np.int32), np.zeros(0, dtype=np.int32), a.covfun, device=local) as pctx:
+            pctx.factor_build(cp)
             zp = np.random.default_rng(5).standard_normal(n)
             pctx.predict_sample(n, w, beta_0, ls, zp)
             t0 = time.perf_counter()
@@ -288,104 +371,152 @@ def run_ours(a):
                 pctx.predict_sample(n, w, beta_0, ls, zp)
             pred_per_s = 5 / (time.perf_counter() - t0)
 
+    e2e_steps = min(a.steps, 200)
     pinned = nb.PinnedArray(n)
     pinned.array[:] = ctx.field_get()
-    e2e_value = timed_e2e(pinned.array)
-    e2e_pageable = timed_e2e(ctx.field_get())
+    e2e_value = timed_e2e(pinned.array, e2e_steps)
+    e2e_pageable = timed_e2e(ctx.field_get(), e2e_steps)
     pinned.free()
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    # ---- the other ordering (the reference default is maxmin, initialize.R:29; "random" is its other option, :30) ----
+    other = None
+    if not a.no_other_ordering:
+        oname = "random" if a.reordering == "maxmin" else "maxmin"
+        rng2, locs2, nn2, col2, lm2, t2 = build_problem(n, m, seed=1, reordering=oname)
+        with nb.NNGPContext(locs2, nn2, col2, lm2, a.covfun, device=local) as c2:
+            c2.factor_build(cp)
+            c2.factor_commit()
+            c2.field_init(0.0, ls, rng2.standard_normal(n))
+            w2 = c2.field_get()
+            c2.obs_set(w2 + np.sqrt(TAU2) * rng2.standard_normal(n))
+            c2.gibbs_sweep(beta_0, ls, lnv, 1, seed=0)
+            c2.time_op("sweep_loglik", reps=3)
+            o = {k: stats(c2.time_op(op, reps=reps)[0]) for k, op in (("sweep", "gibbs_sweep"), ("loglik", "loglik"), ("step", "sweep_loglik"),
+                                                                       ("factor_build", "factor_build"), ("spmv_plus_sptrsv", "sptrsv"))}
+            other = {"reordering": oname, "n_colors": c2.n_colors, "solve_levels": c2.n_levels, "longest_column": c2.max_col,
+                     "steps_per_sec": 1e3 / o["step"]["median"], "ms": o, "setup": t2}
+
     peak, peak_src = measured_peaks()
-    traffic = None
+    ab = algorithmic(n, m)
+    traffic, traffic_meta = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and n == 1_000_000 and m == 10:
+    if os.path.exists(tpath) and n == 1_000_000 and m == 10 and a.covfun == "exponential_isotropic":
         with open(tpath) as f:
-            traffic = json.load(f)["bytes"].get("gibbs_sweep_full")
-    ab = algorithmic_bytes(n, m)
-    sweep_ms = float(np.mean(ms_sweep))
+            tj = json.load(f)
+        traffic = tj["bytes"].get("gibbs_sweep_full")
+        traffic_meta = {k: tj.get(k) for k in ("git_sha", "when", "how") if k in tj}
+    sweep_ms = comp["sweep"]["median"]
     achieved = ab["gibbs_sweep"] / (sweep_ms * 1e-3) / 1e9
+    fac_ms = comp["factor_build"]["median"]
     line = {
-        "metric": "gibbs_sweep_plus_vecchia_loglik_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps,
-        "warmup": max(a.warmup, 3), "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": "gibbs_sweep_plus_vecchia_loglik_per_sec", "value": value, "unit": "steps/s (1M-site blocks)", "n_gpus": 1, "steps": a.steps,
+        "warmup": warm, "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config3: U(0,1)^2, n={n}, m={m}, exponential_isotropic range {RANGE}, sigma2 {SIGMA2}, tau2 {TAU2}, reordering=random",
+        "config": {"workload": workload_string(n, m, a.covfun, a.reordering, 1),
                    "step": "1 chromatic Gibbs sweep (all colours, Philox normals) + 1 Vecchia log-lik evaluation",
-                   "parallelism": "1 chain per GPU" if world > 1 else "single GPU",
+                   "parallelism": "single GPU",
                    "l2": "working set (factor + indices + transpose map, ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
-                   "n_colors": ctx.n_colors, "solve_levels": ctx.n_levels, "layout": ctx.layout},
-        "gibbs_sweeps_per_sec": world * 1e3 / sweep_ms, "loglik_evals_per_sec": world * 1e3 / float(np.mean(ms_ll)),
-        "factor_builds_per_sec": world * 1e3 / float(np.mean(ms_fac)),
-        "chain_iterations_per_sec": chain_it_per_s,
+                   "n_colors": ctx.n_colors, "solve_levels": ctx.n_levels, "longest_column": ctx.max_col, "layout": ctx.layout, "setup": t_setup},
+        "gibbs_sweeps_per_sec": 1e3 / sweep_ms, "loglik_evals_per_sec": 1e3 / comp["loglik"]["median"],
+        "factor_builds_per_sec": 1e3 / fac_ms,
+        "chain_iterations_per_sec": chain_it_per_s, "chain_accepts_ancillary_sufficient": chain_accepts,
+        "chain_iteration": f"nngp_chain_run, {n_chain_it} iterations from iter_start = 0 (adaptive phase: proposals are accepted): reference loop "
+                           "update_Gaussian.R:101-314 (2 factor rebuilds, ancillary SpMV+SpTRSV, 2 log-liks, beta_0, 10 sweeps, noise steps), host wall clock",
+        "multi_chain": multi,
         "predicted_field_samples_per_sec": pred_per_s,
         "predicted_field_sample": f"nngp_predict_sample through the C ABI with host buffers: one stored sample conditionally simulated at {n} new sites",
-        "chain_iteration": "nngp_chain_run: reference loop update_Gaussian.R:101-314 (2 factor rebuilds, ancillary SpMV+SpTRSV, 2 log-liks, beta_0, 10 sweeps, noise steps), whole job",
-        "ms": {"sweep": sweep_ms, "loglik": float(np.mean(ms_ll)), "factor_build": float(np.mean(ms_fac)),
-               "spmv_plus_sptrsv": float(np.mean(ms_solve)), "accept_transpose_precision_diag": float(np.mean(ms_commit)),
-               "wall_timed_region": wall * 1e3},
-        "roofline": {"bound": "hbm", "kernel": "gibbs_tile2_kernel (the K colour launches of one sweep, PDL-chained, replayed from one CUDA graph; 6 CTAs/SM build for colours that would not fit one wave at 5)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "traffic_source": "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the colour launches of one sweep, --cache-control none)",
-                     "algorithmic_bytes_per_sweep": ab["gibbs_sweep"],
-                     "loglik_GBps": ab["loglik"] / (float(np.mean(ms_ll)) * 1e-3) / 1e9,
-                     "factor_build_GBps": ab["factor_build"] / (float(np.mean(ms_fac)) * 1e-3) / 1e9},
-        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 16 * n + 64, "d2h_bytes_per_step": 8 * n + 16,
+        "other_ordering": other,
+        "ms": dict(comp, wall_timed_region=wall * 1e3),
+        "roofline": {"bound": "hbm", "kernel": "gibbs_tile2_kernel (the K colour launches of one sweep, PDL-chained, replayed from one CUDA graph; 6 CTAs/SM build for colours that would not fit one wave at 5)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac_dram": (traffic / (sweep_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                     "traffic_source": "OFFLINE: profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the colour launches of one warm sweep, "
+                                       "--cache-control none); not measured in this run", "traffic_meta": traffic_meta,
+                     "algorithmic_bytes_per_sweep": ab["gibbs_sweep"], "timing": "median of CUDA-event times, %d repetitions" % comp["sweep"]["reps"],
+                     "loglik": {"achieved": ab["loglik"] / (comp["loglik"]["median"] * 1e-3) / 1e9, "frac": ab["loglik"] / (comp["loglik"]["median"] * 1e-3) / 1e9 / peak},
+                     "factor_build": {"bound": "fp64", "flops_per_build": ab["factor_build_flops"], "achieved_gflops": ab["factor_build_flops"] / (fac_ms * 1e-3) / 1e9,
+                                      "peak_gflops": fp64_gflops, "frac": ab["factor_build_flops"] / (fac_ms * 1e-3) / 1e9 / fp64_gflops if fp64_gflops else None,
+                                      "peak_source": "nngp_fp64_peak: dependent-free DFMA chains on every SM, this run",
+                                      "GBps": ab["factor_build"] / (fac_ms * 1e-3) / 1e9}},
+        "e2e": {"value": e2e_value, "unit": "steps/s (1M-site blocks)", "h2d_bytes_per_step": 16 * n + 64, "d2h_bytes_per_step": 8 * n + 16,
                 "what": "nngp_field_set + nngp_gibbs_sweep + nngp_field_get + nngp_loglik_host; host side = pinned buffer (nngp_host_alloc)",
-                "pageable_numpy_value": e2e_pageable},
-        "gpu_launches": int(launches), "launches_per_step": int(launches_per_step), "clocks": clocks,
+                "steps": e2e_steps, "pcie_GBps": e2e_value * (24 * n) / 1e9, "pageable_numpy_value": e2e_pageable},
+        "gpu_launches": int(launches), "launches_per_step": int(launches_per_step), "clocks": clocks, "git_sha": git_sha(),
     }
-    if world == 1 and not a.no_cpu_baseline:
+    if not a.no_cpu_baseline:
         v, ms = oracle_steps_per_sec(n, m, steps=2, warmup=0, procs=1)
-        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": 1, "kind": "port",
-                                "sample": f"oracle restatement (not R/GpGp), 1 thread, full n={n}: 2 steps of reference-form sweep + log-lik"}
+        v2, ms2 = oracle_steps_per_sec(n, m, steps=2, warmup=0, procs=1, form="residual")
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s (1M-site blocks)", "cores": 1, "kind": "port",
+                                "sample": f"oracle restatement (not R/GpGp), 1 thread, full n={n}: 2 steps of reference-form sweep (one mat-vec per colour) + log-lik",
+                                "residual_form_value": v2,
+                                "residual_form": "the same oracle with the O(n m) residual-maintained sweep the GPU kernel uses: separates the algorithmic gain from the hardware gain"}
     print(json.dumps(line), flush=True)
     ctx.close()
-    if dist is not None:
-        dist.destroy_process_group()
 
 
-def run_sharded(a):
-    """One field over all ranks.  Every rank builds the (replicated) host-side structure, keeps its block."""
-    import torch
-    import torch.distributed as dist
-    import nngp_b200 as nb
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n, m = a.n, a.m
-    t_setup = time.perf_counter()
-    # the (replicated) host-side structure is built once, by rank 0 with all host cores, and shared through /dev/shm
-    shm = f"/dev/shm/nngp_bench_{os.environ.get('MASTER_PORT', '0')}_{n}_{m}"
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm, N GPUs: one field sharded by spatial blocks
+# ---------------------------------------------------------------------------------------------------------------------
+def shared_problem(dist, rank, n, m, seed, reordering, tag):
+    """the (replicated) host-side structure is built once, by rank 0 with all host cores, and shared through /dev/shm"""
+    shm = f"/dev/shm/nngp_bench_{os.environ.get('MASTER_PORT', '0')}_{tag}"
+    t = None
     if rank == 0:
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)           # torchrun pins it to 1; the library is not loaded yet
-        rng, locs, nn, coloring, locs_match = build_problem(n, m, seed=1)
-        np.save(shm + "_locs.npy", locs); np.save(shm + "_nn.npy", nn); np.save(shm + "_col.npy", coloring)
+        _, locs, nn, coloring, _, t = build_problem(n, m, seed=seed, reordering=reordering)
+        np.save(shm + "_locs.npy", np.asfortranarray(locs))
+        np.save(shm + "_nn.npy", np.asfortranarray(nn))
+        np.save(shm + "_col.npy", coloring)
+        del locs, nn, coloring
     dist.barrier()
-    if rank != 0:
-        locs, nn, coloring = np.load(shm + "_locs.npy"), np.load(shm + "_nn.npy"), np.load(shm + "_col.npy")
-        locs_match = np.arange(1, n + 1, dtype=np.int32)
+    locs = np.load(shm + "_locs.npy", mmap_mode="r")
+    nn = np.load(shm + "_nn.npy", mmap_mode="r")
+    coloring = np.load(shm + "_col.npy", mmap_mode="r")
     dist.barrier()
     if rank == 0:
         for suffix in ("_locs.npy", "_nn.npy", "_col.npy"):
-            os.remove(shm + suffix)
-    ctx, plan = nb.create_sharded_distributed(locs, nn, coloring, locs_match, "exponential_isotropic", local, dist, transport=a.transport)
-    t_setup = time.perf_counter() - t_setup
-    assert ctx.factor_build([1.0, RANGE, 0.0]) == 0
-    ctx.factor_commit()
-    w = np.random.default_rng(7).standard_normal(n) * 0.5                    # any field will do for throughput; same on all ranks
-    y = w + np.sqrt(TAU2) * np.random.default_rng(8).standard_normal(n)
-    ctx.field_set(w[plan["local_sites"]])
-    ctx.obs_set(y[plan["obs_index"]])
+            os.remove(shm + suffix)        # the mappings stay valid
+    return locs, nn, coloring, np.arange(1, n + 1, dtype=np.int32), t
+
+
+def run_sharded(a):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world < 2:
+        raise SystemExit("--mode sharded needs torchrun with at least 2 ranks")
+    numa = pin_to_gpu_numa(local)
+    if rank == 0:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))                    # rank 0 builds the shared structure with every core
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)               # torchrun pins it to 1; the library is not loaded yet
+    import nngp_b200 as nb
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, m = (a.sites_per_gpu * world if a.n is None else a.n), a.m
+    cp = covparms(a.covfun, RANGE)
     beta_0, ls, lnv = 0.0, float(np.log(SIGMA2)), float(np.log(TAU2))
-    ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=1, seed=1)
 
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
 
-    ctx.time_op("sweep_loglik", reps=max(a.warmup, 3))
+    def make_field(n_, tag, transport):
+        t0 = time.perf_counter()
+        locs, nn, coloring, locs_match, t_host = shared_problem(dist, rank, n_, m, 1, a.reordering, tag)
+        t1 = time.perf_counter()
+        ctx, plan = nb.create_sharded_distributed(locs, nn, coloring, locs_match, a.covfun, local, dist, transport=transport)
+        t2 = time.perf_counter()
+        assert ctx.factor_build(cp) == 0
+        ctx.factor_commit()
+        w = np.random.default_rng(7).standard_normal(n_) * 0.5               # any field will do for throughput; same on all ranks
+        y = w + np.sqrt(TAU2) * np.random.default_rng(8).standard_normal(n_)
+        ctx.field_set(w[plan["local_sites"]])
+        ctx.obs_set(y[plan["obs_index"]])
+        ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=1, seed=1)
+        return ctx, plan, {"host_structure_s": t1 - t0, "plan_and_ctx_s": t2 - t1, "host": t_host}, w[plan["local_sites"]]
+
+    ctx, plan, t_setup, w_local = make_field(n, "weak", a.transport)
+    warm = max(a.warmup, 3)
+    ctx.time_op("sweep_loglik", reps=warm)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -394,36 +525,126 @@ def run_sharded(a):
     ms_steps, launches_per_step = ctx.time_op("sweep_loglik", reps=a.steps)
     barrier()
     launches = nb.launch_count() - launches0
-    ms_sweep, _ = ctx.time_op("gibbs_sweep", reps=max(10, a.steps))
-    ms_ll, _ = ctx.time_op("loglik", reps=max(10, a.steps))
-    ms_fac, _ = ctx.time_op("factor_build", reps=5)
+    reps = max(50, min(a.steps, 200))
+    comp = {}
+    for key, op in (("sweep", "gibbs_sweep"), ("loglik", "loglik"), ("factor_build", "factor_build")):
+        ctx.time_op(op, reps=3)
+        barrier()
+        comp[key] = ctx.time_op(op, reps=reps)[0]
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([float(ms_steps.sum()), float(ms_sweep.mean()), float(ms_ll.mean()), float(ms_fac.mean())], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, sweep_ms, ll_ms, fac_ms = [float(v) for v in t.tolist()]
-    halo = torch.tensor([float(plan["send_ptr"][-1]), float(plan["n_ghost"]), float(plan["n_owned"])], dtype=torch.float64, device="cuda")
-    dist.all_reduce(halo, op=dist.ReduceOp.SUM)
+
+    def maxred(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def sumred(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    total_ms, sweep_med, sweep_min, ll_med, ll_min, fac_med = maxred([float(ms_steps.sum()), float(np.median(comp["sweep"])), float(comp["sweep"].min()),
+                                                                       float(np.median(comp["loglik"])), float(comp["loglik"].min()), float(np.median(comp["factor_build"]))])
+    sp = np.asarray(plan["send_ptr"])
+    pairs = int(((np.diff(sp).reshape(-1, world)) > 0).sum())
+    halo_vals, n_ghost, n_local, pair_sum = sumred([float(sp[-1]), float(plan["n_ghost"]), float(plan["local_sites"].size), float(pairs)])
+
+    # ---- end to end through the C ABI with pinned host buffers, every rank its block ----
+    nl = plan["local_sites"].size
+    pinned = nb.PinnedArray(nl)
+    pinned.array[:] = w_local
+
+    def e2e_loop(steps):
+        ll = 0.0
+        for _ in range(steps):
+            ctx.field_set(pinned.array)
+            ctx.gibbs_sweep(beta_0, ls, lnv, 1, seed=1)
+            ctx.field_get(out=pinned.array)
+            ll = ctx.loglik_host(pinned.array, ls)
+        return ll
+
+    e2e_steps = min(a.steps, 200)
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    ll = e2e_loop(e2e_steps)
+    barrier()
+    (e2e_dt,) = maxred([time.perf_counter() - t0])
+    assert np.isfinite(ll)
+    pinned.free()
+    blocks = n / a.sites_per_gpu
+    line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
-        ab = algorithmic_bytes(n, m)
-        achieved = ab["gibbs_sweep"] / (sweep_ms * 1e-3) / 1e9
+        ab = algorithmic(n, m)
+        achieved = ab["gibbs_sweep"] / (sweep_med * 1e-3) / 1e9
+        steps_per_s = a.steps / (total_ms * 1e-3)
         line = {
-            "metric": "gibbs_sweep_plus_vecchia_loglik_per_sec", "value": a.steps / (total_ms * 1e-3), "unit": "steps/s", "n_gpus": world,
-            "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong",
+            "metric": "gibbs_sweep_plus_vecchia_loglik_per_sec", "value": blocks * steps_per_s, "unit": "steps/s (1M-site blocks)", "n_gpus": world,
+            "steps": a.steps, "warmup": warm, "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak" if a.n is None else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"one field, U(0,1)^2, n={n}, m={m}, exponential_isotropic range {RANGE}, reordering=random",
-                       "step": "1 chromatic Gibbs sweep of the whole field (per-colour NCCL halo exchange) + 1 Vecchia log-lik (all-reduce)",
+            "config": {"workload": workload_string(n, m, a.covfun, a.reordering, world),
+                       "step": "1 chromatic Gibbs sweep of the WHOLE field (boundary values pushed to the peers' ghost slots from inside the sweep kernel) + 1 Vecchia log-lik (scalar all-reduce)",
+                       "value_definition": f"steps/s of the {n}-site field x {blocks:g} (1M-site blocks), so that value_N / (N value_1) is the weak-scaling efficiency",
                        "parallelism": f"field sharded over {world} GPUs by spatial blocks", "transport": a.transport, "n_colors": ctx.n_colors,
-                       "halo_values_per_sweep": int(halo[0].item()), "ghost_sites_total": int(halo[1].item()), "setup_s": t_setup},
-            "gibbs_sweeps_per_sec": 1e3 / sweep_ms, "loglik_evals_per_sec": 1e3 / ll_ms, "factor_builds_per_sec": 1e3 / fac_ms,
-            "ms": {"sweep": sweep_ms, "loglik": ll_ms, "factor_build": fac_ms},
-            "roofline": {"bound": "hbm", "kernel": "gibbs_tile2_kernel + halo exchange (whole-field sweep, all ranks)", "achieved": achieved,
-                         "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
-            "e2e": None, "gpu_launches": int(launches), "launches_per_step": int(launches_per_step), "clocks": clocks,
+                       "halo_values_per_sweep": int(halo_vals), "halo_colour_peer_pairs": int(pair_sum), "ghost_sites_total": int(n_ghost),
+                       "local_sites_total": int(n_local), "setup": t_setup, "numa_cpulist_rank0": numa,
+                       "l2": "per-GPU working set (~0.4 GB per 1M sites) exceeds the 126 MB L2; no explicit flush"},
+            "field_steps_per_sec": steps_per_s,
+            "gibbs_sweeps_per_sec": 1e3 / sweep_med, "loglik_evals_per_sec": 1e3 / ll_med, "factor_builds_per_sec": 1e3 / fac_med,
+            "ms": {"sweep": {"median": sweep_med, "min": sweep_min, "reps": reps}, "loglik": {"median": ll_med, "min": ll_min, "reps": reps},
+                   "factor_build": {"median": fac_med, "reps": reps}},
+            "halo_us_per_colour": None,
+            "roofline": {"bound": "hbm", "kernel": "gibbs_tile2_kernel<SHARD> (whole-field sweep: K colour launches per rank, halo push / apply fused in; max over ranks)",
+                         "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
+                         "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes_per_sweep": ab["gibbs_sweep"],
+                         "loglik": {"achieved": ab["loglik"] / (ll_med * 1e-3) / 1e9, "frac": ab["loglik"] / (ll_med * 1e-3) / 1e9 / (peak * world)}},
+            "e2e": {"value": blocks * e2e_steps / e2e_dt, "unit": "steps/s (1M-site blocks)", "h2d_bytes_per_step": int(16 * n_local + 64 * world),
+                    "d2h_bytes_per_step": int(8 * n_local + 16 * world), "steps": e2e_steps,
+                    "what": "every rank: nngp_field_set + nngp_gibbs_sweep + nngp_field_get + nngp_loglik_host on its block (owned + ghost sites), pinned host buffers",
+                    "pcie_GBps_per_rank": (24 * n_local / world) * e2e_steps / e2e_dt / 1e9},
+            "gpu_launches": int(launches), "launches_per_step": int(launches_per_step), "clocks": clocks, "git_sha": git_sha(),
         }
-        print(json.dumps(line), flush=True)
     ctx.close()
+    del ctx
+
+    # ---- extras: the n = 1M field of the BASELINE metric split over the N GPUs (strong scaling), and N independent replicas ----
+    if not a.no_extras and a.n is None:
+        n1 = a.sites_per_gpu
+        c1, p1, _, _ = make_field(n1, "strong", a.transport)
+        c1.time_op("sweep_loglik", reps=warm)
+        barrier()
+        ms1, _ = c1.time_op("sweep_loglik", reps=min(a.steps, 300))
+        barrier()
+        sw1, _ = c1.time_op("gibbs_sweep", reps=50)
+        (tot1, sw1m) = maxred([float(ms1.sum()), float(np.median(sw1))])
+        c1.close()
+        # replicas: every rank sweeps its own copy of the 1M-site field, no data-path collective
+        locs, nn, coloring, locs_match, _ = shared_problem(dist, rank, n1, m, 1, a.reordering, "rep")
+        with nb.NNGPContext(np.asarray(locs), np.asarray(nn), np.asarray(coloring), locs_match, a.covfun, device=local) as cr:
+            cr.factor_build(cp)
+            cr.factor_commit()
+            wr = np.random.default_rng(7 + rank).standard_normal(n1) * 0.5
+            cr.field_set(wr)
+            cr.obs_set(wr + np.sqrt(TAU2) * np.random.default_rng(8).standard_normal(n1))
+            cr.gibbs_sweep(beta_0, ls, lnv, 1, seed=rank)
+            cr.time_op("sweep_loglik", reps=warm)
+            barrier()
+            msr, _ = cr.time_op("sweep_loglik", reps=min(a.steps, 300))
+            barrier()
+            (totr,) = maxred([float(msr.sum())])
+        if rank == 0:
+            line["strong_scaling_n1M"] = {"steps_per_sec": min(a.steps, 300) / (tot1 * 1e-3), "sweep_ms_median": sw1m,
+                                          "what": f"the n = {n1} field of the BASELINE metric sharded over {world} GPUs (latency-bound: {ctx_colours(line)} dependent colour stages)"}
+            line["replicas"] = {"steps_per_sec": world * min(a.steps, 300) / (totr * 1e-3),
+                                "what": f"{world} independent chains of the n = {n1} field, one per GPU, no data-path collective (BASELINE config 5 / the reference's own parallelism)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     dist.destroy_process_group()
+
+
+def ctx_colours(line):
+    return line["config"]["n_colors"]
 
 
 def main():
@@ -432,21 +653,28 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sites", "--n", dest="n", type=int, default=1_000_000)
+    ap.add_argument("--sites", "--n", dest="n", type=int, default=None, help="total sites (default: --sites-per-gpu x GPUs)")
+    ap.add_argument("--sites-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--nbrs", "--m", dest="m", type=int, default=10)
+    ap.add_argument("--covfun", default="exponential_isotropic", choices=["exponential_isotropic", "matern_isotropic"])
+    ap.add_argument("--reordering", default="random", choices=["random", "maxmin"])
     ap.add_argument("--ref-n", type=int, default=None, help="reference arm: run on a smaller n and scale (bounded sample)")
     ap.add_argument("--ref-procs", type=int, default=32, help="reference arm: at most this many independent chains (one per host core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
-    ap.add_argument("--mode", default="chains", choices=["chains", "sharded"])
+    ap.add_argument("--no-multichain", action="store_true")
+    ap.add_argument("--no-other-ordering", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--mode", default="auto", choices=["auto", "single", "sharded"])
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="sharded mode: halo transport")
     a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.impl == "reference":
         run_reference(a)
-    elif a.mode == "sharded":
+    elif a.mode == "sharded" or (a.mode == "auto" and world > 1):
         run_sharded(a)
     else:
-        run_ours(a)
+        run_single(a)
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ import time
 import numpy as np
 
 from . import _lib as L
-from .context import NNGPContext, find_ordered_nn, greedy_coloring, order_maxmin
+from .context import NNGPContext, chains_run, find_ordered_nn, greedy_coloring, order_maxmin
 
 SHAPE_PARAMS = {
     "exponential_isotropic": lambda d: ["log_range"],
@@ -228,7 +228,8 @@ def mcmc_nngp_update_Gaussian(locs, X, observed_field, space_time_model, vecchia
                               n_cores=None, field_thinning=1, ancillary=True, n_chromatic=10, iterations=None, n_gpus=None,
                               rng="philox", regressor_engine="device"):
     """Returns [ {"state": ..., "records": ...} per chain ] like the reference (:315).  `ancillary` is accepted and ignored,
-    as in the reference (quirk 1).  Chains are not forked: chain i runs on GPU i mod n_gpus inside this process.
+    as in the reference (quirk 1).  Chains are not forked: chain i lives on GPU i mod n_gpus inside this process and all chains
+    advance concurrently behind one nngp_chains_run call (at most n_cores in flight), like the reference's mclapply (:22-26).
     regressor_engine (models with X): "device" = the whole loop behind nngp_chain_run_regressors (X resident in HBM);
     "host" = the loop driven from Python over the device primitives (kept as a cross-check of the former)."""
     n_dev = L.device_count()
@@ -239,19 +240,48 @@ def mcmc_nngp_update_Gaussian(locs, X, observed_field, space_time_model, vecchia
     covfun = space_time_model["covfun"]["stationary_covfun"]
     shape_params = space_time_model["covfun"]["shape_params"]
     var_y = float(np.var(observed_field, ddof=1))
-    out = []
-    for i, name in enumerate(states.keys()):
-        state = states[name]
-        ctx = _chain_context(vecchia_approx, locs, covfun, i, i % n_gpus)
+    names = list(states.keys())
+    ctxs = [_chain_context(vecchia_approx, locs, covfun, i, i % n_gpus) for i in range(len(names))]
+    if X["X"] is not None and regressor_engine == "host":
+        return [_update_chain_regressors(ctxs[i], states[nm], X, observed_field, vecchia_approx, shape_params, var_y, n_iterations_update,
+                                         field_thinning, n_chromatic, iter_start, i + 1) for i, nm in enumerate(names)]
+    # all chains advance concurrently behind ONE call (nngp_chains_run: a host thread and a stream per chain; chain i on GPU
+    # i mod n_gpus), as mclapply does in the reference (:22-26); n_cores bounds the number in flight
+    params_list = []
+    for ctx, nm in zip(ctxs, names):
+        p, tk = states[nm]["params"], states[nm]["transition_kernels"]
         if X["X"] is None:
-            out.append(_update_chain_device(ctx, state, observed_field, shape_params, var_y, n_iterations_update, field_thinning,
-                                            n_chromatic, iter_start, i + 1, rng))
-        elif regressor_engine == "host":
-            out.append(_update_chain_regressors(ctx, state, X, observed_field, vecchia_approx, shape_params, var_y, n_iterations_update,
-                                                field_thinning, n_chromatic, iter_start, i + 1))
-        else:
-            out.append(_update_chain_regressors_device(ctx, state, X, observed_field, vecchia_approx, shape_params, var_y,
-                                                       n_iterations_update, field_thinning, n_chromatic, iter_start, i + 1, rng))
+            ctx.obs_set(observed_field)
+        elif not getattr(ctx, "_regressors_loaded", False):
+            ctx.regressors_set(X["X"], observed_field, xlocs=[int(c) + 1 for c in X["locs"]], first_obs=vecchia_approx["hctam_scol_1"])
+            ctx._regressors_loaded = True
+        ctx.field_set(p["field"])
+        params_list.append({"shape": p["shape"], "beta_0": p["beta_0"], "log_scale": p["log_scale"], "log_noise_variance": p["log_noise_variance"],
+                            "logvar_sufficient": tk["covariance_params_sufficient"]["logvar"],
+                            "logvar_ancillary": tk["covariance_params_ancillary"]["logvar"]})
+    rng_mode = L.RNG_SUPPLIED if rng == "R" else L.RNG_PHILOX
+    kw = dict(thin=field_thinning, n_chromatic=n_chromatic, iter_start=iter_start, chain_indices=list(range(1, len(names) + 1)),
+              rng_mode=rng_mode, max_concurrent=n_cores)
+    if X["X"] is None:
+        res = chains_run(ctxs, params_list, n_iterations_update, var_y, **kw)
+    else:
+        res = chains_run(ctxs, params_list, n_iterations_update, var_y, betas=[states[nm]["params"]["beta"] for nm in names],
+                         solve_1XT1X=X["solve_1XT1X"], chol_solve_1XT1X=X["chol_solve_1XT1X"], **kw)
+    out = []
+    for ctx, nm, r in zip(ctxs, names, res):
+        tk = states[nm]["transition_kernels"]
+        po, rec, frec = r[0], r[1], r[-2]
+        new_params = {"shape": po["shape"], "beta_0": po["beta_0"], "log_scale": po["log_scale"],
+                      "log_noise_variance": po["log_noise_variance"], "field": ctx.field_get()}
+        brec = None
+        if X["X"] is not None:
+            new_params["beta"] = po["beta"]
+            brec = r[2]
+        new_state = {"transition_kernels": {"covariance_params_sufficient": {"logvar": po["logvar_sufficient"]},
+                                            "covariance_params_ancillary": {"logvar": po["logvar_ancillary"]},
+                                            "log_noise_variance": dict(tk["log_noise_variance"])},
+                     "params": new_params}
+        out.append({"state": new_state, "records": _records_dict(rec, shape_params, frec, beta=brec, beta_names=X["names"] if X["X"] is not None else None)})
     return out
 
 
@@ -263,46 +293,6 @@ def _records_dict(rec, shape_params, field_records, beta=None, beta_names=None):
     r["_shape_names"] = list(shape_params)
     r["_beta_names"] = list(beta_names or [])
     return r
-
-
-def _update_chain_device(ctx, state, observed_field, shape_params, var_y, n_iter, thin, n_chromatic, iter_start, chain_index, rng):
-    """no regressors: the whole loop (:101-314) runs behind nngp_chain_run"""
-    p = state["params"]
-    tk = state["transition_kernels"]
-    ctx.field_set(p["field"])
-    ctx.obs_set(observed_field)
-    params = {"shape": p["shape"], "beta_0": p["beta_0"], "log_scale": p["log_scale"], "log_noise_variance": p["log_noise_variance"],
-              "logvar_sufficient": tk["covariance_params_sufficient"]["logvar"], "logvar_ancillary": tk["covariance_params_ancillary"]["logvar"]}
-    po, rec, frec, _ = ctx.chain_run(params, n_iter, var_y, thin=thin, n_chromatic=n_chromatic, iter_start=iter_start,
-                                     chain_index=chain_index, rng_mode=L.RNG_SUPPLIED if rng == "R" else L.RNG_PHILOX)
-    new_state = {"transition_kernels": {"covariance_params_sufficient": {"logvar": po["logvar_sufficient"]},
-                                        "covariance_params_ancillary": {"logvar": po["logvar_ancillary"]},
-                                        "log_noise_variance": dict(tk["log_noise_variance"])},
-                 "params": {"shape": po["shape"], "beta_0": po["beta_0"], "log_scale": po["log_scale"],
-                            "log_noise_variance": po["log_noise_variance"], "field": ctx.field_get()}}
-    return {"state": new_state, "records": _records_dict(rec, shape_params, frec)}
-
-
-def _update_chain_regressors_device(ctx, state, X, y, va, shape_params, var_y, n_iter, thin, n_chromatic, iter_start, chain_index, rng):
-    """Regressor model: the whole loop (:101-314 including the regression block :226-250) behind nngp_chain_run_regressors.
-    X$X, X$X[hctam_scol_1, X$locs] and the observations are uploaded once per context and stay in HBM."""
-    p = state["params"]
-    tk = state["transition_kernels"]
-    if not getattr(ctx, "_regressors_loaded", False):
-        ctx.regressors_set(X["X"], y, xlocs=[int(c) + 1 for c in X["locs"]], first_obs=va["hctam_scol_1"])
-        ctx._regressors_loaded = True
-    ctx.field_set(p["field"])
-    params = {"shape": p["shape"], "beta_0": p["beta_0"], "log_scale": p["log_scale"], "log_noise_variance": p["log_noise_variance"],
-              "logvar_sufficient": tk["covariance_params_sufficient"]["logvar"], "logvar_ancillary": tk["covariance_params_ancillary"]["logvar"]}
-    po, rec, brec, frec, _ = ctx.chain_run_regressors(params, p["beta"], X["solve_1XT1X"], X["chol_solve_1XT1X"], n_iter, var_y, thin=thin,
-                                                      n_chromatic=n_chromatic, iter_start=iter_start, chain_index=chain_index,
-                                                      rng_mode=L.RNG_SUPPLIED if rng == "R" else L.RNG_PHILOX)
-    new_state = {"transition_kernels": {"covariance_params_sufficient": {"logvar": po["logvar_sufficient"]},
-                                        "covariance_params_ancillary": {"logvar": po["logvar_ancillary"]},
-                                        "log_noise_variance": dict(tk["log_noise_variance"])},
-                 "params": {**p, "shape": po["shape"], "beta_0": po["beta_0"], "beta": po["beta"], "log_scale": po["log_scale"],
-                            "log_noise_variance": po["log_noise_variance"], "field": ctx.field_get()}}
-    return {"state": new_state, "records": _records_dict(rec, shape_params, frec, beta=brec, beta_names=X["names"])}
 
 
 def _update_chain_regressors(ctx, state, X, y, va, shape_params, var_y, n_iter, thin, n_chromatic, iter_start, chain_index):

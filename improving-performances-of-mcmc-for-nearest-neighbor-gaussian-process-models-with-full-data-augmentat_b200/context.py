@@ -258,6 +258,80 @@ class NNGPContext:
         return ms, nl.value
 
 
+def time_op_group(contexts, op: str, reps=20) -> float:
+    """nngp_time_op_group: `reps` x op ("gibbs_sweep" or "sweep_loglik") enqueued on all contexts (one device) at once; ms until
+    the last one finished"""
+    ids = (C.c_int * len(contexts))(*[c._id for c in contexts])
+    ms, st = C.c_double(0.0), C.c_int(0)
+    L.load().nngp_time_op_group(ids, L.ci(len(contexts)), L.ci(NNGPContext.OPS[op]), L.ci(reps), C.byref(ms), C.byref(st))
+    L.check(st)
+    return ms.value
+
+
+def fp64_peak(device=0) -> float:
+    """measured FP64 FMA throughput of the device, GFLOP/s (nngp_fp64_peak)"""
+    v, st = C.c_double(0.0), C.c_int(0)
+    L.load().nngp_fp64_peak(L.ci(device), C.byref(v), C.byref(st))
+    L.check(st)
+    return v.value
+
+
+def chains_run(contexts, params_list, n_iter, var_y, thin=1.0, n_chromatic=10, iter_start=0, chain_indices=None, rng_mode=L.RNG_PHILOX,
+               keep_field=True, max_concurrent=None, betas=None, solve_1XT1X=None, chol_solve_1XT1X=None):
+    """nngp_chains_run / nngp_chains_run_regressors: chain k on contexts[k], all advanced concurrently (the reference's mclapply
+    over chains, update_Gaussian.R:22-26); max_concurrent = the reference's n_cores.  Returns one tuple per chain, laid out like
+    NNGPContext.chain_run (or chain_run_regressors when betas is given)."""
+    nc = len(contexts)
+    assert nc >= 1 and len(params_list) == nc
+    chain_indices = list(range(1, nc + 1)) if chain_indices is None else list(chain_indices)
+    n = contexts[0].n
+    assert all(c.n == n for c in contexts)
+    shapes = [np.atleast_1d(np.asarray(p["shape"], dtype=np.float64)) for p in params_list]
+    ns = shapes[0].size
+    P = np.zeros((nc, 5 + ns))
+    for k, p in enumerate(params_list):
+        P[k] = np.concatenate([[p["beta_0"], p["log_scale"], p["log_noise_variance"], p.get("logvar_sufficient", -2.0),
+                                p.get("logvar_ancillary", -2.0)], shapes[k]])
+    n_iter = int(n_iter)
+    n_frec = int(round(n_iter * thin))
+    rec = np.zeros((nc, n_iter * (3 + ns)))
+    frec = np.zeros((nc, max(n_frec, 1) * n)) if keep_field else None
+    acc = np.zeros((nc, 2 * n_iter), dtype=np.int32)
+    ids = (C.c_int * nc)(*[c._id for c in contexts])
+    ci_arr = (C.c_int * nc)(*chain_indices)
+    st = C.c_int(0)
+    mc = nc if max_concurrent is None else max(1, int(max_concurrent))
+    lib = L.load()
+    if betas is None:
+        lib.nngp_chains_run(L.ci(nc), ids, L.ci(ns), L.dptr(P), L.ci(n_iter), L.cd(thin), L.ci(n_chromatic), L.ci(iter_start), ci_arr,
+                            L.ci(rng_mode), L.cd(var_y), L.ci(mc), L.dptr(rec), L.dptr(frec) if keep_field else None, L.iptr(acc), C.byref(st))
+    else:
+        B = np.ascontiguousarray(np.array(betas, dtype=np.float64).reshape(nc, -1))
+        pb = B.shape[1]
+        S = np.asfortranarray(solve_1XT1X, dtype=np.float64)
+        Ch = np.asfortranarray(chol_solve_1XT1X, dtype=np.float64)
+        assert S.shape == (pb + 1, pb + 1) and Ch.shape == (pb + 1, pb + 1)
+        brec = np.zeros((nc, max(n_iter * pb, 1)))
+        lib.nngp_chains_run_regressors(L.ci(nc), ids, L.ci(ns), L.dptr(P), L.dptr(B), S.ctypes.data_as(C.POINTER(C.c_double)),
+                                       Ch.ctypes.data_as(C.POINTER(C.c_double)), L.ci(n_iter), L.cd(thin), L.ci(n_chromatic), L.ci(iter_start),
+                                       ci_arr, L.ci(rng_mode), L.cd(var_y), L.ci(mc), L.dptr(rec), L.dptr(brec),
+                                       L.dptr(frec) if keep_field else None, L.iptr(acc), C.byref(st))
+    L.check(st)
+    out = []
+    for k in range(nc):
+        po = dict(beta_0=P[k, 0], log_scale=P[k, 1], log_noise_variance=P[k, 2], logvar_sufficient=P[k, 3], logvar_ancillary=P[k, 4],
+                  shape=P[k, 5:].copy())
+        frec_m = frec[k, : n_frec * n].reshape((n_frec, n), order="F") if keep_field else None
+        r = rec[k].reshape((n_iter, 3 + ns), order="F")
+        a = acc[k].reshape((n_iter, 2), order="F")
+        if betas is None:
+            out.append((po, r, frec_m, a))
+        else:
+            po["beta"] = B[k].copy()
+            out.append((po, r, brec[k, : n_iter * pb].reshape((n_iter, pb), order="F"), frec_m, a))
+    return out
+
+
 def find_ordered_nn(locs, m) -> np.ndarray:
     """GpGp::find_ordered_nn replacement (Scripts/mcmc_nngp_initialize.R:93): exact, ties by lower index."""
     locs = np.asarray(locs, dtype=np.float64)

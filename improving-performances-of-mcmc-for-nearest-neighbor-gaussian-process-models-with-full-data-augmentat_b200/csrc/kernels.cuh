@@ -1281,6 +1281,21 @@ __global__ void advance_sweep_kernel(SweepParams *spp, unsigned long long n, uns
     }
 }
 
+// FP64 peak micro-benchmark ("a measured FP64 peak from a micro-benchmark", the denominator of the factor
+// kernel's roofline fraction): 8 independent DFMA chains per thread, no memory traffic; 2 flops per DFMA.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[0] = s;   // never true: keeps the chains alive
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // regression coefficients (Scripts/mcmc_nngp_update_Gaussian.R:226-250): the only dense algebra on the path.  X$X
 // (n_obs x p, column-major) and the site-level design cbind(1, X$X[hctam_scol_1, X$locs]) stay resident in HBM; every

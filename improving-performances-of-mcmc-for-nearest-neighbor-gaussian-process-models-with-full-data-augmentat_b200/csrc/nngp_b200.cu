@@ -16,6 +16,8 @@
 #include <cstring>
 #include <mutex>
 #include <numeric>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/nngp_b200.h"
@@ -29,14 +31,16 @@ namespace nngp {
 // ------------------------------------------------------------------------------------------------------------------
 static std::mutex g_err_mu;
 static char g_err[1024] = "";
+static thread_local char t_err[1024] = "";   // the calling thread's last message (chains run on worker threads)
 static std::atomic<long long> g_launches{0};
 
 void set_error(const char *fmt, ...) {
-    std::lock_guard<std::mutex> lk(g_err_mu);
     va_list ap;
     va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
     va_end(ap);
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    std::memcpy(g_err, t_err, sizeof(g_err));
 }
 
 struct CudaFail {};
@@ -1902,12 +1906,14 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
         cp[1 + ns] = 0.0;
         return make_cov(c, cp, ns + 2);
     };
-    auto n_bad = [&]() {
-        int bad;
-        CK(cudaMemcpyAsync(c->h_pinned + 8, c->d_nbad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    auto n_bad = [&]() {   // rows whose block was not positive definite; also surfaces a solve / halo wait that timed out
+        int bad[2];
+        CK(cudaMemcpyAsync(c->h_pinned + 8, c->d_nbad.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        std::memcpy(&bad, c->h_pinned + 8, sizeof(int));
-        return bad;
+        std::memcpy(bad, c->h_pinned + 8, 2 * sizeof(int));
+        if (bad[1] == 2) { set_error("sharded field: timed out waiting for a peer's halo / reduction flag (a rank died or fell out of step)"); throw NcclFail(); }
+        if (bad[1]) { set_error("triangular solve: dependency wait timed out (corrupted neighbour structure?)"); throw CudaFail(); }
+        return bad[0];
     };
     RStream rs;
     rs.set_seed((uint32_t)(iter_start + *chain_index_));                         // :36
@@ -2212,6 +2218,113 @@ void nngp_chain_run_regressors(const int *ctx_id, const int *n_shape_, double *p
     ABI_END
 }
 
+// ---- several chains at once (mclapply over chains, Scripts/mcmc_nngp_update_Gaussian.R:22-26; mcmc_nngp_run.R n_cores) ----
+// One blocking call (so that it works through R's .C(), whose argument copies do not outlive a call): chain k runs on context
+// ctx_ids[k] -- its own device, stream and device-resident state -- driven by its own host thread; at most max_concurrent chains
+// are in flight.  Chains on different GPUs run in parallel; chains that share a GPU overlap on it (a sweep is a chain of
+// latency-bound colour stages that leaves most of the memory system idle, so co-scheduled chains fill each other's gaps).
+// Every chain's result is the one the sequential call gives: all random draws are keyed by (iter_start, chain_index).
+struct ChainJob {
+    Ctx *c;
+    double *params, *beta, *records, *beta_records, *field_records;
+    int *accept;
+    int chain_index, status;
+    std::string error;
+};
+
+static void run_chain_jobs(std::vector<ChainJob> &jobs, int max_concurrent, const int *n_shape, const int *n_iter, const double *thin,
+                           const int *n_chromatic, const int *iter_start, const int *rng_mode, const double *var_y,
+                           const double *solve_1XT1X, const double *chol_1XT1X) {
+    std::atomic<int> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= (int)jobs.size()) return;
+            ChainJob &j = jobs[k];
+            int *status = &j.status;
+            ABI_BEGIN
+            if (solve_1XT1X) {
+                RegRun reg{j.beta, solve_1XT1X, chol_1XT1X, j.beta_records};
+                chain_run_impl(j.c, n_shape, j.params, n_iter, thin, n_chromatic, iter_start, &j.chain_index, rng_mode, var_y, j.records,
+                               j.field_records, j.accept, &reg);
+                j.c->have_obs = true;
+            } else {
+                chain_run_impl(j.c, n_shape, j.params, n_iter, thin, n_chromatic, iter_start, &j.chain_index, rng_mode, var_y, j.records,
+                               j.field_records, j.accept, nullptr);
+            }
+            ABI_END
+            if (j.status != NNGP_OK) j.error = t_err;
+        }
+    };
+    const int n_threads = std::max(1, std::min(max_concurrent, (int)jobs.size()));
+    std::vector<std::thread> pool;
+    for (int w = 1; w < n_threads; w++) pool.emplace_back(worker);
+    worker();
+    for (auto &th : pool) th.join();
+}
+
+static void chains_run_common(const int *n_chains_, const int *ctx_ids, const int *n_shape, double *params_io, double *beta_io,
+                              const double *solve_1XT1X, const double *chol_1XT1X, const int *n_iter, const double *thin,
+                              const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode,
+                              const double *var_y, const int *max_concurrent, double *records_out, double *beta_records_out,
+                              double *field_records_out, int *accept_out, bool with_reg, int *status) {
+    ABI_BEGIN
+    REQUIRE(n_chains_ && ctx_ids && n_shape && params_io && n_iter && thin && n_chromatic && iter_start && chain_index && rng_mode && var_y && max_concurrent,
+            "nngp_chains_run: null argument");
+    REQUIRE(!with_reg || (beta_io && solve_1XT1X && chol_1XT1X), "nngp_chains_run_regressors: null argument");
+    const int nc = *n_chains_, ns = *n_shape, ni = *n_iter;
+    REQUIRE(nc >= 1 && ns >= 1 && ns <= 5 && ni >= 0 && *max_concurrent >= 1, "nngp_chains_run: bad sizes");
+    const long long n_frec = (long long)std::nearbyint(ni * *thin);
+    std::vector<ChainJob> jobs(nc);
+    for (int k = 0; k < nc; k++) {
+        Ctx *c = get_ctx(ctx_ids + k);
+        for (int l = 0; l < k; l++) REQUIRE(jobs[l].c != c, "nngp_chains_run: chains %d and %d share context %d (a context holds the state of ONE chain)", l + 1, k + 1, ctx_ids[k]);
+        NEED(!c->sharded, "nngp_chains_run: not available on a sharded context");
+        NEED(c->have_field && (with_reg || c->have_obs), "nngp_chains_run: field and observations must be set first on every context");
+        if (with_reg) NEED(c->reg_p >= 1, "nngp_chains_run_regressors: nngp_regressors_set must be called first on every context");
+        if (with_reg && k > 0) REQUIRE(c->reg_p == jobs[0].c->reg_p, "nngp_chains_run_regressors: the contexts hold different numbers of regressors");
+        ChainJob &j = jobs[k];
+        j.c = c;
+        j.params = params_io + (size_t)k * (5 + ns);
+        j.beta = with_reg ? beta_io + (size_t)k * c->reg_p : nullptr;
+        j.records = records_out ? records_out + (size_t)k * ni * (3 + ns) : nullptr;
+        j.beta_records = (with_reg && beta_records_out) ? beta_records_out + (size_t)k * ni * c->reg_p : nullptr;
+        j.field_records = field_records_out ? field_records_out + (size_t)k * n_frec * c->n : nullptr;
+        j.accept = accept_out ? accept_out + (size_t)k * 2 * ni : nullptr;
+        j.chain_index = chain_index[k];
+        j.status = NNGP_OK;
+    }
+    run_chain_jobs(jobs, *max_concurrent, n_shape, n_iter, thin, n_chromatic, iter_start, rng_mode, var_y, with_reg ? solve_1XT1X : nullptr, chol_1XT1X);
+    for (int k = 0; k < nc; k++)
+        if (jobs[k].status != NNGP_OK) {
+            set_error("chain %d: %s", k + 1, jobs[k].error.c_str());
+            switch (jobs[k].status) {
+                case NNGP_ERR_CUDA: throw CudaFail();
+                case NNGP_ERR_STATE: throw StateFail();
+                case NNGP_ERR_NCCL: throw NcclFail();
+                case NNGP_ERR_ALLOC: throw std::bad_alloc();
+                default: throw ArgFail();
+            }
+        }
+    ABI_END
+}
+
+void nngp_chains_run(const int *n_chains, const int *ctx_ids, const int *n_shape, double *params_io, const int *n_iter, const double *thin,
+                     const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode, const double *var_y,
+                     const int *max_concurrent, double *records_out, double *field_records_out, int *accept_out, int *status) {
+    chains_run_common(n_chains, ctx_ids, n_shape, params_io, nullptr, nullptr, nullptr, n_iter, thin, n_chromatic, iter_start, chain_index,
+                      rng_mode, var_y, max_concurrent, records_out, nullptr, field_records_out, accept_out, false, status);
+}
+
+void nngp_chains_run_regressors(const int *n_chains, const int *ctx_ids, const int *n_shape, double *params_io, double *beta_io,
+                                const double *solve_1XT1X, const double *chol_solve_1XT1X, const int *n_iter, const double *thin,
+                                const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode,
+                                const double *var_y, const int *max_concurrent, double *records_out, double *beta_records_out,
+                                double *field_records_out, int *accept_out, int *status) {
+    chains_run_common(n_chains, ctx_ids, n_shape, params_io, beta_io, solve_1XT1X, chol_solve_1XT1X, n_iter, thin, n_chromatic, iter_start,
+                      chain_index, rng_mode, var_y, max_concurrent, records_out, beta_records_out, field_records_out, accept_out, true, status);
+}
+
 void nngp_records_summary(const int *ctx_id, const int *first_row, const int *n_rows, const double *offsets, double *out, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
@@ -2275,6 +2388,86 @@ void nngp_time_op(const int *ctx_id, const int *op_, const int *reps_, const int
         if (launches_out) *launches_out = (int)c->launches_in_op;
     }
     CK(cudaGetLastError());
+    ABI_END
+}
+
+// Times `reps` repetitions of one op enqueued on SEVERAL contexts at once (their streams run concurrently on the device(s)):
+// how much chains that share a GPU overlap.  op: 2 = one Gibbs sweep, 6 = sweep + log-lik.  ms_out[0] = time from the first
+// context's start event to the last context's end event, measured with CUDA events per stream (max over the contexts of a
+// common-origin interval); the contexts must live on ONE device.
+void nngp_time_op_group(const int *ctx_ids, const int *n_ctx, const int *op_, const int *reps_, double *ms_out, int *status) {
+    ABI_BEGIN
+    REQUIRE(ctx_ids && n_ctx && op_ && reps_ && ms_out && *n_ctx >= 1 && *n_ctx <= 16 && *reps_ >= 1 && (*op_ == 2 || *op_ == 6), "nngp_time_op_group: bad argument");
+    const int nc = *n_ctx;
+    std::vector<Ctx *> cs(nc);
+    for (int k = 0; k < nc; k++) {
+        cs[k] = get_ctx(ctx_ids + k);
+        NEED(!cs[k]->sharded && cs[k]->can_sweep && cs[k]->have_slot(NNGP_SLOT_CURRENT) && cs[k]->have_field && cs[k]->have_obs, "nngp_time_op_group: every context needs a factor, a field and observations");
+        REQUIRE(cs[k]->device == cs[0]->device, "nngp_time_op_group: the contexts must share a device");
+    }
+    use(cs[0]);
+    for (Ctx *c : cs) {
+        if (!c->committed) op_commit(c);
+        const SweepParams *sp = reinterpret_cast<SweepParams *>(c->h_pinned + 32);
+        set_sweep_params(c, sp->beta0, -std::log(sp->e_ls > 0 ? sp->e_ls : 1.0), -std::log(sp->e_ln > 0 ? sp->e_ln : 1.0), NNGP_RNG_PHILOX, 12345.0);
+        refresh_r(c, sp->beta0);
+        op_sweeps(c, 1);   // instantiates the graph outside the timed region
+        c->sweep_counter++;
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    // a common origin: every stream waits for one event recorded on the first stream
+    CK(cudaEventRecord(cs[0]->ev0, cs[0]->stream));
+    for (int k = 1; k < nc; k++) CK(cudaStreamWaitEvent(cs[k]->stream, cs[0]->ev0, 0));
+    for (int r = 0; r < *reps_; r++)
+        for (Ctx *c : cs) {
+            op_sweeps(c, 1);
+            c->sweep_counter++;
+            if (*op_ == 6) op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, 0.0, 0);
+        }
+    for (Ctx *c : cs) CK(cudaEventRecord(c->ev1, c->stream));
+    double worst = 0.0;
+    for (Ctx *c : cs) {
+        CK(cudaEventSynchronize(c->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, cs[0]->ev0, c->ev1));
+        worst = std::max(worst, (double)ms);
+    }
+    ms_out[0] = worst;
+    ABI_END
+}
+
+// measured FP64 FMA throughput of the device (GFLOP/s, 2 flops per DFMA): dependent-free DFMA chains on every SM, best of 5
+void nngp_fp64_peak(const int *device, double *gflops, int *status) {
+    ABI_BEGIN
+    REQUIRE(device && gflops, "nngp_fp64_peak: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: libnngp_b200 has no CPU fallback"); throw CudaFail(); }
+    REQUIRE(*device >= 0 && *device < ndev, "device %d out of range (%d devices)", *device, ndev);
+    CK(cudaSetDevice(*device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, *device));
+    double *d_out = nullptr;
+    CK(cudaMalloc(&d_out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(e0, 0));
+        fp64_peak_kernel<<<blocks, 256>>>(d_out, iters, 1.0000001, 1e-9);
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        const double flops = (double)blocks * 256.0 * iters * 64.0 * 2.0;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *gflops = best;
     ABI_END
 }
 

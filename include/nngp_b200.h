@@ -282,6 +282,24 @@ void nngp_chain_run_regressors(const int *ctx_id, const int *n_shape, double *pa
                                const double *var_y, double *records_out, double *beta_records_out, double *field_records_out,
                                int *accept_out, int *status);
 
+/* Several chains at once -- the reference advances its chains concurrently (parallel::mclapply over chains,
+ * Scripts/mcmc_nngp_update_Gaussian.R:22-26, n_cores of mcmc_nngp_run.R).  One blocking call, so that it also works through
+ * R's .C(): chain k runs on context ctx_ids[k] (its own device, stream and device-resident state; the contexts must be distinct)
+ * driven by its own host thread, at most max_concurrent (= n_cores) in flight.  Chains on different GPUs run in parallel, chains
+ * sharing a GPU overlap on it.  Every chain's result is bit-identical to what nngp_chain_run gives for it alone.
+ * Scalars (n_shape, n_iter, thin, n_chromatic, iter_start, rng_mode, var_y) are common to all chains; per-chain blocks are
+ * laid out chain after chain: params_io n_chains x (5 + n_shape); chain_index n_chains; records_out n_chains x [n_iter x
+ * (3 + n_shape)]; field_records_out n_chains x [round(n_iter * thin) x n] or NULL; accept_out n_chains x [2 n_iter] or NULL;
+ * beta_io n_chains x p; beta_records_out n_chains x [n_iter x p] or NULL. */
+void nngp_chains_run(const int *n_chains, const int *ctx_ids, const int *n_shape, double *params_io, const int *n_iter, const double *thin,
+                     const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode, const double *var_y,
+                     const int *max_concurrent, double *records_out, double *field_records_out, int *accept_out, int *status);
+void nngp_chains_run_regressors(const int *n_chains, const int *ctx_ids, const int *n_shape, double *params_io, double *beta_io,
+                                const double *solve_1XT1X, const double *chol_solve_1XT1X, const int *n_iter, const double *thin,
+                                const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode,
+                                const double *var_y, const int *max_concurrent, double *records_out, double *beta_records_out,
+                                double *field_records_out, int *accept_out, int *status);
+
 /* Posterior summary of the field samples stored by the last nngp_chain_run, computed on the device from the record store
  * that stays in HBM: get_summary (Scripts/mcmc_nngp_estimate.R:1-6) of rows first_row .. first_row +
  * n_rows - 1 (1-based) of records$field minus offsets[k] (beta_0 of the same iteration, estimate.R:90-92; NULL = none).
@@ -307,6 +325,12 @@ void nngp_predict_sample(const int *ctx_id, const int *slot, const int *n_obs_si
  * per repetition. flush_l2 != 0 writes a 256 MB scratch buffer between repetitions (outside the timed events). */
 void nngp_time_op(const int *ctx_id, const int *op, const int *reps, const int *flush_l2, double *ms_out,
                   int *launches_out, int *status);
+/* `reps` repetitions of op 2 (one Gibbs sweep) or 6 (sweep + log-lik) enqueued on several contexts of ONE device at once (their
+ * streams overlap on the device): ms_out[0] = time until the last context finished, CUDA events with a common origin. */
+void nngp_time_op_group(const int *ctx_ids, const int *n_ctx, const int *op, const int *reps, double *ms_out, int *status);
+/* measured FP64 FMA throughput of the device in GFLOP/s (dependent-free DFMA chains on every SM, 2 flops per DFMA): the
+ * denominator of the factor kernel's roofline fraction */
+void nngp_fp64_peak(const int *device, double *gflops, int *status);
 /* Page-locked host buffers.  Vectors handed to the library from such a buffer are DMA-ed directly (no staging copy); any other
  * host pointer is staged through an internal pinned buffer with a multi-threaded copy.  n_bytes is a double so that .C() can
  * pass sizes beyond 2^31. */

@@ -5,7 +5,7 @@ import pytest
 
 import nngp_b200 as nb
 from oracle import oracle as O
-from problems import make_problem
+from problems import make_problem, make_regression_problem
 
 pytestmark = pytest.mark.gpu
 
@@ -440,3 +440,70 @@ def test_device_record_store_and_summary():
         got = ctx.records_summary(11, 10, offsets=b0)
     want = nb.get_summary(frec[10:] - b0[:, None])
     assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("with_regressors", [False, True])
+def test_concurrent_chains_are_bit_identical_to_sequential_ones(with_regressors):
+    """nngp_chains_run[_regressors] (update_Gaussian.R:22-26: chains advance concurrently) -- three chains co-scheduled on one GPU,
+    each on its own context / stream / host thread -- must return exactly what three nngp_chain_run calls return one after the
+    other: every draw is keyed by (iter_start, chain_index), nothing by timing."""
+    n, m, n_iter = 4000, 5, 12
+    P = make_regression_problem(n, m, seed=61, n_extra_obs=100) if with_regressors else make_problem(n, m, seed=61, n_extra_obs=100)
+    y = P["y"]
+    var_y = float(np.var(y, ddof=1))
+    p0 = [dict(shape=[np.log(0.08 + 0.02 * k)], beta_0=0.1 * k, log_scale=-0.1 * k, log_noise_variance=-0.5) for k in range(3)]
+    rng = np.random.default_rng(3)
+    fields = [P["field"] + 0.1 * rng.standard_normal(n) for _ in range(3)]
+    betas = [0.1 * rng.standard_normal(P["X"].shape[1]) for _ in range(3)] if with_regressors else None
+
+    def make():
+        cs = []
+        for k in range(3):
+            c = nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"])
+            if with_regressors:
+                c.regressors_set(P["X"], y, xlocs=P["xlocs"], first_obs=P["first_obs"])
+            else:
+                c.obs_set(y)
+            c.field_set(fields[k])
+            cs.append(c)
+        return cs
+
+    seq, cs = [], make()
+    try:
+        for k, c in enumerate(cs):
+            if with_regressors:
+                seq.append(c.chain_run_regressors(p0[k], betas[k], P["solve_1XT1X"], P["chol_solve_1XT1X"], n_iter, var_y, thin=0.5,
+                                                  n_chromatic=3, iter_start=0, chain_index=k + 1) + (c.field_get(),))
+            else:
+                seq.append(c.chain_run(p0[k], n_iter, var_y, thin=0.5, n_chromatic=3, iter_start=0, chain_index=k + 1) + (c.field_get(),))
+    finally:
+        for c in cs:
+            c.close()
+    cs = make()
+    try:
+        kw = dict(thin=0.5, n_chromatic=3, iter_start=0, chain_indices=[1, 2, 3])
+        if with_regressors:
+            con = nb.chains_run(cs, p0, n_iter, var_y, betas=betas, solve_1XT1X=P["solve_1XT1X"], chol_solve_1XT1X=P["chol_solve_1XT1X"], **kw)
+        else:
+            con = nb.chains_run(cs, p0, n_iter, var_y, **kw)
+        for k in range(3):
+            for a, b in zip(seq[k][1:-1], con[k][1:]):          # records, (beta records,) field records, accepts
+                assert np.array_equal(a, b)
+            assert np.array_equal(seq[k][-1], cs[k].field_get())
+            for key in ("beta_0", "log_scale", "log_noise_variance", "logvar_sufficient", "logvar_ancillary"):
+                assert seq[k][0][key] == con[k][0][key]
+        # max_concurrent = 1 is the sequential schedule
+        for k, c in enumerate(cs):
+            c.field_set(fields[k])
+            if not with_regressors:
+                c.obs_set(y)
+        if not with_regressors:
+            one = nb.chains_run(cs, p0, n_iter, var_y, max_concurrent=1, **kw)
+            for k in range(3):
+                assert np.array_equal(one[k][1], con[k][1])
+        # two chains on one context are refused
+        with pytest.raises(nb.NNGPError):
+            nb.chains_run([cs[0], cs[0]], p0[:2], 2, var_y)
+    finally:
+        for c in cs:
+            c.close()
