@@ -1,10 +1,12 @@
 # R/mcmc_nngp_predict.R -- drop-in for mcmc_nngp_predict_field of the reference (Scripts/mcmc_nngp_predict.R:1-60): same
 # arguments, same list(predicted_locs, predicted_field_samples, predicted_field_summary).  The joint neighbour table is built
 # by the library's host utility, the Vecchia factor of the joint site set by nngp_factor_build (only when the shape
-# parameters of the stored sample changed, as the reference does), and each stored field sample is carried to the new sites
+# parameters differ from the previous stored sample's; the reference factors once per distinct shape row via !duplicated(),
+# predict.R:24 -- the same set of factorisations, since a shape row only repeats on consecutive rejected iterations), and each
+# stored field sample is carried to the new sites
 # by nngp_predict_sample, which solves the new rows only.  Chains are processed one after the other on one GPU (the
 # reference forks them, :16; a CUDA context does not survive fork()).  Untested in the build image (no R there).
-source(file.path("R", "nngp_b200.R"))
+if(!exists("nngp_b200_load")) source(file.path(Sys.getenv("NNGP_B200_HOME", unset = "."), "R", "nngp_b200.R"))
 
 mcmc_nngp_predict_field = function(mcmc_nngp_list, predicted_locs, burn_in = .5, n_cores = 1, m = 10, device = 0L)
 {

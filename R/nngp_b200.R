@@ -4,7 +4,19 @@
 # would add (INTEGRATION.md).  Every ABI function takes only pointers and returns void, so .C() needs no compiled shim.
 # NAOK = TRUE lets NA_integer_ (INT_MIN) in NNarray reach the library unchanged.
 
-nngp_b200_load = function(path = file.path("improving-performances-of-mcmc-for-nearest-neighbor-gaussian-process-models-with-full-data-augmentat_b200", "libnngp_b200.so"))
+# The library is built to <repo>/lib/libnngp_b200.so (python <package>/build.py).  NNGP_B200_HOME, if set, is the repo root;
+# otherwise the path is resolved relative to this file when it was source()d with chdir / from the repo root.
+nngp_b200_home = function()
+{
+  home = Sys.getenv("NNGP_B200_HOME", unset = NA)
+  if(!is.na(home)) return(home)
+  this = tryCatch(normalizePath(sys.frame(1)$ofile), error = function(e) NA)   # set while source()ing this file
+  if(!is.na(this)) return(dirname(dirname(this)))
+  getwd()
+}
+.nngp_b200_home = nngp_b200_home()
+
+nngp_b200_load = function(path = file.path(.nngp_b200_home, "lib", "libnngp_b200.so"))
 {
   if(!is.loaded("nngp_ctx_create")) dyn.load(path)
   invisible(TRUE)
@@ -22,7 +34,8 @@ nngp_check = function(res)
 {
   if(res$status != 0L)
   {
-    msg = .C("nngp_last_error", buf = paste(rep(" ", 1024), collapse = ""), len = 1024L)$buf
+    # .C() passes a character vector as char **: nngp_last_error_r writes into the first string (1024 blanks = room for the message)
+    msg = .C("nngp_last_error_r", buf = strrep(" ", 1024), len = 1024L)$buf
     stop(paste0("libnngp_b200 status ", res$status, ": ", trimws(msg)))
   }
   res
@@ -41,6 +54,27 @@ nngp_ctx_create = function(locs, vecchia_approx, stationary_covfun, device = 0L,
 }
 
 nngp_ctx_destroy = function(ctx) invisible(.C("nngp_ctx_destroy", ctx_id = as.integer(ctx), status = integer(1)))
+
+# Contexts are kept between the cycles of mcmc_nngp_run (one per chain: structure upload, tile build and colouring check at
+# n = 1M cost more than a whole cycle's compute): an environment keyed by chain, reused while the structure is the same object
+.nngp_b200_cache = new.env()
+nngp_chain_context = function(chain, locs, vecchia_approx, stationary_covfun, device)
+{
+  key = paste0("chain_", chain)
+  sig = list(n = nrow(as.matrix(locs)), m = ncol(vecchia_approx$NNarray) - 1L, covfun = stationary_covfun, device = as.integer(device),
+             nn_head = vecchia_approx$NNarray[seq_len(min(64L, length(vecchia_approx$NNarray)))], n_obs = vecchia_approx$n_obs)
+  hit = .nngp_b200_cache[[key]]
+  if(!is.null(hit) && identical(hit$sig, sig)) return(hit$ctx)
+  if(!is.null(hit)) nngp_ctx_destroy(hit$ctx)
+  ctx = nngp_ctx_create(locs, vecchia_approx, stationary_covfun, device = device)
+  .nngp_b200_cache[[key]] = list(sig = sig, ctx = ctx, regressors = FALSE)
+  ctx
+}
+nngp_b200_release = function()
+{
+  for(key in ls(.nngp_b200_cache)) { nngp_ctx_destroy(.nngp_b200_cache[[key]]$ctx); rm(list = key, envir = .nngp_b200_cache) }
+  invisible(TRUE)
+}
 
 # GpGp::vecchia_Linv replacement; returns the number of non-positive-definite neighbour blocks
 nngp_factor_build = function(ctx, covparms, slot = 0L)
@@ -111,6 +145,39 @@ nngp_chain_run_regressors = function(ctx, params, transition_kernels, X, n_iter,
                 field_records_out = double(max(n_frec, 1) * n_locs), accept_out = integer(2 * n_iter), status = integer(1)))
 }
 
+# all chains of a cycle behind ONE call, advanced concurrently (mclapply over chains, update_Gaussian.R:22-26): chain k runs on
+# ctxs[k] (its own GPU / stream / host thread), at most max_concurrent (= n_cores) in flight.  params: n_chains x (5 + k) matrix
+# with ROWS [beta_0, log_scale, log_noise_variance, logvar_sufficient, logvar_ancillary, shape...]; per-chain blocks come back
+# chain after chain.  .C() cannot carry long vectors: n_chains * round(n_iter * thin) * n_locs must stay below 2^31 (lower
+# field_thinning or use the .Call glue of R/r_glue.c, which has no such limit).
+nngp_chains_run = function(ctxs, params, n_iter, field_thinning, n_chromatic, iter_start, chain_index, var_y, n_locs, rng_mode = 1L,
+                           max_concurrent = length(ctxs))
+{
+  nc = length(ctxs); k = ncol(params) - 5L
+  n_frec = round(n_iter * field_thinning)
+  if(as.double(nc) * max(n_frec, 1) * n_locs >= 2^31) stop("field records exceed what the dot-C interface can carry (2^31 - 1 doubles): lower field_thinning or use R/r_glue.c")
+  nngp_check(.C("nngp_chains_run", n_chains = as.integer(nc), ctx_ids = as.integer(ctxs), n_shape = as.integer(k), params_io = as.double(t(params)),
+                n_iter = as.integer(n_iter), thin = as.double(field_thinning), n_chromatic = as.integer(n_chromatic),
+                iter_start = as.integer(iter_start), chain_index = as.integer(chain_index), rng_mode = as.integer(rng_mode),
+                var_y = as.double(var_y), max_concurrent = as.integer(max(1L, max_concurrent)), records_out = double(nc * n_iter * (3 + k)),
+                field_records_out = double(nc * max(n_frec, 1) * n_locs), accept_out = integer(nc * 2 * n_iter), status = integer(1)))
+}
+
+nngp_chains_run_regressors = function(ctxs, params, beta, X, n_iter, field_thinning, n_chromatic, iter_start, chain_index, var_y, n_locs,
+                                      rng_mode = 1L, max_concurrent = length(ctxs))
+{
+  nc = length(ctxs); k = ncol(params) - 5L; p = ncol(X$X)
+  n_frec = round(n_iter * field_thinning)
+  if(as.double(nc) * max(n_frec, 1) * n_locs >= 2^31) stop("field records exceed what the dot-C interface can carry (2^31 - 1 doubles): lower field_thinning or use R/r_glue.c")
+  nngp_check(.C("nngp_chains_run_regressors", n_chains = as.integer(nc), ctx_ids = as.integer(ctxs), n_shape = as.integer(k),
+                params_io = as.double(t(params)), beta_io = as.double(t(beta)), solve_1XT1X = as.double(X$solve_1XT1X),
+                chol_solve_1XT1X = as.double(X$chol_solve_1XT1X), n_iter = as.integer(n_iter), thin = as.double(field_thinning),
+                n_chromatic = as.integer(n_chromatic), iter_start = as.integer(iter_start), chain_index = as.integer(chain_index),
+                rng_mode = as.integer(rng_mode), var_y = as.double(var_y), max_concurrent = as.integer(max(1L, max_concurrent)),
+                records_out = double(nc * n_iter * (3 + k)), beta_records_out = double(nc * n_iter * p),
+                field_records_out = double(nc * max(n_frec, 1) * n_locs), accept_out = integer(nc * 2 * n_iter), status = integer(1)))
+}
+
 # GpGp::find_ordered_nn replacement (exact m nearest previous sites, ties by lower index; initialize.R:93, predict.R:5)
 nngp_find_ordered_nn = function(locs, m)
 {
@@ -151,3 +218,9 @@ nngp_order_maxmin = function(locs)
   locs = as.matrix(locs)
   nngp_check(.C("nngp_host_order_maxmin", locs = as.double(locs), n = nrow(locs), d = ncol(locs), order = integer(nrow(locs)), status = integer(1)))$order
 }
+
+# the same colouring from the MRF adjacency matrix itself (dgCMatrix slots): what R/Coloring.R, the drop-in for
+# Scripts/Coloring.R, calls
+nngp_greedy_coloring_adj = function(M)
+  nngp_check(.C("nngp_host_greedy_coloring_adj", adj_p = as.integer(M@p), adj_i = as.integer(M@i), n = nrow(M), coloring = integer(nrow(M)),
+                n_colors = integer(1), status = integer(1)))$coloring

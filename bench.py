@@ -162,12 +162,14 @@ def build_problem(n, m, seed, reordering="random"):
 # reference arm / cpu_baseline: the oracle restatement of the reference's CPU path (R + GpGp + Matrix are not in this image)
 # ---------------------------------------------------------------------------------------------------------------------
 def _oracle_chain_worker(args):
-    n, m, seed, steps, warmup, form = args
+    n, m, seed, steps, warmup, form, reordering = args
     from oracle import oracle as O
     rng = np.random.default_rng(seed)
     locs = rng.random((n, 2))
     os.environ["NNGP_QUIET"] = "1"
     import nngp_b200 as nb   # host set-up utilities only (no CUDA call is made in this process)
+    if reordering == "maxmin":
+        locs = locs[nb.order_maxmin(locs) - 1]
     nn = nb.find_ordered_nn(locs, m)
     coloring = nb.greedy_coloring(nn)
     Linv = O.vecchia_Linv([1.0, RANGE, 0.0], "exponential_isotropic", locs, nn)
@@ -188,9 +190,9 @@ def _oracle_chain_worker(args):
     return times[warmup:]
 
 
-def oracle_steps_per_sec(n, m, steps, warmup, procs, form="reference"):
+def oracle_steps_per_sec(n, m, steps, warmup, procs, form="reference", reordering="maxmin"):
     import multiprocessing as mp
-    args = [(n, m, 100 + k, steps, warmup, form) for k in range(procs)]
+    args = [(n, m, 100 + k, steps, warmup, form, reordering) for k in range(procs)]
     if procs == 1:
         res = [_oracle_chain_worker(args[0])]
     else:
@@ -218,7 +220,7 @@ def run_reference(a):
     n = a.sites_per_gpu if a.ref_n is None else a.ref_n
     steps = max(1, min(a.steps, 3))
     warmup = min(a.warmup, 1)
-    value, ms = oracle_steps_per_sec(n, a.m, steps, warmup, procs)
+    value, ms = oracle_steps_per_sec(n, a.m, steps, warmup, procs, reordering=a.reordering)
     scale = n / a.sites_per_gpu
     n_total = a.sites_per_gpu * a.gpus if a.n is None else a.n
     line = {
@@ -311,10 +313,14 @@ def run_single(a):
     # adaptive phase in which proposals ARE accepted (the accept branch -- transposition + precision_diag, field copy -- is in) ----
     var_y = float(np.var(y, ddof=1))
     chain_params = {"shape": [np.log(RANGE)] + ([0.0] if a.covfun.startswith("matern") else []), "beta_0": 0.0, "log_scale": ls, "log_noise_variance": lnv}
-    n_chain_it = 50
-    ctx.chain_run(chain_params, 3, var_y, thin=0.0, n_chromatic=10, iter_start=0, chain_index=1, keep_field=False)
+    n_chain_it, n_adapt = 50, 700
+    # the adaptive phase (update_Gaussian.R:153-157,209-213) shrinks the proposal variances until proposals are accepted: at n = 1M
+    # the posterior of the covariance parameters is so narrow that this takes several hundred iterations from logvar = -2
+    adapted, _, _, _ = ctx.chain_run(chain_params, n_adapt, var_y, thin=0.0, n_chromatic=10, iter_start=0, chain_index=1, keep_field=False)
+    chain_params_t = dict(chain_params, **{k: adapted[k] for k in ("beta_0", "log_scale", "log_noise_variance", "logvar_sufficient", "logvar_ancillary")},
+                          shape=list(adapted["shape"]))
     t0 = time.perf_counter()
-    _, _, _, acc = ctx.chain_run(chain_params, n_chain_it, var_y, thin=0.0, n_chromatic=10, iter_start=0, chain_index=1, keep_field=False)
+    _, _, _, acc = ctx.chain_run(chain_params_t, n_chain_it, var_y, thin=0.0, n_chromatic=10, iter_start=n_adapt, chain_index=1, keep_field=False)
     chain_it_per_s = n_chain_it / (time.perf_counter() - t0)
     chain_accepts = [int(acc[:, 0].sum()), int(acc[:, 1].sum())]
     ctx.field_set(w)
@@ -420,7 +426,7 @@ def run_single(a):
         "gibbs_sweeps_per_sec": 1e3 / sweep_ms, "loglik_evals_per_sec": 1e3 / comp["loglik"]["median"],
         "factor_builds_per_sec": 1e3 / fac_ms,
         "chain_iterations_per_sec": chain_it_per_s, "chain_accepts_ancillary_sufficient": chain_accepts,
-        "chain_iteration": f"nngp_chain_run, {n_chain_it} iterations from iter_start = 0 (adaptive phase: proposals are accepted): reference loop "
+        "chain_iteration": f"nngp_chain_run, {n_chain_it} iterations after {n_adapt} adaptive ones (proposal variances tuned, proposals are accepted: accept branch = transposition + precision_diag + field copy in the number): reference loop "
                            "update_Gaussian.R:101-314 (2 factor rebuilds, ancillary SpMV+SpTRSV, 2 log-liks, beta_0, 10 sweeps, noise steps), host wall clock",
         "multi_chain": multi,
         "predicted_field_samples_per_sec": pred_per_s,
@@ -444,8 +450,8 @@ def run_single(a):
         "gpu_launches": int(launches), "launches_per_step": int(launches_per_step), "clocks": clocks, "git_sha": git_sha(),
     }
     if not a.no_cpu_baseline:
-        v, ms = oracle_steps_per_sec(n, m, steps=2, warmup=0, procs=1)
-        v2, ms2 = oracle_steps_per_sec(n, m, steps=2, warmup=0, procs=1, form="residual")
+        v, ms = oracle_steps_per_sec(n, m, steps=2, warmup=0, procs=1, reordering=a.reordering)
+        v2, ms2 = oracle_steps_per_sec(n, m, steps=2, warmup=0, procs=1, form="residual", reordering=a.reordering)
         line["cpu_baseline"] = {"value": v, "unit": "steps/s (1M-site blocks)", "cores": 1, "kind": "port",
                                 "sample": f"oracle restatement (not R/GpGp), 1 thread, full n={n}: 2 steps of reference-form sweep (one mat-vec per colour) + log-lik",
                                 "residual_form_value": v2,
@@ -657,7 +663,7 @@ def main():
     ap.add_argument("--sites-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--nbrs", "--m", dest="m", type=int, default=10)
     ap.add_argument("--covfun", default="exponential_isotropic", choices=["exponential_isotropic", "matern_isotropic"])
-    ap.add_argument("--reordering", default="random", choices=["random", "maxmin"])
+    ap.add_argument("--reordering", default="maxmin", choices=["random", "maxmin"], help="maxmin = the reference default (initialize.R:29)")
     ap.add_argument("--ref-n", type=int, default=None, help="reference arm: run on a smaller n and scale (bounded sample)")
     ap.add_argument("--ref-procs", type=int, default=32, help="reference arm: at most this many independent chains (one per host core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

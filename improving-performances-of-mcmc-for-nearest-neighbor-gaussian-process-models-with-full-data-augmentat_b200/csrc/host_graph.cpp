@@ -421,6 +421,36 @@ void nngp_host_greedy_coloring(const int *NNarray, const int *n, const int *m, i
     *status = NNGP_OK;
 }
 
+// first-fit colouring straight from an adjacency structure in compressed-column form (0-based row ids, diagonal allowed), i.e.
+// the slots @p / @i of the dgCMatrix the reference hands to naive_greedy_coloring (Scripts/Coloring.R:2-20, called at
+// Scripts/mcmc_nngp_initialize.R:110): same colours 1..K as the R loop, O(n + nnz) instead of its (n+1) x maxdeg double scratch
+void nngp_host_greedy_coloring_adj(const int *adj_p, const int *adj_i, const int *n, int *coloring, int *n_colors, int *status) {
+    if (!adj_p || !adj_i || !n || !coloring || *n < 0) { nngp::set_error("nngp_host_greedy_coloring_adj: bad argument"); if (status) *status = NNGP_ERR_ARG; return; }
+    const int nn = *n;
+    int K = 0;
+    std::vector<int> mark;   // mark[c] = last node whose neighbourhood contained colour c
+    for (int i = 0; i < nn; i++) {
+        if (adj_p[i + 1] < adj_p[i]) { nngp::set_error("nngp_host_greedy_coloring_adj: adj_p is not non-decreasing"); if (status) *status = NNGP_ERR_ARG; return; }
+        coloring[i] = 0;
+    }
+    // Coloring.R marks the neighbours of i (self included) as incompatible with cols[i] AFTER colouring i, so node i sees the
+    // colours of its lower-indexed neighbours only: first colour not used by an already coloured neighbour
+    for (int i = 0; i < nn; i++) {
+        for (int e = adj_p[i]; e < adj_p[i + 1]; e++) {
+            const int j = adj_i[e];
+            if (j < 0 || j >= nn) { nngp::set_error("nngp_host_greedy_coloring_adj: adj_i[%d] = %d out of range", e, j); if (status) *status = NNGP_ERR_ARG; return; }
+            const int c = coloring[j];
+            if (j != i && c > 0) { if ((int)mark.size() <= c) mark.resize(c + 1, -1); mark[c] = i; }
+        }
+        int c = 1;
+        while (c < (int)mark.size() && mark[c] == i) c++;
+        coloring[i] = c;
+        K = std::max(K, c);
+    }
+    if (n_colors) *n_colors = K;
+    if (status) *status = NNGP_OK;
+}
+
 void nngp_host_order_maxmin(const double *locs, const int *n, const int *d, int *order, int *status) {
     if (!locs || !n || !d || !order || *n < 0 || *d < 1) { nngp::set_error("nngp_host_order_maxmin: bad argument"); if (status) *status = NNGP_ERR_ARG; return; }
     nngp::order_maxmin(locs, *n, *d, order);

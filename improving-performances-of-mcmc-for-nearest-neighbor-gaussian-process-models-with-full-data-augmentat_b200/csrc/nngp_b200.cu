@@ -855,6 +855,13 @@ void nngp_last_error(char *buf, const int *len) {
     buf[*len - 1] = '\0';
 }
 
+// R's .C() hands a character vector over as char **: the message goes into the first string, which the caller has sized
+// (e.g. strrep(" ", 1024)) -- writing through nngp_last_error's char * there would overwrite the pointer slot itself
+void nngp_last_error_r(char **buf, const int *len) {
+    if (!buf || !buf[0] || !len || *len <= 0) return;
+    nngp_last_error(buf[0], len);
+}
+
 void nngp_host_alloc(const double *n_bytes, void **ptr, int *status) {
     ABI_BEGIN
     REQUIRE(n_bytes && ptr && *n_bytes >= 0, "nngp_host_alloc: bad argument");

@@ -64,6 +64,9 @@ void nngp_version(int *major, int *minor);
 void nngp_device_count(int *count, int *status);
 /* copies the last error message (NUL-terminated, truncated to *len bytes) */
 void nngp_last_error(char *buf, const int *len);
+/* the same for R's .C(), which passes a character vector as char **: the message is written into buf[0] (a string of at least
+ * *len bytes, e.g. strrep(" ", 1024)) */
+void nngp_last_error_r(char **buf, const int *len);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * host-side set-up utilities (init-time in the reference too)
@@ -75,6 +78,9 @@ void nngp_host_find_ordered_nn(const double *locs, const int *n, const int *d, c
 /* replaces the crossprod() moral graph + naive_greedy_coloring (Scripts/mcmc_nngp_initialize.R:103-110,
  * Scripts/Coloring.R:2-20) without the dense (n+1) x maxdeg scratch: identical first-fit colours 1..K. */
 void nngp_host_greedy_coloring(const int *NNarray, const int *n, const int *m, int *coloring, int *n_colors, int *status);
+/* drop-in for naive_greedy_coloring(M) itself (Scripts/Coloring.R:2-20): M's compressed-column slots M@p (n + 1) and M@i (0-based),
+ * i.e. the MRF adjacency matrix of Scripts/mcmc_nngp_initialize.R:103-109; same colours, no dense (n+1) x maxdeg scratch */
+void nngp_host_greedy_coloring_adj(const int *adj_p, const int *adj_i, const int *n, int *coloring, int *n_colors, int *status);
 /* exact max-min (farthest-point) ordering, 1-based permutation (replaces GpGp::order_maxmin,
  * Scripts/mcmc_nngp_initialize.R:29; GpGp's is a randomised approximation and cannot be reproduced bit-for-bit) */
 void nngp_host_order_maxmin(const double *locs, const int *n, const int *d, int *order, int *status);
