@@ -146,14 +146,14 @@ struct Ctx {
     // peer-to-peer transport: own area + the peers' areas (CUDA IPC mappings, or direct pointers inside one process)
     bool p2p = false;
     double *p2p_area = nullptr;            // [16 halo flags | 16 reduction flags | 2 x 32 reduction slots | recv values x 2 parities]
-    size_t p2p_flag_off = 0, p2p_rflag_off = 16, p2p_slot_off = 32, p2p_val_off = 96, p2p_doubles = 0, p2p_parity_stride = 0;
+    size_t p2p_flag_off = 0, p2p_rflag_off = 16, p2p_slot_off = 32, p2p_hdr_off = 96, p2p_val_off = 112, p2p_doubles = 0, p2p_parity_stride = 0;
+    unsigned int peer_stride[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // parity stride of every peer's receive values (read from its area header)
     PeerTable peers{};
     void *peer_mapped[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned long long red_epoch = 0;
     int graph_launches = 0;
     std::vector<int> send_proc;            // processing id of every entry of the send lists
     std::vector<int> btile_count;          // per colour: tiles that hold boundary sites (they come first inside the colour)
-    std::vector<unsigned int> send_mask, recv_mask;   // per colour: peers this rank sends to / receives from
     DevBuf<unsigned long long> d_shard_state;         // [0] sweeps since connect, [1 + colour] boundary tiles done
     DevBuf<int> d_bptr;
     DevBuf<int2> d_bdst;
@@ -509,7 +509,8 @@ static ShardConst shard_const(Ctx *c) {
     sc.state = c->d_shard_state.p;
     sc.err = c->d_nbad.p + 1;
     sc.world = c->world; sc.rank = c->rank; sc.K = c->K;
-    sc.flag_off = (unsigned int)c->p2p_flag_off; sc.val_off = (unsigned int)c->p2p_val_off; sc.parity_stride = (unsigned int)c->p2p_parity_stride;
+    sc.val_off = (unsigned int)c->p2p_val_off;
+    for (int h = 0; h < 8; h++) sc.peer_stride[h] = c->peer_stride[h];
     return sc;
 }
 
@@ -539,11 +540,9 @@ static int launch_sweep_colors(Ctx *c) {
             cl.n_btiles = c->btile_count[col];
             cl.g0 = c->recv_ptr[(size_t)col * W];
             cl.g1 = c->recv_ptr[(size_t)(col + 1) * W];
-            cl.send_mask = c->send_mask[col];
-            cl.recv_mask = c->recv_mask[col];
             cl.col = col;
             const int ng = cl.g1 - cl.g0;
-            if (ng > 0) grid += std::min(16, (ng + 3) / 4);   // ghost CTAs: one warp per ghost site, 4 warps per CTA
+            if (ng > 0) grid += std::min(32, (ng + 3) / 4);   // ghost CTAs: one warp per ghost site, 4 warps per CTA
         }
         if (grid == 0) continue;
         const bool pdl = c->sweep_variant != 2 && !(c->sharded && !fused_halo);
@@ -630,7 +629,13 @@ static void check_solve_flag(Ctx *c) {
     CK(cudaMemcpyAsync(c->h_pinned + 9, c->d_nbad.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     std::memcpy(&flag, c->h_pinned + 9, sizeof(int));
-    if (flag == 2) { set_error("sharded field: timed out waiting for a peer's halo / reduction flag (a rank died or fell out of step)"); throw NcclFail(); }
+    if (flag == 2) {
+        unsigned long long dbg[4] = {0, 0, 0, 0};
+        if (c->d_shard_state.p) cudaMemcpy(dbg, c->d_shard_state.p, sizeof(dbg), cudaMemcpyDeviceToHost);
+        set_error("sharded field: rank %d timed out waiting for a peer's halo value / reduction flag (a rank died or fell out of step); last halo wait recorded: colour %llu, ghost slot %llu, sweep %llu (this rank is at sweep %llu)",
+                  c->rank, dbg[1] + 1, dbg[2], dbg[3], dbg[0]);
+        throw NcclFail();
+    }
     if (flag) { set_error("triangular solve: dependency wait timed out (corrupted neighbour structure?)"); throw CudaFail(); }
 }
 
@@ -913,6 +918,14 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: libnngp_b200 has no CPU fallback"); throw CudaFail(); }
     REQUIRE(*device >= 0 && *device < ndev, "device %d out of range (%d devices)", *device, ndev);
 
+    const bool prof_create = std::getenv("NNGP_PROFILE_CREATE") != nullptr;
+    auto t_create = std::chrono::steady_clock::now();
+    auto phase = [&](const char *what) {
+        if (!prof_create) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[nngp ctx_create] %-28s %8.1f ms\n", what, 1e3 * std::chrono::duration<double>(now - t_create).count());
+        t_create = now;
+    };
     c = new Ctx();
     c->device = *device;
     c->layout = (*layout == NNGP_LAYOUT_COLOR || *layout == NNGP_LAYOUT_COLOR_MORTON) ? *layout : NNGP_LAYOUT_MORTON;
@@ -928,6 +941,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     CK(cudaEventCreate(&c->ev1));
     CK(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
 
+    phase("cuda stream / events");
     // ---- validate structure, colour classes ----
     // coloring all zero = "no colouring": a context that never sweeps (the joint observed ++ predicted site set of
     // mcmc_nngp_predict_field, predict.R:4-8, has none).  Internally one colour class; every sweep entry point refuses.
@@ -973,6 +987,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
             }
         }
     }
+    phase("validation");
     // ---- numberings ----
     // storage order: NNGP_LAYOUT_MORTON = Z-curve over all sites; NNGP_LAYOUT_COLOR[_MORTON] = colour-major (reference / Z-curve
     // order inside a colour).  processing order (sweep) = colour-major, storage order inside a colour.
@@ -1041,6 +1056,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         }
     }
 
+    phase("orderings (2 sorts)");
     // ---- row structure in storage numbering ----
     const int ld = c->ld;
     std::vector<int> nn((size_t)ld * M, -1);
@@ -1057,6 +1073,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     std::vector<double> locs_int((size_t)n * d);
     for (int q = 0; q < n; q++)
         for (int k = 0; k < d; k++) locs_int[(size_t)q * d + k] = locs[(size_t)c->i2g[q] + (size_t)n * k];
+    phase("row structure");
     // ---- transpose (CSC) structure: columns in processing order, row ids in storage numbering ----
     std::vector<int> colptr(n + 1, 0);
     for (int q = 0; q < n; q++)
@@ -1072,6 +1089,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
                 if (v >= 0) { const int p = pof[v]; crow[pos[p]] = q; csrc[pos[p]] = j * ld + q; pos[p]++; }
             }
     }
+    phase("transpose structure");
     // ---- solve DAG levels ----
     std::vector<int> level;
     c->n_levels = solve_levels(NNarray, n, m, level);
@@ -1104,6 +1122,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         while (rows_padded.size() % 32) rows_padded.push_back(-1);
     }
     c->n_slots = (int)rows_padded.size();
+    phase("solve levels");
     // ---- sweep tiles: runs of consecutive same-colour sites with <= 128 sites and <= 1024 CSC entries; a tile never mixes
     // boundary and interior sites ----
     std::vector<int4> tiles;
@@ -1137,6 +1156,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         for (int q = tl.x; q < tl.y; q++)
             for (int e = colptr[q]; e < colptr[q + 1]; e++) cloc[(size_t)t * 1024 + (size_t)(e - tl.z)] = (unsigned char)(q - tl.x);
     }
+    phase("tiles");
     // ---- observations: lm in storage numbering (gathers of field); per-site lists / counts in processing order ----
     std::vector<int> lm(n_obs), optr(n + 1, 0), oidx(n_obs);
     for (int o = 0; o < n_obs; o++) {
@@ -1150,6 +1170,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         std::vector<int> pos(optr.begin(), optr.end() - 1);
         for (int o = 0; o < n_obs; o++) oidx[pos[pof[lm[o]]]++] = o;
     }
+    phase("observations");
     // ---- upload ----
     cudaStream_t s = c->stream;
     c->d_psite.upload(psite, s); c->d_gid.upload(gid, s);
@@ -1190,13 +1211,6 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
             recv_proc[k] = pof[c->g2i[ref]];
         }
         REQUIRE(W <= 8, "at most 8 ranks per field");
-        c->send_mask.assign(K, 0u);
-        c->recv_mask.assign(K, 0u);
-        for (int col = 0; col < K; col++)
-            for (int h = 0; h < W; h++) {
-                if (c->send_ptr[(size_t)col * W + h + 1] > c->send_ptr[(size_t)col * W + h]) c->send_mask[col] |= 1u << h;
-                if (c->recv_ptr[(size_t)col * W + h + 1] > c->recv_ptr[(size_t)col * W + h]) c->recv_mask[col] |= 1u << h;
-            }
         std::vector<unsigned char> owned_storage(n);
         for (int q = 0; q < n; q++) owned_storage[q] = sh->owned[c->i2g[q]] ? 1 : 0;
         c->d_send_storage.upload(send_storage, s);
@@ -1207,18 +1221,20 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         // rank knows where its peers' flags are: [16 halo flags | 16 reduction flags | 2 x 32 reduction slots | receive values of
         // even sweeps | receive values of odd sweeps] (two parities: a peer one sweep ahead never overwrites unread values)
         const size_t nrecv = (std::max<size_t>(recv_proc.size(), 1) + 15) / 16 * 16;
-        c->p2p_flag_off = 0;
-        c->p2p_rflag_off = 16;
-        c->p2p_slot_off = 32;
-        c->p2p_val_off = 96;
         c->p2p_parity_stride = nrecv;
         c->p2p_doubles = std::max<size_t>(c->p2p_val_off + 2 * nrecv, (size_t)1 << 18);   // >= 2 MB: a whole allocation of its own
         CK(cudaMalloc(&c->p2p_area, c->p2p_doubles * sizeof(double)));
         CK(cudaMemsetAsync(c->p2p_area, 0, c->p2p_doubles * sizeof(double), s));
+        {   // header: what a peer must know about this rank's area (read by the peers when they connect)
+            unsigned long long *hdr = reinterpret_cast<unsigned long long *>(c->h_pinned + 40);
+            hdr[0] = (unsigned long long)nrecv;
+            hdr[1] = (unsigned long long)recv_proc.size();
+            CK(cudaMemcpyAsync(c->p2p_area + c->p2p_hdr_off, hdr, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        }
         c->d_recvbuf.p = c->p2p_area + c->p2p_val_off;      // not owned by the DevBuf (released with the area)
         c->d_recvbuf.n = 0;
-        c->d_shard_state.alloc((size_t)K + 1);
-        CK(cudaMemsetAsync(c->d_shard_state.p, 0, ((size_t)K + 1) * sizeof(unsigned long long), s));
+        c->d_shard_state.alloc(4);
+        CK(cudaMemsetAsync(c->d_shard_state.p, 0, 4 * sizeof(unsigned long long), s));
         CK(cudaStreamSynchronize(s));
         if (W > 1 && sh->comm_id[0] != '\0') {   // collective: every rank of the field creates its context at the same time
             nccl_load();
@@ -1228,6 +1244,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         }
     }
     CK(cudaStreamSynchronize(s));   // host vectors go out of scope below
+    phase("allocations + uploads");
     {
         std::lock_guard<std::mutex> lk(g_ctx_mu);
         int id = -1;
@@ -1518,6 +1535,12 @@ void nngp_shard_p2p_export(const int *ctx_id, char *handle64, int *status) {
 // after the peers' areas are known: destinations of every boundary site's value (peer, slot inside the peer's receive values)
 static void finish_p2p_connect(Ctx *c, const int *peer_recv_base) {
     const int W = c->world, K = c->K;
+    for (int h = 0; h < W; h++) {   // every peer's parity stride, from the header of its (mapped) area
+        unsigned long long hdr[2] = {0, 0};
+        CK(cudaMemcpy(hdr, c->peers.area[h] + c->p2p_hdr_off, sizeof(hdr), cudaMemcpyDeviceToHost));
+        REQUIRE(hdr[0] >= 16 && hdr[0] < (1ull << 31), "peer %d: implausible area header (was its context created?)", h);
+        c->peer_stride[h] = (unsigned int)hdr[0];
+    }
     std::vector<int> bptr((size_t)c->n_owned + 1, 0);
     for (size_t k = 0; k < c->send_proc.size(); k++) bptr[(size_t)c->send_proc[k] + 1]++;
     for (int q = 0; q < c->n_owned; q++) bptr[q + 1] += bptr[q];
@@ -1530,7 +1553,9 @@ static void finish_p2p_connect(Ctx *c, const int *peer_recv_base) {
         }
     c->d_bptr.upload(bptr, c->stream);
     c->d_bdst.upload(bdst, c->stream);
-    CK(cudaMemsetAsync(c->d_shard_state.p, 0, ((size_t)K + 1) * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->d_shard_state.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    // every ghost slot (both parities) starts EMPTY: the value itself is the message (see NNGP_HALO_EMPTY)
+    fill_u64_kernel<<<grid_for(c, (long long)(2 * c->p2p_parity_stride), 256), 256, 0, c->stream>>>(reinterpret_cast<unsigned long long *>(c->p2p_area + c->p2p_val_off), NNGP_HALO_EMPTY, (int)(2 * c->p2p_parity_stride));
     CK(cudaStreamSynchronize(c->stream));
     if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; }
     c->p2p = true;

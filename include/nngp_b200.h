@@ -123,9 +123,9 @@ void nngp_ctx_create_sharded(const int *n, const int *d, const int *m, const dou
  * CUDA IPC handle (64 bytes) of its receive area, the handles are gathered by the caller, and every rank connects with the
  * table of all handles (world * 64 bytes, rank order) plus peer_recv_base[c*world + h] = offset of this rank's colour-c
  * segment inside peer h's receive area (= peer h's recv_ptr[c*world + this rank]).  Afterwards the sweep kernel of a colour
- * stores the new values of its boundary sites (their tiles run first) directly into the peers' ghost slots over NVLink and
- * raises a flag there; the ghost values that arrive are applied by trailing CTAs of the same launch, which wait only for the
- * peers that actually send in that colour.  Scalar all-reduces use the same mapped areas. */
+ * stores the new values of its boundary sites (their tiles run first) directly into the peers' ghost slots over NVLink; the
+ * value itself is the message (an empty slot holds a reserved NaN payload), so there is no fence and no flag: trailing CTAs of
+ * the same launch apply each ghost value as soon as it has landed.  Scalar all-reduces use the same mapped areas. */
 void nngp_shard_p2p_export(const int *ctx_id, char *handle64, int *status);
 void nngp_shard_p2p_connect(const int *ctx_id, const char *all_handles, const int *peer_recv_base, int *status);
 /* Colour-stepping form of one sharded sweep for callers that move the halo themselves (any transport; also how the sharded

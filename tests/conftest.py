@@ -4,6 +4,11 @@ import sys
 import numpy as np
 import pytest
 
+# Several shards of one field on ONE GPU (the single-GPU tests of the peer-to-peer halo protocol) wait for each other from inside
+# their kernels, so their streams must never share a hardware queue: CUDA's default is 8 queues per device, and two streams that
+# alias on one queue would serialise a waiting kernel before the kernel it waits for.  One queue per stream (the maximum is 32).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
