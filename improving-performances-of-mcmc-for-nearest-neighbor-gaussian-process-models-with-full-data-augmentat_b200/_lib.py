@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "nngp_gibbs_sweep", "nngp_ancillary_propose", "nngp_ancillary_accept", "nngp_beta0_moments", "nngp_ssr",
     "nngp_field_init", "nngp_chain_run", "nngp_regressors_set", "nngp_chain_run_regressors", "nngp_records_summary", "nngp_predict_sample", "nngp_time_op", "nngp_launch_count", "nngp_host_alloc", "nngp_host_free",
     "nngp_host_spatial_blocks", "nngp_host_shard_plan_build", "nngp_host_shard_plan_get", "nngp_shard_connect_local", "nngp_shard_group_sweep",
-    "nngp_shard_group_loglik", "nngp_chains_run", "nngp_chains_run_regressors", "nngp_time_op_group", "nngp_fp64_peak",
+    "nngp_shard_group_loglik", "nngp_shard_group_chain_run", "nngp_chains_run", "nngp_chains_run_regressors", "nngp_time_op_group", "nngp_fp64_peak",
 ]
 
 

@@ -46,7 +46,7 @@ static void bisect(const double *locs_cm, int n, int d, int *idx, int count, int
 struct ShardPlan {
     int n_local = 0, n_obs_local = 0, n_owned = 0, K = 0, W = 0, d = 0, M = 0;
     std::vector<double> locs;
-    std::vector<int> nn, coloring, owned, global_id, global_zpos, obs_index, locs_match, send_site, send_ptr, recv_site, recv_ptr;
+    std::vector<int> nn, coloring, owned, global_id, global_zpos, global_level, obs_index, locs_match, send_site, send_ptr, recv_site, recv_ptr;
 };
 
 static std::mutex g_plan_mu;
@@ -79,7 +79,10 @@ static ShardPlan *build_plan(const double *locs, const int *NNarray, const int *
     int nl = 0;
     for (int s = 0; s < n; s++) if (mask[s] & me) g2l[s] = nl++;
     P->n_local = nl;
-    P->global_id.resize(nl); P->coloring.resize(nl); P->owned.resize(nl); P->global_zpos.resize(nl);
+    P->global_id.resize(nl); P->coloring.resize(nl); P->owned.resize(nl); P->global_zpos.resize(nl); P->global_level.resize(nl);
+    // depth of every row in the WHOLE field's solve DAG: all ranks order their owned rows by it (sharded triangular solve)
+    std::vector<int> level;
+    solve_levels(NNarray, n, m, level);
     P->locs.resize((size_t)nl * d);
     P->nn.assign((size_t)nl * M, NNGP_NA_INT);
     // position of every site in the reference's rnorm() hand-out order: colour 1..K, ascending index inside a colour
@@ -91,6 +94,7 @@ static ShardPlan *build_plan(const double *locs, const int *NNarray, const int *
         const int l = g2l[s];
         if (l < 0) continue;
         P->global_zpos[l] = zp;
+        P->global_level[l] = level[s];
         P->global_id[l] = s;
         P->coloring[l] = coloring[s];
         P->owned[l] = owner[s] == rank ? 1 : 0;
@@ -192,7 +196,7 @@ void nngp_host_shard_plan_build(const double *locs, const int *NNarray, const in
 }
 
 void nngp_host_shard_plan_get(const int *plan_id, double *locs, int *NNarray, int *coloring, int *owned, int *global_id, int *global_zpos,
-                              int *obs_index, int *locs_match, int *send_site, int *send_ptr, int *recv_site, int *recv_ptr, int *status) {
+                              int *global_level, int *obs_index, int *locs_match, int *send_site, int *send_ptr, int *recv_site, int *recv_ptr, int *status) {
     nngp::ShardPlan *P = nullptr;
     {
         std::lock_guard<std::mutex> lk(nngp::g_plan_mu);
@@ -201,7 +205,7 @@ void nngp_host_shard_plan_get(const int *plan_id, double *locs, int *NNarray, in
     if (!P) { nngp::set_error("nngp_host_shard_plan_get: unknown plan id"); if (status) *status = NNGP_ERR_ARG; return; }
     auto put = [](auto *dst, const auto &v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
     put(locs, P->locs); put(NNarray, P->nn); put(coloring, P->coloring); put(owned, P->owned); put(global_id, P->global_id);
-    put(global_zpos, P->global_zpos); put(obs_index, P->obs_index); put(locs_match, P->locs_match); put(send_site, P->send_site);
+    put(global_zpos, P->global_zpos); put(global_level, P->global_level); put(obs_index, P->obs_index); put(locs_match, P->locs_match); put(send_site, P->send_site);
     put(send_ptr, P->send_ptr); put(recv_site, P->recv_site); put(recv_ptr, P->recv_ptr);
     delete P;
     if (status) *status = NNGP_OK;

@@ -687,6 +687,16 @@ __global__ void fill_u64_kernel(unsigned long long *__restrict__ dst, unsigned l
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) dst[t] = v;
 }
 
+struct PeerTable { double *area[8]; };   // a sharded field: the peers' areas (own entry = own area), see below
+
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -696,12 +706,23 @@ __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long *p, unsign
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <int MT>
+// SHARD: the rows are the OWNED rows of one spatial block in the order of the whole field's DAG levels; a parent that is a ghost
+// site is awaited exactly like a local one -- its owner stores the solution value straight into this rank's x over NVLink (the
+// 8-byte value is its own ready flag) -- and every owned boundary value is stored into the x of the peers that ghost the site.
+struct ShardSolve {
+    PeerTable peers;
+    const int *sxptr;             // [n_local + 1] by storage id: destinations of an owned boundary site's solution value
+    const int2 *sxdst;            // (peer, storage id of the site on that peer)
+    unsigned int x_off[8];        // offset (doubles) of the current solve's x buffer inside every peer's area
+};
+
+template <int MT, bool SHARD = false>
 __global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
                                                               const int *__restrict__ rows_padded, int n_slots,
                                                               const double *__restrict__ b, unsigned long long *x,
                                                               double *__restrict__ y, double shift, double scale, int ld, int M,
-                                                              int *ticket, int *err, unsigned int sleep_ns) {
+                                                              int *ticket, int *err, unsigned int sleep_ns,
+                                                              const __grid_constant__ ShardSolve ss) {
     // The grid is a sliding window over the level-ordered rows: each CTA repeatedly takes the next chunk of 256 slots.  A
     // bounded window (gridDim.x * 256 rows, a few DAG levels wide) keeps the number of polling threads -- and the L2 traffic
     // they generate -- small; with one thread per row for the whole DAG in flight ncu showed 1.1 GB of DRAM reads and 3 ms.
@@ -760,7 +781,7 @@ __global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restr
             while (pending) {
 #pragma unroll
                 for (int j = 1; j < MC; j++)
-                    if (bits[j] == NNGP_SOLVE_SENTINEL) bits[j] = ld_relaxed_gpu_u64(x + idx[j]);
+                    if (bits[j] == NNGP_SOLVE_SENTINEL) bits[j] = SHARD ? ld_relaxed_sys_u64(x + idx[j]) : ld_relaxed_gpu_u64(x + idx[j]);
                 pending = false;
 #pragma unroll
                 for (int j = 1; j < MC; j++) pending = pending || (bits[j] == NNGP_SOLVE_SENTINEL);
@@ -773,7 +794,15 @@ __global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restr
             for (int j = 1; j < MC; j++)
                 if (j < Mr && idx[j] >= 0) s -= a[j] * __longlong_as_double((long long)bits[j]);
             const double xv = s / a[0];
-            st_relaxed_gpu_u64(x + q0, (unsigned long long)__double_as_longlong(xv));
+            if (SHARD) {
+                st_relaxed_sys_u64(x + q0, (unsigned long long)__double_as_longlong(xv));
+                for (int k = ss.sxptr[q0]; k < ss.sxptr[q0 + 1]; k++) {   // the peers that hold this site as a ghost wait for it
+                    const int2 d = ss.sxdst[k];
+                    st_relaxed_sys_u64(reinterpret_cast<unsigned long long *>(ss.peers.area[d.x] + ss.x_off[d.x]) + d.y, (unsigned long long)__double_as_longlong(xv));
+                }
+            } else {
+                st_relaxed_gpu_u64(x + q0, (unsigned long long)__double_as_longlong(xv));
+            }
             if (y) y[q0] = shift + scale * xv;
         }
         // rotate the pipeline
@@ -960,13 +989,26 @@ template <int HINT> __device__ __forceinline__ unsigned int ld_stream_u8(const u
     return v;
 }
 
+__global__ void int_to_f64_kernel(const int *__restrict__ src, double *__restrict__ dst) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) dst[0] = (double)src[0];
+}
+
+// sharded solve, after every rank has finished: the ghost sites' solution values (stored here by their owners) -> y
+__global__ void shard_solve_ghosts_kernel(const unsigned long long *__restrict__ x, const unsigned char *__restrict__ owned, int n,
+                                          double *__restrict__ xout, double *__restrict__ y, double shift, double scale) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const double xv = __longlong_as_double((long long)x[q]);
+        if (xout) xout[q] = xv;
+        if (y && !owned[q]) y[q] = shift + scale * xv;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Sharded field: peers' receive areas, mapped through CUDA IPC (one process per GPU) or addressed directly
 // (several contexts in one process).  Area layout (doubles; the header is the same on every rank):
 //   [ 16 halo flags (u64) | 16 reduction flags | 2 x 32 reduction slots | 16-double header (u64: parity stride, ...) |
 //     receive values, parity 0 | receive values, parity 1 ]
 // ---------------------------------------------------------------------------------------------------------------
-struct PeerTable { double *area[8]; };   // peers' areas (own entry = own area)
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -983,14 +1025,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 // 2.9 us for payload + system fence + flag), and a ghost site can be applied as soon as ITS value has landed.
 #define NNGP_HALO_EMPTY 0xFFF8DEADBEEF0002ull
 
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // per-context constants of a sharded sweep
 struct ShardConst {
@@ -1022,7 +1056,7 @@ __device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const Sh
     unsigned long long *slots = reinterpret_cast<unsigned long long *>(sc.peers.area[sc.rank] + sc.val_off + (size_t)(epoch & 1ull) * sc.peer_stride[sc.rank]);
     const int warps = (int)(blockDim.x >> 5), lane = threadIdx.x & 31;
     const int n_gcta = (int)gridDim.x - cl.n_tiles;
-    bool waited = false;
+    bool first = true;
     for (int k = cl.g0 + ((int)blockIdx.x - cl.n_tiles) * warps + (int)(threadIdx.x >> 5); k < cl.g1; k += n_gcta * warps) {
         const int p = sc.gsite[k];
         const int sq = psite[p];
@@ -1031,6 +1065,11 @@ __device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const Sh
         int row = -1;
         double val = 0.0;
         if (e < e1) { row = crow[e]; val = valT[e]; }      // the first 32 entries of the column are in registers before the value arrives
+        if (PDL && first) {   // r / field of the previous colour are complete; only then may the NEXT colour's kernel become resident
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        }
+        first = false;
         unsigned long long bits = 0ull;
         if (lane == 0) {
             unsigned int spins = 0;
@@ -1044,7 +1083,6 @@ __device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const Sh
             st_relaxed_sys_u64(slots + k, NNGP_HALO_EMPTY);   // empty again for the sweep after next (same parity)
         }
         bits = __shfl_sync(0xffffffffu, bits, 0);
-        if (PDL && !waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }   // r / field of the previous colour are complete
         const double f_new = __longlong_as_double((long long)bits);
         const double delta = f_new - field[sq];
         __syncwarp();
@@ -1068,7 +1106,13 @@ __device__ __forceinline__ void shard_push_site(const ShardConst &sc, unsigned l
 // ghost CTAs]: boundary tiles come first and store their sites' new values directly into the peers' ghost slots, so the NVLink
 // hop overlaps the interior tiles; the ghost CTAs at the end of the grid wait for the values of this colour's ghost sites and
 // apply them.  One launch per colour, same PDL chain as the unsharded sweep.
-template <int THREADS, bool PDL, int MINB, int HINT = 0, bool SHARD = false>
+// LATE: griddepcontrol.launch_dependents is issued AFTER this kernel's own griddepcontrol.wait instead of at its top.  Triggering at
+// the top lets the whole rest of the sweep become resident early -- colour c+1's CTAs trigger colour c+2 before they wait, and so on --
+// and those waiting CTAs hold SM slots.  That is harmless for one stream per GPU (a kernel's predecessor is always fully resident),
+// but several streams on one GPU (shards of one field on one device, chains sharing a device) then starve, or -- when they wait for
+// each other, as shards do -- deadlock.  With LATE at most two kernels per stream are resident: the running colour and the next
+// colour's prologue.  SHARD kernels are always LATE.
+template <int THREADS, bool PDL, int MINB, int HINT = 0, bool SHARD = false, bool LATE = SHARD>
 __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *__restrict__ tiles, int tile_base,
                                                               const int *__restrict__ colptr, const int *__restrict__ crow,
                                                               const unsigned char *__restrict__ cloc,
@@ -1084,7 +1128,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
     __shared__ double sstart[THREADS], shead[THREADS];
     __shared__ double sbc[2];
     const int tid = threadIdx.x;
-    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (PDL && !LATE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (SHARD && (int)blockIdx.x >= cl.n_tiles) {
         shard_ghost_apply<PDL>(sc, cl, colptr, crow, valT, psite, field, r);
         return;
@@ -1097,6 +1141,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
     if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
         const int q = s0;
         if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (PDL && LATE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         double acc[1] = {0.0};
         for (int e = e0 + tid; e < e1; e += THREADS) acc[0] += valT[e] * r[crow[e]];
         block_reduce_sum<1>(acc);
@@ -1154,6 +1199,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
     }
     if (PDL) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (LATE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #pragma unroll
         for (int k = 0; k < EPT; k++)
             if (row[k] >= 0) rr[k] = (HINT >= 2) ? ld_keep_f64(r + row[k], keep) : r[row[k]];

@@ -153,6 +153,7 @@ struct Ctx {
     unsigned long long red_epoch = 0;
     int graph_launches = 0;
     std::vector<int> send_proc;            // processing id of every entry of the send lists
+    std::vector<int> send_storage_h;       // storage id of the same
     std::vector<int> btile_count;          // per colour: tiles that hold boundary sites (they come first inside the colour)
     DevBuf<unsigned long long> d_shard_state;         // [0] sweeps since connect, [1 + colour] boundary tiles done
     DevBuf<int> d_bptr;
@@ -169,7 +170,8 @@ struct Ctx {
     std::vector<int> tile_ptr;             // per colour, into d_tiles
     // 0 = PDL chain of 128x8 tiles (blocked segmented reduction, L2 eviction hints), 5 CTAs/SM, and the 6-CTAs/SM build for
     //     colours whose tile count would otherwise spill into a second wave (default; profiles/r01_explore_sweep_occupancy.txt)
-    // 1 = the same chain with 5 CTAs/SM everywhere; 2 = the same tiles as plain launches (no PDL); 3 = thread per site
+    // 1 = the same chain with 5 CTAs/SM everywhere; 2 = the same tiles as plain launches (no PDL); 3 = thread per site;
+    // 4 = as 0, each colour triggers its dependent only after its own wait (at most two colours resident per stream)
     int sweep_variant = 0;
     int solve_variant = 0;                 // 0 sync-free single launch, 1 level-scheduled launches
     int commit_variant = 0;                // 0 tiled transposition, 1 thread per column
@@ -217,6 +219,15 @@ struct Ctx {
     bool committed = false;           // valT / pd correspond to linv[cur]
     bool have_field = false, have_obs = false, have_newfield = false;
     bool can_sweep = true;            // false: created without a colouring (prediction context)
+    bool can_solve = true;            // false: sharded context created without the whole field's DAG levels
+    // sharded triangular solve: two solution buffers inside the peer-mapped area (peers store ghost values straight into them)
+    size_t p2p_x_off = 0, p2p_x_stride = 0, p2p_tab_off = 0;
+    unsigned int peer_x_off[8] = {0, 0, 0, 0, 0, 0, 0, 0}, peer_x_stride[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long solve_epoch = 0;
+    DevBuf<int> d_sxptr;
+    DevBuf<int2> d_sxdst;
+    std::vector<int> recv_storage;    // storage id of every ghost site, receive order
+    double n_obs_global = -1.0;       // observations of the whole field (sharded contexts: all-reduced on first use)
     CovConst last_cc{};
     bool have_cc = false;
     unsigned long long sweep_counter = 0;
@@ -460,13 +471,42 @@ static void op_spmv(Ctx *c, const double *linv, const double *v, double shift, d
 
 // x = solve(linv, b); optional y = shift + scale * x
 static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, double *y, double shift, double scale) {
+    if (c->sharded && c->world > 1) {
+        // One spatial block of a larger field: every rank solves its owned rows, in the order of the whole field's DAG levels, with
+        // the same synchronisation-free kernel; a ghost parent is awaited like a local one, because its owner stores the value
+        // straight into this rank's solution buffer over NVLink.  Two buffers alternate: buffer e & 1 serves solve e and is
+        // re-armed ("pending" everywhere) at the start of solve e - 1; the all-reduce that closes every solve keeps any rank from
+        // starting solve e + 1 -- and storing into a peer's buffer -- before every rank has finished solve e.
+        if (!c->p2p || !c->can_solve) { set_error("triangular solves on a sharded field need the peer-to-peer transport (nngp_shard_p2p_connect / nngp_shard_connect_local) and the whole field's DAG levels (global_level of nngp_ctx_create_sharded)"); throw StateFail(); }
+        const unsigned long long e = c->solve_epoch++;
+        unsigned long long *xs = reinterpret_cast<unsigned long long *>(c->p2p_area + c->p2p_x_off + (size_t)(e & 1ull) * c->p2p_x_stride);
+        unsigned long long *xs_next = reinterpret_cast<unsigned long long *>(c->p2p_area + c->p2p_x_off + (size_t)((e + 1ull) & 1ull) * c->p2p_x_stride);
+        CK(cudaMemsetAsync(c->d_ticket.p, 0, sizeof(int), c->stream));
+        fill_u64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(xs_next, NNGP_SOLVE_SENTINEL, c->n);
+        LAUNCHED(c);
+        ShardSolve ss{};
+        ss.peers = c->peers;
+        ss.sxptr = c->d_sxptr.p;
+        ss.sxdst = c->d_sxdst.p;
+        for (int h = 0; h < c->world; h++) ss.x_off[h] = c->peer_x_off[h] + (unsigned int)(e & 1ull) * c->peer_x_stride[h];
+        if (c->n_slots > 0) {
+            const int want = c->solve_window_ctas > 0 ? c->solve_window_ctas : c->n_sm * c->solve_ctas_per_sm;
+            const int blocks = std::max(1, std::min((c->n_slots + 255) / 256, want));
+            DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT, true><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, xs, y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ss)));
+            LAUNCHED(c);
+        }
+        allreduce_scalars(c, 60, 1);   // barrier: every rank has finished this solve (and its stores into the peers' buffers)
+        shard_solve_ghosts_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(xs, c->d_owned.p, c->n, x, y, shift, scale);
+        LAUNCHED(c);
+        return;
+    }
     if (c->solve_variant == 0) {
         CK(cudaMemsetAsync(c->d_ticket.p, 0, sizeof(int), c->stream));
         fill_u64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(reinterpret_cast<unsigned long long *>(x), NNGP_SOLVE_SENTINEL, c->n);
         LAUNCHED(c);
         const int want = c->solve_window_ctas > 0 ? c->solve_window_ctas : c->n_sm * c->solve_ctas_per_sm;
         const int blocks = std::max(1, std::min((c->n_slots + 255) / 256, want));
-        DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns)));
+        DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ShardSolve{})));
         LAUNCHED(c);
         return;
     }
@@ -558,12 +598,15 @@ static int launch_sweep_colors(Ctx *c) {
 #define NNGP_T2_ARGS (const int4 *)(c->d_tiles.p + t0), t0, (const int *)c->d_colptr.p, (const int *)c->d_crow.p, (const unsigned char *)c->d_cloc.p, (const double *)c->d_valT.p, (const double *)c->d_pd.p, (const double *)c->d_nobs.p, (const double *)c->d_S.p, (const int *)c->d_zpos.p, (const int *)c->d_gid.p, (const int *)c->d_psite.p, (const double *)c->d_zbuf.p, (const SweepParams *)c->d_sp.p, c->d_field.p, c->d_r.p, sc, cl
         // a colour with slightly more tiles than 5 CTAs/SM can hold (a 6 % tail wave that costs a whole extra gather -> sum ->
         // scatter round) runs the 6-CTAs/SM build (80 registers) so that all its tiles are co-resident
-        const bool six = c->sweep_variant == 0 && nt > 5 * c->n_sm && nt <= 6 * c->n_sm;
+        const bool six = (c->sweep_variant == 0 || c->sweep_variant == 4) && nt > 5 * c->n_sm && nt <= 6 * c->n_sm;
         if (fused_halo) {
             if (six) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2, true>, NNGP_T2_ARGS));
             else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2, true>, NNGP_T2_ARGS));
         } else if (!pdl) {
             CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, false, 5, 2>, NNGP_T2_ARGS));
+        } else if (c->sweep_variant == 4) {   // as 0, dependents triggered after the wait (see LATE in kernels.cuh)
+            if (six) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2, false, true>, NNGP_T2_ARGS));
+            else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2, false, true>, NNGP_T2_ARGS));
         } else {
             if (six) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2>, NNGP_T2_ARGS));
             else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2>, NNGP_T2_ARGS));
@@ -808,7 +851,7 @@ static void destroy_ctx(Ctx *c) {
     for (int h = 0; h < 8; h++) if (c->peer_mapped[h]) cudaIpcCloseMemHandle(c->peer_mapped[h]);
     c->d_recvbuf.p = nullptr;
     if (c->p2p_area) cudaFree(c->p2p_area);
-    c->d_shard_state.release(); c->d_bptr.release(); c->d_bdst.release();
+    c->d_shard_state.release(); c->d_bptr.release(); c->d_bdst.release(); c->d_sxptr.release(); c->d_sxdst.release();
     c->d_send_storage.release(); c->d_recv_proc.release(); c->d_sendbuf.release(); c->d_owned.release();
     DevBuf<int> *ib[] = {&c->d_psite, &c->d_gid, &c->d_i2g, &c->d_g2i, &c->d_nn, &c->d_colptr, &c->d_crow, &c->d_csrc, &c->d_zpos, &c->d_lvl_rows, &c->d_lvl_ptr,
                          &c->d_lm, &c->d_optr, &c->d_oidx, &c->d_cstart, &c->d_partial_rows, &c->d_nbad};
@@ -897,7 +940,7 @@ void nngp_device_count(int *count, int *status) {
 }
 
 struct ShardArgs {
-    const int *owned, *global_id, *global_zpos, *send_site, *send_ptr, *recv_site, *recv_ptr;
+    const int *owned, *global_id, *global_zpos, *global_level, *send_site, *send_ptr, *recv_site, *recv_ptr;
     int n_colors, world, rank;
     long long n_global;
     const char *comm_id;
@@ -1091,15 +1134,27 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     }
     phase("transpose structure");
     // ---- solve DAG levels ----
+    // A sharded field solves its OWNED rows only, and every rank must walk them in the order of the WHOLE field's levels: with
+    // local levels (ghost sites' rows are cut) a rank could schedule a row before an owned row it transitively depends on through
+    // a peer, and the bounded window of the sync-free solve would deadlock.  Without global levels the solves are unavailable.
     std::vector<int> level;
-    c->n_levels = solve_levels(NNarray, n, m, level);
+    const bool shard_levels = sh && sh->global_level;
+    c->can_solve = !sh || shard_levels;
+    if (shard_levels) {
+        level.assign(sh->global_level, sh->global_level + n);
+        c->n_levels = 0;
+        for (int i = 0; i < n; i++) { REQUIRE(level[i] >= 0, "global_level[%d] < 0", i); if (sh->owned[i]) c->n_levels = std::max(c->n_levels, level[i] + 1); }
+    } else {
+        c->n_levels = solve_levels(NNarray, n, m, level);
+    }
+    auto solved_here = [&](int ref) { return !shard_levels || sh->owned[ref]; };
     c->lvl_ptr.assign(c->n_levels + 1, 0);
-    for (int i = 0; i < n; i++) c->lvl_ptr[level[i] + 1]++;
+    for (int i = 0; i < n; i++) if (solved_here(i)) c->lvl_ptr[level[i] + 1]++;
     for (int l = 0; l < c->n_levels; l++) c->lvl_ptr[l + 1] += c->lvl_ptr[l];
-    std::vector<int> lvl_rows(n);
+    std::vector<int> lvl_rows(c->lvl_ptr[c->n_levels]);
     {
         std::vector<int> pos(c->lvl_ptr.begin(), c->lvl_ptr.end() - 1);
-        for (int q = 0; q < n; q++) lvl_rows[pos[level[c->i2g[q]]]++] = q;  // internal ids ascending inside a level
+        for (int q = 0; q < n; q++) if (solved_here(c->i2g[q])) lvl_rows[pos[level[c->i2g[q]]]++] = q;  // internal ids ascending inside a level
     }
     // plan: runs of narrow levels -> one single-CTA launch; wide levels -> one launch each
     for (int l = 0; l < c->n_levels;) {
@@ -1205,6 +1260,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
             send_storage[k] = c->g2i[ref];
             c->send_proc[k] = pof[send_storage[k]];
         }
+        c->send_storage_h = send_storage;
         for (size_t k = 0; k < recv_proc.size(); k++) {
             const int ref = sh->recv_site[k] - 1;
             REQUIRE(ref >= 0 && ref < n && !sh->owned[ref], "recv_site[%d] is not a ghost site", (int)k + 1);
@@ -1222,14 +1278,25 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         // even sweeps | receive values of odd sweeps] (two parities: a peer one sweep ahead never overwrites unread values)
         const size_t nrecv = (std::max<size_t>(recv_proc.size(), 1) + 15) / 16 * 16;
         c->p2p_parity_stride = nrecv;
-        c->p2p_doubles = std::max<size_t>(c->p2p_val_off + 2 * nrecv, (size_t)1 << 18);   // >= 2 MB: a whole allocation of its own
+        // ... | 2 solution buffers of the sharded triangular solve (n local sites each) | storage id of every ghost site (int32) ]
+        c->p2p_x_off = c->p2p_val_off + 2 * nrecv;
+        c->p2p_x_stride = ((size_t)n + 15) / 16 * 16;
+        c->p2p_tab_off = c->p2p_x_off + 2 * c->p2p_x_stride;
+        c->p2p_doubles = std::max<size_t>(c->p2p_tab_off + (recv_proc.size() + 1) / 2 + 16, (size_t)1 << 18);   // >= 2 MB: a whole allocation of its own
         CK(cudaMalloc(&c->p2p_area, c->p2p_doubles * sizeof(double)));
         CK(cudaMemsetAsync(c->p2p_area, 0, c->p2p_doubles * sizeof(double), s));
         {   // header: what a peer must know about this rank's area (read by the peers when they connect)
             unsigned long long *hdr = reinterpret_cast<unsigned long long *>(c->h_pinned + 40);
             hdr[0] = (unsigned long long)nrecv;
             hdr[1] = (unsigned long long)recv_proc.size();
-            CK(cudaMemcpyAsync(c->p2p_area + c->p2p_hdr_off, hdr, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+            hdr[2] = (unsigned long long)c->p2p_x_off;
+            hdr[3] = (unsigned long long)c->p2p_x_stride;
+            hdr[4] = (unsigned long long)c->p2p_tab_off;
+            CK(cudaMemcpyAsync(c->p2p_area + c->p2p_hdr_off, hdr, 5 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+            c->recv_storage.resize(recv_proc.size());
+            for (size_t k = 0; k < recv_proc.size(); k++) c->recv_storage[k] = psite[recv_proc[k]];
+            if (!c->recv_storage.empty())
+                CK(cudaMemcpyAsync(c->p2p_area + c->p2p_tab_off, c->recv_storage.data(), c->recv_storage.size() * sizeof(int), cudaMemcpyHostToDevice, s));
         }
         c->d_recvbuf.p = c->p2p_area + c->p2p_val_off;      // not owned by the DevBuf (released with the area)
         c->d_recvbuf.n = 0;
@@ -1275,12 +1342,13 @@ void nngp_comm_unique_id(char *id128, int *status) {
 }
 
 void nngp_ctx_create_sharded(const int *n_, const int *d_, const int *m_, const double *locs, const int *NNarray, const int *coloring,
-                             const int *n_colors, const int *owned, const int *global_id, const int *global_zpos, const double *n_global,
+                             const int *n_colors, const int *owned, const int *global_id, const int *global_zpos, const int *global_level,
+                             const double *n_global,
                              const int *n_obs_, const int *locs_match, const int *covfun_id, const int *device, const int *layout,
                              const int *world, const int *rank, const int *send_site, const int *send_ptr, const int *recv_site,
                              const int *recv_ptr, const char *comm_id128, int *ctx_id, int *status) {
     if (!n_colors || !world || !rank || !n_global) { set_error("nngp_ctx_create_sharded: null argument"); if (status) *status = NNGP_ERR_ARG; return; }
-    ShardArgs sh{owned, global_id, global_zpos, send_site, send_ptr, recv_site, recv_ptr, *n_colors, *world, *rank, (long long)*n_global, comm_id128};
+    ShardArgs sh{owned, global_id, global_zpos, global_level, send_site, send_ptr, recv_site, recv_ptr, *n_colors, *world, *rank, (long long)*n_global, comm_id128};
     create_ctx_impl(n_, d_, m_, locs, NNarray, coloring, n_obs_, locs_match, covfun_id, device, layout, &sh, ctx_id, status);
 }
 
@@ -1299,7 +1367,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
     use(c);
     CK(cudaStreamSynchronize(c->stream));
     switch (*key) {
-        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 3, "sweep variant must be 0..3"); c->sweep_variant = *value; break;
+        case NNGP_OPT_SWEEP_VARIANT: REQUIRE(*value >= 0 && *value <= 4, "sweep variant must be 0..4"); c->sweep_variant = *value; break;
         case NNGP_OPT_SOLVE_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "solve variant must be 0..1"); c->solve_variant = *value; break;
         case NNGP_OPT_USE_GRAPH: c->use_graph = (*value != 0); break;
         case NNGP_OPT_SOLVE_CTAS_PER_SM: REQUIRE(*value >= 1 && *value <= 8, "solve CTAs per SM must be 1..8"); c->solve_ctas_per_sm = *value; break;
@@ -1482,7 +1550,6 @@ void nngp_sptmv(const int *ctx_id, const int *slot, const double *u, double *out
 void nngp_sptrsv(const int *ctx_id, const int *slot, const double *b, double *x, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
-    NEED(!c->sharded, "nngp_sptrsv: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
     REQUIRE(slot && b && x && (*slot == 0 || *slot == 1), "nngp_sptrsv: bad argument");
     NEED(c->have_slot(*slot), "nngp_sptrsv: that slot holds no factor");
     use(c);
@@ -1535,11 +1602,37 @@ void nngp_shard_p2p_export(const int *ctx_id, char *handle64, int *status) {
 // after the peers' areas are known: destinations of every boundary site's value (peer, slot inside the peer's receive values)
 static void finish_p2p_connect(Ctx *c, const int *peer_recv_base) {
     const int W = c->world, K = c->K;
-    for (int h = 0; h < W; h++) {   // every peer's parity stride, from the header of its (mapped) area
-        unsigned long long hdr[2] = {0, 0};
+    std::vector<std::vector<int>> peer_tab(W);   // storage id, on peer h, of every ghost site of peer h (its receive order)
+    for (int h = 0; h < W; h++) {   // what every peer's (mapped) area says about itself
+        unsigned long long hdr[5] = {0, 0, 0, 0, 0};
         CK(cudaMemcpy(hdr, c->peers.area[h] + c->p2p_hdr_off, sizeof(hdr), cudaMemcpyDeviceToHost));
-        REQUIRE(hdr[0] >= 16 && hdr[0] < (1ull << 31), "peer %d: implausible area header (was its context created?)", h);
+        REQUIRE(hdr[0] >= 16 && hdr[0] < (1ull << 31) && hdr[2] < (1ull << 32) && hdr[3] < (1ull << 32), "peer %d: implausible area header (was its context created?)", h);
         c->peer_stride[h] = (unsigned int)hdr[0];
+        c->peer_x_off[h] = (unsigned int)hdr[2];
+        c->peer_x_stride[h] = (unsigned int)hdr[3];
+        peer_tab[h].resize((size_t)hdr[1]);
+        if (h != c->rank && hdr[1] > 0) CK(cudaMemcpy(peer_tab[h].data(), c->peers.area[h] + hdr[4], (size_t)hdr[1] * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    {   // sharded solve: an owned boundary site's solution value goes to x[storage id on the peer] of every peer that ghosts it
+        std::vector<int> sxptr((size_t)c->n + 1, 0);
+        for (size_t k = 0; k < c->send_proc.size(); k++) sxptr[(size_t)c->send_storage_h[k] + 1]++;
+        for (int q = 0; q < c->n; q++) sxptr[q + 1] += sxptr[q];
+        std::vector<int2> sxdst(std::max<size_t>(c->send_proc.size(), 1));
+        std::vector<int> pos(sxptr.begin(), sxptr.end() - 1);
+        for (int col = 0; col < K; col++)
+            for (int h = 0; h < W; h++) {
+                const int a = c->send_ptr[(size_t)col * W + h], b = c->send_ptr[(size_t)col * W + h + 1];
+                for (int k = a; k < b; k++) {
+                    const size_t slot = (size_t)peer_recv_base[(size_t)col * W + h] + (size_t)(k - a);
+                    REQUIRE(slot < peer_tab[h].size(), "halo lists of rank %d and rank %d do not match", c->rank, h);
+                    sxdst[pos[c->send_storage_h[k]]++] = make_int2(h, peer_tab[h][slot]);
+                }
+            }
+        c->d_sxptr.upload(sxptr, c->stream);
+        c->d_sxdst.upload(sxdst, c->stream);
+        // both solution buffers start "pending"; buffer e & 1 serves solve e and is re-armed at the start of solve e - 1
+        fill_u64_kernel<<<grid_for(c, (long long)(2 * c->p2p_x_stride), 256), 256, 0, c->stream>>>(reinterpret_cast<unsigned long long *>(c->p2p_area + c->p2p_x_off), NNGP_SOLVE_SENTINEL, (int)(2 * c->p2p_x_stride));
+        c->solve_epoch = 0;
     }
     std::vector<int> bptr((size_t)c->n_owned + 1, 0);
     for (size_t k = 0; k < c->send_proc.size(); k++) bptr[(size_t)c->send_proc[k] + 1]++;
@@ -1768,7 +1861,6 @@ void nngp_ancillary_propose(const int *ctx_id, const double *beta_0, const doubl
                             const double *log_noise_variance, double *field_response_ratio, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
-    NEED(!c->sharded, "nngp_ancillary_propose: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
     REQUIRE(beta_0 && delta_log_scale && log_noise_variance && field_response_ratio, "nngp_ancillary_propose: bad argument");
     NEED(c->have_slot(NNGP_SLOT_CURRENT) && c->have_slot(NNGP_SLOT_PROPOSAL), "nngp_ancillary_propose: needs current and proposal factors");
     NEED(c->have_field && c->have_obs, "nngp_ancillary_propose: field and observations must be set first");
@@ -1828,7 +1920,6 @@ void nngp_ssr(const int *ctx_id, double *ssr, int *status) {
 void nngp_field_init(const int *ctx_id, const int *slot, const double *beta_0, const double *log_scale, const double *z, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
-    NEED(!c->sharded, "nngp_field_init: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
     REQUIRE(slot && beta_0 && log_scale && z && (*slot == 0 || *slot == 1), "nngp_field_init: bad argument");
     NEED(c->have_slot(*slot), "nngp_field_init: that slot holds no factor");
     use(c);
@@ -1890,7 +1981,7 @@ void nngp_predict_sample(const int *ctx_id, const int *slot, const int *n_obs_si
         const int want = c->solve_window_ctas > 0 ? c->solve_window_ctas : c->n_sm * c->solve_ctas_per_sm;
         const int blocks = std::max(1, std::min((c->pred_slots + 255) / 256, want));
         const double *linv = c->linv_slot(*slot);
-        DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_pred_rows.p, c->pred_slots, c->d_tmp1.p, reinterpret_cast<unsigned long long *>(c->d_tmp2.p), nullptr, 0.0, 1.0, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns)));
+        DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_pred_rows.p, c->pred_slots, c->d_tmp1.p, reinterpret_cast<unsigned long long *>(c->d_tmp2.p), nullptr, 0.0, 1.0, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ShardSolve{})));
         LAUNCHED(c);
     }
     CK(cudaGetLastError());
@@ -1927,8 +2018,25 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
         const size_t w = (size_t)std::max(P1, reg_q);
         gvec.resize(w); bmean.resize(w); zz.resize(w); innov.resize(w); coefl.resize(w);
     }
-    const int n = c->n, n_obs = c->n_obs;
+    const int n = c->n;
+    const long long nz = c->n_global;   // normals of a sweep are indexed by the position in the WHOLE field's hand-out order
     const bool matern = c->covfun >= NNGP_MATERN_ISOTROPIC;
+    // a sharded field: every rank runs this loop on its block with the same scalar state and the same R stream; all scalars
+    // that enter a decision are all-reduced (rank-ordered sums, identical everywhere), so the ranks stay in step
+    if (c->n_obs_global < 0) {
+        if (c->sharded && c->world > 1) {
+            c->h_pinned[16] = (double)c->n_obs;
+            CK(cudaMemcpyAsync(c->d_scalars.p + 16, c->h_pinned + 16, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            allreduce_scalars(c, 16, 1);
+            CK(cudaMemcpyAsync(c->h_pinned + 16, c->d_scalars.p + 16, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->n_obs_global = c->h_pinned[16];
+        } else {
+            c->n_obs_global = (double)c->n_obs;
+        }
+    }
+    const double n_obs = c->n_obs_global;
+    const int n_obs_local = c->n_obs;
     double beta_0 = params_io[0], log_scale = params_io[1], lnv = params_io[2], logvar_suf = params_io[3], logvar_anc = params_io[4];
     double shape[5], new_shape[5], cp[8], innovation[6];
     for (int k = 0; k < ns; k++) shape[k] = params_io[5 + k];
@@ -1940,9 +2048,17 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
     };
     auto n_bad = [&]() {   // rows whose block was not positive definite; also surfaces a solve / halo wait that timed out
         int bad[2];
+        const bool reduce = c->sharded && c->world > 1;
+        if (reduce) {   // the accept / reject decision must be the same on every rank: sum the counts over the ranks
+            int_to_f64_kernel<<<1, 32, 0, c->stream>>>(c->d_nbad.p, c->d_scalars.p + 17);
+            LAUNCHED(c);
+            allreduce_scalars(c, 17, 1);
+            CK(cudaMemcpyAsync(c->h_pinned + 17, c->d_scalars.p + 17, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        }
         CK(cudaMemcpyAsync(c->h_pinned + 8, c->d_nbad.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         std::memcpy(bad, c->h_pinned + 8, 2 * sizeof(int));
+        if (reduce) bad[0] = (int)std::min(2.0e9, c->h_pinned[17]);
         if (bad[1] == 2) { set_error("sharded field: timed out waiting for a peer's halo / reduction flag (a rank died or fell out of step)"); throw NcclFail(); }
         if (bad[1]) { set_error("triangular solve: dependency wait timed out (corrupted neighbour structure?)"); throw CudaFail(); }
         return bad[0];
@@ -1955,7 +2071,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
     // :75 current_p = rnorm(n_locs) is dead code in the reference but consumes n draws of R's stream.  In NNGP_RNG_SUPPLIED mode
     // (bit-comparable with R) they are consumed too; in Philox mode the field draws differ from R's anyway, so the 15-20 ms of
     // host RNG per call (n = 1M) are skipped and the scalar draws simply continue from the seeded state.
-    if (rng_mode == NNGP_RNG_SUPPLIED) { zhost.resize(n); rs.rnorm(zhost.data(), n); }
+    if (rng_mode == NNGP_RNG_SUPPLIED) { zhost.resize((size_t)nz); rs.rnorm(zhost.data(), nz); }
     std::vector<int> acc_anc(n_iter + 1, 0), acc_suf(n_iter + 1, 0);
     if (reg_q > 0) op_interweave(c, iw_cov, iw_chol);                            // :77-83
     if (reg) op_set_beta(c, beta.data());                                        // :85
@@ -2056,9 +2172,9 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
         // ---- (C') regression coefficients :226-250 ----
         if (reg) {
             // :229 beta_mean = crossprod(observed_field - field[locs_match] + beta_0, cbind(1, X$X)) %*% X$solve_1XT1X
-            obs_resid_kernel<<<grid_for(c, n_obs, 256), 256, 0, c->stream>>>(c->d_lm.p, c->d_yobs.p, c->d_field.p, beta_0, n_obs, c->d_robs.p);
+            obs_resid_kernel<<<grid_for(c, n_obs_local, 256), 256, 0, c->stream>>>(c->d_lm.p, c->d_yobs.p, c->d_field.p, beta_0, n_obs_local, c->d_robs.p);
             LAUNCHED(c);
-            op_atb(c, c->d_Xa.p, P1, c->d_robs.p, 1, n_obs, gvec.data());
+            op_atb(c, c->d_Xa.p, P1, c->d_robs.p, 1, n_obs_local, gvec.data());
             for (int j = 0; j < P1; j++) {
                 double v = 0.0;
                 for (int k = 0; k < P1; k++) v += gvec[k] * reg->solve_1XT1X[(size_t)k + (size_t)P1 * j];
@@ -2107,10 +2223,10 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
         mark(2);
         // ---- (D) chromatic sweeps :257-275 ----
         if (rng_mode == NNGP_RNG_SUPPLIED) {
-            ensure_zbuf(c, (size_t)n * std::max(1, n_chromatic));
-            zhost.resize((size_t)n * std::max(1, n_chromatic));
-            rs.rnorm(zhost.data(), (int64_t)n * n_chromatic);
-            CK(cudaMemcpyAsync(c->d_zbuf.p, zhost.data(), sizeof(double) * (size_t)n * n_chromatic, cudaMemcpyHostToDevice, c->stream));
+            ensure_zbuf(c, (size_t)nz * std::max(1, n_chromatic));
+            zhost.resize((size_t)nz * std::max(1, n_chromatic));
+            rs.rnorm(zhost.data(), (int64_t)nz * n_chromatic);
+            CK(cudaMemcpyAsync(c->d_zbuf.p, zhost.data(), sizeof(double) * (size_t)nz * n_chromatic, cudaMemcpyHostToDevice, c->stream));
         }
         set_sweep_params(c, beta_0, log_scale, lnv, rng_mode, (double)philox_seed);
         refresh_r(c, beta_0);
@@ -2174,7 +2290,6 @@ void nngp_chain_run(const int *ctx_id, const int *n_shape_, double *params_io, c
                     const double *var_y_, double *records_out, double *field_records_out, int *accept_out, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
-    NEED(!c->sharded, "nngp_chain_run: not available on a sharded context (sweep, log-lik, factor build and the scalar reductions are)");
     REQUIRE(n_shape_ && params_io && n_iter_ && thin_ && n_chromatic_ && iter_start_ && chain_index_ && rng_mode_ && var_y_, "nngp_chain_run: null argument");
     NEED(c->have_field && c->have_obs, "nngp_chain_run: field and observations must be set first");
     chain_run_impl(c, n_shape_, params_io, n_iter_, thin_, n_chromatic_, iter_start_, chain_index_, rng_mode_, var_y_, records_out,
@@ -2355,6 +2470,63 @@ void nngp_chains_run_regressors(const int *n_chains, const int *ctx_ids, const i
                                 double *field_records_out, int *accept_out, int *status) {
     chains_run_common(n_chains, ctx_ids, n_shape, params_io, beta_io, solve_1XT1X, chol_solve_1XT1X, n_iter, thin, n_chromatic, iter_start,
                       chain_index, rng_mode, var_y, max_concurrent, records_out, beta_records_out, field_records_out, accept_out, true, status);
+}
+
+// One chain on a field sharded over the GPUs of THIS process (nngp_shard_connect_local): every member runs the reference loop on its
+// block, on its own host thread, with the same scalar state and the same R stream; the scalars that enter a decision are all-reduced
+// between the members, so they stay in step.  params_io: one parameter vector (in / out, identical on every member);
+// records_out / accept_out: the scalar records (identical on every member; member 0's are returned); field_records_out: member h's
+// block after member h - 1's, each round(n_iter * thin) x n_local(h), or NULL.
+void nngp_shard_group_chain_run(const int *ctx_ids, const int *world, const int *n_shape, double *params_io, const int *n_iter,
+                                const double *thin, const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode,
+                                const double *var_y, double *records_out, double *field_records_out, int *accept_out, int *status) {
+    ABI_BEGIN
+    REQUIRE(ctx_ids && world && n_shape && params_io && n_iter && thin && n_chromatic && iter_start && chain_index && rng_mode && var_y && *world >= 1 && *world <= 8,
+            "nngp_shard_group_chain_run: bad argument");
+    const int W = *world, ns = *n_shape, ni = *n_iter;
+    REQUIRE(ns >= 1 && ns <= 5 && ni >= 0, "nngp_shard_group_chain_run: bad sizes");
+    const long long n_frec = (long long)std::nearbyint(ni * *thin);
+    std::vector<ChainJob> jobs(W);
+    std::vector<std::vector<double>> p(W), rec(W);
+    std::vector<std::vector<int>> acc(W);
+    size_t foff = 0;
+    for (int h = 0; h < W; h++) {
+        Ctx *c = get_ctx(ctx_ids + h);
+        NEED(c->sharded && c->world == W && c->rank == h && (c->p2p || W == 1), "nngp_shard_group_chain_run: context h must be rank h of a locally connected W-rank field");
+        NEED(c->have_field && c->have_obs, "nngp_shard_group_chain_run: field and observations must be set first on every member");
+        p[h].assign(params_io, params_io + 5 + ns);
+        rec[h].assign((size_t)ni * (3 + ns), 0.0);
+        acc[h].assign((size_t)2 * ni, 0);
+        ChainJob &j = jobs[h];
+        j.c = c;
+        j.params = p[h].data();
+        j.beta = nullptr; j.beta_records = nullptr;
+        j.records = rec[h].data();
+        j.field_records = field_records_out ? field_records_out + foff : nullptr;
+        foff += (size_t)n_frec * c->n;
+        j.accept = acc[h].data();
+        j.chain_index = *chain_index;
+        j.status = NNGP_OK;
+    }
+    run_chain_jobs(jobs, W, n_shape, n_iter, thin, n_chromatic, iter_start, rng_mode, var_y, nullptr, nullptr);   // all members at once
+    for (int h = 0; h < W; h++)
+        if (jobs[h].status != NNGP_OK) {
+            set_error("member %d: %s", h, jobs[h].error.c_str());
+            switch (jobs[h].status) {
+                case NNGP_ERR_CUDA: throw CudaFail();
+                case NNGP_ERR_STATE: throw StateFail();
+                case NNGP_ERR_NCCL: throw NcclFail();
+                case NNGP_ERR_ALLOC: throw std::bad_alloc();
+                default: throw ArgFail();
+            }
+        }
+    for (int h = 1; h < W; h++) {
+        REQUIRE(p[h] == p[0] && rec[h] == rec[0] && acc[h] == acc[0], "nngp_shard_group_chain_run: member %d fell out of step with member 0 (their scalar records differ)", h);
+    }
+    std::memcpy(params_io, p[0].data(), sizeof(double) * (5 + ns));
+    if (records_out) std::memcpy(records_out, rec[0].data(), sizeof(double) * rec[0].size());
+    if (accept_out) std::memcpy(accept_out, acc[0].data(), sizeof(int) * acc[0].size());
+    ABI_END
 }
 
 void nngp_records_summary(const int *ctx_id, const int *first_row, const int *n_rows, const double *offsets, double *out, int *status) {

@@ -53,10 +53,10 @@ def shard_plan(locs, NNarray, coloring, locs_match, owner, rank, n_parts):
     out_locs = np.zeros(nl * d)
     NN_loc = np.zeros(nl * M, dtype=np.int32)
     ints = {k: np.zeros(max(sz, 1), dtype=np.int32) for k, sz in
-            dict(coloring=nl, owned=nl, global_id=nl, global_zpos=nl, obs_index=nol, locs_match=nol, send_site=ns, recv_site=nr,
+            dict(coloring=nl, owned=nl, global_id=nl, global_zpos=nl, global_level=nl, obs_index=nol, locs_match=nol, send_site=ns, recv_site=nr,
                  send_ptr=K * n_parts + 1, recv_ptr=K * n_parts + 1).items()}
     lib.nngp_host_shard_plan_get(C.byref(pid), L.dptr(out_locs), L.iptr(NN_loc), L.iptr(ints["coloring"]), L.iptr(ints["owned"]),
-                                 L.iptr(ints["global_id"]), L.iptr(ints["global_zpos"]), L.iptr(ints["obs_index"]), L.iptr(ints["locs_match"]),
+                                 L.iptr(ints["global_id"]), L.iptr(ints["global_zpos"]), L.iptr(ints["global_level"]), L.iptr(ints["obs_index"]), L.iptr(ints["locs_match"]),
                                  L.iptr(ints["send_site"]), L.iptr(ints["send_ptr"]), L.iptr(ints["recv_site"]), L.iptr(ints["recv_ptr"]),
                                  C.byref(st))
     L.check(st)
@@ -64,7 +64,7 @@ def shard_plan(locs, NNarray, coloring, locs_match, owner, rank, n_parts):
     return {
         "rank": rank, "world": n_parts, "n_global": n, "n_colors": K,
         "local_sites": gid.astype(np.int64), "locs": out_locs.reshape((nl, d), order="F"), "NNarray": NN_loc.reshape((nl, M), order="F"),
-        "coloring": ints["coloring"][:nl], "owned": ints["owned"][:nl], "global_id": gid, "global_zpos": ints["global_zpos"][:nl],
+        "coloring": ints["coloring"][:nl], "owned": ints["owned"][:nl], "global_id": gid, "global_zpos": ints["global_zpos"][:nl], "global_level": ints["global_level"][:nl],
         "obs_index": ints["obs_index"][:nol].astype(np.int64), "locs_match": ints["locs_match"][:nol],
         "send_site": ints["send_site"][:ns], "send_ptr": ints["send_ptr"], "recv_site": ints["recv_site"][:nr], "recv_ptr": ints["recv_ptr"],
         "n_owned": n_owned, "n_ghost": nl - n_owned, "n_rows_needed": None,

@@ -40,7 +40,8 @@ class ShardedContext(NNGPContext):
         lib.nngp_ctx_create_sharded(
             L.ci(self.n), L.ci(self.d), L.ci(self.m), L.dptr(L.f64(locs)), L.iptr(L.i32(plan["NNarray"])),
             L.iptr(L.i32(plan["coloring"])), L.ci(plan["n_colors"]), L.iptr(L.i32(plan["owned"])), L.iptr(L.i32(plan["global_id"])),
-            L.iptr(L.i32(plan["global_zpos"])), L.cd(plan["n_global"]), L.ci(self.n_obs), L.iptr(lm), L.ci(L.COVFUN_IDS[covfun_name]),
+            L.iptr(L.i32(plan["global_zpos"])), L.iptr(L.i32(plan["global_level"])) if plan.get("global_level") is not None else None,
+            L.cd(plan["n_global"]), L.ci(self.n_obs), L.iptr(lm), L.ci(L.COVFUN_IDS[covfun_name]),
             L.ci(device), L.ci(layout), L.ci(self.world), L.ci(self.rank), L.iptr(L.i32(plan["send_site"])), L.iptr(L.i32(plan["send_ptr"])),
             L.iptr(L.i32(plan["recv_site"])), L.iptr(L.i32(plan["recv_ptr"])), idbuf, C.byref(cid), C.byref(st))
         L.check(st)
@@ -161,6 +162,36 @@ def group_loglik(contexts, beta_0, log_scale, slot=L.SLOT_CURRENT) -> np.ndarray
     L.load().nngp_shard_group_loglik(ids, L.ci(len(contexts)), L.ci(slot), L.cd(beta_0), L.cd(log_scale), L.dptr(out), C.byref(st))
     L.check(st)
     return out
+
+
+def group_chain_run(contexts, params: dict, n_iter, var_y, thin=1.0, n_chromatic=10, iter_start=0, chain_index=1, rng_mode=L.RNG_PHILOX,
+                    keep_field=True):
+    """nngp_shard_group_chain_run: one chain on a locally connected sharded field.  Returns (params, records, [field records per
+    member], accepts) laid out like NNGPContext.chain_run."""
+    W = len(contexts)
+    shape = np.atleast_1d(np.asarray(params["shape"], dtype=np.float64))
+    p = np.ascontiguousarray(np.concatenate([[params["beta_0"], params["log_scale"], params["log_noise_variance"],
+                                              params.get("logvar_sufficient", -2.0), params.get("logvar_ancillary", -2.0)], shape]))
+    n_iter = int(n_iter)
+    n_frec = int(round(n_iter * thin))
+    rec = np.zeros(n_iter * (3 + shape.size))
+    sizes = [c.n for c in contexts]
+    frec = np.zeros(max(n_frec * sum(sizes), 1)) if keep_field else None
+    acc = np.zeros(2 * n_iter, dtype=np.int32)
+    ids = (C.c_int * W)(*[c._id for c in contexts])
+    st = C.c_int(0)
+    L.load().nngp_shard_group_chain_run(ids, L.ci(W), L.ci(shape.size), L.dptr(p), L.ci(n_iter), L.cd(thin), L.ci(n_chromatic), L.ci(iter_start),
+                                        L.ci(chain_index), L.ci(rng_mode), L.cd(var_y), L.dptr(rec), L.dptr(frec) if keep_field else None,
+                                        L.iptr(acc), C.byref(st))
+    L.check(st)
+    out = dict(beta_0=p[0], log_scale=p[1], log_noise_variance=p[2], logvar_sufficient=p[3], logvar_ancillary=p[4], shape=p[5:].copy())
+    frecs = None
+    if keep_field:
+        frecs, off = [], 0
+        for nl in sizes:
+            frecs.append(frec[off: off + n_frec * nl].reshape((n_frec, nl), order="F"))
+            off += n_frec * nl
+    return out, rec.reshape((n_iter, 3 + shape.size), order="F"), frecs, acc.reshape((n_iter, 2), order="F")
 
 
 def create_sharded_distributed(locs, NNarray, coloring, locs_match, covfun_name, device, dist, transport="p2p"):

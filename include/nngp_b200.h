@@ -106,16 +106,21 @@ void nngp_ctx_destroy(const int *ctx_id, int *status);
  *   owned[n]        1 = this rank updates the site, 0 = ghost copy kept current by the halo exchange
  *   global_id[n]    0-based id of the site in the whole field (Philox key, so that results do not depend on the sharding)
  *   global_zpos[n]  position of the site in the whole field's rnorm() hand-out order (NNGP_RNG_SUPPLIED mode)
+ *   global_level[n] depth of the site's row in the WHOLE field's solve DAG (0 = no parents); every rank orders its owned rows
+ *                   by it in the sharded triangular solve.  NULL = not given: the solve-based entry points are then unavailable
  *   send_site / send_ptr   owned boundary sites per (colour, peer): segment [send_ptr[c*world+h], send_ptr[c*world+h+1])
  *   recv_site / recv_ptr   ghost sites per (colour, peer), in the same order as the owner sends them
  * On such a context nngp_gibbs_sweep exchanges the boundary values of every colour (peer-to-peer transport below: fused into
  * the sweep kernel; NCCL: ncclSend/ncclRecv after it) and nngp_loglik / nngp_ssr / nngp_beta0_moments all-reduce their partial
  * sums; observations are those of the owned sites.  Limits: at most 8 ranks per field.
- * Triangular solves (ancillary step, initial draw, prediction) are not available on a sharded context. */
+ * With the peer-to-peer transport nngp_sptrsv / nngp_field_init / nngp_ancillary_propose and nngp_chain_run (no-regressor model) work
+ * on the block too: every rank solves its owned rows with the synchronisation-free kernel and stores boundary values straight into
+ * the peers' solution vectors; every rank runs the chain loop with the same scalar state (all decisions are taken on all-reduced
+ * scalars).  Vectors are the rank's LOCAL vectors (owned + ghost sites); var_y is the whole field's.  Prediction is not sharded. */
 void nngp_comm_unique_id(char *id128, int *status);
 void nngp_ctx_create_sharded(const int *n, const int *d, const int *m, const double *locs, const int *NNarray,
                              const int *coloring, const int *n_colors, const int *owned, const int *global_id,
-                             const int *global_zpos, const double *n_global, const int *n_obs, const int *locs_match,
+                             const int *global_zpos, const int *global_level, const double *n_global, const int *n_obs, const int *locs_match,
                              const int *covfun_id, const int *device, const int *layout, const int *world, const int *rank,
                              const int *send_site, const int *send_ptr, const int *recv_site, const int *recv_ptr,
                              const char *comm_id128, int *ctx_id, int *status);
@@ -150,25 +155,34 @@ void nngp_shard_group_sweep(const int *ctx_ids, const int *world, const int *n_s
  * all equal */
 void nngp_shard_group_loglik(const int *ctx_ids, const int *world, const int *slot, const double *beta_0, const double *log_scale,
                              double *ll, int *status);
+/* one chain (reference loop, no-regressor model) on a locally connected field: every member runs the loop on its block on its own
+ * host thread with the same scalar state; params_io is the one parameter vector (as nngp_chain_run); records_out / accept_out are the
+ * scalar records (identical on every member); field_records_out holds member h's round(n_iter * thin) x n_local(h) block after member
+ * h - 1's, or is NULL */
+void nngp_shard_group_chain_run(const int *ctx_ids, const int *world, const int *n_shape, double *params_io, const int *n_iter,
+                                const double *thin, const int *n_chromatic, const int *iter_start, const int *chain_index, const int *rng_mode,
+                                const double *var_y, double *records_out, double *field_records_out, int *accept_out, int *status);
 /* host-side set-up of a sharded field (replaces nothing in the reference, which has no multi-GPU path):
  * owner[n] = spatial block (0..n_parts-1) of every site by recursive coordinate bisection into equal counts */
 void nngp_host_spatial_blocks(const double *locs, const int *n, const int *d, const int *n_parts, int *owner, int *status);
 /* everything rank `rank` needs for nngp_ctx_create_sharded, derived from the whole field's structure in O(n (m+1)):
  * build returns a plan id and sizes6 = [n_local, n_obs_local, n_send, n_recv, n_colors, n_owned]; get copies the arrays into
- * caller-allocated buffers (locs n_local x d; NNarray n_local x (m+1); coloring / owned / global_id / global_zpos n_local;
+ * caller-allocated buffers (locs n_local x d; NNarray n_local x (m+1); coloring / owned / global_id / global_zpos / global_level n_local;
  * obs_index (0-based index into the field's observations) / locs_match n_obs_local; send_site n_send; recv_site n_recv;
  * send_ptr / recv_ptr n_colors * world + 1) and frees the plan.  At most 8 ranks. */
 void nngp_host_shard_plan_build(const double *locs, const int *NNarray, const int *coloring, const int *n, const int *d, const int *m,
                                 const int *n_obs, const int *locs_match, const int *owner, const int *rank, const int *world,
                                 int *plan_id, int *sizes6, int *status);
 void nngp_host_shard_plan_get(const int *plan_id, double *locs, int *NNarray, int *coloring, int *owned, int *global_id, int *global_zpos,
-                              int *obs_index, int *locs_match, int *send_site, int *send_ptr, int *recv_site, int *recv_ptr, int *status);
+                              int *global_level, int *obs_index, int *locs_match, int *send_site, int *send_ptr, int *recv_site, int *recv_ptr, int *status);
 /* performance knobs (results are identical up to FP64 summation order):
  *   NNGP_OPT_SWEEP_VARIANT 0 = one launch per colour, tiles of <= 128 sites / 1024 factor entries per CTA, blocked segmented
  *                          reduction, chained with programmatic dependent launch (the r-independent prologue of colour c+1
  *                          overlaps colour c), replayed from a CUDA graph; colours that would spill into a second wave at
  *                          5 CTAs/SM run a 6-CTAs/SM build (default); 1 = the same chain with 5 CTAs/SM everywhere;
- *                          2 = the same tiles as plain launches; 3 = thread per site (unsharded contexts)
+ *                          2 = the same tiles as plain launches; 3 = thread per site (unsharded contexts); 4 = as 0, but a colour
+ *                          triggers its dependent launch only after its own wait (at most two colours resident per stream: for
+ *                          several chains sharing one GPU)
  *   NNGP_OPT_SOLVE_VARIANT 0 = synchronisation-free single-launch triangular solve; 1 = one launch per DAG level
  *   NNGP_OPT_USE_GRAPH     1 = the colour launches of a sweep are replayed from a captured CUDA graph (default) */
 #define NNGP_OPT_SWEEP_VARIANT 1

@@ -52,6 +52,18 @@ def _needed_masks(NNarray: np.ndarray, owner: np.ndarray, n_parts: int):
     return rows_needed, site_local
 
 
+def _levels(NNarray):
+    """depth of every row in the solve DAG: 0 without parents, else 1 + max over the parents"""
+    n = NNarray.shape[0]
+    lvl = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        par = NNarray[i, 1:]
+        par = par[par != NA_INT]
+        if par.size:
+            lvl[i] = lvl[par - 1].max() + 1
+    return lvl
+
+
 def shard_plan(locs, NNarray, coloring, locs_match, owner, rank, n_parts):
     """Everything rank `rank` needs to build its sharded context (indices 1-based / NA like the C ABI expects)."""
     locs = np.asarray(locs, dtype=np.float64)
@@ -101,6 +113,7 @@ def shard_plan(locs, NNarray, coloring, locs_match, owner, rank, n_parts):
         "rank": rank, "world": n_parts, "n_global": n, "n_colors": K,
         "local_sites": local_sites, "locs": locs[local_sites], "NNarray": NN_loc, "coloring": coloring[local_sites],
         "owned": owned.astype(np.int32), "global_id": local_sites.astype(np.int32), "global_zpos": zpos_g[local_sites].astype(np.int32),
+        "global_level": _levels(NNarray)[local_sites].astype(np.int32),
         "obs_index": obs_sel, "locs_match": lm_loc,
         "send_site": np.concatenate(send_site).astype(np.int32) if send_site else np.zeros(0, np.int32),
         "send_ptr": np.array(send_ptr, dtype=np.int32),

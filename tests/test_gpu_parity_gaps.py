@@ -60,17 +60,17 @@ def test_gpu_equals_oracle_at_baseline_sizes(n, m, covfun, cp, order):
             assert ctx.factor_build(cp) == 0
         del Lg
         ctx.factor_commit()
-        assert rel_vec(ctx.precision_diag(), pd_o) < TOL
+        assert rel_vec(ctx.precision_diag(), pd_o) < tol_rows          # everything below inherits the factor rows' bound
         ctx.field_set(P["field"])
         ctx.obs_set(P["y"])
         ll_o = O.ll_compressed_sparse_chol(Lo, P["field"] - beta_0, P["NNarray"], ls)
-        assert abs(ctx.loglik(beta_0, ls) - ll_o) < TOL * abs(ll_o)
+        assert abs(ctx.loglik(beta_0, ls) - ll_o) < tol_rows * abs(ll_o)
         v = P["rng"].standard_normal(n)
         u_o = O.Linv_mult(Lo, v, P["NNarray"])
-        assert rel_vec(ctx.spmv(v), u_o) < TOL
+        assert rel_vec(ctx.spmv(v), u_o) < tol_rows
         assert rel_vec(ctx.sptrsv(u_o), v) < 1e-8                      # solve(L^-1, L^-1 v) = v; conditioning of a depth-~200 recursion
         ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=1, z=z)
-        assert rel_vec(ctx.field_get(), f_o) < TOL
+        assert rel_vec(ctx.field_get(), f_o) < tol_rows
         mu = np.full(P["n_obs"], beta_0)
         assert abs(ctx.ssr() - O.ssr(P["locs_match"], P["y"], f_o, mu, beta_0)) < TOL * P["n_obs"]
 

@@ -26,6 +26,12 @@ def reference(P, n_sweeps, z=None, seed=3):
         return ctx.field_get(), ll, ctx.loglik(B0, LS), ctx.ssr(), ctx.precision_diag()
 
 
+def nb_solve_ref(P, b):
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.factor_build(CP)
+        return ctx.sptrsv(b)
+
+
 def shard_contexts(P, parts):
     owner = nb.spatial_blocks(P["locs"], parts)
     ctxs = []
@@ -117,6 +123,84 @@ def test_fused_peer_to_peer_sweep_on_one_gpu_equals_unsharded(parts, n):
             c.close()
 
 
+def run_concurrently(fns):
+    """the blocking entry points of the members of a locally connected field must be in flight together (they wait for each
+    other inside their kernels): one host thread per member (ctypes releases the GIL during the call)"""
+    import threading
+    out, err = [None] * len(fns), [None] * len(fns)
+
+    def work(k):
+        try:
+            out[k] = fns[k]()
+        except Exception as e:   # noqa: BLE001
+            err[k] = e
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(len(fns))]
+    for th in ts:
+        th.start()
+    for th in ts:
+        th.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+@pytest.mark.parametrize("parts", [2, 3, 4])
+def test_sharded_triangular_solve_ancillary_step_and_whole_chain(parts):
+    """Scripts/mcmc_nngp_update_Gaussian.R:127 (ancillary proposal = SpMV + triangular solve with the proposal factor) and the whole
+    iteration loop (:101-314) on a sharded field: every rank solves its owned rows with the synchronisation-free kernel, boundary
+    values go straight into the peers' solution vectors; the chain makes the same accept / reject decisions as the unsharded one."""
+    n = 24000
+    P = make_problem(n, 10, seed=25)
+    b = P["rng"].standard_normal(n)
+    cp2 = [1.0, 0.06, 0.0]
+    var_y = float(np.var(P["y"], ddof=1))
+    p0 = dict(shape=[np.log(0.05)], beta_0=B0, log_scale=LS, log_noise_variance=LNV)
+    n_iter = 8
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.factor_build(CP)
+        ctx.factor_commit()
+        ctx.field_set(P["field"])
+        ctx.obs_set(P["y"])
+        x_ref = ctx.sptrsv(b)
+        ctx.factor_build(cp2, slot=nb.SLOT_PROPOSAL)
+        ratio_ref = ctx.ancillary_propose(B0, 0.05, LNV)
+        ctx.field_init(B0, LS, b)
+        f_init_ref = ctx.field_get()
+        ctx.field_set(P["field"])
+        chain_ref = {}
+        for mode in (nb.RNG_SUPPLIED, nb.RNG_PHILOX):
+            ctx.field_set(P["field"])
+            chain_ref[mode] = ctx.chain_run(p0, n_iter, var_y, thin=0.5, n_chromatic=2, iter_start=0, chain_index=2, rng_mode=mode) + (ctx.field_get(),)
+    ctxs = shard_contexts(P, parts)
+    try:
+        nb.connect_local(ctxs)
+        xs = run_concurrently([lambda c=c: c.sptrsv(b[c.plan["local_sites"]]) for c in ctxs])
+        for c, x in zip(ctxs, xs):   # owned AND ghost entries hold the solution
+            assert np.max(np.abs(x - x_ref[c.plan["local_sites"]])) < 1e-9 * np.max(np.abs(x_ref))
+        for c in ctxs:
+            c.factor_build(cp2, slot=nb.SLOT_PROPOSAL)
+        ratios = run_concurrently([lambda c=c: c.ancillary_propose(B0, 0.05, LNV) for c in ctxs])
+        assert all(r == ratios[0] for r in ratios) and abs(ratios[0] - ratio_ref) < 1e-9 * max(1.0, abs(ratio_ref))
+        run_concurrently([lambda c=c: c.field_init(B0, LS, b[c.plan["local_sites"]]) for c in ctxs])
+        for c in ctxs:
+            assert np.max(np.abs(c.field_get() - f_init_ref[c.plan["local_sites"]])) < 1e-9 * np.max(np.abs(f_init_ref))
+        for mode in (nb.RNG_SUPPLIED, nb.RNG_PHILOX):
+            for c in ctxs:
+                c.field_set(P["field"][c.plan["local_sites"]])
+            po, rec, frecs, acc = nb.group_chain_run(ctxs, p0, n_iter, var_y, thin=0.5, n_chromatic=2, iter_start=0, chain_index=2, rng_mode=mode)
+            po_r, rec_r, frec_r, acc_r, f_r = chain_ref[mode]
+            assert np.array_equal(acc, acc_r)                                  # the same accept / reject sequence
+            assert np.allclose(rec, rec_r, rtol=1e-8, atol=1e-10)
+            for c, fr in zip(ctxs, frecs):
+                assert np.allclose(fr, frec_r[:, c.plan["local_sites"]], rtol=1e-8, atol=1e-9)
+                assert np.allclose(c.field_get(), f_r[c.plan["local_sites"]], rtol=1e-8, atol=1e-9)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_philox_draws_do_not_depend_on_the_sharding():
     P = make_problem(20000, 10, seed=6)
     f_ref, *_ = reference(P, 1, z=None, seed=9)
@@ -143,8 +227,7 @@ def test_single_rank_sharded_context_is_the_plain_one():
         assert abs(c.loglik(B0, LS) - ll0) < 1e-10 * abs(ll0)
         c.gibbs_sweep(B0, LS, LNV, n_sweeps=1, z=z)              # world = 1: the ordinary entry point works
         assert np.max(np.abs(c.field_get() - f_ref)) < 1e-10
-        with pytest.raises(nb.NNGPError):
-            c.sptrsv(z)                                          # not available on sharded contexts
+        assert np.max(np.abs(c.sptrsv(z) - nb_solve_ref(P, z))) < 1e-9    # a one-rank "sharded" field solves like the plain one
 
 
 def _nccl_worker(rank, world, port, q, transport="nccl"):
@@ -167,7 +250,15 @@ def _nccl_worker(rank, world, port, q, transport="nccl"):
         ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=1, seed=4)
         f = ctx.field_get()
         own = plan["owned"] == 1
-        q.put((rank, ll, plan["local_sites"][own], f[own], ctx.ssr()))
+        extra = None
+        if transport == "p2p":   # the solve-based entry points and the whole chain across two GPUs
+            bvec = np.random.default_rng(2).standard_normal(n)
+            x = ctx.sptrsv(bvec[plan["local_sites"]])
+            ctx.field_set(P["field"][plan["local_sites"]])
+            po, rec, frec, acc = ctx.chain_run(dict(shape=[np.log(0.05)], beta_0=B0, log_scale=LS, log_noise_variance=LNV), 6, float(np.var(P["y"], ddof=1)),
+                                               thin=0.0, n_chromatic=2, iter_start=0, chain_index=1, rng_mode=nb.RNG_SUPPLIED, keep_field=False)
+            extra = (x[own], rec, acc, ctx.field_get()[own])
+        q.put((rank, ll, plan["local_sites"][own], f[own], ctx.ssr(), extra))
         ctx.close()
     except Exception as e:   # report instead of leaving the parent waiting on the queue
         q.put((rank, repr(e)))
@@ -192,7 +283,7 @@ def test_nccl_sharded_sweep_on_two_gpus(transport):
     res = [q.get(timeout=240) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert all(len(r) == 5 for r in res), res
+    assert all(len(r) == 6 for r in res), res
     P = make_problem(40000, 10, seed=8)
     n = P["n"]
     z = np.random.default_rng(1).standard_normal(2 * n)
@@ -205,9 +296,21 @@ def test_nccl_sharded_sweep_on_two_gpus(transport):
         ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=2, z=z)
         ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=1, seed=4)
         f_ref, ssr_ref = ctx.field_get(), ctx.ssr()
+        if transport == "p2p":
+            bvec = np.random.default_rng(2).standard_normal(n)
+            x_ref = ctx.sptrsv(bvec)
+            ctx.field_set(P["field"])
+            _, rec_ref, _, acc_ref = ctx.chain_run(dict(shape=[np.log(0.05)], beta_0=B0, log_scale=LS, log_noise_variance=LNV), 6, float(np.var(P["y"], ddof=1)),
+                                                   thin=0.0, n_chromatic=2, iter_start=0, chain_index=1, rng_mode=nb.RNG_SUPPLIED, keep_field=False)
+            fc_ref = ctx.field_get()
     f = np.full(n, np.nan)
-    for rank, ll, sites, vals, ssr in res:
+    for rank, ll, sites, vals, ssr, extra in res:
         assert abs(ll - ll_ref) < 1e-10 * abs(ll_ref)
         assert abs(ssr - ssr_ref) < 1e-10 * ssr_ref
         f[sites] = vals
+        if transport == "p2p":
+            x, rec, acc, fc = extra
+            assert np.max(np.abs(x - x_ref[sites])) < 1e-9 * np.max(np.abs(x_ref))
+            assert np.array_equal(acc, acc_ref) and np.allclose(rec, rec_ref, rtol=1e-8, atol=1e-10)
+            assert np.allclose(fc, fc_ref[sites], rtol=1e-8, atol=1e-9)
     assert np.max(np.abs(f - f_ref)) < 1e-10 * np.max(np.abs(f_ref))
