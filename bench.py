@@ -468,6 +468,9 @@ def shared_problem(dist, rank, n, m, seed, reordering, tag):
     shm = f"/dev/shm/nngp_bench_{os.environ.get('MASTER_PORT', '0')}_{tag}"
     t = None
     if rank == 0:
+        import nngp_b200 as nb
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        nb.set_host_threads(0)            # torchrun exports OMP_NUM_THREADS=1: rank 0 builds the shared structure with every core
         _, locs, nn, coloring, _, t = build_problem(n, m, seed=seed, reordering=reordering)
         np.save(shm + "_locs.npy", np.asfortranarray(locs))
         np.save(shm + "_nn.npy", np.asfortranarray(nn))

@@ -3,6 +3,8 @@
 // These replace init-time code of the reference (GpGp::find_ordered_nn, GpGp::order_maxmin, the crossprod() moral graph
 // and Coloring.R), which runs once per model on the host in the reference too.  They are NOT a CPU fallback of the GPU
 // hot path.  Semantics (and the reference lines they replace) are documented in the header.
+#include <omp.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -448,6 +450,14 @@ void nngp_host_greedy_coloring_adj(const int *adj_p, const int *adj_i, const int
         K = std::max(K, c);
     }
     if (n_colors) *n_colors = K;
+    if (status) *status = NNGP_OK;
+}
+
+// number of OpenMP threads of the host set-up utilities (a launcher such as torchrun exports OMP_NUM_THREADS=1, which the OpenMP
+// runtime reads once, when it is first loaded -- possibly long before this library is); n <= 0 = all processors
+void nngp_host_set_num_threads(const int *n, int *status) {
+    if (!n) { nngp::set_error("nngp_host_set_num_threads: null argument"); if (status) *status = NNGP_ERR_ARG; return; }
+    omp_set_num_threads(*n > 0 ? *n : omp_get_num_procs());
     if (status) *status = NNGP_OK;
 }
 

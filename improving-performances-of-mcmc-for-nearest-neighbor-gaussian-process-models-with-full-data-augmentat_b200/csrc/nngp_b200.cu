@@ -29,6 +29,13 @@ namespace nngp {
 // ------------------------------------------------------------------------------------------------------------------
 // errors, launch counter
 // ------------------------------------------------------------------------------------------------------------------
+// Kernels of several contexts of ONE process may wait for each other from inside the device (shards of one field connected with
+// nngp_shard_connect_local).  CUDA's default lazy module loading loads a kernel at its first launch and may need the device to
+// drain to do so: a host thread stuck in such a load while its stream's previous kernel waits for a peer whose host thread
+// needs the same lock is a deadlock.  Ask for eager loading before this library makes its first CUDA call (no effect, and no
+// harm, when the process has already initialised CUDA: then there is one context per process and nothing to deadlock with).
+static const int g_eager_loading = (setenv("CUDA_MODULE_LOADING", "EAGER", 0), 0);
+
 static std::mutex g_err_mu;
 static char g_err[1024] = "";
 static thread_local char t_err[1024] = "";   // the calling thread's last message (chains run on worker threads)

@@ -81,6 +81,8 @@ void nngp_host_greedy_coloring(const int *NNarray, const int *n, const int *m, i
 /* drop-in for naive_greedy_coloring(M) itself (Scripts/Coloring.R:2-20): M's compressed-column slots M@p (n + 1) and M@i (0-based),
  * i.e. the MRF adjacency matrix of Scripts/mcmc_nngp_initialize.R:103-109; same colours, no dense (n+1) x maxdeg scratch */
 void nngp_host_greedy_coloring_adj(const int *adj_p, const int *adj_i, const int *n, int *coloring, int *n_colors, int *status);
+/* OpenMP threads used by the nngp_host_* utilities; n <= 0 = all processors (launchers such as torchrun export OMP_NUM_THREADS=1) */
+void nngp_host_set_num_threads(const int *n, int *status);
 /* exact max-min (farthest-point) ordering, 1-based permutation (replaces GpGp::order_maxmin,
  * Scripts/mcmc_nngp_initialize.R:29; GpGp's is a randomised approximation and cannot be reproduced bit-for-bit) */
 void nngp_host_order_maxmin(const double *locs, const int *n, const int *d, int *order, int *status);

@@ -50,7 +50,7 @@ def main():
         ms, nl = ctx.time_op(op, reps=a.reps)
         print(f"  {label}: median {np.median(ms) * 1e3:8.1f} us  min {ms.min() * 1e3:8.1f} us  launches {nl}", flush=True)
 
-    for sv in (0, 1, 2, 3):
+    for sv in (0, 4, 1, 2, 3):
         for g in ((1, 0) if sv == 0 else (1,)):
             ctx.set_option("sweep_variant", sv)
             ctx.set_option("use_graph", g)
@@ -74,6 +74,24 @@ def main():
     ctx.set_option("loglik_variant", 1)
     line("spmv", "spmv")
     line("sweep + loglik", "sweep_loglik")
+    # several chains sharing the GPU: aggregate sweeps/s with the dependents triggered at the top (0) or after the wait (4)
+    others = []
+    for k in range(2):
+        c2 = nb.NNGPContext(locs, nn, col, lm, a.covfun)
+        c2.factor_build(cp)
+        c2.factor_commit()
+        c2.field_set(w)
+        c2.obs_set(w)
+        c2.gibbs_sweep(0.0, 0.0, np.log(0.1), 1, seed=k + 2)
+        others.append(c2)
+    for sv in (0, 4):
+        for c in [ctx] + others:
+            c.set_option("sweep_variant", sv)
+        for nc in (1, 2, 3):
+            ms = nb.time_op_group(([ctx] + others)[:nc], "gibbs_sweep", reps=100)
+            print(f"  {nc} chain(s) on one GPU, sweep variant {sv}: {nc * 100 / ms * 1e3:9.0f} sweeps/s aggregate", flush=True)
+    for c2 in others:
+        c2.close()
     ctx.close()
 
 

@@ -249,6 +249,7 @@ def _nccl_worker(rank, world, port, q, transport="nccl"):
         ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=2, z=z)             # halo exchange over NCCL after every colour
         ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=1, seed=4)
         f = ctx.field_get()
+        ssr = ctx.ssr()
         own = plan["owned"] == 1
         extra = None
         if transport == "p2p":   # the solve-based entry points and the whole chain across two GPUs
@@ -258,7 +259,7 @@ def _nccl_worker(rank, world, port, q, transport="nccl"):
             po, rec, frec, acc = ctx.chain_run(dict(shape=[np.log(0.05)], beta_0=B0, log_scale=LS, log_noise_variance=LNV), 6, float(np.var(P["y"], ddof=1)),
                                                thin=0.0, n_chromatic=2, iter_start=0, chain_index=1, rng_mode=nb.RNG_SUPPLIED, keep_field=False)
             extra = (x[own], rec, acc, ctx.field_get()[own])
-        q.put((rank, ll, plan["local_sites"][own], f[own], ctx.ssr(), extra))
+        q.put((rank, ll, plan["local_sites"][own], f[own], ssr, extra))
         ctx.close()
     except Exception as e:   # report instead of leaving the parent waiting on the queue
         q.put((rank, repr(e)))
