@@ -313,7 +313,7 @@ def run_single(a):
     # adaptive phase in which proposals ARE accepted (the accept branch -- transposition + precision_diag, field copy -- is in) ----
     var_y = float(np.var(y, ddof=1))
     chain_params = {"shape": [np.log(RANGE)] + ([0.0] if a.covfun.startswith("matern") else []), "beta_0": 0.0, "log_scale": ls, "log_noise_variance": lnv}
-    n_chain_it, n_adapt = 50, 700
+    n_chain_it, n_adapt = (50, 700) if not a.no_chain else (2, 2)
     # the adaptive phase (update_Gaussian.R:153-157,209-213) shrinks the proposal variances until proposals are accepted: at n = 1M
     # the posterior of the covariance parameters is so narrow that this takes several hundred iterations from logvar = -2
     adapted, _, _, _ = ctx.chain_run(chain_params, n_adapt, var_y, thin=0.0, n_chromatic=10, iter_start=0, chain_index=1, keep_field=False)
@@ -540,6 +540,27 @@ def run_sharded(a):
         ctx.time_op(op, reps=3)
         barrier()
         comp[key] = ctx.time_op(op, reps=reps)[0]
+    # ---- a whole chain on the sharded field (reference loop update_Gaussian.R:101-314: 2 factor rebuilds, ancillary SpMV + sharded
+    # triangular solve, 2 log-liks, beta_0, 10 sweeps, noise steps), every rank on its block, decisions on all-reduced scalars ----
+    chain_it_per_s, solve_ms = None, None
+    if a.transport == "p2p" and not a.no_chain:
+        yv = np.random.default_rng(8).standard_normal(8)   # (var_y only has to be the same on every rank)
+        var_y = float(1.0 + TAU2 + 0.0 * yv.sum())
+        chain_params = {"shape": [np.log(RANGE)] + ([0.0] if a.covfun.startswith("matern") else []), "beta_0": 0.0, "log_scale": ls, "log_noise_variance": lnv}
+        ctx.chain_run(chain_params, 2, var_y, thin=0.0, n_chromatic=10, iter_start=5000, chain_index=1, keep_field=False)
+        n_it = 10
+        barrier()
+        t0 = time.perf_counter()
+        ctx.chain_run(chain_params, n_it, var_y, thin=0.0, n_chromatic=10, iter_start=5000, chain_index=1, keep_field=False)
+        barrier()
+        chain_it_per_s = n_it / (time.perf_counter() - t0)
+        ctx.field_set(w_local)
+        assert ctx.factor_build(cp) == 0
+        ctx.factor_commit()
+        ctx.gibbs_sweep(beta_0, ls, lnv, n_sweeps=1, seed=1)
+        ctx.time_op("sptrsv", reps=3)
+        barrier()
+        solve_ms = ctx.time_op("sptrsv", reps=20)[0]
     clocks = sampler.stop() if rank == 0 else None
 
     def maxred(vals):
@@ -554,6 +575,9 @@ def run_sharded(a):
 
     total_ms, sweep_med, sweep_min, ll_med, ll_min, fac_med = maxred([float(ms_steps.sum()), float(np.median(comp["sweep"])), float(comp["sweep"].min()),
                                                                        float(np.median(comp["loglik"])), float(comp["loglik"].min()), float(np.median(comp["factor_build"]))])
+    if solve_ms is not None:
+        (solve_med,) = maxred([float(np.median(solve_ms))])
+        (chain_it_per_s,) = [-v for v in maxred([-chain_it_per_s])]
     sp = np.asarray(plan["send_ptr"])
     pairs = int(((np.diff(sp).reshape(-1, world)) > 0).sum())
     halo_vals, n_ghost, n_local, pair_sum = sumred([float(sp[-1]), float(plan["n_ghost"]), float(plan["local_sites"].size), float(pairs)])
@@ -603,7 +627,10 @@ def run_sharded(a):
             "gibbs_sweeps_per_sec": 1e3 / sweep_med, "loglik_evals_per_sec": 1e3 / ll_med, "factor_builds_per_sec": 1e3 / fac_med,
             "ms": {"sweep": {"median": sweep_med, "min": sweep_min, "reps": reps}, "loglik": {"median": ll_med, "min": ll_min, "reps": reps},
                    "factor_build": {"median": fac_med, "reps": reps}},
-            "halo_us_per_colour": None,
+            "chain_iterations_per_sec": chain_it_per_s,
+            "chain_iteration": "nngp_chain_run on the sharded field: reference loop update_Gaussian.R:101-314 (2 factor rebuilds, ancillary SpMV + sharded triangular solve, 2 log-liks, beta_0, 10 sweeps, noise steps), every rank on its block, host wall clock",
+            "spmv_plus_sptrsv_ms": solve_med if solve_ms is not None else None,
+            "halo_us_per_colour_over_1gpu_block": None,
             "roofline": {"bound": "hbm", "kernel": "gibbs_tile2_kernel<SHARD> (whole-field sweep: K colour launches per rank, halo push / apply fused in; max over ranks)",
                          "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
                          "peak_source": peak_src + f" x {world} GPUs", "algorithmic_bytes_per_sweep": ab["gibbs_sweep"],
@@ -674,6 +701,7 @@ def main():
     ap.add_argument("--no-multichain", action="store_true")
     ap.add_argument("--no-other-ordering", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-chain", action="store_true")
     ap.add_argument("--mode", default="auto", choices=["auto", "single", "sharded"])
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="sharded mode: halo transport")
     a = ap.parse_args()

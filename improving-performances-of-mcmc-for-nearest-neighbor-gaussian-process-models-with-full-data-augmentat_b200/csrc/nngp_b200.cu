@@ -1307,6 +1307,7 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         }
         c->d_recvbuf.p = c->p2p_area + c->p2p_val_off;      // not owned by the DevBuf (released with the area)
         c->d_recvbuf.n = 0;
+        ensure_stage(c, (size_t)std::max(n, n_obs));   // no page-locked allocation (a device-synchronising call) once peers may be waiting on this rank
         c->d_shard_state.alloc(4);
         CK(cudaMemsetAsync(c->d_shard_state.p, 0, 4 * sizeof(unsigned long long), s));
         CK(cudaStreamSynchronize(s));
@@ -2000,6 +2001,27 @@ void nngp_predict_sample(const int *ctx_id, const int *slot, const int *n_obs_si
 
 }  // extern "C"
 
+// Buffers a chain needs beyond the context's own (the supplied-normals block, the device-side record store).  Allocating or
+// freeing device memory synchronises the device, which must not happen while a peer of a sharded field waits on this rank from
+// inside a kernel: the group entry points call this for every member BEFORE they start the chain threads.
+static bool prepare_chain_buffers(Ctx *c, int n_iter, double thin, int n_chromatic, int rng_mode, bool want_field_records) {
+    use(c);
+    if (rng_mode == NNGP_RNG_SUPPLIED) ensure_zbuf(c, (size_t)c->n_global * (size_t)std::max(1, n_chromatic));
+    const int n_frec = (int)std::nearbyint(n_iter * thin);
+    bool on_device = false;
+    if (want_field_records && n_frec > 0) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (size_t)n_frec * c->n * sizeof(double);
+        if (c->d_frec.n >= (size_t)n_frec * c->n || need + ((size_t)2 << 30) < free_b + c->d_frec.n * sizeof(double)) {
+            if (c->d_frec.n < (size_t)n_frec * c->n) c->d_frec.alloc((size_t)n_frec * c->n);
+            on_device = true;
+            c->frec_rows = n_frec;
+        }
+    }
+    return on_device;
+}
+
 // regression part of one chain (nngp_chain_run_regressors); nullptr = the no-regressor model
 struct RegRun {
     double *beta_io;              // p: state$params$beta in, out
@@ -2084,17 +2106,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
     if (reg) op_set_beta(c, beta.data());                                        // :85
     const int n_frec = (int)std::nearbyint(n_iter * thin);
     // stored field samples stay in HBM, already in R's n_frec x n column-major layout, and leave in one copy at the end
-    bool frec_on_device = false;
-    if (field_records_out && n_frec > 0) {
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
-        const size_t need = (size_t)n_frec * n * sizeof(double);
-        if (c->d_frec.n >= (size_t)n_frec * n || need + ((size_t)2 << 30) < free_b + c->d_frec.n * sizeof(double)) {
-            if (c->d_frec.n < (size_t)n_frec * n) c->d_frec.alloc((size_t)n_frec * n);
-            frec_on_device = true;
-            c->frec_rows = n_frec;
-        }
-    }
+    const bool frec_on_device = prepare_chain_buffers(c, n_iter, thin, n_chromatic, rng_mode, field_records_out != nullptr);
     const unsigned long long philox_seed = ((unsigned long long)(uint32_t)iter_start << 20) ^ (unsigned long long)(uint32_t)*chain_index_;
     // development aid: NNGP_CHAIN_PROFILE=1 synchronises at the phase boundaries and prints host wall-clock per phase
     const bool prof = std::getenv("NNGP_CHAIN_PROFILE") != nullptr;
@@ -2515,6 +2527,7 @@ void nngp_shard_group_chain_run(const int *ctx_ids, const int *world, const int 
         j.chain_index = *chain_index;
         j.status = NNGP_OK;
     }
+    for (int h = 0; h < W; h++) prepare_chain_buffers(jobs[h].c, ni, *thin, *n_chromatic, *rng_mode, field_records_out != nullptr);
     run_chain_jobs(jobs, W, n_shape, n_iter, thin, n_chromatic, iter_start, rng_mode, var_y, nullptr, nullptr);   // all members at once
     for (int h = 0; h < W; h++)
         if (jobs[h].status != NNGP_OK) {
@@ -2559,7 +2572,7 @@ void nngp_records_summary(const int *ctx_id, const int *first_row, const int *n_
 void nngp_time_op(const int *ctx_id, const int *op_, const int *reps_, const int *flush_l2_, double *ms_out, int *launches_out, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);
-    NEED(!c->sharded || (*op_ == 0 || *op_ == 1 || *op_ == 2 || *op_ == 3 || *op_ == 5 || *op_ == 6), "nngp_time_op: that op is not available on a sharded context");
+    NEED(!c->sharded || *op_ != 4 || c->world == 1 || (c->p2p && c->can_solve), "nngp_time_op: the triangular solve of a sharded context needs the peer-to-peer transport");
     REQUIRE(op_ && reps_ && flush_l2_ && ms_out && *reps_ >= 1, "nngp_time_op: bad argument");
     const int op = *op_;
     use(c);

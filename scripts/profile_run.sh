@@ -3,7 +3,7 @@
 # The plain run of the same command line must exit 0 first (B200_PROFILING.md).
 set -u
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-predict"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-predict --no-multichain --no-other-ordering --no-chain"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
 tail -1 gpurun_out/plain.log | cut -c1-300
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1

@@ -123,5 +123,10 @@ if __name__ == "__main__":
             print(label, "dram traffic (MB):", t / 1e6)
             traffic[label] = t
     # bench.py reports roofline.traffic from here (dram__bytes_read.sum + dram__bytes_write.sum of one full sweep)
+    sha = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    import datetime
     with open(os.path.join(OUT, "traffic.json"), "w") as f:
-        json.dump({"source": f"{tag}: ncu --set full, n=1M m=10 config 3", "bytes": traffic}, f, indent=1)
+        json.dump({"source": f"{tag}: ncu, n=1M m=10 config 3 (max-min ordering)", "git_sha": sha, "when": datetime.datetime.utcnow().isoformat() + "Z",
+                   "how": "dram__bytes_read.sum + dram__bytes_write.sum per capture; gibbs_sweep_full = the K colour launches of ONE warm sweep (--cache-control none); "
+                          "the library that was profiled is the one built from git_sha (scripts/profile_run.sh ran the plain bench first)",
+                   "bytes": traffic}, f, indent=1)

@@ -201,6 +201,50 @@ def test_sharded_triangular_solve_ancillary_step_and_whole_chain(parts):
             c.close()
 
 
+def test_sharded_matern_m20_factor_loglik_and_sweep_equal_unsharded():
+    """config 4's shape (m = 20, matern_isotropic nu 0.75, range 0.02 scaled to this n) on a sharded field: the factor rows of the
+    owned sites, the all-reduced log-likelihood and a fused peer-to-peer sweep reproduce the unsharded context (Scripts/
+    mcmc_nngp_initialize.R:62-69 covariance families; update_Gaussian.R:70 smoothness in (0.5, 1))."""
+    n, m, parts = 30000, 20, 4
+    cp = [1.0, 0.06, 0.75, 0.0]
+    P = make_problem(n, m, seed=35)
+    z = P["rng"].standard_normal(2 * n)
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], "matern_isotropic") as ctx:
+        assert ctx.factor_build(cp) == 0
+        L_ref = ctx.factor_get()
+        ctx.factor_commit()
+        ctx.field_set(P["field"])
+        ctx.obs_set(P["y"])
+        ll_ref = ctx.loglik(B0, LS)
+        ctx.gibbs_sweep(B0, LS, LNV, n_sweeps=2, z=z)
+        f_ref = ctx.field_get()
+    owner = nb.spatial_blocks(P["locs"], parts)
+    ctxs = []
+    try:
+        for r in range(parts):
+            plan = nb.shard_plan(P["locs"], P["NNarray"], P["coloring"], P["locs_match"], owner, r, parts)
+            c = nb.ShardedContext(plan, "matern_isotropic", device=0, comm_id=None)
+            assert c.factor_build(cp) == 0
+            own = plan["owned"] == 1
+            Lg = c.factor_get()[own]
+            Lr = L_ref[plan["local_sites"][own]]
+            # an owned row's parents are all local, in the same order: the same row up to the (local) column layout
+            assert np.max(np.linalg.norm(Lg - Lr, axis=1) / np.linalg.norm(Lr, axis=1)) < 1e-12
+            c.factor_commit()
+            c.field_set(P["field"][plan["local_sites"]])
+            c.obs_set(P["y"][plan["obs_index"]])
+            ctxs.append(c)
+        nb.connect_local(ctxs)
+        ll = nb.group_loglik(ctxs, B0, LS)
+        assert np.all(np.abs(ll - ll_ref) < 1e-10 * abs(ll_ref))
+        nb.group_sweep(ctxs, B0, LS, LNV, n_sweeps=2, z=z)
+        f = gather_owned(ctxs, n)
+        assert np.max(np.abs(f - f_ref)) < 1e-10 * np.max(np.abs(f_ref))
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_philox_draws_do_not_depend_on_the_sharding():
     P = make_problem(20000, 10, seed=6)
     f_ref, *_ = reference(P, 1, z=None, seed=9)
