@@ -63,7 +63,7 @@ class NNGPContext:
         getattr(L.load(), name)(L.ci(self._id), *args, C.byref(st))
         L.check(st)
 
-    OPTIONS = {"sweep_variant": 1, "solve_variant": 2, "use_graph": 3, "solve_ctas_per_sm": 4, "solve_sleep_ns": 5,
+    OPTIONS = {"sweep_variant": 1, "solve_variant": 2, "use_graph": 3, "solve_ctas_per_sm": 4, "solve_sleep_ns": 5, "solve_level_copy": 6,
                "solve_window_ctas": 7, "commit_variant": 8, "matern_table": 9, "loglik_variant": 10}
 
     def set_option(self, name: str, value: int):

@@ -28,6 +28,12 @@ struct CovConst {
     int d;            // raw coordinate dimension
     int dt;           // transformed dimension
     const double *mtab;   // Matern families: piecewise-polynomial table of the kernel (nullptr = evaluate K_nu directly)
+    // second copy of the factor in the order in which the triangular solve walks the rows (DAG level order): row q also goes to
+    // position lpos[q] of linv_lvl ([m+1][nsl]); the solve then reads its rows with coalesced loads instead of one 32-byte
+    // sector per 8-byte value (ncu round 1: 950 MB of DRAM traffic for 228 MB of data).  nullptr = no copy.
+    double *linv_lvl;
+    const int *lpos;
+    int nsl;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -308,6 +314,11 @@ __device__ __noinline__ void factor_row_generic(int q, const int *__restrict__ n
         x[a] = s / L[a * (a + 1) / 2 + a];
     }
     for (int j = 0; j < M; j++) linv[(size_t)j * ld + q] = (j < bsize) ? x[bsize - 1 - j] : 0.0;
+    if (cc.linv_lvl) {
+        const int t = cc.lpos[q];
+        if (t >= 0)
+            for (int j = 0; j < M; j++) cc.linv_lvl[(size_t)j * cc.nsl + t] = (j < bsize) ? x[bsize - 1 - j] : 0.0;
+    }
     if (!ok) atomicAdd(n_bad, 1);
 }
 
@@ -392,6 +403,13 @@ __global__ void __launch_bounds__(128, MINB) vecchia_factor_reg_kernel(const int
     }
 #pragma unroll
     for (int j = 0; j < M; j++) linv[(size_t)j * ld + q] = x[M - 1 - j];
+    if (cc.linv_lvl) {
+        const int t = cc.lpos[q];
+        if (t >= 0) {
+#pragma unroll
+            for (int j = 0; j < M; j++) cc.linv_lvl[(size_t)j * cc.nsl + t] = x[M - 1 - j];
+        }
+    }
     if (!ok) atomicAdd(n_bad, 1);
 }
 
@@ -716,7 +734,8 @@ struct ShardSolve {
     unsigned int x_off[8];        // offset (doubles) of the current solve's x buffer inside every peer's area
 };
 
-template <int MT, bool SHARD = false>
+// LVL: nn / linv are the level-ordered copies ([m+1][n_slots], position t of the row list) instead of the storage-ordered tables.
+template <int MT, bool SHARD = false, bool LVL = false>
 __global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restrict__ nn, const double *__restrict__ linv,
                                                               const int *__restrict__ rows_padded, int n_slots,
                                                               const double *__restrict__ b, unsigned long long *x,
@@ -748,26 +767,27 @@ __global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restr
     int idx[MC], idx1[MC];
     double a[MC], a1[MC];
     double bq = 0.0, bq1 = 0.0;
-    auto load_row = [&](int q, int (&id)[MC], double (&av)[MC], double &bv) {
+    auto load_row = [&](int q, int chunk, int (&id)[MC], double (&av)[MC], double &bv) {
         if (q < 0) return;
+        const size_t at = LVL ? (size_t)chunk * blockDim.x + threadIdx.x : (size_t)q;   // LVL: ld is the row list's padded length
 #pragma unroll
         for (int j = 0; j < MC; j++) {
             if (j < Mr) {
-                id[j] = nn[(size_t)j * ld + q];
-                av[j] = linv[(size_t)j * ld + q];
+                id[j] = nn[(size_t)j * ld + at];
+                av[j] = linv[(size_t)j * ld + at];
             }
         }
         bv = b[q];
     };
     int c0 = take();
     int q0 = row_of(c0);
-    load_row(q0, idx, a, bq);
+    load_row(q0, c0, idx, a, bq);
     int c1 = take();
     int q1 = row_of(c1);
     while (c0 < n_chunks) {
         const int c2 = (c1 < n_chunks) ? take() : n_chunks;   // (A) ticket of chunk i+2 ...
         const int q2 = row_of(c2);                            //     ... and its row id (in flight)
-        load_row(q1, idx1, a1, bq1);                          // (B) loads of chunk i+1 (row id arrived last iteration)
+        load_row(q1, c1, idx1, a1, bq1);                      // (B) loads of chunk i+1 (row id arrived last iteration)
         if (q0 >= 0) {                                        // (C) chunk i
             double s = bq;
             // Poll ALL still-pending parents in every round: the loads of one round are independent and overlap, so a
@@ -786,7 +806,14 @@ __global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restr
 #pragma unroll
                 for (int j = 1; j < MC; j++) pending = pending || (bits[j] == NNGP_SOLVE_SENTINEL);
                 if (pending) {
-                    if (++spins > (1u << 22)) { atomicExch(err, 1); break; }   // never hang the device on a corrupted structure
+                    if (++spins > (1u << 22)) {   // never hang the device on a corrupted structure (or a dead peer): report the row
+                        if (atomicExch(err, 1) == 0 && SHARD) {
+                            int jp = 1;
+                            for (int j = 1; j < MC; j++) if (bits[j] == NNGP_SOLVE_SENTINEL) { jp = j; break; }
+                            err[2] = q0; err[3] = idx[jp]; err[4] = c0;
+                        }
+                        break;
+                    }
                     if (sleep_ns) __nanosleep(sleep_ns);
                 }
             }

@@ -217,6 +217,9 @@ struct Ctx {
     DevBuf<int4> d_tiles;
     DevBuf<unsigned char> d_cloc;          // per tile (padded to 1024): local site id of every CSC entry, 255 = padding
     DevBuf<int> d_rows_padded, d_ticket;
+    DevBuf<int> d_nn_lvl, d_lpos;          // triangular solve: neighbour table in row-list (DAG level) order; position of every row in the list
+    DevBuf<double> d_linv_lvl[2];          // ... and the factor values in the same order, written by the factor build next to d_linv
+    bool level_copy = true;
     double *h_pinned = nullptr;       // 64 doubles of pinned scratch for scalar results
     double *h_stage = nullptr;        // pinned staging for vectors (n doubles at least)
     size_t h_stage_n = 0;
@@ -339,6 +342,7 @@ static uint32_t morton2(uint32_t x, uint32_t y) {
 static CovConst make_cov(Ctx *c, const double *cp, int ncp) {
     CovConst cc{};
     cc.mtab = nullptr;
+    cc.linv_lvl = nullptr; cc.lpos = nullptr; cc.nsl = 0;
     cc.covfun = c->covfun;
     cc.d = c->d;
     cc.dt = c->dt;
@@ -421,6 +425,11 @@ static void op_factor_build(Ctx *c, int slot, const CovConst &cc_in) {
     transform_locs_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_locs.p, c->d_tl.p, c->n, cc);
     LAUNCHED(c);
     double *linv = c->linv_slot(slot);
+    if (c->level_copy && c->d_lpos.p) {
+        cc.linv_lvl = c->d_linv_lvl[slot == NNGP_SLOT_CURRENT ? c->cur : 1 - c->cur].p;
+        cc.lpos = c->d_lpos.p;
+        cc.nsl = c->n_slots;
+    }
     if (c->covfun >= NNGP_MATERN_ISOTROPIC) launch_factor<true>(c, linv, cc);
     else launch_factor<false>(c, linv, cc);
     CK(cudaGetLastError());
@@ -476,6 +485,14 @@ static void op_spmv(Ctx *c, const double *linv, const double *v, double shift, d
     LAUNCHED(c);
 }
 
+// the level-ordered copy of the factor that `linv` points to (nullptr: none kept, or the option is off)
+static const double *level_linv(Ctx *c, const double *linv) {
+    if (!c->level_copy || !c->d_lpos.p) return nullptr;
+    if (linv == c->d_linv[0].p) return c->d_linv_lvl[0].p;
+    if (linv == c->d_linv[1].p) return c->d_linv_lvl[1].p;
+    return nullptr;
+}
+
 // x = solve(linv, b); optional y = shift + scale * x
 static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, double *y, double shift, double scale) {
     if (c->sharded && c->world > 1) {
@@ -499,7 +516,9 @@ static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, do
         if (c->n_slots > 0) {
             const int want = c->solve_window_ctas > 0 ? c->solve_window_ctas : c->n_sm * c->solve_ctas_per_sm;
             const int blocks = std::max(1, std::min((c->n_slots + 255) / 256, want));
-            DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT, true><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, xs, y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ss)));
+            const double *lv = level_linv(c, linv);
+            if (lv) { DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT, true, true><<<blocks, 256, 0, c->stream>>>(c->d_nn_lvl.p, lv, c->d_rows_padded.p, c->n_slots, b, xs, y, shift, scale, c->n_slots, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ss))); }
+            else { DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT, true><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, xs, y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ss))); }
             LAUNCHED(c);
         }
         allreduce_scalars(c, 60, 1);   // barrier: every rank has finished this solve (and its stores into the peers' buffers)
@@ -513,7 +532,9 @@ static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, do
         LAUNCHED(c);
         const int want = c->solve_window_ctas > 0 ? c->solve_window_ctas : c->n_sm * c->solve_ctas_per_sm;
         const int blocks = std::max(1, std::min((c->n_slots + 255) / 256, want));
-        DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ShardSolve{})));
+        const double *lv = level_linv(c, linv);
+        if (lv) { DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT, false, true><<<blocks, 256, 0, c->stream>>>(c->d_nn_lvl.p, lv, c->d_rows_padded.p, c->n_slots, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale, c->n_slots, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ShardSolve{}))); }
+        else { DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ShardSolve{}))); }
         LAUNCHED(c);
         return;
     }
@@ -682,11 +703,19 @@ static void check_solve_flag(Ctx *c) {
     if (flag == 2) {
         unsigned long long dbg[4] = {0, 0, 0, 0};
         if (c->d_shard_state.p) cudaMemcpy(dbg, c->d_shard_state.p, sizeof(dbg), cudaMemcpyDeviceToHost);
-        set_error("sharded field: rank %d timed out waiting for a peer's halo value / reduction flag (a rank died or fell out of step); last halo wait recorded: colour %llu, ghost slot %llu, sweep %llu (this rank is at sweep %llu)",
-                  c->rank, dbg[1] + 1, dbg[2], dbg[3], dbg[0]);
+        int sdbg[3] = {0, 0, 0};
+        cudaMemcpy(sdbg, c->d_nbad.p + 3, sizeof(sdbg), cudaMemcpyDeviceToHost);
+        set_error("sharded field: rank %d timed out waiting for a peer's halo value / reduction flag (a rank died or fell out of step); last halo wait recorded: colour %llu, ghost slot %llu, sweep %llu (this rank is at sweep %llu); last solve wait recorded: row %d for site %d in chunk %d",
+                  c->rank, dbg[1] + 1, dbg[2], dbg[3], dbg[0], sdbg[0], sdbg[1], sdbg[2]);
         throw NcclFail();
     }
-    if (flag) { set_error("triangular solve: dependency wait timed out (corrupted neighbour structure?)"); throw CudaFail(); }
+    if (flag) {
+        int dbg[3] = {0, 0, 0};
+        cudaMemcpy(dbg, c->d_nbad.p + 3, sizeof(dbg), cudaMemcpyDeviceToHost);
+        set_error("triangular solve: dependency wait timed out (corrupted neighbour structure, or a peer of a sharded field that never delivered): rank %d, row (storage id) %d waited for site %d in chunk %d; owned = %d / %d",
+                  c->rank, dbg[0], dbg[1], dbg[2], c->sharded && c->d_owned.p ? 1 : 0, c->n);
+        throw CudaFail();
+    }
 }
 
 static double ll_from_sums(Ctx *c, double sum_log, double sum_sq, double log_scale) {
@@ -874,6 +903,7 @@ static void destroy_ctx(Ctx *c) {
     c->d_sp.release();
     c->d_tiles.release();
     c->d_rows_padded.release(); c->d_ticket.release(); c->d_cloc.release();
+    c->d_nn_lvl.release(); c->d_lpos.release(); c->d_linv_lvl[0].release(); c->d_linv_lvl[1].release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1242,10 +1272,26 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     c->d_lvl_ptr.upload(c->lvl_ptr, s); c->d_lm.upload(lm, s); c->d_optr.upload(optr, s); c->d_oidx.upload(oidx, s);
     c->d_cstart.upload(c->cstart, s); c->d_locs.upload(locs_int, s); c->d_nobs.upload(nobs, s);
     if (!c->partial_rows.empty()) c->d_partial_rows.upload(c->partial_rows, s);
-    c->d_nbad.alloc(2);
-    CK(cudaMemsetAsync(c->d_nbad.p, 0, 2 * sizeof(int), s));
+    c->d_nbad.alloc(8);   // [0] rows with a non-PD block, [1] wait timed out (1 solve, 2 halo / reduction), [3..5] which solve row waited for what
+    CK(cudaMemsetAsync(c->d_nbad.p, 0, 8 * sizeof(int), s));
     c->d_ticket.alloc(1);
     c->d_rows_padded.upload(rows_padded, s);
+    {   // level-ordered copies for the triangular solve: static neighbour table now, factor values at every factor build
+        std::vector<int> lpos(n, -1), nn_lvl((size_t)c->n_slots * M, -1);
+        for (int t = 0; t < c->n_slots; t++) {
+            const int q = rows_padded[t];
+            if (q < 0) continue;
+            lpos[q] = t;
+            for (int j = 0; j < M; j++) nn_lvl[(size_t)j * c->n_slots + t] = nn[(size_t)j * ld + q];
+        }
+        c->d_lpos.upload(lpos, s);
+        c->d_nn_lvl.upload(nn_lvl, s);
+        for (int k = 0; k < 2; k++) {
+            c->d_linv_lvl[k].alloc((size_t)std::max(c->n_slots, 1) * M);
+            CK(cudaMemsetAsync(c->d_linv_lvl[k].p, 0, sizeof(double) * (size_t)std::max(c->n_slots, 1) * M, s));
+        }
+        CK(cudaStreamSynchronize(s));
+    }
     c->d_tiles.upload(tiles, s);
     c->d_cloc.upload(cloc, s);
     c->d_tl.alloc((size_t)n * c->dt);
@@ -1383,6 +1429,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         case NNGP_OPT_MATERN_TABLE: c->matern_table = (*value != 0); break;
         case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "commit variant must be 0..1"); c->commit_variant = *value; break;
         case NNGP_OPT_SOLVE_WINDOW_CTAS: REQUIRE(*value >= 0 && *value <= 4096, "solve window must be 0..4096 CTAs"); c->solve_window_ctas = *value; break;
+        case NNGP_OPT_SOLVE_LEVEL_COPY: c->level_copy = (*value != 0); c->have_factor[0] = c->have_factor[1] = false; c->committed = false; break;
         case NNGP_OPT_SOLVE_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "solve sleep must be 0..100000 ns"); c->solve_sleep_ns = *value; break;
         default: REQUIRE(false, "unknown option key %d", *key);
     }

@@ -63,6 +63,12 @@ def main():
         line(f"spmv+sptrsv variant={sv} window_ctas={win}", "sptrsv")
     ctx.set_option("solve_window_ctas", 0)
     ctx.set_option("solve_variant", 0)
+    for lc in (0, 1):   # the factor build also writes the factor in the solve's row order (1, default) or not (0)
+        ctx.set_option("solve_level_copy", lc)
+        assert ctx.factor_build(cp) == 0
+        ctx.factor_commit()
+        line(f"spmv+sptrsv level_copy={lc}", "sptrsv")
+        line(f"factor_build level_copy={lc}", "factor_build")
     for cv in (0, 1):
         ctx.set_option("commit_variant", cv)
         line(f"transpose+precision_diag variant={cv}", "commit")

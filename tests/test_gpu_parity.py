@@ -365,16 +365,25 @@ def test_every_sweep_variant_matches_the_reference_loop(variant, n, m):
         assert rel_vec(ctx.field_get(), a) < TOL
 
 
-@pytest.mark.parametrize("solve_variant", [0, 1])
-def test_both_solve_variants(solve_variant):
-    P = make_problem(30000, 10, seed=13)
-    cp = [1.0, 0.05, 0.0]
+@pytest.mark.parametrize("solve_variant,level_copy,m", [(0, 1, 10), (0, 0, 10), (1, 1, 10), (0, 1, 7), (0, 1, 20)])
+def test_both_solve_variants(solve_variant, level_copy, m):
+    """sync-free solve reading the level-ordered copy of the factor (default) or the storage-ordered tables, and the level-scheduled
+    launches; both factor slots (the ancillary step solves with the PROPOSAL factor)"""
+    P = make_problem(30000, m, seed=13)
+    cp, cp2 = [1.0, 0.05, 0.0], [1.0, 0.08, 0.0]
     Lo = O.vecchia_Linv(cp, "exponential_isotropic", P["locs"], P["NNarray"])
+    Lo2 = O.vecchia_Linv(cp2, "exponential_isotropic", P["locs"], P["NNarray"])
     v = P["rng"].standard_normal(P["n"])
     with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
         ctx.set_option("solve_variant", solve_variant)
+        ctx.set_option("solve_level_copy", level_copy)
         ctx.factor_build(cp)
+        ctx.factor_build(cp2, slot=nb.SLOT_PROPOSAL)
         assert rel_vec(ctx.sptrsv(v), O.sparse_chol_solve(Lo, P["NNarray"], v)) < 1e-9
+        assert rel_vec(ctx.sptrsv(v, slot=nb.SLOT_PROPOSAL), O.sparse_chol_solve(Lo2, P["NNarray"], v)) < 1e-9
+        ctx.factor_accept()                                    # the proposal becomes the current factor: the copies swap with it
+        assert rel_vec(ctx.sptrsv(v), O.sparse_chol_solve(Lo2, P["NNarray"], v)) < 1e-9
+        assert rel_vec(ctx.sptrsv(v, slot=nb.SLOT_PROPOSAL), O.sparse_chol_solve(Lo, P["NNarray"], v)) < 1e-9
 
 
 @pytest.mark.parametrize("commit_variant", [0, 1])

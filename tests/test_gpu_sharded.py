@@ -140,9 +140,8 @@ def run_concurrently(fns):
         th.start()
     for th in ts:
         th.join()
-    for e in err:
-        if e is not None:
-            raise e
+    if any(e is not None for e in err):
+        raise RuntimeError("; ".join(f"member {k}: {e!r}" for k, e in enumerate(err) if e is not None))
     return out
 
 
