@@ -1088,17 +1088,26 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         }
     }
     c->i2g.resize(n);
-    std::iota(c->i2g.begin(), c->i2g.end(), 0);
     const bool color_major_storage = (c->layout != NNGP_LAYOUT_MORTON);
-    std::stable_sort(c->i2g.begin(), c->i2g.end(), [&](int a, int b) {
-        if (color_major_storage && coloring[a] != coloring[b]) return coloring[a] < coloring[b];
-        return key[a] < key[b];
-    });
+    {   // stable order by (colour if colour-major, key): one sort of packed 64-bit words -- (key, reference id) for the default
+        // Morton layout, (colour, key) with the id carried alongside otherwise
+        if (!color_major_storage) {
+            std::vector<unsigned long long> w(n);
+            for (int i = 0; i < n; i++) w[i] = ((unsigned long long)key[i] << 32) | (unsigned int)i;
+            std::sort(w.begin(), w.end());
+            for (int q = 0; q < n; q++) c->i2g[q] = (int)(w[q] & 0xffffffffull);
+        } else {
+            std::iota(c->i2g.begin(), c->i2g.end(), 0);
+            std::stable_sort(c->i2g.begin(), c->i2g.end(), [&](int a, int b) {
+                if (coloring[a] != coloring[b]) return coloring[a] < coloring[b];
+                return key[a] < key[b];
+            });
+        }
+    }
     c->g2i.resize(n);
     for (int q = 0; q < n; q++) c->g2i[c->i2g[q]] = q;
     // processing order: storage ids sorted by colour (stable => storage order inside a colour)
     std::vector<int> psite(n), pof(n);   // psite[p] = storage id of processing site p; pof = inverse
-    std::iota(psite.begin(), psite.end(), 0);
     // (owned sites colour by colour -- inside a colour of a sharded field the boundary sites, i.e. those some peer ghosts, come
     // first so that their tiles run, and push their values to the peers, before the interior tiles; then the ghost sites)
     std::vector<unsigned char> is_boundary(n, 0);   // by reference id
@@ -1108,13 +1117,16 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
             REQUIRE(ref >= 0 && ref < n && sh->owned[ref], "send_site[%d] is not an owned local site", k + 1);
             is_boundary[ref] = 1;
         }
-    std::stable_sort(psite.begin(), psite.end(), [&](int a, int b) {
-        const int ra = c->i2g[a], rb = c->i2g[b];
-        const bool ga = is_ghost(ra), gb = is_ghost(rb);
-        if (ga != gb) return gb;
-        if (coloring[ra] != coloring[rb]) return coloring[ra] < coloring[rb];
-        return is_boundary[ra] > is_boundary[rb];
-    });
+    {   // stable counting sort of the storage ids by bucket = (ghost, colour, interior)
+        auto bucket = [&](int q) {
+            const int ref = c->i2g[q];
+            return (is_ghost(ref) ? 2 * K : 0) + 2 * (coloring[ref] - 1) + (is_boundary[ref] ? 0 : 1);
+        };
+        std::vector<int> start((size_t)4 * K + 1, 0);
+        for (int q = 0; q < n; q++) start[bucket(q) + 1]++;
+        for (int b = 0; b < 4 * K; b++) start[b + 1] += start[b];
+        for (int q = 0; q < n; q++) psite[start[bucket(q)]++] = q;
+    }
     for (int p = 0; p < n; p++) pof[psite[p]] = p;
     c->cstart.assign(K + 1, 0);
     c->gstart.assign(K + 1, 0);
@@ -1140,17 +1152,19 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     // ---- row structure in storage numbering ----
     const int ld = c->ld;
     std::vector<int> nn((size_t)ld * M, -1);
+    std::vector<unsigned char> is_partial(n, 0);
+#pragma omp parallel for schedule(static)
     for (int q = 0; q < n; q++) {
         const int i = c->i2g[q];
-        bool partial = false;
         for (int j = 0; j < M; j++) {
             const int v = NNarray[(size_t)i + (size_t)n * j];
-            if (v == NNGP_NA_INT) partial = true;
+            if (v == NNGP_NA_INT) is_partial[q] = 1;
             else nn[(size_t)j * ld + q] = c->g2i[v - 1];
         }
-        if (partial) c->partial_rows.push_back(q);
     }
+    for (int q = 0; q < n; q++) if (is_partial[q]) c->partial_rows.push_back(q);
     std::vector<double> locs_int((size_t)n * d);
+#pragma omp parallel for schedule(static)
     for (int q = 0; q < n; q++)
         for (int k = 0; k < d; k++) locs_int[(size_t)q * d + k] = locs[(size_t)c->i2g[q] + (size_t)n * k];
     phase("row structure");
