@@ -35,6 +35,9 @@ namespace nngp {
 // needs the same lock is a deadlock.  Ask for eager loading before this library makes its first CUDA call (no effect, and no
 // harm, when the process has already initialised CUDA: then there is one context per process and nothing to deadlock with).
 static const int g_eager_loading = (setenv("CUDA_MODULE_LOADING", "EAGER", 0), 0);
+// ... which comes too late when the host process initialised CUDA before this library was loaded (e.g. a Python process that
+// asked torch.cuda.is_available() first): the loading mode is fixed at cuInit.  preload_device_code() (below, after the kernels
+// are declared) then loads every kernel of this library explicitly before contexts that wait for each other are connected.
 
 static std::mutex g_err_mu;
 static char g_err[1024] = "";
@@ -114,6 +117,39 @@ static void nccl_load() {
             throw nngp::NcclFail();                                                                            \
         }                                                                                                      \
     } while (0)
+
+// Loads every kernel of this library on the current device now (driver API, resolved with dlopen so that the library still
+// loads on a machine without a driver): cuModuleEnumerateFunctions + cuFuncLoad over the module that holds the kernels
+// (CUDA >= 12.4).  A no-op when the driver is too old; eager module loading (above) is then the only protection.
+static void preload_device_code(int device) {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64 || done[device]) return;
+    done[device] = true;
+    void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    typedef int (*GetModuleFn)(void **, void *);
+    typedef int (*CountFn)(unsigned int *, void *);
+    typedef int (*EnumFn)(void **, unsigned int, void *);
+    typedef int (*LoadFn)(void *);
+    GetModuleFn get_module = (GetModuleFn)dlsym(h, "cuFuncGetModule");
+    CountFn count = (CountFn)dlsym(h, "cuModuleGetFunctionCount");
+    EnumFn enumerate = (EnumFn)dlsym(h, "cuModuleEnumerateFunctions");
+    LoadFn load = (LoadFn)dlsym(h, "cuFuncLoad");
+    if (!get_module || !count || !enumerate || !load) return;
+    cudaFunction_t f = nullptr;
+    if (cudaGetFuncBySymbol(&f, (const void *)fill_u64_kernel) != cudaSuccess || !f) { cudaGetLastError(); return; }
+    void *mod = nullptr;
+    if (get_module(&mod, (void *)f) != 0 || !mod) return;
+    unsigned int nf = 0;
+    if (count(&nf, mod) != 0 || nf == 0) return;
+    std::vector<void *> fs(nf, nullptr);
+    if (enumerate(fs.data(), nf, mod) != 0) return;
+    int loaded = 0;
+    for (void *fn : fs) if (fn && load(fn) == 0) loaded++;
+    if (std::getenv("NNGP_VERBOSE")) std::fprintf(stderr, "[nngp_b200] device %d: %d / %u kernels loaded ahead of use\n", device, loaded, nf);
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // context
@@ -1758,6 +1794,7 @@ void nngp_shard_connect_local(const int *ctx_ids, const int *world, int *status)
     for (int g = 0; g < W; g++) {
         Ctx *c = cs[g];
         use(c);
+        preload_device_code(c->device);   // members wait for each other inside kernels: no lazy module load may happen from now on
         std::vector<int> base((size_t)c->K * W, 0);
         for (int h = 0; h < W; h++) {
             c->peers.area[h] = cs[h]->p2p_area;
