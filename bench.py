@@ -704,7 +704,11 @@ def main():
     ap.add_argument("--no-chain", action="store_true")
     ap.add_argument("--mode", default="auto", choices=["auto", "single", "sharded"])
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="sharded mode: halo transport")
+    ap.add_argument("--range", dest="range_", type=float, default=None, help="covariance range (default 0.05; BASELINE config 4 is run with 0.02)")
     a = ap.parse_args()
+    if a.range_ is not None:
+        global RANGE
+        RANGE = a.range_
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.impl == "reference":
         run_reference(a)

@@ -1070,6 +1070,7 @@ struct ShardColour {
     int n_tiles, n_btiles;        // tiles of the colour on this rank; the first n_btiles hold its boundary sites
     int g0, g1;                   // this colour's ghost sites: [g0, g1) of the receive order
     int col;
+    int ghost_first;              // 1: the ghost CTAs lead the grid (default); 0: they close it (comparison)
 };
 
 // Ghost CTAs of the sweep kernel (blockIdx.x >= n_tiles), one warp per ghost site: load the site's local column (static), wait
@@ -1084,7 +1085,8 @@ __device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const Sh
     const int warps = (int)(blockDim.x >> 5), lane = threadIdx.x & 31;
     const int n_gcta = (int)gridDim.x - cl.n_tiles;
     bool first = true;
-    for (int k = cl.g0 + ((int)blockIdx.x - cl.n_tiles) * warps + (int)(threadIdx.x >> 5); k < cl.g1; k += n_gcta * warps) {
+    const int gcta = cl.ghost_first ? (int)blockIdx.x : (int)blockIdx.x - cl.n_tiles;
+    for (int k = cl.g0 + gcta * warps + (int)(threadIdx.x >> 5); k < cl.g1; k += n_gcta * warps) {
         const int p = sc.gsite[k];
         const int sq = psite[p];
         const int e0 = colptr[p], e1 = colptr[p + 1];
@@ -1156,13 +1158,17 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
     __shared__ double sbc[2];
     const int tid = threadIdx.x;
     if (PDL && !LATE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (SHARD && (int)blockIdx.x >= cl.n_tiles) {
+    // SHARD: the ghost CTAs lead the grid (CTAs are dispatched in index order: they are resident, with their columns loaded,
+    // when the peers' values land -- at the end of the grid they only started after a full wave of tiles had drained)
+    const int n_gcta = SHARD ? (int)gridDim.x - cl.n_tiles : 0;
+    if (SHARD && (cl.ghost_first ? (int)blockIdx.x < n_gcta : (int)blockIdx.x >= cl.n_tiles)) {
         shard_ghost_apply<PDL>(sc, cl, colptr, crow, valT, psite, field, r);
         return;
     }
-    const bool btile = SHARD && (int)blockIdx.x < cl.n_btiles;
+    const int bx = (SHARD && cl.ghost_first) ? (int)blockIdx.x - n_gcta : (int)blockIdx.x;
+    const bool btile = SHARD && bx < cl.n_btiles;
     const unsigned long long epoch = btile ? *reinterpret_cast<volatile unsigned long long *>(sc.state) : 0ull;
-    const int4 tile = tiles[blockIdx.x];
+    const int4 tile = tiles[bx];
     const int s0 = tile.x, s1 = tile.y, e0 = tile.z, e1 = tile.w;
     const SweepParams sp = *spp;
     if (e1 - e0 > ECAP) {   // a single site whose column does not fit the tile: whole-CTA reduction
@@ -1190,7 +1196,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
         for (int e = e0 + tid; e < e1; e += THREADS) r[crow[e]] += valT[e] * delta;
         return;
     }
-    const unsigned char *tloc = cloc + (size_t)(tile_base + blockIdx.x) * ECAP;   // this tile's local site ids (255 = padding)
+    const unsigned char *tloc = cloc + (size_t)(tile_base + bx) * ECAP;   // this tile's local site ids (255 = padding)
     const unsigned long long pol = HINT ? l2_evict_first_policy() : 0ull;
     const unsigned long long keep = HINT >= 2 ? l2_evict_last_policy() : 0ull;
     double val[EPT], rr[EPT];

@@ -226,6 +226,12 @@ struct Ctx {
     int solve_ctas_per_sm = 1;             // window of the sync-free solve = n_sm * this * 256 rows
     int solve_window_ctas = 0;             // if > 0: absolute number of CTAs (overrides the per-SM setting)
     int solve_sleep_ns = 0;                // back-off between polls
+    // sharded sweep: at most this many ghost CTAs (4 ghost sites in flight each) per colour launch, placed at the end of the grid (0)
+    // or at its head (1).  2 GPUs x 1M sites, m = 10 (profiles/r02_shard_explore_2gpu.txt): 32 CTAs 231 us, 96: 194, 148: 186 (one
+    // round of polls instead of three); at the head of the grid 194 us -- the spinning CTAs take tile slots of the first wave
+    // 8 GPUs x 1M sites (profiles/r02_shard_explore_8gpu.txt): 32 CTAs 309 us, 74: 241, 148: 215, 296: 202, 592: 202
+    int shard_ghost_ctas = 296;
+    int shard_ghost_first = 0;
 
     // device structure
     DevBuf<int> d_psite, d_gid, d_i2g, d_g2i, d_nn, d_colptr, d_crow, d_csrc, d_zpos, d_lvl_rows, d_lvl_ptr, d_lm, d_optr, d_oidx, d_cstart,
@@ -646,7 +652,8 @@ static int launch_sweep_colors(Ctx *c) {
             cl.g1 = c->recv_ptr[(size_t)(col + 1) * W];
             cl.col = col;
             const int ng = cl.g1 - cl.g0;
-            if (ng > 0) grid += std::min(32, (ng + 3) / 4);   // ghost CTAs: one warp per ghost site, 4 warps per CTA
+            cl.ghost_first = c->shard_ghost_first;
+            if (ng > 0) grid += std::min(c->shard_ghost_ctas, (ng + 3) / 4);   // ghost CTAs: one warp per ghost site, 4 warps per CTA
         }
         if (grid == 0) continue;
         const bool pdl = c->sweep_variant != 2 && !(c->sharded && !fused_halo);
@@ -1480,6 +1487,8 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         case NNGP_OPT_COMMIT_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "commit variant must be 0..1"); c->commit_variant = *value; break;
         case NNGP_OPT_SOLVE_WINDOW_CTAS: REQUIRE(*value >= 0 && *value <= 4096, "solve window must be 0..4096 CTAs"); c->solve_window_ctas = *value; break;
         case NNGP_OPT_SOLVE_LEVEL_COPY: c->level_copy = (*value != 0); c->have_factor[0] = c->have_factor[1] = false; c->committed = false; break;
+        case NNGP_OPT_SHARD_GHOST_CTAS: REQUIRE(*value >= 1 && *value <= 1024, "ghost CTAs must be 1..1024"); c->shard_ghost_ctas = *value; if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; } break;
+        case NNGP_OPT_SHARD_GHOST_FIRST: c->shard_ghost_first = (*value != 0); if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; } break;
         case NNGP_OPT_SOLVE_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "solve sleep must be 0..100000 ns"); c->solve_sleep_ns = *value; break;
         default: REQUIRE(false, "unknown option key %d", *key);
     }

@@ -196,6 +196,8 @@ void nngp_host_shard_plan_get(const int *plan_id, double *locs, int *NNarray, in
 #define NNGP_OPT_SOLVE_LEVEL_COPY 6  /* 1 = the factor build also writes the factor in the triangular solve's row order, so that the solve reads coalesced (default); 0 = off (comparison; factors must be rebuilt after switching) */
 #define NNGP_OPT_COMMIT_VARIANT 8     /* accept-branch transposition: 0 = tiled, blocked reduction (default), 1 = thread per column */
 #define NNGP_OPT_MATERN_TABLE 9       /* Matern families: 1 = per-build interpolation table of the kernel (default), 0 = K_nu per pair */
+#define NNGP_OPT_SHARD_GHOST_CTAS 11  /* sharded sweep (peer-to-peer): at most this many ghost CTAs per colour launch, 4 ghost sites in flight each (default 296) */
+#define NNGP_OPT_SHARD_GHOST_FIRST 12 /* ... 0 = at the end of the grid (default); 1 = at its head, resident before the peers' values land (measured slower) */
 #define NNGP_OPT_LOGLIK_VARIANT 10    /* log-lik pass: 1 = plain coalesced loads (default, faster); 0 = TMA-staged shared-memory ring (cp.async.bulk + mbarrier) */
 void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);
 /* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,
