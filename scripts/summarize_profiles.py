@@ -107,7 +107,7 @@ def full(tag, rep, label):
 
 
 if __name__ == "__main__":
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     os.makedirs(OUT, exist_ok=True)
     launch_list(tag)
     import json
@@ -126,7 +126,7 @@ if __name__ == "__main__":
     sha = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
     import datetime
     with open(os.path.join(OUT, "traffic.json"), "w") as f:
-        json.dump({"source": f"{tag}: ncu, n=1M m=10 config 3 (max-min ordering)", "git_sha": sha, "when": datetime.datetime.utcnow().isoformat() + "Z",
+        json.dump({"source": f"{tag}: ncu, n=1M m=10 config 3 (max-min ordering)", "git_sha": sha, "when": datetime.datetime.now(datetime.timezone.utc).isoformat(),
                    "how": "dram__bytes_read.sum + dram__bytes_write.sum per capture; gibbs_sweep_full = the K colour launches of ONE warm sweep (--cache-control none); "
                           "the library that was profiled is the one built from git_sha (scripts/profile_run.sh ran the plain bench first)",
                    "bytes": traffic}, f, indent=1)
