@@ -37,17 +37,19 @@ struct CovConst {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// Matern kernel table.  Inside one factor build the smoothness nu is fixed, so  q(x) = normcon * x^nu * K_nu(x) * e^x  is a
-// fixed smooth function of the scaled distance x; evaluating K_nu directly (Temme series / continued fraction, ~2.7 k FP64
-// instructions per call, 55 calls per row at m = 10) made the Matern factor build 26x slower than the exponential one.
-// The table holds, for every binary octave [2^e, 2^(e+1)), e in [MT_EMIN, MT_EMAX), MT_S sub-intervals (uniform in the
-// mantissa) with a degree-7 Newton interpolant on Chebyshev nodes.  The segment and the local coordinate come straight from
-// the exponent / mantissa bits of x; the kernel value is p(u) * exp(-x).  Interpolation error < 1e-13 relative (checked
-// against scipy's kve and, through the factor parity tests, against std::cyl_bessel_k).  Outside the table range the exact
-// routine is used.
+// Matern kernel table.  Inside one factor build the smoothness nu is fixed, so the kernel is a fixed smooth function of the scaled
+// distance; evaluating K_nu directly (Temme series / continued fraction, ~2.7 k FP64 instructions per call, 55 calls per row at
+// m = 10) made the Matern factor build 26x slower than the exponential one.  The table is indexed by the SQUARED scaled distance
+// s = x^2 -- what the factor kernels have at hand, so no square root is taken per pair -- and holds, for every binary octave
+// [2^e, 2^(e+1)) of s, e in [MT_EMIN, MT_EMAX), MT_S sub-intervals (uniform in the mantissa) with a degree-7 Newton interpolant on
+// Chebyshev nodes of   g(s) = normcon x^nu K_nu(x)            for s < 4  (the kernel value itself: no exp per pair either), and of
+//                      g(s) = normcon x^nu K_nu(x) e^x        for s >= 4 (multiplied by exp(-x) at look-up; rare among neighbours).
+// The segment and the local coordinate come straight from the exponent / mantissa bits of s.  Interpolation error < 1e-13
+// relative (checked through the factor parity tests against std::cyl_bessel_k).  Outside the table range the exact routine is used.
 // ---------------------------------------------------------------------------------------------------------------
-#define MT_EMIN (-40)
-#define MT_EMAX 10
+#define MT_EMIN (-80)
+#define MT_EMAX 20
+#define MT_ESCALED 2   /* octaves of s from here on hold the e^x-scaled kernel */
 #define MT_S 16
 #define MT_SEGS ((MT_EMAX - MT_EMIN) * MT_S)
 
@@ -62,8 +64,8 @@ __global__ void __launch_bounds__(128) matern_table_kernel(double *__restrict__ 
     const int seg = blockIdx.x * 16 + (threadIdx.x >> 3), k = threadIdx.x & 7;
     if (seg < MT_SEGS) {
         const int e = MT_EMIN + seg / MT_S, msub = seg % MT_S;
-        const double x = ldexp(1.0 + ((double)msub + mt_node(k)) / MT_S, e);
-        f[threadIdx.x] = normcon * pow(x, nu) * bessel_k_real(nu, x, true);
+        const double x = sqrt(ldexp(1.0 + ((double)msub + mt_node(k)) / MT_S, e));
+        f[threadIdx.x] = normcon * pow(x, nu) * bessel_k_real(nu, x, e >= MT_ESCALED);
     }
     __syncthreads();
     if (seg < MT_SEGS && k == 0) {
@@ -129,8 +131,9 @@ __device__ __forceinline__ double fast_exp_nonpos(double x) {
     return x < -708.0 ? 0.0 : p * scale;
 }
 
-__device__ __forceinline__ double matern_from_table(const double *__restrict__ tab, double x, double &out_ok) {
-    const long long bits = __double_as_longlong(x);
+// s = squared scaled distance (> 0)
+__device__ __forceinline__ double matern_from_table(const double *__restrict__ tab, double s, double &out_ok) {
+    const long long bits = __double_as_longlong(s);
     const int e = (int)((bits >> 52) & 0x7ff) - 1023;
     if (e < MT_EMIN || e >= MT_EMAX) { out_ok = 0.0; return 0.0; }
     const int seg = (e - MT_EMIN) * MT_S + (int)((bits >> 48) & 0xF);
@@ -148,7 +151,7 @@ __device__ __forceinline__ double matern_from_table(const double *__restrict__ t
     p = p * (u - mt_node(1)) + c01.y;
     p = p * (u - mt_node(0)) + c01.x;
     out_ok = 1.0;
-    return p * fast_exp_nonpos(-x);
+    return e >= MT_ESCALED ? p * fast_exp_nonpos(-fast_sqrt_nonneg(s)) : p;
 }
 
 // parameters of the sweep that change between launches live in device memory so that the captured graph is static
@@ -243,17 +246,59 @@ __global__ void transform_locs_kernel(const double *__restrict__ locs /* [n][d] 
     }
 }
 
-template <bool MATERN>
-__device__ __forceinline__ double kernel_value_fast(const CovConst &cc, double d2) {
-    if (!MATERN) return cc.variance * fast_exp_nonpos(-fast_sqrt_nonneg(d2));
+// the shared-memory copy of the Matern table (octaves 2^-16 .. 2^6 of the scaled distance, coefficient-major: 22.5 KB)
+#define MTS_E0 (-26)
+#define MTS_E1 6
+#define MTS_SEGS ((MTS_E1 - MTS_E0) * MT_S)
+
+__device__ __forceinline__ double matern_from_smem(const double *__restrict__ tab_s, double s, double &out_ok) {
+    const long long bits = __double_as_longlong(s);
+    const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    if (e < MTS_E0 || e >= MTS_E1) { out_ok = 0.0; return 0.0; }   // the caller falls back to matern_slow (global table / exact)
+    const int seg = (e - MTS_E0) * MT_S + (int)((bits >> 48) & 0xF);
+    const long long mant = (bits & 0x000FFFFFFFFFFFFFll) | 0x3FF0000000000000ll;
+    const double u = (__longlong_as_double(mant) - __longlong_as_double(mant & (long long)0xFFFF000000000000ull)) * 16.0;
+    // layout [4][MTS_SEGS] of coefficient PAIRS: four 128-bit loads per look-up.  ncu with eight 64-bit loads from an [8][MTS_SEGS]
+    // layout: 5.6 wavefronts per load (the lanes of a warp sit in ~30 different segments), the L1 data pipe 72 % busy and the
+    // top limiter of the Matern build; pairs halve the number of loads at ~7 wavefronts each
+    const double2 *t2 = reinterpret_cast<const double2 *>(tab_s);
+    const double2 c67 = t2[3 * MTS_SEGS + seg], c45 = t2[2 * MTS_SEGS + seg], c23 = t2[1 * MTS_SEGS + seg], c01 = t2[seg];
+    double p = c67.y;
+    p = p * (u - mt_node(6)) + c67.x;
+    p = p * (u - mt_node(5)) + c45.y;
+    p = p * (u - mt_node(4)) + c45.x;
+    p = p * (u - mt_node(3)) + c23.y;
+    p = p * (u - mt_node(2)) + c23.x;
+    p = p * (u - mt_node(1)) + c01.y;
+    p = p * (u - mt_node(0)) + c01.x;
+    out_ok = 1.0;
+    return e >= MT_ESCALED ? p * fast_exp_nonpos(-fast_sqrt_nonneg(s)) : p;
+}
+
+// Everything that is not a hit in the shared-memory table.  NOT inlined: the register-resident kernels evaluate the kernel at 55
+// (m = 10) to 210 (m = 20) unrolled sites, and with the global-table lookup, pow() and the Bessel routine inlined at each of them the
+// Matern build of m = 10 was 20.8 k SASS instructions against 4.7 k for the exponential one -- 330 KB of code, far beyond the
+// instruction cache, which is what made it 3x slower (cuobjdump; profiles/r02_matern_factor.txt).
+__device__ __noinline__ double matern_slow(const CovConst &cc, double d2) {
     if (d2 == 0.0) return cc.variance;
-    const double dist = fast_sqrt_nonneg(d2);
     if (cc.mtab) {
         double ok;
-        const double v = matern_from_table(cc.mtab, dist, ok);
+        const double v = matern_from_table(cc.mtab, d2, ok);
         if (ok != 0.0) return v;
     }
+    const double dist = sqrt(d2);
     return cc.normcon * pow(dist, cc.smooth) * bessel_k_real(cc.smooth, dist);
+}
+
+template <bool MATERN>
+__device__ __forceinline__ double kernel_value_fast(const CovConst &cc, double d2, const double *__restrict__ tab_s = nullptr) {
+    if (!MATERN) return cc.variance * fast_exp_nonpos(-fast_sqrt_nonneg(d2));
+    if (tab_s) {   // d2 == 0 (coincident sites) misses the table like any other out-of-range argument
+        double ok;
+        const double v = matern_from_smem(tab_s, d2, ok);
+        if (ok != 0.0) return v;
+    }
+    return matern_slow(cc, d2);
 }
 
 template <bool MATERN>
@@ -262,7 +307,7 @@ __device__ __forceinline__ double kernel_value(const CovConst &cc, double dist) 
     if (dist == 0.0) return cc.variance;
     if (cc.mtab) {
         double ok;
-        const double v = matern_from_table(cc.mtab, dist, ok);
+        const double v = matern_from_table(cc.mtab, dist * dist, ok);
         if (ok != 0.0) return v;
     }
     return cc.normcon * pow(dist, cc.smooth) * bessel_k_real(cc.smooth, dist);
@@ -333,6 +378,18 @@ template <int M, int DT, bool MATERN, int MINB = 3, bool FAST = true, bool PARTI
 __global__ void __launch_bounds__(128, MINB) vecchia_factor_reg_kernel(const int *__restrict__ nn, const double *__restrict__ tl,
                                                                  double *__restrict__ linv, int n, int ld, CovConst cc,
                                                                  int *__restrict__ n_bad) {
+    // Matern: the interpolation table moves to shared memory, coefficient-major.  The lanes of a warp evaluate the same pair (a, b) of
+    // different rows -- similar distances, a handful of table segments -- but each global 64-byte segment read cost up to 32 L1
+    // wavefronts per 128-bit load (ncu, m = 20: 340 M sectors of table gathers, 1.65 of the 2.55 ms per 500 k rows)
+    __shared__ __align__(16) double tab_s[MATERN ? 8 * MTS_SEGS : 2];
+    const bool smem_tab = MATERN && FAST && cc.mtab != nullptr;
+    if (smem_tab) {
+        for (int i = threadIdx.x; i < 8 * MTS_SEGS; i += blockDim.x) {   // tab_s[((k / 2) * MTS_SEGS + segment) * 2 + (k & 1)] = coefficient k
+            const int kk = i / (2 * MTS_SEGS), sg = (i >> 1) % MTS_SEGS, k = 2 * kk + (i & 1);
+            tab_s[i] = cc.mtab[(size_t)(sg + (MTS_E0 - MT_EMIN) * MT_S) * 8 + k];
+        }
+        __syncthreads();
+    }
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     int idx[M];
@@ -363,6 +420,28 @@ __global__ void __launch_bounds__(128, MINB) vecchia_factor_reg_kernel(const int
     // and 11 square roots are a third.  One reciprocal square root per pivot replaces them: inv[a] = rsqrt(pivot),
     // L[a][a] = pivot * inv[a], L[a][b] = s * inv[b], x[a] = s * inv[a]  (<= 2 ulp per operation away from the oracle's
     // sqrt / divide; the parity tests bound the effect on a factor row at 1e-10).
+    // Matern: the M(M-1)/2 kernel values come from a ROLLED loop (coordinates and values dynamically indexed, i.e. in local memory,
+    // L1-resident) instead of M(M-1)/2 unrolled copies of the table lookup: 120 instructions per site made the kernel 11 k (m = 10)
+    // to 35 k (m = 20) instructions long, several times the instruction cache.
+    constexpr bool ROLLCOV = MATERN && FAST && (M > 11);
+    double Kv[ROLLCOV ? M * (M - 1) / 2 : 1];
+    if (ROLLCOV) {
+        const double *tabp = smem_tab ? tab_s : nullptr;
+        int e = 0;
+#pragma unroll 1
+        for (int a = 1; a < M; a++) {
+#pragma unroll 1
+            for (int b = 0; b < a; b++) {
+                double d2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < DT; c++) {
+                    const double t = p[a][c] - p[b][c];
+                    d2 += t * t;
+                }
+                Kv[e++] = kernel_value_fast<MATERN>(cc, d2, tabp);
+            }
+        }
+    }
     double L[M * (M + 1) / 2];
     double inv[M];
     bool ok = true;
@@ -373,6 +452,8 @@ __global__ void __launch_bounds__(128, MINB) vecchia_factor_reg_kernel(const int
             double s;
             if (a == b) {
                 s = cc.variance + cc.nugget;
+            } else if (ROLLCOV) {
+                s = Kv[a * (a - 1) / 2 + b];
             } else {
                 double d2 = 0.0;
 #pragma unroll
@@ -380,7 +461,7 @@ __global__ void __launch_bounds__(128, MINB) vecchia_factor_reg_kernel(const int
                     const double t = p[a][c] - p[b][c];
                     d2 += t * t;
                 }
-                s = FAST ? kernel_value_fast<MATERN>(cc, d2) : kernel_value<MATERN>(cc, sqrt(d2));
+                s = FAST ? kernel_value_fast<MATERN>(cc, d2, smem_tab ? tab_s : nullptr) : kernel_value<MATERN>(cc, sqrt(d2));
             }
 #pragma unroll
             for (int k = 0; k < b; k++) s -= L[a * (a + 1) / 2 + k] * L[b * (b + 1) / 2 + k];
@@ -411,6 +492,173 @@ __global__ void __launch_bounds__(128, MINB) vecchia_factor_reg_kernel(const int
         }
     }
     if (!ok) atomicAdd(n_bad, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Vecchia factor build, one WARP per row (m = 20: BASELINE config 4).  The 231-entry triangle of a 21 x 21 block does not fit the
+// registers of one thread: ncu of the thread-per-row kernel at M = 21 (profiles/r02_matern_m20_factor_before.txt) shows 214
+// registers, 8 warps per SM, 23.5 M local-memory load instructions (316 M sectors, half of them L1 misses) and, for the Matern
+// family, 340 M sectors of divergent table gathers -- 2.5 ms per 500 k rows against 0.9 ms exponential.  Here lane r owns point r
+// and row r of the triangle (M registers):
+//   * covariances: the M(M-1)/2 pairs are dealt round-robin to the 32 lanes (coordinates by shuffle), staged through a per-warp
+//     shared tile with an odd leading dimension, and read back as rows;
+//   * right-looking Cholesky, fully unrolled: step k broadcasts the pivot (one rsqrt per step, as in the thread-per-row kernel)
+//     and column k by shuffle; entry (a, b) receives its updates in the order k = 0 .. b-1, the same sequence of FMAs as the
+//     row-by-row form of the oracle;
+//   * last row of L^-1 = [-b', 1] / sqrt(F) with L_nn' b = u: the factor is transposed through the shared tile so that lane a
+//     holds column a, then M-1 steps of (broadcast b_k, one FMA);
+//   * the Matern interpolation table (octaves 2^-16 .. 2^6 of the scaled distance: 22.5 KB, coefficient-major so that the lanes
+//     of a warp hit different banks) lives in shared memory; outside that range the global table / the exact routine is used;
+//   * neighbour ids come in and factor rows go out through shared staging of 32 consecutive rows, so that global accesses are
+//     coalesced although a warp works on one row.
+// Rows with fewer than m neighbours (at most m of them) take factor_row_generic on lane 0.
+// ---------------------------------------------------------------------------------------------------------------
+template <int M, int DT, bool MATERN>
+__global__ void __launch_bounds__(256, 2) vecchia_factor_warp_kernel(const int *__restrict__ nn, const double *__restrict__ tl,
+                                                                     double *__restrict__ linv, int n, int ld, CovConst cc,
+                                                                     int *__restrict__ n_bad) {
+    constexpr int WARPS = 8, RPB = 32;          // 32 consecutive rows per block round, 4 per warp
+    constexpr int LDT = M | 1;                  // odd leading dimension of the per-warp tile
+    constexpr int E = M * (M - 1) / 2;          // off-diagonal pairs
+    constexpr int ROUNDS = (E + 31) / 32;
+    extern __shared__ __align__(16) double smem[];
+    double *tab_s = smem;                                                   // [8][MTS_SEGS]   (MATERN only)
+    double *tiles = smem + (MATERN ? 8 * MTS_SEGS : 0);                     // [WARPS][M * LDT]
+    double *sout = tiles + WARPS * M * LDT;                                 // [M][RPB]
+    int *snn = reinterpret_cast<int *>(sout + M * RPB);                     // [M][RPB]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    double *S = tiles + w * (M * LDT);
+    const bool use_tab = MATERN && cc.mtab != nullptr;
+    if (use_tab) {
+        for (int i = tid; i < 8 * MTS_SEGS; i += 256) {
+            const int kk = i / (2 * MTS_SEGS), sg = (i >> 1) % MTS_SEGS, k = 2 * kk + (i & 1);
+            tab_s[i] = cc.mtab[(size_t)(sg + (MTS_E0 - MT_EMIN) * MT_S) * 8 + k];
+        }
+    }
+    // the pair (a, b), b < a, that this lane evaluates in each round: the same for every row
+    int pa_[ROUNDS], pb_[ROUNDS];
+#pragma unroll
+    for (int t = 0; t < ROUNDS; t++) {
+        const int e = t * 32 + lane;
+        int a = (int)((1.0f + sqrtf(8.0f * (float)e + 1.0f)) * 0.5f);
+        if (a * (a - 1) / 2 > e) a--;
+        if (a * (a + 1) / 2 <= e) a++;
+        pa_[t] = (e < E) ? a : 0;
+        pb_[t] = (e < E) ? e - a * (a - 1) / 2 : 0;
+    }
+    const double diag = cc.variance + cc.nugget;
+    for (int base = blockIdx.x * RPB; base < n; base += gridDim.x * RPB) {
+        __syncthreads();   // the previous round's output has been written, its neighbour ids are no longer needed
+        for (int i = tid; i < M * RPB; i += 256) {
+            const int j = i / RPB, q = base + (i % RPB);
+            snn[i] = q < n ? nn[(size_t)j * ld + q] : -1;
+        }
+        __syncthreads();
+        for (int rl = w; rl < RPB; rl += WARPS) {
+            const int q = base + rl;
+            if (q >= n) break;
+            const int id = lane < M ? snn[(M - 1 - lane) * RPB + rl] : 0;   // point `lane` of the block: neighbours farthest first, self last
+            if (!__all_sync(0xffffffffu, id >= 0)) {   // one of the first m rows of the ordering
+                if (lane == 0) {
+                    factor_row_generic<24, MATERN>(q, nn, tl, linv, ld, M, cc, n_bad);
+                    for (int j = 0; j < M; j++) sout[j * RPB + rl] = linv[(size_t)j * ld + q];
+                }
+                __syncwarp();
+                continue;
+            }
+            double p[DT];
+            if (lane < M) {
+                const double *src = tl + (size_t)id * DT;
+                if (DT == 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(src);
+                    p[0] = v.x;
+                    p[1] = v.y;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < DT; c++) p[c] = src[c];
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < DT; c++) p[c] = 0.0;
+            }
+            // ---- covariances ----
+#pragma unroll
+            for (int t = 0; t < ROUNDS; t++) {
+                double d2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < DT; c++) {
+                    const double u = __shfl_sync(0xffffffffu, p[c], pa_[t]) - __shfl_sync(0xffffffffu, p[c], pb_[t]);
+                    d2 += u * u;
+                }
+                if (t * 32 + lane < E) {
+                    double v;
+                    if (!MATERN) {
+                        v = cc.variance * fast_exp_nonpos(-fast_sqrt_nonneg(d2));
+                    } else {
+                        v = kernel_value_fast<true>(cc, d2, use_tab ? tab_s : nullptr);
+                    }
+                    S[pa_[t] * LDT + pb_[t]] = v;
+                }
+            }
+            __syncwarp();
+            double A[M];
+#pragma unroll
+            for (int c = 0; c < M; c++) A[c] = (c < lane && lane < M) ? S[lane * LDT + c] : (c == lane ? diag : 0.0);
+            // ---- right-looking Cholesky: after step k, A[k] of lane r >= k is L[r][k] ----
+            bool ok = true;
+            double myinv = 0.0;
+#pragma unroll
+            for (int k = 0; k < M; k++) {
+                const double dk = __shfl_sync(0xffffffffu, A[k], k);
+                ok = ok && (dk > 0.0);
+                const double ik = rsqrt(dk);
+                myinv = (lane == k) ? ik : myinv;
+                A[k] = (lane == k ? dk : A[k]) * ik;
+#pragma unroll
+                for (int c = 0; c < M; c++) {   // constant trip count (c > k folds at compile time): a triangular bound was left rolled, A[] in local memory
+                    if (c > k) {
+                        const double lc = __shfl_sync(0xffffffffu, A[k], c);
+                        A[c] = (lane >= c) ? fma(-A[k], lc, A[c]) : A[c];
+                    }
+                }
+            }
+            // ---- transpose through the tile: lane a gets column a, C[k] = L[k][a] (reusing A) ----
+            __syncwarp();
+            if (lane < M) {
+#pragma unroll
+                for (int c = 0; c < M; c++)
+                    if (c <= lane) S[lane * LDT + c] = A[c];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < M; k++) A[k] = (k > lane && lane < M) ? S[k * LDT + lane] : 0.0;
+            __syncwarp();
+            // ---- L_nn' b = u (u = row M-1 of L), then x = [-b, 1] / sqrt(F) ----
+            double tacc = A[M - 1], mine = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < M - 1; kk++) {
+                const int k = M - 2 - kk;
+                const double bk = __shfl_sync(0xffffffffu, tacc * myinv, k);
+                mine = (lane == k) ? bk : mine;
+                tacc = (lane < k) ? fma(-A[k], bk, tacc) : tacc;
+            }
+            const double ilast = __shfl_sync(0xffffffffu, myinv, M - 1);
+            if (lane < M) sout[(M - 1 - lane) * RPB + rl] = (lane == M - 1) ? ilast : -mine * ilast;
+            if (!ok && lane == 0) atomicAdd(n_bad, 1);
+        }
+        __syncthreads();
+        for (int i = tid; i < M * RPB; i += 256) {
+            const int j = i / RPB, q = base + (i % RPB);
+            if (q < n) {
+                const double v = sout[i];
+                linv[(size_t)j * ld + q] = v;
+                if (cc.linv_lvl) {
+                    const int t = cc.lpos[q];
+                    if (t >= 0) cc.linv_lvl[(size_t)j * cc.nsl + t] = v;
+                }
+            }
+        }
+    }
 }
 
 // Generic factor build: any M <= MCAP, any DT <= 4, rows listed in `rows` (or all rows when rows == nullptr); handles

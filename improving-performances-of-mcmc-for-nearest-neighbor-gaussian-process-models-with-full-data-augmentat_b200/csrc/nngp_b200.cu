@@ -268,6 +268,7 @@ struct Ctx {
     // measured slower than leaving the head to the sync-free kernel (n = 1M, m = 10, max-min: 92 levels / 5k slots 68 us in either; 125
     // levels / 25k slots 246 us against ~95 us; profiles/r02_solve_timeline.txt): off by default, NNGP_OPT_SOLVE_HEAD turns it on
     bool solve_head = false;
+    int factor_variant = 0;                // 0 = thread per row everywhere (default), 1 = warp-per-row kernel where it exists (m = 20)
     DevBuf<unsigned long long> d_solve_tl;   // development aid: per-chunk completion times of the sync-free solve
     bool solve_tl_on = false;
     double *h_pinned = nullptr;       // 64 doubles of pinned scratch for scalar results
@@ -441,7 +442,20 @@ static void launch_factor(Ctx *c, double *linv, const CovConst &cc) {
     FACTOR_CASE(6, 3)
     FACTOR_CASE(11, 2)
     FACTOR_CASE(11, 3)
-    if (!specialised && M == 21 && c->dt == 2) {   // 231-entry triangle: let ptxas use all 255 registers (spills to L1 beyond)
+    if (!specialised && M == 21 && (c->dt == 2 || c->dt == 3) && c->factor_variant == 1) {   // m = 20: one warp per row (see kernels.cuh; measured option)
+        const size_t smem = sizeof(double) * ((MATERN ? 8 * MTS_SEGS : 0) + 8 * 21 * 21 + 21 * 32) + sizeof(int) * 21 * 32;
+        const int blocks = std::max(1, std::min((n + 31) / 32, c->n_sm * 2));
+        if (c->dt == 2) {
+            CK(cudaFuncSetAttribute(vecchia_factor_warp_kernel<21, 2, MATERN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            vecchia_factor_warp_kernel<21, 2, MATERN><<<blocks, 256, smem, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
+        } else {
+            CK(cudaFuncSetAttribute(vecchia_factor_warp_kernel<21, 3, MATERN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            vecchia_factor_warp_kernel<21, 3, MATERN><<<blocks, 256, smem, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
+        }
+        LAUNCHED(c);
+        return;
+    }
+    if (!specialised && M == 21 && c->dt == 2) {   // thread per row, 231-entry triangle: all 255 registers and spills to L1 beyond (comparison)
         vecchia_factor_reg_kernel<21, 2, MATERN, 1><<<grd, blk, 0, c->stream>>>(c->d_nn.p, c->d_tl.p, linv, n, ld, cc, c->d_nbad.p);
         specialised = true;
     }
@@ -1560,6 +1574,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         case NNGP_OPT_SOLVE_LEVEL_COPY: c->level_copy = (*value != 0); c->have_factor[0] = c->have_factor[1] = false; c->committed = false; break;
         case NNGP_OPT_SHARD_GHOST_CTAS: REQUIRE(*value >= 1 && *value <= 1024, "ghost CTAs must be 1..1024"); c->shard_ghost_ctas = *value; if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; } break;
         case NNGP_OPT_SHARD_GHOST_FIRST: c->shard_ghost_first = (*value != 0); if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; } break;
+        case NNGP_OPT_FACTOR_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "factor variant must be 0..1"); c->factor_variant = *value; break;
         case NNGP_OPT_SOLVE_HEAD: c->solve_head = (*value != 0); break;
         case NNGP_OPT_SOLVE_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "solve sleep must be 0..100000 ns"); c->solve_sleep_ns = *value; break;
         default: REQUIRE(false, "unknown option key %d", *key);
