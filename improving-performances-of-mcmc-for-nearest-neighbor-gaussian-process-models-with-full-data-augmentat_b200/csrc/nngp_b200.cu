@@ -5,6 +5,7 @@
 // cross PCIe.  There is no CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler injects its library (one range per phase A-F)
 
 #include <algorithm>
 #include <atomic>
@@ -2347,6 +2348,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
     if (prof) { CK(cudaStreamSynchronize(c->stream)); t_last = std::chrono::steady_clock::now(); }
     for (int iter = 1; iter <= n_iter; iter++) {
         // ---- (A) ancillary :113-157 ----
+        nvtxRangePushA("nngp A ancillary covariance update");
         const double sd_anc = std::exp(.5 * logvar_anc);
         for (int k = 0; k < ns + 1; k++) innovation[k] = 0.0 + sd_anc * rs.norm_rand();
         double new_log_scale = log_scale + innovation[0];
@@ -2375,7 +2377,9 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
             if (mean_acc > .15) logvar_anc += (.4 + .05 * rs.norm_rand());
         }
         mark(0);
+        nvtxRangePop();
         // ---- (B) sufficient :165-213 ----
+        nvtxRangePushA("nngp B sufficient covariance update");
         const double sd_suf = std::exp(.5 * logvar_suf);
         for (int k = 0; k < ns + 1; k++) innovation[k] = 0.0 + sd_suf * rs.norm_rand();
         new_log_scale = log_scale + innovation[0];
@@ -2405,7 +2409,9 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
             if (mean_acc > .15) logvar_suf += (.2 + .05 * rs.norm_rand());
         }
         mark(1);
+        nvtxRangePop();
         // ---- (C) beta_0 :219-224 (no location-level regressors) ----
+        nvtxRangePushA("nngp C mean parameters");
         if (reg_q == 0) {
             op_beta0_sums(c, 0);
             fetch_scalars(c, 2);
@@ -2465,7 +2471,9 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
             op_set_beta(c, beta.data());                                         // :249 mu
         }
         mark(2);
+        nvtxRangePop();
         // ---- (D) chromatic sweeps :257-275 ----
+        nvtxRangePushA("nngp D chromatic Gibbs sweeps");
         if (rng_mode == NNGP_RNG_SUPPLIED) {
             ensure_zbuf(c, (size_t)nz * std::max(1, n_chromatic));
             zhost.resize((size_t)nz * std::max(1, n_chromatic));
@@ -2477,7 +2485,9 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
         op_sweeps(c, n_chromatic);
         c->sweep_counter += (unsigned long long)n_chromatic;
         mark(3);
+        nvtxRangePop();
         // ---- (E) noise variance :281-293 ----
+        nvtxRangePushA("nngp E noise variance");
         op_obs_sq(c, c->d_field.p, c->d_field.p, 0);
         fetch_scalars(c, 2);
         const double ssr = c->h_pinned[0];
@@ -2488,7 +2498,9 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
             }
         }
         mark(4);
+        nvtxRangePop();
         // ---- (F) records :305-311 ----
+        nvtxRangePushA("nngp F records");
         if (records_out) {
             records_out[(size_t)(iter - 1)] = beta_0;
             records_out[(size_t)(iter - 1) + (size_t)n_iter] = log_scale;
@@ -2515,6 +2527,7 @@ static void chain_run_impl(Ctx *c, const int *n_shape_, double *params_io, const
         }
         if (accept_out) { accept_out[iter - 1] = acc_anc[iter]; accept_out[n_iter + iter - 1] = acc_suf[iter]; }
         mark(5);
+        nvtxRangePop();
     }
     if (prof && n_iter > 0)
         std::fprintf(stderr, "[nngp chain profile] per iteration, us: ancillary %.1f  sufficient %.1f  mean-params %.1f  sweeps(%d) %.1f  noise %.1f  records %.1f\n",

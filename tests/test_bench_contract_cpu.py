@@ -21,12 +21,12 @@ def test_reference_arm_prints_the_contract_line():
     r = run_bench("--impl", "reference", "--n", "20000", "--steps", "2", "--warmup", "1", "--ref-procs", "2")
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["metric"] == "gibbs_sweep_plus_vecchia_loglik_per_sec" and line["unit"] == "steps/s"
+    assert line["impl"] == "reference" and line["metric"] == "gibbs_sweep_plus_vecchia_loglik_per_sec" and line["unit"] == "steps/s (1M-site blocks)"
     assert line["higher_is_better"] is True and line["dtype"] == "f64" and line["data"] == "synthetic" and line["vs_baseline"] is None
     assert line["value"] > 0 and line["steps"] == 2 and line["n_gpus"] == 1
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] == 2 and cb["value"] == line["value"] and "oracle restatement" in cb["sample"]
-    assert line["e2e"] == {"value": line["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["e2e"] == {"value": line["value"], "unit": "steps/s (1M-site blocks)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
 
 
