@@ -102,6 +102,17 @@ nngp_gibbs_sweep = function(ctx, n_sweeps, beta_0, log_scale, log_noise_variance
                           z = as.double(z), seed = as.double(seed), status = integer(1))))
 }
 
+# one step with state$params$field kept in R: n_sweeps sweeps of `field`, returns list(field = new field, ll = its Vecchia log-likelihood)
+nngp_sweep_loglik_host = function(ctx, field, n_sweeps, beta_0, log_scale, log_noise_variance, z = NULL, seed = 0)
+{
+  rng_mode = if(is.null(z)) 1L else 0L
+  if(is.null(z)) z = 0
+  res = nngp_check(.C("nngp_sweep_loglik_host", ctx_id = as.integer(ctx), n_sweeps = as.integer(n_sweeps), beta_0 = as.double(beta_0),
+                      log_scale = as.double(log_scale), log_noise_variance = as.double(log_noise_variance), rng_mode = rng_mode,
+                      z = as.double(z), seed = as.double(seed), field_io = as.double(field), ll = double(1), status = integer(1)))
+  list(field = res$field_io, ll = res$ll)
+}
+
 # initial field draw (initialize.R:201-208) with R's own rnorm stream
 nngp_field_init = function(ctx, beta_0, log_scale, z, slot = 0L)
   invisible(nngp_check(.C("nngp_field_init", ctx_id = as.integer(ctx), slot = as.integer(slot), beta_0 = as.double(beta_0), log_scale = as.double(log_scale), z = as.double(z), status = integer(1))))

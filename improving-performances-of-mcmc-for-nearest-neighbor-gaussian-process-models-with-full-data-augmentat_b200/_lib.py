@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "nngp_host_order_maxmin", "nngp_ctx_create", "nngp_ctx_destroy", "nngp_comm_unique_id", "nngp_ctx_create_sharded", "nngp_shard_p2p_export", "nngp_shard_p2p_connect", "nngp_shard_sweep_begin", "nngp_shard_sweep_colour", "nngp_shard_halo_get", "nngp_shard_halo_put", "nngp_shard_sweep_end", "nngp_ctx_set_option", "nngp_ctx_info", "nngp_solve_timeline", "nngp_factor_build",
     "nngp_factor_get", "nngp_factor_accept", "nngp_factor_commit", "nngp_precision_diag", "nngp_field_set",
     "nngp_field_get", "nngp_obs_set", "nngp_loglik", "nngp_loglik_host", "nngp_spmv", "nngp_sptmv", "nngp_sptrsv",
-    "nngp_gibbs_sweep", "nngp_ancillary_propose", "nngp_ancillary_accept", "nngp_beta0_moments", "nngp_ssr",
+    "nngp_gibbs_sweep", "nngp_sweep_loglik_host", "nngp_ancillary_propose", "nngp_ancillary_accept", "nngp_beta0_moments", "nngp_ssr",
     "nngp_field_init", "nngp_chain_run", "nngp_regressors_set", "nngp_chain_run_regressors", "nngp_records_summary", "nngp_predict_sample", "nngp_time_op", "nngp_launch_count", "nngp_host_alloc", "nngp_host_free",
     "nngp_host_spatial_blocks", "nngp_host_shard_plan_build", "nngp_host_shard_plan_get", "nngp_shard_connect_local", "nngp_shard_group_sweep",
     "nngp_shard_group_loglik", "nngp_shard_group_chain_run", "nngp_chains_run", "nngp_chains_run_regressors", "nngp_time_op_group", "nngp_fp64_peak",

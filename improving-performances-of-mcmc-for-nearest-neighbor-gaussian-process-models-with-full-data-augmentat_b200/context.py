@@ -141,6 +141,21 @@ class NNGPContext:
         return self._vec_op("nngp_sptrsv", b, slot)
 
     # ---- sampler steps
+    def sweep_loglik_host(self, field_io: np.ndarray, beta_0, log_scale, log_noise_variance, n_sweeps=1, z=None, seed=0) -> float:
+        """nngp_sweep_loglik_host: field_io (float64, C-contiguous, n values; may be pinned) is updated in place by n_sweeps sweeps;
+        returns the Vecchia log-likelihood of the new field"""
+        assert field_io.dtype == np.float64 and field_io.size == self.n and field_io.flags.c_contiguous
+        ll = C.c_double(0.0)
+        if z is None:
+            self._call("nngp_sweep_loglik_host", L.ci(n_sweeps), L.cd(beta_0), L.cd(log_scale), L.cd(log_noise_variance), L.ci(L.RNG_PHILOX),
+                       None, L.cd(seed), L.dptr(field_io), C.byref(ll))
+        else:
+            zz = L.f64(z)
+            assert zz.size == getattr(self, "n_z", self.n) * n_sweeps
+            self._call("nngp_sweep_loglik_host", L.ci(n_sweeps), L.cd(beta_0), L.cd(log_scale), L.cd(log_noise_variance), L.ci(L.RNG_SUPPLIED),
+                       L.dptr(zz), L.cd(seed), L.dptr(field_io), C.byref(ll))
+        return ll.value
+
     def gibbs_sweep(self, beta_0, log_scale, log_noise_variance, n_sweeps=1, z=None, seed=0):
         if z is None:
             self._call("nngp_gibbs_sweep", L.ci(n_sweeps), L.cd(beta_0), L.cd(log_scale), L.cd(log_noise_variance),

@@ -1819,6 +1819,46 @@ void nngp_gibbs_sweep(const int *ctx_id, const int *n_sweeps, const double *beta
     ABI_END
 }
 
+// One sampler step for a caller that keeps the field on the host: field_io goes up, n_sweeps sweeps run, the Vecchia log-likelihood of
+// the new field is taken on the device (the field is already there: nngp_field_set + nngp_gibbs_sweep + nngp_field_get +
+// nngp_loglik_host would send it over PCIe a second time), the new field comes down.
+void nngp_sweep_loglik_host(const int *ctx_id, const int *n_sweeps, const double *beta_0, const double *log_scale,
+                            const double *log_noise_variance, const int *rng_mode, const double *z, const double *seed,
+                            double *field_io, double *ll, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(n_sweeps && beta_0 && log_scale && log_noise_variance && rng_mode && field_io && ll && *n_sweeps >= 0, "nngp_sweep_loglik_host: bad argument");
+    REQUIRE(*rng_mode == NNGP_RNG_PHILOX || (*rng_mode == NNGP_RNG_SUPPLIED && z != nullptr), "nngp_sweep_loglik_host: rng_mode 0 needs z");
+    NEED(c->can_sweep, "this context was created without a colouring (all-zero coloring): it cannot run Gibbs sweeps");
+    NEED(c->have_slot(NNGP_SLOT_CURRENT) && c->have_obs, "nngp_sweep_loglik_host: factor and observations must be set first");
+    use(c);
+    if (!c->committed) op_commit(c);
+    const bool pinned = is_pinned(field_io);
+    if (pinned) {   // as upload_site_vector, without its synchronisation: the buffer is not handed back before the download below
+        CK(cudaMemcpyAsync(c->d_io.p, field_io, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+        gather_f64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_field.p, c->d_io.p, c->d_i2g.p, c->n);
+        LAUNCHED(c);
+    } else {
+        upload_site_vector(c, field_io, c->d_field.p);
+    }
+    c->have_field = true;
+    const size_t nz = (size_t)c->n_global * (size_t)std::max(1, *n_sweeps);
+    if (*rng_mode == NNGP_RNG_SUPPLIED) {
+        ensure_zbuf(c, nz);
+        CK(cudaMemcpyAsync(c->d_zbuf.p, z, sizeof(double) * nz, cudaMemcpyHostToDevice, c->stream));
+    }
+    set_sweep_params(c, *beta_0, *log_scale, *log_noise_variance, *rng_mode, seed ? *seed : 0.0);
+    refresh_r(c, *beta_0);
+    op_sweeps(c, *n_sweeps);
+    c->sweep_counter += (unsigned long long)*n_sweeps;
+    op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, *beta_0, 0);
+    CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+    download_site_vector(c, c->d_field.p, field_io);   // synchronises
+    *ll = ll_from_sums(c, c->h_pinned[0], c->h_pinned[1], *log_scale);
+    if (c->p2p) check_solve_flag(c);
+    ABI_END
+}
+
 void nngp_shard_p2p_export(const int *ctx_id, char *handle64, int *status) {
     ABI_BEGIN
     Ctx *c = get_ctx(ctx_id);

@@ -267,6 +267,12 @@ void nngp_sptrsv(const int *ctx_id, const int *slot, const double *b, double *x,
 void nngp_gibbs_sweep(const int *ctx_id, const int *n_sweeps, const double *beta_0, const double *log_scale,
                       const double *log_noise_variance, const int *rng_mode, const double *z, const double *seed,
                       int *status);
+/* One step for a caller that keeps state$params$field on the host: field_io (n values, reference order) is uploaded, n_sweeps sweeps
+ * run as in nngp_gibbs_sweep, ll receives ll_compressed_sparse_chol of the NEW field (current factor, update_Gaussian.R:8-12) and
+ * field_io the new field.  One host->device and one device->host pass over the field per call. */
+void nngp_sweep_loglik_host(const int *ctx_id, const int *n_sweeps, const double *beta_0, const double *log_scale,
+                            const double *log_noise_variance, const int *rng_mode, const double *z, const double *seed,
+                            double *field_io, double *ll, int *status);
 /* ancillary proposal (Scripts/mcmc_nngp_update_Gaussian.R:127-131): new_field = beta_0 + exp(.5 dls) *
  * solve(proposal, current %*% (field - beta_0)) is formed on the device and the Gaussian observation log-density
  * difference field_response_ratio is returned.  nngp_ancillary_accept() makes new_field the field. */

@@ -516,3 +516,33 @@ def test_concurrent_chains_are_bit_identical_to_sequential_ones(with_regressors)
         finally:
             for c in cs:
                 c.close()
+
+
+def test_sweep_loglik_host_equals_the_four_call_sequence():
+    """nngp_sweep_loglik_host = nngp_field_set + nngp_gibbs_sweep + nngp_loglik + nngp_field_get in one call (one PCIe pass each way):
+    the same field bit for bit and the same log-likelihood, with supplied normals and with Philox, from pageable and pinned buffers"""
+    P = make_problem(20000, 10, seed=41)
+    z = P["rng"].standard_normal(P["n"])
+    b0, ls, lnv = 0.3, 0.1, -1.0
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.factor_build([1.0, 0.07, 0.0])
+        ctx.factor_commit()
+        ctx.obs_set(P["y"])
+        ctx.field_set(P["field"])
+        ctx.gibbs_sweep(b0, ls, lnv, n_sweeps=1, z=z)
+        f_ref, ll_ref = ctx.field_get(), ctx.loglik(b0, ls)
+        ctx.field_set(P["field"])
+        ctx.gibbs_sweep(b0, ls, lnv, n_sweeps=2, seed=5)
+        f_ref2, ll_ref2 = ctx.field_get(), ctx.loglik(b0, ls)
+    with nb.NNGPContext(P["locs"], P["NNarray"], P["coloring"], P["locs_match"]) as ctx:
+        ctx.factor_build([1.0, 0.07, 0.0])
+        ctx.factor_commit()
+        ctx.obs_set(P["y"])
+        f = P["field"].copy()
+        ll = ctx.sweep_loglik_host(f, b0, ls, lnv, n_sweeps=1, z=z)
+        assert np.array_equal(f, f_ref) and ll == ll_ref
+        pinned = nb.PinnedArray(P["n"])
+        pinned.array[:] = P["field"]
+        ll2 = ctx.sweep_loglik_host(pinned.array, b0, ls, lnv, n_sweeps=2, seed=5)   # same per-context sweep counter as the reference run
+        assert np.array_equal(pinned.array, f_ref2) and ll2 == ll_ref2
+        pinned.free()
