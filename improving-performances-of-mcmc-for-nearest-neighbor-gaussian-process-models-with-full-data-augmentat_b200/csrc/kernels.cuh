@@ -1416,7 +1416,7 @@ struct ShardConst {
     PeerTable peers;
     const int *bptr;              // [n_owned + 1] by processing id: destinations of a boundary site's value (empty for interior sites)
     const int2 *bdst;             // (peer, offset inside the peer's receive values of one parity)
-    const int *gsite;             // ghost sites (processing ids) in receive order
+    const int4 *ginfo;            // ghost sites in receive order: (storage id, first entry of the local column, its end, processing id)
     unsigned long long *state;    // [0] sweeps completed since the peers were connected; [1..4] timeout report
     int *err;
     int world, rank, K;
@@ -1445,9 +1445,8 @@ __device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const Sh
     bool first = true;
     const int gcta = cl.ghost_first ? (int)blockIdx.x : (int)blockIdx.x - cl.n_tiles;
     for (int k = cl.g0 + gcta * warps + (int)(threadIdx.x >> 5); k < cl.g1; k += n_gcta * warps) {
-        const int p = sc.gsite[k];
-        const int sq = psite[p];
-        const int e0 = colptr[p], e1 = colptr[p + 1];
+        const int4 gi = sc.ginfo[k];
+        const int sq = gi.x, e0 = gi.y, e1 = gi.z;
         const int e = e0 + lane;
         int row = -1;
         double val = 0.0;
@@ -1457,6 +1456,10 @@ __device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const Sh
             asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         }
         first = false;
+        // nothing of this colour touches the ghost site's old value or the r entries along its column (same-colour sites never share a
+        // row): fetch them now, so that once the owner's value lands only arithmetic and stores remain on the boundary cycle
+        const double f_old = field[sq];
+        const double r_old = row >= 0 ? r[row] : 0.0;
         unsigned long long bits = 0ull;
         if (lane == 0) {
             unsigned int spins = 0;
@@ -1471,10 +1474,9 @@ __device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const Sh
         }
         bits = __shfl_sync(0xffffffffu, bits, 0);
         const double f_new = __longlong_as_double((long long)bits);
-        const double delta = f_new - field[sq];
-        __syncwarp();
+        const double delta = f_new - f_old;
         if (lane == 0) field[sq] = f_new;
-        if (row >= 0) r[row] += val * delta;
+        if (row >= 0) r[row] = r_old + val * delta;
         for (int e2 = e + 32; e2 < e1; e2 += 32) r[crow[e2]] += valT[e2] * delta;
     }
 }
@@ -1581,12 +1583,19 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
         for (int k = 0; k < EPT; k++)
             if (row[k] >= 0) rr[k] = r[row[k]];
     }
+    int kb0 = 0, kb1 = 0;
+    int2 dst0 = make_int2(0, 0);
     if (tid < s1 - s0) {
         const int q = s0 + tid;
         k0 = colptr[q] - e0;
         k1 = colptr[q + 1] - e0;
         sq = psite[q];
         scn = site_const(sp, field[sq], pd[q], nobs[q], S[q], sweep_normal(sp, zbuf, zpos, gid, q));
+        if (btile) {   // where the new value goes: known before the wait, so that the push is one store once the value exists
+            kb0 = sc.bptr[q];
+            kb1 = sc.bptr[q + 1];
+            if (kb1 > kb0) dst0 = sc.bdst[kb0];
+        }
     }
     if (PDL) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1604,8 +1613,17 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
         const double a = blocked_site_sum(sstart, shead, tid, k0, k1);
         const double f_new = scn.c0 - scn.c1 * a;
         sstart[tid] = f_new - scn.f_old;   // delta, once per site (sstart[tid] was read by this thread only)
+        if (btile && kb1 > kb0) {
+            const size_t parity = (size_t)(epoch & 1ull);
+            st_relaxed_sys_u64(reinterpret_cast<unsigned long long *>(sc.peers.area[dst0.x] + sc.val_off + parity * sc.peer_stride[dst0.x] + dst0.y),
+                               (unsigned long long)__double_as_longlong(f_new));
+            for (int k = kb0 + 1; k < kb1; k++) {   // a corner site: further peers
+                const int2 d = sc.bdst[k];
+                st_relaxed_sys_u64(reinterpret_cast<unsigned long long *>(sc.peers.area[d.x] + sc.val_off + parity * sc.peer_stride[d.x] + d.y),
+                                   (unsigned long long)__double_as_longlong(f_new));
+            }
+        }
         field[sq] = f_new;
-        if (btile) shard_push_site(sc, epoch, s0 + tid, f_new);
     }
     __syncthreads();
 #pragma unroll

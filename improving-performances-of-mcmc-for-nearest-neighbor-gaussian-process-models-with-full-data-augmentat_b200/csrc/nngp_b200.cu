@@ -232,6 +232,8 @@ struct Ctx {
     // round of polls instead of three); at the head of the grid 194 us -- the spinning CTAs take tile slots of the first wave
     // 8 GPUs x 1M sites (profiles/r02_shard_explore_8gpu.txt): 32 CTAs 309 us, 74: 241, 148: 215, 296: 202, 592: 202
     int shard_ghost_ctas = 296;
+    // 0 end of the grid (default), 1 head, 2 = per colour: head iff tiles + ghost CTAs are co-resident.  After the prologue work of
+    // round 2 (2 GPUs x 1M sites): end 167 us, auto 168, head 180
     int shard_ghost_first = 0;
 
     // device structure
@@ -255,6 +257,7 @@ struct Ctx {
         d_zbuf, d_partials, d_scalars, d_flush;
     DevBuf<SweepParams> d_sp;
     DevBuf<int> d_send_storage, d_recv_proc;
+    DevBuf<int4> d_ginfo;
     DevBuf<double> d_sendbuf, d_recvbuf;
     DevBuf<unsigned char> d_owned;         // per storage id: 1 = owned row (reductions skip ghost rows)
     DevBuf<int4> d_tiles;
@@ -668,7 +671,7 @@ static ShardConst shard_const(Ctx *c) {
     sc.peers = c->peers;
     sc.bptr = c->d_bptr.p;
     sc.bdst = c->d_bdst.p;
-    sc.gsite = c->d_recv_proc.p;
+    sc.ginfo = c->d_ginfo.p;
     sc.state = c->d_shard_state.p;
     sc.err = c->d_nbad.p + 1;
     sc.world = c->world; sc.rank = c->rank; sc.K = c->K;
@@ -705,8 +708,12 @@ static int launch_sweep_colors(Ctx *c) {
             cl.g1 = c->recv_ptr[(size_t)(col + 1) * W];
             cl.col = col;
             const int ng = cl.g1 - cl.g0;
-            cl.ghost_first = c->shard_ghost_first;
-            if (ng > 0) grid += std::min(c->shard_ghost_ctas, (ng + 3) / 4);   // ghost CTAs: one warp per ghost site, 4 warps per CTA
+            const int n_gcta = ng > 0 ? std::min(c->shard_ghost_ctas, (ng + 3) / 4) : 0;   // ghost CTAs: one warp per ghost site, 4 warps per CTA
+            grid += n_gcta;
+            // at the head of the grid the ghost CTAs are resident, with their columns and old values loaded, when the peers' values
+            // land; that only pays when they do not push tiles of this colour into a second wave (auto: head iff everything fits)
+            const int slots = c->n_sm * ((nt > 5 * c->n_sm && nt <= 6 * c->n_sm) ? 6 : 5);
+            cl.ghost_first = c->shard_ghost_first == 2 ? (nt + n_gcta <= slots ? 1 : 0) : c->shard_ghost_first;
         }
         if (grid == 0) continue;
         const bool pdl = c->sweep_variant != 2 && !(c->sharded && !fused_halo);
@@ -984,6 +991,7 @@ static void destroy_ctx(Ctx *c) {
     c->d_recvbuf.p = nullptr;
     if (c->p2p_area) cudaFree(c->p2p_area);
     c->d_shard_state.release(); c->d_bptr.release(); c->d_bdst.release(); c->d_sxptr.release(); c->d_sxdst.release();
+    c->d_ginfo.release();
     c->d_send_storage.release(); c->d_recv_proc.release(); c->d_sendbuf.release(); c->d_owned.release();
     DevBuf<int> *ib[] = {&c->d_psite, &c->d_gid, &c->d_i2g, &c->d_g2i, &c->d_nn, &c->d_colptr, &c->d_crow, &c->d_csrc, &c->d_zpos, &c->d_lvl_rows, &c->d_lvl_ptr,
                          &c->d_lm, &c->d_optr, &c->d_oidx, &c->d_cstart, &c->d_partial_rows, &c->d_nbad};
@@ -1467,6 +1475,11 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         for (int q = 0; q < n; q++) owned_storage[q] = sh->owned[c->i2g[q]] ? 1 : 0;
         c->d_send_storage.upload(send_storage, s);
         c->d_recv_proc.upload(recv_proc, s);
+        {   // (storage id, first entry, end of the column) of every ghost site in receive order: one load in the ghost CTAs' prologue
+            std::vector<int4> ginfo(std::max<size_t>(recv_proc.size(), 1), make_int4(0, 0, 0, 0));
+            for (size_t k = 0; k < recv_proc.size(); k++) { const int pp = recv_proc[k]; ginfo[k] = make_int4(psite[pp], colptr[pp], colptr[pp + 1], pp); }
+            c->d_ginfo.upload(ginfo, s);
+        }
         c->d_owned.upload(owned_storage, s);
         c->d_sendbuf.alloc(std::max<size_t>(send_storage.size(), 1));
         // the receive values live in one plain cudaMalloc area that peers can map through CUDA IPC.  Fixed header so that every
@@ -1574,7 +1587,7 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         case NNGP_OPT_SOLVE_WINDOW_CTAS: REQUIRE(*value >= 0 && *value <= 4096, "solve window must be 0..4096 CTAs"); c->solve_window_ctas = *value; break;
         case NNGP_OPT_SOLVE_LEVEL_COPY: c->level_copy = (*value != 0); c->have_factor[0] = c->have_factor[1] = false; c->committed = false; break;
         case NNGP_OPT_SHARD_GHOST_CTAS: REQUIRE(*value >= 1 && *value <= 1024, "ghost CTAs must be 1..1024"); c->shard_ghost_ctas = *value; if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; } break;
-        case NNGP_OPT_SHARD_GHOST_FIRST: c->shard_ghost_first = (*value != 0); if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; } break;
+        case NNGP_OPT_SHARD_GHOST_FIRST: REQUIRE(*value >= 0 && *value <= 2, "ghost placement must be 0..2"); c->shard_ghost_first = *value; if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; } break;
         case NNGP_OPT_FACTOR_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "factor variant must be 0..1"); c->factor_variant = *value; break;
         case NNGP_OPT_SOLVE_HEAD: c->solve_head = (*value != 0); break;
         case NNGP_OPT_SOLVE_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "solve sleep must be 0..100000 ns"); c->solve_sleep_ns = *value; break;

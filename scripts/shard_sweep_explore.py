@@ -53,7 +53,7 @@ def main():
     per_col_recv = np.diff(rp.reshape(-1)[:: world]) if rp.size % world == 1 else None
     if rank == 0:
         print(f"n={n} world={world} m={a.m} colours={ctx.n_colors}; rank 0: local {plan['local_sites'].size}, ghosts {plan['n_ghost']}, sends {int(sp[-1])}", flush=True)
-    for first, ctas in ((0, 32), (0, 74), (0, 148), (0, 296), (0, 592), (1, 148)):
+    for first, ctas in ((0, 296), (2, 74), (2, 148), (2, 296), (1, 74), (1, 296)):
         if True:
             ctx.set_option("shard_ghost_first", first)
             ctx.set_option("shard_ghost_ctas", ctas)
