@@ -1416,6 +1416,7 @@ struct ShardConst {
     PeerTable peers;
     const int *bptr;              // [n_owned + 1] by processing id: destinations of a boundary site's value (empty for interior sites)
     const int2 *bdst;             // (peer, offset inside the peer's receive values of one parity)
+    unsigned long long *tl;       // development aid (nngp_shard_timeline): [K][6] %globaltimer stamps per colour, or nullptr
     const int4 *ginfo;            // ghost sites in receive order: (storage id, first entry of the local column, its end, processing id)
     unsigned long long *state;    // [0] sweeps completed since the peers were connected; [1..4] timeout report
     int *err;
@@ -1431,10 +1432,20 @@ struct ShardColour {
     int ghost_first;              // 1: the ghost CTAs lead the grid (default); 0: they close it (comparison)
 };
 
+__device__ __forceinline__ unsigned long long nngp_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// stamps per colour: [0] first tile past its wait (min), [1] last boundary push (max), [2] first ghost value seen (min), [3] last ghost
+// value seen (max), [4] last ghost CTA done (max), [5] last tile done (max)
+#define NNGP_TL_MIN(sc, col, k) do { if ((sc).tl) atomicMin((sc).tl + (size_t)(col) * 6 + (k), nngp_globaltimer()); } while (0)
+#define NNGP_TL_MAX(sc, col, k) do { if ((sc).tl) atomicMax((sc).tl + (size_t)(col) * 6 + (k), nngp_globaltimer()); } while (0)
+
 // Ghost CTAs of the sweep kernel (blockIdx.x >= n_tiles), one warp per ghost site: load the site's local column (static), wait
 // until the owner's value has landed in the site's slot, then replace the ghost value and patch r along the column.  Ghost sites of
 // colour c never share a row with owned sites of colour c (the colouring is proper), so this runs concurrently with the tiles.
-template <bool PDL>
+template <bool PDL, bool TL>
 __device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const ShardColour &cl, const int *__restrict__ colptr,
                                                   const int *__restrict__ crow, const double *__restrict__ valT,
                                                   const int *__restrict__ psite, double *field, double *r) {
@@ -1471,6 +1482,7 @@ __device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const Sh
                 }
             }
             st_relaxed_sys_u64(slots + k, NNGP_HALO_EMPTY);   // empty again for the sweep after next (same parity)
+            if (TL) { NNGP_TL_MIN(sc, cl.col, 2); NNGP_TL_MAX(sc, cl.col, 3); }
         }
         bits = __shfl_sync(0xffffffffu, bits, 0);
         const double f_new = __longlong_as_double((long long)bits);
@@ -1478,6 +1490,7 @@ __device__ __forceinline__ void shard_ghost_apply(const ShardConst &sc, const Sh
         if (lane == 0) field[sq] = f_new;
         if (row >= 0) r[row] = r_old + val * delta;
         for (int e2 = e + 32; e2 < e1; e2 += 32) r[crow[e2]] += valT[e2] * delta;
+        if (TL && lane == 0) NNGP_TL_MAX(sc, cl.col, 4);
     }
 }
 
@@ -1501,7 +1514,7 @@ __device__ __forceinline__ void shard_push_site(const ShardConst &sc, unsigned l
 // but several streams on one GPU (shards of one field on one device, chains sharing a device) then starve, or -- when they wait for
 // each other, as shards do -- deadlock.  With LATE at most two kernels per stream are resident: the running colour and the next
 // colour's prologue.  SHARD kernels are always LATE.
-template <int THREADS, bool PDL, int MINB, int HINT = 0, bool SHARD = false, bool LATE = SHARD>
+template <int THREADS, bool PDL, int MINB, int HINT = 0, bool SHARD = false, bool LATE = SHARD, bool TL = false>
 __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *__restrict__ tiles, int tile_base,
                                                               const int *__restrict__ colptr, const int *__restrict__ crow,
                                                               const unsigned char *__restrict__ cloc,
@@ -1522,7 +1535,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
     // when the peers' values land -- at the end of the grid they only started after a full wave of tiles had drained)
     const int n_gcta = SHARD ? (int)gridDim.x - cl.n_tiles : 0;
     if (SHARD && (cl.ghost_first ? (int)blockIdx.x < n_gcta : (int)blockIdx.x >= cl.n_tiles)) {
-        shard_ghost_apply<PDL>(sc, cl, colptr, crow, valT, psite, field, r);
+        shard_ghost_apply<PDL, TL>(sc, cl, colptr, crow, valT, psite, field, r);
         return;
     }
     const int bx = (SHARD && cl.ghost_first) ? (int)blockIdx.x - n_gcta : (int)blockIdx.x;
@@ -1600,6 +1613,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
     if (PDL) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (LATE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (SHARD && TL && tid == 0) NNGP_TL_MIN(sc, cl.col, 0);
 #pragma unroll
         for (int k = 0; k < EPT; k++)
             if (row[k] >= 0) rr[k] = (HINT >= 2) ? ld_keep_f64(r + row[k], keep) : r[row[k]];
@@ -1622,6 +1636,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
                 st_relaxed_sys_u64(reinterpret_cast<unsigned long long *>(sc.peers.area[d.x] + sc.val_off + parity * sc.peer_stride[d.x] + d.y),
                                    (unsigned long long)__double_as_longlong(f_new));
             }
+            if (TL) NNGP_TL_MAX(sc, cl.col, 1);
         }
         field[sq] = f_new;
     }
@@ -1632,6 +1647,7 @@ __global__ void __launch_bounds__(THREADS, MINB) gibbs_tile2_kernel(const int4 *
             const double rn = rr[k] + val[k] * sstart[loc[k]];
             if (HINT >= 2) st_keep_f64(r + row[k], rn, keep); else r[row[k]] = rn;
         }
+    if (SHARD && TL && tid == 0) NNGP_TL_MAX(sc, cl.col, 5);
 }
 
 // transposition + precision_diag with the same blocked reduction (see gibbs_tile2_kernel); csrc / linv are one-touch streams

@@ -258,6 +258,8 @@ struct Ctx {
     DevBuf<SweepParams> d_sp;
     DevBuf<int> d_send_storage, d_recv_proc;
     DevBuf<int4> d_ginfo;
+    DevBuf<unsigned long long> d_shard_tl;   // development aid: per-colour time stamps of one sharded sweep (nngp_shard_timeline)
+    bool shard_tl_on = false;
     DevBuf<double> d_sendbuf, d_recvbuf;
     DevBuf<unsigned char> d_owned;         // per storage id: 1 = owned row (reductions skip ghost rows)
     DevBuf<int4> d_tiles;
@@ -672,6 +674,7 @@ static ShardConst shard_const(Ctx *c) {
     sc.bptr = c->d_bptr.p;
     sc.bdst = c->d_bdst.p;
     sc.ginfo = c->d_ginfo.p;
+    sc.tl = c->shard_tl_on ? c->d_shard_tl.p : nullptr;
     sc.state = c->d_shard_state.p;
     sc.err = c->d_nbad.p + 1;
     sc.world = c->world; sc.rank = c->rank; sc.K = c->K;
@@ -730,7 +733,9 @@ static int launch_sweep_colors(Ctx *c) {
         // a colour with slightly more tiles than 5 CTAs/SM can hold (a 6 % tail wave that costs a whole extra gather -> sum ->
         // scatter round) runs the 6-CTAs/SM build (80 registers) so that all its tiles are co-resident
         const bool six = (c->sweep_variant == 0 || c->sweep_variant == 4) && nt > 5 * c->n_sm && nt <= 6 * c->n_sm;
-        if (fused_halo) {
+        if (fused_halo && c->shard_tl_on) {   // development aid: the time-stamped build
+            CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2, true, true, true>, NNGP_T2_ARGS));
+        } else if (fused_halo) {
             if (six) CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 6, 2, true>, NNGP_T2_ARGS));
             else CK(cudaLaunchKernelEx(&lc, gibbs_tile2_kernel<128, true, 5, 2, true>, NNGP_T2_ARGS));
         } else if (!pdl) {
@@ -991,7 +996,7 @@ static void destroy_ctx(Ctx *c) {
     c->d_recvbuf.p = nullptr;
     if (c->p2p_area) cudaFree(c->p2p_area);
     c->d_shard_state.release(); c->d_bptr.release(); c->d_bdst.release(); c->d_sxptr.release(); c->d_sxdst.release();
-    c->d_ginfo.release();
+    c->d_ginfo.release(); c->d_shard_tl.release();
     c->d_send_storage.release(); c->d_recv_proc.release(); c->d_sendbuf.release(); c->d_owned.release();
     DevBuf<int> *ib[] = {&c->d_psite, &c->d_gid, &c->d_i2g, &c->d_g2i, &c->d_nn, &c->d_colptr, &c->d_crow, &c->d_csrc, &c->d_zpos, &c->d_lvl_rows, &c->d_lvl_ptr,
                          &c->d_lm, &c->d_optr, &c->d_oidx, &c->d_cstart, &c->d_partial_rows, &c->d_nbad};
@@ -1339,6 +1344,12 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     std::vector<int4> tiles;
     {
         const int T = 128, ECAP = 1024;
+        // sites per BOUNDARY tile of a sharded field.  A boundary tile is on the critical path of the colour (tile -> NVLink hop -> ghost
+        // patch on the peer -> next colour): nngp_shard_timeline showed the last push 5 us after the launch's wait with 128-site tiles
+        // (eight gathers per thread in the crowd of the interior tiles) and 2.5 us with 4-site tiles.  2 GPUs x 1M sites: 128 sites
+        // 176 us / sweep, 32: 171, 16: 158, 8: 154, 4: 152, 2: 163 (profiles/r02_shard_boundary_cycle_2gpu.txt); NNGP_BTILE_SITES overrides
+        int Tb = 8;
+        if (const char *e = std::getenv("NNGP_BTILE_SITES")) Tb = std::max(1, std::min(128, std::atoi(e)));
         c->tile_ptr.assign(K + 1, 0);
         c->btile_count.assign(K, 0);
         for (int col = 0; col < K; col++) {
@@ -1349,7 +1360,8 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
             while (s0 < send) {
                 const int lim = s0 < bend ? bend : send;
                 int s1 = s0 + 1;   // at least one site (an oversize column is handled inside the kernel)
-                while (s1 < lim && s1 - s0 < T && colptr[s1 + 1] - colptr[s0] <= ECAP) s1++;
+                const int Tt = s0 < bend ? Tb : T;
+                while (s1 < lim && s1 - s0 < Tt && colptr[s1 + 1] - colptr[s0] <= ECAP) s1++;
                 tiles.push_back(make_int4(s0, s1, colptr[s0], colptr[s1]));
                 if (s0 < bend) c->btile_count[col]++;
                 s0 = s1;
@@ -1594,6 +1606,37 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         default: REQUIRE(false, "unknown option key %d", *key);
     }
     if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; }
+    ABI_END
+}
+
+// development aid: one sweep of a peer-to-peer connected sharded field (every rank calls it together) with six %globaltimer stamps
+// per colour (see NNGP_TL_MIN / NNGP_TL_MAX in kernels.cuh); out_ns[K][6], ns relative to this rank's first stamp, -1 = never set
+void nngp_shard_timeline(const int *ctx_id, const double *beta_0, const double *log_scale, const double *log_noise_variance, double *out_ns, int *status) {
+    ABI_BEGIN
+    Ctx *c = get_ctx(ctx_id);
+    REQUIRE(beta_0 && log_scale && log_noise_variance && out_ns, "nngp_shard_timeline: null argument");
+    NEED(c->sharded && c->p2p && c->world > 1 && c->have_field && c->have_obs && c->have_slot(NNGP_SLOT_CURRENT), "nngp_shard_timeline: needs a connected sharded context with factor, field and observations");
+    use(c);
+    const size_t cnt = (size_t)c->K * 6;
+    std::vector<unsigned long long> init(cnt);
+    for (size_t i = 0; i < cnt; i++) init[i] = (i % 6 == 0 || i % 6 == 2) ? ~0ull : 0ull;   // min-stamps start at +inf
+    c->d_shard_tl.upload(init, c->stream);
+    if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; }
+    c->shard_tl_on = true;
+    if (!c->committed) op_commit(c);
+    set_sweep_params(c, *beta_0, *log_scale, *log_noise_variance, NNGP_RNG_PHILOX, 1.0);
+    refresh_r(c, *beta_0);
+    op_sweeps(c, 1);
+    c->sweep_counter += 1ull;
+    c->shard_tl_on = false;
+    std::vector<unsigned long long> t(cnt);
+    CK(cudaMemcpyAsync(t.data(), c->d_shard_tl.p, sizeof(unsigned long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; }
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < cnt; i++) if (t[i] != 0ull && t[i] != ~0ull && t[i] < t0) t0 = t[i];
+    for (size_t i = 0; i < cnt; i++) out_ns[i] = (t[i] == 0ull || t[i] == ~0ull) ? -1.0 : (double)(t[i] - t0);
+    check_solve_flag(c);
     ABI_END
 }
 

@@ -204,6 +204,12 @@ void nngp_host_shard_plan_get(const int *plan_id, double *locs, int *NNarray, in
 void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);
 /* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,
  * [6]=device, [7]=layout */
+/* development aid: one sweep of a connected sharded field with six time stamps per colour (first tile past its wait, last boundary
+ * push, first / last ghost value seen, last ghost site patched, last tile done); out_ns[n_colors][6], ns, -1 = not set.  Every rank
+ * of the field must call it at the same time. */
+void nngp_shard_timeline(const int *ctx_id, const double *beta_0, const double *log_scale, const double *log_noise_variance,
+                         double *out_ns, int *status);
+
 /* development aid: completion time (ns, %globaltimer) of every 256-row chunk of one triangular solve and the DAG level each chunk
  * starts in; *n_chunks: capacity in, count out */
 void nngp_solve_timeline(const int *ctx_id, double *out_ns, int *level_of_chunk, int *n_chunks, int *status);
