@@ -1002,7 +1002,7 @@ __global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restr
     __shared__ int s_chunk;
     constexpr int MC = MT > 0 ? MT : 32;
     const int Mr = MT > 0 ? MT : M;
-    // slot0 > 0: the first slot0 slots of the row list (the narrow head levels of the DAG) were solved by sptrsv_head_kernel
+    // slot0 > 0: the walk starts at that slot of the row list (the rows before it are already solved)
     const int n_chunks = (n_slots - slot0 + (int)blockDim.x - 1) / (int)blockDim.x;
     auto take = [&]() -> int {
         __syncthreads();
@@ -1098,103 +1098,6 @@ __global__ void __launch_bounds__(256) sptrsv_syncfree_kernel(const int *__restr
 #pragma unroll
         for (int j = 0; j < MC; j++) { idx[j] = idx1[j]; a[j] = a1[j]; }
         c1 = c2; q1 = q2;
-    }
-}
-
-// The narrow head of the DAG.  Under a max-min ordering the first ~60 % of the levels hold ~2 % of the rows (n = 1M, m = 10: 125 of
-// 204 levels, 24k rows, none wider than 1.5k), and the sync-free kernel above pays one L2 store -> poll hop (~1.2 us) for every one
-// of them.  One CTA walks those levels instead: the solution values of the head live in shared memory (a head row's parents are
-// head rows), a level costs one shared-memory gather, the FMA chain and a __syncthreads, and the next level's indices and
-// coefficients are already in registers when the barrier opens.  par[j-1][t] = slot of the j-th parent of the row in slot t.
-// Values also go to x with gpu-scope stores: the sync-free kernel that takes over at slot n_head_slots polls them there.
-#define NNGP_HEAD_MAX_LEVELS 1023
-template <int MT, bool PREFETCH>
-__global__ void __launch_bounds__(512) sptrsv_head_kernel(const int *__restrict__ par, const double *__restrict__ linv_lvl,
-                                                          const int *__restrict__ rows_padded, const int *__restrict__ slot_ptr,
-                                                          int H, int ldp, int ld, int M, const double *__restrict__ b,
-                                                          unsigned long long *x, double *__restrict__ y, double shift, double scale) {
-    extern __shared__ double xs[];
-    __shared__ int s_ptr[NNGP_HEAD_MAX_LEVELS + 1];
-    constexpr int MC = MT > 0 ? MT : 32;
-    const int Mr = MT > 0 ? MT : M;
-    const int tid = threadIdx.x, T = (int)blockDim.x;
-    for (int l = tid; l <= H; l += T) s_ptr[l] = slot_ptr[l];
-    __syncthreads();
-    // The head's static data (3 MB at n = 1M, m = 10) is cold: a level's loads would each pay a DRAM round trip (measured: 2.8 us per
-    // level).  Pull it into L2 now, and put the right-hand side -- the only two-step gather (row id, then b[row]) -- into the
-    // shared array up front: slot t holds b until the row is solved and x afterwards.
-    {
-        const int n_head = s_ptr[H];
-        unsigned int touch = 0u;   // real loads, one per 128-byte line (a prefetch hint may be dropped): the lines are in L2 when needed
-        for (int j = 0; j < Mr; j++) {
-            const char *pa = reinterpret_cast<const char *>(linv_lvl + (size_t)j * ld);
-            for (size_t o = (size_t)tid * 128; o < (size_t)n_head * 8; o += (size_t)T * 128) touch += __ldcg(reinterpret_cast<const unsigned int *>(pa + o));
-            if (j > 0) {
-                const char *pp = reinterpret_cast<const char *>(par + (size_t)(j - 1) * ldp);
-                for (size_t o = (size_t)tid * 128; o < (size_t)n_head * 4; o += (size_t)T * 128) touch += __ldcg(reinterpret_cast<const unsigned int *>(pp + o));
-            }
-        }
-        for (int t = tid; t < n_head; t += T) {
-            const int row = rows_padded[t];
-            xs[t] = row >= 0 ? b[row] : 0.0;
-        }
-        if (touch == 0x9e3779b9u && H < 0) xs[0] = 0.0;   // keeps the loads alive; never true
-        __syncthreads();
-    }
-    // all loads of a slot are issued together: nothing here may depend on a loaded value (a branch on the row id put one L2 round
-    // trip between the row id and the coefficients, and a level cost 1 us); padding slots hold -1 parents and zero coefficients
-    auto load = [&](int t, int lim, int &row, int (&id)[MC], double (&av)[MC], double &bv) {
-        row = -1;
-        if (t >= lim) return;
-        row = rows_padded[t];
-#pragma unroll
-        for (int j = 0; j < MC; j++) {
-            if (j < Mr) {
-                id[j] = j > 0 ? par[(size_t)(j - 1) * ldp + t] : 0;
-                av[j] = linv_lvl[(size_t)j * ld + t];
-            }
-        }
-        bv = 0.0;
-    };
-    auto solve_row = [&](int t, int row, const int (&id)[MC], const double (&av)[MC], double) {
-        if (row < 0) return;
-        double s = xs[t];
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};   // same association as sptrsv_syncfree_kernel: the head changes no bit of the solution
-#pragma unroll
-        for (int j = 1; j < MC; j++)
-            if (j < Mr && id[j] >= 0) acc[j & 3] += av[j] * xs[id[j]];
-        s -= (acc[0] + acc[1]) + (acc[2] + acc[3]);
-        const double xv = s * (1.0 / av[0]);
-        xs[t] = xv;
-        st_relaxed_gpu_u64(x + row, (unsigned long long)__double_as_longlong(xv));
-        if (y) y[row] = shift + scale * xv;
-    };
-    int row_c = -1, idx_c[MC];
-    double a_c[MC], b_c = 0.0;
-    int s0 = s_ptr[0], s1 = s_ptr[1];
-    if (PREFETCH) load(s0 + tid, s1, row_c, idx_c, a_c, b_c);
-    for (int l = 0; l < H; l++) {
-        const int n0 = s1, n1 = (l + 1 < H) ? s_ptr[l + 2] : s1;
-        if (PREFETCH) {
-            int row_n = -1, idx_n[MC];
-            double a_n[MC], b_n = 0.0;
-            load(n0 + tid, n1, row_n, idx_n, a_n, b_n);            // next level's first round: in flight across the barrier
-            solve_row(s0 + tid, row_c, idx_c, a_c, b_c);
-            for (int t = s0 + tid + T; t < s1; t += T) {           // levels wider than the CTA
-                load(t, s1, row_c, idx_c, a_c, b_c);
-                solve_row(t, row_c, idx_c, a_c, b_c);
-            }
-            row_c = row_n; b_c = b_n;
-#pragma unroll
-            for (int j = 0; j < MC; j++) { idx_c[j] = idx_n[j]; a_c[j] = a_n[j]; }
-        } else {
-            for (int t = s0 + tid; t < s1; t += T) {
-                load(t, s1, row_c, idx_c, a_c, b_c);
-                solve_row(t, row_c, idx_c, a_c, b_c);
-            }
-        }
-        __syncthreads();
-        s0 = n0; s1 = n1;
     }
 }
 

@@ -268,12 +268,6 @@ struct Ctx {
     DevBuf<int> d_nn_lvl, d_lpos;          // triangular solve: neighbour table in row-list (DAG level) order; position of every row in the list
     DevBuf<double> d_linv_lvl[2];          // ... and the factor values in the same order, written by the factor build next to d_linv
     bool level_copy = true;
-    // narrow head of the DAG (sptrsv_head_kernel): levels [0, n_head_levels) = slots [0, n_head_slots) of the row list
-    DevBuf<int> d_head_par, d_head_slot_ptr;
-    int n_head_levels = 0, n_head_slots = 0;
-    // measured slower than leaving the head to the sync-free kernel (n = 1M, m = 10, max-min: 92 levels / 5k slots 68 us in either; 125
-    // levels / 25k slots 246 us against ~95 us; profiles/r02_solve_timeline.txt): off by default, NNGP_OPT_SOLVE_HEAD turns it on
-    bool solve_head = false;
     int factor_variant = 0;                // 0 = thread per row everywhere (default), 1 = warp-per-row kernel where it exists (m = 20)
     DevBuf<unsigned long long> d_solve_tl;   // development aid: per-chunk completion times of the sync-free solve
     bool solve_tl_on = false;
@@ -603,35 +597,7 @@ static void op_sptrsv(Ctx *c, const double *linv, const double *b, double *x, do
         const int want = c->solve_window_ctas > 0 ? c->solve_window_ctas : c->n_sm * c->solve_ctas_per_sm;
         const int blocks = std::max(1, std::min((c->n_slots + 255) / 256, want));
         const double *lv = level_linv(c, linv);
-        int slot0 = 0;
-        if (lv && c->solve_head && c->n_head_slots > 0) {   // the narrow head levels: one CTA, solution values in shared memory
-            slot0 = c->n_head_slots;
-            const size_t smem = (size_t)slot0 * sizeof(double);
-            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-            if (c->solve_tl_on) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, c->stream)); }
-#define NNGP_HEAD_LAUNCH(MT_, PF_)                                                                                                        \
-            do {                                                                                                                          \
-                CK(cudaFuncSetAttribute(sptrsv_head_kernel<MT_, PF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-                sptrsv_head_kernel<MT_, PF_><<<1, 512, smem, c->stream>>>(c->d_head_par.p, lv, c->d_rows_padded.p, c->d_head_slot_ptr.p, \
-                    c->n_head_levels, slot0, c->n_slots, c->M, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale);            \
-            } while (0)
-            switch (c->M) {
-                case 6: NNGP_HEAD_LAUNCH(6, true); break;
-                case 11: NNGP_HEAD_LAUNCH(11, true); break;
-                case 21: NNGP_HEAD_LAUNCH(21, false); break;
-                default: NNGP_HEAD_LAUNCH(0, false); break;
-            }
-#undef NNGP_HEAD_LAUNCH
-            LAUNCHED(c);
-            if (c->solve_tl_on) {   // development aid: the head kernel on its own
-                CK(cudaEventRecord(ev1, c->stream));
-                CK(cudaEventSynchronize(ev1));
-                float ms = 0.f;
-                CK(cudaEventElapsedTime(&ms, ev0, ev1));
-                std::fprintf(stderr, "[nngp solve timeline] head kernel: %d levels, %d slots, %.1f us\n", c->n_head_levels, slot0, ms * 1e3);
-                cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-            }
-        }
+        const int slot0 = 0;
         const int blocks_rest = std::max(1, std::min((c->n_slots - slot0 + 255) / 256, want));
         if (lv) { DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT, false, true><<<blocks_rest, 256, 0, c->stream>>>(c->d_nn_lvl.p, lv, c->d_rows_padded.p, c->n_slots, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale, c->n_slots, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ShardSolve{}, slot0, c->solve_tl_on ? c->d_solve_tl.p : nullptr))); }
         else { DISPATCH_MT(c->M, (sptrsv_syncfree_kernel<MT><<<blocks, 256, 0, c->stream>>>(c->d_nn.p, linv, c->d_rows_padded.p, c->n_slots, b, reinterpret_cast<unsigned long long *>(x), y, shift, scale, c->ld, c->M, c->d_ticket.p, c->d_nbad.p + 1, (unsigned int)c->solve_sleep_ns, ShardSolve{}))); }
@@ -1012,7 +978,6 @@ static void destroy_ctx(Ctx *c) {
     c->d_sp.release();
     c->d_tiles.release();
     c->d_rows_padded.release(); c->d_ticket.release(); c->d_cloc.release();
-    c->d_head_par.release(); c->d_head_slot_ptr.release();
     c->d_nn_lvl.release(); c->d_lpos.release(); c->d_linv_lvl[0].release(); c->d_linv_lvl[1].release();
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -1417,38 +1382,6 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
         }
         c->d_lpos.upload(lpos, s);
         c->d_nn_lvl.upload(nn_lvl, s);
-        // head: the longest prefix of levels that fits the shared memory of one CTA (solution values, 8 bytes per slot) and has no
-        // level wider than a few rounds of the CTA; only worth a launch when it spares a good number of level hops
-        if (!sh) {
-            int kHeadCapSlots = 26000, kHeadMaxWidth = 2048;
-            if (const char *e = std::getenv("NNGP_HEAD_CAP_SLOTS")) kHeadCapSlots = std::max(0, std::min(28000, std::atoi(e)));   // development aid
-            if (const char *e = std::getenv("NNGP_HEAD_MAX_WIDTH")) kHeadMaxWidth = std::max(0, std::atoi(e));
-            std::vector<int> slot_ptr(1, 0);
-            int t = 0;
-            for (int l = 0; l < c->n_levels; l++) {
-                const int w = c->lvl_ptr[l + 1] - c->lvl_ptr[l];
-                const int wp = (w + 31) / 32 * 32;
-                if (w > kHeadMaxWidth || t + wp > kHeadCapSlots || l >= NNGP_HEAD_MAX_LEVELS) break;
-                t += wp;
-                slot_ptr.push_back(t);
-            }
-            const int H = (int)slot_ptr.size() - 1;
-            if (H >= 8 && t < c->n_slots) {
-                c->n_head_levels = H;
-                c->n_head_slots = t;
-                std::vector<int> par((size_t)std::max(M - 1, 1) * t, -1);
-                for (int u = 0; u < t; u++) {
-                    const int q = rows_padded[u];
-                    if (q < 0) continue;
-                    for (int j = 1; j < M; j++) {
-                        const int v = nn[(size_t)j * ld + q];
-                        if (v >= 0) { REQUIRE(lpos[v] >= 0 && lpos[v] < t, "solve head: a parent lies outside the head"); par[(size_t)(j - 1) * t + u] = lpos[v]; }
-                    }
-                }
-                c->d_head_par.upload(par, s);
-                c->d_head_slot_ptr.upload(slot_ptr, s);
-            }
-        }
         for (int k = 0; k < 2; k++) {
             c->d_linv_lvl[k].alloc((size_t)std::max(c->n_slots, 1) * M);
             CK(cudaMemsetAsync(c->d_linv_lvl[k].p, 0, sizeof(double) * (size_t)std::max(c->n_slots, 1) * M, s));
@@ -1601,7 +1534,6 @@ void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, in
         case NNGP_OPT_SHARD_GHOST_CTAS: REQUIRE(*value >= 1 && *value <= 1024, "ghost CTAs must be 1..1024"); c->shard_ghost_ctas = *value; if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; } break;
         case NNGP_OPT_SHARD_GHOST_FIRST: REQUIRE(*value >= 0 && *value <= 2, "ghost placement must be 0..2"); c->shard_ghost_first = *value; if (c->sweep_graph) { cudaGraphExecDestroy(c->sweep_graph); c->sweep_graph = nullptr; } break;
         case NNGP_OPT_FACTOR_VARIANT: REQUIRE(*value >= 0 && *value <= 1, "factor variant must be 0..1"); c->factor_variant = *value; break;
-        case NNGP_OPT_SOLVE_HEAD: c->solve_head = (*value != 0); break;
         case NNGP_OPT_SOLVE_SLEEP_NS: REQUIRE(*value >= 0 && *value <= 100000, "solve sleep must be 0..100000 ns"); c->solve_sleep_ns = *value; break;
         default: REQUIRE(false, "unknown option key %d", *key);
     }
@@ -1649,7 +1581,7 @@ void nngp_solve_timeline(const int *ctx_id, double *out_ns, int *level_of_chunk,
     REQUIRE(out_ns && level_of_chunk && n_chunks, "nngp_solve_timeline: null argument");
     NEED(!c->sharded && c->have_slot(NNGP_SLOT_CURRENT) && c->have_field, "nngp_solve_timeline: needs an unsharded context with a factor and a field");
     use(c);
-    const int slot0 = (c->solve_head && c->level_copy && c->n_head_slots > 0) ? c->n_head_slots : 0;
+    const int slot0 = 0;
     const int nc = (c->n_slots - slot0 + 255) / 256;
     REQUIRE(*n_chunks >= nc, "nngp_solve_timeline: need room for %d chunks", nc);
     c->d_solve_tl.alloc((size_t)nc + 1);

@@ -198,7 +198,6 @@ void nngp_host_shard_plan_get(const int *plan_id, double *locs, int *NNarray, in
 #define NNGP_OPT_MATERN_TABLE 9       /* Matern families: 1 = per-build interpolation table of the kernel (default), 0 = K_nu per pair */
 #define NNGP_OPT_SHARD_GHOST_CTAS 11  /* sharded sweep (peer-to-peer): at most this many ghost CTAs per colour launch, 4 ghost sites in flight each (default 296) */
 #define NNGP_OPT_SHARD_GHOST_FIRST 12 /* ... 0 = at the end of the grid (default); 1 = at its head, resident before the peers' values land; 2 = per colour: head iff tiles and ghost CTAs are co-resident; default 0 (measured: 167 / 180 / 168 us on 2 GPUs x 1M sites) */
-#define NNGP_OPT_SOLVE_HEAD 13        /* 1 = the narrow head levels of the solve DAG are walked by one CTA with the solution in shared memory (measured slower); 0 = off (default) */
 #define NNGP_OPT_FACTOR_VARIANT 14    /* factor build at m = 20: 0 = one thread per row, as for m <= 10 (default); 1 = one warp per row (measured slower for the exponential family, equal for Matern) */
 #define NNGP_OPT_LOGLIK_VARIANT 10    /* log-lik pass: 1 = plain coalesced loads (default, faster); 0 = TMA-staged shared-memory ring (cp.async.bulk + mbarrier) */
 void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);

@@ -63,9 +63,6 @@ def main():
         line(f"spmv+sptrsv variant={sv} window_ctas={win}", "sptrsv")
     ctx.set_option("solve_window_ctas", 0)
     ctx.set_option("solve_variant", 0)
-    for hd in (0, 1):   # narrow head levels of the DAG by one CTA (shared-memory solution values) or by the sync-free kernel
-        ctx.set_option("solve_head", hd)
-        line(f"spmv+sptrsv head={hd}", "sptrsv")
     for lc in (0, 1):   # the factor build also writes the factor in the solve's row order (1, default) or not (0)
         ctx.set_option("solve_level_copy", lc)
         assert ctx.factor_build(cp) == 0

@@ -1,5 +1,5 @@
 """Development aid: where the sync-free triangular solve spends its time, per DAG level (nngp_solve_timeline).
-python scripts/solve_timeline.py [--m 10] [--head 0|1]"""
+python scripts/solve_timeline.py [--m 10]"""
 import ctypes as C
 import os
 import sys
@@ -14,14 +14,12 @@ from nngp_b200 import _lib as L  # noqa: E402
 import bench  # noqa: E402
 
 m = int(sys.argv[sys.argv.index("--m") + 1]) if "--m" in sys.argv else 10
-head = int(sys.argv[sys.argv.index("--head") + 1]) if "--head" in sys.argv else 0
 n = 1_000_000
 _, locs, nn, col, lm, _ = bench.build_problem(n, m, seed=1, reordering="maxmin")
 ctx = nb.NNGPContext(locs, nn, col, lm)
 assert ctx.factor_build([1.0, 0.05, 0.0]) == 0
 ctx.factor_commit()
 ctx.field_init(0.0, 0.0, np.random.default_rng(1).standard_normal(n))
-ctx.set_option("solve_head", head)
 ctx.time_op("sptrsv", reps=3)
 cap = 8192
 for rep in range(2):
@@ -30,7 +28,7 @@ for rep in range(2):
     L.check(st)
 k = nc.value
 out, lev = out[:k], lev[:k]
-print(f"n={n} m={m} head={head}: {k} chunks, {ctx.n_levels} levels, last chunk done at {out.max() / 1e3:.1f} us")
+print(f"n={n} m={m}: {k} chunks, {ctx.n_levels} levels, last chunk done at {out.max() / 1e3:.1f} us")
 # time at which the last chunk STARTING in each level finished, and the level's width in chunks
 lv_end = {}
 for c in range(k):
