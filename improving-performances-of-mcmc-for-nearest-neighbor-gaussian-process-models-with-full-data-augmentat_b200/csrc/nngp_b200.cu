@@ -178,6 +178,8 @@ struct DevBuf {
 struct Ctx {
     int device = 0, layout = NNGP_LAYOUT_MORTON;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // nngp_sweep_loglik_host: the field's way back to the host overlaps the log-lik pass
+    cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n = 0, d = 0, m = 0, M = 0, ld = 0, n_obs = 0, covfun = 0, dt = 0, K = 0, n_levels = 0, max_col = 0;
     // ---- sharding (one spatial block of a larger field) ----
@@ -983,6 +985,8 @@ static void destroy_ctx(Ctx *c) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1092,6 +1096,8 @@ static void create_ctx_impl(const int *n_, const int *d_, const int *m_, const d
     CK(cudaGetDeviceProperties(&prop, c->device));
     c->n_sm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     CK(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
@@ -1839,9 +1845,21 @@ void nngp_sweep_loglik_host(const int *ctx_id, const int *n_sweeps, const double
     refresh_r(c, *beta_0);
     op_sweeps(c, *n_sweeps);
     c->sweep_counter += (unsigned long long)*n_sweeps;
-    op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, *beta_0, 0);
-    CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
-    download_site_vector(c, c->d_field.p, field_io);   // synchronises
+    if (pinned) {   // the new field leaves on a second stream while the log-lik pass reads it on the first
+        gather_f64_kernel<<<grid_for(c, c->n, 256), 256, 0, c->stream>>>(c->d_io.p, c->d_field.p, c->d_g2i.p, c->n);
+        LAUNCHED(c);
+        CK(cudaEventRecord(c->ev_copy, c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+        CK(cudaMemcpyAsync(field_io, c->d_io.p, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->copy_stream));
+        op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, *beta_0, 0);
+        CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaStreamSynchronize(c->copy_stream));
+    } else {
+        op_loglik_sums(c, c->linv_slot(NNGP_SLOT_CURRENT), c->d_field.p, *beta_0, 0);
+        CK(cudaMemcpyAsync(c->h_pinned, c->d_scalars.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+        download_site_vector(c, c->d_field.p, field_io);   // synchronises
+    }
     *ll = ll_from_sums(c, c->h_pinned[0], c->h_pinned[1], *log_scale);
     if (c->p2p) check_solve_flag(c);
     ABI_END
