@@ -201,8 +201,6 @@ void nngp_host_shard_plan_get(const int *plan_id, double *locs, int *NNarray, in
 #define NNGP_OPT_FACTOR_VARIANT 14    /* factor build at m = 20: 0 = one thread per row, as for m <= 10 (default); 1 = one warp per row (measured slower for the exponential family, equal for Matern) */
 #define NNGP_OPT_LOGLIK_VARIANT 10    /* log-lik pass: 1 = plain coalesced loads (default, faster); 0 = TMA-staged shared-memory ring (cp.async.bulk + mbarrier) */
 void nngp_ctx_set_option(const int *ctx_id, const int *key, const int *value, int *status);
-/* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,
- * [6]=device, [7]=layout */
 /* development aid: one sweep of a connected sharded field with six time stamps per colour (first tile past its wait, last boundary
  * push, first / last ghost value seen, last ghost site patched, last tile done); out_ns[n_colors][6], ns, -1 = not set.  Every rank
  * of the field must call it at the same time. */
@@ -213,6 +211,8 @@ void nngp_shard_timeline(const int *ctx_id, const double *beta_0, const double *
  * starts in; *n_chunks: capacity in, count out */
 void nngp_solve_timeline(const int *ctx_id, double *out_ns, int *level_of_chunk, int *n_chunks, int *status);
 
+/* info[0]=n, [1]=m, [2]=n_colors, [3]=n_levels (depth of the solve DAG), [4]=nnz, [5]=max column length,
+ * [6]=device, [7]=layout */
 void nngp_ctx_info(const int *ctx_id, int *info8, int *status);
 
 /* ------------------------------------------------------------------------------------------------------------------
