@@ -35,7 +35,7 @@ _lp = C.POINTER(C.c_int64)
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("nngp_oracle.c", "r_rng.c", "bessel_shim.cpp", "nngp_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("nngp_oracle.c", "r_rng.c", "gpgp_order.c", "bessel_shim.cpp", "nngp_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return so
@@ -51,6 +51,8 @@ def lib():
         _LIB.r_qnorm.argtypes = [C.c_double]
         _LIB.r_unif_index.restype = C.c_double
         _LIB.r_unif_index.argtypes = [C.c_double]
+        _LIB.r_rbeta.restype = C.c_double
+        _LIB.r_rbeta.argtypes = [C.c_double, C.c_double]
         _LIB.oracle_bessel_k.restype = C.c_double
         _LIB.oracle_bessel_k.argtypes = [C.c_double, C.c_double]
         _LIB.oracle_ll_compressed_sparse_chol.restype = C.c_double
@@ -103,6 +105,17 @@ def sample_perm(n: int) -> np.ndarray:
     return out
 
 
+def sample_int(n: int, size: int) -> np.ndarray:
+    """sample.int(n, size) without replacement (1-based)"""
+    out = np.empty(size, dtype=np.int32)
+    lib().r_sample_int(C.c_int(n), C.c_int(size), _i(out))
+    return out
+
+
+def rbeta(shape1: float, shape2: float) -> float:
+    return lib().r_rbeta(float(shape1), float(shape2))
+
+
 def bessel_k(nu: float, x: float) -> float:
     return lib().oracle_bessel_k(nu, x)
 
@@ -113,6 +126,25 @@ def find_ordered_nn(locs: np.ndarray, m: int) -> np.ndarray:
     n, d = locs.shape
     nn = np.empty(n * (m + 1), dtype=np.int32)
     lib().oracle_find_ordered_nn(_d(_f64(locs)), C.c_int(n), C.c_int(d), C.c_int(m), _i(nn))
+    return nn.reshape((n, m + 1), order="F")
+
+
+def order_maxmin_gpgp(locs: np.ndarray) -> np.ndarray:
+    """GpGp::order_maxmin(locs) on R's stream (initialize.R:29): 1-based permutation; advances the stream by rnorm(n*d)
+    and sample(n)"""
+    locs = np.asarray(locs, dtype=np.float64)
+    n, d = locs.shape
+    out = np.empty(n, dtype=np.int32)
+    lib().oracle_order_maxmin_gpgp(_d(_f64(locs)), C.c_int(n), C.c_int(d), _i(out))
+    return out
+
+
+def find_ordered_nn_gpgp(locs: np.ndarray, m: int) -> np.ndarray:
+    """GpGp::find_ordered_nn(locs, m) on R's stream (initialize.R:93): the jitter consumes rnorm(n*d)"""
+    locs = np.asarray(locs, dtype=np.float64)
+    n, d = locs.shape
+    nn = np.empty(n * (m + 1), dtype=np.int32)
+    lib().oracle_find_ordered_nn_gpgp(_d(_f64(locs)), C.c_int(n), C.c_int(d), C.c_int(m), _i(nn))
     return nn.reshape((n, m + 1), order="F")
 
 

@@ -190,3 +190,55 @@ void r_rng_set_state(const uint32_t *state625)
     memcpy(g_rng.mt, state625, sizeof(uint32_t) * MT_N);
     g_rng.mti = (int)state625[MT_N];
 }
+
+/* sample.int(n, size) without replacement, 1-based (R >= 3.6 "Rejection"): the first `size` draws of the shuffle that
+ * r_sample_perm completes.  Scripts/mcmc_nngp_initialize.R:154 draws sample(x, 1) = x[sample.int(length(x), 1)]. */
+void r_sample_int(int n, int size, int *out)
+{
+    int *pool = (int *)__builtin_malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) pool[i] = i;
+    int nn = n;
+    for (int i = 0; i < size && i < n; i++) {
+        int j = (int)r_unif_index((double)nn);
+        out[i] = pool[j] + 1;
+        pool[j] = pool[--nn];
+    }
+    __builtin_free(pool);
+}
+
+/* rbeta(1, aa, bb) (Scripts/mcmc_nngp_initialize.R:193-194 with shape1 = shape2 = 10): R's nmath/rbeta.c is Cheng (1978)
+ * -- algorithm BB, the branch for min(aa, bb) > 1 -- with the constants as R prints them (1.3862944, 2.609438, ...).
+ * Pinned by the initial log_scale / log_noise_variance the vignette prints (Vignette.md:486-499). */
+double r_rbeta(double aa, double bb)
+{
+    const double expmax = 1024 * 0.693147180559945309417232121458; /* DBL_MAX_EXP * M_LN2 */
+    if (isnan(aa) || isnan(bb) || aa < 0. || bb < 0.) return NAN;
+    if (isinf(aa) && isinf(bb)) return 0.5;
+    if (aa == 0. && bb == 0.) return (r_unif_rand() < 0.5) ? 0. : 1.;
+    if (isinf(aa) || bb == 0.) return 1.0;
+    if (isinf(bb) || aa == 0.) return 0.0;
+    double a = fmin(aa, bb), b = fmax(aa, bb), alpha = a + b;
+    double r, s, t, u1, u2, v, w, z;
+#define V_W_FROM_U1_BET(AA)                                   \
+    v = beta * log(u1 / (1.0 - u1));                          \
+    if (v <= expmax) { w = AA * exp(v); if (isinf(w)) w = 1.7976931348623157e308; } \
+    else w = 1.7976931348623157e308
+    if (a <= 1.0) return NAN; /* algorithm BC: never reached by the reference (shape1 = shape2 = 10), not restated */
+    { /* algorithm BB */
+        double beta = sqrt((alpha - 2.0) / (2.0 * a * b - alpha));
+        double gamma = a + 1.0 / beta;
+        do {
+            u1 = r_unif_rand();
+            u2 = r_unif_rand();
+            V_W_FROM_U1_BET(a);
+            z = u1 * u1 * u2;
+            r = gamma * v - 1.3862944;
+            s = a + r - w;
+            if (s + 2.609438 >= 5.0 * z) break;
+            t = log(z);
+            if (s > t) break;
+        } while (r + alpha * log(alpha / (b + w)) < t);
+        return (aa != a) ? b / (b + w) : w / (b + w);
+    }
+#undef V_W_FROM_U1_BET
+}

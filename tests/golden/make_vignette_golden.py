@@ -57,6 +57,39 @@ def main():
     assert len(vals) == 100, len(vals)
     g["hctam_scol_1_100"] = vals
     assert len(g["locs_match_100"]) == 100
+    # ---- initial state of chain_1 as printed right after mcmc_nngp_initialize                 # Vignette.md:472-523
+    def scalars(a, b):
+        return [float(t) for r in body(lines, a, b) for t in re.sub(r"^\s*\[\d+\]", "", r).split() if re.match(r"^-?\d", t)]
+    g["init_chain_1"] = {
+        "beta_0": scalars(476, 476)[0],                                                        # :475-476
+        "beta": scalars(483, 483),                                                             # :482-483
+        "log_scale": scalars(489, 489)[0],                                                     # :489
+        "shape": scalars(495, 495),                                                            # :495
+        "log_noise_variance": scalars(501, 501)[0],                                            # :501
+        "field_100": scalars(507, 523),                                                        # :507-523
+    }
+    assert len(g["init_chain_1"]["field_100"]) == 100 and len(g["init_chain_1"]["beta"]) == 2
+    # ---- every Gelman-Rubin-Brooks block the vignette prints: Multivariate, beta_0, slope, white_noise, log_scale,
+    # log_noise_variance, shape.  Blocks 1-5: first run (5 x 200 iterations, n_chromatic 5, thinning .01; :642-684);
+    # 6-31: the run until all univariate values < 1.05 (26 x 100, thinning .2; :687-873); 32-41: 10 x 100 more (:879-953);
+    # 42-46: the second example, the same regressors passed as X_obs (5 x 200; :1139-1178).
+    blocks = []
+    i = 0
+    while i < len(lines):
+        if "Multivariate" in lines[i] and "beta_0" in lines[i]:
+            blocks.append({"line": i + 1, "R_hat": [float(t) for t in body(lines, i + 2, i + 2)[0].split()]
+                           + [float(t) for t in body(lines, i + 4, i + 4)[0].split()]})
+            i += 4
+        else:
+            i += 1
+    assert len(blocks) == 46 and all(len(b["R_hat"]) == 7 for b in blocks)
+    g["R_hat_blocks"] = blocks
+    # ---- mcmc_nngp_estimate(burn_in = .5) after the 4600 iterations                           # Vignette.md:996-1028
+    def table(a, b):
+        return [[float(t) for t in r.split()[-5:]] for r in body(lines, a, b)]
+    g["estimate"] = {"GpGp_covparams": table(1000, 1002),                                       # scale, noise_variance, range
+                     "fixed_effects": table(1009, 1011),                                        # beta_0, slope, white_noise
+                     "field_head": table(1022, 1027)}
     # posterior summary bands (Vignette.md:999-1002,1008-1011): acceptance bands for the end-to-end toy run
     g["posterior_bands"] = {"scale": [11.32, 8.29, 15.86], "noise_variance": [5.217, 4.83, 5.64], "range": [6.21, 4.19, 9.43]}
     with open(OUT, "w") as f:
