@@ -3,8 +3,9 @@ to /root/reference).  Same names, same argument meaning, same list-of-state sche
 arrays instead of R matrices, 1-based index arrays kept 1-based exactly as R stores them).
 
 R is not installed in this image, so this mirror is what drives configs 1, 2, 3 and 5 end to end; `R/` holds the equivalent
-R glue.  Differences that cannot be avoided without R + GpGp + FNN are stated where they occur (random streams of the
-initial states, GpGp's randomised max-min ordering).
+R glue.  With rng = "R" (mcmc_nngp_initialize and mcmc_nngp_run) every random draw is taken from R's own stream in the order
+the reference takes it -- GpGp's randomised max-min ordering and jittered neighbour search included -- so a session gives the
+numbers the reference gives in R: tests/test_gpu_vignette.py replays the reference's vignette and compares with what it prints.
 """
 from __future__ import annotations
 
@@ -14,6 +15,7 @@ import numpy as np
 
 from . import _lib as L
 from .context import NNGPContext, chains_run, find_ordered_nn, greedy_coloring, order_maxmin
+from .rstream import RStream, find_ordered_nn_gpgp, order_maxmin_gpgp
 
 SHAPE_PARAMS = {
     "exponential_isotropic": lambda d: ["log_range"],
@@ -74,9 +76,40 @@ def _model_matrix(Xin):
 # ---------------------------------------------------------------------------------------------------------------------
 def mcmc_nngp_initialize(observed_locs, observed_field, X_obs=None, X_locs=None, m=10, reordering="maxmin",
                          stationary_covfun="exponential_isotropic", response_model="Gaussian", n_chains=3, seed=1,
-                         device=0, build_adjacency=None):
+                         device=0, build_adjacency=None, rng="numpy"):
+    """rng: see _initialize_host, which prepares everything on the host; the initial fields (:201-208: factor build +
+    sqrt(scale) * solve(Linv, z)) are drawn here on the device."""
+    lst, pending = _initialize_host(observed_locs, observed_field, X_obs, X_locs, m, reordering, stationary_covfun, response_model,
+                                    n_chains, seed, build_adjacency, rng)
+    va = lst["vecchia_approx"]
+    ctx = NNGPContext(lst["locs"], va["NNarray"], va["coloring"], va["locs_match"], stationary_covfun, device=device)
+    try:
+        for name, (cp, z) in pending.items():
+            params = lst["states"][name]["params"]
+            ctx.factor_build(cp)                                                                      # :201
+            ctx.field_init(params["beta_0"], params["log_scale"], z)                                  # :202-208
+            params["field"] = ctx.field_get()
+            lst["records"][name]["iterations"][0, 1] = time.time() - lst["t_begin"]
+    finally:
+        ctx.close()
+    print(f"Setup done, {time.time() - lst['t_begin']:.3f} s elapsed")                                # :236
+    return lst
+
+
+def _initialize_host(observed_locs, observed_field, X_obs, X_locs, m, reordering, stationary_covfun, response_model, n_chains, seed,
+                     build_adjacency, rng):
+    """Everything of mcmc_nngp_initialize that the reference does on the host too: ordering, vecchia_approx, regressors, the
+    scalar starting values of every chain.  Returns (list, pending) with pending[chain] = (covparms, z): the factor parameters
+    and the normals of that chain's initial field draw (:201-208), which mcmc_nngp_initialize carries out on the device.
+    rng = "numpy": numpy's generator for the initial states, the exact farthest-point ordering for "maxmin" (fast at any n).
+    rng = "R": R's stream after set.seed(seed) (:17), consumed exactly as the reference consumes it -- GpGp::order_maxmin
+    (:29: jitter rnorm, sample(n)), GpGp::find_ordered_nn (:93: jitter rnorm), sample(., 1) per chain (:154-161), then per chain
+    rnorm(p + 1), rbeta, rbeta, rnorm(n) (:189-208) -- so the returned list equals the one R returns."""
     t_begin = time.time()
-    rng = np.random.default_rng(seed)      # R's set.seed(seed) stream cannot be reproduced without R + GpGp
+    if rng not in ("numpy", "R"):
+        raise ValueError(f"unknown rng {rng!r}")
+    rs = RStream(seed) if rng == "R" else None                                                       # :17 set.seed(seed)
+    gen = np.random.default_rng(seed)
     observed_locs = np.asarray(observed_locs, dtype=np.float64)
     if observed_locs.ndim == 1:
         observed_locs = observed_locs[:, None]
@@ -86,9 +119,12 @@ def mcmc_nngp_initialize(observed_locs, observed_field, X_obs=None, X_locs=None,
     locs = observed_locs[np.sort(first)]
     rkind = reordering if isinstance(reordering, str) else reordering[0]
     if rkind == "maxmin":
-        order = order_maxmin(locs) - 1              # exact farthest-point; GpGp::order_maxmin is a randomised approximation
+        if rs is not None:
+            order = order_maxmin_gpgp(locs, rs, lonlat="sphere" in stationary_covfun) - 1             # :29, GpGp's own ordering
+        else:
+            order = order_maxmin(locs) - 1          # exact farthest-point; GpGp::order_maxmin is a randomised approximation
     elif rkind == "random":
-        order = rng.permutation(locs.shape[0])
+        order = rs.sample_int(locs.shape[0]) - 1 if rs is not None else gen.permutation(locs.shape[0])   # :30
     elif rkind == "coord":
         order = np.argsort(locs[:, int(reordering[1]) - 1], kind="stable")
     elif rkind == "dist_to_point":
@@ -117,7 +153,7 @@ def mcmc_nngp_initialize(observed_locs, observed_field, X_obs=None, X_locs=None,
     va["hctam_scol"] = [order_obs[ptr[s]:ptr[s + 1]] + 1 for s in range(n)]                          # :88
     va["hctam_scol_1"] = np.array([h[0] for h in va["hctam_scol"]], dtype=np.int32)                  # :89
     va["obs_per_loc"] = counts.astype(np.float64)                                                    # :91
-    NN = find_ordered_nn(locs, m)                                                                    # :93 (no lonlat: quirk 3)
+    NN = find_ordered_nn_gpgp(locs, m, rs) if rs is not None else find_ordered_nn(locs, m)           # :93 (no lonlat: quirk 3)
     va["NNarray"] = NN
     non_na = NN != L.NA_INT
     va["NNarray_non_NA"] = non_na                                                                    # :97
@@ -167,44 +203,47 @@ def mcmc_nngp_initialize(observed_locs, observed_field, X_obs=None, X_locs=None,
     def max_dist(P):
         return float(np.sqrt(((P[:, None, :] - P[None, :, :]) ** 2).sum(-1)).max())
 
-    states, records = {}, {}
-    ctx = NNGPContext(locs, NN, va["coloring"], locs_match, stationary_covfun, device=device)
-    try:
-        for i in range(n_chains):
-            shape = []
-            for name in shape_params:                                                                # :154-161
-                if name.startswith("log_range"):
-                    if "scaledim" in stationary_covfun:
-                        P = head[:, [int(name.split("_")[-1]) - 1]]
-                    elif "spacetime" in stationary_covfun:
-                        P = head[:, :-1] if name.endswith("_1") else head[:, [-1]]
-                    else:
-                        P = head
-                    shape.append(np.log(max_dist(P)) - np.log(rng.integers(20, 201)))
+    def draw_shape():                                                                                # :154-161
+        shape = []
+        for name in shape_params:
+            if name.startswith("log_range"):
+                if "scaledim" in stationary_covfun:
+                    P = head[:, [int(name.split("_")[-1]) - 1]]
+                elif "spacetime" in stationary_covfun:
+                    P = head[:, :-1] if name.endswith("_1") else head[:, [-1]]
                 else:
-                    shape.append(rng.standard_normal())
-            shape = np.array(shape)
-            perturb = np.linalg.cholesky(vcov) @ rng.standard_normal(coef.size)                       # :189
-            params = {"shape": shape, "beta_0": float(coef[0] + perturb[0]),
-                      "log_scale": float(np.log(rng.beta(10, 10) * var_resid)),                       # :193
-                      "log_noise_variance": float(np.log(rng.beta(10, 10) * var_resid))}              # :194
-            if X["X"] is not None:
-                params["beta"] = coef[1:] + perturb[1:]
-            cp = shape_to_covparms(shape, shape_params, lambda v: .4 + .7 * plogis(v))                # :196-200
-            ctx.factor_build(cp)                                                                      # :201
-            ctx.field_init(params["beta_0"], params["log_scale"], rng.standard_normal(n))             # :202-208
-            params["field"] = ctx.field_get()
-            states[f"chain_{i + 1}"] = {
-                "transition_kernels": {"covariance_params_sufficient": {"logvar": -2.0}, "covariance_params_ancillary": {"logvar": -2.0},
-                                       "log_noise_variance": {"logvar": -1.0}},                      # :184-187
-                "params": params}
-            records[f"chain_{i + 1}"] = {"iterations": np.array([[0.0, time.time() - t_begin]]), "params": {}}   # :225-227
-    finally:
-        ctx.close()
-    print(f"Setup done, {time.time() - t_begin:.3f} s elapsed")                                       # :236
+                    P = head
+                if rs is not None:
+                    shape.append(rs.sample_one(np.log(max_dist(P)) - np.log(np.arange(20.0, 201.0))))
+                else:
+                    shape.append(np.log(max_dist(P)) - np.log(gen.integers(20, 201)))
+            else:
+                shape.append(rs.rnorm(1)[0] if rs is not None else gen.standard_normal())
+        return np.array(shape)
+
+    normal = (lambda k: rs.rnorm(k)) if rs is not None else (lambda k: gen.standard_normal(k))
+    beta_10_10 = (lambda: rs.rbeta(1, 10, 10)[0]) if rs is not None else (lambda: gen.beta(10, 10))
+    # the reference draws the shapes of ALL chains first (:152-162), then the rest chain by chain (:181-209)
+    shapes = [draw_shape() for _ in range(n_chains)] if rs is not None else None
+    states, records, pending = {}, {}, {}
+    for i in range(n_chains):
+        shape = shapes[i] if shapes is not None else draw_shape()
+        perturb = np.linalg.cholesky(vcov) @ normal(coef.size)                                        # :189
+        params = {"shape": shape, "beta_0": float(coef[0] + perturb[0])}
+        if X["X"] is not None:
+            params["beta"] = coef[1:] + perturb[1:]
+        params["log_scale"] = float(np.log(beta_10_10() * var_resid))                                 # :193
+        params["log_noise_variance"] = float(np.log(beta_10_10() * var_resid))                        # :194
+        cp = shape_to_covparms(shape, shape_params, lambda v: .4 + .7 * plogis(v))                    # :196-200
+        pending[f"chain_{i + 1}"] = (cp, normal(n))                                                   # z of :208
+        states[f"chain_{i + 1}"] = {
+            "transition_kernels": {"covariance_params_sufficient": {"logvar": -2.0}, "covariance_params_ancillary": {"logvar": -2.0},
+                                   "log_noise_variance": {"logvar": -1.0}},                          # :184-187
+            "params": params}
+        records[f"chain_{i + 1}"] = {"iterations": np.array([[0.0, time.time() - t_begin]]), "params": {}}   # :225-227
     return {"locs": locs, "X": X, "observed_field": observed_field, "observed_locs": observed_locs,
             "space_time_model": space_time_model, "vecchia_approx": va, "states": states, "records": records,
-            "diagnostics": {"Gelman_Rubin_Brooks": []}, "t_begin": t_begin, "seed": seed}
+            "diagnostics": {"Gelman_Rubin_Brooks": []}, "t_begin": t_begin, "seed": seed}, pending
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -286,10 +325,12 @@ def mcmc_nngp_update_Gaussian(locs, X, observed_field, space_time_model, vecchia
 
 
 def _records_dict(rec, shape_params, field_records, beta=None, beta_names=None):
-    r = {"beta_0": rec[:, [0]].copy(), "log_scale": rec[:, [1]].copy(), "log_noise_variance": rec[:, [2]].copy(),
-         "shape": rec[:, 3:3 + len(shape_params)].copy(), "field": field_records}
+    # in the order the reference creates them (update_Gaussian.R:42-56): it is the column order of the diagnostics
+    r = {"beta_0": rec[:, [0]].copy()}
     if beta is not None:
         r["beta"] = beta
+    r.update({"log_scale": rec[:, [1]].copy(), "log_noise_variance": rec[:, [2]].copy(),
+              "shape": rec[:, 3:3 + len(shape_params)].copy(), "field": field_records})
     r["_shape_names"] = list(shape_params)
     r["_beta_names"] = list(beta_names or [])
     return r

@@ -98,8 +98,10 @@ inline double dist2(const double *P, int d, int a, int b) {
     return s;
 }
 
-// m nearest among points with index < i, result ascending by (d2, idx) into out[0..found)
-int query_prev(const Grid &g, const double *P, int d, int i, int m, Cand *heap /* size m */) {
+// PREV: m nearest among points with index < i; otherwise m nearest among all points but i itself.
+// Result ascending by (d2, idx) in heap[0..found)
+template <bool PREV>
+int query_knn(const Grid &g, const double *P, int d, int i, int m, Cand *heap /* size m */) {
     int found = 0;
     int ci[3] = {0, 0, 0};
     for (int k = 0; k < g.gd; k++) ci[k] = g.cell_coord(P[(size_t)i * d + k], k);
@@ -120,7 +122,8 @@ int query_prev(const Grid &g, const double *P, int d, int i, int m, Cand *heap /
                     int c = (z * g.nc[1] + y) * g.nc[0] + x;
                     for (int q = g.start[c]; q < g.start[c + 1]; q++) {
                         int p = g.pts[q];
-                        if (p >= i) break;  // ascending inside the cell
+                        if (PREV) { if (p >= i) break; }  // ascending inside the cell
+                        else if (p == i) continue;
                         Cand cd{dist2(P, d, i, p), p};
                         if (found < m) {
                             heap[found++] = cd;
@@ -140,6 +143,26 @@ int query_prev(const Grid &g, const double *P, int d, int i, int m, Cand *heap /
     }
     std::sort_heap(heap, heap + found);
     return found;
+}
+
+inline int query_prev(const Grid &g, const double *P, int d, int i, int m, Cand *heap) { return query_knn<true>(g, P, d, i, m, heap); }
+
+// GpGp's coordinate jitter: locs + matrix(ee * 1e-4 * rnorm(n * d), n, d), ee = the smallest column standard deviation
+// (stats::sd, n - 1).  Column-major in, column-major out; advances R's stream by n * d normals.
+std::vector<double> gpgp_jitter(const double *locs_cm, int n, int d, nngp::RStream &rs) {
+    double ee = INFINITY;
+    for (int k = 0; k < d; k++) {
+        const double *c = locs_cm + (size_t)n * k;
+        double mean = 0.0;
+        for (int i = 0; i < n; i++) mean += c[i];
+        mean /= n;
+        double ss = 0.0;
+        for (int i = 0; i < n; i++) ss += (c[i] - mean) * (c[i] - mean);
+        ee = std::min(ee, std::sqrt(ss / (n - 1)));
+    }
+    std::vector<double> out((size_t)n * d);
+    for (size_t t = 0; t < out.size(); t++) out[t] = locs_cm[t] + ee * 1e-4 * rs.norm_rand();
+    return out;
 }
 
 }  // namespace
@@ -181,6 +204,74 @@ void find_ordered_nn(const double *locs_cm, int n, int d, int m, int *NNarray) {
         }
         s = e;
     }
+}
+
+// GpGp::find_ordered_nn(locs, m) as the reference calls it (Scripts/mcmc_nngp_initialize.R:93): the search above on
+// coordinates jittered with R's stream
+void find_ordered_nn_gpgp(const double *locs_cm, int n, int d, int m, RStream &rs, int *NNarray) {
+    if (n < 2) { find_ordered_nn(locs_cm, n, d, m, NNarray); return; }
+    std::vector<double> x = gpgp_jitter(locs_cm, n, d, rs);
+    find_ordered_nn(x.data(), n, d, m, NNarray);
+}
+
+// GpGp::order_maxmin(locs, lonlat) (Scripts/mcmc_nngp_initialize.R:29), the reference's default reordering, regenerated
+// on R's random stream.  Published algorithm: jitter; k = round(sqrt(n)); a random start permutation sample(n) written
+// into the first half of a list of positions; positions j = 2 .. 2n are visited once, and the index found at j is moved to
+// the end of the list whenever one of its round(min(k, n / (j - nmoved + 1))) nearest neighbours sits at an earlier
+// position (a moved index is visited again later, with fewer neighbours); the ordering is what remains, front to back.
+// GpGp takes the neighbours from one FNN::get.knn(locs, k) table (n x k); here they are queried when a position is visited,
+// which needs the same neighbours (the first nneigh of the k nearest ARE the nneigh nearest) and no n x sqrt(n) table.
+// With set.seed(1) on the vignette's toy locations this reproduces the ordering the vignette prints (Vignette.md:406-419,
+// :322-328; tests/test_abi_cpu.py).  The lon/lat branch (coordinates mapped to the unit sphere after the jitter) follows
+// the same published source but no reference output pins it.
+void order_maxmin_gpgp(const double *locs_cm, int n, int d, bool lonlat, RStream &rs, int *order) {
+    if (n < 2) { if (n == 1) order[0] = 1; return; }
+    std::vector<double> x = gpgp_jitter(locs_cm, n, d, rs);
+    int dd = d;
+    if (lonlat) {  // (lon, lat[, time]) -> (x, y, z[, time])
+        dd = d + 1;
+        std::vector<double> y((size_t)n * dd);
+        const double kPi = 3.14159265358979323846;
+        for (int i = 0; i < n; i++) {
+            double lonrad = x[i] * 2 * kPi / 360, latrad = (x[(size_t)n + i] + 90) * 2 * kPi / 360;
+            y[i] = std::sin(latrad) * std::cos(lonrad);
+            y[(size_t)n + i] = std::sin(latrad) * std::sin(lonrad);
+            y[(size_t)2 * n + i] = std::cos(latrad);
+            for (int k = 2; k < d; k++) y[(size_t)(k + 1) * n + i] = x[(size_t)k * n + i];
+        }
+        x.swap(y);
+    }
+    std::vector<double> P((size_t)n * dd);
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < dd; k++) P[(size_t)i * dd + k] = x[(size_t)i + (size_t)n * k];
+    const int k = std::min((int)std::nearbyint(std::sqrt((double)n)), n - 1);   // R's round(): halves to even
+    Grid g;
+    g.build(P.data(), n, dd, 3.0);
+    std::vector<int> iip((size_t)3 * n + 2, -1);      // index_in_position (0-based index, -1 = NA); grows to < 3n entries
+    std::vector<int> poi(n);                          // position_of_index, 1-based positions
+    rs.sample_int(n, n, iip.data());
+    for (int t = 0; t < n; t++) { iip[t] -= 1; poi[iip[t]] = t + 1; }
+    std::vector<Cand> heap(std::max(k, 1));
+    int curlen = n, nmoved = 0;
+    for (int j = 2; j <= 2 * n; j++) {
+        const int v = iip[j - 1];
+        if (v < 0) continue;                          // an emptied position: R's min(NA, na.rm = TRUE) is Inf
+        const double lim = (double)n / (double)(j - nmoved + 1);
+        int nneigh = (int)std::nearbyint(std::min((double)k, lim));
+        if (nneigh < 1) nneigh = 1;                   // R: NNall[i, 1:0] selects column 1
+        const int found = query_knn<false>(g, P.data(), dd, v, nneigh, heap.data());
+        bool earlier = false;
+        for (int q = 0; q < found && !earlier; q++) earlier = poi[heap[q].idx] < j;
+        if (earlier) {
+            nmoved++;
+            curlen++;
+            poi[v] = curlen;
+            iip[curlen - 1] = v;
+            iip[j - 1] = -1;
+        }
+    }
+    int o = 0;
+    for (int t = 0; t < curlen && o < n; t++) if (iip[t] >= 0) order[o++] = iip[t] + 1;
 }
 
 // children lists: for site s the rows r (0-based) that contain s, r ascending (includes r == s)
@@ -459,6 +550,24 @@ void nngp_host_set_num_threads(const int *n, int *status) {
     if (!n) { nngp::set_error("nngp_host_set_num_threads: null argument"); if (status) *status = NNGP_ERR_ARG; return; }
     omp_set_num_threads(*n > 0 ? *n : omp_get_num_procs());
     if (status) *status = NNGP_OK;
+}
+
+void nngp_host_order_maxmin_gpgp(const double *locs, const int *n, const int *d, const int *lonlat, int *rstate, int *order, int *status) {
+    if (!locs || !n || !d || !lonlat || !rstate || !order || *n < 0 || *d < 1 || (*lonlat && *d < 2)) { nngp::set_error("nngp_host_order_maxmin_gpgp: bad argument"); if (status) *status = NNGP_ERR_ARG; return; }
+    nngp::RStream rs;
+    rs.load(rstate);
+    nngp::order_maxmin_gpgp(locs, *n, *d, *lonlat != 0, rs, order);
+    rs.store(rstate);
+    *status = NNGP_OK;
+}
+
+void nngp_host_find_ordered_nn_gpgp(const double *locs, const int *n, const int *d, const int *m, int *rstate, int *NNarray, int *status) {
+    if (!locs || !n || !d || !m || !rstate || !NNarray || *n < 0 || *d < 1 || *m < 0) { nngp::set_error("nngp_host_find_ordered_nn_gpgp: bad argument"); if (status) *status = NNGP_ERR_ARG; return; }
+    nngp::RStream rs;
+    rs.load(rstate);
+    nngp::find_ordered_nn_gpgp(locs, *n, *d, *m, rs, NNarray);
+    rs.store(rstate);
+    *status = NNGP_OK;
 }
 
 void nngp_host_order_maxmin(const double *locs, const int *n, const int *d, int *order, int *status) {

@@ -5,7 +5,9 @@
 // beta_0, noise-variance steps) follow the same stream, the shim carries R's default generators: Mersenne-Twister
 // MT19937 with R's LCG seed scrambling, and normal.kind = "Inversion" (two uniforms -> 59-bit probability -> Wichura's
 // AS241 quantile).  Published algorithms; nothing here comes from /root/reference (which contains no RNG code).
+#include <algorithm>
 #include <cmath>
+#include "../../include/nngp_b200.h"
 #include "nngp_internal.h"
 
 namespace nngp {
@@ -97,4 +99,119 @@ void RStream::rnorm(double *out, int64_t n) {
     for (int64_t i = 0; i < n; i++) out[i] = norm_rand();
 }
 
+// R >= 3.6, sample.kind = "Rejection": ceil(log2(dn)) random bits, 16 per uniform, redrawn while >= dn
+double RStream::unif_index(double dn) {
+    if (dn <= 0) return 0.0;
+    const int bits = (int)std::ceil(std::log2(dn));
+    double dv;
+    do {
+        int64_t v = 0;
+        for (int b = 0; b <= bits; b += 16) v = 65536 * v + (int)std::floor(unif_rand() * 65536);
+        if (bits < 64) v &= (((int64_t)1) << bits) - 1;
+        dv = (double)v;
+    } while (dn <= dv);
+    return dv;
+}
+
+// sample.int(n, size) without replacement: draw j uniform on the remaining pool, emit pool[j], move the last entry into slot j
+void RStream::sample_int(int n, int size, int *out) {
+    std::vector<int> pool((size_t)std::max(n, 1));
+    for (int i = 0; i < n; i++) pool[i] = i;
+    int left = n;
+    for (int i = 0; i < size && i < n; i++) {
+        int j = (int)unif_index((double)left);
+        out[i] = pool[j] + 1;
+        pool[j] = pool[--left];
+    }
+}
+
+// rbeta(1, aa, bb) for min(aa, bb) > 1: Cheng (1978) algorithm BB with the constants of R's nmath/rbeta.c
+// (Scripts/mcmc_nngp_initialize.R:193-194 draws rbeta(1, 10, 10))
+double RStream::rbeta(double aa, double bb) {
+    const double a = std::min(aa, bb), b = std::max(aa, bb), alpha = a + b;
+    if (!(a > 1.0) || !std::isfinite(b)) return NAN;
+    const double beta = std::sqrt((alpha - 2.0) / (2.0 * a * b - alpha)), gamma = a + 1.0 / beta;
+    const double expmax = 1024 * 0.693147180559945309417232121458, dmax = 1.7976931348623157e308;
+    double r, s, t, v, w, z;
+    do {
+        const double u1 = unif_rand(), u2 = unif_rand();
+        v = beta * std::log(u1 / (1.0 - u1));
+        if (v <= expmax) { w = a * std::exp(v); if (!std::isfinite(w)) w = dmax; } else w = dmax;
+        z = u1 * u1 * u2;
+        r = gamma * v - 1.3862944;
+        s = a + r - w;
+        if (s + 2.609438 >= 5.0 * z) break;
+        t = std::log(z);
+        if (s > t) break;
+    } while (r + alpha * std::log(alpha / (b + w)) < t);
+    return (aa != a) ? b / (b + w) : w / (b + w);
+}
+
+void RStream::load(const int *st) {
+    mti_ = st[0];
+    for (int j = 0; j < 624; j++) mt_[j] = (uint32_t)st[1 + j];
+}
+
+void RStream::store(int *st) const {
+    st[0] = mti_;
+    for (int j = 0; j < 624; j++) st[1 + j] = (int)mt_[j];
+}
+
 }  // namespace nngp
+
+// ---- C ABI: R's random stream for hosts that are not R (include/nngp_b200.h, "R-compatible random stream") ----
+extern "C" {
+
+#define RS_CHECK(cond, name)                                                                              \
+    if (!(cond)) { nngp::set_error(name ": bad argument"); if (status) *status = NNGP_ERR_ARG; return; }
+
+void nngp_r_set_seed(const int *seed, int *rstate, int *status) {
+    RS_CHECK(seed && rstate, "nngp_r_set_seed");
+    nngp::RStream rs;
+    rs.set_seed((uint32_t)*seed);
+    rs.store(rstate);
+    if (status) *status = NNGP_OK;
+}
+
+void nngp_r_runif(int *rstate, const int *n, double *out, int *status) {
+    RS_CHECK(rstate && n && out && *n >= 0, "nngp_r_runif");
+    nngp::RStream rs;
+    rs.load(rstate);
+    for (int i = 0; i < *n; i++) out[i] = rs.unif_rand();
+    rs.store(rstate);
+    if (status) *status = NNGP_OK;
+}
+
+void nngp_r_rnorm(int *rstate, const int *n, double *out, int *status) {
+    RS_CHECK(rstate && n && out && *n >= 0, "nngp_r_rnorm");
+    nngp::RStream rs;
+    rs.load(rstate);
+    rs.rnorm(out, *n);
+    rs.store(rstate);
+    if (status) *status = NNGP_OK;
+}
+
+void nngp_r_sample_int(int *rstate, const int *n, const int *size, int *out, int *status) {
+    RS_CHECK(rstate && n && size && out && *n >= 0 && *size >= 0 && *size <= *n, "nngp_r_sample_int");
+    nngp::RStream rs;
+    rs.load(rstate);
+    rs.sample_int(*n, *size, out);
+    rs.store(rstate);
+    if (status) *status = NNGP_OK;
+}
+
+void nngp_r_rbeta(int *rstate, const int *n, const double *shape1, const double *shape2, double *out, int *status) {
+    RS_CHECK(rstate && n && shape1 && shape2 && out && *n >= 0, "nngp_r_rbeta");
+    if (!(std::min(*shape1, *shape2) > 1.0) || !std::isfinite(*shape1) || !std::isfinite(*shape2)) {
+        nngp::set_error("nngp_r_rbeta: only shape1, shape2 > 1 (the reference draws rbeta(1, 10, 10))");
+        if (status) *status = NNGP_ERR_ARG;
+        return;
+    }
+    nngp::RStream rs;
+    rs.load(rstate);
+    for (int i = 0; i < *n; i++) out[i] = rs.rbeta(*shape1, *shape2);
+    rs.store(rstate);
+    if (status) *status = NNGP_OK;
+}
+
+}  // extern "C"

@@ -83,9 +83,34 @@ void nngp_host_greedy_coloring(const int *NNarray, const int *n, const int *m, i
 void nngp_host_greedy_coloring_adj(const int *adj_p, const int *adj_i, const int *n, int *coloring, int *n_colors, int *status);
 /* OpenMP threads used by the nngp_host_* utilities; n <= 0 = all processors (launchers such as torchrun export OMP_NUM_THREADS=1) */
 void nngp_host_set_num_threads(const int *n, int *status);
-/* exact max-min (farthest-point) ordering, 1-based permutation (replaces GpGp::order_maxmin,
- * Scripts/mcmc_nngp_initialize.R:29; GpGp's is a randomised approximation and cannot be reproduced bit-for-bit) */
+/* exact max-min (farthest-point) ordering, 1-based permutation (an alternative to GpGp::order_maxmin,
+ * Scripts/mcmc_nngp_initialize.R:29, which is a randomised approximation -- see nngp_host_order_maxmin_gpgp) */
 void nngp_host_order_maxmin(const double *locs, const int *n, const int *d, int *order, int *status);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * R-compatible random stream and the reference's own ordering / neighbour search on it, for hosts that are not R
+ * (the Python mirror): with these, mcmc_nngp_initialize(seed) yields the SAME ordering, NNarray, colouring and initial
+ * states as the reference does in R -- checked against the values the reference's vignette prints
+ * (tests/test_abi_cpu.py, tests/test_gpu_vignette.py).  A host written in R needs none of this (it has R's RNG and GpGp).
+ * rstate: 625 ints, caller-owned: rstate[0] = position (mti), rstate[1..624] = the Mersenne-Twister words, i.e. R's
+ * .Random.seed[2:626] for RNGkind("Mersenne-Twister", "Inversion", "Rejection") (the defaults since R 3.6).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* set.seed(seed)  (Scripts/mcmc_nngp_initialize.R:17, Scripts/mcmc_nngp_update_Gaussian.R:36) */
+void nngp_r_set_seed(const int *seed, int *rstate, int *status);
+/* runif(n), rnorm(n) (inversion), sample.int(n, size) without replacement (rejection sampling), rbeta(n, shape1, shape2)
+ * (Cheng's BB; shape1, shape2 > 1 only: initialize.R:193-194 draws rbeta(1, 10, 10)) */
+void nngp_r_runif(int *rstate, const int *n, double *out, int *status);
+void nngp_r_rnorm(int *rstate, const int *n, double *out, int *status);
+void nngp_r_sample_int(int *rstate, const int *n, const int *size, int *out, int *status);
+void nngp_r_rbeta(int *rstate, const int *n, const double *shape1, const double *shape2, double *out, int *status);
+/* GpGp::order_maxmin(locs, lonlat)  (Scripts/mcmc_nngp_initialize.R:29), bit-exact on R's stream: coordinate jitter
+ * 1e-4 * min column sd * rnorm(n*d), start permutation sample(n), one pass that moves an index to the end of the list when
+ * one of its round(min(round(sqrt(n)), n/(j - nmoved + 1))) nearest neighbours precedes it.  order: n, 1-based.  *lonlat != 0:
+ * columns 1-2 are longitude / latitude in degrees, mapped to the unit sphere after the jitter (as published; unpinned). */
+void nngp_host_order_maxmin_gpgp(const double *locs, const int *n, const int *d, const int *lonlat, int *rstate, int *order, int *status);
+/* GpGp::find_ordered_nn(locs, m)  (Scripts/mcmc_nngp_initialize.R:93) bit-exact on R's stream: the same jitter (n*d fresh
+ * normals), then nngp_host_find_ordered_nn on the jittered coordinates */
+void nngp_host_find_ordered_nn_gpgp(const double *locs, const int *n, const int *d, const int *m, int *rstate, int *NNarray, int *status);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * context: graph structure uploaded once (vecchia_approx, Scripts/mcmc_nngp_initialize.R:80-110)
