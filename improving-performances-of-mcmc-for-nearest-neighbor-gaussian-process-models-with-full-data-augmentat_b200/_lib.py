@@ -25,7 +25,7 @@ LAYOUT_COLOR, LAYOUT_COLOR_MORTON, LAYOUT_MORTON = 1, 2, 3
 # every symbol include/nngp_b200.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "nngp_version", "nngp_device_count", "nngp_last_error", "nngp_last_error_r", "nngp_host_greedy_coloring_adj", "nngp_host_set_num_threads", "nngp_host_find_ordered_nn", "nngp_host_greedy_coloring",
-    "nngp_host_order_maxmin", "nngp_host_order_maxmin_gpgp", "nngp_host_find_ordered_nn_gpgp", "nngp_r_set_seed", "nngp_r_runif", "nngp_r_rnorm", "nngp_r_sample_int", "nngp_r_rbeta",
+    "nngp_host_order_maxmin", "nngp_host_order_maxmin_gpgp", "nngp_host_find_ordered_nn_gpgp", "nngp_rng_set_seed", "nngp_rng_runif", "nngp_rng_rnorm", "nngp_rng_sample_int", "nngp_rng_rbeta",
     "nngp_ctx_create", "nngp_ctx_destroy", "nngp_comm_unique_id", "nngp_ctx_create_sharded", "nngp_shard_p2p_export", "nngp_shard_p2p_connect", "nngp_shard_sweep_begin", "nngp_shard_sweep_colour", "nngp_shard_halo_get", "nngp_shard_halo_put", "nngp_shard_sweep_end", "nngp_ctx_set_option", "nngp_ctx_info", "nngp_solve_timeline", "nngp_shard_timeline", "nngp_factor_build",
     "nngp_factor_get", "nngp_factor_accept", "nngp_factor_commit", "nngp_precision_diag", "nngp_field_set",
     "nngp_field_get", "nngp_obs_set", "nngp_loglik", "nngp_loglik_host", "nngp_spmv", "nngp_sptmv", "nngp_sptrsv",

@@ -165,16 +165,16 @@ extern "C" {
 #define RS_CHECK(cond, name)                                                                              \
     if (!(cond)) { nngp::set_error(name ": bad argument"); if (status) *status = NNGP_ERR_ARG; return; }
 
-void nngp_r_set_seed(const int *seed, int *rstate, int *status) {
-    RS_CHECK(seed && rstate, "nngp_r_set_seed");
+void nngp_rng_set_seed(const int *seed, int *rstate, int *status) {
+    RS_CHECK(seed && rstate, "nngp_rng_set_seed");
     nngp::RStream rs;
     rs.set_seed((uint32_t)*seed);
     rs.store(rstate);
     if (status) *status = NNGP_OK;
 }
 
-void nngp_r_runif(int *rstate, const int *n, double *out, int *status) {
-    RS_CHECK(rstate && n && out && *n >= 0, "nngp_r_runif");
+void nngp_rng_runif(int *rstate, const int *n, double *out, int *status) {
+    RS_CHECK(rstate && n && out && *n >= 0, "nngp_rng_runif");
     nngp::RStream rs;
     rs.load(rstate);
     for (int i = 0; i < *n; i++) out[i] = rs.unif_rand();
@@ -182,8 +182,8 @@ void nngp_r_runif(int *rstate, const int *n, double *out, int *status) {
     if (status) *status = NNGP_OK;
 }
 
-void nngp_r_rnorm(int *rstate, const int *n, double *out, int *status) {
-    RS_CHECK(rstate && n && out && *n >= 0, "nngp_r_rnorm");
+void nngp_rng_rnorm(int *rstate, const int *n, double *out, int *status) {
+    RS_CHECK(rstate && n && out && *n >= 0, "nngp_rng_rnorm");
     nngp::RStream rs;
     rs.load(rstate);
     rs.rnorm(out, *n);
@@ -191,8 +191,8 @@ void nngp_r_rnorm(int *rstate, const int *n, double *out, int *status) {
     if (status) *status = NNGP_OK;
 }
 
-void nngp_r_sample_int(int *rstate, const int *n, const int *size, int *out, int *status) {
-    RS_CHECK(rstate && n && size && out && *n >= 0 && *size >= 0 && *size <= *n, "nngp_r_sample_int");
+void nngp_rng_sample_int(int *rstate, const int *n, const int *size, int *out, int *status) {
+    RS_CHECK(rstate && n && size && out && *n >= 0 && *size >= 0 && *size <= *n, "nngp_rng_sample_int");
     nngp::RStream rs;
     rs.load(rstate);
     rs.sample_int(*n, *size, out);
@@ -200,10 +200,10 @@ void nngp_r_sample_int(int *rstate, const int *n, const int *size, int *out, int
     if (status) *status = NNGP_OK;
 }
 
-void nngp_r_rbeta(int *rstate, const int *n, const double *shape1, const double *shape2, double *out, int *status) {
-    RS_CHECK(rstate && n && shape1 && shape2 && out && *n >= 0, "nngp_r_rbeta");
+void nngp_rng_rbeta(int *rstate, const int *n, const double *shape1, const double *shape2, double *out, int *status) {
+    RS_CHECK(rstate && n && shape1 && shape2 && out && *n >= 0, "nngp_rng_rbeta");
     if (!(std::min(*shape1, *shape2) > 1.0) || !std::isfinite(*shape1) || !std::isfinite(*shape2)) {
-        nngp::set_error("nngp_r_rbeta: only shape1, shape2 > 1 (the reference draws rbeta(1, 10, 10))");
+        nngp::set_error("nngp_rng_rbeta: only shape1, shape2 > 1 (the reference draws rbeta(1, 10, 10))");
         if (status) *status = NNGP_ERR_ARG;
         return;
     }

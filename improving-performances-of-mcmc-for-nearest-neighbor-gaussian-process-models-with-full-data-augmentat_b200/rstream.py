@@ -28,23 +28,23 @@ class RStream:
     def set_seed(self, seed: int) -> None:
         """set.seed(seed)"""
         s = int(seed) & 0xFFFFFFFF
-        self._call(L.load().nngp_r_set_seed, L.ci(s - (1 << 32) if s >= (1 << 31) else s), L.iptr(self.state))
+        self._call(L.load().nngp_rng_set_seed, L.ci(s - (1 << 32) if s >= (1 << 31) else s), L.iptr(self.state))
 
     def runif(self, n: int) -> np.ndarray:
         out = np.empty(int(n))
-        self._call(L.load().nngp_r_runif, L.iptr(self.state), L.ci(n), L.dptr(out))
+        self._call(L.load().nngp_rng_runif, L.iptr(self.state), L.ci(n), L.dptr(out))
         return out
 
     def rnorm(self, n: int) -> np.ndarray:
         out = np.empty(int(n))
-        self._call(L.load().nngp_r_rnorm, L.iptr(self.state), L.ci(n), L.dptr(out))
+        self._call(L.load().nngp_rng_rnorm, L.iptr(self.state), L.ci(n), L.dptr(out))
         return out
 
     def sample_int(self, n: int, size: int | None = None) -> np.ndarray:
         """sample.int(n, size) without replacement, 1-based; size = n: sample(n)"""
         size = n if size is None else size
         out = np.empty(int(size), dtype=np.int32)
-        self._call(L.load().nngp_r_sample_int, L.iptr(self.state), L.ci(n), L.ci(size), L.iptr(out))
+        self._call(L.load().nngp_rng_sample_int, L.iptr(self.state), L.ci(n), L.ci(size), L.iptr(out))
         return out
 
     def sample_one(self, x):
@@ -53,7 +53,7 @@ class RStream:
 
     def rbeta(self, n: int, shape1: float, shape2: float) -> np.ndarray:
         out = np.empty(int(n))
-        self._call(L.load().nngp_r_rbeta, L.iptr(self.state), L.ci(n), L.cd(shape1), L.cd(shape2), L.dptr(out))
+        self._call(L.load().nngp_rng_rbeta, L.iptr(self.state), L.ci(n), L.cd(shape1), L.cd(shape2), L.dptr(out))
         return out
 
 

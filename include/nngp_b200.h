@@ -96,13 +96,13 @@ void nngp_host_order_maxmin(const double *locs, const int *n, const int *d, int 
  * .Random.seed[2:626] for RNGkind("Mersenne-Twister", "Inversion", "Rejection") (the defaults since R 3.6).
  * ------------------------------------------------------------------------------------------------------------------ */
 /* set.seed(seed)  (Scripts/mcmc_nngp_initialize.R:17, Scripts/mcmc_nngp_update_Gaussian.R:36) */
-void nngp_r_set_seed(const int *seed, int *rstate, int *status);
+void nngp_rng_set_seed(const int *seed, int *rstate, int *status);
 /* runif(n), rnorm(n) (inversion), sample.int(n, size) without replacement (rejection sampling), rbeta(n, shape1, shape2)
  * (Cheng's BB; shape1, shape2 > 1 only: initialize.R:193-194 draws rbeta(1, 10, 10)) */
-void nngp_r_runif(int *rstate, const int *n, double *out, int *status);
-void nngp_r_rnorm(int *rstate, const int *n, double *out, int *status);
-void nngp_r_sample_int(int *rstate, const int *n, const int *size, int *out, int *status);
-void nngp_r_rbeta(int *rstate, const int *n, const double *shape1, const double *shape2, double *out, int *status);
+void nngp_rng_runif(int *rstate, const int *n, double *out, int *status);
+void nngp_rng_rnorm(int *rstate, const int *n, double *out, int *status);
+void nngp_rng_sample_int(int *rstate, const int *n, const int *size, int *out, int *status);
+void nngp_rng_rbeta(int *rstate, const int *n, const double *shape1, const double *shape2, double *out, int *status);
 /* GpGp::order_maxmin(locs, lonlat)  (Scripts/mcmc_nngp_initialize.R:29), bit-exact on R's stream: coordinate jitter
  * 1e-4 * min column sd * rnorm(n*d), start permutation sample(n), one pass that moves an index to the end of the list when
  * one of its round(min(round(sqrt(n)), n/(j - nmoved + 1))) nearest neighbours precedes it.  order: n, 1-based.  *lonlat != 0:

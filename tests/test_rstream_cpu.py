@@ -1,5 +1,5 @@
 """CPU checks of the product's R-compatible random stream and of the reference's own ordering / neighbour search regenerated
-on it (include/nngp_b200.h: nngp_r_*, nngp_host_order_maxmin_gpgp, nngp_host_find_ordered_nn_gpgp), against the values the
+on it (include/nngp_b200.h: nngp_rng_*, nngp_host_order_maxmin_gpgp, nngp_host_find_ordered_nn_gpgp), against the values the
 reference's vignette prints (tests/golden/vignette_golden.json) and against the oracle (oracle/r_rng.c, oracle/gpgp_order.c).
 None of this needs a GPU: these are host set-up utilities in the reference too (Scripts/mcmc_nngp_initialize.R:17-110)."""
 import numpy as np
