@@ -241,37 +241,72 @@ void order_maxmin_gpgp(const double *locs_cm, int n, int d, bool lonlat, RStream
         }
         x.swap(y);
     }
+    // The pass below touches each visited point's neighbours at random; with the points stored cell by cell (index q = position
+    // in the grid's cell-major list, old index = cell_major[q]) those reads stay inside a few cache lines.  Distances, hence
+    // the neighbour sets, do not depend on the numbering.
+    std::vector<int> cell_major;
     std::vector<double> P((size_t)n * dd);
-    for (int i = 0; i < n; i++)
-        for (int k = 0; k < dd; k++) P[(size_t)i * dd + k] = x[(size_t)i + (size_t)n * k];
+    {
+        std::vector<double> P0((size_t)n * dd);
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < dd; k++) P0[(size_t)i * dd + k] = x[(size_t)i + (size_t)n * k];
+        Grid g0;
+        g0.build(P0.data(), n, dd, 3.0);
+        cell_major.swap(g0.pts);
+        for (int q = 0; q < n; q++)
+            for (int k = 0; k < dd; k++) P[(size_t)q * dd + k] = P0[(size_t)cell_major[q] * dd + k];
+    }
+    std::vector<int> new_of_old(n);
+    for (int q = 0; q < n; q++) new_of_old[cell_major[q]] = q;
     const int k = std::min((int)std::nearbyint(std::sqrt((double)n)), n - 1);   // R's round(): halves to even
     Grid g;
     g.build(P.data(), n, dd, 3.0);
-    std::vector<int> iip((size_t)3 * n + 2, -1);      // index_in_position (0-based index, -1 = NA); grows to < 3n entries
+    std::vector<int> iip((size_t)3 * n + 2, -1);      // index_in_position (0-based NEW index, -1 = NA); grows to < 3n entries
     std::vector<int> poi(n);                          // position_of_index, 1-based positions
     rs.sample_int(n, n, iip.data());
-    for (int t = 0; t < n; t++) { iip[t] -= 1; poi[iip[t]] = t + 1; }
-    std::vector<Cand> heap(std::max(k, 1));
+    for (int t = 0; t < n; t++) { iip[t] = new_of_old[iip[t] - 1]; poi[iip[t]] = t + 1; }
+    // The pass is sequential in j, but the neighbour queries are not: the entries at positions j .. min(j + B - 1, curlen) are
+    // already final (indices are only ever appended behind curlen), and the number of neighbours a visit needs never grows
+    // (j - nmoved counts the visits that kept their index).  So a batch of positions is queried in parallel with the batch's
+    // first -- largest -- neighbour count, and the sequential pass then reads the first nneigh(j) of each sorted list.
     int curlen = n, nmoved = 0;
-    for (int j = 2; j <= 2 * n; j++) {
-        const int v = iip[j - 1];
-        if (v < 0) continue;                          // an emptied position: R's min(NA, na.rm = TRUE) is Inf
+    auto nneigh_at = [&](int j) {
         const double lim = (double)n / (double)(j - nmoved + 1);
-        int nneigh = (int)std::nearbyint(std::min((double)k, lim));
-        if (nneigh < 1) nneigh = 1;                   // R: NNall[i, 1:0] selects column 1
-        const int found = query_knn<false>(g, P.data(), dd, v, nneigh, heap.data());
-        bool earlier = false;
-        for (int q = 0; q < found && !earlier; q++) earlier = poi[heap[q].idx] < j;
-        if (earlier) {
-            nmoved++;
-            curlen++;
-            poi[v] = curlen;
-            iip[curlen - 1] = v;
-            iip[j - 1] = -1;
+        const int v = (int)std::nearbyint(std::min((double)k, lim));
+        return v < 1 ? 1 : v;                         // R: NNall[i, 1:0] selects column 1
+    };
+    std::vector<Cand> cand;
+    std::vector<int> found;
+    for (int j0 = 2; j0 <= 2 * n;) {
+        const int kmax = nneigh_at(j0);
+        const int B = std::max(1, std::min(std::min(8192, (1 << 22) / kmax), std::min(curlen, 2 * n) - j0 + 1));
+        cand.resize((size_t)B * kmax);
+        found.assign(B, 0);
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int b = 0; b < B; b++) {
+            const int v = iip[j0 - 1 + b];
+            if (v >= 0) found[b] = query_knn<false>(g, P.data(), dd, v, kmax, cand.data() + (size_t)b * kmax);
         }
+        for (int b = 0; b < B; b++) {
+            const int j = j0 + b;
+            const int v = iip[j - 1];
+            if (v < 0) continue;                      // an emptied position: R's min(NA, na.rm = TRUE) is Inf
+            const int nneigh = std::min(nneigh_at(j), found[b]);
+            const Cand *c = cand.data() + (size_t)b * kmax;
+            bool earlier = false;
+            for (int q = 0; q < nneigh && !earlier; q++) earlier = poi[c[q].idx] < j;
+            if (earlier) {
+                nmoved++;
+                curlen++;
+                poi[v] = curlen;
+                iip[curlen - 1] = v;
+                iip[j - 1] = -1;
+            }
+        }
+        j0 += B;
     }
     int o = 0;
-    for (int t = 0; t < curlen && o < n; t++) if (iip[t] >= 0) order[o++] = iip[t] + 1;
+    for (int t = 0; t < curlen && o < n; t++) if (iip[t] >= 0) order[o++] = cell_major[iip[t]] + 1;
 }
 
 // children lists: for site s the rows r (0-based) that contain s, r ascending (includes r == s)
