@@ -136,3 +136,38 @@ def test_initialize_host_part_reproduces_the_vignette(golden):
     f = p["beta_0"] + np.sqrt(np.exp(p["log_scale"])) * O.sparse_chol_solve(Linv, va["NNarray"], z)
     assert np.allclose(f[:100], g["field_100"], rtol=0, atol=6e-9)                             # :507-523
     assert np.array_equal(va["coloring"], O.naive_greedy_coloring(*O.moral_graph(va["NNarray"])))
+
+
+@pytest.mark.parametrize("covfun,d,reordering,with_obs_reg", [("matern_isotropic", 2, "maxmin", False), ("exponential_scaledim", 3, "maxmin", True),
+                                                               ("matern_spacetime", 3, "random", True), ("exponential_isotropic", 2, "random", False)])
+def test_initialize_host_part_equals_the_oracle_driver(covfun, d, reordering, with_obs_reg):
+    """every covariance family's starting values (sample(., 1) per range parameter, rnorm(1) per smoothness, :154-161), both
+    seeded reorderings, duplicated locations, regressors at both levels: the product's host part and the oracle's driver are
+    separate implementations of initialize.R on separate implementations of R's stream"""
+    from oracle import reference_driver as R
+    g = np.random.default_rng(17)
+    base = g.random((700, d))
+    obs_locs = np.vstack([base, base[g.integers(0, 700, 60)]])                  # 60 repeated observations
+    n_obs = obs_locs.shape[0]
+    y = g.standard_normal(n_obs) + 2.0 * obs_locs[:, 0]
+    X_locs = np.column_stack([obs_locs[:, 0], np.sin(7 * obs_locs[:, 1])])      # functions of the location
+    X_obs = g.standard_normal((n_obs, 1)) if with_obs_reg else None
+    lst, pending = api._initialize_host(obs_locs, y, X_obs, X_locs, 6, reordering, covfun, "Gaussian", 2, 5, None, "R")
+    ref = R.initialize(obs_locs, y, X_obs=X_obs, X_locs=X_locs, m=6, reordering=reordering, stationary_covfun=covfun, n_chains=2, seed=5)
+    va, vr = lst["vecchia_approx"], ref["vecchia_approx"]
+    assert np.array_equal(lst["locs"], ref["locs"])
+    for k in ("locs_match", "hctam_scol_1", "obs_per_loc", "NNarray", "coloring", "sparse_chol_column_idx", "sparse_chol_row_idx"):
+        assert np.array_equal(va[k], vr[k]), k
+    assert lst["space_time_model"]["covfun"]["shape_params"] == ref["space_time_model"]["shape_params"]
+    assert [c + 1 for c in lst["X"]["locs"]] == ref["X"]["locs"]
+    assert np.allclose(lst["X"]["X"], ref["X"]["X"], rtol=0, atol=1e-14)
+    assert np.allclose(lst["X"]["chol_solve_1XT1X"], ref["X"]["chol_solve_1XT1X"], rtol=1e-10, atol=1e-14)
+    for name in ("chain_1", "chain_2"):
+        p, q = lst["states"][name]["params"], ref["states"][name]["params"]
+        assert np.array_equal(p["shape"], q["shape"])
+        assert abs(p["beta_0"] - q["beta_0"]) < 1e-10 and np.allclose(p["beta"], q["beta"], rtol=0, atol=1e-10)
+        assert abs(p["log_scale"] - q["log_scale"]) < 1e-12 and abs(p["log_noise_variance"] - q["log_noise_variance"]) < 1e-12
+        cp, z = pending[name]
+        Linv = O.vecchia_Linv(cp, covfun, lst["locs"], va["NNarray"])
+        f = p["beta_0"] + np.sqrt(np.exp(p["log_scale"])) * O.sparse_chol_solve(Linv, va["NNarray"], z)
+        assert np.allclose(f, q["field"], rtol=0, atol=1e-9)
