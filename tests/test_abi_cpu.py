@@ -114,3 +114,23 @@ def test_parallel_coloring_equals_the_sequential_first_fit(n, m, d, order, monke
     seq = nb.greedy_coloring(nn)
     assert np.array_equal(par, seq) and np.array_equal(fb, seq)
     assert par.min() == 1
+
+
+def test_abi_links_and_runs_from_plain_c(tmp_path):
+    """include/nngp_b200.h is a C header and the library a C library: tests/c_abi/abi_from_c.c (C11) is compiled with gcc against
+    them and run -- version, R's random stream, the host builders, the error convention, and the refusal of a compute entry
+    point without a device (no CPU fallback)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    L.load()
+    lib_dir = os.path.dirname(L.SO_PATH)
+    exe = str(tmp_path / "abi_from_c")
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c_abi", "abi_from_c.c"), "-o", exe, "-L" + lib_dir, "-lnngp_b200", "-lm",
+                        "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "FAIL" not in r.stdout, r.stdout + r.stderr
+    assert r.stdout.count("ok ") >= 7
