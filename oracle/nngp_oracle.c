@@ -445,7 +445,7 @@ double oracle_ssr(const int *locs_match, int n_obs, const double *observed_field
 void oracle_beta0_moments(const double *Linv, const int *NNarray, int n, int m, const double *field, double log_scale,
                           double *mean, double *var)
 {
-    double *ones = (double *)malloc(sizeof(double) * (size_t)n), *v = (double *)malloc(sizeof(double) * (size_t)n),
+    double *ones = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double)), *v = (double *)malloc(sizeof(double) * (size_t)n),
            *u = (double *)malloc(sizeof(double) * (size_t)n);
     for (int i = 0; i < n; i++) ones[i] = 1.0;
     oracle_linv_mult(Linv, ones, NNarray, n, m, v);
