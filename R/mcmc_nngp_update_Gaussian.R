@@ -8,10 +8,15 @@ if(!exists("nngp_b200_load")) source(file.path(Sys.getenv("NNGP_B200_HOME", unse
 
 mcmc_nngp_update_Gaussian = function(locs, X, observed_field, space_time_model, vecchia_approx, states, n_iterations_update,
                                      n_cores = NULL, field_thinning = 1, ancillary = T, n_chromatic = 10, iterations,
-                                     n_gpus = 1, rng = c("philox", "R"))
+                                     n_gpus = getOption("nngp_b200.n_gpus", 1L), rng = getOption("nngp_b200.rng", "philox"))
 {
+  # mcmc_nngp_run calls this function with the reference's arguments only, so the two extra ones default to options:
+  #   options(nngp_b200.n_gpus = 8L)    chain i on GPU (i - 1) mod n_gpus
+  #   options(nngp_b200.rng = "R")      R's own stream, seeded iter_start + i as in the reference (line 36): the chains then draw
+  #                                     exactly what they draw in the reference; "philox" (default) = the on-device generator
   nngp_b200_load()
-  rng_mode = if(match.arg(rng) == "R") 0L else 1L
+  if(!rng %in% c("philox", "R")) stop(paste("unknown rng", rng))
+  rng_mode = if(rng == "R") 0L else 1L
   iter_start = iterations[nrow(iterations), 1]
   n_locs = vecchia_approx$n_locs
   n_chains = length(states)
