@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstdint>
 #include <cstring>
@@ -310,22 +311,58 @@ void order_maxmin_gpgp(const double *locs_cm, int n, int d, bool lonlat, RStream
 }
 
 // children lists: for site s the rows r (0-based) that contain s, r ascending (includes r == s)
-void build_csc(const int *NNarray, int n, int m, std::vector<int64_t> &ptr, std::vector<int> &rows, std::vector<int> &slots) {
+void build_csc(const int *NNarray, int n, int m, std::vector<int64_t> &ptr, std::vector<int> &rows, std::vector<int> *slots_opt) {
+    // Counting sort by site over the n x (m+1) table, in parallel: counts and fill positions are claimed with atomics, which
+    // leaves the entries of a column in arbitrary order; every column is then sorted by row (a row holds a site at most once, so
+    // the result is the unique ascending-row order -- the same arrays as a sequential fill in row order).
+    const bool prof = std::getenv("NNGP_PROFILE_COLORING") != nullptr;
+    double t0 = omp_get_wtime();
     ptr.assign((size_t)n + 1, 0);
-    for (int j = 0; j <= m; j++)
-        for (int i = 0; i < n; i++) {
-            int v = NNarray[(size_t)i + (size_t)n * j];
-            if (v != NNGP_NA_INT) ptr[v]++;
-        }
-    for (int s = 0; s < n; s++) ptr[s + 1] += ptr[s];
-    rows.resize(ptr[n]);
-    slots.resize(ptr[n]);
-    std::vector<int64_t> pos(ptr.begin(), ptr.end() - 1);
+    int64_t *cnt = ptr.data();
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < n; i++)
         for (int j = 0; j <= m; j++) {
             int v = NNarray[(size_t)i + (size_t)n * j];
-            if (v != NNGP_NA_INT) { rows[pos[v - 1]] = i; slots[pos[v - 1]] = j; pos[v - 1]++; }
+            if (v != NNGP_NA_INT) {
+#pragma omp atomic
+                cnt[v]++;
+            }
         }
+    if (prof) { fprintf(stderr, "[csc] count %.3f\n", omp_get_wtime() - t0); t0 = omp_get_wtime(); }
+    for (int s = 0; s < n; s++) ptr[s + 1] += ptr[s];
+    rows.resize(ptr[n]);
+    if (slots_opt) slots_opt->resize(ptr[n]);
+    int *slots = slots_opt ? slots_opt->data() : nullptr;   // the slot of each entry is optional (the colouring needs rows only)
+    std::vector<int64_t> pos(ptr.begin(), ptr.end() - 1);
+    int64_t *posp = pos.data();
+    if (prof) { fprintf(stderr, "[csc] alloc %.3f\n", omp_get_wtime() - t0); t0 = omp_get_wtime(); }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= m; j++) {
+            int v = NNarray[(size_t)i + (size_t)n * j];
+            if (v != NNGP_NA_INT) {
+                int64_t q;
+#pragma omp atomic capture
+                q = posp[v - 1]++;
+                rows[q] = i;
+                if (slots) slots[q] = j;
+            }
+        }
+    if (prof) { fprintf(stderr, "[csc] fill %.3f\n", omp_get_wtime() - t0); t0 = omp_get_wtime(); }
+#pragma omp parallel
+    {
+        std::vector<int64_t> key;
+#pragma omp for schedule(dynamic, 2048)
+        for (int s = 0; s < n; s++) {
+            const int64_t e0 = ptr[s], e1 = ptr[s + 1];
+            if (e1 - e0 < 2) continue;
+            if (!slots) { std::sort(rows.begin() + e0, rows.begin() + e1); continue; }   // cheap: ~ m + 1 ints
+            key.resize((size_t)(e1 - e0));
+            for (int64_t e = e0; e < e1; e++) key[(size_t)(e - e0)] = ((int64_t)rows[e] << 8) | (int64_t)slots[e];   // m + 1 <= 32 slots
+            std::sort(key.begin(), key.end());
+            for (int64_t e = e0; e < e1; e++) { rows[e] = (int)(key[(size_t)(e - e0)] >> 8); slots[e] = (int)(key[(size_t)(e - e0)] & 255); }
+        }
+    }
 }
 
 // Exact first-fit colouring in index order, in parallel.  colour(i) = smallest colour not used by a moral neighbour j < i, so
@@ -335,14 +372,17 @@ void build_csc(const int *NNarray, int n, int m, std::vector<int64_t> &ptr, std:
 // to the sequential loop (Coloring.R:2-20) by construction; the expensive part -- ~ (m+1)^2 random reads per site -- is
 // spread over the host cores.  Returns 0 when a colour >= 63 shows up (caller falls back to the sequential loop).
 static int greedy_coloring_blocked(const int *nn_rm, int n, int M, const std::vector<int64_t> &ptr, const std::vector<int> &rows, int *coloring) {
-    const int B = 8192, CAP = 24;
+    const int B = 8192, CAP = 96;
     const char *lim_env = std::getenv("NNGP_COLORING_MASK_COLOURS");   // testing hook: pretend the mask is narrower than 63 colours
     const int limit = lim_env ? std::max(1, std::min(63, std::atoi(lim_env))) : 63;
     std::vector<uint64_t> mask(B);
     std::vector<int> ndep(B), dep((size_t)B * CAP);
     int K = 0;
-    for (int b0 = 0; b0 < n; b0 += B) {
-        const int b1 = std::min(n, b0 + B);
+    double tp = 0, ts = 0;
+    long long rescans = 0, rescan_entries = 0;
+    for (int b0 = 0; b0 < n;) {
+        const int b1 = std::min(n, b0 + std::max(32, std::min(B, b0 / 8)));
+        double t0 = omp_get_wtime();
 #pragma omp parallel for schedule(dynamic, 64)
         for (int i = b0; i < b1; i++) {
             uint64_t mk = 0;
@@ -362,12 +402,14 @@ static int greedy_coloring_blocked(const int *nn_rm, int n, int M, const std::ve
             mask[i - b0] = mk;
             ndep[i - b0] = nd;
         }
+        tp += omp_get_wtime() - t0; t0 = omp_get_wtime();
         for (int i = b0; i < b1; i++) {
             uint64_t mk = mask[i - b0];
             const int nd = ndep[i - b0];
             if (nd <= CAP) {
                 for (int k = 0; k < nd; k++) mk |= (uint64_t)1 << coloring[dep[(size_t)(i - b0) * CAP + k]];
             } else {
+                rescans++; rescan_entries += ptr[i + 1] - ptr[i];
                 for (int64_t k = ptr[i]; k < ptr[i + 1]; k++) {
                     const int *row = nn_rm + (size_t)rows[k] * M;
                     for (int j = 0; j < M; j++) {
@@ -382,13 +424,19 @@ static int greedy_coloring_blocked(const int *nn_rm, int n, int M, const std::ve
             coloring[i] = c;
             if (c > K) K = c;
         }
+        ts += omp_get_wtime() - t0;
+        b0 = b1;
     }
+    if (std::getenv("NNGP_PROFILE_COLORING")) fprintf(stderr, "[coloring] parallel scan %.3f s, sequential resolve %.3f s, %lld rescans of %lld rows\n", tp, ts, rescans, rescan_entries);
     return K;
 }
 
 int greedy_coloring(const int *NNarray, int n, int m, int *coloring) {
-    std::vector<int64_t> ptr; std::vector<int> rows, slots;
-    build_csc(NNarray, n, m, ptr, rows, slots);
+    const bool prof = std::getenv("NNGP_PROFILE_COLORING") != nullptr;
+    double t0 = omp_get_wtime();
+    std::vector<int64_t> ptr; std::vector<int> rows;
+    build_csc(NNarray, n, m, ptr, rows, nullptr);
+    if (prof) { fprintf(stderr, "[coloring] build_csc %.3f s\n", omp_get_wtime() - t0); t0 = omp_get_wtime(); }
     std::vector<int> stamp(64, -1);
     int K = 0;
     for (int i = 0; i < n; i++) coloring[i] = 0;
@@ -399,8 +447,10 @@ int greedy_coloring(const int *NNarray, int n, int m, int *coloring) {
 #pragma omp parallel for schedule(static)
     for (int r = 0; r < n; r++)
         for (int j = 0; j < M; j++) nn_rm[(size_t)r * M + j] = NNarray[(size_t)r + (size_t)n * j];
+    if (prof) { fprintf(stderr, "[coloring] row-major copy %.3f s\n", omp_get_wtime() - t0); t0 = omp_get_wtime(); }
     if (std::getenv("NNGP_COLORING_SEQUENTIAL") == nullptr) {
         K = greedy_coloring_blocked(nn_rm.data(), n, M, ptr, rows, coloring);
+        if (prof) fprintf(stderr, "[coloring] blocked first-fit %.3f s\n", omp_get_wtime() - t0);
         if (K > 0 || n == 0) return K;
         for (int i = 0; i < n; i++) coloring[i] = 0;    // 63 colours or more: the mask is too narrow, use the sequential loop
     }

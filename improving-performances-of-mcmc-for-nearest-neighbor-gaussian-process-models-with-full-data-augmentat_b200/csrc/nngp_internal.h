@@ -11,7 +11,7 @@ void set_error(const char *fmt, ...);
 
 // host_graph.cpp
 void find_ordered_nn(const double *locs_cm, int n, int d, int m, int *NNarray);
-void build_csc(const int *NNarray, int n, int m, std::vector<int64_t> &ptr, std::vector<int> &rows, std::vector<int> &slots);
+void build_csc(const int *NNarray, int n, int m, std::vector<int64_t> &ptr, std::vector<int> &rows, std::vector<int> *slots_opt);
 int greedy_coloring(const int *NNarray, int n, int m, int *coloring);
 void order_maxmin(const double *locs_cm, int n, int d, int *order);
 class RStream;
