@@ -115,7 +115,8 @@ def _initialize_host(observed_locs, observed_field, X_obs, X_locs, m, reordering
         observed_locs = observed_locs[:, None]
     observed_field = np.asarray(observed_field, dtype=np.float64).ravel()
     # ---- de-duplicate (first occurrence kept, original order) and re-order: initialize.R:26-34
-    _, first = np.unique(observed_locs, axis=0, return_index=True)
+    _, first, inverse = np.unique(observed_locs, axis=0, return_index=True, return_inverse=True)
+    inverse = np.asarray(inverse).ravel()
     locs = observed_locs[np.sort(first)]
     rkind = reordering if isinstance(reordering, str) else reordering[0]
     if rkind == "maxmin":
@@ -144,14 +145,18 @@ def _initialize_host(observed_locs, observed_field, X_obs, X_locs, m, reordering
 
     # ---- Vecchia approximation: initialize.R:80-110 (all index arrays 1-based like R)
     va = {"n_locs": n, "n_obs": observed_field.size}
-    key = {tuple(r): i + 1 for i, r in enumerate(map(tuple, locs))}
-    locs_match = np.array([key[tuple(r)] for r in observed_locs], dtype=np.int32)                    # :85
+    # match(observed_locs, locs) without a Python loop: unique row -> its rank in first-occurrence order -> its place after reordering
+    rank = np.empty(first.size, dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(first.size)
+    place = np.empty(n, dtype=np.int64)
+    place[order] = np.arange(n)
+    locs_match = (place[rank[inverse]] + 1).astype(np.int32)                                         # :85
     va["locs_match"] = locs_match
     order_obs = np.argsort(locs_match, kind="stable")
     counts = np.bincount(locs_match - 1, minlength=n)
     ptr = np.concatenate([[0], np.cumsum(counts)])
-    va["hctam_scol"] = [order_obs[ptr[s]:ptr[s + 1]] + 1 for s in range(n)]                          # :88
-    va["hctam_scol_1"] = np.array([h[0] for h in va["hctam_scol"]], dtype=np.int32)                  # :89
+    va["hctam_scol"] = np.split(order_obs + 1, ptr[1:-1])                                            # :88
+    va["hctam_scol_1"] = (order_obs[ptr[:-1]] + 1).astype(np.int32)                                  # :89
     va["obs_per_loc"] = counts.astype(np.float64)                                                    # :91
     NN = find_ordered_nn_gpgp(locs, m, rs) if rs is not None else find_ordered_nn(locs, m)           # :93 (no lonlat: quirk 3)
     va["NNarray"] = NN
