@@ -321,3 +321,31 @@ def test_chain_without_regressors_matches_dense_transcription(covfun, shape):
     assert np.array_equal(acc, acco)
     assert np.max(np.abs(rec - reco)) < 1e-8
     assert np.max(np.abs(rec_field - freco)) < 1e-7
+
+
+def test_matern_kernel_against_50_digit_arithmetic():
+    """SURVEY 8(f4) "Matern Bessel-K accuracy study": the oracle's Matern correlation 2^(1-nu)/Gamma(nu) s^nu K_nu(s) (GpGp's
+    parametrisation: no sqrt(2 nu) factor, value 1 at s = 0) over the smoothness range the reference's transforms can reach --
+    .4 + .7 plogis in initialize.R:199, .5 + .5 plogis in update_Gaussian.R:70, 1.5 plogis in predict.R:37, i.e. (0, 1.5) -- and 12
+    decades of scaled distance, against mpmath at 50 digits.  It is read off a 2-point Vecchia factor row, for which
+    Linv[1, 0]^-2 = 1 - rho^2 and -Linv[1, 1] / Linv[1, 0] = rho, so the test goes through the same code the chain uses."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    worst = 0.0
+    for nu in (0.05, 0.3, 0.4, 0.5, 0.75, 1.0, 1.1, 1.45, 1.499):
+        for s in (1e-9, 1e-6, 1e-3, 0.03, 0.4, 1.0, 3.0, 9.0, 25.0, 60.0):
+            rho = 2 ** (1 - mp.mpf(nu)) / mp.gamma(nu) * mp.mpf(s) ** nu * mp.besselk(nu, s)
+            if float(1 - rho ** 2) < 1e-10:
+                continue      # rho = 1 to double precision: the 2 x 2 block is singular (the chain rejects such proposals)
+            locs = np.array([[0.0, 0.0], [s, 0.0]])
+            nn = np.array([[1, NA], [2, 1]], dtype=np.int32)
+            Linv = O.vecchia_Linv([1.0, 1.0, nu, 0.0], "matern_isotropic", locs, nn)
+            got = -Linv[1, 1] / Linv[1, 0]
+            err = abs(mp.mpf(float(got)) - rho) / max(rho, mp.mpf(10) ** -300)
+            if rho > 1e-290:
+                worst = max(worst, float(err))
+            cond_var = 1.0 / Linv[1, 0] ** 2
+            want_var = float(1 - rho ** 2)
+            # 1 - rho^2 from a double rho: absolute error of a few ulps of 1 (the cancellation GpGp's double arithmetic has too)
+            assert abs(cond_var - want_var) <= 1e-14, (nu, s, cond_var, want_var)
+    assert worst < 5e-14, worst          # observed: 6.0e-15 (nu = 0.05, s = 1)
